@@ -1,0 +1,136 @@
+"""Input decks of the BASELINE.json configs as plain numpy arrays (host-side input generation only).
+
+These restate just enough of FJSPH's block generators to reproduce the configs:
+  * square/cube lattice  -- shapes/square.cpp:101-145 (grid order; one jitter value per point, all axes)
+  * circle/sphere lattice -- shapes/circle.cpp:131-189 (grid order; per-axis jitter; |x-c|^2 > R^2 culled)
+The reference perturbs points with std::default_random_engine in U(0, eps*dx); that stream is not
+replicated bit-for-bit here (numpy PCG64 with a fixed seed is used instead) -- full-fidelity shape
+generation is SURVEY 8f row N1.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BOUND, PISTON, BUFFER, BACK, PIPE, FREE, OUTLET, LOST = range(8)
+EPS = float(np.finfo(np.float64).eps)
+
+
+def cole_pressure(rho, rho0, c, gam=7.0, p_back=0.0):
+    """FLUID::get_pressure, Cole EOS (Var.h:203-218)."""
+    B = rho0 * c * c / gam
+    return B * ((rho / rho0) ** gam - 1.0) + p_back
+
+
+def cole_density(p, rho0, c, gam=7.0, p_back=0.0):
+    """FLUID::get_density, Cole EOS (Var.h:221-236)."""
+    B = rho0 * c * c / gam
+    return rho0 * (((p - p_back) / B) + 1.0) ** (1.0 / gam)
+
+
+def lattice(n, dx, start=(0.0, 0.0, 0.0), jitter="eps", seed=1234):
+    """n = (ni, nj[, nk]) lattice, x fastest (square.cpp:107-141).  jitter: 'eps' -> U(0, eps*dx) (the
+    reference's tie-stress perturbation), float f -> U(-f, f)*dx, None -> none."""
+    n = tuple(int(k) for k in n)
+    dim = len(n)
+    rng = np.random.default_rng(seed)
+    grids = np.meshgrid(*[np.arange(k, dtype=np.float64) for k in n[::-1]], indexing="ij")
+    pts = np.stack([g.reshape(-1) for g in grids[::-1]], axis=1) * dx
+    if jitter == "eps":
+        pts = pts + rng.uniform(0.0, EPS * dx, size=(pts.shape[0], 1))
+    elif jitter is not None:
+        pts = pts + rng.uniform(-float(jitter), float(jitter), size=pts.shape) * dx
+    return pts + np.asarray(start, dtype=np.float64)[:dim]
+
+
+def synthetic_block(n=(500, 250, 100), dx=1e-3, jitter=0.1, seed=1234, rho0=1000.0, c=100.0, x_offset_cells=0):
+    """Config C5: FREE-particle block with a smooth density and velocity field.
+    x_offset_cells shifts the slab along x (rank r of a slab decomposition owns cells [r*ni,(r+1)*ni))."""
+    ni, nj, nk = n
+    xi = lattice(n, dx, start=(x_offset_cells * dx, 0.0, 0.0), jitter=jitter, seed=seed + x_offset_cells)
+    L = np.array([ni * dx, nj * dx, nk * dx])
+    rho = rho0 * (1.0 + 1e-3 * np.sin(2 * np.pi * xi[:, 0] / L[0]))
+    v = 0.5 * np.stack(
+        [np.sin(2 * np.pi * xi[:, 1] / L[1]), np.sin(2 * np.pi * xi[:, 2] / L[2]), np.sin(2 * np.pi * xi[:, 0] / L[0])],
+        axis=1,
+    )
+    N = xi.shape[0]
+    return dict(
+        xi=xi, v=v, rho=rho, p=cole_pressure(rho, rho0, c), m=np.full(N, rho0 * dx**3),
+        b=np.full(N, FREE, dtype=np.int32), bound_points=0,
+        params=dict(particle_step=dx, rho_rest=rho0, speed_sound=c, mu=8.94e-4, sig=0.0708, visc_alpha=0.05,
+                    dsph_delta=0.1, grav=(0.0, 0.0, -9.81)),
+    )
+
+
+def droplet(dx=0.0015, radius=0.05, seed=1234, dim=3):
+    """Config C2, Examples/Droplet/{para3D,fluid_3D.bmap}: sphere R=0.05 at the origin, rho 810,
+    Gissler aero with v_inf = (0, 21.55, 0).  Lattice start = centre - radius, end = centre + radius
+    (circle.cpp:131-189).  dx=0.0015 -> ~155 k particles, dx=0.0008 -> ~1.02 M."""
+    n1 = int(np.ceil(2 * radius / dx))
+    n1 = max(n1, 1)
+    pts = lattice((n1,) * dim, dx, start=(-radius,) * dim, jitter=None)
+    rng = np.random.default_rng(seed)
+    pts = pts + rng.uniform(0.0, EPS * dx, size=pts.shape)
+    keep = (pts**2).sum(axis=1) <= radius * radius
+    xi = np.ascontiguousarray(pts[keep])
+    N = xi.shape[0]
+    rho0 = 810.0
+    v_inf = (0.0, 21.55, 0.0) if dim == 3 else (21.55, 0.0, 0.0)
+    return dict(
+        xi=xi, v=np.zeros_like(xi), rho=np.full(N, rho0), p=np.zeros(N), m=np.full(N, rho0 * dx**dim),
+        b=np.full(N, FREE, dtype=np.int32), bound_points=0,
+        params=dict(particle_step=dx, rho_rest=rho0, mu=0.000142, sig=0.0256, speed_sound=100.0, visc_alpha=0.05,
+                    cfl=0.9, subits_factor=0.76, delta_t_max=1.0, delta_t_min=1e-9, frame_time_interval=1e-3,
+                    acase=1, v_inf=v_inf, p_ref=100000.0, rho_g=1.1025, mu_g=1.716e-05, temp_g=298.0),
+    )
+
+
+def box_with_walls(n=(20, 12, 16), dx=0.01, layers=4, rho0=1000.0, c=None, hydro=True, jitter="eps", seed=7,
+                   g=9.81, dim=3):
+    """Open-topped tank: fluid lattice n resting on a floor and inside side walls `layers` particles thick
+    (the 3D extrusion of Examples/Standing_Column, config C3).  Gravity acts along the last axis.  Walls
+    come first in the particle order (Init.cpp:298-352), b = BOUND; hydrostatic initialisation follows
+    Init.cpp:480-493 with the height taken along the gravity axis."""
+    n = tuple(int(k) for k in n)[:dim]
+    up = dim - 1
+    height = n[up] * dx
+    if c is None:
+        c = 10.0 * np.sqrt(g * height)
+    fluid = lattice(n, dx, start=(0.0,) * dim, jitter=jitter, seed=seed)
+    # wall lattice: a shell around the fluid, open at the top
+    nw = [k + 2 * layers for k in n]
+    nw[up] = n[up] + layers + 2  # floor + a little freeboard
+    shell = lattice(nw, dx, start=tuple(-layers * dx for _ in n), jitter=jitter, seed=seed + 1)
+    ijk = np.rint((shell - (-layers * dx)) / dx).astype(np.int64)
+    inside = np.ones(shell.shape[0], dtype=bool)
+    for d in range(dim):
+        if d == up:
+            inside &= ijk[:, d] >= layers
+        else:
+            inside &= (ijk[:, d] >= layers) & (ijk[:, d] < layers + n[d])
+    walls = np.ascontiguousarray(shell[~inside])
+    xi = np.concatenate([walls, fluid], axis=0)
+    nb, nf = walls.shape[0], fluid.shape[0]
+    N = nb + nf
+    rho = np.full(N, rho0)
+    p = np.zeros(N)
+    if hydro:
+        p = np.maximum(0.0, rho0 * g * (height - xi[:, up]))
+        rho = cole_density(p, rho0, c)
+    b = np.concatenate([np.full(nb, BOUND, dtype=np.int32), np.full(nf, FREE, dtype=np.int32)])
+    grav = [0.0, 0.0, 0.0]
+    grav[up] = -g
+    return dict(
+        xi=xi, v=np.zeros_like(xi), rho=rho, p=p, m=np.full(N, rho0 * dx**dim), b=b, bound_points=nb,
+        params=dict(particle_step=dx, rho_rest=rho0, speed_sound=float(c), mu=8.94e-4, sig=0.0, visc_alpha=0.1,
+                    grav=tuple(grav), delta_t_min=1e-9, frame_time_interval=10.0),
+        height=height,
+    )
+
+
+def dam_2d(dx=0.02):
+    """Config C1, Examples/Dam_2D: 2D, fluid Square (0,0)-(2,1) -> 100x50, c=125, alpha 8.94e-4? no --
+    the deck's values are kept in params below; three Pressure-Gradient walls 4 layers deep."""
+    case = box_with_walls(n=(int(round(2.0 / dx)), int(round(1.0 / dx))), dx=dx, layers=4, c=125.0, hydro=True, dim=2)
+    case["params"].update(dict(visc_alpha=0.1, dsph_delta=0.1, sig=0.0))
+    return case

@@ -1,0 +1,124 @@
+/* fjsph_oracle.h — TEST INFRASTRUCTURE ONLY.
+ *
+ * C ABI of the CPU oracle: a dependency-free restatement of FJSPH's WCSPH time-step path
+ * (reference: /root/reference/src/{IO,Neighbours,Shifting,Geometry,Resid,Aero,Newmark_Beta,
+ * Runge_Kutta,Integration}.cpp, Kernel.h, Var.h, shapes/inlet.cpp).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library.  The product (fjsph_b200/) never links, imports or calls it.
+ *
+ * PARITY UNPINNED: the reference ships no tests/golden vectors for this path and cannot be compiled
+ * here (Eigen, nanoflann, TECIO, NetCDF, HDF5 are un-vendored), so this restatement is pinned only by
+ * analytic checks (tests/test_oracle_*.py), not by reference outputs.
+ */
+#ifndef FJSPH_ORACLE_H
+#define FJSPH_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Particle types, VarDefs.h:92-102 */
+enum { ORC_BOUND = 0, ORC_PISTON, ORC_BUFFER, ORC_BACK, ORC_PIPE, ORC_FREE, ORC_OUTLET, ORC_LOST };
+
+/* All settings the path reads (Var.h INTEG_SETT/FLUID/AERO/SIM) followed by the constants
+ * Set_Values derives (IO.cpp:26-128). Vectors always have 3 slots; 2D builds ignore [2]. */
+typedef struct OrcParams
+{
+    /* switches */
+    int32_t dim;          /* SIMDIM the caller expects; checked against the compiled DIM */
+    int32_t ale;          /* 1 = behaviour of the -DALE binary, 0 = the delta-SPH binary */
+    int32_t pressure_rel; /* 0 Cole, 1 isothermal (Var.h:203-236) */
+    int32_t solver_type;  /* 0 Newmark-Beta, 1 Runge-Kutta */
+    int32_t acase;        /* aero_force enum: 0 none, 1 Gissler */
+    int32_t asource;      /* aero_source enum: 0 constVel, 1 meshInfl */
+    int32_t use_lam;
+    int32_t use_TAB_def;
+    int32_t max_subits;
+    int32_t n_stable, n_stable_limit, n_unstable, n_unstable_limit;
+    int32_t reserved0;
+    /* inputs */
+    double particle_step, H_fac, rho_rest, press_pipe, press_back, rho_max, rho_min, rho_var, rho_max_iter;
+    double visc_alpha, speed_sound, mu, sig, gam, dsph_delta;
+    double grav[3];
+    double v_inf[3];
+    double p_ref, rho_g, mu_g, temp_g, R_g, gamma_g, lam_cutoff, i_interp_fac;
+    double tab_Cf, tab_Ck, tab_Cd, tab_Cb;
+    double cfl, cfl_step, cfl_max, cfl_min, subits_factor, min_residual;
+    double delta_t, delta_t_max, delta_t_min, max_shift_vel;
+    double current_time, last_frame_time, frame_time_interval;
+    /* derived by orc_set_values */
+    double B, rho_pipe, dx, sim_mass, bnd_mass, H, H_sq, sr, dsph_cont, nu, W_correc, W_dx, nb_beta, nb_gamma;
+    double aero_L, A_sphere, A_plate, td, omega, tmax, Cdef, ycoef, n_full, i_n_full, interp_fac, sos;
+} OrcParams;
+
+/* Per-step diagnostics = the columns of the reference's step table (Integration.cpp:250-265). */
+typedef struct OrcStepStats
+{
+    double dt, cfl_ratio, rms_error, maxRho_pc, maxf, maxAf, maxShift, safe_dt, npd, logbase;
+    int32_t iterations, n_add, n_del, total_points;
+} OrcStepStats;
+
+typedef struct Orc Orc;
+
+void orc_default_params(OrcParams* p, int dim);   /* defaults of Var.h */
+void orc_set_values(OrcParams* p);                /* IO.cpp:26-128 */
+int orc_compiled_dim(void);
+
+Orc* orc_create(const OrcParams* p);
+void orc_destroy(Orc* o);
+void orc_get_params(Orc* o, OrcParams* out);
+void orc_set_params(Orc* o, const OrcParams* in);
+
+/* Blocks ("limits", Var.h:779-859). Boundary blocks must be added before fluid blocks and cover
+ * [0,bound_points) then [bound_points,total) contiguously.  back/buffer may be NULL/0. */
+int orc_add_block(Orc* o, int is_fluid, int64_t first, int64_t second, int bound_solver, int no_slip,
+                  int block_type, int fixed_vel_or_dynamic, int ntimes, const double* times,
+                  const double* vels /* max(1,ntimes) x 3 */, const double* insert_norm, double insconst,
+                  const double* delete_norm, double delconst, const double* aero_norm, double aeroconst,
+                  int nback, const int64_t* back, int nbuf, const int64_t* buffer /* nback x nbuf */);
+void orc_clear_blocks(Orc* o);
+int orc_get_block_range(Orc* o, int block, int64_t* first, int64_t* second);
+
+/* State: sets N particles on both time levels (pn = pnp1, Init.cpp:496). Missing optional arrays
+ * (NULL) are zero / defaults of the SPHPart constructor (Var.h:502-545). */
+int orc_set_particles(Orc* o, int64_t n, int64_t bound_points, const double* xi, const double* v,
+                      const double* rho, const double* p, const double* m, const int32_t* b,
+                      const int64_t* part_id);
+int64_t orc_count(Orc* o);
+int64_t orc_bound_points(Orc* o);
+/* Generic field access. level 0 = pn, 1 = pnp1. Returns number of doubles/ints per particle, <0 if unknown.
+ * Float fields: xi v acc Af aVisc cellV gradRho norm bNorm vPert (dim each) L (dim*dim) Rrho rho p m curve
+ * norm_curve woccl pDist deltaD cellP cellRho colourG colour lam lam_nb kernsum y.
+ * Int fields (as int64): part_id cellID b surf surfzone internal. */
+int orc_get_f64(Orc* o, int level, const char* name, double* out);
+int orc_set_f64(Orc* o, int level, const char* name, const double* in);
+int orc_get_i64(Orc* o, int level, const char* name, int64_t* out);
+int orc_set_i64(Orc* o, int level, const char* name, const int64_t* in);
+
+/* Stage entry points (operate on pnp1 with the current neighbour list unless noted). */
+void orc_update_neighbours(Orc* o);                       /* Neighbours.cpp:7-31 on pnp1 */
+int64_t orc_neighbour_total(Orc* o);
+void orc_get_neighbours(Orc* o, int64_t* offsets /* n+1 */, int64_t* idx, double* d2); /* ascending j */
+double orc_prestep(Orc* o);                               /* Shifting.cpp:12-123; returns npd */
+void orc_aero_velocity(Orc* o);                           /* Resid.cpp:471-612 (constVel) */
+void orc_detect_surface(Orc* o);                          /* Geometry.cpp:14-280 */
+void orc_dissipation(Orc* o);                             /* Shifting.cpp:126-186 */
+void orc_particle_shift(Orc* o);                          /* Shifting.cpp:189-290 */
+void orc_forces(Orc* o, double npd);                      /* Resid.cpp:426-469 */
+void orc_nb_iter(Orc* o, double npd);                     /* Newmark_Beta.cpp:54-301 */
+double orc_find_timestep(Orc* o);                         /* Integration.cpp:370-443 */
+double orc_integrate_no_update(Orc* o, OrcStepStats* s);  /* Integration.cpp:27-107 */
+double orc_integrate(Orc* o, OrcStepStats* s);            /* Integration.cpp:233-303 */
+
+/* Small-matrix restatements, exposed for unit tests. a is row-major dim x dim. */
+int orc_qr_inverse(const double* a, double* inv);          /* returns isInvertible */
+double orc_min_eigenvalue(const double* a);                /* SelfAdjointEigenSolver::computeDirect */
+double orc_kernel(double r, double H, double Wc);
+double orc_get_n_full(double dx, double H);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

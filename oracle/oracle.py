@@ -1,0 +1,325 @@
+"""ctypes wrapper of the CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+The product package (fjsph_b200/) never does.  See oracle/fjsph_oracle.h for the contract and citations.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_HEADER = os.path.join(_HERE, "fjsph_oracle.h")
+
+
+def _struct_from_header(header: str, name: str):
+    """Build a ctypes.Structure from `typedef struct <name> { ... } <name>;` (int32_t / double fields)."""
+    src = open(header).read()
+    body = re.search(r"typedef struct %s\s*\{(.*?)\}\s*%s;" % (name, name), src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        ctype, rest = stmt.split(None, 1)
+        base = {"int32_t": C.c_int32, "double": C.c_double, "int64_t": C.c_int64}[ctype]
+        for item in rest.split(","):
+            item = item.strip()
+            m = re.match(r"(\w+)\[(\d+)\]", item)
+            if m:
+                fields.append((m.group(1), base * int(m.group(2))))
+            else:
+                fields.append((item, base))
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+OrcParams = _struct_from_header(_HEADER, "OrcParams")
+OrcStepStats = _struct_from_header(_HEADER, "OrcStepStats")
+
+BOUND, PISTON, BUFFER, BACK, PIPE, FREE, OUTLET, LOST = range(8)
+
+_LIBS = {}
+
+
+def build(fast: bool = False) -> None:
+    """Compile the oracle with its committed Makefile (parity builds; fast=True adds the timing builds)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE] + (["fast"] if fast else []))
+
+
+def _load(kind: str):
+    if kind in _LIBS:
+        return _LIBS[kind]
+    path = os.path.join(_HERE, "lib", "liborc%s.so" % kind)
+    if not os.path.exists(path):
+        build(fast="fast" in kind)
+    lib = C.CDLL(path)
+    P = C.POINTER
+    lib.orc_default_params.argtypes = [P(OrcParams), C.c_int]
+    lib.orc_set_values.argtypes = [P(OrcParams)]
+    lib.orc_create.argtypes = [P(OrcParams)]
+    lib.orc_create.restype = C.c_void_p
+    lib.orc_destroy.argtypes = [C.c_void_p]
+    lib.orc_get_params.argtypes = [C.c_void_p, P(OrcParams)]
+    lib.orc_set_params.argtypes = [C.c_void_p, P(OrcParams)]
+    lib.orc_add_block.argtypes = (
+        [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_double]
+        + [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    )
+    lib.orc_clear_blocks.argtypes = [C.c_void_p]
+    lib.orc_get_block_range.argtypes = [C.c_void_p, C.c_int, P(C.c_int64), P(C.c_int64)]
+    lib.orc_set_particles.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 7
+    lib.orc_count.argtypes = [C.c_void_p]
+    lib.orc_count.restype = C.c_int64
+    lib.orc_bound_points.argtypes = [C.c_void_p]
+    lib.orc_bound_points.restype = C.c_int64
+    for f in ("orc_get_f64", "orc_set_f64", "orc_get_i64", "orc_set_i64"):
+        getattr(lib, f).argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p]
+    lib.orc_update_neighbours.argtypes = [C.c_void_p]
+    lib.orc_neighbour_total.argtypes = [C.c_void_p]
+    lib.orc_neighbour_total.restype = C.c_int64
+    lib.orc_get_neighbours.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.orc_prestep.argtypes = [C.c_void_p]
+    lib.orc_prestep.restype = C.c_double
+    for f in ("orc_aero_velocity", "orc_detect_surface", "orc_dissipation", "orc_particle_shift"):
+        getattr(lib, f).argtypes = [C.c_void_p]
+    lib.orc_forces.argtypes = [C.c_void_p, C.c_double]
+    lib.orc_nb_iter.argtypes = [C.c_void_p, C.c_double]
+    lib.orc_find_timestep.argtypes = [C.c_void_p]
+    lib.orc_find_timestep.restype = C.c_double
+    lib.orc_integrate_no_update.argtypes = [C.c_void_p, P(OrcStepStats)]
+    lib.orc_integrate_no_update.restype = C.c_double
+    lib.orc_integrate.argtypes = [C.c_void_p, P(OrcStepStats)]
+    lib.orc_integrate.restype = C.c_double
+    lib.orc_qr_inverse.argtypes = [C.c_void_p, C.c_void_p]
+    lib.orc_min_eigenvalue.argtypes = [C.c_void_p]
+    lib.orc_min_eigenvalue.restype = C.c_double
+    lib.orc_kernel.argtypes = [C.c_double] * 3
+    lib.orc_kernel.restype = C.c_double
+    lib.orc_get_n_full.argtypes = [C.c_double] * 2
+    lib.orc_get_n_full.restype = C.c_double
+    _LIBS[kind] = lib
+    return lib
+
+
+def default_params(dim: int = 3, kind: str | None = None, **kw) -> "OrcParams":
+    """Var.h defaults, overridden by kw, then Set_Values (IO.cpp:26-128)."""
+    lib = _load(kind or ("%dd" % dim))
+    p = OrcParams()
+    lib.orc_default_params(C.byref(p), dim)
+    set_fields(p, **kw)
+    lib.orc_set_values(C.byref(p))
+    return p
+
+
+def set_fields(p, **kw):
+    for k, v in kw.items():
+        cur = getattr(p, k)
+        if hasattr(cur, "__len__"):
+            for i, x in enumerate(v):
+                cur[i] = x
+        else:
+            setattr(p, k, v)
+
+
+def params_to_dict(p) -> dict:
+    out = {}
+    for name, _ in p._fields_:
+        v = getattr(p, name)
+        out[name] = list(v) if hasattr(v, "__len__") else v
+    return out
+
+
+_INT_FIELDS = ("part_id", "cellID", "b", "surf", "surfzone", "internal")
+_VEC_FIELDS = ("xi", "v", "acc", "Af", "aVisc", "cellV", "gradRho", "norm", "bNorm", "vPert")
+_SCALAR_FIELDS = (
+    "Rrho rho p m curve norm_curve woccl pDist deltaD cellP cellRho colourG colour lam lam_nb kernsum y".split()
+)
+ALL_FIELDS = _INT_FIELDS + _VEC_FIELDS + ("L",) + tuple(_SCALAR_FIELDS)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """One simulation on the CPU oracle.  kind: '3d', '2d', '3d_fast', '3d_fast_serialdiss'."""
+
+    def __init__(self, params: "OrcParams", kind: str | None = None):
+        self.dim = int(params.dim)
+        self.kind = kind or ("%dd" % self.dim)
+        self.lib = _load(self.kind)
+        self.h = self.lib.orc_create(C.byref(params))
+        if not self.h:
+            raise RuntimeError("orc_create failed (dim mismatch?)")
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.orc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # -- params
+    @property
+    def params(self) -> "OrcParams":
+        p = OrcParams()
+        self.lib.orc_get_params(self.h, C.byref(p))
+        return p
+
+    def set_params(self, **kw):
+        p = self.params
+        set_fields(p, **kw)
+        self.lib.orc_set_params(self.h, C.byref(p))
+
+    # -- blocks / particles
+    def add_block(self, is_fluid, first, second, bound_solver=1, no_slip=0, block_type=0, fixed_vel_or_dynamic=0,
+                  times=None, vels=None, insert_norm=None, insconst=9999999.0, delete_norm=None,
+                  delconst=9999999.0, aero_norm=None, aeroconst=9999999.0, back=None, buffer=None):
+        times_a = None if times is None else np.ascontiguousarray(times, dtype=np.float64)
+        nt = 0 if times_a is None else len(times_a)
+        vels_a = np.zeros((max(1, nt), 3)) if vels is None else np.ascontiguousarray(vels, dtype=np.float64).reshape(-1, 3)
+
+        def v3(x):
+            if x is None:
+                return None
+            a = np.zeros(3)
+            a[: len(x)] = x
+            return a
+
+        ins, dele, aero = v3(insert_norm), v3(delete_norm), v3(aero_norm)
+        back_a = None if back is None else np.ascontiguousarray(back, dtype=np.int64)
+        buf_a = None if buffer is None else np.ascontiguousarray(buffer, dtype=np.int64)
+        nback = 0 if back_a is None else len(back_a)
+        nbuf = 0 if buf_a is None else buf_a.shape[1]
+        r = self.lib.orc_add_block(
+            self.h, int(is_fluid), int(first), int(second), int(bound_solver), int(no_slip), int(block_type),
+            int(fixed_vel_or_dynamic), nt, _ptr(times_a), _ptr(vels_a), _ptr(ins), float(insconst), _ptr(dele),
+            float(delconst), _ptr(aero), float(aeroconst), nback, _ptr(back_a), nbuf, _ptr(buf_a),
+        )
+        if r < 0:
+            raise RuntimeError("orc_add_block: boundary blocks must precede fluid blocks")
+        return r
+
+    def set_particles(self, xi, v, rho, p, m, b, bound_points=0, part_id=None):
+        xi = np.ascontiguousarray(xi, dtype=np.float64)
+        n = xi.shape[0]
+        assert xi.shape[1] == self.dim
+        v = None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+        rho = np.ascontiguousarray(np.broadcast_to(rho, (n,)), dtype=np.float64)
+        p = np.ascontiguousarray(np.broadcast_to(p, (n,)), dtype=np.float64)
+        m = np.ascontiguousarray(np.broadcast_to(m, (n,)), dtype=np.float64)
+        b = np.ascontiguousarray(np.broadcast_to(b, (n,)), dtype=np.int32)
+        pid = None if part_id is None else np.ascontiguousarray(part_id, dtype=np.int64)
+        self.lib.orc_set_particles(self.h, n, int(bound_points), _ptr(xi), _ptr(v), _ptr(rho), _ptr(p), _ptr(m),
+                                   _ptr(b), _ptr(pid))
+
+    @property
+    def n(self) -> int:
+        return int(self.lib.orc_count(self.h))
+
+    def get(self, name: str, level: int = 1) -> np.ndarray:
+        n = self.n
+        if name in _INT_FIELDS:
+            out = np.empty(n, dtype=np.int64)
+            r = self.lib.orc_get_i64(self.h, level, name.encode(), _ptr(out))
+            assert r == 1, name
+            return out
+        d = self.dim
+        width = d if name in _VEC_FIELDS else (d * d if name == "L" else 1)
+        out = np.empty((n, width), dtype=np.float64)
+        r = self.lib.orc_get_f64(self.h, level, name.encode(), _ptr(out))
+        assert r == width, name
+        if name == "L":
+            return out.reshape(n, d, d)
+        return out if width > 1 else out[:, 0]
+
+    def set(self, name: str, value, level: int = 1) -> None:
+        n = self.n
+        if name in _INT_FIELDS:
+            a = np.ascontiguousarray(value, dtype=np.int64).reshape(n)
+            r = self.lib.orc_set_i64(self.h, level, name.encode(), _ptr(a))
+        else:
+            a = np.ascontiguousarray(value, dtype=np.float64).reshape(n, -1)
+            r = self.lib.orc_set_f64(self.h, level, name.encode(), _ptr(a))
+        assert r > 0, name
+
+    def state(self, level: int = 1) -> dict:
+        return {k: self.get(k, level) for k in ALL_FIELDS}
+
+    # -- stages
+    def update_neighbours(self):
+        self.lib.orc_update_neighbours(self.h)
+
+    def neighbours(self):
+        """CSR (offsets, idx, d2), ascending j within each list, self included."""
+        n = self.n
+        tot = int(self.lib.orc_neighbour_total(self.h))
+        off = np.empty(n + 1, dtype=np.int64)
+        idx = np.empty(tot, dtype=np.int64)
+        d2 = np.empty(tot, dtype=np.float64)
+        self.lib.orc_get_neighbours(self.h, _ptr(off), _ptr(idx), _ptr(d2))
+        return off, idx, d2
+
+    def prestep(self) -> float:
+        return float(self.lib.orc_prestep(self.h))
+
+    def aero_velocity(self):
+        self.lib.orc_aero_velocity(self.h)
+
+    def detect_surface(self):
+        self.lib.orc_detect_surface(self.h)
+
+    def dissipation(self):
+        self.lib.orc_dissipation(self.h)
+
+    def particle_shift(self):
+        self.lib.orc_particle_shift(self.h)
+
+    def forces(self, npd: float):
+        self.lib.orc_forces(self.h, float(npd))
+
+    def nb_iter(self, npd: float):
+        self.lib.orc_nb_iter(self.h, float(npd))
+
+    def find_timestep(self) -> float:
+        return float(self.lib.orc_find_timestep(self.h))
+
+    def integrate_no_update(self):
+        s = OrcStepStats()
+        e = self.lib.orc_integrate_no_update(self.h, C.byref(s))
+        return float(e), s
+
+    def integrate(self):
+        s = OrcStepStats()
+        e = self.lib.orc_integrate(self.h, C.byref(s))
+        return float(e), s
+
+
+def qr_inverse(a: np.ndarray):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    d = a.shape[0]
+    lib = _load("%dd" % d)
+    inv = np.zeros_like(a)
+    ok = lib.orc_qr_inverse(_ptr(a), _ptr(inv))
+    return bool(ok), inv
+
+
+def min_eigenvalue(a: np.ndarray) -> float:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    lib = _load("%dd" % a.shape[0])
+    return float(lib.orc_min_eigenvalue(_ptr(a)))
+
+
+def kernel(r, H, Wc, dim=3) -> float:
+    return float(_load("%dd" % dim).orc_kernel(r, H, Wc))
+
+
+def get_n_full(dx, H, dim=3) -> float:
+    return float(_load("%dd" % dim).orc_get_n_full(dx, H))
