@@ -1,0 +1,126 @@
+"""Loader for libfjsph_b200.so (the C ABI of include/fjsph_b200.h).  There is no CPU fallback: a missing
+library or a missing CUDA device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_PKG)
+HEADER = os.path.join(ROOT, "include", "fjsph_b200.h")
+LIB_PATH = os.path.join(_PKG, "lib", "libfjsph_b200.so")
+
+
+def struct_from_header(name: str, header: str = HEADER):
+    """ctypes.Structure generated from `typedef struct <name> { ... } <name>;` so the Python mirror can
+    never drift from the C header."""
+    src = open(header).read()
+    body = re.search(r"typedef struct %s\s*\{(.*?)\}\s*%s;" % (name, name), src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    base = {"int32_t": C.c_int32, "double": C.c_double, "int64_t": C.c_int64}
+    fields = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        stmt = stmt.replace("const ", "")
+        ctype, rest = stmt.split(None, 1)
+        for item in rest.split(","):
+            item = item.strip()
+            ptr = item.startswith("*") or ctype.endswith("*")
+            item = item.lstrip("*").strip()
+            t = base[ctype.rstrip("*")]
+            m = re.match(r"(\w+)\[(\d+)\]", item)
+            if m:
+                fields.append((m.group(1), t * int(m.group(2))))
+            elif ptr:
+                fields.append((item, C.c_void_p))
+            else:
+                fields.append((item, t))
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+FjsphParams = struct_from_header("FjsphParams")
+FjsphBlock = struct_from_header("FjsphBlock")
+FjsphStateView = struct_from_header("FjsphStateView")
+FjsphStepStats = struct_from_header("FjsphStepStats")
+
+
+def declared_functions(header: str = HEADER):
+    """Names of every function the header declares (used by the CPU test that checks the exports)."""
+    src = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(fjsph_\w+)\s*\(", src)))
+
+
+def build(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_PKG, "csrc"), "-j8"]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building libfjsph_b200.so failed:\n" + out.stdout)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libfjsph_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C fjsph_b200/csrc`. There is no CPU fallback." % LIB_PATH
+        )
+    L = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    vp = C.c_void_p
+    L.fjsph_last_error.restype = C.c_char_p
+    L.fjsph_version.restype = C.c_char_p
+    L.fjsph_default_params.argtypes = [P(FjsphParams), C.c_int]
+    L.fjsph_read_para.argtypes = [C.c_char_p, P(FjsphParams), C.c_char_p, C.c_char_p, C.c_int]
+    L.fjsph_set_values.argtypes = [P(FjsphParams)]
+    L.fjsph_create.argtypes = [P(FjsphParams), C.c_int, C.c_int64, P(vp)]
+    L.fjsph_destroy.argtypes = [vp]
+    L.fjsph_get_params.argtypes = [vp, P(FjsphParams)]
+    L.fjsph_set_params.argtypes = [vp, P(FjsphParams)]
+    L.fjsph_set_blocks.argtypes = [vp, C.c_int32, P(FjsphBlock)]
+    L.fjsph_upload_state.argtypes = [vp, P(FjsphStateView), C.c_int64]
+    L.fjsph_upload_level.argtypes = [vp, C.c_int, P(FjsphStateView)]
+    L.fjsph_download_state.argtypes = [vp, C.c_int, P(FjsphStateView)]
+    L.fjsph_count.argtypes = [vp]
+    L.fjsph_count.restype = C.c_int64
+    L.fjsph_build_neighbours.argtypes = [vp]
+    L.fjsph_neighbour_counts.argtypes = [vp, vp]
+    L.fjsph_get_neighbours.argtypes = [vp, vp, vp]
+    L.fjsph_prestep.argtypes = [vp, P(C.c_double)]
+    for f in ("fjsph_aero_velocity", "fjsph_detect_surface", "fjsph_dissipation", "fjsph_shift"):
+        getattr(L, f).argtypes = [vp]
+    L.fjsph_forces.argtypes = [vp, C.c_double]
+    L.fjsph_nb_iter.argtypes = [vp, C.c_double, P(C.c_double)]
+    L.fjsph_find_timestep.argtypes = [vp, P(C.c_double)]
+    L.fjsph_integrate_no_update.argtypes = [vp, P(FjsphStepStats)]
+    L.fjsph_step.argtypes = [vp, P(FjsphStepStats)]
+    L.fjsph_step_host.argtypes = [vp, P(FjsphStateView), C.c_int64, C.c_int32, P(FjsphStateView), P(FjsphStepStats)]
+    L.fjsph_timers_reset.argtypes = [vp]
+    L.fjsph_timers_enable.argtypes = [vp, C.c_int]
+    L.fjsph_timers_get.argtypes = [vp, C.c_int32, vp, vp, vp, P(C.c_int32)]
+    L.fjsph_launch_count.argtypes = [vp]
+    L.fjsph_launch_count.restype = C.c_int64
+    L.fjsph_set_owned.argtypes = [vp, C.c_int64]
+    _lib = L
+    return L
+
+
+class FjsphError(RuntimeError):
+    pass
+
+
+def check(status: int):
+    if status != 0:
+        raise FjsphError("fjsph status %d: %s" % (status, lib().fjsph_last_error().decode()))

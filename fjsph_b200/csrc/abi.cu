@@ -1,0 +1,1058 @@
+// abi.cu — the extern "C" boundary declared in include/fjsph_b200.h: lifetime, host<->device state
+// transfer (AoS-of-vec3 host arrays <-> 32-byte device records), blocks, stage entry points, timers.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "engine.cuh"
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+
+void fj_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int fj_cuda_fail(cudaError_t err, const char* what, const char* file, int line)
+{
+    fj_set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(err), cudaGetErrorString(err), file, line, what);
+    return FJSPH_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ timers
+KScope::KScope(FjsphEngine* e_, const char* name, int launches) : e(e_), id(-1)
+{
+    e->launches += launches;
+    if (!e->timers_on)
+        return;
+    for (size_t k = 0; k < e->timers.size(); ++k)
+        if (e->timers[k].name == name)
+            id = int(k);
+    if (id < 0)
+    {
+        Timer t;
+        t.name = name;
+        e->timers.push_back(t);
+        id = int(e->timers.size()) - 1;
+    }
+    e->timers[id].launches += launches;
+    cudaEventRecord(e->ev0, e->stream);
+}
+KScope::~KScope()
+{
+    if (id < 0)
+        return;
+    cudaEventRecord(e->ev1, e->stream);
+    cudaEventSynchronize(e->ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->timers[id].ms += ms;
+}
+
+// ------------------------------------------------------------------ constants
+void fj_refresh_constants(FjsphEngine* e)
+{
+    const FjsphParams& P = e->P;
+    DevConst& C = e->C;
+    C.H = P.H;
+    C.H_sq = P.H_sq;
+    C.iH = 1.0 / P.H;
+    C.sr = P.sr;
+    C.W_correc = P.W_correc;
+    C.W_dx = P.W_dx;
+    C.iW_dx = 1.0 / P.W_dx;
+    C.gk_fac = 5.0 * P.W_correc / (P.H * P.H);
+    C.rho_rest = P.rho_rest;
+    C.rho_min = P.rho_min;
+    C.rho_max = P.rho_max;
+    C.B = P.B;
+    C.gam = P.gam;
+    C.c2 = P.speed_sound * P.speed_sound;
+    C.press_back = P.press_back;
+    C.Bgam = P.B * P.gam;
+    C.visc_alpha = P.visc_alpha;
+    C.nu = P.nu;
+    C.dsph_cont = P.dsph_cont;
+    C.sig = P.sig;
+    C.dx = P.dx;
+    C.particle_step = P.particle_step;
+    C.gx = P.grav[0];
+    C.gy = P.grav[1];
+    C.gz = P.grav[2];
+    C.vinf_x = P.v_inf[0];
+    C.vinf_y = P.v_inf[1];
+    C.vinf_z = P.v_inf[2];
+    C.lam_cutoff = P.lam_cutoff;
+    C.interp_fac = P.interp_fac;
+    C.i_n_full = P.i_n_full;
+    C.aero_L = P.aero_L;
+    C.A_sphere = P.A_sphere;
+    C.A_plate = P.A_plate;
+    C.mu_g = P.mu_g;
+    C.sos2 = P.sos * P.sos;
+    C.gamma_g = P.gamma_g;
+    C.ycoef = P.ycoef;
+    C.tab_Cb = P.tab_Cb;
+    C.max_shift_vel = P.max_shift_vel;
+    C.bnd_mass = P.bnd_mass;
+    C.sim_mass = P.sim_mass;
+    C.c_sound = P.speed_sound;
+    C.ale = P.ale;
+    C.pressure_rel = P.pressure_rel;
+    C.acase = P.acase;
+    C.asource = P.asource;
+    C.use_lam = P.use_lam;
+    C.use_TAB_def = P.use_TAB_def;
+}
+
+static int validate_params(const FjsphParams& P)
+{
+    if (P.dim != 3)
+    {
+        fj_set_error("the device path supports SIMDIM=3 only (got dim=%d)", P.dim);
+        return FJSPH_ERR_INVALID;
+    }
+    if (!(P.H > 0.0) || !(P.sr > 0.0) || !(P.W_correc > 0.0))
+    {
+        fj_set_error("derived constants missing: call fjsph_set_values() before fjsph_create()");
+        return FJSPH_ERR_INVALID;
+    }
+    if (P.acase != 0 && P.acase != 1)
+    {
+        fj_set_error("aerodynamic case %d is not supported (NoAero=0 or Gissler=1)", P.acase);
+        return FJSPH_ERR_INVALID;
+    }
+    if (P.asource != 0)
+    {
+        fj_set_error("aero source %d is not supported on the device yet (constVel=0 only)", P.asource);
+        return FJSPH_ERR_INVALID;
+    }
+    if (P.solver_type != 0 && P.solver_type != 1)
+    {
+        fj_set_error("solver_type %d unknown (0 Newmark-Beta, 1 Runge-Kutta)", P.solver_type);
+        return FJSPH_ERR_INVALID;
+    }
+    if (P.pressure_rel != 0 && P.pressure_rel != 1)
+    {
+        fj_set_error("pressure_rel %d unknown (0 Cole, 1 isothermal)", P.pressure_rel);
+        return FJSPH_ERR_INVALID;
+    }
+    return FJSPH_OK;
+}
+
+// ------------------------------------------------------------------ pack / unpack kernels
+struct StageView
+{
+    long long* part_id;
+    long long* cellID;
+    int *b, *surf, *surfzone, *internal;
+    double *xi, *v, *acc, *Af, *aVisc, *cellV, *gradRho, *norm, *bNorm, *vPert, *L;
+    double *Rrho, *rho, *p, *m, *curve, *norm_curve, *woccl, *pDist, *deltaD, *cellP, *cellRho, *colourG, *colour,
+        *lam, *lam_nb, *kernsum, *y;
+};
+
+namespace
+{
+constexpr int TPB = 256;
+
+__global__ void k_init_level(Level S, DevConst C, double cellRho, double cellP, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double4 z = make_double4(0, 0, 0, 0);
+    S.P0[i] = make_double4(0, 0, 0, 1.0);
+    S.P1[i] = make_double4(0, 0, 0, 1.0);
+    S.P2[i] = z;
+    S.P3[i] = z;
+    S.P4[i] = z;
+    S.ACC[i] = z;
+    S.AF[i] = z;
+    S.AV[i] = z;
+    S.CV[i] = make_double4(C.vinf_x, C.vinf_y, C.vinf_z, cellP); /* FJSPH.cpp:115-126 */
+    S.NP[i] = z;
+    S.BN[i] = z;
+    S.TH[i] = make_double4(0.0, 1.0, 0.0, cellRho);
+    S.SC[i] = z;
+    S.L0[i] = S.L1[i] = S.L2[i] = S.L3[i] = S.L4[i] = S.L5[i] = S.L6[i] = S.L7[i] = S.L8[i] = 0.0;
+    S.part_id[i] = i;
+    S.cellID[i] = -3; /* c_no_cell, VarDefs.h:197 */
+    S.b[i] = 0;
+    S.surfzone[i] = 0;
+    S.internal[i] = 0;
+}
+
+__global__ void k_identity_index(int* oidx, int* slot_of, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        oidx[i] = i;
+        slot_of[i] = i;
+    }
+}
+
+__global__ void k_assign_blk(const int* __restrict__ oidx, const long long* __restrict__ ranges, int n_blocks,
+                             int* __restrict__ blk, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const long long c = oidx[i];
+    int out = n_blocks - 1;
+    for (int k = 0; k < n_blocks; ++k)
+        if (c >= ranges[2 * k] && c < ranges[2 * k + 1])
+        {
+            out = k;
+            break;
+        }
+    blk[i] = out;
+}
+
+// host-order staged arrays -> device records (only non-null fields are overwritten)
+__global__ void k_pack(Level S, StageView h, const int* __restrict__ slot_of, int n)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n)
+        return;
+    const int i = slot_of[c];
+    double4 p0 = S.P0[i], p1 = S.P1[i], p2 = S.P2[i], th = S.TH[i];
+    double rho = p1.w, p = th.x, m = th.y;
+    if (h.xi)
+    {
+        p0.x = h.xi[3 * c];
+        p0.y = h.xi[3 * c + 1];
+        p0.z = h.xi[3 * c + 2];
+    }
+    if (h.v)
+    {
+        p1.x = h.v[3 * c];
+        p1.y = h.v[3 * c + 1];
+        p1.z = h.v[3 * c + 2];
+    }
+    if (h.vPert)
+    {
+        p2.x = h.vPert[3 * c];
+        p2.y = h.vPert[3 * c + 1];
+        p2.z = h.vPert[3 * c + 2];
+    }
+    if (h.rho)
+        rho = h.rho[c];
+    if (h.p)
+        p = h.p[c];
+    if (h.m)
+        m = h.m[c];
+    p0.w = m / rho;
+    p1.w = rho;
+    p2.w = p / (rho * rho);
+    th.x = p;
+    th.y = m;
+    if (h.woccl)
+        th.z = h.woccl[c];
+    if (h.cellRho)
+        th.w = h.cellRho[c];
+    S.P0[i] = p0;
+    S.P1[i] = p1;
+    S.P2[i] = p2;
+    S.TH[i] = th;
+    if (h.gradRho || h.lam)
+    {
+        double4 r = S.P3[i];
+        if (h.gradRho)
+        {
+            r.x = h.gradRho[3 * c];
+            r.y = h.gradRho[3 * c + 1];
+            r.z = h.gradRho[3 * c + 2];
+        }
+        if (h.lam)
+            r.w = h.lam[c];
+        S.P3[i] = r;
+    }
+    if (h.norm || h.surf || h.lam_nb)
+    {
+        double4 r = S.P4[i], q = S.NP[i];
+        if (h.norm)
+        {
+            r.x = q.x = h.norm[3 * c];
+            r.y = q.y = h.norm[3 * c + 1];
+            r.z = q.z = h.norm[3 * c + 2];
+        }
+        if (h.surf)
+            r.w = double(h.surf[c]);
+        if (h.lam_nb)
+            q.w = h.lam_nb[c];
+        S.P4[i] = r;
+        S.NP[i] = q;
+    }
+    if (h.acc || h.Rrho)
+    {
+        double4 r = S.ACC[i];
+        if (h.acc)
+        {
+            r.x = h.acc[3 * c];
+            r.y = h.acc[3 * c + 1];
+            r.z = h.acc[3 * c + 2];
+        }
+        if (h.Rrho)
+            r.w = h.Rrho[c];
+        S.ACC[i] = r;
+    }
+    if (h.Af || h.deltaD)
+    {
+        double4 r = S.AF[i];
+        if (h.Af)
+        {
+            r.x = h.Af[3 * c];
+            r.y = h.Af[3 * c + 1];
+            r.z = h.Af[3 * c + 2];
+        }
+        if (h.deltaD)
+            r.w = h.deltaD[c];
+        S.AF[i] = r;
+    }
+    if (h.aVisc || h.curve)
+    {
+        double4 r = S.AV[i];
+        if (h.aVisc)
+        {
+            r.x = h.aVisc[3 * c];
+            r.y = h.aVisc[3 * c + 1];
+            r.z = h.aVisc[3 * c + 2];
+        }
+        if (h.curve)
+            r.w = h.curve[c];
+        S.AV[i] = r;
+    }
+    if (h.cellV || h.cellP)
+    {
+        double4 r = S.CV[i];
+        if (h.cellV)
+        {
+            r.x = h.cellV[3 * c];
+            r.y = h.cellV[3 * c + 1];
+            r.z = h.cellV[3 * c + 2];
+        }
+        if (h.cellP)
+            r.w = h.cellP[c];
+        S.CV[i] = r;
+    }
+    if (h.bNorm || h.y)
+    {
+        double4 r = S.BN[i];
+        if (h.bNorm)
+        {
+            r.x = h.bNorm[3 * c];
+            r.y = h.bNorm[3 * c + 1];
+            r.z = h.bNorm[3 * c + 2];
+        }
+        if (h.y)
+            r.w = h.y[c];
+        S.BN[i] = r;
+    }
+    if (h.colourG || h.colour || h.kernsum || h.pDist)
+    {
+        double4 r = S.SC[i];
+        if (h.colourG)
+            r.x = h.colourG[c];
+        if (h.colour)
+            r.y = h.colour[c];
+        if (h.kernsum)
+            r.z = h.kernsum[c];
+        if (h.pDist)
+            r.w = h.pDist[c];
+        S.SC[i] = r;
+    }
+    if (h.L)
+    {
+        S.L0[i] = h.L[9 * c];
+        S.L1[i] = h.L[9 * c + 1];
+        S.L2[i] = h.L[9 * c + 2];
+        S.L3[i] = h.L[9 * c + 3];
+        S.L4[i] = h.L[9 * c + 4];
+        S.L5[i] = h.L[9 * c + 5];
+        S.L6[i] = h.L[9 * c + 6];
+        S.L7[i] = h.L[9 * c + 7];
+        S.L8[i] = h.L[9 * c + 8];
+    }
+    if (h.part_id)
+        S.part_id[i] = h.part_id[c];
+    if (h.cellID)
+        S.cellID[i] = int(h.cellID[c]);
+    if (h.b)
+        S.b[i] = h.b[c];
+    if (h.surfzone)
+        S.surfzone[i] = h.surfzone[c];
+    if (h.internal)
+        S.internal[i] = h.internal[c];
+}
+
+__global__ void k_unpack(Level S, StageView h, const int* __restrict__ slot_of, double dx, int n)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n)
+        return;
+    const int i = slot_of[c];
+    const double4 p0 = S.P0[i], p1 = S.P1[i], p2 = S.P2[i], th = S.TH[i];
+#define V3(dst, r)            \
+    if (h.dst)                \
+    {                         \
+        h.dst[3 * c] = r.x;   \
+        h.dst[3 * c + 1] = r.y; \
+        h.dst[3 * c + 2] = r.z; \
+    }
+    V3(xi, p0)
+    V3(v, p1)
+    V3(vPert, p2)
+    if (h.rho)
+        h.rho[c] = p1.w;
+    if (h.p)
+        h.p[c] = th.x;
+    if (h.m)
+        h.m[c] = th.y;
+    if (h.woccl)
+        h.woccl[c] = th.z;
+    if (h.cellRho)
+        h.cellRho[c] = th.w;
+    const double4 p3 = S.P3[i], p4 = S.P4[i], np = S.NP[i], acc = S.ACC[i], af = S.AF[i], av = S.AV[i], cv = S.CV[i],
+                  bn = S.BN[i], sc = S.SC[i];
+    V3(gradRho, p3)
+    if (h.lam)
+        h.lam[c] = p3.w;
+    V3(norm, np)
+    if (h.lam_nb)
+        h.lam_nb[c] = np.w;
+    if (h.surf)
+        h.surf[c] = (p4.w != 0.0) ? 1 : 0;
+    V3(acc, acc)
+    if (h.Rrho)
+        h.Rrho[c] = acc.w;
+    V3(Af, af)
+    if (h.deltaD)
+        h.deltaD[c] = af.w;
+    V3(aVisc, av)
+    if (h.curve)
+        h.curve[c] = av.w;
+    if (h.norm_curve)
+        h.norm_curve[c] = dx * av.w; /* Geometry.cpp:259 */
+    V3(cellV, cv)
+    if (h.cellP)
+        h.cellP[c] = cv.w;
+    V3(bNorm, bn)
+    if (h.y)
+        h.y[c] = bn.w;
+    if (h.colourG)
+        h.colourG[c] = sc.x;
+    if (h.colour)
+        h.colour[c] = sc.y;
+    if (h.kernsum)
+        h.kernsum[c] = sc.z;
+    if (h.pDist)
+        h.pDist[c] = sc.w;
+#undef V3
+    if (h.L)
+    {
+        h.L[9 * c] = S.L0[i];
+        h.L[9 * c + 1] = S.L1[i];
+        h.L[9 * c + 2] = S.L2[i];
+        h.L[9 * c + 3] = S.L3[i];
+        h.L[9 * c + 4] = S.L4[i];
+        h.L[9 * c + 5] = S.L5[i];
+        h.L[9 * c + 6] = S.L6[i];
+        h.L[9 * c + 7] = S.L7[i];
+        h.L[9 * c + 8] = S.L8[i];
+    }
+    if (h.part_id)
+        h.part_id[c] = S.part_id[i];
+    if (h.cellID)
+        h.cellID[c] = S.cellID[i];
+    if (h.b)
+        h.b[c] = S.b[i];
+    if (h.surfzone)
+        h.surfzone[c] = S.surfzone[i];
+    if (h.internal)
+        h.internal[c] = S.internal[i];
+}
+
+__global__ void k_counts_out(const int* __restrict__ ncount, const int* __restrict__ slot_of, long long* out, int n)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n)
+        out[c] = ncount[slot_of[c]] + 1;
+}
+
+struct FieldSpec
+{
+    size_t host_off;  // offset of the pointer inside FjsphStateView
+    size_t stage_off; // offset of the pointer inside StageView
+    int bytes;        // bytes per particle
+};
+#define FS(name, bytes) {offsetof(FjsphStateView, name), offsetof(StageView, name), bytes}
+const FieldSpec kFields[] = {
+    FS(part_id, 8), FS(cellID, 8),   FS(b, 4),       FS(surf, 4),       FS(surfzone, 4), FS(internal, 4), FS(xi, 24),
+    FS(v, 24),      FS(acc, 24),     FS(Af, 24),     FS(aVisc, 24),     FS(cellV, 24),   FS(gradRho, 24), FS(norm, 24),
+    FS(bNorm, 24),  FS(vPert, 24),   FS(L, 72),      FS(Rrho, 8),       FS(rho, 8),      FS(p, 8),        FS(m, 8),
+    FS(curve, 8),   FS(norm_curve, 8), FS(woccl, 8), FS(pDist, 8),      FS(deltaD, 8),   FS(cellP, 8),    FS(cellRho, 8),
+    FS(colourG, 8), FS(colour, 8),   FS(lam, 8),     FS(lam_nb, 8),     FS(kernsum, 8),  FS(y, 8),
+};
+constexpr size_t kStageBytesPerParticle = 8 * 2 + 4 * 4 + 24 * 10 + 72 + 8 * 17;
+
+// lays the non-null host fields out in the staging buffer; returns the device-side view
+int stage_layout(FjsphEngine* e, const FjsphStateView* s, StageView* dv, std::vector<std::pair<void*, void*>>* copies,
+                 std::vector<size_t>* sizes)
+{
+    std::memset(dv, 0, sizeof(*dv));
+    const size_t n = size_t(s->n);
+    size_t off = 0;
+    for (const FieldSpec& f : kFields)
+    {
+        void* hp = *(void* const*)((const char*)s + f.host_off);
+        if (!hp)
+            continue;
+        const size_t bytes = n * size_t(f.bytes);
+        if (off + bytes > e->stage_bytes)
+        {
+            fj_set_error("staging buffer too small");
+            return FJSPH_ERR_CAPACITY;
+        }
+        void* dp = (char*)e->stage + off;
+        *(void**)((char*)dv + f.stage_off) = dp;
+        copies->push_back(std::make_pair(hp, dp));
+        sizes->push_back(bytes);
+        off += (bytes + 255) & ~size_t(255);
+    }
+    return FJSPH_OK;
+}
+
+int upload_fields(FjsphEngine* e, int level, const FjsphStateView* s)
+{
+    StageView dv;
+    std::vector<std::pair<void*, void*>> copies;
+    std::vector<size_t> sizes;
+    int st = stage_layout(e, s, &dv, &copies, &sizes);
+    if (st)
+        return st;
+    for (size_t k = 0; k < copies.size(); ++k)
+        FJ_CUDA(cudaMemcpyAsync(copies[k].second, copies[k].first, sizes[k], cudaMemcpyHostToDevice, e->stream));
+    const int n = int(s->n);
+    e->launches++;
+    k_pack<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[level], dv, e->slot_of, n);
+    FJ_CUDA(cudaGetLastError());
+    return FJSPH_OK;
+}
+
+int rebuild_blk(FjsphEngine* e)
+{
+    std::vector<long long> ranges;
+    for (const HostBlock& B : e->blocks)
+    {
+        ranges.push_back(B.first);
+        ranges.push_back(B.second);
+    }
+    long long* d = nullptr;
+    FJ_CUDA(cudaMalloc(&d, ranges.size() * sizeof(long long)));
+    FJ_CUDA(cudaMemcpyAsync(d, ranges.data(), ranges.size() * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    const int n = int(e->n);
+    e->launches++;
+    k_assign_blk<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->oidx, d, int(e->blocks.size()), e->blk, n);
+    FJ_CUDA(cudaGetLastError());
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    cudaFree(d);
+    return FJSPH_OK;
+}
+
+void default_blocks(FjsphEngine* e)
+{
+    e->blocks.clear();
+    e->n_bound_blocks = 0;
+    auto mk = [](int64_t a, int64_t b, int fluid) {
+        HostBlock B;
+        B.first = a;
+        B.second = b;
+        B.is_fluid = fluid;
+        B.bound_solver = FJSPH_PRESSURE_G;
+        B.no_slip = 0;
+        B.block_type = 0;
+        B.fixed_vel_or_dynamic = 0;
+        B.vels.assign(3, 0.0);
+        for (int d = 0; d < 3; ++d) B.insert_norm[d] = B.delete_norm[d] = B.aero_norm[d] = 9999999.0;
+        B.insconst = B.delconst = B.aeroconst = 9999999.0;
+        return B;
+    };
+    if (e->bound_points > 0)
+    {
+        e->blocks.push_back(mk(0, e->bound_points, 0));
+        e->n_bound_blocks = 1;
+    }
+    e->blocks.push_back(mk(e->bound_points, e->n, 1));
+}
+
+} // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+const char* fjsph_last_error(void) { return g_err; }
+const char* fjsph_version(void) { return "fjsph_b200 0.1 (sm_100a)"; }
+
+int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine** out)
+{
+    if (!p || !out || capacity <= 0)
+    {
+        fj_set_error("fjsph_create: bad arguments");
+        return FJSPH_ERR_INVALID;
+    }
+    if (capacity > int64_t(FJ_IDX_MASK))
+    {
+        fj_set_error("capacity %lld exceeds the 2^28-1 particles one engine can index", (long long)capacity);
+        return FJSPH_ERR_CAPACITY;
+    }
+    int st = validate_params(*p);
+    if (st)
+        return st;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+    {
+        fj_set_error("no CUDA device available (%s): the engine has no CPU fallback",
+                     ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+        return FJSPH_ERR_CUDA;
+    }
+    FJ_CUDA(cudaSetDevice(device));
+    FjsphEngine* e = new FjsphEngine();
+    e->P = *p;
+    e->device = device;
+    e->cap = capacity;
+    fj_refresh_constants(e);
+    cudaDeviceProp prop;
+    FJ_CUDA(cudaGetDeviceProperties(&prop, device));
+    e->n_sm = prop.multiProcessorCount;
+    FJ_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    FJ_CUDA(cudaEventCreate(&e->ev0));
+    FJ_CUDA(cudaEventCreate(&e->ev1));
+    const size_t cap = size_t(capacity);
+    for (int l = 0; l < 3; ++l)
+    {
+#define X(T, f) FJ_CUDA(cudaMalloc(&e->lv[l].f, cap * sizeof(T)));
+        FJ_LEVEL_FIELDS(X)
+#undef X
+    }
+    FJ_CUDA(cudaMalloc(&e->oidx, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->oidx_tmp, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->slot_of, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->blk, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->blk_tmp, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->key, cap * sizeof(unsigned)));
+    FJ_CUDA(cudaMalloc(&e->rank_in_cell, cap * sizeof(unsigned)));
+    FJ_CUDA(cudaMalloc(&e->perm, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->perm2, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->ncount, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->near_inlet, cap * sizeof(int)));
+    FJ_CUDA(cudaMemset(e->near_inlet, 0, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->rk_sum_v, cap * sizeof(double4)));
+    FJ_CUDA(cudaMalloc(&e->rk_sum_a, cap * sizeof(double4)));
+    const size_t red_n = std::max<size_t>((cap + 127) / 128 + 16, 2048 * 8);
+    FJ_CUDA(cudaMalloc(&e->red, red_n * sizeof(double)));
+    FJ_CUDA(cudaMalloc(&e->red_out, 16 * sizeof(double)));
+    FJ_CUDA(cudaMallocHost(&e->h_red, 16 * sizeof(double)));
+    FJ_CUDA(cudaMalloc(&e->d_flag, 4 * sizeof(int)));
+    FJ_CUDA(cudaMallocHost(&e->h_flag, 4 * sizeof(int)));
+    e->stage_bytes = cap * kStageBytesPerParticle + 64 * 256;
+    FJ_CUDA(cudaMalloc(&e->stage, e->stage_bytes));
+    *out = e;
+    return FJSPH_OK;
+}
+
+int fjsph_destroy(FjsphEngine* e)
+{
+    if (!e)
+        return FJSPH_OK;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (int l = 0; l < 3; ++l)
+    {
+#define X(T, f) cudaFree(e->lv[l].f);
+        FJ_LEVEL_FIELDS(X)
+#undef X
+    }
+    void* ptrs[] = {e->oidx,       e->oidx_tmp, e->slot_of,  e->blk,      e->blk_tmp,   e->key,     e->rank_in_cell,
+                    e->perm,       e->perm2,    e->ncount,   e->near_inlet, e->rk_sum_v, e->rk_sum_a, e->red,
+                    e->red_out,    e->d_flag,   e->stage,    e->cell_count, e->cell_start, e->scan_tmp, e->mtab_x,
+                    e->nlist};
+    for (void* p : ptrs)
+        if (p)
+            cudaFree(p);
+    if (e->h_red)
+        cudaFreeHost(e->h_red);
+    if (e->h_flag)
+        cudaFreeHost(e->h_flag);
+    cudaEventDestroy(e->ev0);
+    cudaEventDestroy(e->ev1);
+    cudaStreamDestroy(e->stream);
+    delete e;
+    return FJSPH_OK;
+}
+
+int fjsph_get_params(FjsphEngine* e, FjsphParams* out)
+{
+    *out = e->P;
+    return FJSPH_OK;
+}
+int fjsph_set_params(FjsphEngine* e, const FjsphParams* in)
+{
+    int st = validate_params(*in);
+    if (st)
+        return st;
+    e->P = *in;
+    fj_refresh_constants(e);
+    return FJSPH_OK;
+}
+
+int fjsph_set_blocks(FjsphEngine* e, int32_t n_blocks, const FjsphBlock* blocks)
+{
+    cudaSetDevice(e->device);
+    std::vector<HostBlock> out;
+    int n_bound = 0;
+    bool seen_fluid = false;
+    for (int k = 0; k < n_blocks; ++k)
+    {
+        const FjsphBlock& b = blocks[k];
+        HostBlock B;
+        B.first = b.first;
+        B.second = b.second;
+        B.is_fluid = b.is_fluid;
+        B.bound_solver = b.bound_solver;
+        B.no_slip = b.no_slip;
+        B.block_type = b.block_type;
+        B.fixed_vel_or_dynamic = b.fixed_vel_or_dynamic;
+        for (int t = 0; t < b.n_times; ++t) B.times.push_back(b.times[t]);
+        const int nv = std::max(1, b.n_times);
+        for (int t = 0; t < 3 * nv; ++t) B.vels.push_back(b.vels ? b.vels[t] : 0.0);
+        for (int d = 0; d < 3; ++d)
+        {
+            B.insert_norm[d] = b.insert_norm[d];
+            B.delete_norm[d] = b.delete_norm[d];
+            B.aero_norm[d] = b.aero_norm[d];
+        }
+        B.insconst = b.insconst;
+        B.delconst = b.delconst;
+        B.aeroconst = b.aeroconst;
+        for (int i = 0; i < b.n_back; ++i)
+        {
+            B.back.push_back(b.back[i]);
+            std::vector<int64_t> buf;
+            for (int j = 0; j < b.n_buf; ++j) buf.push_back(b.buffer[size_t(i) * b.n_buf + j]);
+            B.buffer.push_back(buf);
+        }
+        if (b.is_fluid)
+            seen_fluid = true;
+        else
+        {
+            if (seen_fluid)
+            {
+                fj_set_error("set_blocks: boundary blocks must precede fluid blocks (Init.cpp:298-475)");
+                return FJSPH_ERR_INVALID;
+            }
+            n_bound++;
+        }
+        out.push_back(B);
+    }
+    if (out.empty() || !seen_fluid)
+    {
+        fj_set_error("set_blocks: at least one fluid block is required");
+        return FJSPH_ERR_INVALID;
+    }
+    e->blocks = out;
+    e->n_bound_blocks = n_bound;
+    if (e->n > 0)
+        return rebuild_blk(e);
+    return FJSPH_OK;
+}
+
+int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_points)
+{
+    cudaSetDevice(e->device);
+    if (!s || s->n <= 0 || !s->xi || !s->rho || !s->p || !s->m || !s->b)
+    {
+        fj_set_error("upload_state: xi, rho, p, m and b are required");
+        return FJSPH_ERR_INVALID;
+    }
+    if (s->n > e->cap)
+    {
+        fj_set_error("upload_state: %lld particles exceed the capacity %lld given to fjsph_create", (long long)s->n,
+                     (long long)e->cap);
+        return FJSPH_ERR_CAPACITY;
+    }
+    if (bound_points < 0 || bound_points > s->n)
+    {
+        fj_set_error("upload_state: bound_points out of range");
+        return FJSPH_ERR_INVALID;
+    }
+    const bool keep_blocks = !e->blocks.empty() && e->blocks.back().second == s->n && e->n == s->n &&
+                             e->bound_points == bound_points;
+    e->n = s->n;
+    e->n_owned = s->n;
+    e->bound_points = bound_points;
+    e->list_valid = false;
+    const int n = int(e->n);
+    e->launches += 2;
+    k_identity_index<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->oidx, e->slot_of, n);
+    k_init_level<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], e->C, e->P.rho_g, e->P.p_ref, n);
+    FJ_CUDA(cudaGetLastError());
+    int st = upload_fields(e, 1, s);
+    if (st)
+        return st;
+    st = fj_copy_level(e, 0, 1); /* pnp1 = pn, Init.cpp:496 */
+    if (st)
+        return st;
+    if (!keep_blocks)
+        default_blocks(e);
+    st = rebuild_blk(e);
+    if (st)
+        return st;
+    e->maxShift = 0.0;
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+
+int fjsph_upload_level(FjsphEngine* e, int level, const FjsphStateView* s)
+{
+    cudaSetDevice(e->device);
+    if (level < 0 || level > 1 || !s || s->n != e->n)
+    {
+        fj_set_error("upload_level: bad level or particle count (have %lld)", (long long)e->n);
+        return FJSPH_ERR_INVALID;
+    }
+    if (s->xi)
+        e->list_valid = false;
+    int st = upload_fields(e, level, s);
+    if (st)
+        return st;
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+
+int fjsph_download_state(FjsphEngine* e, int level, FjsphStateView* s)
+{
+    cudaSetDevice(e->device);
+    if (level < 0 || level > 1 || !s)
+    {
+        fj_set_error("download_state: bad arguments");
+        return FJSPH_ERR_INVALID;
+    }
+    if (s->n < e->n_owned)
+    {
+        fj_set_error("download_state: view holds %lld particles, engine has %lld", (long long)s->n,
+                     (long long)e->n_owned);
+        return FJSPH_ERR_INVALID;
+    }
+    FjsphStateView view = *s;
+    view.n = e->n_owned;
+    StageView dv;
+    std::vector<std::pair<void*, void*>> copies;
+    std::vector<size_t> sizes;
+    int st = stage_layout(e, &view, &dv, &copies, &sizes);
+    if (st)
+        return st;
+    const int n = int(e->n_owned);
+    e->launches++;
+    k_unpack<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[level], dv, e->slot_of, e->P.dx, n);
+    FJ_CUDA(cudaGetLastError());
+    for (size_t k = 0; k < copies.size(); ++k)
+        FJ_CUDA(cudaMemcpyAsync(copies[k].first, copies[k].second, sizes[k], cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    s->n = e->n_owned;
+    return FJSPH_OK;
+}
+
+int64_t fjsph_count(FjsphEngine* e) { return e ? e->n_owned : -1; }
+
+int fjsph_build_neighbours(FjsphEngine* e)
+{
+    cudaSetDevice(e->device);
+    return fj_build_neighbours(e);
+}
+
+int fjsph_neighbour_counts(FjsphEngine* e, int64_t* counts)
+{
+    cudaSetDevice(e->device);
+    if (!e->list_valid)
+    {
+        fj_set_error("neighbour_counts: list not built");
+        return FJSPH_ERR_STATE;
+    }
+    const int n = int(e->n_owned);
+    long long* d = (long long*)e->stage;
+    k_counts_out<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->ncount, e->slot_of, d, n);
+    FJ_CUDA(cudaGetLastError());
+    FJ_CUDA(cudaMemcpyAsync(counts, d, size_t(n) * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+
+// Debug / parity view of the neighbour list in the reference's shape: CSR over caller indices, self
+// included, ascending j.  offsets must be the exclusive prefix sum of fjsph_neighbour_counts.
+int fjsph_get_neighbours(FjsphEngine* e, const int64_t* offsets, int64_t* idx)
+{
+    cudaSetDevice(e->device);
+    if (!e->list_valid)
+    {
+        fj_set_error("get_neighbours: list not built");
+        return FJSPH_ERR_STATE;
+    }
+    const size_t n = size_t(e->n_owned);
+    const size_t nw = (n + 31) / 32;
+    std::vector<int> cnt(n), oidx(n);
+    std::vector<unsigned> list(nw * size_t(e->nb_cap) * 32u);
+    FJ_CUDA(cudaMemcpyAsync(cnt.data(), e->ncount, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaMemcpyAsync(oidx.data(), e->oidx, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaMemcpyAsync(list.data(), e->nlist, list.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < n; ++i)
+    {
+        const int64_t c = oidx[i];
+        int64_t* dst = idx + offsets[c];
+        const size_t base = (i >> 5) * size_t(e->nb_cap) * 32u + (i & 31);
+        int k = 0;
+        for (; k < cnt[i]; ++k) dst[k] = oidx[list[base + size_t(k) * 32u] & FJ_IDX_MASK];
+        dst[k++] = c;
+        if (offsets[c + 1] - offsets[c] != k)
+        {
+            fj_set_error("get_neighbours: offsets do not match neighbour_counts");
+            return FJSPH_ERR_INVALID;
+        }
+        std::sort(dst, dst + k);
+    }
+    return FJSPH_OK;
+}
+
+int fjsph_prestep(FjsphEngine* e, double* npd)
+{
+    cudaSetDevice(e->device);
+    return fj_prestep(e, npd);
+}
+int fjsph_aero_velocity(FjsphEngine* e)
+{
+    cudaSetDevice(e->device);
+    int st = fj_aero_velocity(e);
+    if (st)
+        return st;
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+int fjsph_detect_surface(FjsphEngine* e)
+{
+    cudaSetDevice(e->device);
+    int st = fj_surface_and_dissipation(e, true, false);
+    if (st)
+        return st;
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+int fjsph_dissipation(FjsphEngine* e)
+{
+    cudaSetDevice(e->device);
+    int st = fj_surface_and_dissipation(e, false, true);
+    if (st)
+        return st;
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+int fjsph_shift(FjsphEngine* e)
+{
+    cudaSetDevice(e->device);
+    int st = fj_shift(e);
+    if (st)
+        return st;
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+int fjsph_forces(FjsphEngine* e, double npd)
+{
+    cudaSetDevice(e->device);
+    int st = fj_forces(e, 1, npd);
+    if (st)
+        return st;
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+int fjsph_nb_iter(FjsphEngine* e, double npd, double* errsum)
+{
+    cudaSetDevice(e->device);
+    return fj_nb_iter(e, npd, errsum);
+}
+int fjsph_find_timestep(FjsphEngine* e, double* dt)
+{
+    cudaSetDevice(e->device);
+    return fj_find_timestep(e, dt);
+}
+int fjsph_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
+{
+    cudaSetDevice(e->device);
+    return fj_integrate_no_update(e, s);
+}
+int fjsph_step(FjsphEngine* e, FjsphStepStats* s)
+{
+    cudaSetDevice(e->device);
+    int st = fj_step(e, s);
+    if (st)
+        return st;
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+
+int fjsph_step_host(FjsphEngine* e, const FjsphStateView* in, int64_t bound_points, int32_t n_steps,
+                    FjsphStateView* out, FjsphStepStats* last)
+{
+    int st = fjsph_upload_state(e, in, bound_points);
+    if (st)
+        return st;
+    for (int k = 0; k < n_steps; ++k)
+    {
+        st = fjsph_step(e, last);
+        if (st)
+            return st;
+    }
+    return fjsph_download_state(e, 1, out);
+}
+
+int fjsph_timers_reset(FjsphEngine* e)
+{
+    e->timers.clear();
+    return FJSPH_OK;
+}
+int fjsph_timers_enable(FjsphEngine* e, int on)
+{
+    e->timers_on = on != 0;
+    return FJSPH_OK;
+}
+int fjsph_timers_get(FjsphEngine* e, int32_t cap, char* names, double* ms, int64_t* launches, int32_t* n_out)
+{
+    const int n = std::min<int>(cap, int(e->timers.size()));
+    for (int k = 0; k < n; ++k)
+    {
+        std::snprintf(names + size_t(k) * 32, 32, "%s", e->timers[k].name.c_str());
+        ms[k] = e->timers[k].ms;
+        launches[k] = e->timers[k].launches;
+    }
+    *n_out = n;
+    return FJSPH_OK;
+}
+int64_t fjsph_launch_count(FjsphEngine* e) { return e->launches; }
+
+int fjsph_set_owned(FjsphEngine* e, int64_t n_owned)
+{
+    if (n_owned < 0 || n_owned > e->n)
+    {
+        fj_set_error("set_owned: out of range");
+        return FJSPH_ERR_INVALID;
+    }
+    e->n_owned = n_owned;
+    return FJSPH_OK;
+}
+
+} // extern "C"

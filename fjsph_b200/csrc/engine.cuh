@@ -1,0 +1,190 @@
+// engine.cuh — device data layout and shared helpers of the B200 WCSPH engine (sm_100a only).
+//
+// Layout (DESIGN.md "Data layout in HBM"): particles live in cell-sorted order; every quantity a pair
+// sweep GATHERS from neighbour j is packed in a 32-byte record (one DRAM/L2 sector, two LDG.128):
+//   P0 = {x, y, z, V=m/rho}   P1 = {vx, vy, vz, rho}   P2 = {vPert.xyz, p/rho^2}
+//   P3 = {gradRho.xyz, lam}   P4 = {norm.xyz, surf}     (norm = Detect_Surface normals, surf as 0.0/1.0)
+// V and p/rho^2 are the per-particle quotients the reference recomputes per PAIR (m_j/rho_j in every
+// loop, p_j/rho_j^2 in BasePos, Kernel.h:153-157); m_j is recovered as rho_j*V_j.  Quantities only ever
+// read for particle i itself are packed the same way (one coalesced 32-byte access per thread):
+//   ACC = {acc.xyz, Rrho}  AF = {Af.xyz, deltaD}  AV = {aVisc.xyz, curve}  CV = {cellV.xyz, cellP}
+//   NP = {normal.xyz, lam_nb}  BN = {bNorm.xyz, y}  TH = {p, m, woccl, cellRho}
+//   SC = {colourG, colour, kernsum, pDist}          L0..L8 = the 3x3 renormalisation matrix
+// Field list = SPHPart, reference src/Var.h:499-642.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fjsph_b200.h"
+
+#define FJ_IDX_MASK 0x0FFFFFFFu
+#define FJ_NB_FLUID 0x80000000u /* neighbour j has b > PISTON (VarDefs.h:92-102) */
+#define FJ_NB_BOUND 0x40000000u /* neighbour j has b == BOUND */
+
+// X(type, name): every per-particle array of one time level
+#define FJ_LEVEL_FIELDS(X)                                                                                     \
+    X(double4, P0) X(double4, P1) X(double4, P2) X(double4, P3) X(double4, P4)                                 \
+    X(double4, ACC) X(double4, AF) X(double4, AV) X(double4, CV) X(double4, NP) X(double4, BN)                 \
+    X(double4, TH) X(double4, SC)                                                                              \
+    X(double, L0) X(double, L1) X(double, L2) X(double, L3) X(double, L4) X(double, L5) X(double, L6)          \
+    X(double, L7) X(double, L8)                                                                                \
+    X(long long, part_id) X(int, cellID) X(int, b) X(int, surfzone) X(int, internal)
+
+struct Level
+{
+#define X(T, n) T* n = nullptr;
+    FJ_LEVEL_FIELDS(X)
+#undef X
+};
+
+// constants the kernels read (subset of FjsphParams, pre-combined where the reference recomputes them)
+struct DevConst
+{
+    double H, H_sq, iH, sr, W_correc, W_dx, iW_dx, gk_fac /* 5*Wc/H^2 */;
+    double rho_rest, rho_min, rho_max, B, gam, c2, press_back, Bgam;
+    double visc_alpha, nu, dsph_cont, sig, dx, particle_step;
+    double gx, gy, gz;
+    double vinf_x, vinf_y, vinf_z;
+    double lam_cutoff, interp_fac, i_n_full, aero_L, A_sphere, A_plate, mu_g, sos2, gamma_g, ycoef, tab_Cb;
+    double max_shift_vel, bnd_mass, sim_mass, c_sound;
+    int ale, pressure_rel, acase, asource, use_lam, use_TAB_def;
+};
+
+struct Grid
+{
+    double ox, oy, oz, inv_cell;
+    int nx, ny, nz;           // cells per axis
+    int bx, by, bz;           // Morton bits per axis
+    unsigned int n_keys;      // 2^(bx+by+bz)
+};
+
+struct HostBlock
+{
+    int64_t first, second;
+    int is_fluid, bound_solver, no_slip, block_type, fixed_vel_or_dynamic;
+    std::vector<double> times;
+    std::vector<double> vels; // [max(1,nt)][3]
+    double insert_norm[3], insconst, delete_norm[3], delconst, aero_norm[3], aeroconst;
+    std::vector<int64_t> back;
+    std::vector<std::vector<int64_t>> buffer;
+};
+
+struct Timer
+{
+    std::string name;
+    double ms = 0.0;
+    long long launches = 0;
+};
+
+struct FjsphEngine
+{
+    FjsphParams P;
+    DevConst C;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t cap = 0;          // particle capacity
+    int64_t n = 0;            // particles held (owned + ghosts)
+    int64_t n_owned = 0;
+    int64_t bound_points = 0;
+    int64_t next_part_id = 0;
+    int n_sm = 148;
+
+    Level lv[3];              // 0 = pn, 1 = pnp1, 2 = scratch for permutes
+    int* oidx = nullptr;      // slot -> caller index
+    int* oidx_tmp = nullptr;
+    int* slot_of = nullptr;   // caller index -> slot (rebuilt after each sort)
+    int* blk = nullptr;       // slot -> block id
+    int* blk_tmp = nullptr;
+
+    // neighbour structures
+    Grid grid;
+    unsigned int* key = nullptr;        // [cap]
+    unsigned int* rank_in_cell = nullptr;
+    int* perm = nullptr;                // [cap] new slot -> old slot
+    int* perm2 = nullptr;
+    unsigned int* cell_count = nullptr; // [key_cap]
+    unsigned int* cell_start = nullptr; // [key_cap+1]
+    unsigned int* scan_tmp = nullptr;
+    size_t key_cap = 0;
+    unsigned int *mtab_x = nullptr, *mtab_y = nullptr, *mtab_z = nullptr; // Morton spread tables
+    int mtab_cap = 0;
+    unsigned int* nlist = nullptr;      // warp-transposed ELL: [(warp*nb_cap + s)*32 + lane]
+    int* ncount = nullptr;              // [cap] neighbours excluding self
+    int* near_inlet = nullptr;          // [cap] Boundary_Ghost flag, valid within one sub-iteration
+    int nb_cap = 0;
+    size_t nlist_words = 0;
+    bool list_valid = false;
+
+    // reductions / scalars
+    double* red = nullptr;              // device scratch for block partials
+    double* red_out = nullptr;          // device [16]
+    double* h_red = nullptr;            // pinned [16]
+    int* d_flag = nullptr;              // device error / overflow flags [4]
+    int* h_flag = nullptr;              // pinned
+
+    // RK4 accumulators (Runge_Kutta.cpp:363-389): sum of (v+vPert), acc, Rrho over stages
+    double4* rk_sum_v = nullptr;        // {sum (v+vPert).xyz, sum Rrho}
+    double4* rk_sum_a = nullptr;        // {sum acc.xyz, unused}
+
+    // staging for upload / download
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+
+    std::vector<HostBlock> blocks;
+    int n_bound_blocks = 0;
+
+    // Integrator members, Integration.h:53-68
+    double safe_dt = 0.0, maxf = 0.0, maxAf = 0.0, maxRho_pc = 0.0, maxRhoi = 0.0, maxdrho = 0.0, minST = 0.0,
+           maxU = 0.0, maxShift = 0.0;
+    unsigned iteration = 0;
+    double npd = 1.0;
+
+    // instrumentation
+    bool timers_on = false;
+    std::vector<Timer> timers;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long launches = 0;
+    int force_evals = 0, nb_builds = 0;
+};
+
+void fj_set_error(const char* fmt, ...);
+int fj_cuda_fail(cudaError_t err, const char* what, const char* file, int line);
+#define FJ_CUDA(call)                                                   \
+    do                                                                  \
+    {                                                                   \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess)                                          \
+            return fj_cuda_fail(_e, #call, __FILE__, __LINE__);         \
+    } while (0)
+
+// RAII-free kernel timing scope: records CUDA events around a kernel family when timers are enabled.
+struct KScope
+{
+    FjsphEngine* e;
+    int id;
+    KScope(FjsphEngine* e_, const char* name, int launches = 1);
+    ~KScope();
+};
+
+static inline int fj_blocks(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// stage implementations (each returns FjsphStatus)
+int fj_build_neighbours(FjsphEngine* e);
+int fj_prestep(FjsphEngine* e, double* npd);
+int fj_aero_velocity(FjsphEngine* e);
+int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipation);
+int fj_shift(FjsphEngine* e);
+int fj_check_pipe_outlet(FjsphEngine* e);
+int fj_forces(FjsphEngine* e, int level_idx, double npd);
+int fj_walls(FjsphEngine* e, int level_idx, bool nb_comparator);
+int fj_nb_iter(FjsphEngine* e, double npd, double* errsum);
+int fj_find_timestep(FjsphEngine* e, double* dt);
+int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s);
+int fj_step(FjsphEngine* e, FjsphStepStats* s);
+int fj_copy_level(FjsphEngine* e, int dst, int src);
+int fj_permute_levels(FjsphEngine* e);
+int fj_reduce_sum(FjsphEngine* e, int nblocks, int ncomp, double* out_host);
+void fj_refresh_constants(FjsphEngine* e);

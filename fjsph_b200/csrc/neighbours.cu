@@ -1,0 +1,554 @@
+// neighbours.cu — uniform cell list replacing FJSPH's nanoflann KD-tree radius search.
+//
+// Replaces update_neighbours / find_neighbours / radius_search (reference src/Neighbours.cpp:7-47):
+//   list_i = { j : ((xi-xj)^2 + (yi-yj)^2) + (zi-zj)^2 < sr }, strict '<', evaluated WITHOUT fma
+// contraction in the order nanoflann's metric_L2_Simple accumulates it, so the sets are bit-exact with
+// the CPU oracle.  Self is not stored (callers add the self terms explicitly; outlist[i].size() is
+// count+1).
+//
+// Pipeline per build (all on e->stream):
+//   bounds -> Morton key + warp-aggregated histogram -> block prefix scan -> scatter
+//   -> per-cell ordering by caller index (determinism) -> permute both time levels into cell order
+//   -> neighbour list in a warp-transposed ELL layout (entry (warp w, slot s, lane l) at
+//      ((w*nb_cap)+s)*32+l, so a warp reads slot s of its 32 particles with one 128-byte load).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "engine.cuh"
+
+namespace
+{
+
+constexpr int TPB = 256;
+
+// ---------------------------------------------------------------- bounds
+__global__ void k_bounds(const double4* __restrict__ P0, int n, double* __restrict__ partial)
+{
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        double4 a = P0[i];
+        lo[0] = fmin(lo[0], a.x);
+        hi[0] = fmax(hi[0], a.x);
+        lo[1] = fmin(lo[1], a.y);
+        hi[1] = fmax(hi[1], a.y);
+        lo[2] = fmin(lo[2], a.z);
+        hi[2] = fmax(hi[2], a.z);
+    }
+    __shared__ double sm[6][TPB / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+    {
+        double l = lo[c], h = hi[c];
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            l = fmin(l, __shfl_xor_sync(0xffffffffu, l, o));
+            h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
+        }
+        if (lane == 0)
+        {
+            sm[c][w] = l;
+            sm[3 + c][w] = h;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6)
+    {
+        double v = sm[threadIdx.x][0];
+        for (int k = 1; k < TPB / 32; ++k)
+            v = (threadIdx.x < 3) ? fmin(v, sm[threadIdx.x][k]) : fmax(v, sm[threadIdx.x][k]);
+        partial[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+__global__ void k_bounds_final(const double* __restrict__ partial, int nblocks, double* __restrict__ out)
+{
+    const int c = threadIdx.x;
+    if (c < 6)
+    {
+        double v = partial[c];
+        for (int b = 1; b < nblocks; ++b) v = (c < 3) ? fmin(v, partial[b * 6 + c]) : fmax(v, partial[b * 6 + c]);
+        out[c] = v;
+    }
+}
+
+// ---------------------------------------------------------------- keys + histogram
+__device__ __forceinline__ void cell_of(const Grid& g, double x, double y, double z, int& cx, int& cy, int& cz)
+{
+    cx = min(max(int(floor((x - g.ox) * g.inv_cell)), 0), g.nx - 1);
+    cy = min(max(int(floor((y - g.oy) * g.inv_cell)), 0), g.ny - 1);
+    cz = min(max(int(floor((z - g.oz) * g.inv_cell)), 0), g.nz - 1);
+}
+
+__global__ void k_key_hist(const double4* __restrict__ P0, int n, Grid g, const unsigned* __restrict__ mx,
+                           const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
+                           unsigned* __restrict__ key, unsigned* __restrict__ rank, unsigned* __restrict__ count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    unsigned k = 0xFFFFFFFFu;
+    if (i < n)
+    {
+        double4 a = P0[i];
+        int cx, cy, cz;
+        cell_of(g, a.x, a.y, a.z, cx, cy, cz);
+        k = mx[cx] | my[cy] | mz[cz];
+        key[i] = k;
+    }
+    // warp-aggregated atomics: one atomicAdd per distinct key in the warp
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (i < n && int(lane) == leader)
+        base = atomicAdd(&count[k], unsigned(__popc(peers)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n)
+        rank[i] = base + __popc(peers & ((1u << lane) - 1u));
+}
+
+// ---------------------------------------------------------------- block prefix scan (exclusive)
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
+
+__global__ void k_scan_tiles(const unsigned* __restrict__ in, unsigned* __restrict__ out, unsigned n,
+                             unsigned* __restrict__ tile_sum)
+{
+    __shared__ unsigned warp_tot[TPB / 32];
+    const unsigned base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    unsigned v[SCAN_ITEMS];
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+    {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        s += v[k];
+    }
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned inc = s;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= unsigned(o))
+            inc += t;
+    }
+    if (lane == 31)
+        warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0)
+    {
+        unsigned t = (lane < TPB / 32) ? warp_tot[lane] : 0u;
+        unsigned ti = t;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            unsigned u = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= unsigned(o))
+                ti += u;
+        }
+        if (lane < TPB / 32)
+            warp_tot[lane] = ti - t; // exclusive warp offsets
+        if (lane == TPB / 32 - 1)
+            tile_sum[blockIdx.x] = ti;
+    }
+    __syncthreads();
+    unsigned run = warp_tot[w] + inc - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+    {
+        if (base + k < n)
+            out[base + k] = run;
+        run += v[k];
+    }
+}
+
+// single block: exclusive scan of tile sums in place, total written to tile_sum[ntiles]
+__global__ void k_scan_tile_sums(unsigned* __restrict__ tile_sum, unsigned ntiles)
+{
+    __shared__ unsigned warp_tot[32];
+    __shared__ unsigned carry_s;
+    if (threadIdx.x == 0)
+        carry_s = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (unsigned start = 0; start < ntiles; start += blockDim.x)
+    {
+        const unsigned idx = start + threadIdx.x;
+        const unsigned v = (idx < ntiles) ? tile_sum[idx] : 0u;
+        unsigned inc = v;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= unsigned(o))
+                inc += t;
+        }
+        if (lane == 31)
+            warp_tot[w] = inc;
+        __syncthreads();
+        if (w == 0)
+        {
+            unsigned t = (lane < (blockDim.x >> 5)) ? warp_tot[lane] : 0u;
+            unsigned ti = t;
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                unsigned u = __shfl_up_sync(0xffffffffu, ti, o);
+                if (lane >= unsigned(o))
+                    ti += u;
+            }
+            warp_tot[lane] = ti - t;
+        }
+        __syncthreads();
+        const unsigned carry = carry_s;
+        if (idx < ntiles)
+            tile_sum[idx] = carry + warp_tot[w] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1)
+            carry_s = carry + warp_tot[w] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        tile_sum[ntiles] = carry_s;
+}
+
+__global__ void k_scan_add(unsigned* __restrict__ out, unsigned n, const unsigned* __restrict__ tile_sum,
+                           unsigned ntiles)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] += tile_sum[i / SCAN_TILE];
+    if (i == 0)
+        out[n] = tile_sum[ntiles];
+}
+
+// ---------------------------------------------------------------- scatter + deterministic cell order
+__global__ void k_scatter(const unsigned* __restrict__ key, const unsigned* __restrict__ rank,
+                          const unsigned* __restrict__ cell_start, int n, int* __restrict__ perm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        perm[cell_start[key[i]] + rank[i]] = i;
+}
+
+// One warp per occupied cell segment: order its members by caller index (rank sort).  The atomics above
+// leave an arbitrary order inside a cell; this makes the layout — and with it every FP64 summation
+// order downstream — reproducible run to run.
+__global__ void k_cell_order(const unsigned* __restrict__ cell_start, unsigned n_keys, const int* __restrict__ perm,
+                             const int* __restrict__ oidx, int* __restrict__ perm2)
+{
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    if (warp >= n_keys)
+        return;
+    const unsigned s = cell_start[warp], e = cell_start[warp + 1];
+    const unsigned c = e - s;
+    if (c == 0)
+        return;
+    for (unsigned t = lane; t < c; t += 32)
+    {
+        const int mine = perm[s + t];
+        const int mo = oidx[mine];
+        unsigned r = 0;
+        for (unsigned u = 0; u < c; ++u) r += (oidx[perm[s + u]] < mo) ? 1u : 0u;
+        perm2[s + r] = mine;
+    }
+}
+
+// ---------------------------------------------------------------- permute one level
+__global__ void k_permute_level(Level in, Level out, const int* __restrict__ perm, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const int s = perm[i];
+#define X(T, f) out.f[i] = in.f[s];
+    FJ_LEVEL_FIELDS(X)
+#undef X
+}
+
+__global__ void k_permute_index(const int* __restrict__ oidx_in, const int* __restrict__ blk_in,
+                                const int* __restrict__ perm, int n, int* __restrict__ oidx_out,
+                                int* __restrict__ blk_out, int* __restrict__ slot_of)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const int s = perm[i];
+    const int o = oidx_in[s];
+    oidx_out[i] = o;
+    blk_out[i] = blk_in[s];
+    slot_of[o] = i;
+}
+
+// ---------------------------------------------------------------- neighbour list
+__global__ void __launch_bounds__(TPB)
+    k_build_list(const double4* __restrict__ P0, const int* __restrict__ b, int n, Grid g,
+                 const unsigned* __restrict__ mx, const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
+                 const unsigned* __restrict__ cell_start, double sr, int nb_cap, unsigned* __restrict__ nlist,
+                 int* __restrict__ ncount, int* __restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double4 a = P0[i];
+    int cx, cy, cz;
+    cell_of(g, a.x, a.y, a.z, cx, cy, cz);
+    unsigned* __restrict__ dst = nlist + (size_t(i >> 5) * size_t(nb_cap)) * 32u + (i & 31);
+    int cnt = 0;
+    for (int dz = -1; dz <= 1; ++dz)
+    {
+        const int z = cz + dz;
+        if (z < 0 || z >= g.nz)
+            continue;
+        const unsigned kz = mz[z];
+        for (int dy = -1; dy <= 1; ++dy)
+        {
+            const int y = cy + dy;
+            if (y < 0 || y >= g.ny)
+                continue;
+            const unsigned kyz = kz | my[y];
+            for (int dx = -1; dx <= 1; ++dx)
+            {
+                const int x = cx + dx;
+                if (x < 0 || x >= g.nx)
+                    continue;
+                const unsigned k = kyz | mx[x];
+                const unsigned s = cell_start[k], e = cell_start[k + 1];
+                for (unsigned j = s; j < e; ++j)
+                {
+                    const double4 q = P0[j];
+                    // nanoflann metric_L2_Simple order, no fma contraction (bit-exact sets)
+                    const double ddx = __dsub_rn(a.x, q.x), ddy = __dsub_rn(a.y, q.y), ddz = __dsub_rn(a.z, q.z);
+                    const double d2 =
+                        __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+                    if (d2 < sr && int(j) != i)
+                    {
+                        if (cnt < nb_cap)
+                        {
+                            const int bj = b[j];
+                            unsigned ent = j;
+                            if (bj > FJSPH_PISTON)
+                                ent |= FJ_NB_FLUID;
+                            if (bj == FJSPH_BOUND)
+                                ent |= FJ_NB_BOUND;
+                            dst[size_t(cnt) * 32u] = ent;
+                        }
+                        cnt++;
+                    }
+                }
+            }
+        }
+    }
+    ncount[i] = cnt;
+    if (cnt > nb_cap)
+        atomicMax(flag, cnt);
+}
+
+int bits_for(int n)
+{
+    int b = 0;
+    while ((1 << b) < n) b++;
+    return b;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ host orchestration
+int fj_permute_levels(FjsphEngine* e)
+{
+    const int n = int(e->n);
+    const int nb = fj_blocks(n, TPB);
+    {
+        KScope ks(e, "permute", 3);
+        k_permute_level<<<nb, TPB, 0, e->stream>>>(e->lv[0], e->lv[2], e->perm, n);
+        std::swap(e->lv[0], e->lv[2]);
+        k_permute_level<<<nb, TPB, 0, e->stream>>>(e->lv[1], e->lv[2], e->perm, n);
+        std::swap(e->lv[1], e->lv[2]);
+        k_permute_index<<<nb, TPB, 0, e->stream>>>(e->oidx, e->blk, e->perm, n, e->oidx_tmp, e->blk_tmp, e->slot_of);
+        std::swap(e->oidx, e->oidx_tmp);
+        std::swap(e->blk, e->blk_tmp);
+    }
+    FJ_CUDA(cudaGetLastError());
+    return FJSPH_OK;
+}
+
+static int ensure_key_capacity(FjsphEngine* e, size_t n_keys)
+{
+    if (n_keys <= e->key_cap)
+        return FJSPH_OK;
+    if (n_keys > (size_t(1) << 29))
+    {
+        fj_set_error("cell table needs %zu keys (> 2^29): domain too sparse for the dense Morton table", n_keys);
+        return FJSPH_ERR_CAPACITY;
+    }
+    if (e->cell_count)
+        cudaFree(e->cell_count);
+    if (e->cell_start)
+        cudaFree(e->cell_start);
+    if (e->scan_tmp)
+        cudaFree(e->scan_tmp);
+    e->cell_count = e->cell_start = e->scan_tmp = nullptr;
+    size_t cap = 1;
+    while (cap < n_keys) cap <<= 1;
+    FJ_CUDA(cudaMalloc(&e->cell_count, cap * sizeof(unsigned)));
+    FJ_CUDA(cudaMalloc(&e->cell_start, (cap + 1) * sizeof(unsigned)));
+    FJ_CUDA(cudaMalloc(&e->scan_tmp, (cap / SCAN_TILE + 2) * sizeof(unsigned)));
+    e->key_cap = cap;
+    return FJSPH_OK;
+}
+
+static int ensure_list_capacity(FjsphEngine* e, int nb_cap)
+{
+    const size_t words = size_t((e->cap + 31) / 32) * size_t(nb_cap) * 32u;
+    if (nb_cap <= e->nb_cap && words <= e->nlist_words)
+        return FJSPH_OK;
+    if (e->nlist)
+        cudaFree(e->nlist);
+    e->nlist = nullptr;
+    FJ_CUDA(cudaMalloc(&e->nlist, words * sizeof(unsigned)));
+    e->nlist_words = words;
+    e->nb_cap = nb_cap;
+    return FJSPH_OK;
+}
+
+int fj_build_neighbours(FjsphEngine* e)
+{
+    const int n = int(e->n);
+    if (n <= 0)
+    {
+        fj_set_error("build_neighbours: no particles uploaded");
+        return FJSPH_ERR_STATE;
+    }
+    e->list_valid = false;
+    Level& S = e->lv[1];
+    const int nb = fj_blocks(n, TPB);
+
+    // 1. bounds (one 48-byte readback: the grid shape decides table sizes on the host)
+    {
+        KScope ks(e, "nb_bounds", 2);
+        const int rb = std::min(nb, 1024);
+        k_bounds<<<rb, TPB, 0, e->stream>>>(S.P0, n, e->red);
+        k_bounds_final<<<1, 32, 0, e->stream>>>(e->red, rb, e->red_out);
+    }
+    FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 6 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    double lo[3] = {e->h_red[0], e->h_red[1], e->h_red[2]}, hi[3] = {e->h_red[3], e->h_red[4], e->h_red[5]};
+    for (int d = 0; d < 3; ++d)
+        if (!(std::isfinite(lo[d]) && std::isfinite(hi[d])))
+        {
+            fj_set_error("build_neighbours: non-finite particle positions");
+            return FJSPH_ERR_STATE;
+        }
+
+    // 2. grid: cell edge a hair above the support radius 2H so +-1 cell always covers d < 2H
+    Grid g;
+    const double cell = std::sqrt(e->P.sr) * (1.0 + 1e-7);
+    g.inv_cell = 1.0 / cell;
+    g.ox = lo[0];
+    g.oy = lo[1];
+    g.oz = lo[2];
+    g.nx = int(std::floor((hi[0] - lo[0]) * g.inv_cell)) + 1;
+    g.ny = int(std::floor((hi[1] - lo[1]) * g.inv_cell)) + 1;
+    g.nz = int(std::floor((hi[2] - lo[2]) * g.inv_cell)) + 1;
+    g.bx = bits_for(g.nx);
+    g.by = bits_for(g.ny);
+    g.bz = bits_for(g.nz);
+    if (g.bx + g.by + g.bz > 29)
+    {
+        fj_set_error("cell grid %d x %d x %d needs more than 2^29 Morton keys", g.nx, g.ny, g.nz);
+        return FJSPH_ERR_CAPACITY;
+    }
+    g.n_keys = 1u << (g.bx + g.by + g.bz);
+    int st = ensure_key_capacity(e, g.n_keys);
+    if (st)
+        return st;
+    // Morton spread tables: bit l of each axis is placed round-robin x,y,z among the axes that still have bits
+    {
+        const int need = std::max(g.nx, std::max(g.ny, g.nz));
+        if (need > e->mtab_cap)
+        {
+            if (e->mtab_x)
+                cudaFree(e->mtab_x);
+            int cap = 64;
+            while (cap < need) cap <<= 1;
+            FJ_CUDA(cudaMalloc(&e->mtab_x, size_t(3) * cap * sizeof(unsigned)));
+            e->mtab_y = e->mtab_x + cap;
+            e->mtab_z = e->mtab_y + cap;
+            e->mtab_cap = cap;
+        }
+        int pos[3][32];
+        int out = 0;
+        const int bits[3] = {g.bx, g.by, g.bz};
+        for (int l = 0; l < 32; ++l)
+            for (int a = 0; a < 3; ++a)
+                if (l < bits[a])
+                    pos[a][l] = out++;
+        std::vector<unsigned> tab(size_t(3) * e->mtab_cap, 0u);
+        const int dims[3] = {g.nx, g.ny, g.nz};
+        for (int a = 0; a < 3; ++a)
+            for (int c = 0; c < dims[a]; ++c)
+            {
+                unsigned v = 0;
+                for (int l = 0; l < bits[a]; ++l)
+                    if (c & (1 << l))
+                        v |= 1u << pos[a][l];
+                tab[size_t(a) * e->mtab_cap + c] = v;
+            }
+        FJ_CUDA(cudaMemcpyAsync(e->mtab_x, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice,
+                                e->stream));
+        FJ_CUDA(cudaStreamSynchronize(e->stream)); // tab is a stack-lifetime buffer
+    }
+    e->grid = g;
+
+    // 3. counting sort by Morton key
+    {
+        KScope ks(e, "nb_sort", 7);
+        FJ_CUDA(cudaMemsetAsync(e->cell_count, 0, size_t(g.n_keys) * sizeof(unsigned), e->stream));
+        k_key_hist<<<nb, TPB, 0, e->stream>>>(S.P0, n, g, e->mtab_x, e->mtab_y, e->mtab_z, e->key, e->rank_in_cell,
+                                              e->cell_count);
+        const unsigned ntiles = (g.n_keys + SCAN_TILE - 1) / SCAN_TILE;
+        k_scan_tiles<<<ntiles, TPB, 0, e->stream>>>(e->cell_count, e->cell_start, g.n_keys, e->scan_tmp);
+        k_scan_tile_sums<<<1, 1024, 0, e->stream>>>(e->scan_tmp, ntiles);
+        k_scan_add<<<fj_blocks(g.n_keys, TPB), TPB, 0, e->stream>>>(e->cell_start, g.n_keys, e->scan_tmp, ntiles);
+        k_scatter<<<nb, TPB, 0, e->stream>>>(e->key, e->rank_in_cell, e->cell_start, n, e->perm2);
+        k_cell_order<<<fj_blocks(int64_t(g.n_keys) * 32, TPB), TPB, 0, e->stream>>>(e->cell_start, g.n_keys, e->perm2,
+                                                                                   e->oidx, e->perm);
+    }
+    FJ_CUDA(cudaGetLastError());
+
+    // 4. move both time levels into cell order
+    st = fj_permute_levels(e);
+    if (st)
+        return st;
+
+    // 5. neighbour list (retry with a larger per-particle capacity on overflow)
+    if (e->nb_cap == 0)
+    {
+        st = ensure_list_capacity(e, 288);
+        if (st)
+            return st;
+    }
+    for (int attempt = 0; attempt < 4; ++attempt)
+    {
+        FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
+        {
+            KScope ks(e, "nb_list", 1);
+            k_build_list<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, g, e->mtab_x, e->mtab_y, e->mtab_z,
+                                                    e->cell_start, e->P.sr, e->nb_cap, e->nlist, e->ncount, e->d_flag);
+        }
+        FJ_CUDA(cudaGetLastError());
+        FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        FJ_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->h_flag[0] == 0)
+        {
+            e->list_valid = true;
+            e->nb_builds++;
+            return FJSPH_OK;
+        }
+        const int want = ((e->h_flag[0] + 31) / 32) * 32 + 32;
+        st = ensure_list_capacity(e, want);
+        if (st)
+            return st;
+    }
+    fj_set_error("neighbour list capacity could not be satisfied");
+    return FJSPH_ERR_CAPACITY;
+}

@@ -1,0 +1,1046 @@
+// sweeps.cu — the FP64 pair sweeps of the WCSPH step (one thread per particle, neighbour slots read
+// with one coalesced 128-byte load per warp, neighbour records gathered as 32-byte sectors through L1).
+//
+// Replaces, with results within 1e-10 (normwise) of the CPU oracle:
+//   dSPH_PreStep        reference src/Shifting.cpp:12-123
+//   get_aero_velocity   reference src/Resid.cpp:569-611 (constVel)
+//   Detect_Surface      reference src/Geometry.cpp:14-280   (loops 1 / 2 / 3)
+//   dissipation_terms   reference src/Shifting.cpp:126-186  (fused with Detect_Surface loop 1)
+//   particle_shift      reference src/Shifting.cpp:189-290
+//   get_acc_and_Rrho    reference src/Resid.cpp:243-469, Kernel.h, Aero.h:10-98
+//   Get_Boundary_Pressure / Boundary_Ghost / Set_No_Slip / Boundary_DBC   reference src/Resid.cpp:21-186
+//
+// Sweep fusion: prestep | surface loop 1 + dissipation | surface loops 2+3 | shifting | force.
+#include <cmath>
+
+#include "engine.cuh"
+#include "small_matrix.cuh"
+
+namespace
+{
+
+constexpr int TPB = 128;
+#define FJ_PI 3.14159265358979323846
+
+struct ListView
+{
+    const unsigned* __restrict__ nlist;
+    const int* __restrict__ ncount;
+    int nb_cap;
+};
+
+#define FJ_FOR_NEIGHBOURS(i, LV, ent, j)                                                                   \
+    const unsigned* __restrict__ _lp = (LV).nlist + (size_t((i) >> 5) * size_t((LV).nb_cap)) * 32u + ((i)&31); \
+    const int _cnt = (LV).ncount[i];                                                                       \
+    for (int _s = 0; _s < _cnt; ++_s)                                                                      \
+        for (unsigned ent = _lp[size_t(_s) * 32u], j = ent & FJ_IDX_MASK, _once = 1; _once; _once = 0)
+
+// Wendland C2 (Kernel.h:37-61).  t = 1 - q/2.  W = t^4 (2q+1) Wc ; GradK(R, r) = R * gk with
+// gk = 5 Wc/H^2 * t^3, and 0 when r/H < 1e-12.
+__device__ __forceinline__ double wend_t(const DevConst& C, double r) { return 1.0 - 0.5 * r * C.iH; }
+__device__ __forceinline__ double wend_W(const DevConst& C, double r, double t)
+{
+    const double t2 = t * t;
+    return (t2 * t2) * (2.0 * r * C.iH + 1.0) * C.W_correc;
+}
+__device__ __forceinline__ double wend_gk(const DevConst& C, double r, double t)
+{
+    return (r * C.iH < 1e-12) ? 0.0 : C.gk_fac * (t * t * t);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sm)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+        sm[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < (int(blockDim.x) >> 5); ++k) r += sm[k];
+    __syncthreads();
+    return r;
+}
+
+// ================================================================= dSPH_PreStep
+__global__ void __launch_bounds__(TPB)
+    k_prestep(Level S, ListView lv, DevConst C, int n, double* __restrict__ npd_partial)
+{
+    __shared__ double sm[TPB / 32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double npd_ = 0.0;
+    if (i < n)
+    {
+        const double4 pi = S.P0[i];
+        const double rho_i = S.P1[i].w;
+        double l00 = 0, l01 = 0, l02 = 0, l11 = 0, l12 = 0, l22 = 0;
+        double n00 = 0, n01 = 0, n02 = 0, n11 = 0, n12 = 0, n22 = 0;
+        double g0 = 0, g1 = 0, g2 = 0, m0 = 0, m1 = 0, m2 = 0;
+        double kernsum = C.W_correc; /* self term, Shifting.cpp:39-45 */
+        double colour = 0.0;
+        FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+        {
+            const double4 pj = S.P0[j];
+            const double rho_j = S.P1[j].w;
+            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+            const double rr = rx * rx + ry * ry + rz * rz;
+            const double r = sqrt(rr);
+            const double t = wend_t(C, r);
+            const double vg = pj.w * wend_gk(C, r, t); /* V_j * gk ; Grad = GradK(-Rji) = -Rji*gk */
+            const double ax = vg * rx, ay = vg * ry, az = vg * rz;
+            /* Lmat -= V Rji (x) Grad  ==  += V gk Rji (x) Rji */
+            l00 += ax * rx;
+            l01 += ax * ry;
+            l02 += ax * rz;
+            l11 += ay * ry;
+            l12 += ay * rz;
+            l22 += az * rz;
+            const double dr = rho_j - rho_i;
+            g0 -= dr * ax;
+            g1 -= dr * ay;
+            g2 -= dr * az;
+            if (ent & FJ_NB_FLUID)
+            {
+                n00 += ax * rx;
+                n01 += ax * ry;
+                n02 += ax * rz;
+                n11 += ay * ry;
+                n12 += ay * rz;
+                n22 += az * rz;
+                m0 -= ax;
+                m1 -= ay;
+                m2 -= az;
+                const double W = wend_W(C, r, t);
+                kernsum += W;
+                colour += pj.w * W;
+                npd_ += W;
+            }
+        }
+        double Lm[3][3] = {{l00, l01, l02}, {l01, l11, l12}, {l02, l12, l22}};
+        double Li[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        double tmp[3][3];
+        if (fj_qr_inverse3(Lm, tmp))
+        {
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Li[a][c] = tmp[a][c];
+        }
+        const double gr0 = Li[0][0] * g0 + Li[0][1] * g1 + Li[0][2] * g2;
+        const double gr1 = Li[1][0] * g0 + Li[1][1] * g1 + Li[1][2] * g2;
+        const double gr2 = Li[2][0] * g0 + Li[2][1] * g1 + Li[2][2] * g2;
+        double lam = 1.0, lam_nb = 1.0;
+        if (S.b[i] != FJSPH_BOUND)
+        {
+            lam = fj_min_eig3(l00, l01, l11, l02, l12, l22);
+            lam_nb = fj_min_eig3(n00, n01, n11, n02, n12, n22);
+        }
+        S.L0[i] = Li[0][0];
+        S.L1[i] = Li[0][1];
+        S.L2[i] = Li[0][2];
+        S.L3[i] = Li[1][0];
+        S.L4[i] = Li[1][1];
+        S.L5[i] = Li[1][2];
+        S.L6[i] = Li[2][0];
+        S.L7[i] = Li[2][1];
+        S.L8[i] = Li[2][2];
+        S.P3[i] = make_double4(gr0, gr1, gr2, lam);
+        S.NP[i] = make_double4(Li[0][0] * m0 + Li[0][1] * m1 + Li[0][2] * m2,
+                               Li[1][0] * m0 + Li[1][1] * m1 + Li[1][2] * m2,
+                               Li[2][0] * m0 + Li[2][1] * m1 + Li[2][2] * m2, lam_nb);
+        const double colourG = (lam > 0.7) ? 2.0 : 2.0 * fmax(1.0, 1.0 / (2.0 * colour));
+        double4 sc = S.SC[i];
+        sc.x = colourG;
+        sc.y = colour;
+        sc.z = kernsum;
+        S.SC[i] = sc;
+    }
+    const double tot = block_sum(npd_, sm);
+    if (threadIdx.x == 0)
+        npd_partial[blockIdx.x] = tot;
+}
+
+// ================================================================= get_aero_velocity (constVel)
+__global__ void k_aero_velocity(Level S, const int* __restrict__ ncount, const int* __restrict__ blk,
+                                int n_bound_blocks, DevConst C, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] < n_bound_blocks)
+        return;
+    bool cond;
+    if (C.use_lam)
+        cond = S.NP[i].w < C.lam_cutoff;
+    else
+        cond = double(ncount[i] + 1) * C.i_n_full < C.lam_cutoff;
+    double4 cv = S.CV[i];
+    if (cond && S.b[i] == FJSPH_FREE)
+    {
+        cv.x = C.vinf_x;
+        cv.y = C.vinf_y;
+        cv.z = C.vinf_z;
+        S.cellID[i] = 1;
+    }
+    else
+    {
+        cv.x = cv.y = cv.z = 0.0;
+        S.cellID[i] = -3;
+    }
+    S.CV[i] = cv;
+}
+
+// ================================================================= Detect_Surface loop 1 + dissipation_terms
+template <bool SURF, bool DISS>
+__global__ void __launch_bounds__(TPB)
+    k_surf1_diss(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] < n_bound_blocks)
+        return;
+    const double4 pi = S.P0[i];
+    const double4 vi = S.P1[i];
+    const double4 gi = S.P3[i]; /* gradRho_i, lam_i */
+    const double4 npi = S.NP[i]; /* prestep normal, lam_nb */
+    const int b_i = S.b[i];
+    const double rho_i = vi.w, lam_i = gi.w, lam_nb = npi.w;
+    const double h = 1.33 * C.particle_step;
+    const double sqrt2h = sqrt(2.0) * h;
+
+    // --- surface flag set-up (Geometry.cpp:31-103)
+    int surf = 0;
+    bool need_test = false;
+    double nhx = 0, nhy = 0, nhz = 0, Tx = 0, Ty = 0, Tz = 0;
+    if (SURF)
+    {
+        if (b_i < FJSPH_PIPE)
+            surf = 0;
+        else if (lam_nb < 0.2)
+            surf = 1;
+        else if (lam_nb < 0.75)
+        {
+            surf = 1;
+            need_test = true;
+            const double nn = npi.x * npi.x + npi.y * npi.y + npi.z * npi.z;
+            const double inv = (nn > 0.0) ? 1.0 / sqrt(nn) : 1.0;
+            nhx = npi.x * inv;
+            nhy = npi.y * inv;
+            nhz = npi.z * inv;
+            Tx = pi.x + h * nhx;
+            Ty = pi.y + h * nhy;
+            Tz = pi.z + h * nhz;
+        }
+    }
+    const bool hi_lam = lam_i > 0.7;
+    const double cs_i = DISS ? sqrt(C.Bgam / rho_i) : 0.0;
+    double nx = 0, ny = 0, nz = 0;
+    double avx = 0, avy = 0, avz = 0, Rrhod = 0;
+    const double cos_pi4 = 0.70710678118654757;
+
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    {
+        const double4 pj = S.P0[j];
+        const double4 gj = S.P3[j];
+        const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+        const double rr = rx * rx + ry * ry + rz * rz;
+        const double r = sqrt(rr);
+        const double t = wend_t(C, r);
+        const double gk = wend_gk(C, r, t);
+        const double vg = pj.w * gk;
+        if (SURF)
+        {
+            /* normal from the eigenvalue gradient, GradK(Rij = xi - xj) = -Rji*gk (Geometry.cpp:109-137) */
+            const double w = hi_lam ? (gj.w - lam_i) : gj.w;
+            const double s = -vg * w;
+            nx += s * rx;
+            ny += s * ry;
+            nz += s * rz;
+            if (need_test)
+            {
+                if (r >= sqrt2h)
+                {
+                    const double ex = pj.x - Tx, ey = pj.y - Ty, ez = pj.z - Tz;
+                    if (sqrt(ex * ex + ey * ey + ez * ez) < h)
+                        surf = 0;
+                }
+                else
+                {
+                    /* acos(nhat . (Rji/r)) < pi/4 ; acos is NaN outside [-1,1] so those never trigger */
+                    const double c = (nhx * rx + nhy * ry + nhz * rz) / r;
+                    if (c > cos_pi4 && c <= 1.0)
+                        surf = 0;
+                }
+            }
+        }
+        if (DISS)
+        {
+            const double4 vj = S.P1[j];
+            const double rho_j = vj.w;
+            const double idist2 = 1.0 / (rr + 0.0001 * C.H_sq);
+            const double rdg = rr * gk; /* Rji . gradK */
+            if (ent & FJ_NB_FLUID)
+            {
+                const double vdotr = (vj.x - vi.x) * rx + (vj.y - vi.y) * ry + (vj.z - vi.z) * rz;
+                if (!(vdotr > 0.0))
+                {
+                    const double muij = C.H * vdotr * idist2;
+                    const double rhoij = 0.5 * (rho_i + rho_j);
+                    const double cbar = 0.5 * (cs_i + sqrt(C.Bgam / rho_j));
+                    const double m_j = rho_j * pj.w;
+                    const double f = m_j * gk * C.visc_alpha * cbar * muij / rhoij;
+                    avx += f * rx;
+                    avy += f * ry;
+                    avz += f * rz;
+                }
+                const double gdot = (gi.x + gj.x) * rx + (gi.y + gj.y) * ry + (gi.z + gj.z) * rz;
+                Rrhod += pj.w * ((rho_j - rho_i) + 0.5 * gdot) * rdg * idist2;
+            }
+            else
+            {
+                Rrhod += pj.w * (rho_j - rho_i) * rdg * idist2;
+            }
+        }
+    }
+    if (SURF)
+    {
+        const double tx = S.L0[i] * nx + S.L1[i] * ny + S.L2[i] * nz;
+        const double ty = S.L3[i] * nx + S.L4[i] * ny + S.L5[i] * nz;
+        const double tz = S.L6[i] * nx + S.L7[i] * ny + S.L8[i] * nz;
+        const double nn = sqrt(tx * tx + ty * ty + tz * tz);
+        double4 out = make_double4(0.0, 0.0, 0.0, double(surf));
+        if (nn > 0.1 * lam_i / C.H)
+        {
+            const double inv = 1.0 / nn;
+            out.x = tx * inv;
+            out.y = ty * inv;
+            out.z = tz * inv;
+        }
+        S.P4[i] = out;
+        if (b_i < FJSPH_PIPE)
+        {
+            double4 th = S.TH[i];
+            th.z = 1.0; /* woccl = 1, Geometry.cpp:33-37 */
+            S.TH[i] = th;
+        }
+    }
+    if (DISS)
+    {
+        double4 av = S.AV[i];
+        av.x = avx;
+        av.y = avy;
+        av.z = avz;
+        S.AV[i] = av;
+        double4 af = S.AF[i];
+        af.w = C.dsph_cont * Rrhod;
+        S.AF[i] = af;
+    }
+}
+
+// ================================================================= Detect_Surface loops 2 and 3
+__global__ void __launch_bounds__(TPB)
+    k_surf23(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] < n_bound_blocks)
+        return;
+    const double4 pi = S.P0[i];
+    const double4 ni = S.P4[i];
+    const int b_i = S.b[i];
+    const double lam_nb = S.NP[i].w;
+    const bool ni_nz = (ni.x * ni.x + ni.y * ni.y + ni.z * ni.z) > 0.0;
+    const bool occl = (b_i == FJSPH_FREE) && (C.acase == 1);
+    double vdx = 0, vdy = 0, vdz = 0;
+    if (S.cellID[i] != -1 && occl)
+    {
+        const double4 vi = S.P1[i];
+        if (C.asource == 1)
+        {
+            const double4 cv = S.CV[i];
+            vdx = cv.x - vi.x;
+            vdy = cv.y - vi.y;
+            vdz = cv.z - vi.z;
+        }
+        else
+        {
+            vdx = C.vinf_x - vi.x;
+            vdy = C.vinf_y - vi.y;
+            vdz = C.vinf_z - vi.z;
+        }
+    }
+    const double vdn = sqrt(vdx * vdx + vdy * vdy + vdz * vdz);
+    const double L0 = S.L0[i], L1 = S.L1[i], L2 = S.L2[i], L3 = S.L3[i], L4 = S.L4[i], L5 = S.L5[i], L6 = S.L6[i],
+                 L7 = S.L7[i], L8 = S.L8[i];
+    double curve = 0.0, woccl_ = 0.0;
+    int zone = (ni.w != 0.0) ? 1 : 0; /* the list of the reference includes self */
+    /* woccl is overwritten with 1 when lam_nb >= lam_cutoff, so the occlusion max is only needed below it */
+    const bool need_occl = occl && (lam_nb < C.lam_cutoff);
+
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    {
+        const double4 nj = S.P4[j];
+        if (nj.w != 0.0)
+            zone = 1;
+        const bool curv = ni_nz && ((nj.x * nj.x + nj.y * nj.y + nj.z * nj.z) > 0.0);
+        if (curv || need_occl)
+        {
+            const double4 pj = S.P0[j];
+            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+            const double rr = rx * rx + ry * ry + rz * rz;
+            const double r = sqrt(rr);
+            if (curv)
+            {
+                const double t = wend_t(C, r);
+                const double vg = pj.w * wend_gk(C, r, t);
+                const double dx_ = nj.x - ni.x, dy_ = nj.y - ni.y, dz_ = nj.z - ni.z;
+                const double lx = L0 * dx_ + L1 * dy_ + L2 * dz_;
+                const double ly = L3 * dx_ + L4 * dy_ + L5 * dz_;
+                const double lz = L6 * dx_ + L7 * dy_ + L8 * dz_;
+                curve += vg * (lx * rx + ly * ry + lz * rz);
+            }
+            if (need_occl)
+            {
+                /* frac = -Rji.Vdiff / (|Vdiff| r); 0/0 = NaN never passes the '>' (Geometry.cpp:237-246) */
+                const double frac = -(rx * vdx + ry * vdy + rz * vdz) / (vdn * r);
+                if (frac > woccl_)
+                    woccl_ = frac;
+            }
+        }
+    }
+    double4 th = S.TH[i];
+    th.z = (lam_nb < C.lam_cutoff) ? fmax(0.0, fmin(woccl_, 1.0)) : 1.0;
+    S.TH[i] = th;
+    double4 np = S.NP[i];
+    np.x = ni.x;
+    np.y = ni.y;
+    np.z = ni.z;
+    S.NP[i] = np; /* pi.norm = norms[ii] */
+    double4 av = S.AV[i];
+    av.w = curve;
+    S.AV[i] = av;
+    double4 sc = S.SC[i];
+    sc.w = S.P3[i].w; /* pDist = lam */
+    S.SC[i] = sc;
+    if (C.ale)
+        S.surfzone[i] = zone;
+}
+
+// ================================================================= particle_shift (ALE)
+__global__ void __launch_bounds__(TPB)
+    k_shift(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] < n_bound_blocks)
+        return;
+    const double4 np = S.NP[i];
+    const double lam_nb = np.w;
+    double4 out = S.P2[i];
+    if (lam_nb < 0.55 || S.b[i] == FJSPH_BUFFER)
+    {
+        out.x = out.y = out.z = 0.0;
+        S.P2[i] = out;
+        return;
+    }
+    const double4 pi = S.P0[i];
+    const double4 vi = S.P1[i];
+    const bool bulk = (S.surfzone[i] == 0) && (lam_nb > 0.55);
+    /* own unit normal; Eigen normalized() leaves the zero vector unchanged */
+    double nhx = np.x, nhy = np.y, nhz = np.z;
+    {
+        const double nn = nhx * nhx + nhy * nhy + nhz * nhz;
+        if (nn > 0.0)
+        {
+            const double inv = 1.0 / sqrt(nn);
+            nhx *= inv;
+            nhy *= inv;
+            nhz *= inv;
+        }
+    }
+    double dux = 0, duy = 0, duz = 0, maxU2 = 0.0;
+    /* max_j acos(c_j) over c_j in [-1,1] == acos(min_j c_j); NaNs (|c|>1) are skipped by the reference's '>' */
+    double min_c = 2.0;
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    {
+        const double4 pj = S.P0[j];
+        const double4 vj = S.P1[j];
+        const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+        const double rr = rx * rx + ry * ry + rz * rz;
+        const double r = sqrt(rr);
+        const double t = wend_t(C, r);
+        const double W = wend_W(C, r, t);
+        const double gk = wend_gk(C, r, t);
+        const double kq = W * C.iW_dx;
+        const double kq2 = kq * kq;
+        const double f = (1.0 + 0.2 * (kq2 * kq2)) * gk * pj.w;
+        dux += f * rx;
+        duy += f * ry;
+        duz += f * rz;
+        if (!bulk && (ent & FJ_NB_FLUID))
+        {
+            const double4 nj = S.P4[j];
+            const double nn = nj.x * nj.x + nj.y * nj.y + nj.z * nj.z;
+            const double inv = (nn > 0.0) ? 1.0 / sqrt(nn) : 1.0;
+            const double c = (nhx * nj.x + nhy * nj.y + nhz * nj.z) * inv;
+            if (c >= -1.0 && c <= 1.0)
+                min_c = fmin(min_c, c);
+        }
+        const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
+        maxU2 = fmax(maxU2, ux * ux + uy * uy + uz * uz);
+    }
+    const double vnorm = sqrt(vi.x * vi.x + vi.y * vi.y + vi.z * vi.z);
+    const double sc = -2.0 * C.H * vnorm;
+    dux *= sc;
+    duy *= sc;
+    duz *= sc;
+    const double dn = sqrt(dux * dux + duy * duy + duz * duz);
+    const double lim = fmin(dn, fmin(sqrt(maxU2) / 2.0, C.max_shift_vel));
+    if (dn > 0.0)
+    {
+        const double s2 = lim / dn;
+        dux *= s2;
+        duy *= s2;
+        duz *= s2;
+    }
+    else
+    {
+        dux *= lim;
+        duy *= lim;
+        duz *= lim;
+    }
+    if (bulk)
+    {
+        out.x = dux;
+        out.y = duy;
+        out.z = duz;
+    }
+    else
+    {
+        const double woccl = (min_c <= 1.0) ? acos(min_c) : 0.0;
+        if (woccl < FJ_PI / 12.0)
+        {
+            /* (I - n n^T) deltaU with n = -nhat */
+            const double nd = nhx * dux + nhy * duy + nhz * duz;
+            out.x = dux - nhx * nd;
+            out.y = duy - nhy * nd;
+            out.z = duz - nhz * nd;
+        }
+        else
+        {
+            out.x = out.y = out.z = 0.0;
+        }
+    }
+    S.P2[i] = out;
+}
+
+// ================================================================= get_acc_and_Rrho
+__device__ __forceinline__ double get_cd(double Re)
+{
+    return (1.0 + 0.197 * pow(Re, 0.63) + 2.6e-04 * pow(Re, 1.38)) * (24.0 / (Re + 0.00001));
+}
+
+template <bool ALE>
+__global__ void __launch_bounds__(TPB)
+    k_force(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, double npdm2, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] < n_bound_blocks)
+        return;
+    const double4 pi = S.P0[i];
+    const double4 vi = S.P1[i];
+    const double4 qi = S.P2[i]; /* vPert_i, p_i/rho_i^2 */
+    const double rho_i = vi.w, irho_i = 1.0 / rho_i;
+    const double4 th = S.TH[i]; /* p, m, woccl, cellRho */
+    const int b_i = S.b[i];
+    const bool do_st = ALE ? (S.surfzone[i] == 1) : true;
+    const double pi3o4 = 3.0 * FJ_PI / 4.0;
+    const double st_bound_fac = 1.0 + 0.5 * cos(0.5 * FJ_PI * 7.0 / 9.0);
+
+    double ax = 0, ay = 0, az = 0;       /* acc_ (aero + pressure + wall repulsion) */
+    double alx = 0, aly = 0, alz = 0;    /* acc_ale_ */
+    double vx = 0, vy = 0, vz = 0;       /* visc_ */
+    double sx = 0, sy = 0, sz = 0;       /* surf_t_ */
+    double Rrho_ = 0.0, Rrhoc_ = 0.0;
+    double4 af = S.AF[i];                /* Af, deltaD */
+
+    /* aero term, Resid.cpp:267-277 (Q1: evaluated whenever cellID != -1) */
+    if (S.cellID[i] != -1 && C.acase == 1)
+    {
+        const double4 cv = S.CV[i];
+        const double dx_ = cv.x - vi.x, dy_ = cv.y - vi.y, dz_ = cv.z - vi.z;
+        const double vd2 = dx_ * dx_ + dy_ * dy_ + dz_ * dz_;
+        const double vd = sqrt(vd2);
+        const double Re = 2.0 * th.w * vd * C.aero_L / C.mu_g;
+        const double lam_nb = S.NP[i].w;
+        double frac2;
+        if (C.use_lam)
+            frac2 = fmin(C.interp_fac * lam_nb, 1.0);
+        else
+            frac2 = fmin(C.interp_fac * double(lv.ncount[i] + 1) * C.i_n_full, 1.0);
+        const double frac1 = 1.0 - frac2;
+        const double Cds = get_cd(Re);
+        double Cdl, Adrop;
+        if (C.use_TAB_def)
+        {
+            double ymax = vd2 * C.ycoef;
+            if (ymax > 1.0)
+                ymax = 1.0;
+            Cdl = Cds * (1 + 2.632 * ymax);
+            const double rr_ = C.aero_L + C.tab_Cb * C.aero_L * ymax;
+            Adrop = FJ_PI * rr_ * rr_;
+        }
+        else
+        {
+            Cdl = Cds;
+            Adrop = C.A_sphere;
+        }
+        const double Cdi = frac1 * Cdl + frac2;
+        const double Ai = (1.0 - th.z) * (frac1 * Adrop + frac2 * C.A_plate);
+        const double f = 0.5 * vd / C.sos2 * C.gamma_g * cv.w * Cdi * Ai / th.y;
+        af.x = f * dx_;
+        af.y = f * dy_;
+        af.z = f * dz_;
+        ax += af.x;
+        ay += af.y;
+        az += af.z;
+    }
+    else if (S.cellID[i] != -1)
+    {
+        af.x = af.y = af.z = 0.0; /* CalcAeroAcc default branch returns zero */
+    }
+
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    {
+        const double4 pj = S.P0[j];
+        const double4 vj = S.P1[j];
+        const double4 qj = S.P2[j];
+        const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+        const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
+        const double rr = rx * rx + ry * ry + rz * rz;
+        const double r = sqrt(rr);
+        const double idist2 = 1.0 / (rr + 0.001 * C.H_sq);
+        const double t = wend_t(C, r);
+        const double gk = wend_gk(C, r, t);
+        const double V_j = pj.w, rho_j = vj.w;
+        const double m_j = rho_j * V_j;
+        const double gx = gk * rx, gy = gk * ry, gz = gk * rz; /* gradK */
+        /* BasePos, Kernel.h:153-157 */
+        const double pf = m_j * (qi.w + qj.w);
+        ax -= pf * gx;
+        ay -= pf * gy;
+        az -= pf * gz;
+        /* Viscosity, Kernel.h:262-269: m_j nu (rho_i+rho_j)/(rho_i rho_j) (Rji.gradK) idist2 Vji */
+        const double vf = C.nu * (V_j + m_j * irho_i) * (rr * gk) * idist2;
+        vx += vf * ux;
+        vy += vf * uy;
+        vz += vf * uz;
+        /* pairwise surface tension, Kernel.h:101-113 */
+        if (do_st)
+        {
+            const double fac = (b_i == FJSPH_BOUND || (ent & FJ_NB_BOUND)) ? st_bound_fac : 1.0;
+            const double sf = -npdm2 * fac * cos(pi3o4 * r * C.iH) / r;
+            sx += sf * rx;
+            sy += sf * ry;
+            sz += sf * rz;
+        }
+        if (ALE)
+        {
+            /* ALEMomentum, ALEContinuity, ALECont2ndterm, Kernel.h:179-196 */
+            const double pjg = qj.x * gx + qj.y * gy + qj.z * gz;
+            const double pig = qi.x * gx + qi.y * gy + qi.z * gz;
+            const double dpg = pjg - pig;
+            alx += ((vj.x * pjg + vi.x * pig) - vi.x * dpg) * V_j;
+            aly += ((vj.y * pjg + vi.y * pig) - vi.y * dpg) * V_j;
+            alz += ((vj.z * pjg + vi.z * pig) - vi.z * dpg) * V_j;
+            const double ug = ux * gx + uy * gy + uz * gz;
+            Rrho_ -= (ug + dpg) * V_j;
+            Rrhoc_ += (rho_j * pjg + rho_i * pig) * V_j;
+        }
+        else
+        {
+            Rrho_ -= V_j * (ux * gx + uy * gy + uz * gz);
+        }
+    }
+    if (S.internal[i] == 1)
+    {
+        /* NormalBoundaryRepulsion, Kernel.h:64-75,272-277 */
+        const double4 bn = S.BN[i];
+        const double beta = 4.0 * C.c_sound * C.c_sound;
+        const double q = bn.w * C.iH;
+        double kern = 0.0;
+        if (q < 2.0 / 3.0)
+            kern = beta * 2.0 / 3.0;
+        else if (q < 1.0)
+            kern = beta * (2 * q - 3.0 / 2.0 * q * q);
+        else if (q < 2.0)
+            kern = 0.5 * beta * ((2 - q) * (2 - q));
+        const double f = C.bnd_mass / (C.bnd_mass + C.sim_mass) * kern;
+        ax += f * bn.x;
+        ay += f * bn.y;
+        az += f * bn.z;
+    }
+    const double4 av = S.AV[i];
+    const double im = 1.0 / th.y;
+    double4 acc;
+    acc.x = ax + alx + av.x + vx + sx * im + C.gx;
+    acc.y = ay + aly + av.y + vy + sy * im + C.gy;
+    acc.z = az + alz + av.z + vz + sz * im + C.gz;
+    acc.w = Rrho_ * rho_i + Rrhoc_ + af.w;
+    S.ACC[i] = acc;
+    S.AF[i] = af;
+}
+
+// ================================================================= walls (Resid.cpp:21-186)
+__global__ void k_wall_velocity(Level S, const int* __restrict__ blk, int block, double vx, double vy, double vz, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] != block)
+        return;
+    double4 v = S.P1[i];
+    v.x = vx;
+    v.y = vy;
+    v.z = vz;
+    S.P1[i] = v;
+}
+
+// Set_No_Slip: v_i = 2 v_i - sum(v_j W)/sum(W) over fluid neighbours
+__global__ void k_wall_no_slip(Level S, ListView lv, const int* __restrict__ blk, int block, DevConst C, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] != block)
+        return;
+    const double4 pi = S.P0[i];
+    double sxx = 0, syy = 0, szz = 0, ks = 0;
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    {
+        if (!(ent & FJ_NB_FLUID))
+            continue;
+        const double4 pj = S.P0[j];
+        const double4 vj = S.P1[j];
+        const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+        const double r = sqrt(rx * rx + ry * ry + rz * rz);
+        const double W = wend_W(C, r, wend_t(C, r));
+        ks += W;
+        sxx += vj.x * W;
+        syy += vj.y * W;
+        szz += vj.z * W;
+    }
+    if (ks > 0.0)
+    {
+        double4 v = S.P1[i];
+        v.x = 2.0 * v.x - sxx / ks;
+        v.y = 2.0 * v.y - syy / ks;
+        v.z = 2.0 * v.z - szz / ks;
+        S.P1[i] = v;
+    }
+}
+
+__device__ __forceinline__ double eos_pressure(const DevConst& C, double rho)
+{
+    if (C.pressure_rel == 0)
+        return C.B * (pow(rho / C.rho_rest, C.gam) - 1.0) + C.press_back;
+    return C.c2 * (rho - C.rho_rest) + C.press_back;
+}
+__device__ __forceinline__ double eos_density(const DevConst& C, double p)
+{
+    if (C.pressure_rel == 0)
+        return C.rho_rest * pow(((p - C.press_back) / C.B) + 1.0, 1.0 / C.gam);
+    return (p - C.press_back) / C.c2 + C.rho_rest;
+}
+// keeps the derived gather quantities V = m/rho and p/rho^2 consistent with (rho, p)
+__device__ __forceinline__ void store_thermo(Level& S, int i, double rho, double p)
+{
+    double4 th = S.TH[i];
+    th.x = p;
+    S.TH[i] = th;
+    double4 a = S.P0[i];
+    a.w = th.y / rho;
+    S.P0[i] = a;
+    double4 v = S.P1[i];
+    v.w = rho;
+    S.P1[i] = v;
+    double4 q = S.P2[i];
+    q.w = p / (rho * rho);
+    S.P2[i] = q;
+}
+
+// Get_Boundary_Pressure (Adami et al. 2012): walls read fluid records only, so in-place update is race free
+__global__ void k_wall_pressure(Level S, ListView lv, const int* __restrict__ blk, int block, DevConst C, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] != block)
+        return;
+    const double4 pi = S.P0[i];
+    const double4 acc = S.ACC[i];
+    double ks = 0, pk = 0, akx = 0, aky = 0, akz = 0;
+    int near_surface = 0;
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    {
+        if (!(ent & FJ_NB_FLUID))
+            continue;
+        const double4 pj = S.P0[j];
+        const double rho_j = S.P1[j].w;
+        const double p_j = S.TH[j].x;
+        const double rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+        const double r = sqrt(rx * rx + ry * ry + rz * rz);
+        const double kern = pj.w * wend_W(C, r, wend_t(C, r));
+        ks += kern;
+        pk += p_j * kern;
+        const double kr = kern * rho_j;
+        akx += kr * rx;
+        aky += kr * ry;
+        akz += kr * rz;
+        if (S.surfzone[j])
+            near_surface = 1;
+    }
+    double p = 0.0;
+    if (ks > 0.0)
+    {
+        p = (pk + ((C.gx - acc.x) * akx + (C.gy - acc.y) * aky + (C.gz - acc.z) * akz)) / ks;
+        if (near_surface)
+            p = fmax(0.0, p);
+    }
+    store_thermo(S, i, eos_density(C, p), p);
+}
+
+// Boundary_Ghost: Rrho_i = -rho_i sum V_j Vji.gradK over all neighbours; near_inlet = no PIPE/FREE neighbour.
+__global__ void k_wall_ghost(Level S, ListView lv, const int* __restrict__ blk, int block, DevConst C, int n,
+                             int* __restrict__ near_inlet_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] != block)
+        return;
+    const double4 pi = S.P0[i];
+    const double4 vi = S.P1[i];
+    double Rrhoi = 0.0;
+    int near_inlet = 1;
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    {
+        const int bj = S.b[j];
+        if (bj == FJSPH_PIPE || bj == FJSPH_FREE)
+            near_inlet = 0;
+        const double4 pj = S.P0[j];
+        const double4 vj = S.P1[j];
+        const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+        const double r = sqrt(rx * rx + ry * ry + rz * rz);
+        const double gk = wend_gk(C, r, wend_t(C, r));
+        Rrhoi -= pj.w * gk * ((vj.x - vi.x) * rx + (vj.y - vi.y) * ry + (vj.z - vi.z) * rz);
+    }
+    double4 acc = S.ACC[i];
+    acc.w = Rrhoi * vi.w;
+    S.ACC[i] = acc;
+    near_inlet_out[i] = near_inlet;
+}
+
+// Boundary_DBC: the reference accumulates out of bounds (Resid.cpp:84,107); its defined effect is acc = 0
+__global__ void k_wall_dbc(Level S, const int* __restrict__ blk, int block, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] != block)
+        return;
+    double4 acc = S.ACC[i];
+    acc.x = acc.y = acc.z = 0.0;
+    S.ACC[i] = acc;
+}
+
+// Check_Pipe_Outlet (Containment.cpp:822-847), constVel part: PIPE -> FREE past the block's aero plane
+__global__ void k_pipe_outlet(Level S, const int* __restrict__ blk, int block, double nx, double ny, double nz,
+                              double aeroconst, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || blk[i] != block)
+        return;
+    if (S.b[i] == FJSPH_PIPE)
+    {
+        const double4 p = S.P0[i];
+        if (p.x * nx + p.y * ny + p.z * nz > aeroconst)
+            S.b[i] = FJSPH_FREE;
+    }
+}
+
+ListView list_view(FjsphEngine* e)
+{
+    ListView v;
+    v.nlist = e->nlist;
+    v.ncount = e->ncount;
+    v.nb_cap = e->nb_cap;
+    return v;
+}
+
+int need_list(FjsphEngine* e, const char* who)
+{
+    if (!e->list_valid)
+    {
+        fj_set_error("%s: neighbour list not built (call fjsph_build_neighbours first)", who);
+        return FJSPH_ERR_STATE;
+    }
+    return FJSPH_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ host wrappers
+int fj_prestep(FjsphEngine* e, double* npd)
+{
+    int st = need_list(e, "prestep");
+    if (st)
+        return st;
+    const int n = int(e->n_owned);
+    const int nb = fj_blocks(n, TPB);
+    {
+        KScope ks(e, "prestep", 1);
+        k_prestep<<<nb, TPB, 0, e->stream>>>(e->lv[1], list_view(e), e->C, n, e->red);
+    }
+    FJ_CUDA(cudaGetLastError());
+    double sum = 0.0;
+    st = fj_reduce_sum(e, nb, 1, &sum);
+    if (st)
+        return st;
+    /* npd = npd_ / end (Shifting.cpp:121); Q4: the race-free sum */
+    e->npd = sum / double(e->n_owned);
+    if (npd)
+        *npd = e->npd;
+    return FJSPH_OK;
+}
+
+int fj_aero_velocity(FjsphEngine* e)
+{
+    int st = need_list(e, "aero_velocity");
+    if (st)
+        return st;
+    if (e->P.asource != 0)
+    {
+        fj_set_error("aero source %d (mesh containment) is not available on the device yet", e->P.asource);
+        return FJSPH_ERR_INVALID;
+    }
+    const int n = int(e->n_owned);
+    KScope ks(e, "aero_vel", 1);
+    k_aero_velocity<<<fj_blocks(n, 256), 256, 0, e->stream>>>(e->lv[1], e->ncount, e->blk, e->n_bound_blocks, e->C, n);
+    FJ_CUDA(cudaGetLastError());
+    return FJSPH_OK;
+}
+
+int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipation)
+{
+    int st = need_list(e, "detect_surface/dissipation");
+    if (st)
+        return st;
+    const int n = int(e->n_owned);
+    const int nb = fj_blocks(n, TPB);
+    ListView lv = list_view(e);
+    if (do_surface && do_dissipation)
+    {
+        KScope ks(e, "surf1+diss", 1);
+        k_surf1_diss<true, true><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+    }
+    else if (do_surface)
+    {
+        KScope ks(e, "surf1", 1);
+        k_surf1_diss<true, false><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+    }
+    else if (do_dissipation)
+    {
+        KScope ks(e, "diss", 1);
+        k_surf1_diss<false, true><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+    }
+    if (do_surface)
+    {
+        KScope ks(e, "surf2+3", 1);
+        k_surf23<<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+    }
+    FJ_CUDA(cudaGetLastError());
+    return FJSPH_OK;
+}
+
+int fj_shift(FjsphEngine* e)
+{
+    int st = need_list(e, "shift");
+    if (st)
+        return st;
+    if (!e->P.ale)
+        return FJSPH_OK;
+    const int n = int(e->n_owned);
+    KScope ks(e, "shift", 1);
+    k_shift<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], list_view(e), e->blk, e->n_bound_blocks, e->C, n);
+    FJ_CUDA(cudaGetLastError());
+    return FJSPH_OK;
+}
+
+int fj_check_pipe_outlet(FjsphEngine* e)
+{
+    const int n = int(e->n_owned);
+    for (size_t bl = size_t(e->n_bound_blocks); bl < e->blocks.size(); ++bl)
+    {
+        const HostBlock& B = e->blocks[bl];
+        if (B.aeroconst == 9999999.0)
+            continue; /* plane undefined: x.dot(default) > default never holds for sane coordinates */
+        KScope ks(e, "pipe_outlet", 1);
+        k_pipe_outlet<<<fj_blocks(n, 256), 256, 0, e->stream>>>(e->lv[1], e->blk, int(bl), B.aero_norm[0],
+                                                                B.aero_norm[1], B.aero_norm[2], B.aeroconst, n);
+    }
+    FJ_CUDA(cudaGetLastError());
+    return FJSPH_OK;
+}
+
+int fj_forces(FjsphEngine* e, int level_idx, double npd)
+{
+    int st = need_list(e, "forces");
+    if (st)
+        return st;
+    const int n = int(e->n_owned);
+    /* Resid.cpp:437-448 */
+    const double lam = (6.0 / 81.0 * std::pow((2.0 * e->P.H), 3.0) / std::pow(FJ_PI, 4.0) *
+                        (9.0 / 4.0 * std::pow(FJ_PI, 3.0) - 6.0 * FJ_PI - 4.0));
+    const double npdm2 = (0.5 * e->P.sig / lam) / (npd * npd);
+    {
+        KScope ks(e, "force", 1);
+        if (e->P.ale)
+            k_force<true><<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[level_idx], list_view(e), e->blk,
+                                                                     e->n_bound_blocks, e->C, npdm2, n);
+        else
+            k_force<false><<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[level_idx], list_view(e), e->blk,
+                                                                      e->n_bound_blocks, e->C, npdm2, n);
+    }
+    e->force_evals++;
+    FJ_CUDA(cudaGetLastError());
+    return FJSPH_OK;
+}
+
+// Wall treatment at the head of Do_NB_Iter (Newmark_Beta.cpp:69-132) and of the RK stages
+// (Runge_Kutta.cpp:36-135).  nb_comparator selects the schedule comparison (Q10).
+int fj_walls(FjsphEngine* e, int level_idx, bool nb_comparator)
+{
+    if (e->n_bound_blocks == 0)
+        return FJSPH_OK;
+    int st = need_list(e, "walls");
+    if (st)
+        return st;
+    const int n = int(e->n_owned);
+    const int nb = fj_blocks(n, TPB);
+    ListView lv = list_view(e);
+    Level& S = e->lv[level_idx];
+    for (int bl = 0; bl < e->n_bound_blocks; ++bl)
+    {
+        const HostBlock& B = e->blocks[bl];
+        double vel[3] = {B.vels[0], B.vels[1], B.vels[2]};
+        if (!B.times.empty())
+        {
+            vel[0] = vel[1] = vel[2] = 0.0;
+            for (size_t t = 0; t < B.times.size(); ++t)
+            {
+                const bool take = nb_comparator ? (e->P.current_time > B.times[t]) : (B.times[t] > e->P.current_time);
+                if (take)
+                    for (int d = 0; d < 3; ++d) vel[d] = B.vels[3 * t + d];
+            }
+        }
+        KScope ks(e, "walls", 3);
+        k_wall_velocity<<<nb, TPB, 0, e->stream>>>(S, e->blk, bl, vel[0], vel[1], vel[2], n);
+        if (B.no_slip)
+            k_wall_no_slip<<<nb, TPB, 0, e->stream>>>(S, lv, e->blk, bl, e->C, n);
+        switch (B.bound_solver)
+        {
+        case FJSPH_DBC: k_wall_dbc<<<nb, TPB, 0, e->stream>>>(S, e->blk, bl, n); break;
+        case FJSPH_PRESSURE_G: k_wall_pressure<<<nb, TPB, 0, e->stream>>>(S, lv, e->blk, bl, e->C, n); break;
+        case FJSPH_GHOST: k_wall_ghost<<<nb, TPB, 0, e->stream>>>(S, lv, e->blk, bl, e->C, n, e->near_inlet); break;
+        default: break;
+        }
+    }
+    FJ_CUDA(cudaGetLastError());
+    return FJSPH_OK;
+}

@@ -1,0 +1,292 @@
+"""Host-side mirror of FJSPH's time-step interface on top of the C ABI (include/fjsph_b200.h).
+
+Method names follow the reference functions they replace:
+    update_neighbours  Neighbours.h:9        dSPH_PreStep      Shifting.h:10
+    get_aero_velocity  Resid.h:43-46         Detect_Surface    Geometry.h:98-101
+    dissipation_terms  Shifting.h:13-15      particle_shift    Shifting.h:18-20
+    get_acc_and_Rrho   Resid.h:39-41         Do_NB_Iter        Newmark_Beta.h:11-26
+    integrate / integrate_no_update          Integration.h:20-28
+The arithmetic runs in hand-written sm_100a kernels; this file only moves numpy arrays across the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FjsphBlock, FjsphParams, FjsphStateView, FjsphStepStats, check
+
+INT64_FIELDS = ("part_id", "cellID")
+INT32_FIELDS = ("b", "surf", "surfzone", "internal")
+VEC_FIELDS = ("xi", "v", "acc", "Af", "aVisc", "cellV", "gradRho", "norm", "bNorm", "vPert")
+SCALAR_FIELDS = tuple(
+    "Rrho rho p m curve norm_curve woccl pDist deltaD cellP cellRho colourG colour lam lam_nb kernsum y".split()
+)
+ALL_FIELDS = INT64_FIELDS + INT32_FIELDS + VEC_FIELDS + ("L",) + SCALAR_FIELDS
+
+
+def default_params(dim: int = 3, **kw) -> FjsphParams:
+    """Var.h defaults, overridden by kw, then Set_Values (IO.cpp:26-128) — all in the C++ host library."""
+    p = FjsphParams()
+    check(_lib.lib().fjsph_default_params(C.byref(p), dim))
+    set_fields(p, **kw)
+    if p.frame_time_interval < 0:
+        p.frame_time_interval = 1.0
+    check(_lib.lib().fjsph_set_values(C.byref(p)))
+    return p
+
+
+def read_para(path: str, dim: int = 3, **kw):
+    """GetInput + Set_Values for a FJSPH para file; returns (params, fluid_file, boundary_file)."""
+    p = FjsphParams()
+    L = _lib.lib()
+    check(L.fjsph_default_params(C.byref(p), dim))
+    fl, bd = C.create_string_buffer(512), C.create_string_buffer(512)
+    check(L.fjsph_read_para(path.encode(), C.byref(p), fl, bd, 512))
+    set_fields(p, **kw)
+    check(L.fjsph_set_values(C.byref(p)))
+    return p, fl.value.decode(), bd.value.decode()
+
+
+def set_fields(p, **kw):
+    for k, v in kw.items():
+        cur = getattr(p, k)
+        if hasattr(cur, "__len__"):
+            for i, x in enumerate(v):
+                cur[i] = x
+        else:
+            setattr(p, k, v)
+
+
+def params_to_dict(p) -> dict:
+    return {n: (list(getattr(p, n)) if hasattr(getattr(p, n), "__len__") else getattr(p, n)) for n, _ in p._fields_}
+
+
+def _dtype_of(name):
+    if name in INT64_FIELDS:
+        return np.int64
+    if name in INT32_FIELDS:
+        return np.int32
+    return np.float64
+
+
+def _shape_of(name, n):
+    if name in VEC_FIELDS:
+        return (n, 3)
+    if name == "L":
+        return (n, 3, 3)
+    return (n,)
+
+
+def make_view(arrays: dict, n: int):
+    """FjsphStateView over numpy arrays (kept alive by the returned list)."""
+    view = FjsphStateView()
+    view.n = n
+    keep = []
+    for name, a in arrays.items():
+        if a is None:
+            continue
+        a = np.ascontiguousarray(a, dtype=_dtype_of(name))
+        if a.shape != _shape_of(name, n):
+            a = np.ascontiguousarray(np.broadcast_to(a, _shape_of(name, n)))
+        keep.append(a)
+        arrays[name] = a
+        setattr(view, name, a.ctypes.data)
+    return view, keep
+
+
+class Engine:
+    """One simulation resident on one B200."""
+
+    def __init__(self, params: FjsphParams, capacity: int, device: int = 0):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        check(self._L.fjsph_create(C.byref(params), device, int(capacity), C.byref(self._h)))
+        self.capacity = int(capacity)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.fjsph_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- settings
+    @property
+    def params(self) -> FjsphParams:
+        p = FjsphParams()
+        check(self._L.fjsph_get_params(self._h, C.byref(p)))
+        return p
+
+    def set_params(self, **kw):
+        p = self.params
+        set_fields(p, **kw)
+        check(self._L.fjsph_set_params(self._h, C.byref(p)))
+
+    def set_blocks(self, blocks):
+        """blocks: list of dicts with the bound_block fields (Var.h:779-859)."""
+        arr = (FjsphBlock * len(blocks))()
+        keep = []
+        for k, b in enumerate(blocks):
+            B = arr[k]
+            B.first, B.second = int(b["first"]), int(b["second"])
+            B.is_fluid = int(b.get("is_fluid", 0))
+            B.bound_solver = int(b.get("bound_solver", 1))
+            B.no_slip = int(b.get("no_slip", 0))
+            B.block_type = int(b.get("block_type", 0))
+            B.fixed_vel_or_dynamic = int(b.get("fixed_vel_or_dynamic", 0))
+            times = b.get("times")
+            nt = 0 if times is None else len(times)
+            B.n_times = nt
+            if nt:
+                t = np.ascontiguousarray(times, dtype=np.float64)
+                keep.append(t)
+                B.times = t.ctypes.data
+            vels = np.zeros((max(1, nt), 3))
+            if b.get("vels") is not None:
+                vels[:] = np.asarray(b["vels"], dtype=np.float64).reshape(-1, 3)
+            keep.append(vels)
+            B.vels = vels.ctypes.data
+            for key, const in (("insert_norm", "insconst"), ("delete_norm", "delconst"), ("aero_norm", "aeroconst")):
+                vec = b.get(key)
+                for d in range(3):
+                    getattr(B, key)[d] = 9999999.0 if vec is None else float(vec[d])
+                setattr(B, const, float(b.get(const, 9999999.0)))
+            back = b.get("back")
+            if back is not None:
+                ba = np.ascontiguousarray(back, dtype=np.int64)
+                bu = np.ascontiguousarray(b["buffer"], dtype=np.int64)
+                keep += [ba, bu]
+                B.n_back, B.n_buf = len(ba), bu.shape[1]
+                B.back, B.buffer = ba.ctypes.data, bu.ctypes.data
+        check(self._L.fjsph_set_blocks(self._h, len(blocks), arr))
+
+    # -- state
+    def upload_state(self, xi, v, rho, p, m, b, bound_points=0, **extra):
+        xi = np.ascontiguousarray(xi, dtype=np.float64)
+        n = xi.shape[0]
+        arrays = dict(xi=xi, v=np.zeros_like(xi) if v is None else v, rho=rho, p=p, m=m, b=b, **extra)
+        view, keep = make_view(arrays, n)
+        check(self._L.fjsph_upload_state(self._h, C.byref(view), int(bound_points)))
+
+    def upload_level(self, level: int, **fields):
+        n = self.n
+        view, keep = make_view(dict(fields), n)
+        check(self._L.fjsph_upload_level(self._h, level, C.byref(view)))
+
+    def download(self, fields=ALL_FIELDS, level: int = 1, out: dict | None = None) -> dict:
+        n = self.n
+        arrays = {}
+        for f in fields:
+            if out is not None and f in out:
+                arrays[f] = out[f]
+            else:
+                arrays[f] = np.empty(_shape_of(f, n), dtype=_dtype_of(f))
+        view, keep = make_view(arrays, n)
+        check(self._L.fjsph_download_state(self._h, level, C.byref(view)))
+        return arrays
+
+    def get(self, name: str, level: int = 1) -> np.ndarray:
+        return self.download((name,), level)[name]
+
+    @property
+    def n(self) -> int:
+        return int(self._L.fjsph_count(self._h))
+
+    # -- stages (reference function names)
+    def update_neighbours(self):
+        check(self._L.fjsph_build_neighbours(self._h))
+
+    def neighbour_counts(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.int64)
+        check(self._L.fjsph_neighbour_counts(self._h, out.ctypes.data))
+        return out
+
+    def neighbours(self):
+        """CSR (offsets, idx): ascending j per particle, self included — the shape of the reference's OUTL."""
+        cnt = self.neighbour_counts()
+        off = np.zeros(self.n + 1, dtype=np.int64)
+        np.cumsum(cnt, out=off[1:])
+        idx = np.empty(int(off[-1]), dtype=np.int64)
+        check(self._L.fjsph_get_neighbours(self._h, off.ctypes.data, idx.ctypes.data))
+        return off, idx
+
+    def dSPH_PreStep(self) -> float:
+        npd = C.c_double()
+        check(self._L.fjsph_prestep(self._h, C.byref(npd)))
+        return npd.value
+
+    def get_aero_velocity(self):
+        check(self._L.fjsph_aero_velocity(self._h))
+
+    def Detect_Surface(self):
+        check(self._L.fjsph_detect_surface(self._h))
+
+    def dissipation_terms(self):
+        check(self._L.fjsph_dissipation(self._h))
+
+    def particle_shift(self):
+        check(self._L.fjsph_shift(self._h))
+
+    def get_acc_and_Rrho(self, npd: float):
+        check(self._L.fjsph_forces(self._h, float(npd)))
+
+    def Do_NB_Iter(self, npd: float) -> float:
+        err = C.c_double()
+        check(self._L.fjsph_nb_iter(self._h, float(npd), C.byref(err)))
+        return err.value
+
+    def find_timestep(self) -> float:
+        dt = C.c_double()
+        check(self._L.fjsph_find_timestep(self._h, C.byref(dt)))
+        return dt.value
+
+    def integrate_no_update(self) -> FjsphStepStats:
+        s = FjsphStepStats()
+        check(self._L.fjsph_integrate_no_update(self._h, C.byref(s)))
+        return s
+
+    def integrate(self) -> FjsphStepStats:
+        """One Integrator::integrate (Integration.cpp:233-303) on the device-resident state."""
+        s = FjsphStepStats()
+        check(self._L.fjsph_step(self._h, C.byref(s)))
+        return s
+
+    def step_host(self, inputs: dict, bound_points: int, n_steps: int, out_fields=("xi", "v", "rho", "p")):
+        """End-to-end call with HOST buffers: upload -> n_steps x integrate -> download."""
+        n = np.asarray(inputs["xi"]).shape[0]
+        vin, k1 = make_view(dict(inputs), n)
+        outs = {f: np.empty(_shape_of(f, n), dtype=_dtype_of(f)) for f in out_fields}
+        vout, k2 = make_view(outs, n)
+        s = FjsphStepStats()
+        check(self._L.fjsph_step_host(self._h, C.byref(vin), int(bound_points), int(n_steps), C.byref(vout), C.byref(s)))
+        return outs, s
+
+    # -- instrumentation
+    def timers_enable(self, on=True):
+        check(self._L.fjsph_timers_enable(self._h, int(on)))
+
+    def timers_reset(self):
+        check(self._L.fjsph_timers_reset(self._h))
+
+    def timers(self) -> dict:
+        cap = 64
+        names = C.create_string_buffer(cap * 32)
+        ms = (C.c_double * cap)()
+        launches = (C.c_int64 * cap)()
+        n = C.c_int32()
+        check(self._L.fjsph_timers_get(self._h, cap, names, ms, launches, C.byref(n)))
+        out = {}
+        for k in range(n.value):
+            nm = names.raw[k * 32:(k + 1) * 32].split(b"\0", 1)[0].decode()
+            out[nm] = dict(ms=ms[k], launches=int(launches[k]))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.fjsph_launch_count(self._h))

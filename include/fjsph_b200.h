@@ -1,0 +1,177 @@
+/* fjsph_b200.h — C ABI of the B200-native WCSPH time-step engine.
+ *
+ * Drop-in boundary for FJSPH's time-step path.  FJSPH has no plugin/FFI layer; the path
+ * sits behind ordinary C++ functions called from main's frame loop (reference src/FJSPH.cpp:278-280).
+ * Each entry point below names the reference function it replaces.  The binding a FJSPH maintainer
+ * would add is shown in INTEGRATION.md.
+ *
+ * Conventions: opaque handle; every function returns 0 on success and a non-zero FjsphStatus on error
+ * (text via fjsph_last_error()); never calls exit().  Single-threaded caller, one simulation per handle.
+ * All arrays are caller-owned HOST memory, row-major, FP64 / int32 / int64, copied in/out explicitly.
+ * Vectors are [n][3] (3D only on the device), L is [n][3][3].  Particle order is the reference's:
+ * boundary blocks first, then fluid blocks (Init.cpp:298-475); the engine re-sorts internally and
+ * returns everything in the caller's order.
+ */
+#ifndef FJSPH_B200_H
+#define FJSPH_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum FjsphStatus
+{
+    FJSPH_OK = 0,
+    FJSPH_ERR_INVALID = 1,     /* bad argument / unsupported compile-time option of the reference */
+    FJSPH_ERR_CUDA = 2,        /* CUDA runtime failure (no device, out of memory, launch error) */
+    FJSPH_ERR_STATE = 3,       /* call order (e.g. stage before upload / neighbour build) */
+    FJSPH_ERR_CAPACITY = 4,    /* particle / neighbour / cell-table capacity exceeded */
+    FJSPH_ERR_IO = 5           /* settings file problems */
+} FjsphStatus;
+
+/* partType, VarDefs.h:92-102 */
+enum { FJSPH_BOUND = 0, FJSPH_PISTON, FJSPH_BUFFER, FJSPH_BACK, FJSPH_PIPE, FJSPH_FREE, FJSPH_OUTLET, FJSPH_LOST };
+/* bound_solve_type, VarDefs.h:142-147 */
+enum { FJSPH_DBC = 0, FJSPH_PRESSURE_G = 1, FJSPH_GHOST = 2 };
+/* shape_type inletZone, VarDefs.h:118-129 */
+enum { FJSPH_INLET_ZONE = 6 };
+
+/* Every setting the path reads (Var.h INTEG_SETT / FLUID / AERO / SIM), then the constants that
+ * Set_Values derives from them (IO.cpp:26-128).  fjsph_set_values() fills the second half. */
+typedef struct FjsphParams
+{
+    /* switches */
+    int32_t dim;          /* SIMDIM; the device path supports 3 only */
+    int32_t ale;          /* 1 = the -DALE binary (shifting, surfzone-gated ST), 0 = the delta-SPH binary */
+    int32_t pressure_rel; /* 0 Cole, 1 isothermal (Var.h:203-236, IO.cpp:397) */
+    int32_t solver_type;  /* 0 Newmark-Beta, 1 Runge-Kutta (IO.cpp:393) */
+    int32_t acase;        /* aero_force: 0 none, 1 Gissler (IO.cpp:432) */
+    int32_t asource;      /* aero_source: 0 constVel, 1 meshInfl */
+    int32_t use_lam;
+    int32_t use_TAB_def;
+    int32_t max_subits;
+    int32_t n_stable, n_stable_limit, n_unstable, n_unstable_limit;
+    int32_t reserved0;
+    /* inputs */
+    double particle_step, H_fac, rho_rest, press_pipe, press_back, rho_max, rho_min, rho_var, rho_max_iter;
+    double visc_alpha, speed_sound, mu, sig, gam, dsph_delta;
+    double grav[3];
+    double v_inf[3];
+    double p_ref, rho_g, mu_g, temp_g, R_g, gamma_g, lam_cutoff, i_interp_fac;
+    double tab_Cf, tab_Ck, tab_Cd, tab_Cb;
+    double cfl, cfl_step, cfl_max, cfl_min, subits_factor, min_residual;
+    double delta_t, delta_t_max, delta_t_min, max_shift_vel;
+    double current_time, last_frame_time, frame_time_interval;
+    /* derived by fjsph_set_values (IO.cpp:26-128, Var.h:244-266, Geometry.cpp:282-308) */
+    double B, rho_pipe, dx, sim_mass, bnd_mass, H, H_sq, sr, dsph_cont, nu, W_correc, W_dx, nb_beta, nb_gamma;
+    double aero_L, A_sphere, A_plate, td, omega, tmax, Cdef, ycoef, n_full, i_n_full, interp_fac, sos;
+} FjsphParams;
+
+/* One block of the reference's LIMITS vector (bound_block, Var.h:779-859). */
+typedef struct FjsphBlock
+{
+    int64_t first, second;        /* index range [first, second) in the caller's particle order */
+    int32_t is_fluid;             /* 0 boundary block, 1 fluid block */
+    int32_t bound_solver;         /* FJSPH_DBC / FJSPH_PRESSURE_G / FJSPH_GHOST */
+    int32_t no_slip;
+    int32_t block_type;           /* FJSPH_INLET_ZONE for inlets */
+    int32_t fixed_vel_or_dynamic;
+    int32_t n_times;              /* 0: static velocity vels[0..2] */
+    const double* times;          /* [n_times] */
+    const double* vels;           /* [max(1,n_times)][3] */
+    double insert_norm[3], insconst;
+    double delete_norm[3], delconst;
+    double aero_norm[3], aeroconst;
+    int32_t n_back, n_buf;
+    const int64_t* back;          /* [n_back] */
+    const int64_t* buffer;        /* [n_back][n_buf] */
+} FjsphBlock;
+
+/* Host view of one time level: the field list of SPHPart (Var.h:499-642).  NULL pointers are skipped
+ * (upload: keep the device value / default; download: do not fetch). */
+typedef struct FjsphStateView
+{
+    int64_t n;
+    int64_t* part_id;
+    int64_t* cellID;
+    int32_t *b, *surf, *surfzone, *internal;
+    double *xi, *v, *acc, *Af, *aVisc, *cellV, *gradRho, *norm, *bNorm, *vPert; /* [n][3] */
+    double* L;                                                                   /* [n][3][3] */
+    double *Rrho, *rho, *p, *m, *curve, *norm_curve, *woccl, *pDist, *deltaD, *cellP, *cellRho, *colourG, *colour,
+        *lam, *lam_nb, *kernsum, *y; /* [n] */
+} FjsphStateView;
+
+/* Columns of the reference's per-step table (Integration.cpp:250-265) plus counters. */
+typedef struct FjsphStepStats
+{
+    double dt, cfl_ratio, rms_error, maxRho_pc, maxf, maxAf, maxShift, safe_dt, npd, logbase;
+    int32_t iterations, n_add, n_del, total_points;
+    int32_t force_evals, neighbour_builds, kernel_launches, reserved;
+} FjsphStepStats;
+
+typedef struct FjsphEngine FjsphEngine;
+
+const char* fjsph_last_error(void);
+const char* fjsph_version(void);
+
+/* Host-side restatement of the settings path: Var.h defaults; GetInput's `key : value` para parser
+ * (IO.cpp:305-456, the keys of SURVEY Appendix B); Set_Values (IO.cpp:26-128). */
+int fjsph_default_params(FjsphParams* p, int dim);
+int fjsph_read_para(const char* path, FjsphParams* p, char* fluid_file, char* bound_file, int name_cap);
+int fjsph_set_values(FjsphParams* p);
+
+/* Lifetime.  device = CUDA ordinal.  capacity = max particles this rank will ever hold (>= n). */
+int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine** out);
+int fjsph_destroy(FjsphEngine* e);
+int fjsph_get_params(FjsphEngine* e, FjsphParams* out);
+int fjsph_set_params(FjsphEngine* e, const FjsphParams* in);
+
+/* LIMITS (Init.cpp:298-475).  Optional: without it one pressure_G wall block [0,bound_points) and one
+ * fluid block [bound_points,n) are assumed. */
+int fjsph_set_blocks(FjsphEngine* e, int32_t n_blocks, const FjsphBlock* blocks);
+
+/* pn / pnp1 (FJSPH.cpp:49-58).  fjsph_upload_state sets BOTH time levels from `s` (pn = pnp1,
+ * Init.cpp:496); fjsph_upload_level overwrites the given fields of one level (0 = pn, 1 = pnp1). */
+int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_points);
+int fjsph_upload_level(FjsphEngine* e, int level, const FjsphStateView* s);
+int fjsph_download_state(FjsphEngine* e, int level, FjsphStateView* s);
+int64_t fjsph_count(FjsphEngine* e);
+
+/* Stage entry points; each replaces the reference function named on the right and acts on pnp1. */
+int fjsph_build_neighbours(FjsphEngine* e);                     /* update_neighbours      Neighbours.h:9 */
+int fjsph_neighbour_counts(FjsphEngine* e, int64_t* counts);    /* outlist[i].size() incl. self */
+int fjsph_get_neighbours(FjsphEngine* e, const int64_t* offsets, int64_t* idx); /* CSR, ascending j, self incl. */
+int fjsph_prestep(FjsphEngine* e, double* npd);                 /* dSPH_PreStep           Shifting.h:10 */
+int fjsph_aero_velocity(FjsphEngine* e);                        /* get_aero_velocity      Resid.h:43-46 */
+int fjsph_detect_surface(FjsphEngine* e);                       /* Detect_Surface         Geometry.h:98-101 */
+int fjsph_dissipation(FjsphEngine* e);                          /* dissipation_terms      Shifting.h:13-15 */
+int fjsph_shift(FjsphEngine* e);                                /* particle_shift         Shifting.h:18-20 */
+int fjsph_forces(FjsphEngine* e, double npd);                   /* get_acc_and_Rrho       Resid.h:39-41 */
+int fjsph_nb_iter(FjsphEngine* e, double npd, double* errsum);  /* Newmark_Beta::Do_NB_Iter + the sum of
+                                                                   Check_Error, Newmark_Beta.h:11-26 */
+int fjsph_find_timestep(FjsphEngine* e, double* dt);            /* Integrator::find_timestep */
+int fjsph_integrate_no_update(FjsphEngine* e, FjsphStepStats* s); /* Integration.h:25-28 */
+int fjsph_step(FjsphEngine* e, FjsphStepStats* s);              /* Integrator::integrate  Integration.h:20-23 */
+
+/* Convenience for hosts that keep particles on the host between steps (the end-to-end path):
+ * upload -> n_steps x fjsph_step -> download, one call. */
+int fjsph_step_host(FjsphEngine* e, const FjsphStateView* in, int64_t bound_points, int32_t n_steps,
+                    FjsphStateView* out, FjsphStepStats* last);
+
+/* Instrumentation: CUDA-event time (ms) and launch count per kernel family since the last reset. */
+int fjsph_timers_reset(FjsphEngine* e);
+int fjsph_timers_enable(FjsphEngine* e, int on);
+int fjsph_timers_get(FjsphEngine* e, int32_t cap, char* names /* cap x 32 */, double* ms, int64_t* launches,
+                     int32_t* n_out);
+int64_t fjsph_launch_count(FjsphEngine* e);
+
+/* Slab decomposition: ghost particles are appended by the caller's exchange layer.
+ * The engine packs / unpacks halo records on the device; the transport (NCCL send/recv) lives in the
+ * host layer (fjsph_b200/slab.py).  See DESIGN.md "Multi-GPU". */
+int fjsph_set_owned(FjsphEngine* e, int64_t n_owned);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
