@@ -62,7 +62,7 @@ def synthetic_block(n=(500, 250, 100), dx=1e-3, jitter=0.1, seed=1234, rho0=1000
     )
 
 
-def droplet(dx=0.0015, radius=0.05, seed=1234, dim=3):
+def droplet(dx=0.0015, radius=0.05, seed=1234, dim=3, jitter="eps"):
     """Config C2, Examples/Droplet/{para3D,fluid_3D.bmap}: sphere R=0.05 at the origin, rho 810,
     Gissler aero with v_inf = (0, 21.55, 0).  Lattice start = centre - radius, end = centre + radius
     (circle.cpp:131-189).  dx=0.0015 -> ~155 k particles, dx=0.0008 -> ~1.02 M."""
@@ -70,7 +70,10 @@ def droplet(dx=0.0015, radius=0.05, seed=1234, dim=3):
     n1 = max(n1, 1)
     pts = lattice((n1,) * dim, dx, start=(-radius,) * dim, jitter=None)
     rng = np.random.default_rng(seed)
-    pts = pts + rng.uniform(0.0, EPS * dx, size=pts.shape)
+    if jitter == "eps":  # the reference's own perturbation (circle.cpp:136-137): a tie-stress input
+        pts = pts + rng.uniform(0.0, EPS * dx, size=pts.shape)
+    else:  # generic positions: no neighbour sits on the support edge to the last bit
+        pts = pts + rng.uniform(-float(jitter), float(jitter), size=pts.shape) * dx
     keep = (pts**2).sum(axis=1) <= radius * radius
     xi = np.ascontiguousarray(pts[keep])
     N = xi.shape[0]

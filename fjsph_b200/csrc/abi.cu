@@ -682,7 +682,7 @@ int fjsph_destroy(FjsphEngine* e)
     void* ptrs[] = {e->oidx,       e->oidx_tmp, e->slot_of,  e->blk,      e->blk_tmp,   e->key,     e->rank_in_cell,
                     e->perm,       e->perm2,    e->ncount,   e->near_inlet, e->rk_sum_v, e->rk_sum_a, e->red,
                     e->red_out,    e->d_flag,   e->stage,    e->cell_count, e->cell_start, e->scan_tmp, e->mtab_x,
-                    e->nlist};
+                    e->nlist,      e->nr};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);

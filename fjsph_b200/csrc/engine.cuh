@@ -112,6 +112,7 @@ struct FjsphEngine
     unsigned int *mtab_x = nullptr, *mtab_y = nullptr, *mtab_z = nullptr; // Morton spread tables
     int mtab_cap = 0;
     unsigned int* nlist = nullptr;      // warp-transposed ELL: [(warp*nb_cap + s)*32 + lane]
+    double* nr = nullptr;               // same layout: r = sqrt(d^2) at list-build time (OUTL's .second, frozen)
     int* ncount = nullptr;              // [cap] neighbours excluding self
     int* near_inlet = nullptr;          // [cap] Boundary_Ghost flag, valid within one sub-iteration
     int nb_cap = 0;

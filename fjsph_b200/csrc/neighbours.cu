@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(TPB)
     k_build_list(const double4* __restrict__ P0, const int* __restrict__ b, int n, Grid g,
                  const unsigned* __restrict__ mx, const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
                  const unsigned* __restrict__ cell_start, double sr, int nb_cap, unsigned* __restrict__ nlist,
-                 int* __restrict__ ncount, int* __restrict__ flag)
+                 double* __restrict__ nr, int* __restrict__ ncount, int* __restrict__ flag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(TPB)
     int cx, cy, cz;
     cell_of(g, a.x, a.y, a.z, cx, cy, cz);
     unsigned* __restrict__ dst = nlist + (size_t(i >> 5) * size_t(nb_cap)) * 32u + (i & 31);
+    double* __restrict__ rdst = nr + (size_t(i >> 5) * size_t(nb_cap)) * 32u + (i & 31);
     int cnt = 0;
     for (int dz = -1; dz <= 1; ++dz)
     {
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(TPB)
                             if (bj == FJSPH_BOUND)
                                 ent |= FJ_NB_BOUND;
                             dst[size_t(cnt) * 32u] = ent;
+                            rdst[size_t(cnt) * 32u] = sqrt(d2); /* r = sqrt(jj.second), as every pair loop takes it */
                         }
                         cnt++;
                     }
@@ -403,8 +405,12 @@ static int ensure_list_capacity(FjsphEngine* e, int nb_cap)
         return FJSPH_OK;
     if (e->nlist)
         cudaFree(e->nlist);
+    if (e->nr)
+        cudaFree(e->nr);
     e->nlist = nullptr;
+    e->nr = nullptr;
     FJ_CUDA(cudaMalloc(&e->nlist, words * sizeof(unsigned)));
+    FJ_CUDA(cudaMalloc(&e->nr, words * sizeof(double)));
     e->nlist_words = words;
     e->nb_cap = nb_cap;
     return FJSPH_OK;
@@ -533,7 +539,8 @@ int fj_build_neighbours(FjsphEngine* e)
         {
             KScope ks(e, "nb_list", 1);
             k_build_list<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, g, e->mtab_x, e->mtab_y, e->mtab_z,
-                                                    e->cell_start, e->P.sr, e->nb_cap, e->nlist, e->ncount, e->d_flag);
+                                                    e->cell_start, e->P.sr, e->nb_cap, e->nlist, e->nr, e->ncount,
+                                                    e->d_flag);
         }
         FJ_CUDA(cudaGetLastError());
         FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));

@@ -25,15 +25,23 @@ constexpr int TPB = 128;
 struct ListView
 {
     const unsigned* __restrict__ nlist;
+    const double* __restrict__ nr;
     const int* __restrict__ ncount;
     int nb_cap;
 };
 
-#define FJ_FOR_NEIGHBOURS(i, LV, ent, j)                                                                   \
-    const unsigned* __restrict__ _lp = (LV).nlist + (size_t((i) >> 5) * size_t((LV).nb_cap)) * 32u + ((i)&31); \
+// The reference carries d^2 in the neighbour list (OUTL = vector<vector<pair<idx, dist2>>>, Var.h:889-890) and
+// every pair loop reads r = sqrt(jj.second) from it, so r stays FROZEN at its list-build value while
+// Rji = xj - xi follows the positions through the Newmark-Beta sub-iterations / RK stages.  The list
+// therefore stores r next to the index (same warp-transposed layout, one 256-byte load per warp and slot).
+#define FJ_FOR_NEIGHBOURS(i, LV, ent, j, r)                                                                \
+    const size_t _lb = (size_t((i) >> 5) * size_t((LV).nb_cap)) * 32u + ((i)&31);                          \
+    const unsigned* __restrict__ _lp = (LV).nlist + _lb;                                                   \
+    const double* __restrict__ _rp = (LV).nr + _lb;                                                        \
     const int _cnt = (LV).ncount[i];                                                                       \
     for (int _s = 0; _s < _cnt; ++_s)                                                                      \
-        for (unsigned ent = _lp[size_t(_s) * 32u], j = ent & FJ_IDX_MASK, _once = 1; _once; _once = 0)
+        for (double r = _rp[size_t(_s) * 32u]; r >= 0.0; r = -1.0)                                         \
+            for (unsigned ent = _lp[size_t(_s) * 32u], j = ent & FJ_IDX_MASK, _once = 1; _once; _once = 0)
 
 // Wendland C2 (Kernel.h:37-61).  t = 1 - q/2.  W = t^4 (2q+1) Wc ; GradK(R, r) = R * gk with
 // gk = 5 Wc/H^2 * t^3, and 0 when r/H < 1e-12.
@@ -78,13 +86,12 @@ __global__ void __launch_bounds__(TPB)
         double g0 = 0, g1 = 0, g2 = 0, m0 = 0, m1 = 0, m2 = 0;
         double kernsum = C.W_correc; /* self term, Shifting.cpp:39-45 */
         double colour = 0.0;
-        FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+        FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
         {
             const double4 pj = S.P0[j];
             const double rho_j = S.P1[j].w;
             const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-            const double rr = rx * rx + ry * ry + rz * rz;
-            const double r = sqrt(rr);
+            const double rr = r * r;
             const double t = wend_t(C, r);
             const double vg = pj.w * wend_gk(C, r, t); /* V_j * gk ; Grad = GradK(-Rji) = -Rji*gk */
             const double ax = vg * rx, ay = vg * ry, az = vg * rz;
@@ -235,13 +242,12 @@ __global__ void __launch_bounds__(TPB)
     double avx = 0, avy = 0, avz = 0, Rrhod = 0;
     const double cos_pi4 = 0.70710678118654757;
 
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
     {
         const double4 pj = S.P0[j];
         const double4 gj = S.P3[j];
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-        const double rr = rx * rx + ry * ry + rz * rz;
-        const double r = sqrt(rr);
+        const double rr = r * r;
         const double t = wend_t(C, r);
         const double gk = wend_gk(C, r, t);
         const double vg = pj.w * gk;
@@ -373,7 +379,7 @@ __global__ void __launch_bounds__(TPB)
     /* woccl is overwritten with 1 when lam_nb >= lam_cutoff, so the occlusion max is only needed below it */
     const bool need_occl = occl && (lam_nb < C.lam_cutoff);
 
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
     {
         const double4 nj = S.P4[j];
         if (nj.w != 0.0)
@@ -383,8 +389,7 @@ __global__ void __launch_bounds__(TPB)
         {
             const double4 pj = S.P0[j];
             const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-            const double rr = rx * rx + ry * ry + rz * rz;
-            const double r = sqrt(rr);
+            const double rr = r * r;
             if (curv)
             {
                 const double t = wend_t(C, r);
@@ -456,13 +461,12 @@ __global__ void __launch_bounds__(TPB)
     double dux = 0, duy = 0, duz = 0, maxU2 = 0.0;
     /* max_j acos(c_j) over c_j in [-1,1] == acos(min_j c_j); NaNs (|c|>1) are skipped by the reference's '>' */
     double min_c = 2.0;
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
     {
         const double4 pj = S.P0[j];
         const double4 vj = S.P1[j];
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-        const double rr = rx * rx + ry * ry + rz * rz;
-        const double r = sqrt(rr);
+        const double rr = r * r;
         const double t = wend_t(C, r);
         const double W = wend_W(C, r, t);
         const double gk = wend_gk(C, r, t);
@@ -605,15 +609,14 @@ __global__ void __launch_bounds__(TPB)
         af.x = af.y = af.z = 0.0; /* CalcAeroAcc default branch returns zero */
     }
 
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
     {
         const double4 pj = S.P0[j];
         const double4 vj = S.P1[j];
         const double4 qj = S.P2[j];
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
         const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
-        const double rr = rx * rx + ry * ry + rz * rz;
-        const double r = sqrt(rr);
+        const double rr = r * r;
         const double idist2 = 1.0 / (rr + 0.001 * C.H_sq);
         const double t = wend_t(C, r);
         const double gk = wend_gk(C, r, t);
@@ -707,14 +710,13 @@ __global__ void k_wall_no_slip(Level S, ListView lv, const int* __restrict__ blk
         return;
     const double4 pi = S.P0[i];
     double sxx = 0, syy = 0, szz = 0, ks = 0;
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
     {
         if (!(ent & FJ_NB_FLUID))
             continue;
         const double4 pj = S.P0[j];
         const double4 vj = S.P1[j];
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-        const double r = sqrt(rx * rx + ry * ry + rz * rz);
         const double W = wend_W(C, r, wend_t(C, r));
         ks += W;
         sxx += vj.x * W;
@@ -770,7 +772,7 @@ __global__ void k_wall_pressure(Level S, ListView lv, const int* __restrict__ bl
     const double4 acc = S.ACC[i];
     double ks = 0, pk = 0, akx = 0, aky = 0, akz = 0;
     int near_surface = 0;
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
     {
         if (!(ent & FJ_NB_FLUID))
             continue;
@@ -778,7 +780,6 @@ __global__ void k_wall_pressure(Level S, ListView lv, const int* __restrict__ bl
         const double rho_j = S.P1[j].w;
         const double p_j = S.TH[j].x;
         const double rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-        const double r = sqrt(rx * rx + ry * ry + rz * rz);
         const double kern = pj.w * wend_W(C, r, wend_t(C, r));
         ks += kern;
         pk += p_j * kern;
@@ -810,7 +811,7 @@ __global__ void k_wall_ghost(Level S, ListView lv, const int* __restrict__ blk, 
     const double4 vi = S.P1[i];
     double Rrhoi = 0.0;
     int near_inlet = 1;
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j)
+    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
     {
         const int bj = S.b[j];
         if (bj == FJSPH_PIPE || bj == FJSPH_FREE)
@@ -818,7 +819,6 @@ __global__ void k_wall_ghost(Level S, ListView lv, const int* __restrict__ blk, 
         const double4 pj = S.P0[j];
         const double4 vj = S.P1[j];
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-        const double r = sqrt(rx * rx + ry * ry + rz * rz);
         const double gk = wend_gk(C, r, wend_t(C, r));
         Rrhoi -= pj.w * gk * ((vj.x - vi.x) * rx + (vj.y - vi.y) * ry + (vj.z - vi.z) * rz);
     }
@@ -858,6 +858,7 @@ ListView list_view(FjsphEngine* e)
 {
     ListView v;
     v.nlist = e->nlist;
+    v.nr = e->nr;
     v.ncount = e->ncount;
     v.nb_cap = e->nb_cap;
     return v;
