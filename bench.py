@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the full 3D WCSPH step (BASELINE.json's metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload block|droplet]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one Integrator::integrate (reference src/Integration.cpp:233-303): find_timestep, 2 neighbour
+builds, 2 x (prestep, surface detection, dissipation, shifting), 1 + k force evaluations with Newmark-Beta
+updates and the on-device residual, pn = pnp1.  The workload is config C5 of SURVEY.md 8d (BASELINE.json
+configs[4]): a synthetic 500 x 250 x 100 FREE-particle block per GPU (12.5 M particles, dx = 1 mm, jitter
++-0.1 dx, smooth density / velocity fields), slab-decomposed along x for N > 1.  k is pinned to 4
+sub-iterations (max_subits = 3, min_residual = -30), so one step holds 5 force evaluations.
+
+One JSON line on stdout (rank 0).  `value` times K steps on device-resident state with CUDA events on the
+engine's stream; `e2e` times the same K steps through fjsph_step_host with pinned HOST buffers (upload of
+x, v, acc, rho, Rrho, p, m, b and download of x, v, acc, rho, Rrho, p inside the timed region).  `roofline`
+is the force kernel (get_acc_and_Rrho), `cpu_baseline` the CPU restatement of the reference (oracle/, built
+with the reference's own flags, makefile:16) on this box's host cores.  `--impl reference` times that CPU
+restatement alone: the reference itself cannot be compiled here (Eigen, nanoflann, TECIO, NetCDF and HDF5
+are un-vendored).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec (full 3D WCSPH step incl. neighbour build)"
+UNIT = "particle-steps/s"
+K_SUBITS = 4
+# SURVEY.md 8d, algorithmic (compulsory) HBM bytes and FP64 flops of one force evaluation
+FORCE_BYTES_PER_PARTICLE = 292.0
+FORCE_FLOP_PER_PAIR = 150.0
+STEP_BYTES_PER_PARTICLE = 2120.0 + 444.0 * (1 + K_SUBITS)
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 DFMA/clk x 2 flop x clocks.max.sm
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="block", choices=["block", "droplet"])
+    ap.add_argument("--cells", default="500,250,100", help="block lattice per GPU (x,y,z)")
+    ap.add_argument("--droplet-dx", type=float, default=0.0008)
+    ap.add_argument("--solver", default="newmark_beta", choices=["newmark_beta", "runge_kutta"])
+    ap.add_argument("--cpu-sample", default="64,56,56", help="lattice of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def step_params(args, base):
+    p = dict(base)
+    p.update(delta_t_min=1e-9, frame_time_interval=1e9)
+    if args.solver == "newmark_beta":
+        p.update(solver_type=0, max_subits=K_SUBITS - 1, min_residual=-30.0)
+    else:
+        p.update(solver_type=1)
+    return p
+
+
+def make_case(args, rank=0, cells=None):
+    from fjsph_b200 import cases
+
+    if args.workload == "droplet":
+        return cases.droplet(dx=args.droplet_dx)
+    n = tuple(int(k) for k in (cells or args.cells).split(","))
+    return cases.synthetic_block(n, 1e-3, jitter=0.1, seed=1234, x_offset_cells=rank * n[0])
+
+
+def workload_name(args, world):
+    if args.workload == "droplet":
+        return "Examples/Droplet 3D (para3D), dx=%g" % args.droplet_dx
+    n = [int(k) for k in args.cells.split(",")]
+    return "synthetic 3D block C5, %dx%dx%d = %.2fM FREE particles per GPU, dx=1e-3, jitter 0.1dx%s" % (
+        n[0], n[1], n[2], n[0] * n[1] * n[2] / 1e6, ", slab-decomposed along x" if world > 1 else "")
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                power.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), power_w_max=float(max(power)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(args, steps, warmup, sample_cells):
+    """Times the CPU restatement of the reference step (oracle/, the reference's flags + OpenMP) on a bounded
+    sample of the same workload.  Returns (particle-steps/s, cores, description)."""
+    from oracle import oracle as orc  # bench.py's CPU-baseline leg: the checker timed as the baseline
+
+    subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "lib/liborc3d_fast.so"])
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    case = make_case(args, 0, cells=sample_cells) if args.workload == "block" else make_case(args)
+    params = step_params(args, case["params"])
+    o = orc.Oracle(orc.default_params(3, kind="3d_fast", **params), kind="3d_fast")
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
+    n = case["xi"].shape[0] - case["bound_points"]
+    its = 0
+    for _ in range(warmup):
+        o.integrate()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, st = o.integrate()
+        its = st.iterations
+    dt = time.perf_counter() - t0
+    desc = ("oracle/fjsph_oracle.cpp (-O3 -ffast-math -funroll-loops -fopenmp -march=native), %d threads, %d steps "
+            "after %d warm-up on %s, %d particles, %d sub-iterations" % (
+                cores, steps, warmup, "a %s lattice of the block workload" % sample_cells
+                if args.workload == "block" else "the droplet", n, its))
+    return n * steps / dt, cores, desc, dt / steps * 1e3
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    value, cores, desc, ms = cpu_reference(args, max(1, args.steps), max(1, min(args.warmup, 1)), args.cpu_sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, world), "solver": args.solver,
+                   "force_evals_per_step": 1 + K_SUBITS if args.solver == "newmark_beta" else 4,
+                   "note": "CPU restatement of the reference path on host cores; each step is a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from fjsph_b200 import engine as eng
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    case = make_case(args, rank)
+    params = step_params(args, case["params"])
+    n = case["xi"].shape[0]
+    n_fluid = n - case["bound_points"]
+    stream = torch.cuda.Stream()
+    if world > 1:
+        from fjsph_b200 import slab
+
+        e = slab.SlabEngine(eng.default_params(3, **params), case, rank, world, local_rank, stream)
+    else:
+        e = eng.Engine(eng.default_params(3, **params), n, device=local_rank)
+        e.set_stream(stream.cuda_stream)
+        e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            stats = e.integrate()
+        # ---- timed region: K steps on device-resident state
+        e.timers_reset()
+        e.timers_enable(True)
+        sampler = ClockSampler(local_rank)
+        launches0 = e.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        force_evals = 0
+        for _ in range(args.steps):
+            stats = e.integrate()
+            force_evals += stats.force_evals
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        clocks = sampler.stop()
+        launches = e.launch_count - launches0
+        timers = e.timers()
+        e.timers_enable(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(n_fluid), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    total_fluid = float(cnt[0].item())
+    value = total_fluid * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (force evaluation), measured over the timed region
+    pairs = float(np.sum(e.neighbour_counts() - 1)) if world == 1 else float(e.pair_count())
+    fk = timers.get("force", {"ms": 0.0, "calls": 0})
+    force_ms = fk["ms"] / max(1, fk["calls"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = FORCE_BYTES_PER_PARTICLE * n_fluid / (force_ms * 1e-3) / 1e9 if force_ms > 0 else 0.0
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "force_traffic.json")))
+        traffic = float(tr["dram_bytes_per_particle"]) * n_fluid
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline = {
+        "kernel": "k_force (get_acc_and_Rrho, Resid.cpp:243-469)", "bound": "hbm", "achieved": achieved,
+        "peak": hbm_peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback", "unit": "GB/s",
+        "frac": achieved / hbm_peak, "traffic": traffic, "ms_per_launch": force_ms,
+        "algorithmic_bytes_per_launch": FORCE_BYTES_PER_PARTICLE * n_fluid,
+        "fp64": {"achieved_tflops": FORCE_FLOP_PER_PAIR * pairs / (force_ms * 1e-3) / 1e12 if force_ms > 0 else 0.0,
+                 "nominal_peak_tflops": FP64_NOMINAL_TFLOPS, "flop_per_pair": FORCE_FLOP_PER_PAIR, "pairs": pairs,
+                 "note": "the pair sweeps are FP64-pipe bound (SURVEY.md 8d), the HBM figure is the yardstick north_star names"},
+        "step_hbm_frac": (value / max(1, world)) * STEP_BYTES_PER_PARTICLE / 1e9 / hbm_peak,
+    }
+    total_ms = sum(v["ms"] for v in timers.values())
+    kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                   "share": v["ms"] / total_ms if total_ms > 0 else 0.0} for k, v in sorted(timers.items())}
+
+    # ---- end to end: the same steps through the C-ABI call with pinned HOST buffers
+    e2e = None
+    if not args.no_e2e and world == 1:
+        def pinned(a):
+            t_ = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+            t_.numpy()[...] = a
+            return t_
+
+        st = e.download(("xi", "v", "acc", "rho", "Rrho", "p", "m", "b"))
+        ins_t = {k: pinned(v) for k, v in st.items()}
+        out_fields = ("xi", "v", "acc", "rho", "Rrho", "p")
+        with torch.cuda.stream(stream):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ins = {k: v.numpy() for k, v in ins_t.items()}
+                outs, s2 = e.step_host(ins, case["bound_points"], 1, out_fields=out_fields, out=ins)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        h2d = sum(v.numpy().nbytes for v in ins_t.values())
+        d2h = sum(ins_t[k].numpy().nbytes for k in out_fields)
+        e2e = {"value": n_fluid * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt / args.steps * 1e3}
+    elif not args.no_e2e:
+        e2e = e.e2e(args.steps)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, desc, _ = cpu_reference(args, 2, 1, args.cpu_sample)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "particles_total": int(total_fluid), "solver": args.solver,
+                       "force_evals_per_step": force_evals / args.steps, "neighbour_builds_per_step": 2,
+                       "mean_neighbours": pairs / max(1, n_fluid),
+                       "l2": "inputs larger than L2 (state + neighbour list >> 126 MB), no explicit flush"
+                       if n_fluid > 2_000_000 else "working set may fit L2 (small workload)",
+                       "parallelism": "slab%d" % world if world > 1 else "single"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(cnt[1].item()),
+            "clocks": clocks, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

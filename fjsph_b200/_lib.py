@@ -109,7 +109,8 @@ def lib():
     L.fjsph_step_host.argtypes = [vp, P(FjsphStateView), C.c_int64, C.c_int32, P(FjsphStateView), P(FjsphStepStats)]
     L.fjsph_timers_reset.argtypes = [vp]
     L.fjsph_timers_enable.argtypes = [vp, C.c_int]
-    L.fjsph_timers_get.argtypes = [vp, C.c_int32, vp, vp, vp, P(C.c_int32)]
+    L.fjsph_timers_get.argtypes = [vp, C.c_int32, vp, vp, vp, vp, P(C.c_int32)]
+    L.fjsph_set_stream.argtypes = [vp, vp]
     L.fjsph_launch_count.argtypes = [vp]
     L.fjsph_launch_count.restype = C.c_int64
     L.fjsph_set_owned.argtypes = [vp, C.c_int64]

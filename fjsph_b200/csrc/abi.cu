@@ -41,17 +41,45 @@ KScope::KScope(FjsphEngine* e_, const char* name, int launches) : e(e_), id(-1)
         id = int(e->timers.size()) - 1;
     }
     e->timers[id].launches += launches;
-    cudaEventRecord(e->ev0, e->stream);
+    e->timers[id].calls += 1;
+    PendingTiming pt;
+    pt.id = id;
+    for (cudaEvent_t* ev : {&pt.a, &pt.b})
+    {
+        if (e->event_pool.empty())
+            cudaEventCreate(ev);
+        else
+        {
+            *ev = e->event_pool.back();
+            e->event_pool.pop_back();
+        }
+    }
+    cudaEventRecord(pt.a, e->stream);
+    e->pending.push_back(pt);
 }
 KScope::~KScope()
 {
     if (id < 0)
         return;
-    cudaEventRecord(e->ev1, e->stream);
-    cudaEventSynchronize(e->ev1);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-    e->timers[id].ms += ms;
+    cudaEventRecord(e->pending.back().b, e->stream);
+    if (e->pending.size() >= 4096)
+        fj_timers_flush(e);
+}
+// resolve the recorded event pairs into per-family milliseconds (one synchronisation for all of them)
+void fj_timers_flush(FjsphEngine* e)
+{
+    if (e->pending.empty())
+        return;
+    cudaEventSynchronize(e->pending.back().b);
+    for (const PendingTiming& pt : e->pending)
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pt.a, pt.b) == cudaSuccess && pt.id < int(e->timers.size()))
+            e->timers[pt.id].ms += ms;
+        e->event_pool.push_back(pt.a);
+        e->event_pool.push_back(pt.b);
+    }
+    e->pending.clear();
 }
 
 // ------------------------------------------------------------------ constants
@@ -692,7 +720,10 @@ int fjsph_destroy(FjsphEngine* e)
         cudaFreeHost(e->h_flag);
     cudaEventDestroy(e->ev0);
     cudaEventDestroy(e->ev1);
-    cudaStreamDestroy(e->stream);
+    fj_timers_flush(e);
+    for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->own_stream)
+        cudaStreamDestroy(e->stream);
     delete e;
     return FJSPH_OK;
 }
@@ -1022,27 +1053,54 @@ int fjsph_step_host(FjsphEngine* e, const FjsphStateView* in, int64_t bound_poin
 
 int fjsph_timers_reset(FjsphEngine* e)
 {
+    fj_timers_flush(e);
     e->timers.clear();
     return FJSPH_OK;
 }
 int fjsph_timers_enable(FjsphEngine* e, int on)
 {
+    fj_timers_flush(e);
     e->timers_on = on != 0;
     return FJSPH_OK;
 }
-int fjsph_timers_get(FjsphEngine* e, int32_t cap, char* names, double* ms, int64_t* launches, int32_t* n_out)
+int fjsph_timers_get(FjsphEngine* e, int32_t cap, char* names, double* ms, int64_t* launches, int64_t* calls,
+                     int32_t* n_out)
 {
+    cudaSetDevice(e->device);
+    fj_timers_flush(e);
     const int n = std::min<int>(cap, int(e->timers.size()));
     for (int k = 0; k < n; ++k)
     {
         std::snprintf(names + size_t(k) * 32, 32, "%s", e->timers[k].name.c_str());
         ms[k] = e->timers[k].ms;
         launches[k] = e->timers[k].launches;
+        if (calls)
+            calls[k] = e->timers[k].calls;
     }
     *n_out = n;
     return FJSPH_OK;
 }
 int64_t fjsph_launch_count(FjsphEngine* e) { return e->launches; }
+
+int fjsph_set_stream(FjsphEngine* e, void* cuda_stream)
+{
+    cudaSetDevice(e->device);
+    fj_timers_flush(e);
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->own_stream && e->stream)
+        cudaStreamDestroy(e->stream);
+    if (cuda_stream)
+    {
+        e->stream = (cudaStream_t)cuda_stream;
+        e->own_stream = false;
+    }
+    else
+    {
+        FJ_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->own_stream = true;
+    }
+    return FJSPH_OK;
+}
 
 int fjsph_set_owned(FjsphEngine* e, int64_t n_owned)
 {

@@ -77,6 +77,12 @@ struct Timer
     std::string name;
     double ms = 0.0;
     long long launches = 0;
+    long long calls = 0; // timed scopes (one force evaluation = one call)
+};
+struct PendingTiming
+{
+    int id;
+    cudaEvent_t a, b;
 };
 
 struct FjsphEngine
@@ -85,6 +91,7 @@ struct FjsphEngine
     DevConst C;
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     int64_t cap = 0;          // particle capacity
     int64_t n = 0;            // particles held (owned + ghosts)
     int64_t n_owned = 0;
@@ -146,6 +153,8 @@ struct FjsphEngine
     // instrumentation
     bool timers_on = false;
     std::vector<Timer> timers;
+    std::vector<PendingTiming> pending;   // event pairs recorded on the stream, resolved lazily (no sync per kernel)
+    std::vector<cudaEvent_t> event_pool;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long launches = 0;
     int force_evals = 0, nb_builds = 0;
@@ -189,3 +198,4 @@ int fj_copy_level(FjsphEngine* e, int dst, int src);
 int fj_permute_levels(FjsphEngine* e);
 int fj_reduce_sum(FjsphEngine* e, int nblocks, int ncomp, double* out_host);
 void fj_refresh_constants(FjsphEngine* e);
+void fj_timers_flush(FjsphEngine* e);

@@ -257,11 +257,14 @@ class Engine:
         check(self._L.fjsph_step(self._h, C.byref(s)))
         return s
 
-    def step_host(self, inputs: dict, bound_points: int, n_steps: int, out_fields=("xi", "v", "rho", "p")):
-        """End-to-end call with HOST buffers: upload -> n_steps x integrate -> download."""
+    def step_host(self, inputs: dict, bound_points: int, n_steps: int, out_fields=("xi", "v", "rho", "p"),
+                  out: dict | None = None):
+        """End-to-end call with HOST buffers: upload -> n_steps x integrate -> download.  `out` may supply
+        preallocated (e.g. pinned) result arrays; they may alias the inputs."""
         n = np.asarray(inputs["xi"]).shape[0]
         vin, k1 = make_view(dict(inputs), n)
-        outs = {f: np.empty(_shape_of(f, n), dtype=_dtype_of(f)) for f in out_fields}
+        outs = {f: (out[f] if out is not None and f in out else np.empty(_shape_of(f, n), dtype=_dtype_of(f)))
+                for f in out_fields}
         vout, k2 = make_view(outs, n)
         s = FjsphStepStats()
         check(self._L.fjsph_step_host(self._h, C.byref(vin), int(bound_points), int(n_steps), C.byref(vout), C.byref(s)))
@@ -279,13 +282,18 @@ class Engine:
         names = C.create_string_buffer(cap * 32)
         ms = (C.c_double * cap)()
         launches = (C.c_int64 * cap)()
+        calls = (C.c_int64 * cap)()
         n = C.c_int32()
-        check(self._L.fjsph_timers_get(self._h, cap, names, ms, launches, C.byref(n)))
+        check(self._L.fjsph_timers_get(self._h, cap, names, ms, launches, calls, C.byref(n)))
         out = {}
         for k in range(n.value):
             nm = names.raw[k * 32:(k + 1) * 32].split(b"\0", 1)[0].decode()
-            out[nm] = dict(ms=ms[k], launches=int(launches[k]))
+            out[nm] = dict(ms=ms[k], launches=int(launches[k]), calls=int(calls[k]))
         return out
+
+    def set_stream(self, cuda_stream: int | None):
+        """Run on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(self._L.fjsph_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
     @property
     def launch_count(self) -> int:

@@ -163,8 +163,13 @@ int fjsph_step_host(FjsphEngine* e, const FjsphStateView* in, int64_t bound_poin
 int fjsph_timers_reset(FjsphEngine* e);
 int fjsph_timers_enable(FjsphEngine* e, int on);
 int fjsph_timers_get(FjsphEngine* e, int32_t cap, char* names /* cap x 32 */, double* ms, int64_t* launches,
-                     int32_t* n_out);
+                     int64_t* calls /* timed scopes, may be NULL */, int32_t* n_out);
 int64_t fjsph_launch_count(FjsphEngine* e);
+
+/* Run on the caller's CUDA stream (a cudaStream_t, e.g. the host framework's current stream) instead of the
+ * engine's own; NULL goes back to a private stream.  The reference is single-threaded host code with no notion
+ * of streams (FJSPH.cpp:262-283); this is what lets a host time or order the engine with its own events. */
+int fjsph_set_stream(FjsphEngine* e, void* cuda_stream);
 
 /* Slab decomposition: ghost particles are appended by the caller's exchange layer.
  * The engine packs / unpacks halo records on the device; the transport (NCCL send/recv) lives in the
