@@ -1,5 +1,5 @@
 import numpy as np, sys
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fjsph_b200 import cases, engine as eng
 from oracle import oracle as orc
 from tests.util import relerr

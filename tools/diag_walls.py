@@ -1,5 +1,5 @@
 import numpy as np, sys
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fjsph_b200 import cases
 from tests.util import relerr, make_pair
 F = ("xi","v","rho","p","acc","Rrho","aVisc","deltaD","vPert","lam","lam_nb","norm","curve","surf","surfzone","gradRho","L","colour","kernsum")
