@@ -947,9 +947,8 @@ int fjsph_get_neighbours(FjsphEngine* e, const int64_t* offsets, int64_t* idx)
     {
         const int64_t c = oidx[i];
         int64_t* dst = idx + offsets[c];
-        const size_t base = (i >> 5) * size_t(e->nb_cap) * 32u + (i & 31);
         int k = 0;
-        for (; k < cnt[i]; ++k) dst[k] = oidx[list[base + size_t(k) * 32u] & FJ_IDX_MASK];
+        for (; k < cnt[i]; ++k) dst[k] = oidx[list[FJ_LIST_WORD(i, k, e->nb_cap)] & FJ_IDX_MASK];
         dst[k++] = c;
         if (offsets[c + 1] - offsets[c] != k)
         {

@@ -23,6 +23,9 @@
 #define FJ_IDX_MASK 0x0FFFFFFFu
 #define FJ_NB_FLUID 0x80000000u /* neighbour j has b > PISTON (VarDefs.h:92-102) */
 #define FJ_NB_BOUND 0x40000000u /* neighbour j has b == BOUND */
+/* word index of slot s of particle i in the chunked ELL list (nb_cap slots per particle, a multiple of 4) */
+#define FJ_LIST_WORD(i, s, nb_cap) \
+    ((((size_t((i) >> 5) * size_t((nb_cap) >> 2) + size_t((s) >> 2)) * 32u + size_t((i)&31)) << 2) + size_t((s)&3))
 
 // X(type, name): every per-particle array of one time level
 #define FJ_LEVEL_FIELDS(X)                                                                                     \
@@ -118,7 +121,10 @@ struct FjsphEngine
     size_t key_cap = 0;
     unsigned int *mtab_x = nullptr, *mtab_y = nullptr, *mtab_z = nullptr; // Morton spread tables
     int mtab_cap = 0;
-    unsigned int* nlist = nullptr;      // warp-transposed ELL: [(warp*nb_cap + s)*32 + lane]
+    // chunked warp-transposed ELL: slots come in chunks of 4 per lane; chunk c of lane l of warp w is element
+    // (w*nchunk + c)*32 + l of a uint4 array (indices + flag bits) and of a double4 array (frozen r), so a lane
+    // reads 4 slots with one 128-bit + one 256-bit load and a warp's loads are contiguous (512 B / 1 KB).
+    unsigned int* nlist = nullptr;      // slot s of particle i at FJ_LIST_WORD(i, s, nb_cap)
     double* nr = nullptr;               // same layout: r = sqrt(d^2) at list-build time (OUTL's .second, frozen)
     int* ncount = nullptr;              // [cap] neighbours excluding self
     int* near_inlet = nullptr;          // [cap] Boundary_Ghost flag, valid within one sub-iteration

@@ -292,8 +292,12 @@ __global__ void __launch_bounds__(TPB)
     const double4 a = P0[i];
     int cx, cy, cz;
     cell_of(g, a.x, a.y, a.z, cx, cy, cz);
-    unsigned* __restrict__ dst = nlist + (size_t(i >> 5) * size_t(nb_cap)) * 32u + (i & 31);
-    double* __restrict__ rdst = nr + (size_t(i >> 5) * size_t(nb_cap)) * 32u + (i & 31);
+    /* chunk c of this lane: one uint4 + one double4, written whole (full 16 B / 32 B sectors per lane) */
+    const size_t base = (size_t(i >> 5) * size_t(nb_cap >> 2)) * 32u + (i & 31);
+    uint4* __restrict__ dst = reinterpret_cast<uint4*>(nlist) + base;
+    double4* __restrict__ rdst = reinterpret_cast<double4*>(nr) + base;
+    unsigned eb[4] = {unsigned(i), unsigned(i), unsigned(i), unsigned(i)};
+    double rb[4] = {0.0, 0.0, 0.0, 0.0};
     int cnt = 0;
     for (int dz = -1; dz <= 1; ++dz)
     {
@@ -323,22 +327,37 @@ __global__ void __launch_bounds__(TPB)
                         __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
                     if (d2 < sr && int(j) != i)
                     {
-                        if (cnt < nb_cap)
+                        const int bj = b[j];
+                        unsigned ent = j;
+                        if (bj > FJSPH_PISTON)
+                            ent |= FJ_NB_FLUID;
+                        if (bj == FJSPH_BOUND)
+                            ent |= FJ_NB_BOUND;
+                        const double rv = sqrt(d2); /* r = sqrt(jj.second), as every pair loop takes it */
+                        const int kk = cnt & 3;
+                        /* static register indexing only */
+                        if (kk == 0) { eb[0] = ent; rb[0] = rv; }
+                        else if (kk == 1) { eb[1] = ent; rb[1] = rv; }
+                        else if (kk == 2) { eb[2] = ent; rb[2] = rv; }
+                        else
                         {
-                            const int bj = b[j];
-                            unsigned ent = j;
-                            if (bj > FJSPH_PISTON)
-                                ent |= FJ_NB_FLUID;
-                            if (bj == FJSPH_BOUND)
-                                ent |= FJ_NB_BOUND;
-                            dst[size_t(cnt) * 32u] = ent;
-                            rdst[size_t(cnt) * 32u] = sqrt(d2); /* r = sqrt(jj.second), as every pair loop takes it */
+                            if (cnt < nb_cap)
+                            {
+                                dst[size_t(cnt >> 2) * 32u] = make_uint4(eb[0], eb[1], eb[2], ent);
+                                rdst[size_t(cnt >> 2) * 32u] = make_double4(rb[0], rb[1], rb[2], rv);
+                            }
                         }
                         cnt++;
                     }
                 }
             }
         }
+    }
+    if ((cnt & 3) && cnt < nb_cap)
+    {
+        /* partial last chunk; unused slots are never read (sweeps stop at ncount) */
+        dst[size_t(cnt >> 2) * 32u] = make_uint4(eb[0], eb[1], eb[2], unsigned(i));
+        rdst[size_t(cnt >> 2) * 32u] = make_double4(rb[0], rb[1], rb[2], 0.0);
     }
     ncount[i] = cnt;
     if (cnt > nb_cap)

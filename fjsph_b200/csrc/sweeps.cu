@@ -33,15 +33,81 @@ struct ListView
 // The reference carries d^2 in the neighbour list (OUTL = vector<vector<pair<idx, dist2>>>, Var.h:889-890) and
 // every pair loop reads r = sqrt(jj.second) from it, so r stays FROZEN at its list-build value while
 // Rji = xj - xi follows the positions through the Newmark-Beta sub-iterations / RK stages.  The list
-// therefore stores r next to the index (same warp-transposed layout, one 256-byte load per warp and slot).
-#define FJ_FOR_NEIGHBOURS(i, LV, ent, j, r)                                                                \
-    const size_t _lb = (size_t((i) >> 5) * size_t((LV).nb_cap)) * 32u + ((i)&31);                          \
-    const unsigned* __restrict__ _lp = (LV).nlist + _lb;                                                   \
-    const double* __restrict__ _rp = (LV).nr + _lb;                                                        \
-    const int _cnt = (LV).ncount[i];                                                                       \
-    for (int _s = 0; _s < _cnt; ++_s)                                                                      \
-        for (double r = _rp[size_t(_s) * 32u]; r >= 0.0; r = -1.0)                                         \
-            for (unsigned ent = _lp[size_t(_s) * 32u], j = ent & FJ_IDX_MASK, _once = 1; _once; _once = 0)
+// therefore stores r next to the index, in chunks of 4 slots per lane (engine.cuh).
+__device__ __forceinline__ uint4 ld_list_idx(const uint4* p)
+{
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double4 ld_list_r(const double4* p)
+{
+    double4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+// 32-byte record gather with ONE 256-bit load (LDG.E.256): half the L1 wavefronts of two 128-bit loads.
+// Only for arrays no thread writes during the kernel (read-only path).
+__device__ __forceinline__ double4 gather(const double4* __restrict__ base, unsigned j)
+{
+    double4 v;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(base + j));
+    return v;
+}
+// same, through the coherent path: for arrays some thread of the SAME kernel updates (its own record only)
+__device__ __forceinline__ double4 gather_rw(const double4* base, unsigned j)
+{
+    double4 v;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(base + j) : "memory");
+    return v;
+}
+
+template <class Body>
+__device__ __forceinline__ void for_neighbours(const ListView& lv, int i, Body&& body)
+{
+    const size_t base = (size_t(i >> 5) * size_t(lv.nb_cap >> 2)) * 32u + (i & 31);
+    const uint4* __restrict__ lp = reinterpret_cast<const uint4*>(lv.nlist) + base;
+    const double4* __restrict__ rp = reinterpret_cast<const double4*>(lv.nr) + base;
+    const int cnt = lv.ncount[i];
+    const int nchunk = (cnt + 3) >> 2;
+    if (nchunk == 0)
+        return;
+    uint4 id = ld_list_idx(lp);
+    double4 rr = ld_list_r(rp);
+    for (int c = 0; c < nchunk; ++c)
+    {
+        /* next chunk in flight while this one is processed (the list streams from HBM) */
+        uint4 idn = id;
+        double4 rn = rr;
+        if (c + 1 < nchunk)
+        {
+            idn = ld_list_idx(lp + size_t(c + 1) * 32u);
+            rn = ld_list_r(rp + size_t(c + 1) * 32u);
+        }
+        const int left = cnt - (c << 2);
+        if (left >= 4)
+        {
+            body(id.x, rr.x);
+            body(id.y, rr.y);
+            body(id.z, rr.z);
+            body(id.w, rr.w);
+        }
+        else
+        {
+            body(id.x, rr.x);
+            if (left > 1)
+                body(id.y, rr.y);
+            if (left > 2)
+                body(id.z, rr.z);
+        }
+        id = idn;
+        rr = rn;
+    }
+}
+#define FJ_NEIGHBOURS_BEGIN(i, LV, ent, j, r)                          \
+    for_neighbours(LV, i, [&](const unsigned ent, const double r) {    \
+        const unsigned j = ent & FJ_IDX_MASK;
+#define FJ_NEIGHBOURS_END });
 
 // Wendland C2 (Kernel.h:37-61).  t = 1 - q/2.  W = t^4 (2q+1) Wc ; GradK(R, r) = R * gk with
 // gk = 5 Wc/H^2 * t^3, and 0 when r/H < 1e-12.
@@ -86,9 +152,8 @@ __global__ void __launch_bounds__(TPB)
         double g0 = 0, g1 = 0, g2 = 0, m0 = 0, m1 = 0, m2 = 0;
         double kernsum = C.W_correc; /* self term, Shifting.cpp:39-45 */
         double colour = 0.0;
-        FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
-        {
-            const double4 pj = S.P0[j];
+        FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
+            const double4 pj = gather(S.P0, j);
             const double rho_j = S.P1[j].w;
             const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
             const double rr = r * r;
@@ -122,7 +187,7 @@ __global__ void __launch_bounds__(TPB)
                 colour += pj.w * W;
                 npd_ += W;
             }
-        }
+        FJ_NEIGHBOURS_END
         double Lm[3][3] = {{l00, l01, l02}, {l01, l11, l12}, {l02, l12, l22}};
         double Li[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
         double tmp[3][3];
@@ -242,10 +307,9 @@ __global__ void __launch_bounds__(TPB)
     double avx = 0, avy = 0, avz = 0, Rrhod = 0;
     const double cos_pi4 = 0.70710678118654757;
 
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
-    {
-        const double4 pj = S.P0[j];
-        const double4 gj = S.P3[j];
+    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
+        const double4 pj = gather(S.P0, j);
+        const double4 gj = gather(S.P3, j);
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
         const double rr = r * r;
         const double t = wend_t(C, r);
@@ -278,7 +342,7 @@ __global__ void __launch_bounds__(TPB)
         }
         if (DISS)
         {
-            const double4 vj = S.P1[j];
+            const double4 vj = gather(S.P1, j);
             const double rho_j = vj.w;
             const double idist2 = 1.0 / (rr + 0.0001 * C.H_sq);
             const double rdg = rr * gk; /* Rji . gradK */
@@ -304,7 +368,7 @@ __global__ void __launch_bounds__(TPB)
                 Rrhod += pj.w * (rho_j - rho_i) * rdg * idist2;
             }
         }
-    }
+    FJ_NEIGHBOURS_END
     if (SURF)
     {
         const double tx = S.L0[i] * nx + S.L1[i] * ny + S.L2[i] * nz;
@@ -379,15 +443,14 @@ __global__ void __launch_bounds__(TPB)
     /* woccl is overwritten with 1 when lam_nb >= lam_cutoff, so the occlusion max is only needed below it */
     const bool need_occl = occl && (lam_nb < C.lam_cutoff);
 
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
-    {
-        const double4 nj = S.P4[j];
+    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
+        const double4 nj = gather(S.P4, j);
         if (nj.w != 0.0)
             zone = 1;
         const bool curv = ni_nz && ((nj.x * nj.x + nj.y * nj.y + nj.z * nj.z) > 0.0);
         if (curv || need_occl)
         {
-            const double4 pj = S.P0[j];
+            const double4 pj = gather(S.P0, j);
             const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
             const double rr = r * r;
             if (curv)
@@ -408,7 +471,7 @@ __global__ void __launch_bounds__(TPB)
                     woccl_ = frac;
             }
         }
-    }
+    FJ_NEIGHBOURS_END
     double4 th = S.TH[i];
     th.z = (lam_nb < C.lam_cutoff) ? fmax(0.0, fmin(woccl_, 1.0)) : 1.0;
     S.TH[i] = th;
@@ -461,10 +524,9 @@ __global__ void __launch_bounds__(TPB)
     double dux = 0, duy = 0, duz = 0, maxU2 = 0.0;
     /* max_j acos(c_j) over c_j in [-1,1] == acos(min_j c_j); NaNs (|c|>1) are skipped by the reference's '>' */
     double min_c = 2.0;
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
-    {
-        const double4 pj = S.P0[j];
-        const double4 vj = S.P1[j];
+    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
+        const double4 pj = gather(S.P0, j);
+        const double4 vj = gather(S.P1, j);
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
         const double rr = r * r;
         const double t = wend_t(C, r);
@@ -478,7 +540,7 @@ __global__ void __launch_bounds__(TPB)
         duz += f * rz;
         if (!bulk && (ent & FJ_NB_FLUID))
         {
-            const double4 nj = S.P4[j];
+            const double4 nj = gather(S.P4, j);
             const double nn = nj.x * nj.x + nj.y * nj.y + nj.z * nj.z;
             const double inv = (nn > 0.0) ? 1.0 / sqrt(nn) : 1.0;
             const double c = (nhx * nj.x + nhy * nj.y + nhz * nj.z) * inv;
@@ -487,7 +549,7 @@ __global__ void __launch_bounds__(TPB)
         }
         const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
         maxU2 = fmax(maxU2, ux * ux + uy * uy + uz * uz);
-    }
+    FJ_NEIGHBOURS_END
     const double vnorm = sqrt(vi.x * vi.x + vi.y * vi.y + vi.z * vi.z);
     const double sc = -2.0 * C.H * vnorm;
     dux *= sc;
@@ -609,11 +671,10 @@ __global__ void __launch_bounds__(TPB)
         af.x = af.y = af.z = 0.0; /* CalcAeroAcc default branch returns zero */
     }
 
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
-    {
-        const double4 pj = S.P0[j];
-        const double4 vj = S.P1[j];
-        const double4 qj = S.P2[j];
+    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
+        const double4 pj = gather(S.P0, j);
+        const double4 vj = gather(S.P1, j);
+        const double4 qj = gather(S.P2, j);
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
         const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
         const double rr = r * r;
@@ -659,7 +720,7 @@ __global__ void __launch_bounds__(TPB)
         {
             Rrho_ -= V_j * (ux * gx + uy * gy + uz * gz);
         }
-    }
+    FJ_NEIGHBOURS_END
     if (S.internal[i] == 1)
     {
         /* NormalBoundaryRepulsion, Kernel.h:64-75,272-277 */
@@ -710,19 +771,18 @@ __global__ void k_wall_no_slip(Level S, ListView lv, const int* __restrict__ blk
         return;
     const double4 pi = S.P0[i];
     double sxx = 0, syy = 0, szz = 0, ks = 0;
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
-    {
+    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
         if (!(ent & FJ_NB_FLUID))
-            continue;
-        const double4 pj = S.P0[j];
-        const double4 vj = S.P1[j];
+            return;
+        const double4 pj = gather_rw(S.P0, j);
+        const double4 vj = gather_rw(S.P1, j);
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
         const double W = wend_W(C, r, wend_t(C, r));
         ks += W;
         sxx += vj.x * W;
         syy += vj.y * W;
         szz += vj.z * W;
-    }
+    FJ_NEIGHBOURS_END
     if (ks > 0.0)
     {
         double4 v = S.P1[i];
@@ -772,11 +832,10 @@ __global__ void k_wall_pressure(Level S, ListView lv, const int* __restrict__ bl
     const double4 acc = S.ACC[i];
     double ks = 0, pk = 0, akx = 0, aky = 0, akz = 0;
     int near_surface = 0;
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
-    {
+    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
         if (!(ent & FJ_NB_FLUID))
-            continue;
-        const double4 pj = S.P0[j];
+            return;
+        const double4 pj = gather_rw(S.P0, j);
         const double rho_j = S.P1[j].w;
         const double p_j = S.TH[j].x;
         const double rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
@@ -789,7 +848,7 @@ __global__ void k_wall_pressure(Level S, ListView lv, const int* __restrict__ bl
         akz += kr * rz;
         if (S.surfzone[j])
             near_surface = 1;
-    }
+    FJ_NEIGHBOURS_END
     double p = 0.0;
     if (ks > 0.0)
     {
@@ -811,17 +870,16 @@ __global__ void k_wall_ghost(Level S, ListView lv, const int* __restrict__ blk, 
     const double4 vi = S.P1[i];
     double Rrhoi = 0.0;
     int near_inlet = 1;
-    FJ_FOR_NEIGHBOURS(i, lv, ent, j, r)
-    {
+    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
         const int bj = S.b[j];
         if (bj == FJSPH_PIPE || bj == FJSPH_FREE)
             near_inlet = 0;
-        const double4 pj = S.P0[j];
-        const double4 vj = S.P1[j];
+        const double4 pj = gather_rw(S.P0, j);
+        const double4 vj = gather_rw(S.P1, j);
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
         const double gk = wend_gk(C, r, wend_t(C, r));
         Rrhoi -= pj.w * gk * ((vj.x - vi.x) * rx + (vj.y - vi.y) * ry + (vj.z - vi.z) * rz);
-    }
+    FJ_NEIGHBOURS_END
     double4 acc = S.ACC[i];
     acc.w = Rrhoi * vi.w;
     S.ACC[i] = acc;
