@@ -10,7 +10,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)
 HEADER = os.path.join(ROOT, "include", "fjsph_b200.h")
-LIB_PATH = os.path.join(_PKG, "lib", "libfjsph_b200.so")
+LIB_PATH = os.environ.get("FJSPH_B200_LIB") or os.path.join(_PKG, "lib", "libfjsph_b200.so")
 
 
 def struct_from_header(name: str, header: str = HEADER):

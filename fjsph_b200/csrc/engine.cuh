@@ -191,7 +191,7 @@ static inline int fj_blocks(int64_t n, int threads) { return (int)((n + threads 
 int fj_build_neighbours(FjsphEngine* e);
 int fj_prestep(FjsphEngine* e, double* npd);
 int fj_aero_velocity(FjsphEngine* e);
-int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipation);
+int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipation, bool fuse_shift = false);
 int fj_shift(FjsphEngine* e);
 int fj_check_pipe_outlet(FjsphEngine* e);
 int fj_forces(FjsphEngine* e, int level_idx, double npd);

@@ -553,10 +553,7 @@ static int frozen_terms(FjsphEngine* e, bool all)
     st = fj_aero_velocity(e);
     if (st)
         return st;
-    st = fj_surface_and_dissipation(e, true, true);
-    if (st)
-        return st;
-    st = fj_shift(e);
+    st = fj_surface_and_dissipation(e, true, true, true); /* loops 2+3 fused with particle_shift (ALE) */
     if (st)
         return st;
     return fj_check_pipe_outlet(e);

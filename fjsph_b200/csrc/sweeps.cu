@@ -109,6 +109,73 @@ __device__ __forceinline__ void for_neighbours(const ListView& lv, int i, Body&&
         const unsigned j = ent & FJ_IDX_MASK;
 #define FJ_NEIGHBOURS_END });
 
+// Software-pipelined form for the hot sweeps: load(ent) issues the record gathers of one neighbour and
+// returns them; body(ent, r, rec) consumes them.  The gathers of neighbour k+1 are issued before the
+// arithmetic of neighbour k, and the next list chunk one chunk ahead, so every warp always has one
+// neighbour's records and one chunk of the list in flight behind its FP64 work.  Unused slots of the
+// last chunk hold the particle's own index (safe to gather, never consumed).
+template <class Load, class Body>
+__device__ __forceinline__ void for_neighbours_pipelined(const ListView& lv, int i, Load&& load, Body&& body)
+{
+    const size_t base = (size_t(i >> 5) * size_t(lv.nb_cap >> 2)) * 32u + (i & 31);
+    const uint4* __restrict__ lp = reinterpret_cast<const uint4*>(lv.nlist) + base;
+    const double4* __restrict__ rp = reinterpret_cast<const double4*>(lv.nr) + base;
+    const int cnt = lv.ncount[i];
+    const int nchunk = (cnt + 3) >> 2;
+    if (nchunk == 0)
+        return;
+    uint4 id = ld_list_idx(lp);
+    double4 rr = ld_list_r(rp);
+    auto cur = load(id.x);
+    for (int c = 0; c < nchunk; ++c)
+    {
+        uint4 idn = id;
+        double4 rn = rr;
+        if (c + 1 < nchunk)
+        {
+            idn = ld_list_idx(lp + size_t(c + 1) * 32u);
+            rn = ld_list_r(rp + size_t(c + 1) * 32u);
+        }
+        const int left = cnt - (c << 2);
+        auto nx = load(id.y);
+        body(id.x, rr.x, cur);
+        cur = load(id.z);
+        if (left > 1)
+            body(id.y, rr.y, nx);
+        nx = load(id.w);
+        if (left > 2)
+            body(id.z, rr.z, cur);
+        cur = load(idn.x);
+        if (left > 3)
+            body(id.w, rr.w, nx);
+        id = idn;
+        rr = rn;
+    }
+}
+
+// 1/x for positive normal x without the IEEE-division slow path: MUFU.RCP64H seed + two Newton steps
+// (relative error ~1 ulp; the parity bar is 1e-10).
+__device__ __forceinline__ double fj_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+// 1/sqrt(x) for positive normal x: MUFU.RSQ64H seed + two Newton steps
+__device__ __forceinline__ double fj_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    return fma(y, e, y);
+}
+
 // Wendland C2 (Kernel.h:37-61).  t = 1 - q/2.  W = t^4 (2q+1) Wc ; GradK(R, r) = R * gk with
 // gk = 5 Wc/H^2 * t^3, and 0 when r/H < 1e-12.
 __device__ __forceinline__ double wend_t(const DevConst& C, double r) { return 1.0 - 0.5 * r * C.iH; }
@@ -137,7 +204,13 @@ __device__ __forceinline__ double block_sum(double v, double* sm)
 }
 
 // ================================================================= dSPH_PreStep
-__global__ void __launch_bounds__(TPB)
+struct RecPre
+{
+    double4 p;
+    double rho;
+};
+
+__global__ void __launch_bounds__(TPB, 3)
     k_prestep(Level S, ListView lv, DevConst C, int n, double* __restrict__ npd_partial)
 {
     __shared__ double sm[TPB / 32];
@@ -152,42 +225,49 @@ __global__ void __launch_bounds__(TPB)
         double g0 = 0, g1 = 0, g2 = 0, m0 = 0, m1 = 0, m2 = 0;
         double kernsum = C.W_correc; /* self term, Shifting.cpp:39-45 */
         double colour = 0.0;
-        FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
-            const double4 pj = gather(S.P0, j);
-            const double rho_j = S.P1[j].w;
-            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-            const double rr = r * r;
-            const double t = wend_t(C, r);
-            const double vg = pj.w * wend_gk(C, r, t); /* V_j * gk ; Grad = GradK(-Rji) = -Rji*gk */
-            const double ax = vg * rx, ay = vg * ry, az = vg * rz;
-            /* Lmat -= V Rji (x) Grad  ==  += V gk Rji (x) Rji */
-            l00 += ax * rx;
-            l01 += ax * ry;
-            l02 += ax * rz;
-            l11 += ay * ry;
-            l12 += ay * rz;
-            l22 += az * rz;
-            const double dr = rho_j - rho_i;
-            g0 -= dr * ax;
-            g1 -= dr * ay;
-            g2 -= dr * az;
-            if (ent & FJ_NB_FLUID)
-            {
-                n00 += ax * rx;
-                n01 += ax * ry;
-                n02 += ax * rz;
-                n11 += ay * ry;
-                n12 += ay * rz;
-                n22 += az * rz;
-                m0 -= ax;
-                m1 -= ay;
-                m2 -= az;
-                const double W = wend_W(C, r, t);
-                kernsum += W;
-                colour += pj.w * W;
-                npd_ += W;
-            }
-        FJ_NEIGHBOURS_END
+        for_neighbours_pipelined(
+            lv, i,
+            [&](const unsigned ent) {
+                const unsigned j = ent & FJ_IDX_MASK;
+                RecPre q;
+                q.p = gather(S.P0, j);
+                q.rho = __ldg(&S.P1[j].w);
+                return q;
+            },
+            [&](const unsigned ent, const double r, const RecPre& q) {
+                const double4 pj = q.p;
+                const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+                const double t = wend_t(C, r);
+                const double vg = pj.w * wend_gk(C, r, t); /* V_j * gk ; Grad = GradK(-Rji) = -Rji*gk */
+                const double ax = vg * rx, ay = vg * ry, az = vg * rz;
+                /* Lmat -= V Rji (x) Grad  ==  += V gk Rji (x) Rji */
+                l00 += ax * rx;
+                l01 += ax * ry;
+                l02 += ax * rz;
+                l11 += ay * ry;
+                l12 += ay * rz;
+                l22 += az * rz;
+                const double dr = q.rho - rho_i;
+                g0 -= dr * ax;
+                g1 -= dr * ay;
+                g2 -= dr * az;
+                if (ent & FJ_NB_FLUID)
+                {
+                    n00 += ax * rx;
+                    n01 += ax * ry;
+                    n02 += ax * rz;
+                    n11 += ay * ry;
+                    n12 += ay * rz;
+                    n22 += az * rz;
+                    m0 -= ax;
+                    m1 -= ay;
+                    m2 -= az;
+                    const double W = wend_W(C, r, t);
+                    kernsum += W;
+                    colour += pj.w * W;
+                    npd_ += W;
+                }
+            });
         double Lm[3][3] = {{l00, l01, l02}, {l01, l11, l12}, {l02, l12, l22}};
         double Li[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
         double tmp[3][3];
@@ -261,8 +341,13 @@ __global__ void k_aero_velocity(Level S, const int* __restrict__ ncount, const i
 }
 
 // ================================================================= Detect_Surface loop 1 + dissipation_terms
+struct RecS1
+{
+    double4 p, g, v;
+};
+
 template <bool SURF, bool DISS>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, 3)
     k_surf1_diss(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -302,73 +387,86 @@ __global__ void __launch_bounds__(TPB)
         }
     }
     const bool hi_lam = lam_i > 0.7;
+    const double lam_ref = hi_lam ? lam_i : 0.0;
+    /* cbar = (sqrt(B gam / rho_i) + sqrt(B gam / rho_j)) / 2, Kernel.h:217-244 */
+    const double sqrt_Bgam = sqrt(C.Bgam);
     const double cs_i = DISS ? sqrt(C.Bgam / rho_i) : 0.0;
+    const double eps_d = 0.0001 * C.H_sq; /* Q3: 0.0001 here, 0.001 in the force loop */
     double nx = 0, ny = 0, nz = 0;
     double avx = 0, avy = 0, avz = 0, Rrhod = 0;
     const double cos_pi4 = 0.70710678118654757;
 
-    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
-        const double4 pj = gather(S.P0, j);
-        const double4 gj = gather(S.P3, j);
-        const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-        const double rr = r * r;
-        const double t = wend_t(C, r);
-        const double gk = wend_gk(C, r, t);
-        const double vg = pj.w * gk;
-        if (SURF)
-        {
-            /* normal from the eigenvalue gradient, GradK(Rij = xi - xj) = -Rji*gk (Geometry.cpp:109-137) */
-            const double w = hi_lam ? (gj.w - lam_i) : gj.w;
-            const double s = -vg * w;
-            nx += s * rx;
-            ny += s * ry;
-            nz += s * rz;
-            if (need_test)
+    for_neighbours_pipelined(
+        lv, i,
+        [&](const unsigned ent) {
+            const unsigned j = ent & FJ_IDX_MASK;
+            RecS1 q;
+            q.p = gather(S.P0, j);
+            q.g = gather(S.P3, j);
+            if (DISS)
+                q.v = gather(S.P1, j);
+            return q;
+        },
+        [&](const unsigned ent, const double r, const RecS1& q) {
+            const double4 pj = q.p;
+            const double4 gj = q.g;
+            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+            const double rr = r * r;
+            const double t = wend_t(C, r);
+            const double gk = wend_gk(C, r, t);
+            const double vg = pj.w * gk;
+            if (SURF)
             {
-                if (r >= sqrt2h)
+                /* normal from the eigenvalue gradient, GradK(Rij = xi - xj) = -Rji*gk (Geometry.cpp:109-137) */
+                const double s = -vg * (gj.w - lam_ref);
+                nx += s * rx;
+                ny += s * ry;
+                nz += s * rz;
+                if (need_test)
                 {
-                    const double ex = pj.x - Tx, ey = pj.y - Ty, ez = pj.z - Tz;
-                    if (sqrt(ex * ex + ey * ey + ez * ez) < h)
-                        surf = 0;
-                }
-                else
-                {
-                    /* acos(nhat . (Rji/r)) < pi/4 ; acos is NaN outside [-1,1] so those never trigger */
-                    const double c = (nhx * rx + nhy * ry + nhz * rz) / r;
-                    if (c > cos_pi4 && c <= 1.0)
-                        surf = 0;
+                    if (r >= sqrt2h)
+                    {
+                        const double ex = pj.x - Tx, ey = pj.y - Ty, ez = pj.z - Tz;
+                        if (sqrt(ex * ex + ey * ey + ez * ez) < h)
+                            surf = 0;
+                    }
+                    else
+                    {
+                        /* acos(nhat . (Rji/r)) < pi/4 ; acos is NaN outside [-1,1] so those never trigger */
+                        const double c = (nhx * rx + nhy * ry + nhz * rz) / r;
+                        if (c > cos_pi4 && c <= 1.0)
+                            surf = 0;
+                    }
                 }
             }
-        }
-        if (DISS)
-        {
-            const double4 vj = gather(S.P1, j);
-            const double rho_j = vj.w;
-            const double idist2 = 1.0 / (rr + 0.0001 * C.H_sq);
-            const double rdg = rr * gk; /* Rji . gradK */
-            if (ent & FJ_NB_FLUID)
+            if (DISS)
             {
-                const double vdotr = (vj.x - vi.x) * rx + (vj.y - vi.y) * ry + (vj.z - vi.z) * rz;
-                if (!(vdotr > 0.0))
+                const double4 vj = q.v;
+                const double rho_j = vj.w;
+                const double idist2 = fj_rcp(rr + eps_d);
+                const double w = vg * (rr * idist2); /* V_j (Rji . gradK) idist2 */
+                const double drho = rho_j - rho_i;
+                if (ent & FJ_NB_FLUID)
                 {
+                    const double vdotr = (vj.x - vi.x) * rx + (vj.y - vi.y) * ry + (vj.z - vi.z) * rz;
+                    /* ArtVisc = 0 when Vji.Rji > 0 (select, no branch) */
                     const double muij = C.H * vdotr * idist2;
-                    const double rhoij = 0.5 * (rho_i + rho_j);
-                    const double cbar = 0.5 * (cs_i + sqrt(C.Bgam / rho_j));
-                    const double m_j = rho_j * pj.w;
-                    const double f = m_j * gk * C.visc_alpha * cbar * muij / rhoij;
+                    const double cbar = 0.5 * (cs_i + sqrt_Bgam * fj_rsqrt(rho_j));
+                    /* m_j gk alpha cbar mu / rhobar, m_j = rho_j V_j, rhobar = (rho_i + rho_j)/2 */
+                    double f = (rho_j * vg) * (C.visc_alpha * cbar) * muij * fj_rcp(0.5 * (rho_i + rho_j));
+                    f = (vdotr > 0.0) ? 0.0 : f;
                     avx += f * rx;
                     avy += f * ry;
                     avz += f * rz;
+                    const double gdot = (gi.x + gj.x) * rx + (gi.y + gj.y) * ry + (gi.z + gj.z) * rz;
+                    Rrhod += (drho + 0.5 * gdot) * w;
                 }
-                const double gdot = (gi.x + gj.x) * rx + (gi.y + gj.y) * ry + (gi.z + gj.z) * rz;
-                Rrhod += pj.w * ((rho_j - rho_i) + 0.5 * gdot) * rdg * idist2;
+                else
+                {
+                    Rrhod += drho * w;
+                }
             }
-            else
-            {
-                Rrhod += pj.w * (rho_j - rho_i) * rdg * idist2;
-            }
-        }
-    FJ_NEIGHBOURS_END
+        });
     if (SURF)
     {
         const double tx = S.L0[i] * nx + S.L1[i] * ny + S.L2[i] * nz;
@@ -404,23 +502,35 @@ __global__ void __launch_bounds__(TPB)
     }
 }
 
-// ================================================================= Detect_Surface loops 2 and 3
-__global__ void __launch_bounds__(TPB)
-    k_surf23(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
+// ================================================================= Detect_Surface loops 2 and 3 + particle_shift
+// One sweep: everything particle_shift reads from neighbour j (positions, velocities, the Detect_Surface
+// normals) is final after loop 1, and what it reads from i itself (surfzone, the kept normal) is produced by
+// this very loop, so loops 2+3 of Detect_Surface (Geometry.cpp:145-277) and particle_shift
+// (Shifting.cpp:189-290) share one pass over the list.  The stage entry points run the halves separately.
+struct RecS2
+{
+    double4 n, p, v;
+};
+
+template <bool SURF23, bool SHIFT>
+__global__ void __launch_bounds__(TPB, 3)
+    k_surf23_shift(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || blk[i] < n_bound_blocks)
         return;
     const double4 pi = S.P0[i];
-    const double4 ni = S.P4[i];
+    const double4 vi = S.P1[i];
+    const double4 ni = S.P4[i]; /* Detect_Surface loop-1 normal (unit or zero), surf */
     const int b_i = S.b[i];
     const double lam_nb = S.NP[i].w;
     const bool ni_nz = (ni.x * ni.x + ni.y * ni.y + ni.z * ni.z) > 0.0;
+
+    // ---- Detect_Surface loop 2 set-up
     const bool occl = (b_i == FJSPH_FREE) && (C.acase == 1);
     double vdx = 0, vdy = 0, vdz = 0;
-    if (S.cellID[i] != -1 && occl)
+    if (SURF23 && S.cellID[i] != -1 && occl)
     {
-        const double4 vi = S.P1[i];
         if (C.asource == 1)
         {
             const double4 cv = S.CV[i];
@@ -435,164 +545,171 @@ __global__ void __launch_bounds__(TPB)
             vdz = C.vinf_z - vi.z;
         }
     }
-    const double vdn = sqrt(vdx * vdx + vdy * vdy + vdz * vdz);
-    const double L0 = S.L0[i], L1 = S.L1[i], L2 = S.L2[i], L3 = S.L3[i], L4 = S.L4[i], L5 = S.L5[i], L6 = S.L6[i],
-                 L7 = S.L7[i], L8 = S.L8[i];
+    /* -1/|Vdiff|: inf for Vdiff = 0, so frac = 0 * inf = NaN never passes the '>' (Geometry.cpp:237-246) */
+    const double mivdn = -1.0 / sqrt(vdx * vdx + vdy * vdy + vdz * vdz);
+    double L0 = 0, L1 = 0, L2 = 0, L3 = 0, L4 = 0, L5 = 0, L6 = 0, L7 = 0, L8 = 0;
+    if (SURF23 && ni_nz)
+    {
+        L0 = S.L0[i];
+        L1 = S.L1[i];
+        L2 = S.L2[i];
+        L3 = S.L3[i];
+        L4 = S.L4[i];
+        L5 = S.L5[i];
+        L6 = S.L6[i];
+        L7 = S.L7[i];
+        L8 = S.L8[i];
+    }
     double curve = 0.0, woccl_ = 0.0;
     int zone = (ni.w != 0.0) ? 1 : 0; /* the list of the reference includes self */
     /* woccl is overwritten with 1 when lam_nb >= lam_cutoff, so the occlusion max is only needed below it */
-    const bool need_occl = occl && (lam_nb < C.lam_cutoff);
+    const bool need_occl = SURF23 && occl && (lam_nb < C.lam_cutoff);
 
-    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
-        const double4 nj = gather(S.P4, j);
-        if (nj.w != 0.0)
-            zone = 1;
-        const bool curv = ni_nz && ((nj.x * nj.x + nj.y * nj.y + nj.z * nj.z) > 0.0);
-        if (curv || need_occl)
-        {
-            const double4 pj = gather(S.P0, j);
-            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-            const double rr = r * r;
-            if (curv)
-            {
-                const double t = wend_t(C, r);
-                const double vg = pj.w * wend_gk(C, r, t);
-                const double dx_ = nj.x - ni.x, dy_ = nj.y - ni.y, dz_ = nj.z - ni.z;
-                const double lx = L0 * dx_ + L1 * dy_ + L2 * dz_;
-                const double ly = L3 * dx_ + L4 * dy_ + L5 * dz_;
-                const double lz = L6 * dx_ + L7 * dy_ + L8 * dz_;
-                curve += vg * (lx * rx + ly * ry + lz * rz);
-            }
-            if (need_occl)
-            {
-                /* frac = -Rji.Vdiff / (|Vdiff| r); 0/0 = NaN never passes the '>' (Geometry.cpp:237-246) */
-                const double frac = -(rx * vdx + ry * vdy + rz * vdz) / (vdn * r);
-                if (frac > woccl_)
-                    woccl_ = frac;
-            }
-        }
-    FJ_NEIGHBOURS_END
-    double4 th = S.TH[i];
-    th.z = (lam_nb < C.lam_cutoff) ? fmax(0.0, fmin(woccl_, 1.0)) : 1.0;
-    S.TH[i] = th;
-    double4 np = S.NP[i];
-    np.x = ni.x;
-    np.y = ni.y;
-    np.z = ni.z;
-    S.NP[i] = np; /* pi.norm = norms[ii] */
-    double4 av = S.AV[i];
-    av.w = curve;
-    S.AV[i] = av;
-    double4 sc = S.SC[i];
-    sc.w = S.P3[i].w; /* pDist = lam */
-    S.SC[i] = sc;
-    if (C.ale)
-        S.surfzone[i] = zone;
-}
-
-// ================================================================= particle_shift (ALE)
-__global__ void __launch_bounds__(TPB)
-    k_shift(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || blk[i] < n_bound_blocks)
-        return;
-    const double4 np = S.NP[i];
-    const double lam_nb = np.w;
-    double4 out = S.P2[i];
-    if (lam_nb < 0.55 || S.b[i] == FJSPH_BUFFER)
-    {
-        out.x = out.y = out.z = 0.0;
-        S.P2[i] = out;
-        return;
-    }
-    const double4 pi = S.P0[i];
-    const double4 vi = S.P1[i];
-    const bool bulk = (S.surfzone[i] == 0) && (lam_nb > 0.55);
-    /* own unit normal; Eigen normalized() leaves the zero vector unchanged */
-    double nhx = np.x, nhy = np.y, nhz = np.z;
-    {
-        const double nn = nhx * nhx + nhy * nhy + nhz * nhz;
-        if (nn > 0.0)
-        {
-            const double inv = 1.0 / sqrt(nn);
-            nhx *= inv;
-            nhy *= inv;
-            nhz *= inv;
-        }
-    }
+    // ---- particle_shift set-up (Shifting.cpp:205-212)
+    const bool do_shift = SHIFT && !(lam_nb < 0.55 || b_i == FJSPH_BUFFER);
+    /* with the stage entry point surfzone is already known; fused, it is this loop's `zone` */
+    const bool known_bulk = SHIFT && !SURF23 && (S.surfzone[i] == 0) && (lam_nb > 0.55);
     double dux = 0, duy = 0, duz = 0, maxU2 = 0.0;
     /* max_j acos(c_j) over c_j in [-1,1] == acos(min_j c_j); NaNs (|c|>1) are skipped by the reference's '>' */
     double min_c = 2.0;
-    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
-        const double4 pj = gather(S.P0, j);
-        const double4 vj = gather(S.P1, j);
-        const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-        const double rr = r * r;
-        const double t = wend_t(C, r);
-        const double W = wend_W(C, r, t);
-        const double gk = wend_gk(C, r, t);
-        const double kq = W * C.iW_dx;
-        const double kq2 = kq * kq;
-        const double f = (1.0 + 0.2 * (kq2 * kq2)) * gk * pj.w;
-        dux += f * rx;
-        duy += f * ry;
-        duz += f * rz;
-        if (!bulk && (ent & FJ_NB_FLUID))
+    const bool need_pos = (SURF23 && (ni_nz || need_occl)) || do_shift;
+
+    for_neighbours_pipelined(
+        lv, i,
+        [&](const unsigned ent) {
+            const unsigned j = ent & FJ_IDX_MASK;
+            RecS2 q;
+            q.n = gather(S.P4, j);
+            if (need_pos)
+                q.p = gather(S.P0, j);
+            if (do_shift)
+                q.v = gather(S.P1, j);
+            return q;
+        },
+        [&](const unsigned ent, const double r, const RecS2& q) {
+            const double4 nj = q.n;
+            if (nj.w != 0.0)
+                zone = 1;
+            if (!need_pos)
+                return;
+            const double4 pj = q.p;
+            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+            const double t = wend_t(C, r);
+            const double gk = wend_gk(C, r, t);
+            if (SURF23)
+            {
+                if (ni_nz && ((nj.x * nj.x + nj.y * nj.y + nj.z * nj.z) > 0.0))
+                {
+                    const double vg = pj.w * gk;
+                    const double dx_ = nj.x - ni.x, dy_ = nj.y - ni.y, dz_ = nj.z - ni.z;
+                    const double lx = L0 * dx_ + L1 * dy_ + L2 * dz_;
+                    const double ly = L3 * dx_ + L4 * dy_ + L5 * dz_;
+                    const double lz = L6 * dx_ + L7 * dy_ + L8 * dz_;
+                    curve += vg * (lx * rx + ly * ry + lz * rz);
+                }
+                if (need_occl)
+                {
+                    const double frac = (rx * vdx + ry * vdy + rz * vdz) * mivdn * fj_rcp(r);
+                    if (frac > woccl_)
+                        woccl_ = frac;
+                }
+            }
+            if (do_shift)
+            {
+                const double4 vj = q.v;
+                const double W = wend_W(C, r, t);
+                const double kq = W * C.iW_dx;
+                const double kq2 = kq * kq;
+                const double f = (1.0 + 0.2 * (kq2 * kq2)) * gk * pj.w;
+                dux += f * rx;
+                duy += f * ry;
+                duz += f * rz;
+                if (!known_bulk && (ent & FJ_NB_FLUID))
+                {
+                    /* n_i and n_j are unit vectors or zero already (loop 1), normalized() is the identity */
+                    const double c = ni.x * nj.x + ni.y * nj.y + ni.z * nj.z;
+                    if (c >= -1.0 && c <= 1.0)
+                        min_c = fmin(min_c, c);
+                }
+                const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
+                maxU2 = fmax(maxU2, ux * ux + uy * uy + uz * uz);
+            }
+        });
+
+    if (SURF23)
+    {
+        double4 th = S.TH[i];
+        th.z = (lam_nb < C.lam_cutoff) ? fmax(0.0, fmin(woccl_, 1.0)) : 1.0;
+        S.TH[i] = th;
+        double4 np = S.NP[i];
+        np.x = ni.x;
+        np.y = ni.y;
+        np.z = ni.z;
+        S.NP[i] = np; /* pi.norm = norms[ii] */
+        double4 av = S.AV[i];
+        av.w = curve;
+        S.AV[i] = av;
+        double4 sc = S.SC[i];
+        sc.w = S.P3[i].w; /* pDist = lam */
+        S.SC[i] = sc;
+        if (C.ale)
+            S.surfzone[i] = zone;
+    }
+    if (SHIFT)
+    {
+        double4 out = S.P2[i];
+        if (!do_shift)
         {
-            const double4 nj = gather(S.P4, j);
-            const double nn = nj.x * nj.x + nj.y * nj.y + nj.z * nj.z;
-            const double inv = (nn > 0.0) ? 1.0 / sqrt(nn) : 1.0;
-            const double c = (nhx * nj.x + nhy * nj.y + nhz * nj.z) * inv;
-            if (c >= -1.0 && c <= 1.0)
-                min_c = fmin(min_c, c);
+            out.x = out.y = out.z = 0.0;
+            S.P2[i] = out;
+            return;
         }
-        const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
-        maxU2 = fmax(maxU2, ux * ux + uy * uy + uz * uz);
-    FJ_NEIGHBOURS_END
-    const double vnorm = sqrt(vi.x * vi.x + vi.y * vi.y + vi.z * vi.z);
-    const double sc = -2.0 * C.H * vnorm;
-    dux *= sc;
-    duy *= sc;
-    duz *= sc;
-    const double dn = sqrt(dux * dux + duy * duy + duz * duz);
-    const double lim = fmin(dn, fmin(sqrt(maxU2) / 2.0, C.max_shift_vel));
-    if (dn > 0.0)
-    {
-        const double s2 = lim / dn;
-        dux *= s2;
-        duy *= s2;
-        duz *= s2;
-    }
-    else
-    {
-        dux *= lim;
-        duy *= lim;
-        duz *= lim;
-    }
-    if (bulk)
-    {
-        out.x = dux;
-        out.y = duy;
-        out.z = duz;
-    }
-    else
-    {
-        const double woccl = (min_c <= 1.0) ? acos(min_c) : 0.0;
-        if (woccl < FJ_PI / 12.0)
+        const int surfzone = SURF23 ? zone : S.surfzone[i];
+        const bool bulk = (surfzone == 0) && (lam_nb > 0.55);
+        const double vnorm = sqrt(vi.x * vi.x + vi.y * vi.y + vi.z * vi.z);
+        const double sc = -2.0 * C.H * vnorm;
+        dux *= sc;
+        duy *= sc;
+        duz *= sc;
+        const double dn = sqrt(dux * dux + duy * duy + duz * duz);
+        const double lim = fmin(dn, fmin(sqrt(maxU2) / 2.0, C.max_shift_vel));
+        if (dn > 0.0)
         {
-            /* (I - n n^T) deltaU with n = -nhat */
-            const double nd = nhx * dux + nhy * duy + nhz * duz;
-            out.x = dux - nhx * nd;
-            out.y = duy - nhy * nd;
-            out.z = duz - nhz * nd;
+            const double s2 = lim / dn;
+            dux *= s2;
+            duy *= s2;
+            duz *= s2;
         }
         else
         {
-            out.x = out.y = out.z = 0.0;
+            dux *= lim;
+            duy *= lim;
+            duz *= lim;
         }
+        if (bulk)
+        {
+            out.x = dux;
+            out.y = duy;
+            out.z = duz;
+        }
+        else
+        {
+            const double woccl = (min_c <= 1.0) ? acos(min_c) : 0.0;
+            if (woccl < FJ_PI / 12.0)
+            {
+                /* (I - n n^T) deltaU with n = -nhat */
+                const double nd = ni.x * dux + ni.y * duy + ni.z * duz;
+                out.x = dux - ni.x * nd;
+                out.y = duy - ni.y * nd;
+                out.z = duz - ni.z * nd;
+            }
+            else
+            {
+                out.x = out.y = out.z = 0.0;
+            }
+        }
+        S.P2[i] = out;
     }
-    S.P2[i] = out;
 }
 
 // ================================================================= get_acc_and_Rrho
@@ -601,8 +718,25 @@ __device__ __forceinline__ double get_cd(double Re)
     return (1.0 + 0.197 * pow(Re, 0.63) + 2.6e-04 * pow(Re, 1.38)) * (24.0 / (Re + 0.00001));
 }
 
+struct RecF
+{
+    double4 p, v, q;
+};
+
+// Pair algebra (V_j = m_j / rho_j, G = V_j gradK, Pi = p_i / rho_i^2, u = v_j - v_i, w = vPert):
+//   pressure    BasePos, Kernel.h:153-157          acc_     -= m_j (Pi + Pj) gradK         = rho_j (Pi + Pj) G
+//   viscosity   Kernel.h:262-269                   visc_    += m_j nu (rho_i + rho_j)/(rho_i rho_j) (Rji.gradK) idist2 u
+//                                                            = (nu + nu rho_j / rho_i) (V_j gk rr idist2) u
+//   ALE moment. Kernel.h:179-185                   acc_ale_ += V_j [(v_j (w_j.gK) + v_i (w_i.gK)) - v_i ((w_j - w_i).gK)]
+//                                                            = u (w_j.G) + 2 v_i (w_i.G)
+//   continuity  Kernel.h:187-196                   Rrho_    -= V_j ((u + w_j - w_i).gK)     = -(u.G + w_j.G) + w_i.G
+//                                                  Rrhoc_   += V_j (rho_j w_j.gK + rho_i w_i.gK) = rho_j (w_j.G) + rho_i (w_i.G)
+// The w_i.G terms are linear in G, so sum_j G is accumulated once and w_i applied after the loop.
+#ifndef FJ_FORCE_MINBLOCKS
+#define FJ_FORCE_MINBLOCKS 3
+#endif
 template <bool ALE>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, FJ_FORCE_MINBLOCKS)
     k_force(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, double npdm2, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -615,13 +749,16 @@ __global__ void __launch_bounds__(TPB)
     const double4 th = S.TH[i]; /* p, m, woccl, cellRho */
     const int b_i = S.b[i];
     const bool do_st = ALE ? (S.surfzone[i] == 1) : true;
-    const double pi3o4 = 3.0 * FJ_PI / 4.0;
     const double st_bound_fac = 1.0 + 0.5 * cos(0.5 * FJ_PI * 7.0 / 9.0);
+    const double eps_f = 0.001 * C.H_sq;
+    const double nu_irho_i = C.nu * irho_i;
+    const double q_st = 0.75 * C.iH; /* cos(3 pi/4 r/H) = cospi(0.75 r/H) */
 
     double ax = 0, ay = 0, az = 0;       /* acc_ (aero + pressure + wall repulsion) */
     double alx = 0, aly = 0, alz = 0;    /* acc_ale_ */
     double vx = 0, vy = 0, vz = 0;       /* visc_ */
     double sx = 0, sy = 0, sz = 0;       /* surf_t_ */
+    double sgx = 0, sgy = 0, sgz = 0;    /* sum_j G */
     double Rrho_ = 0.0, Rrhoc_ = 0.0;
     double4 af = S.AF[i];                /* Af, deltaD */
 
@@ -671,56 +808,72 @@ __global__ void __launch_bounds__(TPB)
         af.x = af.y = af.z = 0.0; /* CalcAeroAcc default branch returns zero */
     }
 
-    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
-        const double4 pj = gather(S.P0, j);
-        const double4 vj = gather(S.P1, j);
-        const double4 qj = gather(S.P2, j);
-        const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-        const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
-        const double rr = r * r;
-        const double idist2 = 1.0 / (rr + 0.001 * C.H_sq);
-        const double t = wend_t(C, r);
-        const double gk = wend_gk(C, r, t);
-        const double V_j = pj.w, rho_j = vj.w;
-        const double m_j = rho_j * V_j;
-        const double gx = gk * rx, gy = gk * ry, gz = gk * rz; /* gradK */
-        /* BasePos, Kernel.h:153-157 */
-        const double pf = m_j * (qi.w + qj.w);
-        ax -= pf * gx;
-        ay -= pf * gy;
-        az -= pf * gz;
-        /* Viscosity, Kernel.h:262-269: m_j nu (rho_i+rho_j)/(rho_i rho_j) (Rji.gradK) idist2 Vji */
-        const double vf = C.nu * (V_j + m_j * irho_i) * (rr * gk) * idist2;
-        vx += vf * ux;
-        vy += vf * uy;
-        vz += vf * uz;
-        /* pairwise surface tension, Kernel.h:101-113 */
-        if (do_st)
-        {
-            const double fac = (b_i == FJSPH_BOUND || (ent & FJ_NB_BOUND)) ? st_bound_fac : 1.0;
-            const double sf = -npdm2 * fac * cos(pi3o4 * r * C.iH) / r;
-            sx += sf * rx;
-            sy += sf * ry;
-            sz += sf * rz;
-        }
-        if (ALE)
-        {
-            /* ALEMomentum, ALEContinuity, ALECont2ndterm, Kernel.h:179-196 */
-            const double pjg = qj.x * gx + qj.y * gy + qj.z * gz;
-            const double pig = qi.x * gx + qi.y * gy + qi.z * gz;
-            const double dpg = pjg - pig;
-            alx += ((vj.x * pjg + vi.x * pig) - vi.x * dpg) * V_j;
-            aly += ((vj.y * pjg + vi.y * pig) - vi.y * dpg) * V_j;
-            alz += ((vj.z * pjg + vi.z * pig) - vi.z * dpg) * V_j;
-            const double ug = ux * gx + uy * gy + uz * gz;
-            Rrho_ -= (ug + dpg) * V_j;
-            Rrhoc_ += (rho_j * pjg + rho_i * pig) * V_j;
-        }
-        else
-        {
-            Rrho_ -= V_j * (ux * gx + uy * gy + uz * gz);
-        }
-    FJ_NEIGHBOURS_END
+    for_neighbours_pipelined(
+        lv, i,
+        [&](const unsigned ent) {
+            const unsigned j = ent & FJ_IDX_MASK;
+            RecF q;
+            q.p = gather(S.P0, j);
+            q.v = gather(S.P1, j);
+            q.q = gather(S.P2, j);
+            return q;
+        },
+        [&](const unsigned ent, const double r, const RecF& q) {
+            const double4 pj = q.p;
+            const double4 vj = q.v;
+            const double4 qj = q.q;
+            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+            const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
+            const double rr = r * r;
+            const double idist2 = fj_rcp(rr + eps_f);
+            const double t = wend_t(C, r);
+            const double rho_j = vj.w;
+            const double s = pj.w * wend_gk(C, r, t);               /* V_j gk */
+            const double Gx = s * rx, Gy = s * ry, Gz = s * rz;     /* V_j gradK */
+            const double pf = rho_j * (qi.w + qj.w);
+            ax -= pf * Gx;
+            ay -= pf * Gy;
+            az -= pf * Gz;
+            const double vf = fma(nu_irho_i, rho_j, C.nu) * ((s * rr) * idist2);
+            vx += vf * ux;
+            vy += vf * uy;
+            vz += vf * uz;
+            /* pairwise surface tension, Kernel.h:101-113 */
+            if (do_st)
+            {
+                const double fac = (b_i == FJSPH_BOUND || (ent & FJ_NB_BOUND)) ? st_bound_fac : 1.0;
+                const double sf = -npdm2 * fac * cospi(q_st * r) * fj_rcp(r);
+                sx += sf * rx;
+                sy += sf * ry;
+                sz += sf * rz;
+            }
+            const double ug = ux * Gx + uy * Gy + uz * Gz;
+            if (ALE)
+            {
+                const double pjg = qj.x * Gx + qj.y * Gy + qj.z * Gz; /* V_j (vPert_j . gradK) */
+                alx += ux * pjg;
+                aly += uy * pjg;
+                alz += uz * pjg;
+                sgx += Gx;
+                sgy += Gy;
+                sgz += Gz;
+                Rrho_ -= ug + pjg;
+                Rrhoc_ += rho_j * pjg;
+            }
+            else
+            {
+                Rrho_ -= ug;
+            }
+        });
+    if (ALE)
+    {
+        const double pig = qi.x * sgx + qi.y * sgy + qi.z * sgz; /* vPert_i . sum_j G */
+        alx += 2.0 * vi.x * pig;
+        aly += 2.0 * vi.y * pig;
+        alz += 2.0 * vi.z * pig;
+        Rrho_ += pig;
+        Rrhoc_ += rho_i * pig;
+    }
     if (S.internal[i] == 1)
     {
         /* NormalBoundaryRepulsion, Kernel.h:64-75,272-277 */
@@ -975,7 +1128,7 @@ int fj_aero_velocity(FjsphEngine* e)
     return FJSPH_OK;
 }
 
-int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipation)
+int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipation, bool fuse_shift)
 {
     int st = need_list(e, "detect_surface/dissipation");
     if (st)
@@ -998,10 +1151,15 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
         KScope ks(e, "diss", 1);
         k_surf1_diss<false, true><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
     }
-    if (do_surface)
+    if (do_surface && fuse_shift && e->P.ale)
+    {
+        KScope ks(e, "surf2+3+shift", 1);
+        k_surf23_shift<true, true><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+    }
+    else if (do_surface)
     {
         KScope ks(e, "surf2+3", 1);
-        k_surf23<<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+        k_surf23_shift<true, false><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
     }
     FJ_CUDA(cudaGetLastError());
     return FJSPH_OK;
@@ -1016,7 +1174,8 @@ int fj_shift(FjsphEngine* e)
         return FJSPH_OK;
     const int n = int(e->n_owned);
     KScope ks(e, "shift", 1);
-    k_shift<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], list_view(e), e->blk, e->n_bound_blocks, e->C, n);
+    k_surf23_shift<false, true><<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], list_view(e), e->blk,
+                                                                          e->n_bound_blocks, e->C, n);
     FJ_CUDA(cudaGetLastError());
     return FJSPH_OK;
 }
