@@ -114,6 +114,7 @@ def lib():
     L.fjsph_launch_count.argtypes = [vp]
     L.fjsph_launch_count.restype = C.c_int64
     L.fjsph_set_owned.argtypes = [vp, C.c_int64]
+    L.fjsph_set_skin.argtypes = [vp, C.c_double]
     _lib = L
     return L
 

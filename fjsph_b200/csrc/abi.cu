@@ -679,6 +679,9 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
     FJ_CUDA(cudaMalloc(&e->perm, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->perm2, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->ncount, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->scount, cap * sizeof(int)));
+    FJ_CUDA(cudaMalloc(&e->xref, cap * sizeof(double4)));
+    e->skin = 0.4 * e->P.particle_step; /* default skin: 0.4 dx = 5 % of the support radius at H_fac = 2 */
     FJ_CUDA(cudaMalloc(&e->near_inlet, cap * sizeof(int)));
     FJ_CUDA(cudaMemset(e->near_inlet, 0, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->rk_sum_v, cap * sizeof(double4)));
@@ -710,7 +713,7 @@ int fjsph_destroy(FjsphEngine* e)
     void* ptrs[] = {e->oidx,       e->oidx_tmp, e->slot_of,  e->blk,      e->blk_tmp,   e->key,     e->rank_in_cell,
                     e->perm,       e->perm2,    e->ncount,   e->near_inlet, e->rk_sum_v, e->rk_sum_a, e->red,
                     e->red_out,    e->d_flag,   e->stage,    e->cell_count, e->cell_start, e->scan_tmp, e->mtab_x,
-                    e->nlist,      e->nr};
+                    e->nlist,      e->nr,       e->slist,    e->scount,     e->xref};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -738,6 +741,13 @@ int fjsph_set_params(FjsphEngine* e, const FjsphParams* in)
     int st = validate_params(*in);
     if (st)
         return st;
+    if (in->sr != e->P.sr || in->particle_step != e->P.particle_step)
+    {
+        /* the support radius changed: keep skin/dx, drop both lists */
+        e->skin = (e->P.particle_step > 0.0 ? e->skin / e->P.particle_step : 0.4) * in->particle_step;
+        e->skin_valid = false;
+        e->list_valid = false;
+    }
     e->P = *in;
     fj_refresh_constants(e);
     return FJSPH_OK;
@@ -829,6 +839,7 @@ int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_po
     e->n_owned = s->n;
     e->bound_points = bound_points;
     e->list_valid = false;
+    e->skin_valid = false; /* slots are reset to the caller's order below */
     const int n = int(e->n);
     e->launches += 2;
     k_identity_index<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->oidx, e->slot_of, n);
@@ -1098,6 +1109,19 @@ int fjsph_set_stream(FjsphEngine* e, void* cuda_stream)
         FJ_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         e->own_stream = true;
     }
+    return FJSPH_OK;
+}
+
+int fjsph_set_skin(FjsphEngine* e, double skin_over_dx)
+{
+    if (!(skin_over_dx >= 0.0) || skin_over_dx > 2.0)
+    {
+        fj_set_error("set_skin: skin/dx must lie in [0, 2]");
+        return FJSPH_ERR_INVALID;
+    }
+    e->skin = skin_over_dx * e->P.particle_step;
+    e->skin_valid = false;
+    e->list_valid = false;
     return FJSPH_OK;
 }
 

@@ -127,6 +127,16 @@ struct FjsphEngine
     unsigned int* nlist = nullptr;      // slot s of particle i at FJ_LIST_WORD(i, s, nb_cap)
     double* nr = nullptr;               // same layout: r = sqrt(d^2) at list-build time (OUTL's .second, frozen)
     int* ncount = nullptr;              // [cap] neighbours excluding self
+    // skin list (superset with d < 2H + skin at its build time), same chunked layout, indices only
+    unsigned int* slist = nullptr;
+    int* scount = nullptr;
+    double4* xref = nullptr;            // positions at the skin build
+    int scap = 0;
+    size_t slist_words = 0;
+    bool skin_valid = false;
+    int64_t skin_n = 0;
+    double skin = 0.0;                  // skin width (m); 0 = rebuild the cell list at every update_neighbours
+    long long skin_builds = 0;
     int* near_inlet = nullptr;          // [cap] Boundary_Ghost flag, valid within one sub-iteration
     int nb_cap = 0;
     size_t nlist_words = 0;

@@ -612,6 +612,7 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
     const long long launches0 = e->launches;
     e->force_evals = 0;
     e->nb_builds = 0;
+    const long long skin0 = e->skin_builds;
     e->iteration = 0;
     double rms_error = 0.0, logbase = 0.0;
     e->npd = 1.0;
@@ -759,6 +760,7 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
         s->total_points = int(e->n_owned);
         s->force_evals = e->force_evals;
         s->neighbour_builds = e->nb_builds;
+        s->skin_builds = int(e->skin_builds - skin0);
         s->kernel_launches = int(e->launches - launches0);
     }
     return FJSPH_OK;

@@ -22,10 +22,12 @@ namespace
 
 constexpr int TPB = 256;
 
-// ---------------------------------------------------------------- bounds
-__global__ void k_bounds(const double4* __restrict__ P0, int n, double* __restrict__ partial)
+// ---------------------------------------------------------------- bounds (+ displacement since the skin build)
+// partial[b*7 + {lo.xyz, hi.xyz, max |x - xref|^2}]
+__global__ void k_bounds(const double4* __restrict__ P0, const double4* __restrict__ xref, int n,
+                         double* __restrict__ partial)
 {
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    double lo[3] = {1e300, 1e300, 1e300}, hi[4] = {-1e300, -1e300, -1e300, 0.0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         double4 a = P0[i];
@@ -35,43 +37,65 @@ __global__ void k_bounds(const double4* __restrict__ P0, int n, double* __restri
         hi[1] = fmax(hi[1], a.y);
         lo[2] = fmin(lo[2], a.z);
         hi[2] = fmax(hi[2], a.z);
+        if (xref)
+        {
+            const double4 r = xref[i];
+            const double dx = a.x - r.x, dy = a.y - r.y, dz = a.z - r.z;
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            hi[3] = (d2 <= hi[3]) ? hi[3] : d2; /* NaN propagates to "moved too far" */
+        }
     }
-    __shared__ double sm[6][TPB / 32];
+    __shared__ double sm[7][TPB / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int c = 0; c < 4; ++c)
     {
-        double l = lo[c], h = hi[c];
+        double l = (c < 3) ? lo[c] : 0.0, h = hi[c];
         for (int o = 16; o > 0; o >>= 1)
         {
             l = fmin(l, __shfl_xor_sync(0xffffffffu, l, o));
-            h = fmax(h, __shfl_xor_sync(0xffffffffu, h, o));
+            const double h2 = __shfl_xor_sync(0xffffffffu, h, o);
+            h = (h2 <= h) ? h : h2;
         }
         if (lane == 0)
         {
-            sm[c][w] = l;
+            if (c < 3)
+                sm[c][w] = l;
             sm[3 + c][w] = h;
         }
     }
     __syncthreads();
-    if (threadIdx.x < 6)
+    if (threadIdx.x < 7)
     {
         double v = sm[threadIdx.x][0];
         for (int k = 1; k < TPB / 32; ++k)
-            v = (threadIdx.x < 3) ? fmin(v, sm[threadIdx.x][k]) : fmax(v, sm[threadIdx.x][k]);
-        partial[blockIdx.x * 6 + threadIdx.x] = v;
+        {
+            const double u = sm[threadIdx.x][k];
+            v = (threadIdx.x < 3) ? fmin(v, u) : ((u <= v) ? v : u);
+        }
+        partial[blockIdx.x * 7 + threadIdx.x] = v;
     }
 }
 
 __global__ void k_bounds_final(const double* __restrict__ partial, int nblocks, double* __restrict__ out)
 {
-    const int c = threadIdx.x;
-    if (c < 6)
+    // one warp per component, lanes stride the block partials
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= 7)
+        return;
+    double v = (c < 3) ? 1e300 : ((c < 6) ? -1e300 : 0.0);
+    for (int b = lane; b < nblocks; b += 32)
     {
-        double v = partial[c];
-        for (int b = 1; b < nblocks; ++b) v = (c < 3) ? fmin(v, partial[b * 6 + c]) : fmax(v, partial[b * 6 + c]);
-        out[c] = v;
+        const double u = partial[b * 7 + c];
+        v = (c < 3) ? fmin(v, u) : ((u <= v) ? v : u);
     }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const double u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (c < 3) ? fmin(v, u) : ((u <= v) ? v : u);
+    }
+    if (lane == 0)
+        out[c] = v;
 }
 
 // ---------------------------------------------------------------- keys + histogram
@@ -279,25 +303,34 @@ __global__ void k_permute_index(const int* __restrict__ oidx_in, const int* __re
     slot_of[o] = i;
 }
 
-// ---------------------------------------------------------------- neighbour list
+// ---------------------------------------------------------------- skin list + exact list
+// Two-level neighbour build.  The SKIN list holds every j with d < 2H + skin at the time it was built (27-cell
+// sweep over the Morton cell list); it stays valid while no particle has moved more than skin/2 since.  The
+// EXACT list -- the reference's OUTL: { j : d2 < sr } with r = sqrt(d2), rebuilt at every update_neighbours --
+// is filtered from the skin list with the bit-exact nanoflann distance on the CURRENT positions, ~1.3 N_nb
+// candidates per particle instead of the 27-cell sweep's ~7 N_nb.  Both use the chunked ELL layout.
+__device__ __forceinline__ double4 ldg256(const double4* __restrict__ base, unsigned j)
+{
+    double4 v;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(base + j));
+    return v;
+}
+
 __global__ void __launch_bounds__(TPB)
-    k_build_list(const double4* __restrict__ P0, const int* __restrict__ b, int n, Grid g,
+    k_build_skin(const double4* __restrict__ P0, const int* __restrict__ b, int n, Grid g,
                  const unsigned* __restrict__ mx, const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
-                 const unsigned* __restrict__ cell_start, double sr, int nb_cap, unsigned* __restrict__ nlist,
-                 double* __restrict__ nr, int* __restrict__ ncount, int* __restrict__ flag)
+                 const unsigned* __restrict__ cell_start, double sr_skin, int scap, unsigned* __restrict__ slist,
+                 int* __restrict__ scount, double4* __restrict__ xref, int* __restrict__ flag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
     const double4 a = P0[i];
+    xref[i] = a;
     int cx, cy, cz;
     cell_of(g, a.x, a.y, a.z, cx, cy, cz);
-    /* chunk c of this lane: one uint4 + one double4, written whole (full 16 B / 32 B sectors per lane) */
-    const size_t base = (size_t(i >> 5) * size_t(nb_cap >> 2)) * 32u + (i & 31);
-    uint4* __restrict__ dst = reinterpret_cast<uint4*>(nlist) + base;
-    double4* __restrict__ rdst = reinterpret_cast<double4*>(nr) + base;
-    unsigned eb[4] = {unsigned(i), unsigned(i), unsigned(i), unsigned(i)};
-    double rb[4] = {0.0, 0.0, 0.0, 0.0};
+    uint4* __restrict__ dst = reinterpret_cast<uint4*>(slist) + (size_t(i >> 5) * size_t(scap >> 2)) * 32u + (i & 31);
+    unsigned eb0 = unsigned(i), eb1 = unsigned(i), eb2 = unsigned(i);
     int cnt = 0;
     for (int dz = -1; dz <= 1; ++dz)
     {
@@ -321,11 +354,9 @@ __global__ void __launch_bounds__(TPB)
                 for (unsigned j = s; j < e; ++j)
                 {
                     const double4 q = P0[j];
-                    // nanoflann metric_L2_Simple order, no fma contraction (bit-exact sets)
-                    const double ddx = __dsub_rn(a.x, q.x), ddy = __dsub_rn(a.y, q.y), ddz = __dsub_rn(a.z, q.z);
-                    const double d2 =
-                        __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
-                    if (d2 < sr && int(j) != i)
+                    const double ddx = a.x - q.x, ddy = a.y - q.y, ddz = a.z - q.z;
+                    const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                    if (d2 < sr_skin && int(j) != i)
                     {
                         const int bj = b[j];
                         unsigned ent = j;
@@ -333,31 +364,107 @@ __global__ void __launch_bounds__(TPB)
                             ent |= FJ_NB_FLUID;
                         if (bj == FJSPH_BOUND)
                             ent |= FJ_NB_BOUND;
-                        const double rv = sqrt(d2); /* r = sqrt(jj.second), as every pair loop takes it */
                         const int kk = cnt & 3;
-                        /* static register indexing only */
-                        if (kk == 0) { eb[0] = ent; rb[0] = rv; }
-                        else if (kk == 1) { eb[1] = ent; rb[1] = rv; }
-                        else if (kk == 2) { eb[2] = ent; rb[2] = rv; }
-                        else
-                        {
-                            if (cnt < nb_cap)
-                            {
-                                dst[size_t(cnt >> 2) * 32u] = make_uint4(eb[0], eb[1], eb[2], ent);
-                                rdst[size_t(cnt >> 2) * 32u] = make_double4(rb[0], rb[1], rb[2], rv);
-                            }
-                        }
+                        if (kk == 0)
+                            eb0 = ent;
+                        else if (kk == 1)
+                            eb1 = ent;
+                        else if (kk == 2)
+                            eb2 = ent;
+                        else if (cnt < scap)
+                            dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, eb1, eb2, ent);
                         cnt++;
                     }
                 }
             }
         }
     }
+    if ((cnt & 3) && cnt < scap)
+        dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, (cnt & 3) > 1 ? eb1 : unsigned(i), (cnt & 3) > 2 ? eb2 : unsigned(i),
+                                                 unsigned(i));
+    scount[i] = cnt;
+    if (cnt > scap)
+        atomicMax(flag, cnt);
+}
+
+// exact list from the skin list: list_i = { j in skin_i : ((xi-xj)^2 + (yi-yj)^2) + (zi-zj)^2 < sr }
+__global__ void __launch_bounds__(TPB)
+    k_exact_from_skin(const double4* __restrict__ P0, int n, const unsigned* __restrict__ slist,
+                      const int* __restrict__ scount, int scap, double sr, int nb_cap, unsigned* __restrict__ nlist,
+                      double* __restrict__ nr, int* __restrict__ ncount, int* __restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double4 a = P0[i];
+    const uint4* __restrict__ sp =
+        reinterpret_cast<const uint4*>(slist) + (size_t(i >> 5) * size_t(scap >> 2)) * 32u + (i & 31);
+    const size_t base = (size_t(i >> 5) * size_t(nb_cap >> 2)) * 32u + (i & 31);
+    uint4* __restrict__ dst = reinterpret_cast<uint4*>(nlist) + base;
+    double4* __restrict__ rdst = reinterpret_cast<double4*>(nr) + base;
+    const int sc = scount[i];
+    const int nchunk = (sc + 3) >> 2;
+    unsigned eb0 = unsigned(i), eb1 = unsigned(i), eb2 = unsigned(i);
+    double rb0 = 0.0, rb1 = 0.0, rb2 = 0.0;
+    int cnt = 0;
+    auto test = [&](const unsigned ent, const double4 q, const bool valid) {
+        // nanoflann metric_L2_Simple order, no fma contraction (bit-exact sets)
+        const double ddx = __dsub_rn(a.x, q.x), ddy = __dsub_rn(a.y, q.y), ddz = __dsub_rn(a.z, q.z);
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
+        if (valid && d2 < sr)
+        {
+            const double rv = sqrt(d2); /* r = sqrt(jj.second), as every pair loop takes it */
+            const int kk = cnt & 3;
+            if (kk == 0)
+            {
+                eb0 = ent;
+                rb0 = rv;
+            }
+            else if (kk == 1)
+            {
+                eb1 = ent;
+                rb1 = rv;
+            }
+            else if (kk == 2)
+            {
+                eb2 = ent;
+                rb2 = rv;
+            }
+            else if (cnt < nb_cap)
+            {
+                dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, eb1, eb2, ent);
+                rdst[size_t(cnt >> 2) * 32u] = make_double4(rb0, rb1, rb2, rv);
+            }
+            cnt++;
+        }
+    };
+    if (nchunk > 0)
+    {
+        uint4 id = sp[0];
+        for (int c = 0; c < nchunk; ++c)
+        {
+            uint4 idn = id;
+            if (c + 1 < nchunk)
+                idn = sp[size_t(c + 1) * 32u];
+            /* four independent gathers in flight (unused slots of the last chunk hold i itself) */
+            const double4 q0 = ldg256(P0, id.x & FJ_IDX_MASK);
+            const double4 q1 = ldg256(P0, id.y & FJ_IDX_MASK);
+            const double4 q2 = ldg256(P0, id.z & FJ_IDX_MASK);
+            const double4 q3 = ldg256(P0, id.w & FJ_IDX_MASK);
+            const int left = sc - (c << 2);
+            test(id.x, q0, true);
+            test(id.y, q1, left > 1);
+            test(id.z, q2, left > 2);
+            test(id.w, q3, left > 3);
+            id = idn;
+        }
+    }
     if ((cnt & 3) && cnt < nb_cap)
     {
-        /* partial last chunk; unused slots are never read (sweeps stop at ncount) */
-        dst[size_t(cnt >> 2) * 32u] = make_uint4(eb[0], eb[1], eb[2], unsigned(i));
-        rdst[size_t(cnt >> 2) * 32u] = make_double4(rb[0], rb[1], rb[2], 0.0);
+        /* partial last chunk; unused slots hold i itself (safe to gather) and are never consumed */
+        const int kk = cnt & 3;
+        dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, kk > 1 ? eb1 : unsigned(i), kk > 2 ? eb2 : unsigned(i), unsigned(i));
+        rdst[size_t(cnt >> 2) * 32u] = make_double4(rb0, kk > 1 ? rb1 : 0.0, kk > 2 ? rb2 : 0.0, 0.0);
     }
     ncount[i] = cnt;
     if (cnt > nb_cap)
@@ -435,27 +542,25 @@ static int ensure_list_capacity(FjsphEngine* e, int nb_cap)
     return FJSPH_OK;
 }
 
-int fj_build_neighbours(FjsphEngine* e)
+static int ensure_skin_capacity(FjsphEngine* e, int scap)
+{
+    const size_t words = size_t((e->cap + 31) / 32) * size_t(scap) * 32u;
+    if (scap <= e->scap && words <= e->slist_words)
+        return FJSPH_OK;
+    if (e->slist)
+        cudaFree(e->slist);
+    e->slist = nullptr;
+    FJ_CUDA(cudaMalloc(&e->slist, words * sizeof(unsigned)));
+    e->slist_words = words;
+    e->scap = scap;
+    return FJSPH_OK;
+}
+
+// full rebuild: bounds are in h_red[0..5]
+static int rebuild_skin(FjsphEngine* e)
 {
     const int n = int(e->n);
-    if (n <= 0)
-    {
-        fj_set_error("build_neighbours: no particles uploaded");
-        return FJSPH_ERR_STATE;
-    }
-    e->list_valid = false;
-    Level& S = e->lv[1];
     const int nb = fj_blocks(n, TPB);
-
-    // 1. bounds (one 48-byte readback: the grid shape decides table sizes on the host)
-    {
-        KScope ks(e, "nb_bounds", 2);
-        const int rb = std::min(nb, 1024);
-        k_bounds<<<rb, TPB, 0, e->stream>>>(S.P0, n, e->red);
-        k_bounds_final<<<1, 32, 0, e->stream>>>(e->red, rb, e->red_out);
-    }
-    FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 6 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    FJ_CUDA(cudaStreamSynchronize(e->stream));
     double lo[3] = {e->h_red[0], e->h_red[1], e->h_red[2]}, hi[3] = {e->h_red[3], e->h_red[4], e->h_red[5]};
     for (int d = 0; d < 3; ++d)
         if (!(std::isfinite(lo[d]) && std::isfinite(hi[d])))
@@ -463,10 +568,10 @@ int fj_build_neighbours(FjsphEngine* e)
             fj_set_error("build_neighbours: non-finite particle positions");
             return FJSPH_ERR_STATE;
         }
-
-    // 2. grid: cell edge a hair above the support radius 2H so +-1 cell always covers d < 2H
+    // grid: cell edge a hair above the skin radius 2H + skin so +-1 cell always covers it
     Grid g;
-    const double cell = std::sqrt(e->P.sr) * (1.0 + 1e-7);
+    const double r_skin = std::sqrt(e->P.sr) + e->skin;
+    const double cell = r_skin * (1.0 + 1e-7);
     g.inv_cell = 1.0 / cell;
     g.ox = lo[0];
     g.oy = lo[1];
@@ -524,7 +629,8 @@ int fj_build_neighbours(FjsphEngine* e)
     }
     e->grid = g;
 
-    // 3. counting sort by Morton key
+    // counting sort by Morton key
+    Level& S = e->lv[1];
     {
         KScope ks(e, "nb_sort", 7);
         FJ_CUDA(cudaMemsetAsync(e->cell_count, 0, size_t(g.n_keys) * sizeof(unsigned), e->stream));
@@ -540,15 +646,81 @@ int fj_build_neighbours(FjsphEngine* e)
     }
     FJ_CUDA(cudaGetLastError());
 
-    // 4. move both time levels into cell order
+    // move both time levels into cell order
     st = fj_permute_levels(e);
     if (st)
         return st;
 
-    // 5. neighbour list (retry with a larger per-particle capacity on overflow)
+    // skin list (retry with a larger per-particle capacity on overflow)
+    if (e->scap == 0)
+    {
+        /* expected count N_nb (1 + skin/2H)^3 with N_nb ~ 270, plus headroom */
+        const double f = r_skin / std::sqrt(e->P.sr);
+        const int want = ((int(300.0 * f * f * f) + 31) / 32) * 32;
+        st = ensure_skin_capacity(e, want);
+        if (st)
+            return st;
+    }
+    for (int attempt = 0; attempt < 4; ++attempt)
+    {
+        FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
+        {
+            KScope ks(e, "nb_skin", 1);
+            k_build_skin<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, g, e->mtab_x, e->mtab_y, e->mtab_z,
+                                                    e->cell_start, r_skin * r_skin, e->scap, e->slist, e->scount,
+                                                    e->xref, e->d_flag);
+        }
+        FJ_CUDA(cudaGetLastError());
+        FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        FJ_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->h_flag[0] == 0)
+        {
+            e->skin_valid = true;
+            e->skin_n = e->n;
+            e->skin_builds++;
+            return FJSPH_OK;
+        }
+        st = ensure_skin_capacity(e, ((e->h_flag[0] + 31) / 32) * 32 + 32);
+        if (st)
+            return st;
+    }
+    fj_set_error("skin list capacity could not be satisfied");
+    return FJSPH_ERR_CAPACITY;
+}
+
+int fj_build_neighbours(FjsphEngine* e)
+{
+    const int n = int(e->n);
+    if (n <= 0)
+    {
+        fj_set_error("build_neighbours: no particles uploaded");
+        return FJSPH_ERR_STATE;
+    }
+    e->list_valid = false;
+    const int nb = fj_blocks(n, TPB);
+    const bool have_skin = e->skin_valid && e->skin_n == e->n && e->skin > 0.0;
+
+    // 1. bounds and the largest displacement since the skin build (one 56-byte readback)
+    {
+        KScope ks(e, "nb_bounds", 2);
+        const int rb = std::min(nb, 1024);
+        k_bounds<<<rb, TPB, 0, e->stream>>>(e->lv[1].P0, have_skin ? e->xref : nullptr, n, e->red);
+        k_bounds_final<<<1, 7 * 32, 0, e->stream>>>(e->red, rb, e->red_out);
+    }
+    FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    const double lim = 0.49 * e->skin; /* valid while nobody moved more than skin/2 (a hair below, for rounding) */
+    if (!(have_skin && e->h_red[6] <= lim * lim))
+    {
+        int st = rebuild_skin(e);
+        if (st)
+            return st;
+    }
+
+    // 2. exact list (retry with a larger per-particle capacity on overflow)
     if (e->nb_cap == 0)
     {
-        st = ensure_list_capacity(e, 288);
+        int st = ensure_list_capacity(e, 288);
         if (st)
             return st;
     }
@@ -557,9 +729,8 @@ int fj_build_neighbours(FjsphEngine* e)
         FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
         {
             KScope ks(e, "nb_list", 1);
-            k_build_list<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, g, e->mtab_x, e->mtab_y, e->mtab_z,
-                                                    e->cell_start, e->P.sr, e->nb_cap, e->nlist, e->nr, e->ncount,
-                                                    e->d_flag);
+            k_exact_from_skin<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, n, e->slist, e->scount, e->scap, e->P.sr,
+                                                         e->nb_cap, e->nlist, e->nr, e->ncount, e->d_flag);
         }
         FJ_CUDA(cudaGetLastError());
         FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -571,7 +742,7 @@ int fj_build_neighbours(FjsphEngine* e)
             return FJSPH_OK;
         }
         const int want = ((e->h_flag[0] + 31) / 32) * 32 + 32;
-        st = ensure_list_capacity(e, want);
+        int st = ensure_list_capacity(e, want);
         if (st)
             return st;
     }

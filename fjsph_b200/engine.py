@@ -295,6 +295,10 @@ class Engine:
         """Run on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
         check(self._L.fjsph_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
+    def set_skin(self, skin_over_dx: float):
+        """Width of the neighbour superset list in units of dx (0 = cell-list sweep at every update_neighbours)."""
+        check(self._L.fjsph_set_skin(self._h, float(skin_over_dx)))
+
     @property
     def launch_count(self) -> int:
         return int(self._L.fjsph_launch_count(self._h))

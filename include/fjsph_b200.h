@@ -107,7 +107,8 @@ typedef struct FjsphStepStats
 {
     double dt, cfl_ratio, rms_error, maxRho_pc, maxf, maxAf, maxShift, safe_dt, npd, logbase;
     int32_t iterations, n_add, n_del, total_points;
-    int32_t force_evals, neighbour_builds, kernel_launches, reserved;
+    int32_t force_evals, neighbour_builds, kernel_launches;
+    int32_t skin_builds; /* cell-list sweeps behind those neighbour builds (the rest were filtered from the skin list) */
 } FjsphStepStats;
 
 typedef struct FjsphEngine FjsphEngine;
@@ -170,6 +171,13 @@ int64_t fjsph_launch_count(FjsphEngine* e);
  * engine's own; NULL goes back to a private stream.  The reference is single-threaded host code with no notion
  * of streams (FJSPH.cpp:262-283); this is what lets a host time or order the engine with its own events. */
 int fjsph_set_stream(FjsphEngine* e, void* cuda_stream);
+
+/* Neighbour-build policy.  update_neighbours (Neighbours.cpp:7-31) rebuilds the KD-tree and searches it at every
+ * call; the engine instead keeps a superset ("skin") list of every j within 2H + skin and filters the exact
+ * list { j : d2 < 4H^2 } from it with the bit-exact distance test at every call, falling back to a cell-list
+ * sweep when some particle has moved more than skin/2 since the superset was built.  The neighbour sets are
+ * identical either way.  skin_over_dx = 0 sweeps the cell list at every call; default 0.4. */
+int fjsph_set_skin(FjsphEngine* e, double skin_over_dx);
 
 /* Slab decomposition: ghost particles are appended by the caller's exchange layer.
  * The engine packs / unpacks halo records on the device; the transport (NCCL send/recv) lives in the

@@ -43,6 +43,37 @@ def test_neighbour_sets_bit_exact(name, case):
     assert np.array_equal(got["part_id"], np.arange(case["xi"].shape[0]))
 
 
+@pytest.mark.parametrize("jitter", ["eps", 0.1], ids=["lattice_eps", "jitter"])
+def test_neighbour_sets_through_skin_list(jitter):
+    """update_neighbours on moved particles: the exact list filtered from the superset ("skin") list is the
+    oracle's set, bit for bit, while the superset is still valid (moves < skin/2), after it has expired
+    (moves > skin/2 force a cell-list sweep) and with the superset disabled (skin = 0)."""
+    case = cases.synthetic_block((13, 10, 9), 1e-3, jitter=jitter, seed=11)
+    o, e, p = make_pair(case)
+    dx = 1e-3
+    rng = np.random.default_rng(5)
+    xi = case["xi"].copy()
+    o.update_neighbours()
+    e.update_neighbours()
+    base = e.integrate_no_update  # noqa: F841  (keeps the engine alive in tracebacks)
+    sweeps = []
+    for step, amp in enumerate((0.05, 0.05, 0.05, 0.3, 0.01)):
+        # amp*dx moves: three small ones (cumulative 0.15 dx < skin/2 = 0.2 dx), one big, one small again
+        xi = xi + rng.uniform(-1.0, 1.0, size=xi.shape) * (amp * dx / np.sqrt(3.0))
+        o.set("xi", xi)
+        e.upload_level(1, xi=xi)
+        o.update_neighbours()
+        e.update_neighbours()
+        off_o, idx_o, _ = o.neighbours()
+        off_e, idx_e = e.neighbours()
+        assert np.array_equal(off_o, off_e), step
+        assert np.array_equal(idx_o, idx_e), step
+    e.set_skin(0.0)
+    e.update_neighbours()
+    off_e, idx_e = e.neighbours()
+    assert np.array_equal(off_o, off_e) and np.array_equal(idx_o, idx_e)
+
+
 def run_stages(o, e, ale=True, check=True, label="", tol_eigen=TOL):
     o.update_neighbours()
     e.update_neighbours()
