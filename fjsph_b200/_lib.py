@@ -48,6 +48,11 @@ FjsphStateView = struct_from_header("FjsphStateView")
 FjsphStepStats = struct_from_header("FjsphStepStats")
 
 
+# FjsphCommFn, include/fjsph_b200.h
+COMM_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                      C.c_void_p, C.c_int64)
+
+
 def declared_functions(header: str = HEADER):
     """Names of every function the header declares (used by the CPU test that checks the exports)."""
     src = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
@@ -115,6 +120,8 @@ def lib():
     L.fjsph_launch_count.restype = C.c_int64
     L.fjsph_set_owned.argtypes = [vp, C.c_int64]
     L.fjsph_set_skin.argtypes = [vp, C.c_double]
+    L.fjsph_set_slab.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_double, COMM_FN, vp]
+    L.fjsph_slab_stats.argtypes = [vp, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)]
     _lib = L
     return L
 

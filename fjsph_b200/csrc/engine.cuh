@@ -64,6 +64,37 @@ struct Grid
     unsigned int n_keys;      // 2^(bx+by+bz)
 };
 
+// X(name): the double4 record arrays of a level, in halo-mask bit order
+#define FJ_D4_FIELDS(X) X(P0) X(P1) X(P2) X(P3) X(P4) X(ACC) X(AF) X(AV) X(CV) X(NP) X(BN) X(TH) X(SC)
+enum
+{
+    FJ_HX_P0 = 1 << 0, FJ_HX_P1 = 1 << 1, FJ_HX_P2 = 1 << 2, FJ_HX_P3 = 1 << 3, FJ_HX_P4 = 1 << 4,
+    FJ_HX_TH = 1 << 11, FJ_HX_SURFZONE = 1 << 13, FJ_HX_B = 1 << 14
+};
+
+// 1-D slab decomposition along x: this rank owns x in [x_lo, x_hi); ghosts are the neighbours'
+// particles within 2H + skin of the faces.  Transport is the host's (FjsphCommFn): the engine only packs
+// and unpacks on the device.
+struct Slab
+{
+    bool on = false;
+    int rank = 0, world = 1;
+    double x_lo = -1e300, x_hi = 1e300;
+    FjsphCommFn fn = nullptr;
+    void* user = nullptr;
+    int64_t n_send[2] = {0, 0}, n_recv[2] = {0, 0}; // side 0 = lower-x neighbour, 1 = upper-x neighbour
+    int* send_idx[2] = {nullptr, nullptr};          // caller indices of the owned particles sent as ghosts
+    int64_t send_cap = 0;
+    char* sbuf[2] = {nullptr, nullptr};
+    char* rbuf[2] = {nullptr, nullptr};
+    size_t buf_bytes = 0;
+    unsigned *flag[3] = {nullptr, nullptr, nullptr}, *scan[3] = {nullptr, nullptr, nullptr}; // classify scratch
+    int* list[3] = {nullptr, nullptr, nullptr};
+    unsigned* scan_tmp = nullptr;
+    double n_fluid_global = 0.0, n_total_global = 0.0;
+    long long exchanges = 0, redecomps = 0, bytes_sent = 0;
+};
+
 struct HostBlock
 {
     int64_t first, second;
@@ -159,6 +190,7 @@ struct FjsphEngine
 
     std::vector<HostBlock> blocks;
     int n_bound_blocks = 0;
+    Slab slab;
 
     // Integrator members, Integration.h:53-68
     double safe_dt = 0.0, maxf = 0.0, maxAf = 0.0, maxRho_pc = 0.0, maxRhoi = 0.0, maxdrho = 0.0, minST = 0.0,
@@ -215,3 +247,9 @@ int fj_permute_levels(FjsphEngine* e);
 int fj_reduce_sum(FjsphEngine* e, int nblocks, int ncomp, double* out_host);
 void fj_refresh_constants(FjsphEngine* e);
 void fj_timers_flush(FjsphEngine* e);
+// slab decomposition (halo.cu); all are no-ops / identities on a single rank
+int fj_halo_exchange(FjsphEngine* e, int level, unsigned mask);
+int fj_allreduce(FjsphEngine* e, int op, double* v, int n);
+int fj_redecompose(FjsphEngine* e);
+double fj_fluid_count(FjsphEngine* e);
+double fj_total_count(FjsphEngine* e);

@@ -17,6 +17,8 @@ namespace
 {
 constexpr int TPB = 256;
 #define FJ_PI 3.14159265358979323846
+// what a Newmark-Beta / RK update (or a wall treatment) changes on a particle and a neighbour reads
+constexpr unsigned FJ_HX_STATE = FJ_HX_P0 | FJ_HX_P1 | FJ_HX_P2 | FJ_HX_TH;
 
 struct BlockTable
 {
@@ -454,7 +456,7 @@ int fj_reduce_sum(FjsphEngine* e, int nblocks, int ncomp, double* out_host)
     FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, ncomp * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     FJ_CUDA(cudaStreamSynchronize(e->stream));
     for (int c = 0; c < ncomp; ++c) out_host[c] = e->h_red[c];
-    return FJSPH_OK;
+    return fj_allreduce(e, FJSPH_COMM_SUM, out_host, ncomp); /* slab decomposition: the sum over all ranks */
 }
 
 int fj_copy_level(FjsphEngine* e, int dst, int src)
@@ -479,6 +481,15 @@ int fj_find_timestep(FjsphEngine* e, double* dt_out)
     FJ_CUDA(cudaGetLastError());
     FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     FJ_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->slab.on)
+    {
+        double v[7];
+        for (int c = 0; c < 7; ++c) v[c] = (c == 4) ? -e->h_red[c] : e->h_red[c]; /* min as -max(-x) */
+        int st = fj_allreduce(e, FJSPH_COMM_MAX, v, 7);
+        if (st)
+            return st;
+        for (int c = 0; c < 7; ++c) e->h_red[c] = (c == 4) ? -v[c] : v[c];
+    }
     const FjsphParams& P = e->P;
     const double MEPS = 2.220446049250313e-16;
     e->maxf = std::max(MEPS, std::sqrt(e->h_red[0]));
@@ -519,6 +530,12 @@ int fj_nb_iter(FjsphEngine* e, double npd, double* errsum)
     st = fj_walls(e, 1, true);
     if (st)
         return st;
+    if (e->n_bound_blocks > 0)
+    {
+        st = fj_halo_exchange(e, 1, FJ_HX_STATE); /* wall rho, p, v seen by the neighbour rank's fluid */
+        if (st)
+            return st;
+    }
     st = fj_forces(e, 1, npd);
     if (st)
         return st;
@@ -536,6 +553,9 @@ int fj_nb_iter(FjsphEngine* e, double npd, double* errsum)
                                                           e->P.nb_gamma, n, e->red);
     }
     FJ_CUDA(cudaGetLastError());
+    st = fj_halo_exchange(e, 1, FJ_HX_STATE); /* x, v, rho, p of the ghosts for the next sweep */
+    if (st)
+        return st;
     double s = 0.0;
     st = fj_reduce_sum(e, nb, 1, &s);
     if (st)
@@ -550,13 +570,19 @@ static int frozen_terms(FjsphEngine* e, bool all)
     int st = fj_prestep(e, nullptr);
     if (st || !all)
         return st;
+    st = fj_halo_exchange(e, 1, FJ_HX_P3); /* gradRho_j, lam_j */
+    if (st)
+        return st;
     st = fj_aero_velocity(e);
     if (st)
         return st;
     st = fj_surface_and_dissipation(e, true, true, true); /* loops 2+3 fused with particle_shift (ALE) */
     if (st)
         return st;
-    return fj_check_pipe_outlet(e);
+    st = fj_check_pipe_outlet(e);
+    if (st)
+        return st;
+    return fj_halo_exchange(e, 1, FJ_HX_P2 | FJ_HX_SURFZONE | FJ_HX_B); /* vPert_j; surfzone_j and b_j for the walls */
 }
 
 static int rk_stage(FjsphEngine* e, double dt_s, double* errsum)
@@ -564,6 +590,12 @@ static int rk_stage(FjsphEngine* e, double dt_s, double* errsum)
     int st = fj_walls(e, 1, false);
     if (st)
         return st;
+    if (e->n_bound_blocks > 0)
+    {
+        st = fj_halo_exchange(e, 1, FJ_HX_STATE);
+        if (st)
+            return st;
+    }
     st = fj_forces(e, 1, e->npd);
     if (st)
         return st;
@@ -579,6 +611,9 @@ static int rk_stage(FjsphEngine* e, double dt_s, double* errsum)
                                                          e->near_inlet, e->C, dt_s, n, e->red);
     }
     FJ_CUDA(cudaGetLastError());
+    st = fj_halo_exchange(e, 1, FJ_HX_STATE);
+    if (st)
+        return st;
     if (errsum)
         return fj_reduce_sum(e, nb, 1, errsum);
     return FJSPH_OK;
@@ -616,7 +651,9 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
     e->iteration = 0;
     double rms_error = 0.0, logbase = 0.0;
     e->npd = 1.0;
-    const double nfluid = double(e->n_owned - e->bound_points);
+    /* fluid particles of the whole domain; with slabs it can change at the first neighbour build (migration
+     * keeps the global count), so it is read where it is used */
+    #define nfluid fj_fluid_count(e)
 
     st = fj_find_timestep(e, &e->P.delta_t);
     if (st)
@@ -668,6 +705,12 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
         st = fj_walls(e, 1, false);
         if (st)
             return st;
+        if (e->n_bound_blocks > 0)
+        {
+            st = fj_halo_exchange(e, 1, FJ_HX_STATE);
+            if (st)
+                return st;
+        }
         st = fj_forces(e, 1, e->npd);
         if (st)
             return st;
@@ -679,6 +722,9 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
                                                   e->rk_sum_v, e->rk_sum_a, e->C, e->P.delta_t, n, e->red);
         }
         FJ_CUDA(cudaGetLastError());
+        st = fj_halo_exchange(e, 1, FJ_HX_STATE);
+        if (st)
+            return st;
         st = fj_reduce_sum(e, nb, 1, &errsum);
         if (st)
             return st;
@@ -758,6 +804,7 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
         s->logbase = logbase;
         s->iterations = int(e->iteration);
         s->total_points = int(e->n_owned);
+#undef nfluid
         s->force_evals = e->force_evals;
         s->neighbour_builds = e->nb_builds;
         s->skin_builds = int(e->skin_builds - skin0);

@@ -16,6 +16,7 @@
 #include <cstdio>
 
 #include "engine.cuh"
+#include "prims.cuh"
 
 namespace
 {
@@ -106,7 +107,7 @@ __device__ __forceinline__ void cell_of(const Grid& g, double x, double y, doubl
     cz = min(max(int(floor((z - g.oz) * g.inv_cell)), 0), g.nz - 1);
 }
 
-__global__ void k_key_hist(const double4* __restrict__ P0, int n, Grid g, const unsigned* __restrict__ mx,
+__global__ void k_key_hist(const double4* __restrict__ P0, int n, int n_owned, Grid g, const unsigned* __restrict__ mx,
                            const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
                            unsigned* __restrict__ key, unsigned* __restrict__ rank, unsigned* __restrict__ count)
 {
@@ -119,6 +120,8 @@ __global__ void k_key_hist(const double4* __restrict__ P0, int n, Grid g, const 
         int cx, cy, cz;
         cell_of(g, a.x, a.y, a.z, cx, cy, cz);
         k = mx[cx] | my[cy] | mz[cz];
+        if (i >= n_owned)
+            k += g.n_keys; /* ghosts sort behind the owned particles: slots [0, n_owned) stay the owned ones */
         key[i] = k;
     }
     // warp-aggregated atomics: one atomicAdd per distinct key in the warp
@@ -130,118 +133,6 @@ __global__ void k_key_hist(const double4* __restrict__ P0, int n, Grid g, const 
     base = __shfl_sync(0xffffffffu, base, leader);
     if (i < n)
         rank[i] = base + __popc(peers & ((1u << lane) - 1u));
-}
-
-// ---------------------------------------------------------------- block prefix scan (exclusive)
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = TPB * SCAN_ITEMS;
-
-__global__ void k_scan_tiles(const unsigned* __restrict__ in, unsigned* __restrict__ out, unsigned n,
-                             unsigned* __restrict__ tile_sum)
-{
-    __shared__ unsigned warp_tot[TPB / 32];
-    const unsigned base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    unsigned v[SCAN_ITEMS];
-    unsigned s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k)
-    {
-        v[k] = (base + k < n) ? in[base + k] : 0u;
-        s += v[k];
-    }
-    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned inc = s;
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= unsigned(o))
-            inc += t;
-    }
-    if (lane == 31)
-        warp_tot[w] = inc;
-    __syncthreads();
-    if (w == 0)
-    {
-        unsigned t = (lane < TPB / 32) ? warp_tot[lane] : 0u;
-        unsigned ti = t;
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            unsigned u = __shfl_up_sync(0xffffffffu, ti, o);
-            if (lane >= unsigned(o))
-                ti += u;
-        }
-        if (lane < TPB / 32)
-            warp_tot[lane] = ti - t; // exclusive warp offsets
-        if (lane == TPB / 32 - 1)
-            tile_sum[blockIdx.x] = ti;
-    }
-    __syncthreads();
-    unsigned run = warp_tot[w] + inc - s;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k)
-    {
-        if (base + k < n)
-            out[base + k] = run;
-        run += v[k];
-    }
-}
-
-// single block: exclusive scan of tile sums in place, total written to tile_sum[ntiles]
-__global__ void k_scan_tile_sums(unsigned* __restrict__ tile_sum, unsigned ntiles)
-{
-    __shared__ unsigned warp_tot[32];
-    __shared__ unsigned carry_s;
-    if (threadIdx.x == 0)
-        carry_s = 0;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (unsigned start = 0; start < ntiles; start += blockDim.x)
-    {
-        const unsigned idx = start + threadIdx.x;
-        const unsigned v = (idx < ntiles) ? tile_sum[idx] : 0u;
-        unsigned inc = v;
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= unsigned(o))
-                inc += t;
-        }
-        if (lane == 31)
-            warp_tot[w] = inc;
-        __syncthreads();
-        if (w == 0)
-        {
-            unsigned t = (lane < (blockDim.x >> 5)) ? warp_tot[lane] : 0u;
-            unsigned ti = t;
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                unsigned u = __shfl_up_sync(0xffffffffu, ti, o);
-                if (lane >= unsigned(o))
-                    ti += u;
-            }
-            warp_tot[lane] = ti - t;
-        }
-        __syncthreads();
-        const unsigned carry = carry_s;
-        if (idx < ntiles)
-            tile_sum[idx] = carry + warp_tot[w] + inc - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1)
-            carry_s = carry + warp_tot[w] + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0)
-        tile_sum[ntiles] = carry_s;
-}
-
-__global__ void k_scan_add(unsigned* __restrict__ out, unsigned n, const unsigned* __restrict__ tile_sum,
-                           unsigned ntiles)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n)
-        out[i] += tile_sum[i / SCAN_TILE];
-    if (i == 0)
-        out[n] = tile_sum[ntiles];
 }
 
 // ---------------------------------------------------------------- scatter + deterministic cell order
@@ -277,18 +168,6 @@ __global__ void k_cell_order(const unsigned* __restrict__ cell_start, unsigned n
     }
 }
 
-// ---------------------------------------------------------------- permute one level
-__global__ void k_permute_level(Level in, Level out, const int* __restrict__ perm, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
-    const int s = perm[i];
-#define X(T, f) out.f[i] = in.f[s];
-    FJ_LEVEL_FIELDS(X)
-#undef X
-}
-
 __global__ void k_permute_index(const int* __restrict__ oidx_in, const int* __restrict__ blk_in,
                                 const int* __restrict__ perm, int n, int* __restrict__ oidx_out,
                                 int* __restrict__ blk_out, int* __restrict__ slot_of)
@@ -317,7 +196,7 @@ __device__ __forceinline__ double4 ldg256(const double4* __restrict__ base, unsi
 }
 
 __global__ void __launch_bounds__(TPB)
-    k_build_skin(const double4* __restrict__ P0, const int* __restrict__ b, int n, Grid g,
+    k_build_skin(const double4* __restrict__ P0, const int* __restrict__ b, int n, int n_owned, Grid g,
                  const unsigned* __restrict__ mx, const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
                  const unsigned* __restrict__ cell_start, double sr_skin, int scap, unsigned* __restrict__ slist,
                  int* __restrict__ scount, double4* __restrict__ xref, int* __restrict__ flag)
@@ -327,6 +206,9 @@ __global__ void __launch_bounds__(TPB)
         return;
     const double4 a = P0[i];
     xref[i] = a;
+    if (i >= n_owned)
+        return; /* ghosts are neighbours only */
+    const int n_seg = (n > n_owned) ? 2 : 1;
     int cx, cy, cz;
     cell_of(g, a.x, a.y, a.z, cx, cy, cz);
     uint4* __restrict__ dst = reinterpret_cast<uint4*>(slist) + (size_t(i >> 5) * size_t(scap >> 2)) * 32u + (i & 31);
@@ -349,7 +231,9 @@ __global__ void __launch_bounds__(TPB)
                 const int x = cx + dx;
                 if (x < 0 || x >= g.nx)
                     continue;
-                const unsigned k = kyz | mx[x];
+                for (int seg = 0; seg < n_seg; ++seg)
+                {
+                const unsigned k = (kyz | mx[x]) + (seg ? g.n_keys : 0u);
                 const unsigned s = cell_start[k], e = cell_start[k + 1];
                 for (unsigned j = s; j < e; ++j)
                 {
@@ -375,6 +259,7 @@ __global__ void __launch_bounds__(TPB)
                             dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, eb1, eb2, ent);
                         cnt++;
                     }
+                }
                 }
             }
         }
@@ -588,7 +473,8 @@ static int rebuild_skin(FjsphEngine* e)
         return FJSPH_ERR_CAPACITY;
     }
     g.n_keys = 1u << (g.bx + g.by + g.bz);
-    int st = ensure_key_capacity(e, g.n_keys);
+    const unsigned n_tab = (e->n > e->n_owned) ? 2u * g.n_keys : g.n_keys; /* second half: ghost cells */
+    int st = ensure_key_capacity(e, n_tab);
     if (st)
         return st;
     // Morton spread tables: bit l of each axis is placed round-robin x,y,z among the axes that still have bits
@@ -633,16 +519,13 @@ static int rebuild_skin(FjsphEngine* e)
     Level& S = e->lv[1];
     {
         KScope ks(e, "nb_sort", 7);
-        FJ_CUDA(cudaMemsetAsync(e->cell_count, 0, size_t(g.n_keys) * sizeof(unsigned), e->stream));
-        k_key_hist<<<nb, TPB, 0, e->stream>>>(S.P0, n, g, e->mtab_x, e->mtab_y, e->mtab_z, e->key, e->rank_in_cell,
+        FJ_CUDA(cudaMemsetAsync(e->cell_count, 0, size_t(n_tab) * sizeof(unsigned), e->stream));
+        k_key_hist<<<nb, TPB, 0, e->stream>>>(S.P0, n, int(e->n_owned), g, e->mtab_x, e->mtab_y, e->mtab_z, e->key, e->rank_in_cell,
                                               e->cell_count);
-        const unsigned ntiles = (g.n_keys + SCAN_TILE - 1) / SCAN_TILE;
-        k_scan_tiles<<<ntiles, TPB, 0, e->stream>>>(e->cell_count, e->cell_start, g.n_keys, e->scan_tmp);
-        k_scan_tile_sums<<<1, 1024, 0, e->stream>>>(e->scan_tmp, ntiles);
-        k_scan_add<<<fj_blocks(g.n_keys, TPB), TPB, 0, e->stream>>>(e->cell_start, g.n_keys, e->scan_tmp, ntiles);
+        prim_exclusive_scan(e->stream, e->cell_count, e->cell_start, n_tab, e->scan_tmp);
         k_scatter<<<nb, TPB, 0, e->stream>>>(e->key, e->rank_in_cell, e->cell_start, n, e->perm2);
-        k_cell_order<<<fj_blocks(int64_t(g.n_keys) * 32, TPB), TPB, 0, e->stream>>>(e->cell_start, g.n_keys, e->perm2,
-                                                                                   e->oidx, e->perm);
+        k_cell_order<<<fj_blocks(int64_t(n_tab) * 32, TPB), TPB, 0, e->stream>>>(e->cell_start, n_tab, e->perm2, e->oidx,
+                                                                                 e->perm);
     }
     FJ_CUDA(cudaGetLastError());
 
@@ -666,7 +549,7 @@ static int rebuild_skin(FjsphEngine* e)
         FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
         {
             KScope ks(e, "nb_skin", 1);
-            k_build_skin<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, g, e->mtab_x, e->mtab_y, e->mtab_z,
+            k_build_skin<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, int(e->n_owned), g, e->mtab_x, e->mtab_y, e->mtab_z,
                                                     e->cell_start, r_skin * r_skin, e->scap, e->slist, e->scount,
                                                     e->xref, e->d_flag);
         }
@@ -710,8 +593,29 @@ int fj_build_neighbours(FjsphEngine* e)
     FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     FJ_CUDA(cudaStreamSynchronize(e->stream));
     const double lim = 0.49 * e->skin; /* valid while nobody moved more than skin/2 (a hair below, for rounding) */
-    if (!(have_skin && e->h_red[6] <= lim * lim))
+    double moved = (have_skin && e->h_red[6] <= lim * lim) ? 0.0 : 1.0;
+    if (e->slab.on)
     {
+        /* all ranks rebuild together: the ghost sets are only re-made with the superset lists */
+        int st = fj_allreduce(e, FJSPH_COMM_MAX, &moved, 1);
+        if (st)
+            return st;
+    }
+    if (moved != 0.0)
+    {
+        if (e->slab.on && e->slab.world > 1)
+        {
+            int st = fj_redecompose(e); /* migration + new ghost sets; particle counts change */
+            if (st)
+                return st;
+            const int n2 = int(e->n);
+            const int rb = std::min(fj_blocks(n2, TPB), 1024);
+            k_bounds<<<rb, TPB, 0, e->stream>>>(e->lv[1].P0, nullptr, n2, e->red);
+            k_bounds_final<<<1, 7 * 32, 0, e->stream>>>(e->red, rb, e->red_out);
+            e->launches += 2;
+            FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            FJ_CUDA(cudaStreamSynchronize(e->stream));
+        }
         int st = rebuild_skin(e);
         if (st)
             return st;
@@ -729,7 +633,7 @@ int fj_build_neighbours(FjsphEngine* e)
         FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
         {
             KScope ks(e, "nb_list", 1);
-            k_exact_from_skin<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, n, e->slist, e->scount, e->scap, e->P.sr,
+            k_exact_from_skin<<<fj_blocks(e->n_owned, TPB), TPB, 0, e->stream>>>(e->lv[1].P0, int(e->n_owned), e->slist, e->scount, e->scap, e->P.sr,
                                                          e->nb_cap, e->nlist, e->nr, e->ncount, e->d_flag);
         }
         FJ_CUDA(cudaGetLastError());

@@ -1105,7 +1105,7 @@ int fj_prestep(FjsphEngine* e, double* npd)
     if (st)
         return st;
     /* npd = npd_ / end (Shifting.cpp:121); Q4: the race-free sum */
-    e->npd = sum / double(e->n_owned);
+    e->npd = sum / fj_total_count(e);
     if (npd)
         *npd = e->npd;
     return FJSPH_OK;
@@ -1150,6 +1150,12 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
     {
         KScope ks(e, "diss", 1);
         k_surf1_diss<false, true><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+    }
+    if (do_surface)
+    {
+        st = fj_halo_exchange(e, 1, FJ_HX_P4); /* loop-1 normals and surf flags of the ghosts */
+        if (st)
+            return st;
     }
     if (do_surface && fuse_shift && e->P.ale)
     {

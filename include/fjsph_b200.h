@@ -179,9 +179,22 @@ int fjsph_set_stream(FjsphEngine* e, void* cuda_stream);
  * identical either way.  skin_over_dx = 0 sweeps the cell list at every call; default 0.4. */
 int fjsph_set_skin(FjsphEngine* e, double skin_over_dx);
 
-/* Slab decomposition: ghost particles are appended by the caller's exchange layer.
- * The engine packs / unpacks halo records on the device; the transport (NCCL send/recv) lives in the
- * host layer (fjsph_b200/slab.py).  See DESIGN.md "Multi-GPU". */
+/* Slab decomposition.  The reference is one shared-memory process (OpenMP only, FJSPH.cpp:62); large
+ * cases are split into x-slabs, one engine per GPU.  Rank r owns the particles with x in [x_lo, x_hi) (the end
+ * ranks pass -/+1e300).  The engine selects, packs and unpacks migrating and ghost particles on the device; the
+ * transport belongs to the host, which supplies one callback used for every exchange:
+ *   op FJSPH_COMM_SUM / MAX : all-reduce of the host array a (na/8 doubles) in place;
+ *   op FJSPH_COMM_SENDRECV_DEV / _HOST : send a (na bytes) to rank-1 and b (nb bytes) to rank+1, receive c (nc bytes)
+ *      from rank-1 and d (nd bytes) from rank+1; device or host pointers respectively; zero sizes at the domain ends.
+ * The callback returns 0 on success.  fjsph_b200/slab.py implements it with NCCL send/recv over NVLink
+ * (torch.distributed); upload the rank's own particles with fjsph_upload_state first, then call fjsph_set_slab. */
+enum { FJSPH_COMM_SUM = 0, FJSPH_COMM_MAX = 1, FJSPH_COMM_SENDRECV_DEV = 2, FJSPH_COMM_SENDRECV_HOST = 3 };
+typedef int (*FjsphCommFn)(void* user, int32_t op, void* a, int64_t na, void* b, int64_t nb, void* c, int64_t nc,
+                           void* d, int64_t nd);
+int fjsph_set_slab(FjsphEngine* e, int32_t rank, int32_t world, double x_lo, double x_hi, FjsphCommFn fn, void* user);
+/* owned / ghost particle counts, halo exchanges, re-decompositions and bytes sent since fjsph_set_slab */
+int fjsph_slab_stats(FjsphEngine* e, int64_t* n_owned, int64_t* n_ghost, int64_t* exchanges, int64_t* redecomps,
+                     int64_t* bytes_sent);
 int fjsph_set_owned(FjsphEngine* e, int64_t n_owned);
 
 #ifdef __cplusplus
