@@ -140,8 +140,14 @@ def cpu_reference(args, steps, warmup, sample_cells):
     from oracle import oracle as orc  # bench.py's CPU-baseline leg: the checker timed as the baseline
 
     subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "lib/liborc3d_fast.so"])
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; the baseline gets every host core
+    try:
+        import ctypes
+
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)  # in case libgomp was initialised before
+    except OSError:
+        pass
     case = make_case(args, 0, cells=sample_cells) if args.workload == "block" else make_case(args)
     params = step_params(args, case["params"])
     o = orc.Oracle(orc.default_params(3, kind="3d_fast", **params), kind="3d_fast")
@@ -209,7 +215,14 @@ def main():
     if world > 1:
         from fjsph_b200 import slab
 
-        e = slab.SlabEngine(eng.default_params(3, **params), case, rank, world, local_rank, stream)
+        # rank r owns lattice columns [r*nx, (r+1)*nx): faces half a spacing outside its first / last column
+        nx = int(args.cells.split(",")[0])
+        dx = case["params"]["particle_step"]
+        x_lo = -1e300 if rank == 0 else (rank * nx - 0.5) * dx
+        x_hi = 1e300 if rank == world - 1 else ((rank + 1) * nx - 0.5) * dx
+        with torch.cuda.stream(stream):
+            e = slab.SlabEngine(eng.default_params(3, **params), case, rank, world, x_lo, x_hi, device=local_rank,
+                                stream=stream, part_id=np.arange(n, dtype=np.int64) + rank * n)
     else:
         e = eng.Engine(eng.default_params(3, **params), n, device=local_rank)
         e.set_stream(stream.cuda_stream)
@@ -306,7 +319,38 @@ def main():
         e2e = {"value": n_fluid * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt / args.steps * 1e3}
     elif not args.no_e2e:
-        e2e = e.e2e(args.steps)
+        # every rank round-trips its own slab through pinned host memory each step (upload -> step -> download)
+        def pinned(a):
+            t_ = torch.empty(a.shape, dtype=torch.from_numpy(a).dtype, pin_memory=True)
+            t_.numpy()[...] = a
+            return t_
+
+        fields = ("xi", "v", "acc", "rho", "Rrho", "p", "m", "b", "part_id")
+        out_fields = fields  # migration reorders the owned set, so every per-particle array comes back
+        with torch.cuda.stream(stream):
+            st = e.download(fields)
+            ins_t = {k: pinned(v) for k, v in st.items()}
+            n_own = st["xi"].shape[0]
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ins = {k: v.numpy()[:n_own] for k, v in ins_t.items()}
+                e.reupload_owned(ins)
+                e.integrate()
+                n_own = e.n
+                for k in ins_t:  # migration changes the owned count by a few particles
+                    if ins_t[k].shape[0] < n_own:
+                        ins_t[k] = pinned(np.resize(ins_t[k].numpy(), (int(n_own * 1.01),) + tuple(ins_t[k].shape[1:])))
+                e.download(out_fields, out={k: ins_t[k].numpy()[:n_own] for k in out_fields})
+            barrier()
+            dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = sum(v.numpy()[:n_own].nbytes for v in ins_t.values())
+        d2h = sum(ins_t[k].numpy()[:n_own].nbytes for k in out_fields)
+        e2e = {"value": total_fluid * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt / args.steps * 1e3, "note": "bytes are per rank"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -327,6 +371,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(cnt[1].item()),
             "clocks": clocks, "kernels": kernels,
         }
+        if world > 1:
+            line["slab"] = e.slab_stats()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -98,6 +98,7 @@ def lib():
     L.fjsph_upload_state.argtypes = [vp, P(FjsphStateView), C.c_int64]
     L.fjsph_upload_level.argtypes = [vp, C.c_int, P(FjsphStateView)]
     L.fjsph_download_state.argtypes = [vp, C.c_int, P(FjsphStateView)]
+    L.fjsph_upload_owned.argtypes = [vp, P(FjsphStateView)]
     L.fjsph_count.argtypes = [vp]
     L.fjsph_count.restype = C.c_int64
     L.fjsph_build_neighbours.argtypes = [vp]

@@ -878,6 +878,26 @@ int fjsph_upload_level(FjsphEngine* e, int level, const FjsphStateView* s)
     return FJSPH_OK;
 }
 
+int fjsph_upload_owned(FjsphEngine* e, const FjsphStateView* s)
+{
+    cudaSetDevice(e->device);
+    if (!s || s->n != e->n_owned)
+    {
+        fj_set_error("upload_owned: view holds %lld particles, this rank owns %lld", s ? (long long)s->n : -1LL,
+                     (long long)e->n_owned);
+        return FJSPH_ERR_INVALID;
+    }
+    for (int level = 0; level < 2; ++level)
+    {
+        int st = upload_fields(e, level, s);
+        if (st)
+            return st;
+        FJ_CUDA(cudaStreamSynchronize(e->stream)); /* the staging buffer is reused */
+    }
+    e->list_valid = false;
+    return fj_halo_exchange(e, 1, FJ_HX_P0 | FJ_HX_P1 | FJ_HX_P2 | FJ_HX_TH);
+}
+
 int fjsph_download_state(FjsphEngine* e, int level, FjsphStateView* s)
 {
     cudaSetDevice(e->device);

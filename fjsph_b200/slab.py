@@ -142,6 +142,13 @@ class SlabEngine(eng.Engine):
             self._raise_transport_error()
             raise
 
+    def reupload_owned(self, fields: dict):
+        """Overwrite both time levels of the OWNED particles from host arrays given in the current download order
+        (hosts that keep the particles on the CPU between steps); ghosts are refreshed by the next exchanges."""
+        n = self.n
+        view, keep = eng.make_view(dict(fields), n)
+        check(self._L.fjsph_upload_owned(self._h, C.byref(view)))
+
     def slab_stats(self) -> dict:
         v = [C.c_int64() for _ in range(5)]
         check(self._L.fjsph_slab_stats(self._h, *[C.byref(x) for x in v]))

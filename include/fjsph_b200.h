@@ -195,6 +195,10 @@ int fjsph_set_slab(FjsphEngine* e, int32_t rank, int32_t world, double x_lo, dou
 /* owned / ghost particle counts, halo exchanges, re-decompositions and bytes sent since fjsph_set_slab */
 int fjsph_slab_stats(FjsphEngine* e, int64_t* n_owned, int64_t* n_ghost, int64_t* exchanges, int64_t* redecomps,
                      int64_t* bytes_sent);
+/* Slab mode: overwrite the given fields of BOTH time levels of the owned particles (s->n == fjsph_count, in the
+ * order fjsph_download_state returns them), keeping the decomposition; the end-to-end path of a host that holds
+ * the particles between steps.  Positions may have changed: the neighbour lists are rebuilt by the next step. */
+int fjsph_upload_owned(FjsphEngine* e, const FjsphStateView* s);
 int fjsph_set_owned(FjsphEngine* e, int64_t n_owned);
 
 #ifdef __cplusplus
