@@ -137,3 +137,43 @@ def dam_2d(dx=0.02):
     case = box_with_walls(n=(int(round(2.0 / dx)), int(round(1.0 / dx))), dx=dx, layers=4, c=125.0, hydro=True, dim=2)
     case["params"].update(dict(visc_alpha=0.1, dsph_delta=0.1, sig=0.0))
     return case
+
+
+def inlet_jet(n=(5, 5, 4), dx=1e-3, v_jet=10.0, fixed=0, n_buf=4, aero_x=1.5, delete_x=None, rho0=1000.0, c=100.0,
+              jitter="eps", seed=21):
+    """A square inlet block along +x (the squareCube branch of InletShape::generate_points, shapes/inlet.cpp:455-520,
+    without rotation): nk PIPE layers at x = -k dx, one BACK layer at x = -nk dx and n_buf BUFFER layers behind
+    it; insertion plane normal (1,0,0) with insconst = -(nk - 0.01) dx (inlet.cpp:207-210), aero entry plane at
+    aero_x*dx (PIPE -> FREE, Containment.cpp:822-847), optional delete plane at delete_x*dx (Integration.cpp:127-205).
+    Returns the case plus the bound_block fields of its single fluid block."""
+    ni, nj, nk = n
+    rng = np.random.default_rng(seed)
+    pts, b = [], []
+    layers = list(range(nk)) + [nk] + list(range(nk + 1, nk + 1 + n_buf))
+    kinds = [PIPE] * nk + [BACK] + [BUFFER] * n_buf
+    for kk, kind in zip(layers, kinds):
+        for jj in range(nj):
+            for ii in range(ni):
+                pts.append((-kk * dx, ii * dx, jj * dx))
+                b.append(kind)
+    xi = np.asarray(pts, dtype=np.float64)
+    if jitter == "eps":
+        xi = xi + rng.uniform(0.0, EPS * dx, size=xi.shape)
+    elif jitter is not None:
+        xi = xi + rng.uniform(-float(jitter), float(jitter), size=xi.shape) * dx
+    ncol = ni * nj
+    back = np.arange(nk * ncol, (nk + 1) * ncol, dtype=np.int64)
+    buffer = np.stack([np.arange((nk + 1 + r) * ncol, (nk + 2 + r) * ncol, dtype=np.int64) for r in range(n_buf)], axis=1)
+    N = xi.shape[0]
+    v = np.zeros_like(xi)
+    v[:, 0] = v_jet
+    block = dict(first=0, second=N, is_fluid=1, block_type=6, fixed_vel_or_dynamic=int(fixed), insert_norm=(1.0, 0.0, 0.0),
+                 insconst=-(nk - 0.01) * dx, aero_norm=(1.0, 0.0, 0.0), aeroconst=aero_x * dx, back=back, buffer=buffer)
+    if delete_x is not None:
+        block.update(delete_norm=(1.0, 0.0, 0.0), delconst=delete_x * dx)
+    return dict(
+        xi=xi, v=v, rho=np.full(N, rho0), p=np.zeros(N), m=np.full(N, rho0 * dx**3), b=np.asarray(b, dtype=np.int32),
+        bound_points=0, block=block,
+        params=dict(particle_step=dx, rho_rest=rho0, speed_sound=c, mu=8.94e-4, sig=0.0708, visc_alpha=0.05,
+                    delta_t_min=1e-9, frame_time_interval=1e9),
+    )

@@ -710,6 +710,15 @@ int fjsph_destroy(FjsphEngine* e)
         FJ_LEVEL_FIELDS(X)
 #undef X
     }
+    for (HostBlock& B : e->blocks)
+    {
+        if (B.d_back)
+            cudaFree(B.d_back);
+        if (B.d_buffer)
+            cudaFree(B.d_buffer);
+    }
+    if (e->scan_particles)
+        cudaFree(e->scan_particles);
     void* ptrs[] = {e->oidx,       e->oidx_tmp, e->slot_of,  e->blk,      e->blk_tmp,   e->key,     e->rank_in_cell,
                     e->perm,       e->perm2,    e->ncount,   e->near_inlet, e->rk_sum_v, e->rk_sum_a, e->red,
                     e->red_out,    e->d_flag,   e->stage,    e->cell_count, e->cell_start, e->scan_tmp, e->mtab_x,
@@ -807,7 +816,15 @@ int fjsph_set_blocks(FjsphEngine* e, int32_t n_blocks, const FjsphBlock* blocks)
         fj_set_error("set_blocks: at least one fluid block is required");
         return FJSPH_ERR_INVALID;
     }
+    for (HostBlock& B : e->blocks)
+    {
+        if (B.d_back)
+            cudaFree(B.d_back);
+        if (B.d_buffer)
+            cudaFree(B.d_buffer);
+    }
     e->blocks = out;
+    e->inlet_tables_dirty = true;
     e->n_bound_blocks = n_bound;
     if (e->n > 0)
         return rebuild_blk(e);
@@ -840,6 +857,8 @@ int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_po
     e->bound_points = bound_points;
     e->list_valid = false;
     e->skin_valid = false; /* slots are reset to the caller's order below */
+    e->next_part_id = s->n;
+    e->inlet_tables_dirty = true;
     const int n = int(e->n);
     e->launches += 2;
     k_identity_index<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->oidx, e->slot_of, n);

@@ -104,6 +104,7 @@ struct HostBlock
     double insert_norm[3], insconst, delete_norm[3], delconst, aero_norm[3], aeroconst;
     std::vector<int64_t> back;
     std::vector<std::vector<int64_t>> buffer;
+    int *d_back = nullptr, *d_buffer = nullptr; // device copies of back / buffer (caller indices)
 };
 
 struct Timer
@@ -190,6 +191,8 @@ struct FjsphEngine
 
     std::vector<HostBlock> blocks;
     int n_bound_blocks = 0;
+    bool inlet_tables_dirty = true;
+    unsigned* scan_particles = nullptr; // scan scratch sized for the particle count (delete planes)
     Slab slab;
 
     // Integrator members, Integration.h:53-68
@@ -253,3 +256,7 @@ int fj_allreduce(FjsphEngine* e, int op, double* v, int n);
 int fj_redecompose(FjsphEngine* e);
 double fj_fluid_count(FjsphEngine* e);
 double fj_total_count(FjsphEngine* e);
+// inlet buffer regions and end-of-step bookkeeping (inlet.cu)
+bool fj_has_inlets(FjsphEngine* e);
+int fj_inlet_motion(FjsphEngine* e, double dt, bool nb_solver, int* n_partials);
+int fj_update_data(FjsphEngine* e, int* n_add, int* n_del);

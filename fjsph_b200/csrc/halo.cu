@@ -57,14 +57,6 @@ __global__ void k_ghost_flags(const double4* __restrict__ P0, int n_owned, doubl
     f_hi[i] = !(x < x_ghost_hi);
 }
 
-__global__ void k_compact(const unsigned* __restrict__ flag, const unsigned* __restrict__ scan, int n,
-                          int* __restrict__ list)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && flag[i])
-        list[scan[i]] = i;
-}
-
 // whole-level pack / unpack (migration, ghost creation)
 __global__ void k_pack_level(Level L, const int* __restrict__ blk, const int* __restrict__ slots, int cnt,
                              char* __restrict__ buf)

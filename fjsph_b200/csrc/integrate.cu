@@ -436,12 +436,11 @@ int check_supported(FjsphEngine* e)
         fj_set_error("more than 64 boundary blocks are not supported");
         return FJSPH_ERR_INVALID;
     }
-    for (const HostBlock& B : e->blocks)
-        if (B.block_type == FJSPH_INLET_ZONE)
-        {
-            fj_set_error("inlet blocks (buffer/back particles, update_buffer_region) are not on the device path yet");
-            return FJSPH_ERR_INVALID;
-        }
+    if (e->slab.on && e->slab.world > 1 && fj_has_inlets(e))
+    {
+        fj_set_error("inlet blocks are not available with slab decomposition yet");
+        return FJSPH_ERR_INVALID;
+    }
     return FJSPH_OK;
 }
 
@@ -553,11 +552,15 @@ int fj_nb_iter(FjsphEngine* e, double npd, double* errsum)
                                                           e->P.nb_gamma, n, e->red);
     }
     FJ_CUDA(cudaGetLastError());
+    int nparts = nb;
+    st = fj_inlet_motion(e, e->P.delta_t, true, &nparts); /* BUFFER particles, Newmark_Beta.cpp:243-297 */
+    if (st)
+        return st;
     st = fj_halo_exchange(e, 1, FJ_HX_STATE); /* x, v, rho, p of the ghosts for the next sweep */
     if (st)
         return st;
     double s = 0.0;
-    st = fj_reduce_sum(e, nb, 1, &s);
+    st = fj_reduce_sum(e, nparts, 1, &s);
     if (st)
         return st;
     if (errsum)
@@ -611,11 +614,15 @@ static int rk_stage(FjsphEngine* e, double dt_s, double* errsum)
                                                          e->near_inlet, e->C, dt_s, n, e->red);
     }
     FJ_CUDA(cudaGetLastError());
+    int nparts = nb;
+    st = fj_inlet_motion(e, dt_s, false, &nparts); /* Runge_Kutta.cpp:175-228 */
+    if (st)
+        return st;
     st = fj_halo_exchange(e, 1, FJ_HX_STATE);
     if (st)
         return st;
     if (errsum)
-        return fj_reduce_sum(e, nb, 1, errsum);
+        return fj_reduce_sum(e, nparts, 1, errsum);
     return FJSPH_OK;
 }
 
@@ -722,10 +729,14 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
                                                   e->rk_sum_v, e->rk_sum_a, e->C, e->P.delta_t, n, e->red);
         }
         FJ_CUDA(cudaGetLastError());
+        int nparts = nb;
+        st = fj_inlet_motion(e, e->P.delta_t, false, &nparts); /* Runge_Kutta.cpp:397-452 */
+        if (st)
+            return st;
         st = fj_halo_exchange(e, 1, FJ_HX_STATE);
         if (st)
             return st;
-        st = fj_reduce_sum(e, nb, 1, &errsum);
+        st = fj_reduce_sum(e, nparts, 1, &errsum);
         if (st)
             return st;
         rms_error = std::log10(std::sqrt(errsum / nfluid)) - logbase;
@@ -822,9 +833,16 @@ int fj_step(FjsphEngine* e, FjsphStepStats* s)
     int st = fj_integrate_no_update(e, ss);
     if (st)
         return st;
+    int n_add = 0, n_del = 0;
+    st = fj_update_data(e, &n_add, &n_del); /* inlet insertion, delete planes; Integration.cpp:109-226 */
+    if (st)
+        return st;
     st = fj_copy_level(e, 0, 1); /* pn = pnp1 */
     if (st)
         return st;
+    ss->n_add = n_add;
+    ss->n_del = n_del;
+    ss->total_points = int(e->n_owned);
     ss->kernel_launches = int(e->launches - launches0);
     FjsphParams& P = e->P;
     const double step_error = ss->rms_error;

@@ -133,6 +133,16 @@ __global__ void k_permute_level(Level in, Level out, const int* __restrict__ per
 }
 
 
+// stream compaction: list[scan[i]] = i for flagged i (scan = exclusive scan of flag)
+__global__ void k_compact(const unsigned* __restrict__ flag, const unsigned* __restrict__ scan, int n,
+                          int* __restrict__ list)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i])
+        list[scan[i]] = i;
+}
+
+
 // exclusive scan of in[0..n) into out[0..n], out[n] = total; tmp holds n/SCAN_TILE + 2 words
 inline void prim_exclusive_scan(cudaStream_t st, const unsigned* in, unsigned* out, unsigned n, unsigned* tmp)
 {
