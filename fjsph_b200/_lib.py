@@ -46,6 +46,7 @@ FjsphParams = struct_from_header("FjsphParams")
 FjsphBlock = struct_from_header("FjsphBlock")
 FjsphStateView = struct_from_header("FjsphStateView")
 FjsphStepStats = struct_from_header("FjsphStepStats")
+FjsphMesh = struct_from_header("FjsphMesh")
 
 
 # FjsphCommFn, include/fjsph_b200.h
@@ -99,6 +100,7 @@ def lib():
     L.fjsph_upload_level.argtypes = [vp, C.c_int, P(FjsphStateView)]
     L.fjsph_download_state.argtypes = [vp, C.c_int, P(FjsphStateView)]
     L.fjsph_upload_owned.argtypes = [vp, P(FjsphStateView)]
+    L.fjsph_upload_mesh.argtypes = [vp, P(FjsphMesh)]
     L.fjsph_count.argtypes = [vp]
     L.fjsph_count.restype = C.c_int64
     L.fjsph_build_neighbours.argtypes = [vp]

@@ -177,3 +177,74 @@ def inlet_jet(n=(5, 5, 4), dx=1e-3, v_jet=10.0, fixed=0, n_buf=4, aero_x=1.5, de
         params=dict(particle_step=dx, rho_rest=rho0, speed_sound=c, mu=8.94e-4, sig=0.0708, visc_alpha=0.05,
                     delta_t_min=1e-9, frame_time_interval=1e9),
     )
+
+
+def hex_mesh(lo, hi, n, vel=(0.0, 0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-2):
+    """Uniform hexahedral mesh of the box [lo, hi] with n = (nx, ny, nz) cells, every quad face split into two
+    triangles (what FOAM::Read_FOAM produces by tri-fanning, FOAMIO.cpp:604-624), in the layout of the reference's
+    MESH (Var.h:396-451): verts, faces as vertex lists (CSR), leftright = (owner cell, neighbour cell or the
+    boundary marker: -2 outer, -1 inner wall), cell -> faces (CSR), cell centres and the cell solution.
+    vel / p / rho may be constants or callables of the cell centres [nc,3]."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    nx, ny, nz = (int(k) for k in n)
+    xs = [np.linspace(lo[d], hi[d], k + 1) for d, k in enumerate((nx, ny, nz))]
+    vid = lambda i, j, k: (k * (ny + 1) + j) * (nx + 1) + i
+    cid = lambda i, j, k: (k * ny + j) * nx + i
+    gi, gj, gk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    verts = np.zeros(((nx + 1) * (ny + 1) * (nz + 1), 3))
+    verts[vid(gi, gj, gk).ravel()] = np.stack([xs[0][gi.ravel()], xs[1][gj.ravel()], xs[2][gk.ravel()]], axis=1)
+    faces, leftright, cfaces = [], [], [[] for _ in range(nx * ny * nz)]
+
+    def add_quad(q, left, right):
+        for tri in ((q[0], q[1], q[2]), (q[0], q[2], q[3])):
+            f = len(faces)
+            faces.append(tri)
+            leftright.append((left, right))
+            cfaces[left].append(f)
+            if right >= 0:
+                cfaces[right].append(f)
+
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx + 1):   # x-normal faces
+                q = (vid(i, j, k), vid(i, j + 1, k), vid(i, j + 1, k + 1), vid(i, j, k + 1))
+                if i == 0:
+                    add_quad(q, cid(0, j, k), outer_marker)
+                elif i == nx:
+                    add_quad(q, cid(nx - 1, j, k), outer_marker)
+                else:
+                    add_quad(q, cid(i - 1, j, k), cid(i, j, k))
+    for k in range(nz):
+        for j in range(ny + 1):
+            for i in range(nx):       # y-normal faces
+                q = (vid(i, j, k), vid(i + 1, j, k), vid(i + 1, j, k + 1), vid(i, j, k + 1))
+                if j == 0:
+                    add_quad(q, cid(i, 0, k), outer_marker)
+                elif j == ny:
+                    add_quad(q, cid(i, ny - 1, k), outer_marker)
+                else:
+                    add_quad(q, cid(i, j - 1, k), cid(i, j, k))
+    for k in range(nz + 1):
+        for j in range(ny):
+            for i in range(nx):       # z-normal faces
+                q = (vid(i, j, k), vid(i + 1, j, k), vid(i + 1, j + 1, k), vid(i, j + 1, k))
+                if k == 0:
+                    add_quad(q, cid(i, j, 0), outer_marker)
+                elif k == nz:
+                    add_quad(q, cid(i, j, nz - 1), outer_marker)
+                else:
+                    add_quad(q, cid(i, j, k - 1), cid(i, j, k))
+    ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    centre = np.zeros((nx * ny * nz, 3))
+    mid = [0.5 * (x[1:] + x[:-1]) for x in xs]
+    centre[cid(ci, cj, ck).ravel()] = np.stack([mid[0][ci.ravel()], mid[1][cj.ravel()], mid[2][ck.ravel()]], axis=1)
+    nc = centre.shape[0]
+    ev = lambda f, shape: (np.asarray(f(centre), float) if callable(f) else np.broadcast_to(np.asarray(f, float), shape)).copy()
+    face_vtx = np.asarray(faces, dtype=np.int64).ravel()
+    return dict(
+        verts=verts, face_ptr=np.arange(0, 3 * len(faces) + 1, 3, dtype=np.int64), face_vtx=face_vtx,
+        leftright=np.asarray(leftright, dtype=np.int32),
+        cell_ptr=np.concatenate([[0], np.cumsum([len(c) for c in cfaces])]).astype(np.int64),
+        cell_faces=np.concatenate([np.asarray(c, dtype=np.int64) for c in cfaces]),
+        cCentre=centre, cVel=ev(vel, (nc, 3)), cP=ev(p, (nc,)), cRho=ev(rho, (nc,)),
+    )

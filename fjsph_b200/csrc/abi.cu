@@ -155,9 +155,9 @@ static int validate_params(const FjsphParams& P)
         fj_set_error("aerodynamic case %d is not supported (NoAero=0 or Gissler=1)", P.acase);
         return FJSPH_ERR_INVALID;
     }
-    if (P.asource != 0)
+    if (P.asource != 0 && P.asource != 1)
     {
-        fj_set_error("aero source %d is not supported on the device yet (constVel=0 only)", P.asource);
+        fj_set_error("aero source %d is not supported (0 constVel, 1 meshInfl; VLM is out of scope)", P.asource);
         return FJSPH_ERR_INVALID;
     }
     if (P.solver_type != 0 && P.solver_type != 1)
@@ -503,7 +503,7 @@ __global__ void k_unpack(Level S, StageView h, const int* __restrict__ slot_of, 
     if (h.surfzone)
         h.surfzone[c] = S.surfzone[i];
     if (h.internal)
-        h.internal[c] = S.internal[i];
+        h.internal[c] = S.internal[i] & 0xFF; /* the upper bytes count FindCell's failed queries (ipt_n_failed) */
 }
 
 __global__ void k_counts_out(const int* __restrict__ ncount, const int* __restrict__ slot_of, long long* out, int n)
@@ -719,6 +719,7 @@ int fjsph_destroy(FjsphEngine* e)
     }
     if (e->scan_particles)
         cudaFree(e->scan_particles);
+    fj_free_mesh(e);
     void* ptrs[] = {e->oidx,       e->oidx_tmp, e->slot_of,  e->blk,      e->blk_tmp,   e->key,     e->rank_in_cell,
                     e->perm,       e->perm2,    e->ncount,   e->near_inlet, e->rk_sum_v, e->rk_sum_a, e->red,
                     e->red_out,    e->d_flag,   e->stage,    e->cell_count, e->cell_start, e->scan_tmp, e->mtab_x,

@@ -95,6 +95,22 @@ struct Slab
     long long exchanges = 0, redecomps = 0, bytes_sent = 0;
 };
 
+// aero mesh on the device (mesh.cu): per-face vertex coordinates, boundary markers, cell -> faces, cell centres and
+// solution, and the host-built bins over the cell centres
+struct DeviceMesh
+{
+    bool loaded = false;
+    int n_cells = 0, n_faces = 0;
+    double4* fx = nullptr;
+    int* fmark = nullptr;
+    int *cell_ptr = nullptr, *cell_faces = nullptr;
+    double4 *cc = nullptr, *cvp = nullptr;
+    double ox = 0, oy = 0, oz = 0, hx = 0, hy = 0, hz = 0, bin = 1;
+    int bx = 1, by = 1, bz = 1;
+    int *bin_start = nullptr, *bin_cells = nullptr;
+    int* counters = nullptr;
+};
+
 struct HostBlock
 {
     int64_t first, second;
@@ -194,6 +210,8 @@ struct FjsphEngine
     bool inlet_tables_dirty = true;
     unsigned* scan_particles = nullptr; // scan scratch sized for the particle count (delete planes)
     Slab slab;
+    DeviceMesh mesh;
+    long long mesh_deleted = 0;
 
     // Integrator members, Integration.h:53-68
     double safe_dt = 0.0, maxf = 0.0, maxAf = 0.0, maxRho_pc = 0.0, maxRhoi = 0.0, maxdrho = 0.0, minST = 0.0,
@@ -260,3 +278,8 @@ double fj_total_count(FjsphEngine* e);
 bool fj_has_inlets(FjsphEngine* e);
 int fj_inlet_motion(FjsphEngine* e, double dt, bool nb_solver, int* n_partials);
 int fj_update_data(FjsphEngine* e, int* n_add, int* n_del);
+int fj_delete_flagged(FjsphEngine* e, unsigned* d_del_by_caller, bool both_levels, int* n_del);
+// aero-mesh containment (mesh.cu)
+int fj_aero_velocity_mesh(FjsphEngine* e);
+int fj_pipe_outlet_mesh(FjsphEngine* e);
+void fj_free_mesh(FjsphEngine* e);

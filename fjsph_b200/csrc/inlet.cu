@@ -345,6 +345,96 @@ int fj_inlet_motion(FjsphEngine* e, double dt, bool nb_solver, int* n_partials)
     return FJSPH_OK;
 }
 
+// Erase the particles flagged in d_del (one unsigned per CALLER index, the key scratch array) from pnp1 -- and from pn
+// when both_levels -- keeping the reference's order: later indices shift down, block ranges and the inlet tables
+// follow (Integration.cpp:171-205, Resid.cpp:483-523).  The neighbour lists become invalid.
+int fj_delete_flagged(FjsphEngine* e, unsigned* d_del, bool both_levels, int* n_del_out)
+{
+    cudaStream_t st_ = e->stream;
+    const int n = int(e->n);
+    const int nbb = e->n_bound_blocks;
+    unsigned* d_scan = e->rank_in_cell; /* [cap] */
+    *n_del_out = 0;
+    if (n <= 0)
+        return FJSPH_OK;
+    if (!e->scan_particles)
+        FJ_CUDA(cudaMalloc(&e->scan_particles, (size_t(e->cap) / SCAN_TILE + 2) * sizeof(unsigned)));
+    /* exclusive scan in caller order: the arrays hold cap entries, so scan n-1 flags and add the last flag */
+    prim_exclusive_scan(st_, d_del, d_scan, unsigned(n - 1), e->scan_particles);
+    unsigned h_tail[2] = {0, 0};
+    FJ_CUDA(cudaMemcpyAsync(&h_tail[0], d_scan + (n - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
+    FJ_CUDA(cudaMemcpyAsync(&h_tail[1], d_del + (n - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
+    FJ_CUDA(cudaStreamSynchronize(st_));
+    e->launches += 3;
+    const int n_del = int(h_tail[0] + h_tail[1]);
+    if (n_del == 0)
+        return FJSPH_OK;
+    KScope ks(e, "delete_particles", 8);
+    /* survivors in slot order; their new caller index = old - (#deleted before it) */
+    unsigned* d_keep = reinterpret_cast<unsigned*>(e->perm);
+    unsigned* d_keep_scan = reinterpret_cast<unsigned*>(e->perm2);
+    int* d_new_oidx = e->oidx_tmp;
+    k_survivors<<<fj_blocks(n, TPB), TPB, 0, st_>>>(d_del, d_scan, e->oidx, n, d_keep, d_new_oidx);
+    prim_exclusive_scan(st_, d_keep, d_keep_scan, unsigned(n - 1), e->scan_particles);
+    int* d_list = e->near_inlet; /* [cap] scratch: surviving slots */
+    k_compact<<<fj_blocks(n, TPB), TPB, 0, st_>>>(d_keep, d_keep_scan, n, d_list);
+    const int n_new = n - n_del;
+    k_permute_level<<<fj_blocks(n_new, PRIM_TPB), PRIM_TPB, 0, st_>>>(e->lv[1], e->lv[2], d_list, n_new);
+    std::swap(e->lv[1], e->lv[2]);
+    if (both_levels)
+    {
+        k_permute_level<<<fj_blocks(n_new, PRIM_TPB), PRIM_TPB, 0, st_>>>(e->lv[0], e->lv[2], d_list, n_new);
+        std::swap(e->lv[0], e->lv[2]);
+    }
+    k_gather_int2<<<fj_blocks(n_new, TPB), TPB, 0, st_>>>(d_new_oidx, e->blk, d_list, n_new, e->oidx, e->blk_tmp);
+    std::swap(e->blk, e->blk_tmp);
+    /* per-block counts and the inlet tables in the new numbering */
+    for (size_t bl = 0; bl < e->blocks.size(); ++bl)
+    {
+        HostBlock& B = e->blocks[bl];
+        unsigned a = 0, b2 = 0;
+        const int64_t f = std::min<int64_t>(B.first, n - 1), s2 = std::min<int64_t>(B.second, n - 1);
+        FJ_CUDA(cudaMemcpyAsync(&a, d_scan + f, sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
+        FJ_CUDA(cudaMemcpyAsync(&b2, d_scan + s2, sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
+        FJ_CUDA(cudaStreamSynchronize(st_));
+        const unsigned before_first = (B.first >= n) ? unsigned(n_del) : a;
+        const unsigned before_second = (B.second >= n) ? unsigned(n_del) : b2;
+        if (int(bl) >= nbb && B.block_type == FJSPH_INLET_ZONE && !B.back.empty())
+        {
+            if (e->inlet_tables_dirty)
+            {
+                int st = upload_tables(e);
+                if (st)
+                    return st;
+            }
+            const int nb = int(B.back.size()), nf = int(B.buffer[0].size());
+            k_map_callers<<<fj_blocks(nb, TPB), TPB, 0, st_>>>(d_scan, B.d_back, nb);
+            k_map_callers<<<fj_blocks(nb * nf, TPB), TPB, 0, st_>>>(d_scan, B.d_buffer, nb * nf);
+            std::vector<int> hb(nb), hf(size_t(nb) * nf);
+            FJ_CUDA(cudaMemcpyAsync(hb.data(), B.d_back, nb * sizeof(int), cudaMemcpyDeviceToHost, st_));
+            FJ_CUDA(cudaMemcpyAsync(hf.data(), B.d_buffer, size_t(nb) * nf * sizeof(int), cudaMemcpyDeviceToHost, st_));
+            FJ_CUDA(cudaStreamSynchronize(st_));
+            for (int i = 0; i < nb; ++i)
+            {
+                B.back[i] = hb[i];
+                for (int j = 0; j < nf; ++j) B.buffer[i][j] = hf[size_t(i) * nf + j];
+            }
+        }
+        B.first -= before_first;
+        B.second -= before_second;
+    }
+    e->bound_points = e->n_bound_blocks > 0 ? e->blocks[size_t(e->n_bound_blocks) - 1].second : 0;
+    e->n = n_new;
+    e->n_owned = n_new;
+    k_fill_slot_of<<<fj_blocks(n_new, TPB), TPB, 0, st_>>>(e->oidx, n_new, e->slot_of);
+    FJ_CUDA(cudaGetLastError());
+    FJ_CUDA(cudaStreamSynchronize(st_));
+    e->skin_valid = false;
+    e->list_valid = false;
+    *n_del_out = n_del;
+    return FJSPH_OK;
+}
+
 // Integrator::update_data without the final pn = pnp1 (the caller copies the level): insertions, the rho fix,
 // deletions, and a neighbour rebuild when the particle set changed.
 int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
@@ -519,76 +609,9 @@ int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
         }
         if (any_delete_plane)
         {
-            /* number of deleted particles: exclusive scan in caller order (n+1 entries: perm2 as the output) */
-            unsigned* d_out = reinterpret_cast<unsigned*>(e->perm2);
-            if (!e->scan_particles)
-                FJ_CUDA(cudaMalloc(&e->scan_particles, (size_t(e->cap) / SCAN_TILE + 2) * sizeof(unsigned)));
-            /* perm2 has cap entries; the total lands in entry n, so scan n-1 flags + read the last flag */
-            prim_exclusive_scan(st_, d_del, d_scan, unsigned(n - 1), e->scan_particles);
-            unsigned h_tail[2] = {0, 0};
-            FJ_CUDA(cudaMemcpyAsync(&h_tail[0], d_scan + (n - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
-            FJ_CUDA(cudaMemcpyAsync(&h_tail[1], d_del + (n - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
-            FJ_CUDA(cudaStreamSynchronize(st_));
-            (void)d_out;
-            n_del = int(h_tail[0] + h_tail[1]);
-        }
-        if (n_del > 0)
-        {
-            KScope ks(e, "delete_plane", 8);
-            /* survivors in slot order; their new caller index = old - (#deleted before it) */
-            unsigned* d_keep = reinterpret_cast<unsigned*>(e->perm);
-            unsigned* d_keep_scan = reinterpret_cast<unsigned*>(e->perm2);
-            int* d_new_oidx = e->oidx_tmp;
-            k_survivors<<<fj_blocks(n, TPB), TPB, 0, st_>>>(d_del, d_scan, e->oidx, n, d_keep, d_new_oidx);
-            prim_exclusive_scan(st_, d_keep, d_keep_scan, unsigned(n - 1), e->scan_particles);
-            int* d_list = e->near_inlet; /* [cap] scratch: surviving slots */
-            k_compact<<<fj_blocks(n, TPB), TPB, 0, st_>>>(d_keep, d_keep_scan, n, d_list);
-            const int n_new = n - n_del;
-            k_permute_level<<<fj_blocks(n_new, PRIM_TPB), PRIM_TPB, 0, st_>>>(e->lv[1], e->lv[2], d_list, n_new);
-            std::swap(e->lv[1], e->lv[2]);
-            k_gather_int2<<<fj_blocks(n_new, TPB), TPB, 0, st_>>>(d_new_oidx, e->blk, d_list, n_new, e->oidx, e->blk_tmp);
-            std::swap(e->blk, e->blk_tmp);
-            /* per-block counts and the inlet tables in the new numbering */
-            std::vector<unsigned> h_scan_at;
-            for (size_t bl = size_t(nbb); bl < e->blocks.size(); ++bl)
-            {
-                HostBlock& B = e->blocks[bl];
-                unsigned a = 0, b2 = 0;
-                const int64_t f = std::min<int64_t>(B.first, n - 1), s2 = std::min<int64_t>(B.second, n - 1);
-                FJ_CUDA(cudaMemcpyAsync(&a, d_scan + f, sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
-                FJ_CUDA(cudaMemcpyAsync(&b2, d_scan + s2, sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
-                FJ_CUDA(cudaStreamSynchronize(st_));
-                const unsigned before_first = (B.first >= n) ? unsigned(n_del) : a;
-                const unsigned before_second = (B.second >= n) ? unsigned(n_del) : b2;
-                if (B.block_type == FJSPH_INLET_ZONE && !B.back.empty())
-                {
-                    if (e->inlet_tables_dirty)
-                    {
-                        int st = upload_tables(e);
-                        if (st)
-                            return st;
-                    }
-                    const int nb = int(B.back.size()), nf = int(B.buffer[0].size());
-                    k_map_callers<<<fj_blocks(nb, TPB), TPB, 0, st_>>>(d_scan, B.d_back, nb);
-                    k_map_callers<<<fj_blocks(nb * nf, TPB), TPB, 0, st_>>>(d_scan, B.d_buffer, nb * nf);
-                    std::vector<int> hb(nb), hf(size_t(nb) * nf);
-                    FJ_CUDA(cudaMemcpyAsync(hb.data(), B.d_back, nb * sizeof(int), cudaMemcpyDeviceToHost, st_));
-                    FJ_CUDA(cudaMemcpyAsync(hf.data(), B.d_buffer, size_t(nb) * nf * sizeof(int), cudaMemcpyDeviceToHost, st_));
-                    FJ_CUDA(cudaStreamSynchronize(st_));
-                    for (int i = 0; i < nb; ++i)
-                    {
-                        B.back[i] = hb[i];
-                        for (int j = 0; j < nf; ++j) B.buffer[i][j] = hf[size_t(i) * nf + j];
-                    }
-                }
-                B.first -= before_first;
-                B.second -= before_second;
-            }
-            e->n = n_new;
-            e->n_owned = n_new;
-            k_fill_slot_of<<<fj_blocks(n_new, TPB), TPB, 0, st_>>>(e->oidx, n_new, e->slot_of);
-            FJ_CUDA(cudaGetLastError());
-            FJ_CUDA(cudaStreamSynchronize(st_));
+            int st = fj_delete_flagged(e, d_del, false, &n_del); /* pn = pnp1 follows (Integration.cpp:220-223) */
+            if (st)
+                return st;
         }
     }
     *n_add_out = n_add;

@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(TPB, FJ_FORCE_MINBLOCKS)
         Rrho_ += pig;
         Rrhoc_ += rho_i * pig;
     }
-    if (S.internal[i] == 1)
+    if ((S.internal[i] & 0xFF) == 1)
     {
         /* NormalBoundaryRepulsion, Kernel.h:64-75,272-277 */
         const double4 bn = S.BN[i];
@@ -1116,11 +1116,8 @@ int fj_aero_velocity(FjsphEngine* e)
     int st = need_list(e, "aero_velocity");
     if (st)
         return st;
-    if (e->P.asource != 0)
-    {
-        fj_set_error("aero source %d (mesh containment) is not available on the device yet", e->P.asource);
-        return FJSPH_ERR_INVALID;
-    }
+    if (e->P.asource == 1)
+        return fj_aero_velocity_mesh(e); /* FindCell; may erase particles and redo the list and the prestep */
     const int n = int(e->n_owned);
     KScope ks(e, "aero_vel", 1);
     k_aero_velocity<<<fj_blocks(n, 256), 256, 0, e->stream>>>(e->lv[1], e->ncount, e->blk, e->n_bound_blocks, e->C, n);
@@ -1188,6 +1185,8 @@ int fj_shift(FjsphEngine* e)
 
 int fj_check_pipe_outlet(FjsphEngine* e)
 {
+    if (e->P.asource == 1)
+        return fj_pipe_outlet_mesh(e);
     const int n = int(e->n_owned);
     for (size_t bl = size_t(e->n_bound_blocks); bl < e->blocks.size(); ++bl)
     {

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import FjsphBlock, FjsphParams, FjsphStateView, FjsphStepStats, check
+from ._lib import FjsphBlock, FjsphMesh, FjsphParams, FjsphStateView, FjsphStepStats, check
 
 INT64_FIELDS = ("part_id", "cellID")
 INT32_FIELDS = ("b", "surf", "surfzone", "internal")
@@ -165,6 +165,21 @@ class Engine:
                 B.n_back, B.n_buf = len(ba), bu.shape[1]
                 B.back, B.buffer = ba.ctypes.data, bu.ctypes.data
         check(self._L.fjsph_set_blocks(self._h, len(blocks), arr))
+
+    def upload_mesh(self, mesh: dict):
+        """The reference's MESH (Var.h:396-451) for aero source meshInfl: verts [nv,3], face_ptr/face_vtx (CSR),
+        leftright [nf,2], cell_ptr/cell_faces (CSR), cCentre [nc,3], cVel [nc,3], cP [nc], cRho [nc]."""
+        m = FjsphMesh()
+        keep = {}
+        for k in ("verts", "cCentre", "cVel", "cP", "cRho"):
+            keep[k] = np.ascontiguousarray(mesh[k], dtype=np.float64)
+        for k in ("face_ptr", "face_vtx", "cell_ptr", "cell_faces"):
+            keep[k] = np.ascontiguousarray(mesh[k], dtype=np.int64)
+        keep["leftright"] = np.ascontiguousarray(mesh["leftright"], dtype=np.int32)
+        for k, a in keep.items():
+            setattr(m, k, a.ctypes.data)
+        m.n_verts, m.n_faces, m.n_cells = keep["verts"].shape[0], keep["leftright"].shape[0], keep["cCentre"].shape[0]
+        check(self._L.fjsph_upload_mesh(self._h, C.byref(m)))
 
     # -- state
     def upload_state(self, xi, v, rho, p, m, b, bound_points=0, **extra):

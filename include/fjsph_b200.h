@@ -111,6 +111,26 @@ typedef struct FjsphStepStats
     int32_t skin_builds; /* cell-list sweeps behind those neighbour builds (the rest were filtered from the skin list) */
 } FjsphStepStats;
 
+/* The reference's MESH (Var.h:396-451) as plain arrays: vertices, faces as vertex lists (CSR), leftright (owner cell,
+ * neighbour cell or boundary marker: -1 inner wall, -2 outer boundary), cell -> faces (CSR), cell centres and the
+ * cell-averaged CFD solution.  What TAU::Read_* (CDFIO.cpp:1103-1356) or FOAM::Read_FOAM (FOAMIO.cpp:538-955) fill. */
+typedef struct FjsphMesh
+{
+    int64_t n_verts;
+    const double* verts;        /* [n_verts][3] */
+    int64_t n_faces;
+    const int64_t* face_ptr;    /* [n_faces+1] */
+    const int64_t* face_vtx;
+    const int32_t* leftright;   /* [n_faces][2] */
+    int64_t n_cells;
+    const int64_t* cell_ptr;    /* [n_cells+1] */
+    const int64_t* cell_faces;
+    const double* cCentre;      /* [n_cells][3] */
+    const double* cVel;         /* [n_cells][3] */
+    const double* cP;           /* [n_cells] */
+    const double* cRho;         /* [n_cells] */
+} FjsphMesh;
+
 typedef struct FjsphEngine FjsphEngine;
 
 const char* fjsph_last_error(void);
@@ -138,6 +158,11 @@ int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_po
 int fjsph_upload_level(FjsphEngine* e, int level, const FjsphStateView* s);
 int fjsph_download_state(FjsphEngine* e, int level, FjsphStateView* s);
 int64_t fjsph_count(FjsphEngine* e);
+
+/* Aero mesh for aero source meshInfl (asource = 1): replaces the MESH argument and the cell-centre KD-tree
+ * (Vec_Tree CELL_TREE, FJSPH.cpp:148-149) of get_aero_velocity / FindCell / FirstCell / Check_Pipe_Outlet
+ * (Resid.h:43-46, Containment.h:20-31). */
+int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m);
 
 /* Stage entry points; each replaces the reference function named on the right and acts on pnp1. */
 int fjsph_build_neighbours(FjsphEngine* e);                     /* update_neighbours      Neighbours.h:9 */

@@ -115,6 +115,17 @@ static inline Vec normalized(Vec const& x)
     return x;
 }
 
+#if DIM == 3
+static inline Vec cross3(Vec const& a, Vec const& b)
+{
+    Vec r;
+    r[0] = a[1] * b[2] - a[2] * b[1];
+    r[1] = a[2] * b[0] - a[0] * b[2];
+    r[2] = a[0] * b[1] - a[1] * b[0];
+    return r;
+}
+#endif
+
 struct Mat
 {
     real a[DIM][DIM];
@@ -353,7 +364,7 @@ struct State
 {
     size_t n = 0;
     std::vector<long> part_id, cellID;
-    std::vector<int> b, surf, surfzone, internal;
+    std::vector<int> b, surf, surfzone, internal, ipt_n_failed;
     std::vector<Vec> xi, v, acc, Af, aVisc, cellV, gradRho, norm, bNorm, vPert;
     std::vector<Mat> L;
     std::vector<real> Rrho, rho, p, m, curve, norm_curve, woccl, pDist, deltaD, cellP, cellRho, colourG,
@@ -368,6 +379,7 @@ struct State
         surf.resize(n, 0);
         surfzone.resize(n, 0);
         internal.resize(n, 0);
+        ipt_n_failed.resize(n, 0);
         for (auto* f : vecs()) f->resize(n, vzero());
         L.resize(n, mzero());
         for (auto* f : scalars()) f->resize(n, 0.0);
@@ -389,6 +401,7 @@ struct State
         surf.erase(surf.begin() + i);
         surfzone.erase(surfzone.begin() + i);
         internal.erase(internal.begin() + i);
+        ipt_n_failed.erase(ipt_n_failed.begin() + i);
         for (auto* f : vecs()) f->erase(f->begin() + i);
         L.erase(L.begin() + i);
         for (auto* f : scalars()) f->erase(f->begin() + i);
@@ -405,6 +418,7 @@ struct State
         surf.insert(surf.begin() + pos, 0);
         surfzone.insert(surfzone.begin() + pos, 0);
         internal.insert(internal.begin() + pos, 0);
+        ipt_n_failed.insert(ipt_n_failed.begin() + pos, 0);
         for (auto* f : vecs()) f->insert(f->begin() + pos, vzero());
         L.insert(L.begin() + pos, mzero());
         for (auto* f : scalars()) f->insert(f->begin() + pos, 0.0);
@@ -453,10 +467,25 @@ enum
     meshInfl
 };
 
+/* MESH, Var.h:396-451 (faces as vertex lists, leftright, cell -> faces, cell centres and solution) */
+struct Mesh
+{
+    std::vector<Vec> verts;
+    std::vector<std::vector<long>> faces;
+    std::vector<std::pair<int, int>> leftright;
+    std::vector<std::vector<long>> cFaces;
+    std::vector<Vec> cCentre, cVel;
+    std::vector<real> cP, cRho;
+    size_t size() const { return cCentre.size(); }
+};
+
 struct Orc
 {
     OrcParams P;
     State pn, pnp1;
+    Mesh cells;
+    std::vector<size_t> pipe_outlet_del;
+    int first_cell_errors = 0; /* FirstCell's exit(-1) (Containment.cpp:563-571), reported instead of exiting */
     std::vector<Block> limits;
     size_t n_bound_blocks = 0, n_fluid_blocks = 0;
     size_t bound_points = 0, total_points = 0, fluid_points = 0;
@@ -1407,11 +1436,247 @@ static void get_acc_and_Rrho(Orc& o, real npd, State& S)
 }
 
 /* ------------------------------------------------------------------ Resid.cpp:471-612 (constVel) */
+#if DIM == 3
+/* Geometry.cpp:485-575.  Only the SIGN of the 4x4 determinants |p 1; a 1; b 1; c 1| is used; expanding along the
+ * last column gives det4 = -det3[(a-p); (b-p); (c-p)], which is how it is evaluated here (Eigen's cofactor
+ * formula is not available; the two agree in sign except within rounding of a degenerate configuration).
+ * Q6: only face[0..2], the plane of the first three vertices and the edges (last,0),(0,1),(1,2) are tested. */
+static inline real det4_sign_arg(Vec const& p, Vec const& a, Vec const& b, Vec const& c)
+{
+    Vec const u = a - p, v = b - p, w = c - p;
+    real const det3 = u[0] * (v[1] * w[2] - v[2] * w[1]) - u[1] * (v[0] * w[2] - v[2] * w[0]) +
+                      u[2] * (v[0] * w[1] - v[1] * w[0]);
+    return -det3;
+}
+static int Crossings3D(Mesh const& M, std::vector<long> const& face, Vec const& testp, Vec const& rayp)
+{
+    Vec const &f0 = M.verts[face[0]], &f1 = M.verts[face[1]], &f2 = M.verts[face[2]];
+    int const flag1 = det4_sign_arg(testp, f0, f1, f2) < 0.0;
+    int const flag2 = det4_sign_arg(rayp, f0, f1, f2) < 0.0;
+    if (flag1 != flag2)
+    {
+        Vec vtx0 = M.verts[face.back()], vtx1 = f0;
+        /* rows: testp, vtx0, vtx1, rayp */
+        int const flag3 = det4_sign_arg(testp, vtx0, vtx1, rayp) < 0.0;
+        for (size_t ii = 1; ii < 3; ++ii)
+        {
+            vtx0 = vtx1;
+            vtx1 = M.verts[face[ii]];
+            int const flag4 = det4_sign_arg(testp, vtx0, vtx1, rayp) < 0.0;
+            if (flag4 != flag3)
+                return 0;
+        }
+        return 1;
+    }
+    return 0;
+}
+/* Containment.cpp:385-420; Q7: a negative (or out of range) cell is "not contained" */
+static unsigned CheckCell(Mesh const& M, long cell, Vec const& testp)
+{
+    if (cell < 0 || size_t(cell) >= M.size())
+        return 0;
+    Vec rayp = testp;
+    rayp[0] += 1e+5;
+    unsigned line_flag = 0, inside_flag = 0;
+    for (long f : M.cFaces[size_t(cell)])
+        if (Crossings3D(M, M.faces[size_t(f)], testp, rayp))
+        {
+            inside_flag = !inside_flag;
+            if (line_flag)
+                break; /* convex assumption */
+            line_flag = 1;
+        }
+    return inside_flag;
+}
+/* nanoflann KNNResultSet on the cell centres: the k nearest in ascending distance; ties by cell index */
+static std::vector<long> nearest_cells(Mesh const& M, Vec const& p, size_t k)
+{
+    std::vector<std::pair<real, long>> d(M.size());
+    for (size_t c = 0; c < M.size(); ++c)
+    {
+        real d2 = 0.0;
+        for (int a = 0; a < DIM; ++a) d2 += (p[a] - M.cCentre[c][a]) * (p[a] - M.cCentre[c][a]);
+        d[c] = std::make_pair(d2, long(c));
+    }
+    k = std::min(k, d.size());
+    std::partial_sort(d.begin(), d.begin() + long(k), d.end());
+    std::vector<long> out(k);
+    for (size_t i = 0; i < k; ++i) out[i] = d[i].second;
+    return out;
+}
+static void take_cell(Mesh const& M, State& S, size_t ii, long cell)
+{
+    S.cellID[ii] = cell;
+    S.cellV[ii] = M.cVel[size_t(cell)];
+    S.cellP[ii] = M.cP[size_t(cell)];
+    S.cellRho[ii] = M.cRho[size_t(cell)];
+}
+/* FindCell, Containment.cpp:579-820.  Returns the particles to delete (each once: the reference can list a
+ * particle several times, which would make it erase the wrong ones). */
+static std::vector<size_t> FindCell(Orc& o, State& pnp1)
+{
+    Mesh const& M = o.cells;
+    std::vector<size_t> toDelete;
+    for (size_t ii = o.bound_points; ii < o.total_points; ++ii)
+    {
+        if (pnp1.b[ii] != ORC_FREE || pnp1.lam_nb[ii] > o.P.lam_cutoff)
+        {
+            pnp1.cellID[ii] = c_no_cell;
+            continue;
+        }
+        Vec const testp = pnp1.xi[ii];
+        if (CheckCell(M, pnp1.cellID[ii], testp))
+        {
+            take_cell(M, pnp1, ii, pnp1.cellID[ii]);
+            pnp1.ipt_n_failed[ii] = 0;
+            continue;
+        }
+        bool inside = false;
+        std::vector<long> ret;
+        for (size_t num_results : {size_t(5), size_t(500)})
+        {
+            ret = nearest_cells(M, testp, num_results);
+            for (long cell : ret)
+                if (CheckCell(M, cell, testp))
+                {
+                    take_cell(M, pnp1, ii, cell);
+                    pnp1.ipt_n_failed[ii] = 0;
+                    pnp1.internal[ii] = 0;
+                    inside = true;
+                    break;
+                }
+            if (inside)
+                break;
+        }
+        if (inside)
+            continue;
+        /* across a boundary?  ray from the point to each of the 500 nearest cell centres */
+        unsigned cross = 0;
+        bool del = false;
+        for (long index : ret)
+        {
+            Vec const rayp = M.cCentre[size_t(index)];
+            for (long findex : M.cFaces[size_t(index)])
+                if (M.leftright[size_t(findex)].second < 0)
+                    if (Crossings3D(M, M.faces[size_t(findex)], testp, rayp))
+                    {
+                        cross = !cross;
+                        if (M.leftright[size_t(findex)].second == -1)
+                        {
+                            pnp1.internal[ii] = 1;
+                            break;
+                        }
+                        else if (M.leftright[size_t(findex)].second == -2)
+                        {
+                            del = true;
+                            break;
+                        }
+                    }
+        }
+        if (cross == 0)
+        {
+            if (pnp1.ipt_n_failed[ii] > 10)
+                del = true;
+            else
+                pnp1.ipt_n_failed[ii]++;
+        }
+        if (del)
+            toDelete.push_back(ii);
+    }
+    return toDelete;
+}
+/* FirstCell, Containment.cpp:425-573: PIPE -> FREE transition, no previous cell */
+static void FirstCell(Orc& o, State& S, size_t ii, unsigned& to_del)
+{
+    Mesh const& M = o.cells;
+    Vec const testp = S.xi[ii];
+    std::vector<long> const ret = nearest_cells(M, testp, 150);
+    for (long cell : ret)
+        if (CheckCell(M, cell, testp))
+        {
+            take_cell(M, S, ii, cell);
+            return;
+        }
+    unsigned cross = 0;
+    for (long index : ret)
+    {
+        Vec const rayp = M.cCentre[size_t(index)];
+        for (long findex : M.cFaces[size_t(index)])
+            if (M.leftright[size_t(findex)].second < 0)
+            {
+                std::vector<long> const& face = M.faces[size_t(findex)];
+                if (Crossings3D(M, face, testp, rayp))
+                {
+                    cross = !cross;
+                    if (M.leftright[size_t(findex)].second == -1)
+                    {
+                        Vec const r1 = M.verts[face[1]] - M.verts[face[0]], r2 = M.verts[face[2]] - M.verts[face[0]];
+                        Vec nrm = normalized(cross3(r1, r2));
+                        S.v[ii] = S.v[ii] - (2 * dot(S.v[ii], nrm)) * nrm;
+                        real const plane = dot(nrm, M.verts[face[1]]);
+                        real const dist = (plane - dot(S.xi[ii], nrm)) / dot(nrm, nrm);
+                        S.xi[ii] = S.xi[ii] + dist * nrm;
+                    }
+                    else if (M.leftright[size_t(findex)].second == -2)
+                        to_del = 1;
+                }
+            }
+    }
+    if (cross == 0)
+        o.first_cell_errors++; /* the reference prints and calls exit(-1) here */
+}
+#endif
+
+static void dSPH_PreStep(Orc& o, size_t end, State& S, real& npd);
+static void update_neighbours(Orc& o, State const& S);
+
+/* Resid.cpp:471-523: meshInfl.  Escaped particles are erased from both time levels, then the neighbour list and
+ * the prestep are redone. */
+static void get_aero_velocity_mesh(Orc& o, State& pn, State& pnp1, real& npd)
+{
+#if DIM == 3
+    std::vector<size_t> toDelete = FindCell(o, pnp1);
+    if (toDelete.empty())
+        return;
+    std::sort(toDelete.begin(), toDelete.end());
+    size_t const nDel = toDelete.size();
+    for (auto it = toDelete.rbegin(); it != toDelete.rend(); ++it)
+    {
+        pnp1.erase(*it);
+        pn.erase(*it);
+    }
+    /* block ranges: the reference only shifts back/buffer (by nDel, whatever their block) and leaves
+     * limits[].index stale; the contract keeps the ranges consistent with the erased particles */
+    for (Block& B : o.limits)
+    {
+        long before_first = 0, before_second = 0;
+        for (size_t d : toDelete)
+        {
+            before_first += long(d) < B.first;
+            before_second += long(d) < B.second;
+        }
+        B.first -= before_first;
+        B.second -= before_second;
+        for (long& x : B.back) x -= long(nDel);
+        for (auto& buf : B.buffer)
+            for (long& x : buf) x -= long(nDel);
+    }
+    o.delete_count += nDel;
+    o.fluid_points -= nDel;
+    o.total_points -= nDel;
+    o.end_index -= nDel;
+    update_neighbours(o, pnp1);
+    dSPH_PreStep(o, o.total_points, pnp1, npd);
+#else
+    (void)o; (void)pn; (void)pnp1; (void)npd;
+#endif
+}
+
 static void get_aero_velocity(Orc& o, size_t start, size_t end, State& S)
 {
     OrcParams const& P = o.P;
     if (P.asource != constVel)
-        return; /* meshInfl: FindCell, not restated yet */
+        return; /* meshInfl goes through get_aero_velocity_mesh (needs both time levels) */
     for (size_t ii = start; ii < end; ++ii)
     {
         bool cond;
@@ -1441,7 +1706,51 @@ static void Check_Pipe_Outlet(Orc& o, State& S)
         for (long ii = B.first; ii < B.second; ++ii)
             if (S.b[ii] == ORC_PIPE)
                 if (dot(S.xi[ii], B.aero_norm) > B.aeroconst)
+                {
                     S.b[ii] = ORC_FREE;
+#if DIM == 3
+                    if (S.lam_nb[ii] < o.P.lam_cutoff && o.P.asource == meshInfl)
+                    {
+                        unsigned to_del = 0;
+                        FirstCell(o, S, size_t(ii), to_del);
+                        if (to_del)
+                            o.pipe_outlet_del.push_back(size_t(ii));
+                    }
+#endif
+                }
+    }
+    /* Containment.cpp:849-890: erase the particles that left through an outer boundary (pnp1 only) */
+    if (!o.pipe_outlet_del.empty())
+    {
+        std::vector<size_t>& del = o.pipe_outlet_del;
+        std::sort(del.begin(), del.end());
+        for (auto it = del.rbegin(); it != del.rend(); ++it)
+        {
+            S.erase(*it);
+            if (&S == &o.pnp1)
+                o.pn.erase(*it); /* the reference erases pnp1 only and leaves pn misaligned; the contract keeps
+                                    the two time levels index-aligned */
+            o.total_points--;
+            o.fluid_points--;
+            o.end_index--;
+            o.delete_count++;
+        }
+        for (size_t block = o.n_bound_blocks; block < o.limits.size(); ++block)
+        {
+            Block& B = o.limits[block];
+            long before_first = 0, before_second = 0;
+            for (size_t d : del)
+            {
+                before_first += long(d) < B.first;
+                before_second += long(d) < B.second;
+            }
+            B.first -= before_first;
+            B.second -= before_second;
+            for (long& x : B.back) x -= before_second;
+            for (auto& buf : B.buffer)
+                for (long& x : buf) x -= before_second;
+        }
+        del.clear();
     }
 }
 
@@ -1852,6 +2161,8 @@ static real find_timestep(Orc& o, State const& S, size_t start, size_t end)
 static void frozen_terms(Orc& o, State& S, real& npd)
 {
     dSPH_PreStep(o, o.total_points, S, npd);
+    if (o.P.asource == meshInfl)
+        get_aero_velocity_mesh(o, o.pn, S, npd); /* S is pnp1 on this path (Integration.cpp:47,82) */
     get_aero_velocity(o, o.start_index, o.end_index, S);
     Detect_Surface(o, o.start_index, o.end_index, S);
     dissipation_terms(o, o.start_index, o.end_index, S);
@@ -2299,6 +2610,7 @@ int orc_get_i64(Orc* o, int level, const char* name, int64_t* out)
         else if (n == "surf") out[i] = S.surf[i];
         else if (n == "surfzone") out[i] = S.surfzone[i];
         else if (n == "internal") out[i] = S.internal[i];
+        else if (n == "ipt_n_failed") out[i] = S.ipt_n_failed[i];
         else return -1;
     }
     return 1;
@@ -2315,6 +2627,7 @@ int orc_set_i64(Orc* o, int level, const char* name, const int64_t* in)
         else if (n == "surf") S.surf[i] = int(in[i]);
         else if (n == "surfzone") S.surfzone[i] = int(in[i]);
         else if (n == "internal") S.internal[i] = int(in[i]);
+        else if (n == "ipt_n_failed") S.ipt_n_failed[i] = int(in[i]);
         else return -1;
     }
     return 1;
@@ -2346,8 +2659,47 @@ double orc_prestep(Orc* o)
 void orc_aero_velocity(Orc* o)
 {
     set_range(o);
+    if (o->P.asource == meshInfl)
+    {
+        real npd = 1.0;
+        get_aero_velocity_mesh(*o, o->pn, o->pnp1, npd);
+    }
     get_aero_velocity(*o, o->start_index, o->end_index, o->pnp1);
 }
+/* MESH upload: faces as CSR vertex lists, leftright pairs, cell -> faces CSR, centres and the cell solution */
+void orc_set_mesh(Orc* o, int64_t n_verts, const double* verts, int64_t n_faces, const int64_t* face_ptr,
+                  const int64_t* face_vtx, const int32_t* leftright, int64_t n_cells, const int64_t* cell_ptr,
+                  const int64_t* cell_faces, const double* cCentre, const double* cVel, const double* cP,
+                  const double* cRho)
+{
+    Mesh& M = o->cells;
+    M = Mesh();
+    M.verts.resize(size_t(n_verts));
+    for (int64_t i = 0; i < n_verts; ++i)
+        for (int d = 0; d < DIM; ++d) M.verts[size_t(i)][d] = verts[i * DIM + d];
+    M.faces.resize(size_t(n_faces));
+    M.leftright.resize(size_t(n_faces));
+    for (int64_t f = 0; f < n_faces; ++f)
+    {
+        M.faces[size_t(f)].assign(face_vtx + face_ptr[f], face_vtx + face_ptr[f + 1]);
+        M.leftright[size_t(f)] = std::make_pair(int(leftright[2 * f]), int(leftright[2 * f + 1]));
+    }
+    M.cFaces.resize(size_t(n_cells));
+    M.cCentre.resize(size_t(n_cells));
+    M.cVel.resize(size_t(n_cells));
+    M.cP.assign(cP, cP + n_cells);
+    M.cRho.assign(cRho, cRho + n_cells);
+    for (int64_t c = 0; c < n_cells; ++c)
+    {
+        M.cFaces[size_t(c)].assign(cell_faces + cell_ptr[c], cell_faces + cell_ptr[c + 1]);
+        for (int d = 0; d < DIM; ++d)
+        {
+            M.cCentre[size_t(c)][d] = cCentre[c * DIM + d];
+            M.cVel[size_t(c)][d] = cVel[c * DIM + d];
+        }
+    }
+}
+int orc_first_cell_errors(Orc* o) { return o->first_cell_errors; }
 void orc_detect_surface(Orc* o)
 {
     set_range(o);

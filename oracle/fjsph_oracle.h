@@ -103,6 +103,11 @@ int64_t orc_neighbour_total(Orc* o);
 void orc_get_neighbours(Orc* o, int64_t* offsets /* n+1 */, int64_t* idx, double* d2); /* ascending j */
 double orc_prestep(Orc* o);                               /* Shifting.cpp:12-123; returns npd */
 void orc_aero_velocity(Orc* o);                           /* Resid.cpp:471-612 (constVel) */
+void orc_set_mesh(Orc* o, int64_t n_verts, const double* verts, int64_t n_faces, const int64_t* face_ptr,
+                  const int64_t* face_vtx, const int32_t* leftright, int64_t n_cells, const int64_t* cell_ptr,
+                  const int64_t* cell_faces, const double* cCentre, const double* cVel, const double* cP,
+                  const double* cRho);                     /* MESH, Var.h:396-451 (aero source meshInfl) */
+int orc_first_cell_errors(Orc* o);                        /* FirstCell failures (the reference exits) */
 void orc_detect_surface(Orc* o);                          /* Geometry.cpp:14-280 */
 void orc_dissipation(Orc* o);                             /* Shifting.cpp:126-186 */
 void orc_particle_shift(Orc* o);                          /* Shifting.cpp:189-290 */

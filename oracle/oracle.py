@@ -80,6 +80,9 @@ def _load(kind: str):
     lib.orc_bound_points.restype = C.c_int64
     for f in ("orc_get_f64", "orc_set_f64", "orc_get_i64", "orc_set_i64"):
         getattr(lib, f).argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p]
+    lib.orc_set_mesh.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.orc_set_mesh.argtypes += [C.c_void_p] * 6
+    lib.orc_first_cell_errors.argtypes = [C.c_void_p]
     lib.orc_update_neighbours.argtypes = [C.c_void_p]
     lib.orc_neighbour_total.argtypes = [C.c_void_p]
     lib.orc_neighbour_total.restype = C.c_int64
@@ -135,7 +138,7 @@ def params_to_dict(p) -> dict:
     return out
 
 
-_INT_FIELDS = ("part_id", "cellID", "b", "surf", "surfzone", "internal")
+_INT_FIELDS = ("part_id", "cellID", "b", "surf", "surfzone", "internal", "ipt_n_failed")
 _VEC_FIELDS = ("xi", "v", "acc", "Af", "aVisc", "cellV", "gradRho", "norm", "bNorm", "vPert")
 _SCALAR_FIELDS = (
     "Rrho rho p m curve norm_curve woccl pDist deltaD cellP cellRho colourG colour lam lam_nb kernsum y".split()
@@ -219,6 +222,21 @@ class Oracle:
         pid = None if part_id is None else np.ascontiguousarray(part_id, dtype=np.int64)
         self.lib.orc_set_particles(self.h, n, int(bound_points), _ptr(xi), _ptr(v), _ptr(rho), _ptr(p), _ptr(m),
                                    _ptr(b), _ptr(pid))
+
+    def set_mesh(self, mesh: dict):
+        """mesh: dict with verts [nv,3], face_ptr/face_vtx (CSR), leftright [nf,2] int32, cell_ptr/cell_faces (CSR),
+        cCentre [nc,3], cVel [nc,3], cP [nc], cRho [nc] -- the reference's MESH (Var.h:396-451)."""
+        a = {k: np.ascontiguousarray(mesh[k], dtype=(np.int32 if k == "leftright" else
+                                                      np.int64 if k in ("face_ptr", "face_vtx", "cell_ptr", "cell_faces")
+                                                      else np.float64)) for k in
+             ("verts", "face_ptr", "face_vtx", "leftright", "cell_ptr", "cell_faces", "cCentre", "cVel", "cP", "cRho")}
+        self.lib.orc_set_mesh(self.h, a["verts"].shape[0], _ptr(a["verts"]), a["leftright"].shape[0], _ptr(a["face_ptr"]),
+                              _ptr(a["face_vtx"]), _ptr(a["leftright"]), a["cCentre"].shape[0], _ptr(a["cell_ptr"]),
+                              _ptr(a["cell_faces"]), _ptr(a["cCentre"]), _ptr(a["cVel"]), _ptr(a["cP"]), _ptr(a["cRho"]))
+
+    @property
+    def first_cell_errors(self) -> int:
+        return int(self.lib.orc_first_cell_errors(self.h))
 
     @property
     def n(self) -> int:
