@@ -118,13 +118,23 @@ __global__ void k_timestep_partials(Level S, const int* __restrict__ blk, int n_
 }
 __global__ void k_timestep_final(const double* __restrict__ partial, int nblocks, double* __restrict__ out)
 {
-    const int c = threadIdx.x;
-    if (c < 7)
+    // one warp per component, lanes stride the block partials
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= 7)
+        return;
+    double x = (c == 4) ? 1e300 : 0.0;
+    for (int b = lane; b < nblocks; b += 32)
     {
-        double x = partial[c];
-        for (int b = 1; b < nblocks; ++b) x = (c == 4) ? fmin(x, partial[b * 7 + c]) : fmax(x, partial[b * 7 + c]);
-        out[c] = x;
+        const double y = partial[b * 7 + c];
+        x = (c == 4) ? fmin(x, y) : fmax(x, y);
     }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const double y = __shfl_xor_sync(0xffffffffu, x, o);
+        x = (c == 4) ? fmin(x, y) : fmax(x, y);
+    }
+    if (lane == 0)
+        out[c] = x;
 }
 
 // keeps V = m/rho and p/rho^2 consistent with (rho, p)
@@ -475,7 +485,7 @@ int fj_find_timestep(FjsphEngine* e, double* dt_out)
     {
         KScope ks(e, "timestep", 2);
         k_timestep_partials<<<nb, TPB, 0, e->stream>>>(e->lv[1], e->blk, e->n_bound_blocks, e->C, n, e->red);
-        k_timestep_final<<<1, 32, 0, e->stream>>>(e->red, nb, e->red_out);
+        k_timestep_final<<<1, 7 * 32, 0, e->stream>>>(e->red, nb, e->red_out);
     }
     FJ_CUDA(cudaGetLastError());
     FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
