@@ -210,7 +210,10 @@ struct RecPre
     double rho;
 };
 
-__global__ void __launch_bounds__(TPB, 3)
+#ifndef FJ_PRESTEP_MINBLOCKS
+#define FJ_PRESTEP_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(TPB, FJ_PRESTEP_MINBLOCKS)
     k_prestep(Level S, ListView lv, DevConst C, int n, double* __restrict__ npd_partial)
 {
     __shared__ double sm[TPB / 32];
@@ -512,8 +515,14 @@ struct RecS2
     double4 n, p, v;
 };
 
+#ifndef FJ_S23_MINBLOCKS
+#define FJ_S23_MINBLOCKS 2
+#endif
+#ifndef FJ_FUSE_SHIFT
+#define FJ_FUSE_SHIFT 1
+#endif
 template <bool SURF23, bool SHIFT>
-__global__ void __launch_bounds__(TPB, 3)
+__global__ void __launch_bounds__(TPB, FJ_S23_MINBLOCKS)
     k_surf23_shift(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1154,15 +1163,22 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
         if (st)
             return st;
     }
-    if (do_surface && fuse_shift && e->P.ale)
+    if (do_surface && fuse_shift && e->P.ale && FJ_FUSE_SHIFT)
     {
         KScope ks(e, "surf2+3+shift", 1);
         k_surf23_shift<true, true><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
     }
     else if (do_surface)
     {
-        KScope ks(e, "surf2+3", 1);
-        k_surf23_shift<true, false><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+        {
+            KScope ks(e, "surf2+3", 1);
+            k_surf23_shift<true, false><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+        }
+        if (fuse_shift && e->P.ale)
+        {
+            FJ_CUDA(cudaGetLastError());
+            return fj_shift(e);
+        }
     }
     FJ_CUDA(cudaGetLastError());
     return FJSPH_OK;
