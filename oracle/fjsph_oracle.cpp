@@ -1751,6 +1751,7 @@ static void Check_Pipe_Outlet(Orc& o, State& S)
                 for (long& x : buf) x -= before_second;
         }
         del.clear();
+        update_neighbours(o, S); /* the reference carries on with a stale, index-based list; contract: rebuilt */
     }
 }
 

@@ -233,6 +233,26 @@ def test_walls_nb_iteration_parity(ale):
         assert_fields_close(e, o, ("xi", "v", "rho", "p", "acc", "Rrho"), tol=1e-9, context="walls nb_iter %d" % it)
 
 
+def test_state_after_1000_steps():
+    """north_star: "state after 1000 steps within a stated tolerance".  1000 Integrator::integrate calls on a jittered
+    block (free surfaces on all sides, ALE shifting, surface tension): the sub-iteration count and dt of every step
+    and every surface flag must agree, positions to 1e-8 of the domain, density 1e-10, velocity 1e-7 (measured:
+    2e-9, 5e-13, 3e-9; tools/long_run.py prints the growth curve, also for the droplet and the walled tank)."""
+    case = cases.synthetic_block((10, 9, 8), 1e-3, jitter=0.1, seed=8)
+    o, e, p = make_pair(case, delta_t_min=1e-9)
+    for step in range(1000):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert se.iterations == so.iterations, step
+        assert abs(se.dt - so.dt) <= 1e-9 * so.dt, step
+    assert_fields_close(e, o, ("surf", "surfzone", "b"), context="1000 steps")
+    assert_fields_close(e, o, ("xi",), tol=1e-8, context="1000 steps")
+    assert_fields_close(e, o, ("rho",), tol=1e-10, context="1000 steps")
+    assert_fields_close(e, o, ("v",), tol=1e-7, context="1000 steps")
+    displacement = np.abs(o.get("xi") - case["xi"]).max()
+    assert displacement > 5 * 1e-3   # the block really moved (several particle spacings)
+
+
 def test_engine_errors_are_reported_not_fatal():
     from fjsph_b200 import engine as eng
     from fjsph_b200._lib import FjsphError
