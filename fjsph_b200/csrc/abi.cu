@@ -133,6 +133,7 @@ void fj_refresh_constants(FjsphEngine* e)
     C.ale = P.ale;
     C.pressure_rel = P.pressure_rel;
     C.acase = P.acase;
+    C.rho_g = P.rho_g;
     C.asource = P.asource;
     C.use_lam = P.use_lam;
     C.use_TAB_def = P.use_TAB_def;
@@ -150,9 +151,9 @@ static int validate_params(const FjsphParams& P)
         fj_set_error("derived constants missing: call fjsph_set_values() before fjsph_create()");
         return FJSPH_ERR_INVALID;
     }
-    if (P.acase != 0 && P.acase != 1)
+    if (P.acase < 0 || P.acase > 3)
     {
-        fj_set_error("aerodynamic case %d is not supported (NoAero=0 or Gissler=1)", P.acase);
+        fj_set_error("aerodynamic case %d unknown (0 none, 1 Gissler, 2 Induced_pressure, 3 Skin_friction)", P.acase);
         return FJSPH_ERR_INVALID;
     }
     if (P.asource != 0 && P.asource != 1)

@@ -52,7 +52,7 @@ struct DevConst
     double gx, gy, gz;
     double vinf_x, vinf_y, vinf_z;
     double lam_cutoff, interp_fac, i_n_full, aero_L, A_sphere, A_plate, mu_g, sos2, gamma_g, ycoef, tab_Cb;
-    double max_shift_vel, bnd_mass, sim_mass, c_sound;
+    double max_shift_vel, bnd_mass, sim_mass, c_sound, rho_g;
     int ale, pressure_rel, acase, asource, use_lam, use_TAB_def;
 };
 

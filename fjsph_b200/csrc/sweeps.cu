@@ -727,6 +727,138 @@ __device__ __forceinline__ double get_cd(double Re)
     return (1.0 + 0.197 * pow(Re, 0.63) + 2.6e-04 * pow(Re, 1.38)) * (24.0 / (Re + 0.00001));
 }
 
+// CalcAeroAcc, Aero.h:204-263: Gissler (Aero.h:37-98), induced pressure (Aero.h:106-202), skin friction (Aero.h:224-257).
+// Vd = cellV - v; np = {surface normal, lam_nb}; th = {p, m, woccl, cellRho}; norm_curve = dx * curvature.
+__device__ void calc_aero_acc(const DevConst& C, double dx_, double dy_, double dz_, const double4& np, const double4& th,
+                              double cellP, double norm_curve, double nneigh, double (&out)[3])
+{
+    const double vd2 = dx_ * dx_ + dy_ * dy_ + dz_ * dz_;
+    const double vd = sqrt(vd2);
+    const double lam_nb = np.w, mass = th.y, cellRho = th.w;
+    out[0] = out[1] = out[2] = 0.0;
+    if (C.acase == 1)
+    {
+        const double Re = 2.0 * cellRho * vd * C.aero_L / C.mu_g;
+        double frac2;
+        if (C.use_lam)
+            frac2 = fmin(C.interp_fac * lam_nb, 1.0);
+        else
+            frac2 = fmin(C.interp_fac * nneigh * C.i_n_full, 1.0);
+        const double frac1 = 1.0 - frac2;
+        const double Cds = get_cd(Re);
+        double Cdl, Adrop;
+        if (C.use_TAB_def)
+        {
+            double ymax = vd2 * C.ycoef;
+            if (ymax > 1.0)
+                ymax = 1.0;
+            Cdl = Cds * (1 + 2.632 * ymax);
+            const double rr_ = C.aero_L + C.tab_Cb * C.aero_L * ymax;
+            Adrop = FJ_PI * rr_ * rr_;
+        }
+        else
+        {
+            Cdl = Cds;
+            Adrop = C.A_sphere;
+        }
+        const double Cdi = frac1 * Cdl + frac2;
+        const double Ai = (1.0 - th.z) * (frac1 * Adrop + frac2 * C.A_plate);
+        const double f = 0.5 * vd / C.sos2 * C.gamma_g * cellP * Cdi * Ai / mass;
+        out[0] = f * dx_;
+        out[1] = f * dy_;
+        out[2] = f * dz_;
+        return;
+    }
+    /* unit normal and unit Vdiff; Eigen's normalized() leaves the zero vector unchanged */
+    double nx = np.x, ny = np.y, nz = np.z;
+    {
+        const double nn = nx * nx + ny * ny + nz * nz;
+        if (nn > 0.0)
+        {
+            const double inv = 1.0 / sqrt(nn);
+            nx *= inv;
+            ny *= inv;
+            nz *= inv;
+        }
+    }
+    const double Vnorm = dx_ * nx + dy_ * ny + dz_ * nz;
+    if (C.acase == 2)
+    {
+        const double ivd = vd2 > 0.0 ? 1.0 / vd : 1.0;
+        const double theta = fabs(acos(-(nx * dx_ + ny * dy_ + nz * dz_) * ivd));
+        double Cp_s, Cp_p, Cp_b, Cp_tot;
+        if (theta < 2.4455)
+        {
+            const double st = sin(theta);
+            Cp_s = 1.0 - 2.25 * (st * st);
+        }
+        else
+            Cp_s = 0.075;
+        if (theta < 1.570797)
+            Cp_p = cos(theta);
+        else if (theta < 1.9918)
+            Cp_p = -pow(cos(6.0 * theta + 0.5 * FJ_PI), 1.5);
+        else if (theta < 2.0838)
+            Cp_p = 5.5836 * theta - 11.5601;
+        else
+            Cp_p = 0.075;
+        if (theta < 0.7854)
+            Cp_b = 1.0;
+        else if (theta < 1.570797)
+            Cp_b = 0.5 * (cos(4.0 * theta - FJ_PI) + 1.0);
+        else
+            Cp_b = 0.0;
+        const double fac1 = 0.25, ifac1 = 4.0;
+        if (norm_curve < -fac1)
+            Cp_tot = Cp_b;
+        else if (norm_curve < 0.0)
+        {
+            const double frac = (norm_curve + fac1) * ifac1;
+            Cp_tot = frac * Cp_b + (1.0 - frac) * Cp_p;
+        }
+        else if (norm_curve < fac1)
+        {
+            const double frac = norm_curve * ifac1;
+            Cp_tot = frac * Cp_p + (1.0 - frac) * Cp_s;
+        }
+        else
+            Cp_tot = Cp_s;
+        const double q = C.gamma_g * cellP / C.sos2; /* compressible dynamic pressure factor */
+        const double Plocali = 0.5 * vd2 * q * Cp_tot;
+        const double Cdi = get_cd(cellRho * vd * C.aero_L / C.mu_g);
+        const double fd = 0.5 * vd * q * (FJ_PI * C.aero_L * C.aero_L * 0.25) * Cdi / mass;
+        const double fk = -Plocali * C.A_plate / mass;
+        const double px = dx_ - Vnorm * nx, py = dy_ - Vnorm * ny, pz = dz_ - Vnorm * nz;
+        const double vpar = sqrt(px * px + py * py + pz * pz);
+        const double Cf = 0.027 / pow(cellRho * vpar * C.aero_L / C.mu_g + 1e-6, 1.0 / 7.0);
+        const double fs = 0.5 * vpar * q * Cf * C.A_plate / mass;
+        double frac1;
+        if (C.use_lam)
+            frac1 = fmin(C.interp_fac * lam_nb, 1.0);
+        else
+            frac1 = fmin(C.interp_fac * nneigh * C.i_n_full, 1.0);
+        out[0] = frac1 * (fk * nx + fs * px) + (1.0 - frac1) * (fd * dx_);
+        out[1] = frac1 * (fk * ny + fs * py) + (1.0 - frac1) * (fd * dy_);
+        out[2] = frac1 * (fk * nz + fs * pz) + (1.0 - frac1) * (fd * dz_);
+        return;
+    }
+    if (C.acase == 3 && Vnorm > 0.001)
+    {
+        const double Re = C.rho_g * vd * C.aero_L / C.mu_g;
+        const double fp = 0.5 * C.rho_g * Vnorm * Vnorm * C.A_plate / mass;
+        const double an = fabs(Vnorm);
+        const double px = dx_ - an * nx, py = dy_ - an * ny, pz = dz_ - an * nz;
+        const double vpar = sqrt(px * px + py * py + pz * pz);
+        const double Cf = 0.027 / pow(Re, 1.0 / 7.0);
+        const double fs = 0.5 * C.rho_g * vpar * Cf * C.A_plate / mass;
+        const double frac2 = fmin(1.5 * lam_nb, 1.0), frac1 = 1.0 - frac2;
+        const double fd = 0.5 * C.rho_g * vd * (FJ_PI * C.aero_L * C.aero_L / 4) * get_cd(Re) / mass;
+        out[0] = frac2 * (fp * nx + fs * px) + frac1 * (fd * dx_);
+        out[1] = frac2 * (fp * ny + fs * py) + frac1 * (fd * dy_);
+        out[2] = frac2 * (fp * nz + fs * pz) + frac1 * (fd * dz_);
+    }
+}
+
 struct RecF
 {
     double4 p, v, q;
@@ -772,49 +904,23 @@ __global__ void __launch_bounds__(TPB, FJ_FORCE_MINBLOCKS)
     double4 af = S.AF[i];                /* Af, deltaD */
 
     /* aero term, Resid.cpp:267-277 (Q1: evaluated whenever cellID != -1) */
-    if (S.cellID[i] != -1 && C.acase == 1)
+    if (S.cellID[i] != -1)
     {
-        const double4 cv = S.CV[i];
-        const double dx_ = cv.x - vi.x, dy_ = cv.y - vi.y, dz_ = cv.z - vi.z;
-        const double vd2 = dx_ * dx_ + dy_ * dy_ + dz_ * dz_;
-        const double vd = sqrt(vd2);
-        const double Re = 2.0 * th.w * vd * C.aero_L / C.mu_g;
-        const double lam_nb = S.NP[i].w;
-        double frac2;
-        if (C.use_lam)
-            frac2 = fmin(C.interp_fac * lam_nb, 1.0);
-        else
-            frac2 = fmin(C.interp_fac * double(lv.ncount[i] + 1) * C.i_n_full, 1.0);
-        const double frac1 = 1.0 - frac2;
-        const double Cds = get_cd(Re);
-        double Cdl, Adrop;
-        if (C.use_TAB_def)
+        af.x = af.y = af.z = 0.0; /* CalcAeroAcc returns zero for NoAero */
+        if (C.acase != 0)
         {
-            double ymax = vd2 * C.ycoef;
-            if (ymax > 1.0)
-                ymax = 1.0;
-            Cdl = Cds * (1 + 2.632 * ymax);
-            const double rr_ = C.aero_L + C.tab_Cb * C.aero_L * ymax;
-            Adrop = FJ_PI * rr_ * rr_;
+            const double4 cv = S.CV[i];
+            const double4 np = S.NP[i]; /* surface normal, lam_nb */
+            double a3[3];
+            calc_aero_acc(C, cv.x - vi.x, cv.y - vi.y, cv.z - vi.z, np, th, cv.w, S.AV[i].w * C.dx,
+                          double(lv.ncount[i] + 1), a3);
+            af.x = a3[0];
+            af.y = a3[1];
+            af.z = a3[2];
+            ax += af.x;
+            ay += af.y;
+            az += af.z;
         }
-        else
-        {
-            Cdl = Cds;
-            Adrop = C.A_sphere;
-        }
-        const double Cdi = frac1 * Cdl + frac2;
-        const double Ai = (1.0 - th.z) * (frac1 * Adrop + frac2 * C.A_plate);
-        const double f = 0.5 * vd / C.sos2 * C.gamma_g * cv.w * Cdi * Ai / th.y;
-        af.x = f * dx_;
-        af.y = f * dy_;
-        af.z = f * dz_;
-        ax += af.x;
-        ay += af.y;
-        az += af.z;
-    }
-    else if (S.cellID[i] != -1)
-    {
-        af.x = af.y = af.z = 0.0; /* CalcAeroAcc default branch returns zero */
     }
 
     for_neighbours_pipelined(

@@ -1207,11 +1207,93 @@ static Vec gissler_force(OrcParams const& P, Vec const& Vdiff, real rho, real pr
     real const Ai = (1.0 - woccl) * Aunocc;
     return 0.5 * norm(Vdiff) * Vdiff / (P.sos * P.sos) * P.gamma_g * press * Cdi * Ai / mass;
 }
-/* Aero.h:204-263; only NoAero and Gissler are in scope */
+/* Aero.h:106-202 */
+static Vec induced_pressure(OrcParams const& P, State const& S, size_t ii, Vec const& Vdiff, Vec const& nrm, real lam,
+                            real nneigh)
+{
+    Vec const nh = normalized(nrm);
+    real const theta = std::fabs(std::acos(-dot(nh, normalized(Vdiff))));
+    real Cp_s, Cp_p, Cp_b, Cp_tot;
+    if (theta < 2.4455)
+        Cp_s = 1.0 - (2.25) * std::pow(std::sin(theta), 2.0);
+    else
+        Cp_s = 0.075;
+    if (theta < 1.570797)
+        Cp_p = std::cos(theta);
+    else if (theta < 1.9918)
+        Cp_p = -std::pow(std::cos(6.0 * theta + 0.5 * M_PI), 1.5);
+    else if (theta < 2.0838)
+        Cp_p = 5.5836 * theta - 11.5601;
+    else
+        Cp_p = 0.075;
+    if (theta < 0.7854)
+        Cp_b = 1.0;
+    else if (theta < 1.570797)
+        Cp_b = 0.5 * (std::cos(4.0 * theta - M_PI) + 1.0);
+    else
+        Cp_b = 0.0;
+    real const normCurve = S.norm_curve[ii];
+    real const fac1 = 0.25, ifac1 = 1 / fac1;
+    if (normCurve < -fac1)
+        Cp_tot = Cp_b;
+    else if (normCurve < 0.0)
+    {
+        real const frac = (normCurve + fac1) * ifac1;
+        Cp_tot = frac * Cp_b + (1.0 - frac) * Cp_p;
+    }
+    else if (normCurve < fac1)
+    {
+        real const frac = (normCurve)*ifac1;
+        Cp_tot = frac * Cp_p + (1.0 - frac) * Cp_s;
+    }
+    else
+        Cp_tot = Cp_s;
+    real const sos2 = P.sos * P.sos;
+    real const Plocali = 0.5 * sqnorm(Vdiff) / sos2 * P.gamma_g * S.cellP[ii] * Cp_tot;
+    real const Re = S.cellRho[ii] * norm(Vdiff) * P.aero_L / P.mu_g;
+    real const Cdi = GetCd(Re);
+    Vec const acc_drop = 0.5 * Vdiff * norm(Vdiff) / sos2 * P.gamma_g * S.cellP[ii] *
+                         (M_PI * P.aero_L * P.aero_L * 0.25) * Cdi / S.m[ii];
+    Vec const acc_kern = -Plocali * P.A_plate * nh / S.m[ii];
+    real const Vnorm = dot(Vdiff, nh);
+    Vec const Vpar = Vdiff - Vnorm * nh;
+    real const Re_par = S.cellRho[ii] * norm(Vpar) * P.aero_L / P.mu_g;
+    real const Cf = 0.027 / std::pow(Re_par + 1e-6, 1.0 / 7.0);
+    Vec const acc_skin = 0.5 * norm(Vpar) * Vpar / sos2 * P.gamma_g * S.cellP[ii] * Cf * P.A_plate / S.m[ii];
+    real frac1;
+    if (P.use_lam)
+        frac1 = std::min(P.interp_fac * lam, 1.0);
+    else
+        frac1 = std::min(P.interp_fac * nneigh * P.i_n_full, 1.0);
+    return (frac1 * (acc_kern + acc_skin) + (1.0 - frac1) * acc_drop);
+}
+/* Aero.h:224-257 */
+static Vec skin_friction(OrcParams const& P, State const& S, size_t ii, Vec const& Vdiff, Vec const& nrm, real lam)
+{
+    Vec const nh = normalized(nrm);
+    real const Vnorm = dot(Vdiff, nh);
+    if (!(Vnorm > 0.001))
+        return vzero();
+    real const Re = P.rho_g * norm(Vdiff) * P.aero_L / P.mu_g;
+    Vec const acc_press = 0.5 * P.rho_g * Vnorm * Vnorm * P.A_plate * nh / S.m[ii];
+    Vec const Vpar = Vdiff - std::fabs(Vnorm) * nh;
+    real const Cf = 0.027 / std::pow(Re, 1.0 / 7.0);
+    Vec const acc_skin = 0.5 * P.rho_g * norm(Vpar) * Cf * P.A_plate * Vpar / S.m[ii];
+    real const frac2 = std::min(1.5 * lam, 1.0);
+    real const frac1 = (1.0 - frac2);
+    real const Cdi = GetCd(Re);
+    Vec const acc_drop = 0.5 * P.rho_g * norm(Vdiff) * Vdiff * (M_PI * P.aero_L * P.aero_L / 4) * Cdi / S.m[ii];
+    return frac2 * (acc_press + acc_skin) + frac1 * acc_drop;
+}
+/* Aero.h:204-263 */
 static Vec CalcAeroAcc(OrcParams const& P, State const& S, size_t ii, Vec const& Vdiff, real lam, real nneigh)
 {
     if (P.acase == Gissler)
         return gissler_force(P, Vdiff, S.cellRho[ii], S.cellP[ii], S.m[ii], lam, nneigh, S.woccl[ii]);
+    if (P.acase == 2) /* InducedPressure */
+        return induced_pressure(P, S, ii, Vdiff, S.norm[ii], lam, nneigh);
+    if (P.acase == 3) /* SkinFric */
+        return skin_friction(P, S, ii, Vdiff, S.norm[ii], lam);
     return vzero();
 }
 

@@ -233,6 +233,23 @@ def test_walls_nb_iteration_parity(ale):
         assert_fields_close(e, o, ("xi", "v", "rho", "p", "acc", "Rrho"), tol=1e-9, context="walls nb_iter %d" % it)
 
 
+@pytest.mark.parametrize("acase", [2, 3], ids=["induced_pressure", "skin_friction"])
+def test_other_aero_models(acase):
+    """CalcAeroAcc's other two models (Aero.h:106-202 induced pressure, Aero.h:224-257 skin friction) on the droplet in
+    a 21.55 m/s freestream: per-particle, no pair loop, evaluated in the prologue of the force kernel."""
+    case = cases.droplet(dx=0.005, jitter=0.05)
+    o, e, p = make_pair(case, acase=acase, delta_t_min=1e-9)
+    for step in range(3):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert se.iterations == so.iterations, step
+        assert abs(se.maxAf - so.maxAf) <= 1e-6 * so.maxAf, step
+        assert_fields_close(e, o, ("xi", "rho"), tol=1e-10, context="aero %d step %d" % (acase, step))
+        assert_fields_close(e, o, ("v",), tol=1e-8, context="aero %d step %d" % (acase, step))
+        assert_fields_close(e, o, ("Af", "acc"), tol=1e-6, context="aero %d step %d" % (acase, step))
+    assert np.abs(o.get("Af")).max() > 0.1   # the model is really acting
+
+
 def test_state_after_1000_steps():
     """north_star: "state after 1000 steps within a stated tolerance".  1000 Integrator::integrate calls on a jittered
     block (free surfaces on all sides, ALE shifting, surface tension): the sub-iteration count and dt of every step
