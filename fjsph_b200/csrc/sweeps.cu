@@ -19,7 +19,10 @@
 namespace
 {
 
-constexpr int TPB = 128;
+#ifndef FJ_SWEEP_TPB
+#define FJ_SWEEP_TPB 128
+#endif
+constexpr int TPB = FJ_SWEEP_TPB;
 #define FJ_PI 3.14159265358979323846
 
 struct ListView
@@ -350,7 +353,10 @@ struct RecS1
 };
 
 template <bool SURF, bool DISS>
-__global__ void __launch_bounds__(TPB, 3)
+#ifndef FJ_S1_MINBLOCKS
+#define FJ_S1_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
     k_surf1_diss(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
