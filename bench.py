@@ -52,7 +52,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="block", choices=["block", "droplet"])
+    ap.add_argument("--workload", default="block", choices=["block", "jet", "droplet"])
+    ap.add_argument("--jet-columns", type=int, default=255, help="jet workload: lattice columns along x per GPU (R = 125 dx)")
     ap.add_argument("--cells", default="500,250,100", help="block lattice per GPU (x,y,z)")
     ap.add_argument("--droplet-dx", type=float, default=0.0008)
     ap.add_argument("--solver", default="newmark_beta", choices=["newmark_beta", "runge_kutta"])
@@ -77,6 +78,9 @@ def make_case(args, rank=0, cells=None):
 
     if args.workload == "droplet":
         return cases.droplet(dx=args.droplet_dx)
+    if args.workload == "jet":
+        nx = int(cells.split(",")[0]) if cells else args.jet_columns
+        return cases.synthetic_jet(nx=nx, dx=1e-3, jitter=0.1, seed=1234, x_offset_cells=rank * nx)
     n = tuple(int(k) for k in (cells or args.cells).split(","))
     return cases.synthetic_block(n, 1e-3, jitter=0.1, seed=1234, x_offset_cells=rank * n[0])
 
@@ -84,6 +88,10 @@ def make_case(args, rank=0, cells=None):
 def workload_name(args, world):
     if args.workload == "droplet":
         return "Examples/Droplet 3D (para3D), dx=%g" % args.droplet_dx
+    if args.workload == "jet":
+        return ("synthetic 3D jet C5: cylinder R=125dx along x, %d columns = ~%.2fM FREE particles per GPU, dx=1e-3, "
+                "jitter 0.1dx, v=(30,0,0), Gissler aero in a (0,100,0) cross flow%s" % (
+                    args.jet_columns, 49080 * args.jet_columns / 1e6, ", slab-decomposed along x" if world > 1 else ""))
     n = [int(k) for k in args.cells.split(",")]
     return "synthetic 3D block C5, %dx%dx%d = %.2fM FREE particles per GPU, dx=1e-3, jitter 0.1dx%s" % (
         n[0], n[1], n[2], n[0] * n[1] * n[2] / 1e6, ", slab-decomposed along x" if world > 1 else "")
@@ -148,7 +156,14 @@ def cpu_reference(args, steps, warmup, sample_cells):
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)  # in case libgomp was initialised before
     except OSError:
         pass
-    case = make_case(args, 0, cells=sample_cells) if args.workload == "block" else make_case(args)
+    if args.workload == "block":
+        case = make_case(args, 0, cells=sample_cells)
+    elif args.workload == "jet":
+        from fjsph_b200 import cases
+
+        case = cases.synthetic_jet(nx=64, radius_cells=32, dx=1e-3, jitter=0.1, seed=1234)
+    else:
+        case = make_case(args)
     params = step_params(args, case["params"])
     o = orc.Oracle(orc.default_params(3, kind="3d_fast", **params), kind="3d_fast")
     o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
@@ -164,7 +179,8 @@ def cpu_reference(args, steps, warmup, sample_cells):
     desc = ("oracle/fjsph_oracle.cpp (-O3 -ffast-math -funroll-loops -fopenmp -march=native), %d threads, %d steps "
             "after %d warm-up on %s, %d particles, %d sub-iterations" % (
                 cores, steps, warmup, "a %s lattice of the block workload" % sample_cells
-                if args.workload == "block" else "the droplet", n, its))
+                if args.workload == "block" else ("a 64-column, R=32dx cylinder of the jet workload"
+                                                  if args.workload == "jet" else "the droplet"), n, its))
     return n * steps / dt, cores, desc, dt / steps * 1e3
 
 
@@ -216,7 +232,7 @@ def main():
         from fjsph_b200 import slab
 
         # rank r owns lattice columns [r*nx, (r+1)*nx): faces half a spacing outside its first / last column
-        nx = int(args.cells.split(",")[0])
+        nx = args.jet_columns if args.workload == "jet" else int(args.cells.split(",")[0])
         dx = case["params"]["particle_step"]
         x_lo = -1e300 if rank == 0 else (rank * nx - 0.5) * dx
         x_hi = 1e300 if rank == world - 1 else ((rank + 1) * nx - 0.5) * dx

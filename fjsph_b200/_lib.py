@@ -124,6 +124,8 @@ def lib():
     L.fjsph_set_owned.argtypes = [vp, C.c_int64]
     L.fjsph_set_skin.argtypes = [vp, C.c_double]
     L.fjsph_set_slab.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_double, COMM_FN, vp]
+    L.fjsph_slab_comm_stream.argtypes = [vp, P(vp)]
+    L.fjsph_slab_overlapped.argtypes = [vp, P(C.c_int64)]
     L.fjsph_slab_stats.argtypes = [vp, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)]
     _lib = L
     return L

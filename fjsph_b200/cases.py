@@ -62,6 +62,31 @@ def synthetic_block(n=(500, 250, 100), dx=1e-3, jitter=0.1, seed=1234, rho0=1000
     )
 
 
+def synthetic_jet(nx=255, radius_cells=125, dx=1e-3, jitter=0.1, seed=1234, rho0=1000.0, c=100.0, x_offset_cells=0,
+                  v_jet=30.0, v_inf=(0.0, 100.0, 0.0)):
+    """Config C5, "jet" flavour: a liquid cylinder of radius radius_cells*dx along x moving at
+    v = (v_jet, 0, 0) in a cross flow v_inf with the Gissler aero model on.  nx lattice columns per slab
+    (nx = 255 -> 12.5 M particles at R = 125 dx); x_offset_cells shifts the slab as in synthetic_block."""
+    side = 2 * int(radius_cells) + 1
+    pts = lattice((nx, side, side), dx, start=(x_offset_cells * dx, -radius_cells * dx, -radius_cells * dx), jitter=None)
+    keep = (pts[:, 1] ** 2 + pts[:, 2] ** 2) <= (radius_cells * dx) ** 2 * (1.0 + 1e-12)
+    pts = pts[keep]
+    rng = np.random.default_rng(seed + x_offset_cells)
+    xi = np.ascontiguousarray(pts + rng.uniform(-float(jitter), float(jitter), size=pts.shape) * dx)
+    N = xi.shape[0]
+    Lx = nx * dx
+    rho = rho0 * (1.0 + 1e-3 * np.sin(2 * np.pi * xi[:, 0] / Lx))
+    v = np.zeros_like(xi)
+    v[:, 0] = v_jet
+    return dict(
+        xi=xi, v=v, rho=rho, p=cole_pressure(rho, rho0, c), m=np.full(N, rho0 * dx**3),
+        b=np.full(N, FREE, dtype=np.int32), bound_points=0,
+        params=dict(particle_step=dx, rho_rest=rho0, speed_sound=c, mu=8.94e-4, sig=0.0708, visc_alpha=0.05,
+                    dsph_delta=0.1, grav=(0.0, 0.0, -9.81), acase=1, v_inf=tuple(v_inf), p_ref=100000.0, rho_g=1.1025,
+                    mu_g=1.716e-05, temp_g=298.0),
+    )
+
+
 def droplet(dx=0.0015, radius=0.05, seed=1234, dim=3, jitter="eps"):
     """Config C2, Examples/Droplet/{para3D,fluid_3D.bmap}: sphere R=0.05 at the origin, rho 810,
     Gissler aero with v_inf = (0, 21.55, 0).  Lattice start = centre - radius, end = centre + radius

@@ -28,6 +28,8 @@ int fj_cuda_fail(cudaError_t err, const char* what, const char* file, int line)
 KScope::KScope(FjsphEngine* e_, const char* name, int launches) : e(e_), id(-1)
 {
     e->launches += launches;
+    if (e->slab.pending && !e->slab.hold)
+        fj_halo_wait(e); /* every kernel family but the interior launches of the split sweeps sees complete ghosts */
     if (!e->timers_on)
         return;
     for (size_t k = 0; k < e->timers.size(); ++k)
@@ -704,6 +706,7 @@ int fjsph_destroy(FjsphEngine* e)
     if (!e)
         return FJSPH_OK;
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     cudaStreamSynchronize(e->stream);
     for (int l = 0; l < 3; ++l)
     {
@@ -736,6 +739,13 @@ int fjsph_destroy(FjsphEngine* e)
     cudaEventDestroy(e->ev1);
     fj_timers_flush(e);
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->slab.comm_stream)
+    {
+        cudaStreamSynchronize(e->slab.comm_stream);
+        cudaStreamDestroy(e->slab.comm_stream);
+        cudaEventDestroy(e->slab.ev_ready);
+        cudaEventDestroy(e->slab.ev_done);
+    }
     if (e->own_stream)
         cudaStreamDestroy(e->stream);
     delete e;
@@ -767,6 +777,7 @@ int fjsph_set_params(FjsphEngine* e, const FjsphParams* in)
 int fjsph_set_blocks(FjsphEngine* e, int32_t n_blocks, const FjsphBlock* blocks)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     std::vector<HostBlock> out;
     int n_bound = 0;
     bool seen_fluid = false;
@@ -836,6 +847,7 @@ int fjsph_set_blocks(FjsphEngine* e, int32_t n_blocks, const FjsphBlock* blocks)
 int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_points)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     if (!s || s->n <= 0 || !s->xi || !s->rho || !s->p || !s->m || !s->b)
     {
         fj_set_error("upload_state: xi, rho, p, m and b are required");
@@ -885,6 +897,7 @@ int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_po
 int fjsph_upload_level(FjsphEngine* e, int level, const FjsphStateView* s)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     if (level < 0 || level > 1 || !s || s->n != e->n)
     {
         fj_set_error("upload_level: bad level or particle count (have %lld)", (long long)e->n);
@@ -902,6 +915,7 @@ int fjsph_upload_level(FjsphEngine* e, int level, const FjsphStateView* s)
 int fjsph_upload_owned(FjsphEngine* e, const FjsphStateView* s)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     if (!s || s->n != e->n_owned)
     {
         fj_set_error("upload_owned: view holds %lld particles, this rank owns %lld", s ? (long long)s->n : -1LL,
@@ -922,6 +936,7 @@ int fjsph_upload_owned(FjsphEngine* e, const FjsphStateView* s)
 int fjsph_download_state(FjsphEngine* e, int level, FjsphStateView* s)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     if (level < 0 || level > 1 || !s)
     {
         fj_set_error("download_state: bad arguments");
@@ -957,12 +972,14 @@ int64_t fjsph_count(FjsphEngine* e) { return e ? e->n_owned : -1; }
 int fjsph_build_neighbours(FjsphEngine* e)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     return fj_build_neighbours(e);
 }
 
 int fjsph_neighbour_counts(FjsphEngine* e, int64_t* counts)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     if (!e->list_valid)
     {
         fj_set_error("neighbour_counts: list not built");
@@ -982,6 +999,7 @@ int fjsph_neighbour_counts(FjsphEngine* e, int64_t* counts)
 int fjsph_get_neighbours(FjsphEngine* e, const int64_t* offsets, int64_t* idx)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     if (!e->list_valid)
     {
         fj_set_error("get_neighbours: list not built");
@@ -1015,11 +1033,13 @@ int fjsph_get_neighbours(FjsphEngine* e, const int64_t* offsets, int64_t* idx)
 int fjsph_prestep(FjsphEngine* e, double* npd)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     return fj_prestep(e, npd);
 }
 int fjsph_aero_velocity(FjsphEngine* e)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     int st = fj_aero_velocity(e);
     if (st)
         return st;
@@ -1029,6 +1049,7 @@ int fjsph_aero_velocity(FjsphEngine* e)
 int fjsph_detect_surface(FjsphEngine* e)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     int st = fj_surface_and_dissipation(e, true, false);
     if (st)
         return st;
@@ -1038,6 +1059,7 @@ int fjsph_detect_surface(FjsphEngine* e)
 int fjsph_dissipation(FjsphEngine* e)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     int st = fj_surface_and_dissipation(e, false, true);
     if (st)
         return st;
@@ -1047,6 +1069,7 @@ int fjsph_dissipation(FjsphEngine* e)
 int fjsph_shift(FjsphEngine* e)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     int st = fj_shift(e);
     if (st)
         return st;
@@ -1056,6 +1079,7 @@ int fjsph_shift(FjsphEngine* e)
 int fjsph_forces(FjsphEngine* e, double npd)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     int st = fj_forces(e, 1, npd);
     if (st)
         return st;
@@ -1065,21 +1089,25 @@ int fjsph_forces(FjsphEngine* e, double npd)
 int fjsph_nb_iter(FjsphEngine* e, double npd, double* errsum)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     return fj_nb_iter(e, npd, errsum);
 }
 int fjsph_find_timestep(FjsphEngine* e, double* dt)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     return fj_find_timestep(e, dt);
 }
 int fjsph_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     return fj_integrate_no_update(e, s);
 }
 int fjsph_step(FjsphEngine* e, FjsphStepStats* s)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     int st = fj_step(e, s);
     if (st)
         return st;
@@ -1118,6 +1146,7 @@ int fjsph_timers_get(FjsphEngine* e, int32_t cap, char* names, double* ms, int64
                      int32_t* n_out)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     fj_timers_flush(e);
     const int n = std::min<int>(cap, int(e->timers.size()));
     for (int k = 0; k < n; ++k)
@@ -1136,6 +1165,7 @@ int64_t fjsph_launch_count(FjsphEngine* e) { return e->launches; }
 int fjsph_set_stream(FjsphEngine* e, void* cuda_stream)
 {
     cudaSetDevice(e->device);
+    fj_halo_wait(e); /* slab mode: an exchange may still be in flight on the comm stream */
     fj_timers_flush(e);
     FJ_CUDA(cudaStreamSynchronize(e->stream));
     if (e->own_stream && e->stream)

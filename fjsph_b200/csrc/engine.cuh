@@ -93,6 +93,17 @@ struct Slab
     unsigned* scan_tmp = nullptr;
     double n_fluid_global = 0.0, n_total_global = 0.0;
     long long exchanges = 0, redecomps = 0, bytes_sent = 0;
+    // Forward exchanges overlapped with interior work: pack, NCCL send/recv and unpack run on comm_stream while the
+    // main stream sweeps the INTERIOR owned particles (slots [0, n_interior): farther than 2H + skin from every face
+    // with a neighbour rank, so none of their neighbours is a ghost); the EDGE particles [n_interior, n_owned) are
+    // swept after the main stream has waited for ev_done.  Every other kernel family waits first (KScope).
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    bool overlap = true;      // FJSPH_SLAB_OVERLAP=0 in the environment: exchanges complete before the next launch
+    bool pending = false;     // an exchange is in flight on comm_stream
+    bool hold = false;        // set around the interior launches: KScope does not wait
+    int64_t n_interior = 0;   // multiple of 32 (whole list warps)
+    long long overlapped = 0; // exchanges that ran beside an interior sweep
 };
 
 // aero mesh on the device (mesh.cu): per-face vertex coordinates, boundary markers, cell -> faces, cell centres and
@@ -269,7 +280,13 @@ int fj_reduce_sum(FjsphEngine* e, int nblocks, int ncomp, double* out_host);
 void fj_refresh_constants(FjsphEngine* e);
 void fj_timers_flush(FjsphEngine* e);
 // slab decomposition (halo.cu); all are no-ops / identities on a single rank
-int fj_halo_exchange(FjsphEngine* e, int level, unsigned mask);
+int fj_halo_exchange(FjsphEngine* e, int level, unsigned mask); /* begin; completed by the next fj_halo_wait */
+int fj_halo_wait(FjsphEngine* e);                               /* main stream waits for the exchange in flight */
+/* true while an exchange is in flight that an interior/edge split sweep may run beside */
+static inline bool fj_halo_overlappable(const FjsphEngine* e)
+{
+    return e->slab.on && e->slab.pending && e->slab.n_interior > 0 && e->slab.n_interior < e->n_owned;
+}
 int fj_allreduce(FjsphEngine* e, int op, double* v, int n);
 int fj_redecompose(FjsphEngine* e);
 double fj_fluid_count(FjsphEngine* e);

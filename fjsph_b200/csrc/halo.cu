@@ -11,6 +11,7 @@
 //     are all-reduced so every rank takes identical decisions.
 // Transport is the host's (FjsphCommFn, include/fjsph_b200.h): NCCL send/recv in fjsph_b200/slab.py.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.cuh"
@@ -251,42 +252,69 @@ double fj_fluid_count(FjsphEngine* e)
 }
 double fj_total_count(FjsphEngine* e) { return e->slab.on ? e->slab.n_total_global : double(e->n_owned); }
 
+int fj_halo_wait(FjsphEngine* e)
+{
+    Slab& S = e->slab;
+    if (!S.pending)
+        return FJSPH_OK;
+    S.pending = false;
+    FJ_CUDA(cudaStreamWaitEvent(e->stream, S.ev_done, 0));
+    return FJSPH_OK;
+}
+
+// Forward exchange of the fields in `mask` for the current ghost set.  The pack kernels, the transport (NCCL send/recv,
+// FJSPH_COMM_SENDRECV_DEV_ASYNC: ordered on comm_stream) and the unpack kernels are queued on comm_stream behind
+// everything the main stream has launched so far; the main stream picks the result up at the next fj_halo_wait --
+// issued by KScope before any kernel family, except the interior launches of the split sweeps (sweeps.cu).
 int fj_halo_exchange(FjsphEngine* e, int level, unsigned mask)
 {
     Slab& S = e->slab;
     if (!S.on || S.world == 1)
         return FJSPH_OK;
+    int st = fj_halo_wait(e); /* one exchange in flight at a time: the buffers are shared */
+    if (st)
+        return st;
     Level& L = e->lv[level];
     const size_t bs[2] = {fields_bytes(mask, size_t(S.n_send[0])), fields_bytes(mask, size_t(S.n_send[1]))};
     const size_t br[2] = {fields_bytes(mask, size_t(S.n_recv[0])), fields_bytes(mask, size_t(S.n_recv[1]))};
-    int st = ensure_buffers(e, std::max(std::max(bs[0], bs[1]), std::max(br[0], br[1])));
-    if (st)
-        return st;
+    if (std::max(std::max(bs[0], bs[1]), std::max(br[0], br[1])) > S.buf_bytes)
+    {
+        FJ_CUDA(cudaStreamSynchronize(S.comm_stream)); /* the old buffers may still be in use */
+        st = ensure_buffers(e, std::max(std::max(bs[0], bs[1]), std::max(br[0], br[1])));
+        if (st)
+            return st;
+    }
+    cudaStream_t cs = S.overlap ? S.comm_stream : e->stream;
+    if (S.overlap)
+    {
+        FJ_CUDA(cudaEventRecord(S.ev_ready, e->stream));
+        FJ_CUDA(cudaStreamWaitEvent(cs, S.ev_ready, 0));
+    }
     D4Table T = table_of(L);
-    {
-        KScope ks(e, "halo_pack", 2);
-        for (int s = 0; s < 2; ++s)
-            if (S.n_send[s] > 0)
-                k_pack_fields<<<fj_blocks(S.n_send[s], TPB), TPB, 0, e->stream>>>(T, L.surfzone, L.b, mask, S.send_idx[s],
-                                                                                  e->slot_of, int(S.n_send[s]), S.sbuf[s]);
-    }
+    e->launches += 4;
+    for (int s = 0; s < 2; ++s)
+        if (S.n_send[s] > 0)
+            k_pack_fields<<<fj_blocks(S.n_send[s], TPB), TPB, 0, cs>>>(T, L.surfzone, L.b, mask, S.send_idx[s], e->slot_of,
+                                                                       int(S.n_send[s]), S.sbuf[s]);
     FJ_CUDA(cudaGetLastError());
-    st = comm(e, FJSPH_COMM_SENDRECV_DEV, S.sbuf[0], int64_t(bs[0]), S.sbuf[1], int64_t(bs[1]), S.rbuf[0], int64_t(br[0]),
-              S.rbuf[1], int64_t(br[1]));
+    st = comm(e, S.overlap ? FJSPH_COMM_SENDRECV_DEV_ASYNC : FJSPH_COMM_SENDRECV_DEV, S.sbuf[0], int64_t(bs[0]), S.sbuf[1],
+              int64_t(bs[1]), S.rbuf[0], int64_t(br[0]), S.rbuf[1], int64_t(br[1]));
     if (st)
         return st;
+    int first = int(e->n_owned);
+    for (int s = 0; s < 2; ++s)
     {
-        KScope ks(e, "halo_unpack", 2);
-        int first = int(e->n_owned);
-        for (int s = 0; s < 2; ++s)
-        {
-            if (S.n_recv[s] > 0)
-                k_unpack_fields<<<fj_blocks(S.n_recv[s], TPB), TPB, 0, e->stream>>>(T, L.surfzone, L.b, mask, first,
-                                                                                    e->slot_of, int(S.n_recv[s]), S.rbuf[s]);
-            first += int(S.n_recv[s]);
-        }
+        if (S.n_recv[s] > 0)
+            k_unpack_fields<<<fj_blocks(S.n_recv[s], TPB), TPB, 0, cs>>>(T, L.surfzone, L.b, mask, first, e->slot_of,
+                                                                         int(S.n_recv[s]), S.rbuf[s]);
+        first += int(S.n_recv[s]);
     }
     FJ_CUDA(cudaGetLastError());
+    if (S.overlap)
+    {
+        FJ_CUDA(cudaEventRecord(S.ev_done, cs));
+        S.pending = true;
+    }
     S.exchanges++;
     S.bytes_sent += (long long)(bs[0] + bs[1]);
     return FJSPH_OK;
@@ -303,7 +331,9 @@ int fj_redecompose(FjsphEngine* e)
     const bool has_lo = S.rank > 0, has_hi = S.rank < S.world - 1;
     const int n0 = int(e->n_owned);
     cudaStream_t st_ = e->stream;
-    int st;
+    int st = fj_halo_wait(e);
+    if (st)
+        return st;
 
     // ---- 1. classify the owned particles of pnp1 by slab, compact the three classes in slot order
     {
@@ -495,6 +525,16 @@ extern "C" int fjsph_set_slab(FjsphEngine* e, int32_t rank, int32_t world, doubl
     S.fn = fn;
     S.user = user;
     S.n_send[0] = S.n_send[1] = S.n_recv[0] = S.n_recv[1] = 0;
+    S.pending = false;
+    S.n_interior = 0;
+    if (const char* ov = getenv("FJSPH_SLAB_OVERLAP"))
+        S.overlap = atoi(ov) != 0;
+    if (!S.comm_stream)
+    {
+        FJ_CUDA(cudaStreamCreateWithFlags(&S.comm_stream, cudaStreamNonBlocking));
+        FJ_CUDA(cudaEventCreateWithFlags(&S.ev_ready, cudaEventDisableTiming));
+        FJ_CUDA(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+    }
     if (!S.flag[0])
     {
         const size_t cap = size_t(e->cap) + 1;
@@ -517,6 +557,25 @@ extern "C" int fjsph_set_slab(FjsphEngine* e, int32_t rank, int32_t world, doubl
         return st;
     S.n_fluid_global = v[0];
     S.n_total_global = v[1];
+    return FJSPH_OK;
+}
+
+/* the stream device-buffer exchanges with op FJSPH_COMM_SENDRECV_DEV_ASYNC must be ordered on */
+extern "C" int fjsph_slab_comm_stream(FjsphEngine* e, void** stream)
+{
+    if (!e->slab.on || !e->slab.comm_stream)
+    {
+        fj_set_error("slab_comm_stream: call fjsph_set_slab first");
+        return FJSPH_ERR_STATE;
+    }
+    *stream = (void*)e->slab.comm_stream;
+    return FJSPH_OK;
+}
+
+/* forward exchanges that ran beside an interior sweep since fjsph_set_slab */
+extern "C" int fjsph_slab_overlapped(FjsphEngine* e, int64_t* n)
+{
+    *n = e->slab.overlapped;
     return FJSPH_OK;
 }
 

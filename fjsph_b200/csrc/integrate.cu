@@ -583,10 +583,11 @@ static int frozen_terms(FjsphEngine* e, bool all)
     int st = fj_prestep(e, nullptr);
     if (st || !all)
         return st;
-    st = fj_halo_exchange(e, 1, FJ_HX_P3); /* gradRho_j, lam_j */
+    st = fj_aero_velocity(e); /* reads and writes particle i only: ahead of the exchange so that the surface sweep's
+                                 interior launch follows the exchange directly and runs beside it */
     if (st)
         return st;
-    st = fj_aero_velocity(e);
+    st = fj_halo_exchange(e, 1, FJ_HX_P3); /* gradRho_j, lam_j */
     if (st)
         return st;
     st = fj_surface_and_dissipation(e, true, true, true); /* loops 2+3 fused with particle_shift (ALE) */

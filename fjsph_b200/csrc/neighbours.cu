@@ -107,9 +107,13 @@ __device__ __forceinline__ void cell_of(const Grid& g, double x, double y, doubl
     cz = min(max(int(floor((z - g.oz) * g.inv_cell)), 0), g.nz - 1);
 }
 
+// Slab mode sorts three classes one behind the other (key offsets 0, n_keys, 2 n_keys): INTERIOR owned particles
+// (x in [x_edge_lo, x_edge_hi): farther than 2H + skin from every face with a neighbour rank, so no ghost can be
+// their neighbour), EDGE owned particles (the ones sent as ghosts, same predicate as k_ghost_flags) and GHOSTS.
 __global__ void k_key_hist(const double4* __restrict__ P0, int n, int n_owned, Grid g, const unsigned* __restrict__ mx,
                            const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
-                           unsigned* __restrict__ key, unsigned* __restrict__ rank, unsigned* __restrict__ count)
+                           unsigned* __restrict__ key, unsigned* __restrict__ rank, unsigned* __restrict__ count,
+                           int n_class, double x_edge_lo, double x_edge_hi)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
@@ -120,8 +124,13 @@ __global__ void k_key_hist(const double4* __restrict__ P0, int n, int n_owned, G
         int cx, cy, cz;
         cell_of(g, a.x, a.y, a.z, cx, cy, cz);
         k = mx[cx] | my[cy] | mz[cz];
-        if (i >= n_owned)
-            k += g.n_keys; /* ghosts sort behind the owned particles: slots [0, n_owned) stay the owned ones */
+        if (n_class == 3)
+        {
+            if (i >= n_owned)
+                k += 2u * g.n_keys; /* ghosts sort behind the owned particles: slots [0, n_owned) stay the owned ones */
+            else if (a.x < x_edge_lo || !(a.x < x_edge_hi))
+                k += g.n_keys;
+        }
         key[i] = k;
     }
     // warp-aggregated atomics: one atomicAdd per distinct key in the warp
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(TPB)
     k_build_skin(const double4* __restrict__ P0, const int* __restrict__ b, int n, int n_owned, Grid g,
                  const unsigned* __restrict__ mx, const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
                  const unsigned* __restrict__ cell_start, double sr_skin, int scap, unsigned* __restrict__ slist,
-                 int* __restrict__ scount, double4* __restrict__ xref, int* __restrict__ flag)
+                 int* __restrict__ scount, double4* __restrict__ xref, int* __restrict__ flag, int n_seg)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -208,7 +217,6 @@ __global__ void __launch_bounds__(TPB)
     xref[i] = a;
     if (i >= n_owned)
         return; /* ghosts are neighbours only */
-    const int n_seg = (n > n_owned) ? 2 : 1;
     int cx, cy, cz;
     cell_of(g, a.x, a.y, a.z, cx, cy, cz);
     uint4* __restrict__ dst = reinterpret_cast<uint4*>(slist) + (size_t(i >> 5) * size_t(scap >> 2)) * 32u + (i & 31);
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(TPB)
                     continue;
                 for (int seg = 0; seg < n_seg; ++seg)
                 {
-                const unsigned k = (kyz | mx[x]) + (seg ? g.n_keys : 0u);
+                const unsigned k = (kyz | mx[x]) + unsigned(seg) * g.n_keys;
                 const unsigned s = cell_start[k], e = cell_start[k + 1];
                 for (unsigned j = s; j < e; ++j)
                 {
@@ -473,7 +481,13 @@ static int rebuild_skin(FjsphEngine* e)
         return FJSPH_ERR_CAPACITY;
     }
     g.n_keys = 1u << (g.bx + g.by + g.bz);
-    const unsigned n_tab = (e->n > e->n_owned) ? 2u * g.n_keys : g.n_keys; /* second half: ghost cells */
+    /* slab mode: interior | edge | ghost classes, each with its own copy of the cell table */
+    const bool three = e->slab.on && e->slab.world > 1;
+    const int n_class = three ? 3 : 1;
+    const unsigned n_tab = unsigned(n_class) * g.n_keys;
+    const double wg = std::sqrt(e->P.sr) + e->skin;
+    const double x_edge_lo = (three && e->slab.rank > 0) ? e->slab.x_lo + wg : -1e300;
+    const double x_edge_hi = (three && e->slab.rank < e->slab.world - 1) ? e->slab.x_hi - wg : 1e300;
     int st = ensure_key_capacity(e, n_tab);
     if (st)
         return st;
@@ -521,7 +535,7 @@ static int rebuild_skin(FjsphEngine* e)
         KScope ks(e, "nb_sort", 7);
         FJ_CUDA(cudaMemsetAsync(e->cell_count, 0, size_t(n_tab) * sizeof(unsigned), e->stream));
         k_key_hist<<<nb, TPB, 0, e->stream>>>(S.P0, n, int(e->n_owned), g, e->mtab_x, e->mtab_y, e->mtab_z, e->key, e->rank_in_cell,
-                                              e->cell_count);
+                                              e->cell_count, n_class, x_edge_lo, x_edge_hi);
         prim_exclusive_scan(e->stream, e->cell_count, e->cell_start, n_tab, e->scan_tmp);
         k_scatter<<<nb, TPB, 0, e->stream>>>(e->key, e->rank_in_cell, e->cell_start, n, e->perm2);
         k_cell_order<<<fj_blocks(int64_t(n_tab) * 32, TPB), TPB, 0, e->stream>>>(e->cell_start, n_tab, e->perm2, e->oidx,
@@ -551,11 +565,15 @@ static int rebuild_skin(FjsphEngine* e)
             KScope ks(e, "nb_skin", 1);
             k_build_skin<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, int(e->n_owned), g, e->mtab_x, e->mtab_y, e->mtab_z,
                                                     e->cell_start, r_skin * r_skin, e->scap, e->slist, e->scount,
-                                                    e->xref, e->d_flag);
+                                                    e->xref, e->d_flag, n_class);
         }
         FJ_CUDA(cudaGetLastError());
         FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        if (three) /* first slot of the edge class = number of interior particles */
+            FJ_CUDA(cudaMemcpyAsync(e->h_flag + 1, e->cell_start + g.n_keys, sizeof(unsigned), cudaMemcpyDeviceToHost,
+                                    e->stream));
         FJ_CUDA(cudaStreamSynchronize(e->stream));
+        e->slab.n_interior = three ? int64_t(e->h_flag[1]) & ~int64_t(31) : 0;
         if (e->h_flag[0] == 0)
         {
             e->skin_valid = true;

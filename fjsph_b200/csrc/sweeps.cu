@@ -357,9 +357,9 @@ template <bool SURF, bool DISS>
 #define FJ_S1_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
-    k_surf1_diss(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
+    k_surf1_diss(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n, int i0)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; /* slots [i0, n) */
     if (i >= n || blk[i] < n_bound_blocks)
         return;
     const double4 pi = S.P0[i];
@@ -529,9 +529,9 @@ struct RecS2
 #endif
 template <bool SURF23, bool SHIFT>
 __global__ void __launch_bounds__(TPB, FJ_S23_MINBLOCKS)
-    k_surf23_shift(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n)
+    k_surf23_shift(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n, int i0)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; /* slots [i0, n) */
     if (i >= n || blk[i] < n_bound_blocks)
         return;
     const double4 pi = S.P0[i];
@@ -884,9 +884,9 @@ struct RecF
 #endif
 template <bool ALE>
 __global__ void __launch_bounds__(TPB, FJ_FORCE_MINBLOCKS)
-    k_force(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, double npdm2, int n)
+    k_force(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, double npdm2, int n, int i0)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; /* slots [i0, n) */
     if (i >= n || blk[i] < n_bound_blocks)
         return;
     const double4 pi = S.P0[i];
@@ -1196,6 +1196,46 @@ ListView list_view(FjsphEngine* e)
     return v;
 }
 
+// Launches a sweep over the owned slots [0, n).  Slab mode, with a forward exchange in flight on the comm stream:
+// the INTERIOR slots first (none of their neighbours is a ghost, so they run beside the exchange), then -- once the
+// main stream has waited for the ghosts -- the EDGE slots.  launch(i0, i1) must queue the kernel for slots [i0, i1).
+// Call with e->slab.hold set while the KScope of the sweep is constructed (SplitScope below).
+template <class F>
+int launch_split(FjsphEngine* e, int n, F&& launch)
+{
+    if (fj_halo_overlappable(e))
+    {
+        const int ni = int(e->slab.n_interior);
+        launch(0, ni);
+        int st = fj_halo_wait(e);
+        if (st)
+            return st;
+        launch(ni, n);
+        e->slab.overlapped++;
+    }
+    else
+    {
+        int st = fj_halo_wait(e);
+        if (st)
+            return st;
+        launch(0, n);
+    }
+    return FJSPH_OK;
+}
+// KScope that does not wait for the exchange in flight when the sweep is going to split
+struct SplitScope
+{
+    bool split;
+    KScope ks;
+    static bool arm(FjsphEngine* e)
+    {
+        const bool s = fj_halo_overlappable(e);
+        e->slab.hold = s;
+        return s;
+    }
+    SplitScope(FjsphEngine* e, const char* name) : split(arm(e)), ks(e, name, split ? 2 : 1) { e->slab.hold = false; }
+};
+
 int need_list(FjsphEngine* e, const char* who)
 {
     if (!e->list_valid)
@@ -1252,23 +1292,27 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
     if (st)
         return st;
     const int n = int(e->n_owned);
-    const int nb = fj_blocks(n, TPB);
     ListView lv = list_view(e);
+#define FJ_SWEEP(KERNEL) \
+    launch_split(e, n, [&](int i0, int i1) { \
+        KERNEL<<<fj_blocks(i1 - i0, TPB), TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, i1, i0); })
     if (do_surface && do_dissipation)
     {
-        KScope ks(e, "surf1+diss", 1);
-        k_surf1_diss<true, true><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+        SplitScope ks(e, "surf1+diss");
+        st = FJ_SWEEP((k_surf1_diss<true, true>));
     }
     else if (do_surface)
     {
-        KScope ks(e, "surf1", 1);
-        k_surf1_diss<true, false><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+        SplitScope ks(e, "surf1");
+        st = FJ_SWEEP((k_surf1_diss<true, false>));
     }
     else if (do_dissipation)
     {
-        KScope ks(e, "diss", 1);
-        k_surf1_diss<false, true><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+        SplitScope ks(e, "diss");
+        st = FJ_SWEEP((k_surf1_diss<false, true>));
     }
+    if (st)
+        return st;
     if (do_surface)
     {
         st = fj_halo_exchange(e, 1, FJ_HX_P4); /* loop-1 normals and surf flags of the ghosts */
@@ -1277,21 +1321,25 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
     }
     if (do_surface && fuse_shift && e->P.ale && FJ_FUSE_SHIFT)
     {
-        KScope ks(e, "surf2+3+shift", 1);
-        k_surf23_shift<true, true><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+        SplitScope ks(e, "surf2+3+shift");
+        st = FJ_SWEEP((k_surf23_shift<true, true>));
     }
     else if (do_surface)
     {
         {
-            KScope ks(e, "surf2+3", 1);
-            k_surf23_shift<true, false><<<nb, TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, n);
+            SplitScope ks(e, "surf2+3");
+            st = FJ_SWEEP((k_surf23_shift<true, false>));
         }
+        if (st)
+            return st;
         if (fuse_shift && e->P.ale)
         {
             FJ_CUDA(cudaGetLastError());
             return fj_shift(e);
         }
     }
+    if (st)
+        return st;
     FJ_CUDA(cudaGetLastError());
     return FJSPH_OK;
 }
@@ -1306,7 +1354,7 @@ int fj_shift(FjsphEngine* e)
     const int n = int(e->n_owned);
     KScope ks(e, "shift", 1);
     k_surf23_shift<false, true><<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], list_view(e), e->blk,
-                                                                          e->n_bound_blocks, e->C, n);
+                                                                          e->n_bound_blocks, e->C, n, 0);
     FJ_CUDA(cudaGetLastError());
     return FJSPH_OK;
 }
@@ -1340,13 +1388,18 @@ int fj_forces(FjsphEngine* e, int level_idx, double npd)
                         (9.0 / 4.0 * std::pow(FJ_PI, 3.0) - 6.0 * FJ_PI - 4.0));
     const double npdm2 = (0.5 * e->P.sig / lam) / (npd * npd);
     {
-        KScope ks(e, "force", 1);
-        if (e->P.ale)
-            k_force<true><<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[level_idx], list_view(e), e->blk,
-                                                                     e->n_bound_blocks, e->C, npdm2, n);
-        else
-            k_force<false><<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[level_idx], list_view(e), e->blk,
-                                                                      e->n_bound_blocks, e->C, npdm2, n);
+        SplitScope ks(e, "force");
+        ListView lv = list_view(e);
+        st = launch_split(e, n, [&](int i0, int i1) {
+            if (e->P.ale)
+                k_force<true><<<fj_blocks(i1 - i0, TPB), TPB, 0, e->stream>>>(e->lv[level_idx], lv, e->blk, e->n_bound_blocks,
+                                                                               e->C, npdm2, i1, i0);
+            else
+                k_force<false><<<fj_blocks(i1 - i0, TPB), TPB, 0, e->stream>>>(e->lv[level_idx], lv, e->blk, e->n_bound_blocks,
+                                                                                e->C, npdm2, i1, i0);
+        });
+        if (st)
+            return st;
     }
     e->force_evals++;
     FJ_CUDA(cudaGetLastError());

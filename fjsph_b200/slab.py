@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib, engine as eng
 from ._lib import check
 
-COMM_SUM, COMM_MAX, COMM_SENDRECV_DEV, COMM_SENDRECV_HOST = 0, 1, 2, 3
+COMM_SUM, COMM_MAX, COMM_SENDRECV_DEV, COMM_SENDRECV_HOST, COMM_SENDRECV_DEV_ASYNC = 0, 1, 2, 3, 4
 COMM_FN = _lib.COMM_FN
 
 
@@ -56,9 +56,15 @@ class Transport:
         self.backend = dist.get_backend(group)
         self.device = device if device is not None else (
             torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu"))
-        self.calls = {COMM_SUM: 0, COMM_MAX: 0, COMM_SENDRECV_DEV: 0, COMM_SENDRECV_HOST: 0}
+        self.calls = {COMM_SUM: 0, COMM_MAX: 0, COMM_SENDRECV_DEV: 0, COMM_SENDRECV_HOST: 0, COMM_SENDRECV_DEV_ASYNC: 0}
         self.error = None
+        self.comm_stream = None  # torch view of the engine's comm stream (set_comm_stream), for the ASYNC exchanges
         self.fn = COMM_FN(self._callback)  # keep alive as long as the engine uses it
+
+    def set_comm_stream(self, cuda_stream_ptr: int):
+        """The engine's comm stream (fjsph_slab_comm_stream): FJSPH_COMM_SENDRECV_DEV_ASYNC exchanges are ordered on it,
+        so that they run beside the interior sweeps the engine queues on its main stream."""
+        self.comm_stream = self.torch.cuda.ExternalStream(int(cuda_stream_ptr), device=self.device)
 
     # -- pieces
     def _host_array(self, ptr, nbytes, dtype):
@@ -94,10 +100,18 @@ class Transport:
             torch = self.torch
             if op in (COMM_SUM, COMM_MAX):
                 self.allreduce(a, na, op)
-            elif op == COMM_SENDRECV_DEV:
+            elif op in (COMM_SENDRECV_DEV, COMM_SENDRECV_DEV_ASYNC):
                 t = [torch.as_tensor(_DevBuf(p, n), device=self.device) if (p and n > 0) else None
                      for p, n in ((a, na), (b, nb), (c, nc), (d, nd))]
-                self.sendrecv(t)
+                if op == COMM_SENDRECV_DEV_ASYNC:
+                    if self.comm_stream is None:
+                        raise RuntimeError("ASYNC exchange requested but set_comm_stream was never called")
+                    # NCCL orders the send/recv behind the CURRENT stream and req.wait() makes that stream wait for
+                    # them: neither blocks the host, so the engine goes on queueing interior work on its main stream
+                    with torch.cuda.stream(self.comm_stream):
+                        self.sendrecv(t)
+                else:
+                    self.sendrecv(t)
             elif op == COMM_SENDRECV_HOST:
                 hosts = [self._host_array(p, n, np.uint8) if (p and n > 0) else None
                          for p, n in ((a, na), (b, nb), (c, nc), (d, nd))]
@@ -129,6 +143,10 @@ class SlabEngine(eng.Engine):
         self.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"], **extra)
         self.transport = Transport(group=group)
         check(self._L.fjsph_set_slab(self._h, rank, world, float(x_lo), float(x_hi), self.transport.fn, None))
+        if self.transport.backend == "nccl":
+            cs = C.c_void_p()
+            check(self._L.fjsph_slab_comm_stream(self._h, C.byref(cs)))
+            self.transport.set_comm_stream(cs.value)
 
     def _raise_transport_error(self):
         if self.transport.error is not None:
@@ -152,7 +170,11 @@ class SlabEngine(eng.Engine):
     def slab_stats(self) -> dict:
         v = [C.c_int64() for _ in range(5)]
         check(self._L.fjsph_slab_stats(self._h, *[C.byref(x) for x in v]))
-        return dict(zip(("n_owned", "n_ghost", "exchanges", "redecomps", "bytes_sent"), (int(x.value) for x in v)))
+        out = dict(zip(("n_owned", "n_ghost", "exchanges", "redecomps", "bytes_sent"), (int(x.value) for x in v)))
+        ov = C.c_int64()
+        check(self._L.fjsph_slab_overlapped(self._h, C.byref(ov)))
+        out["overlapped"] = int(ov.value)
+        return out
 
     def pair_count(self) -> float:
         return float(np.sum(self.neighbour_counts() - 1))

@@ -211,12 +211,20 @@ int fjsph_set_skin(FjsphEngine* e, double skin_over_dx);
  *   op FJSPH_COMM_SUM / MAX : all-reduce of the host array a (na/8 doubles) in place;
  *   op FJSPH_COMM_SENDRECV_DEV / _HOST : send a (na bytes) to rank-1 and b (nb bytes) to rank+1, receive c (nc bytes)
  *      from rank-1 and d (nd bytes) from rank+1; device or host pointers respectively; zero sizes at the domain ends.
+ *   op FJSPH_COMM_SENDRECV_DEV_ASYNC : the same on device pointers, but ordered on the engine's COMM stream
+ *      (fjsph_slab_comm_stream) instead of its main stream: the forward halo exchanges run there while the main
+ *      stream sweeps the interior particles.  The callback must not block the host on it.
  * The callback returns 0 on success.  fjsph_b200/slab.py implements it with NCCL send/recv over NVLink
  * (torch.distributed); upload the rank's own particles with fjsph_upload_state first, then call fjsph_set_slab. */
-enum { FJSPH_COMM_SUM = 0, FJSPH_COMM_MAX = 1, FJSPH_COMM_SENDRECV_DEV = 2, FJSPH_COMM_SENDRECV_HOST = 3 };
+enum { FJSPH_COMM_SUM = 0, FJSPH_COMM_MAX = 1, FJSPH_COMM_SENDRECV_DEV = 2, FJSPH_COMM_SENDRECV_HOST = 3,
+       FJSPH_COMM_SENDRECV_DEV_ASYNC = 4 };
 typedef int (*FjsphCommFn)(void* user, int32_t op, void* a, int64_t na, void* b, int64_t nb, void* c, int64_t nc,
                            void* d, int64_t nd);
 int fjsph_set_slab(FjsphEngine* e, int32_t rank, int32_t world, double x_lo, double x_hi, FjsphCommFn fn, void* user);
+/* the cudaStream_t FJSPH_COMM_SENDRECV_DEV_ASYNC exchanges must be ordered on (valid after fjsph_set_slab) */
+int fjsph_slab_comm_stream(FjsphEngine* e, void** stream);
+/* forward exchanges that ran beside an interior sweep since fjsph_set_slab */
+int fjsph_slab_overlapped(FjsphEngine* e, int64_t* n);
 /* owned / ghost particle counts, halo exchanges, re-decompositions and bytes sent since fjsph_set_slab */
 int fjsph_slab_stats(FjsphEngine* e, int64_t* n_owned, int64_t* n_ghost, int64_t* exchanges, int64_t* redecomps,
                      int64_t* bytes_sent);

@@ -56,9 +56,10 @@ def run(name, case, params, steps, rank, world, local_rank):
         want = ref.download(FIELDS)
         pid = np.concatenate([g[0]["part_id"] for g in gathered])
         assert len(pid) == n and len(np.unique(pid)) == n, "%s: particles lost or duplicated (%d of %d)" % (name, len(np.unique(pid)), n)
-        print("%s: owned per rank %s, ghosts %s, exchanges %s, redecomps %s" % (
+        print("%s: owned per rank %s, ghosts %s, exchanges %s (beside an interior sweep: %s), redecomps %s" % (
             name, [g[2]["n_owned"] for g in gathered], [g[2]["n_ghost"] for g in gathered],
-            [g[2]["exchanges"] for g in gathered], [g[2]["redecomps"] for g in gathered]))
+            [g[2]["exchanges"] for g in gathered], [g[2]["overlapped"] for g in gathered],
+            [g[2]["redecomps"] for g in gathered]))
         for r, g in enumerate(gathered):
             for a, b in zip(g[1], rits):
                 if a[0] != b[0] or abs(a[1] - b[1]) > 1e-12 * b[1] or abs(a[2] - b[2]) > 1e-10 * abs(b[2]):
