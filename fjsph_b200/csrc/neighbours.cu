@@ -24,57 +24,56 @@ namespace
 constexpr int TPB = 256;
 
 // ---------------------------------------------------------------- bounds (+ displacement since the skin build)
-// partial[b*7 + {lo.xyz, hi.xyz, max |x - xref|^2}]
+// partial[b*NRED + c]: c = 0-2 min x,y,z | 3-5 max x,y,z | 6 max |x - xref|^2 | 7-9 min (x - xref) | 10-12 max (x - xref)
+// Components 7-12 bound the RELATIVE displacement of any two particles: a uniform drift of the whole fluid (a jet)
+// moves every particle far but no pair apart, and must not trigger a rebuild of the superset list.
+constexpr int NRED = 13;
+__device__ __forceinline__ bool red_is_min(int c) { return c < 3 || (c >= 7 && c < 10); }
+__device__ __forceinline__ double red_combine(int c, double v, double u)
+{
+    /* min for the lower bounds; NaN-propagating max (u <= v ? v : u) for the rest: a NaN reads as "moved too far" */
+    return red_is_min(c) ? fmin(v, u) : ((u <= v) ? v : u);
+}
+__device__ __forceinline__ double red_identity(int c) { return red_is_min(c) ? 1e300 : (c == 6 ? 0.0 : -1e300); }
+
 __global__ void k_bounds(const double4* __restrict__ P0, const double4* __restrict__ xref, int n,
                          double* __restrict__ partial)
 {
-    double lo[3] = {1e300, 1e300, 1e300}, hi[4] = {-1e300, -1e300, -1e300, 0.0};
+    double acc[NRED];
+#pragma unroll
+    for (int c = 0; c < NRED; ++c) acc[c] = red_identity(c);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
-        double4 a = P0[i];
-        lo[0] = fmin(lo[0], a.x);
-        hi[0] = fmax(hi[0], a.x);
-        lo[1] = fmin(lo[1], a.y);
-        hi[1] = fmax(hi[1], a.y);
-        lo[2] = fmin(lo[2], a.z);
-        hi[2] = fmax(hi[2], a.z);
+        const double4 a = P0[i];
+        double v[NRED] = {a.x, a.y, a.z, a.x, a.y, a.z, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         if (xref)
         {
             const double4 r = xref[i];
             const double dx = a.x - r.x, dy = a.y - r.y, dz = a.z - r.z;
-            const double d2 = dx * dx + dy * dy + dz * dz;
-            hi[3] = (d2 <= hi[3]) ? hi[3] : d2; /* NaN propagates to "moved too far" */
+            v[6] = dx * dx + dy * dy + dz * dz;
+            v[7] = v[10] = dx;
+            v[8] = v[11] = dy;
+            v[9] = v[12] = dz;
         }
+#pragma unroll
+        for (int c = 0; c < NRED; ++c) acc[c] = red_combine(c, acc[c], v[c]);
     }
-    __shared__ double sm[7][TPB / 32];
+    __shared__ double sm[NRED][TPB / 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < NRED; ++c)
     {
-        double l = (c < 3) ? lo[c] : 0.0, h = hi[c];
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            l = fmin(l, __shfl_xor_sync(0xffffffffu, l, o));
-            const double h2 = __shfl_xor_sync(0xffffffffu, h, o);
-            h = (h2 <= h) ? h : h2;
-        }
+        double v = acc[c];
+        for (int o = 16; o > 0; o >>= 1) v = red_combine(c, v, __shfl_xor_sync(0xffffffffu, v, o));
         if (lane == 0)
-        {
-            if (c < 3)
-                sm[c][w] = l;
-            sm[3 + c][w] = h;
-        }
+            sm[c][w] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 7)
+    if (threadIdx.x < NRED)
     {
         double v = sm[threadIdx.x][0];
-        for (int k = 1; k < TPB / 32; ++k)
-        {
-            const double u = sm[threadIdx.x][k];
-            v = (threadIdx.x < 3) ? fmin(v, u) : ((u <= v) ? v : u);
-        }
-        partial[blockIdx.x * 7 + threadIdx.x] = v;
+        for (int k = 1; k < TPB / 32; ++k) v = red_combine(threadIdx.x, v, sm[threadIdx.x][k]);
+        partial[blockIdx.x * NRED + threadIdx.x] = v;
     }
 }
 
@@ -82,19 +81,11 @@ __global__ void k_bounds_final(const double* __restrict__ partial, int nblocks, 
 {
     // one warp per component, lanes stride the block partials
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (c >= 7)
+    if (c >= NRED)
         return;
-    double v = (c < 3) ? 1e300 : ((c < 6) ? -1e300 : 0.0);
-    for (int b = lane; b < nblocks; b += 32)
-    {
-        const double u = partial[b * 7 + c];
-        v = (c < 3) ? fmin(v, u) : ((u <= v) ? v : u);
-    }
-    for (int o = 16; o > 0; o >>= 1)
-    {
-        const double u = __shfl_xor_sync(0xffffffffu, v, o);
-        v = (c < 3) ? fmin(v, u) : ((u <= v) ? v : u);
-    }
+    double v = red_identity(c);
+    for (int b = lane; b < nblocks; b += 32) v = red_combine(c, v, partial[b * NRED + c]);
+    for (int o = 16; o > 0; o >>= 1) v = red_combine(c, v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0)
         out[c] = v;
 }
@@ -606,19 +597,33 @@ int fj_build_neighbours(FjsphEngine* e)
         KScope ks(e, "nb_bounds", 2);
         const int rb = std::min(nb, 1024);
         k_bounds<<<rb, TPB, 0, e->stream>>>(e->lv[1].P0, have_skin ? e->xref : nullptr, n, e->red);
-        k_bounds_final<<<1, 7 * 32, 0, e->stream>>>(e->red, rb, e->red_out);
+        k_bounds_final<<<1, NRED * 32, 0, e->stream>>>(e->red, rb, e->red_out);
     }
-    FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, NRED * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     FJ_CUDA(cudaStreamSynchronize(e->stream));
-    const double lim = 0.49 * e->skin; /* valid while nobody moved more than skin/2 (a hair below, for rounding) */
-    double moved = (have_skin && e->h_red[6] <= lim * lim) ? 0.0 : 1.0;
+    /* The superset list holds every pair closer than 2H + skin at its build, so it stays valid while no PAIR has
+       closed in by more than skin: either nobody moved more than skin/2 (a hair below, for rounding), or -- a fluid
+       drifting as a whole -- every displacement lies within skin/2 of the centre of the displacements' bounding box.
+       Ownership and ghost sets are re-made with the list, so the same test covers the slab decomposition. */
+    const double lim = 0.49 * e->skin;
+    double disp[7] = {e->h_red[6], e->h_red[10], e->h_red[11], e->h_red[12], -e->h_red[7], -e->h_red[8], -e->h_red[9]};
+    if (!have_skin)
+        disp[0] = 1e300;
     if (e->slab.on)
     {
         /* all ranks rebuild together: the ghost sets are only re-made with the superset lists */
-        int st = fj_allreduce(e, FJSPH_COMM_MAX, &moved, 1);
+        int st = fj_allreduce(e, FJSPH_COMM_MAX, disp, 7);
         if (st)
             return st;
     }
+    double half_diag2 = 0.0;
+    for (int d = 0; d < 3; ++d)
+    {
+        const double h = 0.5 * (disp[1 + d] + disp[4 + d]); /* (max - min) / 2 of component d */
+        half_diag2 += h * h;
+    }
+    const bool valid = have_skin && (disp[0] <= lim * lim || half_diag2 <= lim * lim);
+    double moved = valid ? 0.0 : 1.0;
     if (moved != 0.0)
     {
         if (e->slab.on && e->slab.world > 1)
@@ -629,7 +634,7 @@ int fj_build_neighbours(FjsphEngine* e)
             const int n2 = int(e->n);
             const int rb = std::min(fj_blocks(n2, TPB), 1024);
             k_bounds<<<rb, TPB, 0, e->stream>>>(e->lv[1].P0, nullptr, n2, e->red);
-            k_bounds_final<<<1, 7 * 32, 0, e->stream>>>(e->red, rb, e->red_out);
+            k_bounds_final<<<1, NRED * 32, 0, e->stream>>>(e->red, rb, e->red_out);
             e->launches += 2;
             FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
             FJ_CUDA(cudaStreamSynchronize(e->stream));

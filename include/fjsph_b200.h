@@ -200,8 +200,9 @@ int fjsph_set_stream(FjsphEngine* e, void* cuda_stream);
 /* Neighbour-build policy.  update_neighbours (Neighbours.cpp:7-31) rebuilds the KD-tree and searches it at every
  * call; the engine instead keeps a superset ("skin") list of every j within 2H + skin and filters the exact
  * list { j : d2 < 4H^2 } from it with the bit-exact distance test at every call, falling back to a cell-list
- * sweep when some particle has moved more than skin/2 since the superset was built.  The neighbour sets are
- * identical either way.  skin_over_dx = 0 sweeps the cell list at every call; default 0.4. */
+ * sweep when some PAIR may have closed in by more than skin since the superset was built: some particle has moved
+ * more than skin/2 AND the displacements do not all lie within skin/2 of a common drift (a jet moving as a whole
+ * displaces every particle but no pair, and keeps its superset list).  The neighbour sets are identical either way.  skin_over_dx = 0 sweeps the cell list at every call; default 0.4. */
 int fjsph_set_skin(FjsphEngine* e, double skin_over_dx);
 
 /* Slab decomposition.  The reference is one shared-memory process (OpenMP only, FJSPH.cpp:62); large

@@ -195,6 +195,32 @@ def test_full_step_parity(which, solver):
     assert pe.cfl == po.cfl and pe.n_stable == po.n_stable and pe.n_unstable == po.n_unstable
 
 
+def test_uniform_drift_keeps_the_superset_list():
+    """A block drifting at 30 m/s moves every particle by more than skin/2 per step but no pair apart: the superset
+    (skin) list must survive (no cell-list sweep after the first step), and the exact lists filtered from it must
+    still be the oracle's sets, bit for bit; the state keeps the full-step parity bars."""
+    case = cases.synthetic_block((14, 11, 9), 1e-3, jitter=0.1, seed=43)
+    case["v"] = case["v"] + np.array([30.0, 0.0, 0.0])
+    o, e, p = make_pair(case, delta_t_min=1e-9)
+    x0 = case["xi"][:, 0].mean()
+    for step in range(4):
+        err_o, so = o.integrate()
+        se = e.integrate()
+        ctx = "drift step %d" % step
+        assert se.iterations == so.iterations, ctx
+        if step > 0:
+            assert se.skin_builds == 0, (ctx, se.skin_builds)
+        off_o, idx_o, _ = o.neighbours()
+        off_e, idx_e = e.neighbours()
+        assert np.array_equal(off_o, off_e) and np.array_equal(idx_o, idx_e), ctx
+        assert_fields_close(e, o, FLAG_FIELDS, context=ctx)
+        assert_fields_close(e, o, STATE_FIELDS, tol=1e-10, context=ctx)
+        assert_fields_close(e, o, ("v", "p"), tol=1e-8, context=ctx)
+        assert_fields_close(e, o, RATE_FIELDS, tol=1e-6, context=ctx)
+    moved = e.download(("xi",))["xi"][:, 0].mean() - x0
+    assert moved > 0.5e-3, moved  # > skin/2 = 0.2 mm per step: the plain criterion would have swept every step
+
+
 @pytest.mark.parametrize("which", ["droplet", "walls"])
 def test_full_step_tie_stress(which):
     """The reference's own lattice + U(0, eps dx) inputs (square.cpp:103, circle.cpp:136): ~6 of ~257 neighbours sit
