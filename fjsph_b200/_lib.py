@@ -127,6 +127,18 @@ def lib():
     L.fjsph_slab_comm_stream.argtypes = [vp, P(vp)]
     L.fjsph_slab_overlapped.argtypes = [vp, P(C.c_int64)]
     L.fjsph_slab_stats.argtypes = [vp, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)]
+    L.fjsph_case_read.argtypes = [C.c_char_p, C.c_int, P(vp)]
+    L.fjsph_case_free.argtypes = [vp]
+    L.fjsph_case_free.restype = None
+    for f in ("fjsph_case_count", "fjsph_case_bound_points"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = C.c_int64
+    for f in ("fjsph_case_num_blocks", "fjsph_case_dim"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = C.c_int32
+    L.fjsph_case_params.argtypes = [vp, P(FjsphParams)]
+    L.fjsph_case_block.argtypes = [vp, C.c_int32, P(FjsphBlock), C.c_char_p, C.c_int32]
+    L.fjsph_case_state.argtypes = [vp, P(FjsphStateView)]
     _lib = L
     return L
 

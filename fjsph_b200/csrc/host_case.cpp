@@ -1,0 +1,1748 @@
+// host_case.cpp — host-side case front end: block files (bmap) -> shape blocks -> particles in FJSPH's order.
+//
+// Restates, for 2D and 3D builds selected at run time (the reference selects with -DSIMDIM):
+//   read_shapes_bmap                     reference src/shapes/shapes.cpp:408-625
+//   ShapeBlock::check_input / _post      reference src/shapes/shapes.cpp:21-166
+//   Line/Plane, Square/Cube, Circle/Sphere, Cylinder (Hollow | Solid), Inlet (Square | Circle), Coordinates
+//                                        reference src/shapes/{line,square,circle,cylinder,inlet,coordinates}.cpp
+//   GetRotationMat                       reference src/Geometry.h:14-42
+//   Generate_Points, Check_Intersection, Init_Particles, get_boundary_velocity
+//                                        reference src/Init.cpp:26-38,61-268,270-496
+// The perturbation stream is the reference's: std::default_random_engine (default seed) through
+// std::uniform_real_distribution<double>(0, eps*dx), drawn in the reference's order, one engine per block.
+// Reference behaviour kept on purpose: the solid cylinder's inner loop never runs (`kk > nk`, cylinder.cpp:378,490),
+// local `rotmat` variables shadow the member so only "Rotation angles" rotates a block (cylinder.cpp:196-241,
+// inlet.cpp:141-213), the hydrostatic initialisation always measures height along y (Init.cpp:480-493).
+// Not restated: Arc/Arch blocks (rejected with an error), JSON block files (nlohmann/json is not vendored).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <memory>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/fjsph_b200.h"
+
+void fj_set_error(const char* fmt, ...);
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+#ifndef M_PI_4
+#define M_PI_4 0.78539816339744830962
+#endif
+
+namespace
+{
+constexpr double DEFV = 9999999.0; /* default_val, VarDefs.h:195 */
+constexpr double MEPS = std::numeric_limits<double>::epsilon();
+const char* WS = " \n\r\t\f\v";
+
+enum ShapeType /* shape_type, VarDefs.h:116-127 */
+{
+    linePlane = 0,
+    squareCube,
+    circleSphere,
+    cylinderT,
+    arcSection,
+    coordDef,
+    inletZone,
+    hollowT,
+    solidT
+};
+
+struct V3
+{
+    double c[3];
+    V3() : c{0.0, 0.0, 0.0} {}
+    V3(double a, double b, double d) : c{a, b, d} {}
+    double& operator[](int i) { return c[i]; }
+    double operator[](int i) const { return c[i]; }
+};
+V3 constant(double v, int dim) { return dim == 3 ? V3(v, v, v) : V3(v, v, 0.0); }
+V3 operator+(const V3& a, const V3& b) { return V3(a[0] + b[0], a[1] + b[1], a[2] + b[2]); }
+V3 operator-(const V3& a, const V3& b) { return V3(a[0] - b[0], a[1] - b[1], a[2] - b[2]); }
+V3 operator*(const V3& a, double s) { return V3(a[0] * s, a[1] * s, a[2] * s); }
+V3 operator*(double s, const V3& a) { return a * s; }
+V3 operator/(const V3& a, double s) { return V3(a[0] / s, a[1] / s, a[2] / s); }
+double dot(const V3& a, const V3& b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+double norm(const V3& a) { return std::sqrt(dot(a, a)); }
+V3 normalized(const V3& a) /* Eigen: the zero vector stays zero */
+{
+    const double n2 = dot(a, a);
+    return n2 > 0.0 ? a / std::sqrt(n2) : a;
+}
+V3 cross(const V3& a, const V3& b) { return V3(a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]); }
+bool same(const V3& a, const V3& b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
+/* the perturbation vector; a function call so that the draws happen in the order the compiler gives the
+   reference's StateVecD(unif(re), unif(re), unif(re)) constructor call */
+V3 make3(double a, double b, double d) { return V3(a, b, d); }
+V3 make2(double a, double b) { return V3(a, b, 0.0); }
+
+struct M3
+{
+    double m[3][3];
+    M3() { set_identity(); }
+    void set_identity()
+    {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) m[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    bool is_identity() const
+    {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                if (m[i][j] != ((i == j) ? 1.0 : 0.0))
+                    return false;
+        return true;
+    }
+};
+V3 operator*(const M3& A, const V3& v)
+{
+    return V3(A.m[0][0] * v[0] + A.m[0][1] * v[1] + A.m[0][2] * v[2], A.m[1][0] * v[0] + A.m[1][1] * v[1] + A.m[1][2] * v[2],
+              A.m[2][0] * v[0] + A.m[2][1] * v[1] + A.m[2][2] * v[2]);
+}
+
+// GetRotationMat (Geometry.h:14-42): 3D = AngleAxis(a0, X) * AngleAxis(-a1, Y) * AngleAxis(a2, Z), which Eigen
+// evaluates as a quaternion product turned into a matrix (Quaternion::toRotationMatrix); 2D = [[c,-s],[s,c]].
+struct Quat
+{
+    double w, x, y, z;
+};
+Quat axis_quat(double angle, int axis)
+{
+    Quat q{std::cos(0.5 * angle), 0.0, 0.0, 0.0};
+    const double s = std::sin(0.5 * angle);
+    (axis == 0 ? q.x : axis == 1 ? q.y : q.z) = s;
+    return q;
+}
+Quat qmul(const Quat& a, const Quat& b)
+{
+    return Quat{a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+                a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+}
+M3 rotation_matrix(const V3& angles, int dim)
+{
+    M3 R;
+    if (dim == 3)
+    {
+        const Quat q = qmul(qmul(axis_quat(angles[0], 0), axis_quat(-angles[1], 1)), axis_quat(angles[2], 2));
+        const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+        const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+        const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+        R.m[0][0] = 1 - (tyy + tzz);
+        R.m[0][1] = txy - twz;
+        R.m[0][2] = txz + twy;
+        R.m[1][0] = txy + twz;
+        R.m[1][1] = 1 - (txx + tzz);
+        R.m[1][2] = tyz - twx;
+        R.m[2][0] = txz - twy;
+        R.m[2][1] = tyz + twx;
+        R.m[2][2] = 1 - (txx + tyy);
+    }
+    else
+    {
+        R.m[0][0] = std::cos(angles[0]);
+        R.m[0][1] = -std::sin(angles[0]);
+        R.m[1][0] = std::sin(angles[0]);
+        R.m[1][1] = std::cos(angles[0]);
+    }
+    return R;
+}
+
+struct Block /* ShapeBlock, shapes.h:10-116 */
+{
+    int dim = 3;
+    bool write_data = false, no_slip = false, particle_order = false;
+    std::string name, shape, subshape, filename, position_filename, solver_name;
+    int bound_type = -1, sub_bound_type = -1, fixed_vel_or_dynamic = 0, bound_solver = FJSPH_PRESSURE_G;
+    int ni = 0, nj = 0, nk = 0;
+    size_t npts = 0, ntimes = 0;
+    double insconst = DEFV, delconst = DEFV, aeroconst = DEFV;
+    double dx = -1, radius = -1, arc_start = -1, arc_end = -1, arclength = DEFV, thickness = -1, length = -1, sstraight = 0,
+           estraight = 0;
+    double vmag = 0, press = 0, dens = 1000, nu = -1, rho_rest = 1000, gamma = 7, speedOfSound = -1, backgroundP = 0,
+           renorm_vol = -1;
+    V3 stretch, insert_norm{1, 0, 0}, delete_norm{1, 0, 0}, aero_norm{1, 0, 0}, normal{1, 0, 0}, angles;
+    M3 rotmat;
+    V3 start, end, right, mid, centre, vel;
+    std::vector<size_t> back;
+    std::vector<std::vector<size_t>> buffer;
+    std::vector<unsigned> bc;
+    std::vector<int> intersect;
+    std::vector<double> times;
+    std::vector<V3> pos, vels, coords;
+
+    explicit Block(int d) : dim(d)
+    {
+        stretch = constant(1.0, d);
+        start = end = right = mid = centre = constant(DEFV, d);
+    }
+    bool defined(const V3& v) const /* check_vector, Var.h:38-46 */
+    {
+        return v[0] != DEFV && v[1] != DEFV && (dim == 2 || v[2] != DEFV);
+    }
+};
+
+struct Ctx /* what the shapes read from SIM */
+{
+    int dim;
+    double scale, rho_rest, speed_sound, gam, press_pipe, nu;
+};
+
+std::string ltrim(const std::string& s)
+{
+    const size_t a = s.find_first_not_of(WS);
+    return a == std::string::npos ? "" : s.substr(a);
+}
+std::string rtrim(const std::string& s)
+{
+    const size_t b = s.find_last_not_of(WS);
+    return b == std::string::npos ? "" : s.substr(0, b + 1);
+}
+// Get_String & co (IOFunctions.h:32-131): the key is the left-trimmed text before the FIRST ':', compared exactly
+bool key_value(const std::string& line, const char* key, std::string& value)
+{
+    const size_t pos = line.find(':');
+    if (pos == std::string::npos || ltrim(line.substr(0, pos)) != key)
+        return false;
+    value = ltrim(rtrim(line.substr(pos + 1)));
+    return true;
+}
+void get_string(const std::string& line, const char* key, std::string& out)
+{
+    std::string v;
+    if (key_value(line, key, v))
+        out = v;
+}
+template <class T>
+void get_number(const std::string& line, const char* key, T& out)
+{
+    std::string v;
+    if (key_value(line, key, v))
+    {
+        std::istringstream iss(v);
+        T t;
+        if (iss >> t)
+            out = t;
+    }
+}
+void get_vector(const std::string& line, const char* key, V3& out, int dim)
+{
+    std::string v;
+    if (!key_value(line, key, v))
+        return;
+    std::istringstream iss(v);
+    std::string item;
+    V3 r = out; /* a component that fails to parse keeps its old value (the reference leaves it uninitialised) */
+    for (int d = 0; d < dim; ++d)
+    {
+        if (!std::getline(iss, item, ','))
+            break;
+        std::istringstream is2(item);
+        double t;
+        if (is2 >> t)
+            r[d] = t;
+    }
+    out = r;
+}
+
+int shape_type_of(const std::string& shape, int dim)
+{
+    if (shape == (dim == 2 ? "Line" : "Plane"))
+        return linePlane;
+    if (shape == (dim == 2 ? "Square" : "Cube"))
+        return squareCube;
+    if (shape == (dim == 2 ? "Circle" : "Sphere"))
+        return circleSphere;
+    if (shape == (dim == 2 ? "Arc" : "Arch"))
+        return arcSection;
+    if (shape == "Cylinder")
+        return cylinderT;
+    if (shape == "Inlet")
+        return inletZone;
+    if (shape == "Coordinates")
+        return coordDef;
+    return -1;
+}
+
+// ---------------------------------------------------------------- common checks (shapes.cpp:21-166)
+bool common_check(Block& b, const Ctx& C, std::string& err)
+{
+    if (C.scale != 1.0)
+    {
+        for (V3* v : {&b.start, &b.end, &b.right, &b.mid, &b.centre})
+            if (b.defined(*v))
+                *v = *v * C.scale;
+        for (double* s : {&b.aeroconst, &b.insconst, &b.delconst})
+            if (*s != DEFV)
+                *s *= C.scale;
+    }
+    if (!b.position_filename.empty() && b.ntimes != 0)
+    {
+        if (b.times.empty())
+            err += "Block \"" + b.name + "\" has no time information. ";
+        if (b.pos.empty() && b.vels.empty())
+            err += "Block \"" + b.name + "\" position or velocity data has not been ingested properly. ";
+    }
+    if (b.bound_type == -1)
+        err += "Block \"" + b.name + "\" shape has not been correctly defined. ";
+    if (!b.solver_name.empty())
+    {
+        if (b.solver_name == "DBC")
+            b.bound_solver = FJSPH_DBC;
+        else if (b.solver_name == "Pressure-Gradient")
+            b.bound_solver = FJSPH_PRESSURE_G;
+        else if (b.solver_name == "Ghost")
+            b.bound_solver = FJSPH_GHOST;
+        /* anything else: the reference warns and keeps Pressure-Gradient */
+    }
+    if (b.press != 0)
+    {
+        const double Bc = C.rho_rest * (C.speed_sound * C.speed_sound) / C.gam;
+        b.dens = std::pow(((b.press - C.press_pipe) / Bc + 1.0), C.gam) * C.rho_rest; /* sic: exponent gam, shapes.cpp:151-156 */
+    }
+    else
+        b.dens = C.rho_rest;
+    if (b.nu < 0)
+        b.nu = C.nu;
+    return err.empty();
+}
+void post_check(Block& b, double& gs)
+{
+    gs = std::max(b.dx, gs);
+    b.npts = b.npts > 1 ? b.npts : 1;
+}
+int ceil_i(double v) { return static_cast<int>(std::ceil(v)); }
+
+// rotation set-up shared by Cylinder and Inlet: only "Rotation angles" reaches the member matrix
+void rotation_from_angles(Block& b, bool is_inlet)
+{
+    if (norm(b.angles) != 0)
+    {
+        b.angles = b.angles * (M_PI / 180.0);
+        b.rotmat = rotation_matrix(b.angles, b.dim);
+        b.normal = b.rotmat * V3(1, 0, 0);
+        if (is_inlet)
+            b.insert_norm = b.normal;
+    }
+    else if (!same(b.normal, V3(1, 0, 0)))
+    {
+        b.normal = normalized(b.normal); /* the matrix built here is a shadowing local in the reference */
+        if (b.dim == 2)
+            b.angles[0] = std::atan2(b.normal[1], b.normal[0]);
+        if (is_inlet)
+            b.insert_norm = b.normal;
+    }
+    else if (is_inlet && !same(b.insert_norm, V3(1, 0, 0)))
+    {
+        b.normal = normalized(b.insert_norm);
+        if (b.dim == 2)
+            b.angles[0] = std::atan2(b.normal[1], b.normal[0]) - M_PI / 2.0;
+    }
+}
+
+// ---------------------------------------------------------------- Line / Plane (line.cpp)
+void line_check(Block& b, const Ctx& C, double& gs, std::string& err)
+{
+    common_check(b, C, err);
+    if (!b.defined(b.start))
+        err += "Block \"" + b.name + "\" starting position has not been correctly defined. ";
+    if (!b.defined(b.end))
+        err += "Block \"" + b.name + "\" ending position has not been correctly defined. ";
+    if (b.dim == 3 && !b.defined(b.right))
+        err += "Block \"" + b.name + "\" right position has not been correctly defined. ";
+    if (!err.empty())
+        return;
+    if (b.dx < 0 && (b.ni < 0 || (b.dim == 3 && b.nj < 0)))
+        b.dx = gs;
+    if (b.dim == 2)
+    {
+        if (b.ni > 0 && b.dx < 0)
+            b.dx = norm(b.end - b.start) / double(b.ni);
+    }
+    else if (b.ni > 0 && b.nj > 0)
+        b.dx = std::min(norm(b.right - b.start) / double(b.ni), norm(b.end - b.right) / double(b.nj));
+    if (b.thickness < 0)
+    {
+        if (b.nk < 0)
+            err += "Block \"" + b.name + "\" line thickness has not been correctly defined. ";
+    }
+    else if (b.nk < 0)
+        b.nk = b.particle_order ? ceil_i(b.thickness / b.dx / std::sqrt(3.0) * 2.0) : ceil_i(b.thickness / b.dx);
+    b.nk = b.nk > 1 ? b.nk : 1;
+    if (b.ni > 0)
+    {
+        if (b.dim == 2)
+            b.npts = size_t(b.ni) * b.nk;
+        else
+        {
+            if (b.nj < 1)
+            {
+                b.nj = ceil_i(norm(b.end - b.right) / gs);
+                b.nj = b.nj > 1 ? b.nj : 1;
+            }
+            b.npts = size_t(b.ni) * b.nj * b.nk;
+        }
+    }
+    else if (b.dim == 2)
+    {
+        b.ni = ceil_i(norm(b.end - b.start) / gs);
+        b.ni = b.ni > 1 ? b.ni : 1;
+        b.npts = size_t(b.ni) * b.nk;
+    }
+    else
+    {
+        b.ni = ceil_i(norm(b.right - b.start) / gs);
+        b.nj = b.particle_order ? ceil_i(norm(b.end - b.right) / gs / std::sqrt(3.0) * 2.0) : ceil_i(norm(b.end - b.right) / gs);
+        b.ni = b.ni > 1 ? b.ni : 1;
+        b.nj = b.nj > 1 ? b.nj : 1;
+        b.npts = size_t(b.ni) * b.nj * b.nk;
+    }
+    post_check(b, gs);
+}
+void line_generate(Block& b, double gs)
+{
+    std::uniform_real_distribution<double> unif(0.0, MEPS * gs);
+    std::default_random_engine re;
+    std::vector<V3>& pts = b.coords;
+    if (b.dim == 2)
+    {
+        const V3 delta = normalized(b.end - b.start) * gs;
+        const V3 nrm(delta[1], -delta[0], 0.0);
+        for (int ii = 0; ii < b.ni; ++ii)
+            for (int jj = 0; jj < b.nk; ++jj)
+            {
+                V3 p = b.particle_order ? delta * double(ii + 0.5 * (jj % 2)) + 0.5 * nrm * std::sqrt(3.0) * double(jj)
+                                        : delta * double(ii) + nrm * double(jj);
+                p = p + constant(unif(re), 2);
+                pts.push_back(p + b.start);
+            }
+        return;
+    }
+    const V3 di = normalized(b.right - b.start) * gs;
+    const V3 dj = normalized(b.end - b.right) * gs;
+    const V3 nrm = normalized(cross(dj, di)) * gs;
+    for (int jj = 0; jj < b.nj; ++jj)
+        for (int ii = 0; ii < b.ni; ++ii)
+            for (int kk = 0; kk < b.nk; ++kk)
+            {
+                V3 p = b.particle_order ? 0.5 * (di * double(2 * ii + ((jj + kk) % 2)) +
+                                                 dj * (std::sqrt(3.0) * (double(jj) + double(kk % 2) / 3)) +
+                                                 nrm * 2 * std::sqrt(6.0) / 3.0 * double(kk))
+                                        : di * double(ii) + dj * double(jj) + nrm * double(kk);
+                p = p + constant(unif(re), 3);
+                pts.push_back(p + b.start);
+            }
+}
+
+// ---------------------------------------------------------------- Square / Cube (square.cpp)
+void lattice_counts(const Block& b, double gs, int& ni, int& nj, int& nk)
+{
+    if (b.particle_order)
+    {
+        ni = ceil_i((b.end[0] - b.start[0]) / gs);
+        nj = ceil_i((b.end[1] - b.start[1]) / gs / std::sqrt(3.0) * 2.0);
+        nk = b.dim == 3 ? ceil_i((b.end[2] - b.start[2]) / gs / std::sqrt(6.0) * 3.0) : 1;
+    }
+    else
+    {
+        ni = ceil_i((b.end[0] - b.start[0]) / gs);
+        nj = ceil_i((b.end[1] - b.start[1]) / gs);
+        nk = b.dim == 3 ? ceil_i((b.end[2] - b.start[2]) / gs) : 1;
+    }
+    ni = ni > 1 ? ni : 1;
+    nj = nj > 1 ? nj : 1;
+    nk = nk > 1 ? nk : 1;
+}
+V3 lattice_point(const Block& b, int i, int j, int k)
+{
+    if (b.dim == 2)
+        return b.particle_order ? 0.5 * V3(double(2 * i + (j % 2)), std::sqrt(3.0) * double(j), 0.0) : V3(double(i), double(j), 0.0);
+    return b.particle_order ? 0.5 * V3(double(2 * i + ((j + k) % 2)), std::sqrt(3.0) * (double(j) + double(k % 2) / 3.0),
+                                       2.0 / 3.0 * std::sqrt(6.0) * double(k))
+                            : V3(double(i), double(j), double(k));
+}
+void square_check(Block& b, const Ctx& C, double& gs, std::string& err)
+{
+    common_check(b, C, err);
+    if (!b.defined(b.start))
+        err += "Block \"" + b.name + "\" starting position has not been correctly defined. ";
+    if (!b.defined(b.end))
+        err += "Block \"" + b.name + "\" ending position has not been correctly defined. ";
+    if (!err.empty())
+        return;
+    if (b.dx < 0 && (b.ni < 0 || b.nj < 0))
+        b.dx = gs;
+    if (b.ni > 0 && b.nj > 0 && (b.dim == 2 || b.nk > 0) && b.dx < 0)
+    {
+        const V3 dist = b.end - b.start;
+        const double di = dist[0] / double(b.ni), dj = dist[1] / double(b.nj);
+        b.dx = b.dim == 2 ? std::min(di, dj) : std::min(di, std::min(dj, dist[1] / double(b.nk))); /* sic: dist[1], square.cpp:54 */
+    }
+    lattice_counts(b, gs, b.ni, b.nj, b.nk);
+    b.npts = size_t(b.ni) * b.nj * (b.dim == 3 ? b.nk : 1);
+    post_check(b, gs);
+}
+void square_generate(Block& b, double gs)
+{
+    std::uniform_real_distribution<double> unif(0.0, MEPS * gs);
+    std::default_random_engine re;
+    const int nk = b.dim == 3 ? b.nk : 1;
+    for (int k = 0; k < nk; ++k)
+        for (int j = 0; j < b.nj; ++j)
+            for (int i = 0; i < b.ni; ++i)
+            {
+                V3 p = lattice_point(b, i, j, k) * gs;
+                p = p + constant(unif(re), b.dim);
+                b.coords.push_back(p + b.start);
+            }
+}
+
+// ---------------------------------------------------------------- Circle / Sphere (circle.cpp)
+void circle_check(Block& b, const Ctx& C, double& gs, std::string& err)
+{
+    common_check(b, C, err);
+    if (!b.defined(b.centre))
+        err += "Block \"" + b.name + "\" centre position has not been correctly defined. ";
+    if (b.radius < 0)
+        err += "Block \"" + b.name + "\" radius has not been correctly defined. ";
+    if (!err.empty())
+        return;
+    b.start = b.centre - constant(b.radius, b.dim);
+    b.end = b.centre + constant(b.radius, b.dim);
+    if (b.dx < 0)
+        b.dx = (b.ni < 0) ? gs : (2.0 * b.radius) / double(b.ni);
+    int ni, nj, nk;
+    lattice_counts(b, gs, ni, nj, nk); /* local counts: the member ni, nj, nk are left alone (circle.cpp:46-81) */
+    long np = long(ni) * nj * (b.dim == 3 ? nk : 1);
+    np = np > 1 ? np : 1;
+    b.npts = size_t(std::ceil(double(np) * (b.dim == 2 ? M_PI / 4.0 : M_PI / 6.0)));
+    post_check(b, gs);
+}
+void ring_points(std::vector<V3>& pts, std::default_random_engine& re, std::uniform_real_distribution<double>& unif, double gs,
+                 double radius, double x_layer, const M3& rot, const V3& centre, int dim)
+{
+    /* concentric rings (circle.cpp:98-129 in 2D, inlet.cpp create_radial_disk in 3D) */
+    for (double rad = radius; rad > 0.99 * gs; rad -= gs)
+    {
+        double dtheta = std::atan(gs / rad);
+        const int ncirc = int(std::floor(std::fabs(2.0 * M_PI / dtheta)));
+        dtheta = 2.0 * M_PI / double(ncirc);
+        for (double theta = 0.0; theta < 2 * M_PI - 0.5 * dtheta; theta += dtheta)
+        {
+            V3 p = dim == 2 ? V3(rad * std::sin(theta), rad * std::cos(theta), 0.0)
+                            : V3(x_layer, rad * std::sin(theta), rad * std::cos(theta));
+            p = p + (dim == 2 ? make2(unif(re), unif(re)) : make3(unif(re), unif(re), unif(re)));
+            pts.push_back(rot * p + centre);
+        }
+    }
+    V3 p = dim == 2 ? V3() : V3(x_layer, 0.0, 0.0);
+    p = p + (dim == 2 ? make2(unif(re), unif(re)) : make3(unif(re), unif(re), unif(re)));
+    pts.push_back(rot * p + centre);
+}
+void circle_generate(Block& b, double gs)
+{
+    std::uniform_real_distribution<double> unif(0.0, MEPS * gs);
+    std::default_random_engine re;
+    if (b.dim == 2)
+    {
+        ring_points(b.coords, re, unif, gs, b.radius, 0.0, b.rotmat, b.centre, 2);
+        return;
+    }
+    const double rsq = b.radius * b.radius;
+    int ni, nj, nk;
+    lattice_counts(b, gs, ni, nj, nk);
+    for (int k = 0; k < nk; ++k)
+        for (int j = 0; j < nj; ++j)
+            for (int i = 0; i < ni; ++i)
+            {
+                V3 p = b.rotmat * (lattice_point(b, i, j, k) * gs);
+                p = p + make3(unif(re), unif(re), unif(re));
+                p = p + b.start;
+                const V3 d = p - b.centre;
+                if (dot(d, d) > rsq)
+                    continue;
+                b.coords.push_back(p);
+            }
+}
+
+// ---------------------------------------------------------------- Cylinder (cylinder.cpp)
+void cylinder_check(Block& b, const Ctx& C, double& gs, std::string& err)
+{
+    common_check(b, C, err);
+    const bool d3 = b.dim == 3;
+    int has_config = 0;
+    auto centre_radius_frame = [&]() {
+        b.start = b.centre;
+        b.start[1] -= b.radius;
+        b.end = b.centre;
+        b.end[1] += b.radius;
+        if (d3)
+        {
+            b.start[2] -= b.radius;
+            b.end[2] += b.radius;
+            b.right = b.centre;
+            b.right[1] += b.radius;
+            b.right[2] -= b.radius;
+        }
+    };
+    auto centre_right_end_frame = [&]() {
+        const V3 v = b.right - b.centre, u = b.end - b.right;
+        b.start = b.centre - v - u;
+        b.right = b.start + 2.0 * v;
+        b.end = b.right + 2.0 * u;
+        b.radius = norm(v);
+    };
+    if (b.subshape == "Hollow")
+    {
+        b.sub_bound_type = hollowT;
+        if (b.thickness < 0 && b.nk < 0)
+            err += "Cylinder block \"" + b.name + "\" thickness or wall count has not been defined. ";
+        if (b.length < 0 && b.nj < 0)
+            err += "Cylinder block \"" + b.name + "\" length or j-count has not been defined. ";
+        if (b.defined(b.centre))
+        {
+            if (b.radius > 0)
+            {
+                has_config = 3;
+                centre_radius_frame();
+            }
+            else if (d3 && b.defined(b.right) && b.defined(b.end))
+            {
+                has_config = 4;
+                centre_right_end_frame();
+            }
+        }
+        else if (b.defined(b.start) && b.defined(b.end) && (!d3 || b.defined(b.right)))
+        {
+            has_config = 1;
+            b.centre = 0.5 * (b.start + b.end);
+            const V3 v = b.right - b.start;
+            b.radius = 0.5 * norm(v);
+            b.right = b.centre + 0.5 * v;
+        }
+    }
+    else if (b.subshape == "Solid")
+    {
+        b.sub_bound_type = solidT;
+        if (b.length < 0 || b.nk < 0)
+            err += "Cylinder block \"" + b.name + "\" length or k-count has not been defined. ";
+        if (b.defined(b.start) && b.defined(b.right) && b.defined(b.end))
+        {
+            has_config = 1;
+            b.centre = 0.5 * (b.start + b.end);
+            b.radius = 0.5 * norm(b.right - b.start);
+        }
+        else if (b.defined(b.centre))
+        {
+            if (b.radius > 0)
+            {
+                has_config = 3;
+                centre_radius_frame();
+            }
+            if (b.defined(b.right) && b.defined(b.end))
+            {
+                has_config = 4;
+                centre_right_end_frame();
+            }
+        }
+        else if (b.defined(b.start) && b.ni > 0 && b.nj > 0)
+            has_config = 2;
+    }
+    else
+        err += "Cylinder block \"" + b.name + "\" subtype not defined appropriately: choose Hollow or Solid. ";
+    if (has_config == 0)
+        err += "Cylinder block \"" + b.name + "\" geometry has not been sufficiently defined. ";
+    if (!err.empty())
+        return;
+    rotation_from_angles(b, false);
+    if (has_config == 1)
+    {
+        const V3 ab = normalized(b.end - b.start);
+        if (d3)
+            b.normal = normalized(cross(ab, normalized(b.right - b.start)));
+        else
+        {
+            b.angles[0] = std::atan2(ab[1], ab[0]);
+            /* normal = R * (1,0) with the local R = [[c, s], [-s, c]] */
+            b.normal = V3(std::cos(b.angles[0]), -std::sin(b.angles[0]), 0.0);
+        }
+    }
+    if (has_config == 2)
+    {
+        b.centre = b.start;
+        b.radius = 0.5 * gs * b.ni;
+        b.centre[1] += b.radius;
+        if (d3)
+        {
+            b.right = b.start;
+            b.right[1] += gs * b.ni;
+            b.end = b.right;
+            b.end[2] += gs * b.nj;
+            b.centre[2] += b.radius;
+        }
+        else
+        {
+            b.end = b.start;
+            b.end[1] += gs * b.ni;
+        }
+        if (!b.rotmat.is_identity())
+        {
+            b.centre = b.rotmat * (b.centre - b.start) + b.start;
+            b.end = b.rotmat * (b.end - b.start) + b.start;
+            if (d3)
+                b.right = b.rotmat * (b.right - b.start) + b.start;
+        }
+    }
+    else if ((has_config == 3 || has_config == 4) && !b.rotmat.is_identity())
+    {
+        b.start = b.rotmat * (b.start - b.centre) + b.centre;
+        b.end = b.rotmat * (b.end - b.centre) + b.centre;
+        if (d3)
+            b.right = b.rotmat * (b.right - b.centre) + b.centre;
+    }
+    b.dx = gs;
+    if (b.sub_bound_type == hollowT)
+    {
+        if (b.thickness < 0)
+            b.thickness = b.particle_order ? double(b.nk) * gs * std::sqrt(3.0) * 2.0 : double(b.nk) * gs;
+        else if (b.nk < 0)
+        {
+            b.nk = b.particle_order ? ceil_i(b.thickness / (gs * std::sqrt(3.0) * 2.0)) : ceil_i(b.thickness / gs);
+            b.nk = b.nk > 1 ? b.nk : 1;
+        }
+        if (d3)
+        {
+            const double dtheta = gs / b.radius;
+            b.ni = ceil_i((2 * M_PI) / dtheta);
+            b.ni = b.ni > 1 ? b.ni : 1;
+        }
+        b.nj = int(std::ceil(b.length / gs) + 1);
+        b.nj = b.nj > 1 ? b.nj : 1;
+        b.npts = size_t(b.nj) * b.nk * (d3 ? b.ni : 2);
+    }
+    else
+    {
+        b.ni = int(std::ceil(2.0 * b.radius / gs));
+        b.nj = int(std::ceil(b.length / gs));
+        if (d3)
+            b.nk = int(std::ceil(2.0 * b.radius / gs));
+        b.ni = b.ni > 1 ? b.ni : 1;
+        b.nj = b.nj > 1 ? b.nj : 1;
+        b.nk = b.nk > 1 ? b.nk : 1;
+        b.npts = d3 ? size_t(b.nj * b.nk * M_PI_4 * b.ni) * b.ni : size_t(b.ni) * b.nj;
+    }
+    post_check(b, gs);
+}
+void cylinder_generate(Block& b, double gs)
+{
+    std::uniform_real_distribution<double> unif(0.0, MEPS * gs);
+    std::default_random_engine re;
+    if (b.sub_bound_type != hollowT)
+        return; /* Solid: the reference's loops `for (ii = 0; ii > ni; ++ii)` / `for (kk = 0; kk > nk; ++kk)` never run */
+    if (b.dim == 2)
+    {
+        const V3 nrm = normalized(b.normal);
+        const V3 left(nrm[1], -nrm[0], 0.0);
+        const double r = b.radius;
+        for (int side = 0; side < 2; ++side)
+        {
+            const double sg = side == 0 ? 1.0 : -1.0;
+            for (int ii = 0; ii < b.nj; ii++)
+                for (int kk = 0; kk < b.nk; kk++)
+                {
+                    V3 p = b.particle_order ? gs * (nrm * double(-ii + 0.5 * (kk % 2)) + sg * 0.5 * left * std::sqrt(3.0) * double(kk)) +
+                                                  sg * r * left
+                                            : gs * (nrm * double(-ii) + sg * left * double(kk)) + sg * r * left;
+                    p = p + make2(unif(re), unif(re));
+                    b.coords.push_back(p + b.centre);
+                }
+        }
+        return;
+    }
+    const double dtheta = 2 * M_PI / double(b.ni);
+    for (int jj = 0; jj < b.nj; jj++)
+        for (int kk = 0; kk < b.nk; kk++)
+        {
+            double r = b.radius, l = double(jj) * gs, doffset = 0;
+            if (b.particle_order)
+            {
+                r += 1.0 / 3.0 * std::sqrt(6.0) * double(kk) * gs;
+                l = 0.5 * std::sqrt(3) * (double(jj) + double(kk % 2) / 3.0) * gs;
+                doffset = 0.5 * dtheta * ((kk + jj) % 2);
+            }
+            else
+                r += double(kk) * gs;
+            for (int ii = 0; ii < b.ni; ii++)
+            {
+                double theta = double(ii) * dtheta;
+                if (b.particle_order)
+                    theta += doffset;
+                V3 p(-l, std::cos(theta) * r, std::sin(theta) * r);
+                p = p + make3(unif(re), unif(re), unif(re));
+                b.coords.push_back(b.rotmat * p + b.centre);
+            }
+        }
+}
+
+// ---------------------------------------------------------------- Inlet (inlet.cpp:7-305, 307-575)
+void inlet_check(Block& b, const Ctx& C, double& gs, std::string& err)
+{
+    common_check(b, C, err);
+    const bool d3 = b.dim == 3;
+    int has_config = 0;
+    if (d3)
+    {
+        if (b.subshape == "Square")
+        {
+            b.sub_bound_type = squareCube;
+            if (b.defined(b.start) && b.defined(b.right) && b.defined(b.end))
+                has_config = 1;
+            if (b.defined(b.start) && b.ni > 0 && b.nj > 0)
+                has_config = 2;
+        }
+        else if (b.subshape == "Circle")
+        {
+            b.sub_bound_type = circleSphere;
+            if (b.defined(b.centre))
+            {
+                if (b.defined(b.right) && b.defined(b.end))
+                {
+                    has_config = 4;
+                    const V3 v = b.right - b.centre, u = b.end - b.right;
+                    b.start = b.centre - v - u;
+                    b.right = b.start + 2.0 * v;
+                    b.end = b.right + 2.0 * u;
+                }
+                if (b.radius > 0)
+                {
+                    has_config = 3;
+                    b.start = b.centre;
+                    b.start[1] -= b.radius;
+                    b.start[2] -= b.radius;
+                    b.end = b.centre;
+                    b.end[1] += b.radius;
+                    b.end[2] += b.radius;
+                    b.right = b.centre;
+                    b.right[1] += b.radius;
+                    b.right[2] -= b.radius;
+                }
+            }
+            else if (b.defined(b.start) && b.defined(b.right) && b.defined(b.end))
+            {
+                has_config = 1;
+                b.centre = 0.5 * (b.start + b.end);
+                const V3 v = b.right - b.start;
+                b.radius = 0.5 * norm(v);
+                b.right = b.centre + 0.5 * v;
+            }
+        }
+        else
+            err += "Inlet block \"" + b.name + "\" sub shape type has not been correctly defined: choose Square or Circle. ";
+    }
+    else if (b.defined(b.start) && b.defined(b.end))
+    {
+        has_config = 1;
+        b.centre = 0.5 * (b.start + b.end);
+        b.radius = norm(b.centre - b.start);
+    }
+    else if (b.defined(b.centre) && b.radius > 0)
+    {
+        has_config = 3;
+        b.start = b.centre;
+        b.start[1] -= b.radius;
+        b.end = b.centre;
+        b.end[1] += b.radius;
+    }
+    if (has_config == 0)
+        err += "Inlet block \"" + b.name + "\" geometry not sufficiently defined. ";
+    if (b.particle_order)
+        err += "Inlet block \"" + b.name + "\": HCP ordering makes the reference index its 4-entry buffer rows with 5 "
+               "(Init.cpp:358 against inlet.cpp:491); not supported. ";
+    if (!err.empty())
+        return;
+    b.dx = gs;
+    rotation_from_angles(b, true);
+    if (has_config == 1)
+    {
+        const V3 ab = normalized(b.end - b.start);
+        if (d3)
+            b.normal = normalized(cross(ab, normalized(b.right - b.start)));
+        else
+        {
+            b.angles[0] = std::atan2(ab[1], ab[0]);
+            /* normal = R * (0,1) with the local R = [[c, s], [-s, c]] */
+            b.normal = V3(std::sin(b.angles[0]), std::cos(b.angles[0]), 0.0);
+        }
+        b.insert_norm = b.normal;
+        const V3 test = b.start - (b.length - 0.01 * gs) * b.insert_norm;
+        b.insconst = dot(b.insert_norm, test);
+    }
+    else if (has_config == 2)
+    {
+        if (d3)
+        {
+            b.right = b.start;
+            b.right[1] += gs * b.ni;
+            b.end = b.right;
+            b.end[2] += gs * b.nj;
+        }
+        else
+        {
+            b.end = b.start;
+            b.end[1] += gs * b.ni;
+        }
+        if (!b.rotmat.is_identity())
+        {
+            b.end = b.rotmat * (b.end - b.start) + b.start;
+            if (d3)
+                b.right = b.rotmat * (b.right - b.start) + b.start;
+        }
+    }
+    else if (!b.rotmat.is_identity())
+    {
+        b.start = b.rotmat * (b.start - b.centre) + b.centre;
+        b.end = b.rotmat * (b.end - b.centre) + b.centre;
+        if (d3)
+            b.right = b.rotmat * (b.right - b.centre) + b.centre;
+    }
+    const double xlength = d3 ? norm(b.right - b.start) : norm(b.end - b.start);
+    b.ni = ceil_i(xlength / gs);
+    if (d3)
+        b.nj = ceil_i(norm(b.end - b.right) / gs);
+    b.nk = ceil_i(b.length / gs);
+    b.ni = b.ni > 1 ? b.ni : 1;
+    b.nk = b.nk > 1 ? b.nk : 1;
+    const int nBuff = 4;
+    if (d3)
+    {
+        b.nj = b.nj > 1 ? b.nj : 1;
+        if (b.sub_bound_type == circleSphere)
+        {
+            if (!b.defined(b.centre))
+                b.centre = 0.5 * (b.start + b.end);
+            if (b.radius < 0)
+                b.radius = norm(b.centre - b.start) * std::cos(M_PI_4);
+            b.npts = size_t(b.ni * b.nj * M_PI_4 * (b.nk + nBuff + 1));
+        }
+        else
+            b.npts = size_t(b.ni) * b.nj * (b.nk + nBuff + 1);
+    }
+    else
+        b.npts = size_t(b.ni) * (b.nk + nBuff);
+    if (b.vmag != 0)
+        b.vel = b.vmag * b.insert_norm;
+    post_check(b, gs);
+}
+std::vector<V3> lattice_disk(const Block& b, double dx, int kk)
+{
+    std::vector<V3> pts;
+    std::uniform_real_distribution<double> unif(0.0, MEPS * dx);
+    std::default_random_engine re;
+    const double rsq = b.radius * b.radius;
+    for (int jj = 0; jj < b.nj; ++jj)
+        for (int ii = 0; ii < b.ni; ++ii)
+        {
+            V3 p = V3(-double(kk), double(ii), double(jj)) * dx;
+            const double a = p[1] - b.radius, c = p[2] - b.radius;
+            if ((a * a + c * c) > rsq)
+                continue;
+            p = p + make3(unif(re), unif(re), unif(re));
+            pts.push_back(b.rotmat * p + b.start);
+        }
+    return pts;
+}
+void inlet_generate(Block& b, double gs)
+{
+    std::uniform_real_distribution<double> unif(0.0, MEPS * gs);
+    std::default_random_engine re;
+    std::vector<V3>& pts = b.coords;
+    const int nBuff = 4;
+    if (b.dim == 2)
+    {
+        const V3 delta = (b.end - b.start) / double(b.ni);
+        const V3 nrm(delta[1], -delta[0], 0.0);
+        int jj = 0;
+        for (jj = 0; jj < b.nk; ++jj)
+            for (int ii = 0; ii < b.ni; ++ii)
+            {
+                V3 p = delta * double(ii) + nrm * double(-jj);
+                p = p + constant(unif(re), 2);
+                pts.push_back(p + b.start);
+                b.bc.push_back(FJSPH_PIPE);
+            }
+        for (int ii = 0; ii < b.ni; ++ii)
+        {
+            V3 p = delta * double(ii) + nrm * double(-jj);
+            p = p + constant(unif(re), 2);
+            pts.push_back(p + b.start);
+            b.bc.push_back(FJSPH_BACK);
+            b.back.push_back(pts.size() - 1);
+        }
+        b.buffer.assign(size_t(b.ni), std::vector<size_t>(nBuff));
+        size_t buff = 0;
+        for (jj = b.nk + 1; jj <= b.nk + nBuff; ++jj)
+        {
+            for (int ii = 0; ii < b.ni; ++ii)
+            {
+                V3 p = delta * double(ii) + nrm * double(-jj);
+                p = p + constant(unif(re), 2);
+                pts.push_back(p + b.start);
+                b.bc.push_back(FJSPH_BUFFER);
+                b.buffer[size_t(ii)][buff] = pts.size() - 1;
+            }
+            buff++;
+        }
+        return;
+    }
+    if (b.sub_bound_type == squareCube)
+    {
+        int kk = 0;
+        for (kk = 0; kk < b.nk; ++kk)
+            for (int jj = 0; jj < b.nj; ++jj)
+                for (int ii = 0; ii < b.ni; ++ii)
+                {
+                    V3 p = V3(double(-kk), double(ii), double(jj)) * gs;
+                    p = p + make3(unif(re), unif(re), unif(re));
+                    pts.push_back(b.rotmat * p + b.start);
+                    b.bc.push_back(FJSPH_PIPE);
+                }
+        for (int jj = 0; jj < b.nj; ++jj)
+            for (int ii = 0; ii < b.ni; ++ii)
+            {
+                V3 p = V3(double(-kk), double(jj), double(ii)) * gs; /* sic: (jj, ii) swapped, inlet.cpp:488 */
+                p = p + make3(unif(re), unif(re), unif(re));
+                pts.push_back(b.rotmat * p + b.start);
+                b.bc.push_back(FJSPH_BACK);
+                b.back.push_back(pts.size() - 1);
+            }
+        b.buffer.assign(b.back.size(), std::vector<size_t>(nBuff));
+        size_t buff = 0;
+        for (kk = b.nk + 1; kk <= b.nk + nBuff; ++kk)
+        {
+            size_t col = 0;
+            for (int jj = 0; jj < b.nj; ++jj)
+                for (int ii = 0; ii < b.ni; ++ii)
+                {
+                    V3 p = V3(double(-kk), double(ii), double(jj)) * gs;
+                    p = p + make3(unif(re), unif(re), unif(re));
+                    pts.push_back(b.rotmat * p + b.start);
+                    b.bc.push_back(FJSPH_BUFFER);
+                    b.buffer[col++][buff] = pts.size() - 1;
+                }
+            buff++;
+        }
+        return;
+    }
+    /* Circle: one disk per layer, each from a fresh engine (create_disk, inlet.cpp:370-445) */
+    auto disk = [&](int kk) {
+        if (!b.particle_order)
+            return lattice_disk(b, gs, kk);
+        std::vector<V3> d;
+        std::uniform_real_distribution<double> u2(0.0, MEPS * gs);
+        std::default_random_engine r2;
+        ring_points(d, r2, u2, gs, b.radius, -gs * kk, b.rotmat, b.centre, 3);
+        return d;
+    };
+    int kk = 0;
+    for (kk = 0; kk < b.nk; ++kk)
+        for (const V3& p : disk(kk))
+        {
+            pts.push_back(p);
+            b.bc.push_back(FJSPH_PIPE);
+        }
+    for (const V3& p : disk(kk))
+    {
+        b.back.push_back(pts.size());
+        pts.push_back(p);
+        b.bc.push_back(FJSPH_BACK);
+    }
+    b.buffer.assign(b.back.size(), std::vector<size_t>(nBuff));
+    size_t buff = 0;
+    for (kk = b.nk + 1; kk <= b.nk + nBuff; ++kk)
+    {
+        const std::vector<V3> d = disk(kk);
+        for (size_t ii = 0; ii < d.size() && ii < b.buffer.size(); ii++)
+        {
+            b.buffer[ii][buff] = pts.size();
+            pts.push_back(d[ii]);
+            b.bc.push_back(FJSPH_BUFFER);
+        }
+        buff++;
+    }
+}
+
+// ---------------------------------------------------------------- Coordinates (coordinates.cpp)
+void coord_check(Block& b, const Ctx& C, double& gs, std::string& err)
+{
+    common_check(b, C, err);
+    if (b.filename.empty())
+    {
+        if (b.coords.empty())
+            err += "Block \"" + b.name + "\" coordinates have not been ingested properly. ";
+        else
+            b.npts = b.coords.size();
+    }
+    post_check(b, gs);
+}
+
+// ---------------------------------------------------------------- block file (shapes.cpp:408-625)
+struct Shapes
+{
+    std::vector<std::unique_ptr<Block>> block;
+    size_t total_points = 0;
+};
+
+bool read_bmap(const std::string& path, const Ctx& C, double& gs, Shapes& out, std::string& err)
+{
+    std::ifstream fin(path);
+    if (!fin.is_open())
+    {
+        err = path + " file missing";
+        return false;
+    }
+    const int dim = C.dim;
+    std::string line, shape_name;
+    /* pass 1: one block per "block end", typed by the last "Shape" seen */
+    while (std::getline(fin, line))
+    {
+        const size_t hash = line.find('#');
+        if (hash != std::string::npos)
+            line = line.substr(0, hash);
+        get_string(line, "Shape", shape_name);
+        if (line.find("block end") != std::string::npos)
+        {
+            std::unique_ptr<Block> b(new Block(dim));
+            b->bound_type = shape_type_of(shape_name, dim);
+            if (b->bound_type < 0)
+                err += "Unrecognised boundary shape, \"" + shape_name + "\". ";
+            else if (b->bound_type == arcSection)
+                err += "Arc/Arch blocks are not restated by this front end. ";
+            out.block.push_back(std::move(b));
+            shape_name.clear();
+        }
+    }
+    if (!err.empty())
+        return false;
+    fin.clear();
+    fin.seekg(0);
+    size_t ib = 0;
+    const size_t nblocks = out.block.size();
+    while (ib < nblocks && std::getline(fin, line))
+    {
+        const size_t hash = line.find('#');
+        if (hash != std::string::npos)
+            line = line.substr(0, hash);
+        Block& b = *out.block[ib];
+        get_string(line, "Name", b.name);
+        get_string(line, "Shape", b.shape);
+        get_string(line, "Sub-shape", b.subshape);
+        get_string(line, "Boundary solver", b.solver_name);
+        get_number(line, "Write surface data (0/1)", b.write_data);
+        get_number(line, "Fixed velocity or dynamic inlet BC (0/1)", b.fixed_vel_or_dynamic);
+        get_vector(line, "Aerodynamic entry normal", b.aero_norm, dim);
+        get_vector(line, "Deletion normal", b.delete_norm, dim);
+        get_vector(line, "Insertion normal", b.insert_norm, dim);
+        get_number(line, "Aerodynamic entry plane constant", b.aeroconst);
+        get_number(line, "Deletion plane constant", b.delconst);
+        get_number(line, "Insertion plane constant", b.insconst);
+        get_number(line, "Pipe depth", b.thickness);
+        get_number(line, "i-direction count", b.ni);
+        get_number(line, "j-direction count", b.nj);
+        get_number(line, "k-direction count", b.nk);
+        get_vector(line, "Stretching factor", b.stretch, dim);
+        get_vector(line, "Normal vector", b.normal, dim);
+        get_vector(line, "Rotation angles", b.angles, dim);
+        get_number(line, "Rotation angle", b.angles[0]);
+        get_vector(line, "Start coordinate", b.start, dim);
+        get_vector(line, "End coordinate", b.end, dim);
+        get_vector(line, "Right coordinate", b.right, dim);
+        get_vector(line, "Midpoint coordinate", b.mid, dim);
+        get_vector(line, "Centre coordinate", b.centre, dim);
+        get_vector(line, "Arch normal", b.right, dim);
+        get_number(line, "Radius", b.radius);
+        get_number(line, "Length", b.length);
+        get_number(line, "Arc start (degree)", b.arc_start);
+        get_number(line, "Arc end (degree)", b.arc_end);
+        get_number(line, "Arc length (degree)", b.arclength);
+        get_number(line, "Starting straight length", b.sstraight);
+        get_number(line, "Ending straight length", b.estraight);
+        get_number(line, "Particle spacing", b.dx);
+        get_number(line, "Particle ordering (0=grid,1=HCP)", b.particle_order);
+        get_number(line, "Wall thickness", b.thickness);
+        get_number(line, "Wall radial particle count", b.nk);
+        get_number(line, "Wall is no slip (0/1)", b.no_slip);
+        get_string(line, "Coordinate filename", b.filename);
+        get_vector(line, "Starting velocity", b.vel, dim);
+        get_number(line, "Starting jet velocity", b.vmag);
+        get_number(line, "Starting pressure", b.press);
+        get_number(line, "Starting density", b.dens);
+        get_number(line, "Cole EOS gamma", b.gamma);
+        get_number(line, "Speed of sound", b.speedOfSound);
+        get_number(line, "Resting density", b.rho_rest);
+        get_number(line, "Volume to target", b.renorm_vol);
+        get_string(line, "Time data filename", b.position_filename);
+        if (line.find("Coordinate data:") != std::string::npos)
+        {
+            std::string tmp;
+            std::getline(fin, tmp);
+            size_t npts = 0;
+            fin >> npts;
+            b.npts = npts;
+            b.coords.assign(npts, V3());
+            for (size_t ii = 0; ii < npts; ++ii)
+                for (int d = 0; d < dim; ++d) fin >> b.coords[ii][d];
+        }
+        const bool tpos = line.find("Time position data") != std::string::npos;
+        const bool tvel = line.find("Time velocity data") != std::string::npos;
+        if (tpos || tvel)
+        {
+            std::string tmp;
+            std::getline(fin, tmp);
+            size_t nt = 0;
+            std::istringstream iss(tmp);
+            iss >> nt;
+            b.ntimes = nt;
+            b.times.assign(nt, 0.0);
+            std::vector<V3>& dst = tpos ? b.pos : b.vels;
+            dst.assign(nt, V3());
+            for (size_t ii = 0; ii < nt; ++ii)
+            {
+                std::getline(fin, tmp);
+                std::istringstream is2(tmp);
+                is2 >> b.times[ii];
+                for (int d = 0; d < dim; ++d) is2 >> dst[ii][d];
+            }
+        }
+        if (line.find("block end") != std::string::npos)
+            ib++;
+    }
+    for (auto& bp : out.block)
+    {
+        Block& b = *bp;
+        std::string e;
+        switch (b.bound_type)
+        {
+        case linePlane: line_check(b, C, gs, e); break;
+        case squareCube: square_check(b, C, gs, e); break;
+        case circleSphere: circle_check(b, C, gs, e); break;
+        case cylinderT: cylinder_check(b, C, gs, e); break;
+        case inletZone: inlet_check(b, C, gs, e); break;
+        case coordDef: coord_check(b, C, gs, e); break;
+        default: e = "unsupported shape. ";
+        }
+        err += e;
+    }
+    if (!err.empty())
+        return false;
+    for (auto& bp : out.block) out.total_points += bp->npts;
+    return true;
+}
+
+void generate_points(Shapes& S, double gs, const Ctx& C)
+{
+    size_t total = 0;
+    for (auto& bp : S.block)
+    {
+        Block& b = *bp;
+        switch (b.bound_type)
+        {
+        case linePlane: line_generate(b, gs); break;
+        case squareCube: square_generate(b, gs); break;
+        case circleSphere: circle_generate(b, gs); break;
+        case cylinderT: cylinder_generate(b, gs); break;
+        case inletZone: inlet_generate(b, gs); break;
+        default: break;
+        }
+        b.npts = b.coords.size();
+        total += b.npts;
+        /* use_global_gas_law = 1 (Var.h:382): block gas-law values are the global ones */
+        b.rho_rest = C.rho_rest;
+        b.gamma = C.gam;
+        b.speedOfSound = C.speed_sound;
+        b.backgroundP = C.press_pipe;
+    }
+    S.total_points = total;
+}
+
+// ---------------------------------------------------------------- Check_Intersection (Init.cpp:61-225)
+// radius_search(tree, q, searchDist) = every point p of the tree with |p - q|^2 < searchDist (nanoflann, strict).
+struct PointGrid
+{
+    const std::vector<V3>& pts;
+    double cell, inv;
+    V3 lo;
+    int n[3];
+    std::vector<int> start, items;
+    PointGrid(const std::vector<V3>& p, double radius, int dim) : pts(p), cell(radius), inv(1.0 / radius)
+    {
+        n[0] = n[1] = n[2] = 1;
+        if (pts.empty())
+            return;
+        V3 hi = pts[0];
+        lo = pts[0];
+        for (const V3& q : pts)
+            for (int d = 0; d < dim; ++d)
+            {
+                lo[d] = std::min(lo[d], q[d]);
+                hi[d] = std::max(hi[d], q[d]);
+            }
+        for (int d = 0; d < dim; ++d) n[d] = std::max(1, std::min(1024, int((hi[d] - lo[d]) * inv) + 1));
+        inv = 1.0 / cell;
+        std::vector<int> count(size_t(n[0]) * n[1] * n[2] + 1, 0);
+        for (const V3& q : pts) count[size_t(key(q)) + 1]++;
+        for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
+        start = count;
+        items.resize(pts.size());
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (size_t i = 0; i < pts.size(); ++i) items[size_t(fill[size_t(key(pts[i]))]++)] = int(i);
+    }
+    int coord(double v, int d) const { return std::max(0, std::min(n[d] - 1, int(std::floor((v - lo[d]) * inv)))); }
+    int key(const V3& q) const { return (coord(q[2], 2) * n[1] + coord(q[1], 1)) * n[0] + coord(q[0], 0); }
+    template <class F>
+    void search(const V3& q, double r2, F&& hit) const
+    {
+        if (pts.empty())
+            return;
+        /* cells may be wider than `cell` when an axis was clamped to 1024 cells: sweep by coordinate range */
+        const double r = std::sqrt(r2);
+        int a[3], b[3];
+        for (int d = 0; d < 3; ++d)
+        {
+            a[d] = coord(q[d] - r, d);
+            b[d] = coord(q[d] + r, d);
+        }
+        for (int z = a[2]; z <= b[2]; ++z)
+            for (int y = a[1]; y <= b[1]; ++y)
+                for (int x = a[0]; x <= b[0]; ++x)
+                {
+                    const size_t k = size_t((z * n[1] + y) * n[0] + x);
+                    for (int s = start[k]; s < start[k + 1]; ++s)
+                    {
+                        const V3 d = pts[size_t(items[size_t(s)])] - q;
+                        if (dot(d, d) < r2)
+                            hit(size_t(items[size_t(s)]));
+                    }
+                }
+    }
+};
+
+void check_intersection(double dx, int dim, Shapes& bound, Shapes& fluid)
+{
+    const double sd = (0.9 * dx) * (0.9 * dx);
+    for (auto& b : bound.block) b->intersect.assign(b->npts, 0);
+    for (size_t id = 0; id < bound.block.size(); ++id)
+    {
+        PointGrid tree(bound.block[id]->coords, 0.9 * dx, dim);
+        for (size_t ii = id; ii < bound.block.size(); ++ii)
+        {
+            Block& other = *bound.block[ii];
+            for (size_t jj = 0; jj < other.coords.size(); ++jj)
+                if (other.intersect[jj] == 0)
+                    tree.search(other.coords[jj], sd, [&](size_t m) {
+                        if (m != jj) /* sic: also compared across different blocks, Init.cpp:95-96 */
+                            bound.block[id]->intersect[m] = 1;
+                    });
+        }
+    }
+    for (auto& b : fluid.block) b->intersect.assign(b->npts, 0);
+    for (size_t id = 0; id < fluid.block.size(); ++id)
+    {
+        Block& me = *fluid.block[id];
+        PointGrid tree(me.coords, 0.9 * dx, dim);
+        for (auto& bb : bound.block)
+            for (size_t jj = 0; jj < bb->coords.size(); ++jj)
+                if (bb->intersect[jj] == 0)
+                    tree.search(bb->coords[jj], sd, [&](size_t m) { me.intersect[m] = 1; });
+        for (size_t ii = id + 1; ii < fluid.block.size(); ++ii)
+        {
+            Block& other = *fluid.block[ii];
+            for (size_t jj = 0; jj < other.npts; ++jj)
+                if (other.intersect[jj] == 0)
+                    tree.search(other.coords[jj], sd, [&](size_t m) { me.intersect[m] = 1; });
+        }
+    }
+    for (auto& fb : fluid.block)
+        for (size_t bID = 0; bID < fb->back.size(); bID++)
+        {
+            int does = fb->intersect[fb->back[bID]] ? 1 : 0;
+            if (!does)
+                for (size_t id : fb->buffer[bID])
+                    if (fb->intersect[id])
+                        does = 1;
+            if (does)
+            {
+                fb->intersect[fb->back[bID]] = 1;
+                for (size_t id : fb->buffer[bID]) fb->intersect[id] = 1;
+            }
+        }
+    for (Shapes* S : {&bound, &fluid})
+    {
+        size_t tot = 0;
+        for (auto& b : S->block)
+        {
+            b->npts = size_t(std::count(b->intersect.begin(), b->intersect.end(), 0));
+            tot += b->npts;
+        }
+        S->total_points = tot;
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------- the case object behind the C ABI
+struct FjsphCase
+{
+    int dim = 3;
+    FjsphParams params;
+    int init_hydro = 0;
+    double hydro_height = -1.0;
+    int64_t bound_points = 0;
+    int n_bound_blocks = 0;
+    std::vector<double> xi, v, rho, p, m;
+    std::vector<int32_t> b;
+    struct Limit
+    {
+        std::string name;
+        FjsphBlock blk;
+        std::vector<double> times, vels;
+        std::vector<int64_t> back, buffer;
+    };
+    std::vector<Limit> limits;
+};
+
+namespace
+{
+void emit(FjsphCase& c, const V3& x, const V3& vel, double dens, double mass, double press, int bflag)
+{
+    for (int d = 0; d < c.dim; ++d)
+    {
+        c.xi.push_back(x[d]);
+        c.v.push_back(vel[d]);
+    }
+    c.rho.push_back(dens);
+    c.m.push_back(mass);
+    c.p.push_back(press);
+    c.b.push_back(bflag);
+}
+
+// get_boundary_velocity (Init.cpp:26-38)
+void boundary_velocity(Block& b)
+{
+    if (b.ntimes != 0)
+    {
+        b.vels.assign(b.ntimes - 1, V3());
+        for (size_t j = 0; j + 1 < b.ntimes; ++j) b.vels[j] = (b.pos[j + 1] - b.pos[j]) / (b.times[j + 1] - b.times[j]);
+    }
+}
+
+void fill_common(FjsphCase::Limit& L, const Block& b, int dim, bool is_fluid)
+{
+    std::memset(&L.blk, 0, sizeof(L.blk));
+    L.name = b.name;
+    L.blk.is_fluid = is_fluid ? 1 : 0;
+    L.blk.bound_solver = b.bound_solver;
+    L.blk.no_slip = b.no_slip ? 1 : 0;
+    L.blk.block_type = b.bound_type;
+    L.blk.fixed_vel_or_dynamic = b.fixed_vel_or_dynamic;
+    for (int d = 0; d < 3; ++d)
+    {
+        L.blk.insert_norm[d] = d == 0 ? 1.0 : 0.0;
+        L.blk.delete_norm[d] = d == 0 ? 1.0 : 0.0;
+        L.blk.aero_norm[d] = d == 0 ? 1.0 : 0.0;
+    }
+    L.blk.insconst = L.blk.delconst = L.blk.aeroconst = DEFV;
+    (void)dim;
+}
+
+// Init_Particles (Init.cpp:270-496)
+int init_particles(FjsphCase& c, Shapes& bound, Shapes& fluid)
+{
+    const FjsphParams& P = c.params;
+    const int dim = c.dim;
+    int64_t part_id = 0;
+    for (auto& bp : bound.block)
+    {
+        Block& b = *bp;
+        c.limits.emplace_back();
+        FjsphCase::Limit& L = c.limits.back();
+        fill_common(L, b, dim, false);
+        L.blk.first = part_id;
+        for (size_t ii = 0; ii < b.coords.size(); ii++)
+            if (!b.intersect[ii])
+            {
+                emit(c, b.coords[ii], b.vel, b.dens, P.bnd_mass, b.press, FJSPH_BOUND);
+                part_id++;
+            }
+        if (!b.times.empty())
+        {
+            if (!b.pos.empty() && b.vels.empty())
+                boundary_velocity(b);
+            else if (b.vels.empty())
+            {
+                fj_set_error("No velocity or position data available for boundary block \"%s\" even though times were defined.",
+                             b.name.c_str());
+                return FJSPH_ERR_INVALID;
+            }
+            L.times = b.times;
+            for (const V3& u : b.vels)
+                for (int d = 0; d < 3; ++d) L.vels.push_back(u[d]);
+            L.blk.n_times = int32_t(b.ntimes);
+        }
+        else
+        {
+            L.blk.n_times = 0;
+            for (int d = 0; d < 3; ++d) L.vels.push_back(b.vel[d]);
+        }
+        L.blk.second = part_id;
+    }
+    c.n_bound_blocks = int(bound.block.size());
+    c.bound_points = part_id;
+    for (auto& bp : fluid.block)
+    {
+        Block& b = *bp;
+        c.limits.emplace_back();
+        FjsphCase::Limit& L = c.limits.back();
+        fill_common(L, b, dim, true);
+        L.blk.first = part_id;
+        if (b.bound_type == inletZone)
+        {
+            const size_t nBuff = 4;
+            size_t ii = 0;
+            while (ii < b.bc.size() && b.bc[ii] == FJSPH_PIPE)
+            {
+                if (!b.intersect[ii])
+                {
+                    emit(c, b.coords[ii], b.vel, b.dens, P.bnd_mass, b.press, FJSPH_PIPE); /* sic: bnd_mass, Init.cpp:364 */
+                    part_id++;
+                }
+                ii++;
+            }
+            std::vector<char> skip(b.back.size(), 0);
+            for (size_t k = 0; k < b.back.size(); k++) skip[k] = b.intersect[b.back[k]] ? 1 : 0;
+            for (size_t k = 0; k < b.back.size(); k++)
+                if (!skip[k])
+                {
+                    emit(c, b.coords[b.back[k]], b.vel, b.dens, P.sim_mass, b.press, FJSPH_BACK);
+                    L.back.push_back(part_id);
+                    L.buffer.insert(L.buffer.end(), nBuff, 0);
+                    part_id++;
+                }
+            for (size_t f = 0; f < nBuff; f++)
+            {
+                size_t col = 0;
+                for (size_t k = 0; k < b.back.size(); k++)
+                    if (!skip[k])
+                    {
+                        emit(c, b.coords[b.buffer[k][f]], b.vel, b.dens, P.sim_mass, b.press, FJSPH_BUFFER);
+                        L.buffer[col * nBuff + f] = part_id;
+                        part_id++;
+                        col++;
+                    }
+            }
+        }
+        else
+        {
+            for (size_t ii = 0; ii < b.coords.size(); ii++)
+                if (!b.intersect[ii])
+                {
+                    emit(c, b.coords[ii], b.vel, b.dens, P.sim_mass, b.press, FJSPH_FREE);
+                    part_id++;
+                }
+        }
+        L.blk.second = part_id;
+        if (!b.times.empty())
+        {
+            L.times = b.times;
+            for (const V3& u : b.vels)
+                for (int d = 0; d < 3; ++d) L.vels.push_back(u[d]);
+            L.blk.n_times = int32_t(b.ntimes);
+        }
+        else
+        {
+            L.blk.n_times = 0;
+            L.vels.assign(3, 0.0);
+        }
+        for (int d = 0; d < 3; ++d)
+        {
+            L.blk.insert_norm[d] = b.insert_norm[d];
+            L.blk.delete_norm[d] = b.delete_norm[d];
+            L.blk.aero_norm[d] = b.aero_norm[d];
+        }
+        L.blk.insconst = b.insconst;
+        L.blk.delconst = b.delconst;
+        L.blk.aeroconst = b.aeroconst;
+    }
+    if (c.init_hydro)
+    {
+        /* Init.cpp:480-493: height along y whatever the dimension */
+        const size_t n = c.rho.size();
+        for (size_t i = 0; i < n; ++i)
+        {
+            const double y = c.xi[i * size_t(dim) + 1];
+            const double press = std::max(0.0, -P.rho_rest * P.grav[1] * (c.hydro_height - y));
+            double dens;
+            if (P.pressure_rel == 0)
+                dens = P.rho_rest * std::pow(((press - P.press_back) / P.B) + 1.0, 1.0 / P.gam);
+            else
+                dens = (press - P.press_back) / (P.speed_sound * P.speed_sound) + P.rho_rest;
+            c.p[i] = press;
+            c.rho[i] = dens;
+        }
+    }
+    for (FjsphCase::Limit& L : c.limits)
+    {
+        L.blk.times = L.times.empty() ? nullptr : L.times.data();
+        L.blk.vels = L.vels.empty() ? nullptr : L.vels.data();
+        L.blk.n_back = int32_t(L.back.size());
+        L.blk.n_buf = L.back.empty() ? 0 : 4;
+        L.blk.back = L.back.empty() ? nullptr : L.back.data();
+        L.blk.buffer = L.buffer.empty() ? nullptr : L.buffer.data();
+    }
+    return FJSPH_OK;
+}
+
+std::string dir_of(const std::string& path)
+{
+    const size_t s = path.find_last_of('/');
+    return s == std::string::npos ? "" : path.substr(0, s + 1);
+}
+std::string resolve(const std::string& name, const std::string& para_dir)
+{
+    if (name.empty() || name[0] == '/')
+        return name;
+    std::ifstream probe(name);
+    if (probe.is_open())
+        return name; /* the reference opens names relative to the working directory */
+    return para_dir + name;
+}
+} // namespace
+
+// GetInput (IO.cpp:305-723) for the keys the path reads + Init_Particles.  dim = the SIMDIM of the build the deck is for.
+extern "C" int fjsph_case_read(const char* para_path, int dim, FjsphCase** out)
+{
+    if (!para_path || !out || (dim != 2 && dim != 3))
+    {
+        fj_set_error("case_read: need a para file, dim 2 or 3 and an output pointer");
+        return FJSPH_ERR_INVALID;
+    }
+    std::unique_ptr<FjsphCase> c(new FjsphCase());
+    c->dim = dim;
+    int st = fjsph_default_params(&c->params, dim);
+    if (st)
+        return st;
+    char fluid_file[1024] = "", bound_file[1024] = "";
+    st = fjsph_read_para(para_path, &c->params, fluid_file, bound_file, 1024);
+    if (st)
+        return st;
+    double scale = 1.0;
+    {
+        /* case-level keys GetInput reads that are not part of FjsphParams (IO.cpp:356,387-388) */
+        std::ifstream fin(para_path);
+        std::string line;
+        while (std::getline(fin, line))
+        {
+            const size_t hash = line.find('#');
+            if (hash != std::string::npos)
+                line = line.substr(0, hash);
+            get_number(line, "Grid scale", scale);
+            get_number(line, "Init hydrostatic pressure (0/1)", c->init_hydro);
+            get_number(line, "Hydrostatic height", c->hydro_height);
+        }
+    }
+    st = fjsph_set_values(&c->params);
+    if (st)
+        return st;
+    if (c->init_hydro && c->hydro_height < 0)
+    {
+        fj_set_error("Hydrostatic initialisation requested but no hydrostatic height given."); /* IO.cpp:596-602 */
+        return FJSPH_ERR_INVALID;
+    }
+    const FjsphParams& P = c->params;
+    Ctx C{dim, scale, P.rho_rest, P.speed_sound, P.gam, P.press_pipe, P.nu};
+    const std::string pdir = dir_of(para_path);
+    Shapes bound, fluid;
+    std::string err;
+    double gs = P.dx; /* Init_Particles passes a local copy of svar.dx the checks may raise (Init.cpp:272-290) */
+    if (bound_file[0] && !read_bmap(resolve(bound_file, pdir), C, gs, bound, err))
+    {
+        fj_set_error("boundary blocks: %s", err.c_str());
+        return FJSPH_ERR_IO;
+    }
+    if (!fluid_file[0])
+    {
+        fj_set_error("Input fluid definition filename is not set in \"%s\"", para_path);
+        return FJSPH_ERR_IO;
+    }
+    if (!read_bmap(resolve(fluid_file, pdir), C, gs, fluid, err))
+    {
+        fj_set_error("fluid blocks: %s", err.c_str());
+        return FJSPH_ERR_IO;
+    }
+    generate_points(bound, P.dx, C);
+    generate_points(fluid, P.dx, C);
+    check_intersection(P.dx, dim, bound, fluid);
+    st = init_particles(*c, bound, fluid);
+    if (st)
+        return st;
+    *out = c.release();
+    return FJSPH_OK;
+}
+
+extern "C" void fjsph_case_free(FjsphCase* c) { delete c; }
+extern "C" int64_t fjsph_case_count(const FjsphCase* c) { return c ? int64_t(c->rho.size()) : 0; }
+extern "C" int64_t fjsph_case_bound_points(const FjsphCase* c) { return c ? c->bound_points : 0; }
+extern "C" int32_t fjsph_case_num_blocks(const FjsphCase* c) { return c ? int32_t(c->limits.size()) : 0; }
+extern "C" int32_t fjsph_case_dim(const FjsphCase* c) { return c ? c->dim : 0; }
+extern "C" int fjsph_case_params(const FjsphCase* c, FjsphParams* out)
+{
+    if (!c || !out)
+        return FJSPH_ERR_INVALID;
+    *out = c->params;
+    return FJSPH_OK;
+}
+extern "C" int fjsph_case_block(const FjsphCase* c, int32_t i, FjsphBlock* out, char* name, int32_t name_cap)
+{
+    if (!c || !out || i < 0 || size_t(i) >= c->limits.size())
+    {
+        fj_set_error("case_block: index out of range");
+        return FJSPH_ERR_INVALID;
+    }
+    *out = c->limits[size_t(i)].blk;
+    if (name && name_cap > 0)
+        std::snprintf(name, size_t(name_cap), "%s", c->limits[size_t(i)].name.c_str());
+    return FJSPH_OK;
+}
+// xi and v are [n][dim] (dim = fjsph_case_dim); part_id is 0..n-1 in the emitted order (Init.cpp:298-475)
+extern "C" int fjsph_case_state(const FjsphCase* c, FjsphStateView* s)
+{
+    if (!c || !s)
+        return FJSPH_ERR_INVALID;
+    const size_t n = c->rho.size();
+    if (s->n != int64_t(n))
+    {
+        fj_set_error("case_state: view holds %lld particles, the case %zu", (long long)s->n, n);
+        return FJSPH_ERR_INVALID;
+    }
+    if (s->xi)
+        std::memcpy(s->xi, c->xi.data(), c->xi.size() * sizeof(double));
+    if (s->v)
+        std::memcpy(s->v, c->v.data(), c->v.size() * sizeof(double));
+    if (s->rho)
+        std::memcpy(s->rho, c->rho.data(), n * sizeof(double));
+    if (s->p)
+        std::memcpy(s->p, c->p.data(), n * sizeof(double));
+    if (s->m)
+        std::memcpy(s->m, c->m.data(), n * sizeof(double));
+    if (s->b)
+        std::memcpy(s->b, c->b.data(), n * sizeof(int32_t));
+    if (s->part_id)
+        for (size_t i = 0; i < n; ++i) s->part_id[i] = int64_t(i);
+    return FJSPH_OK;
+}

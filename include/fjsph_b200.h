@@ -235,6 +235,27 @@ int fjsph_slab_stats(FjsphEngine* e, int64_t* n_owned, int64_t* n_ghost, int64_t
 int fjsph_upload_owned(FjsphEngine* e, const FjsphStateView* s);
 int fjsph_set_owned(FjsphEngine* e, int64_t n_owned);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Case front end (host only): GetInput + Init_Particles (reference src/IO.cpp:305-723, src/Init.cpp:270-496,
+ * src/shapes/{shapes,line,square,circle,cylinder,inlet,coordinates}.cpp).  Reads a FJSPH para file and the fluid /
+ * boundary block files (bmap) it names, generates every block's particles with the reference's perturbation stream
+ * (std::default_random_engine through uniform_real_distribution(0, eps dx)), removes intersecting particles
+ * (Check_Intersection) and lays the particles out in the reference's order: boundary blocks first, then fluid blocks,
+ * inlet blocks as PIPE layers | BACK row | BUFFER rows with their back / buffer tables.  dim is the SIMDIM of the
+ * build the deck was written for (shape names differ: Line/Plane, Square/Cube, Circle/Sphere); xi and v of
+ * fjsph_case_state are [n][dim].  Arc/Arch blocks and JSON block files are rejected. */
+typedef struct FjsphCase FjsphCase;
+int fjsph_case_read(const char* para_path, int dim, FjsphCase** out);
+void fjsph_case_free(FjsphCase* c);
+int64_t fjsph_case_count(const FjsphCase* c);
+int64_t fjsph_case_bound_points(const FjsphCase* c);
+int32_t fjsph_case_num_blocks(const FjsphCase* c);
+int32_t fjsph_case_dim(const FjsphCase* c);
+int fjsph_case_params(const FjsphCase* c, FjsphParams* out);               /* after Set_Values */
+int fjsph_case_block(const FjsphCase* c, int32_t i, FjsphBlock* out, char* name, int32_t name_cap); /* LIMITS[i]; the
+                                                                              pointers live as long as the case */
+int fjsph_case_state(const FjsphCase* c, FjsphStateView* s);               /* fills xi, v, rho, p, m, b, part_id */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,224 @@
+"""Case front end (GetInput + Init_Particles restated in csrc/host_case.cpp): para + bmap decks -> particles in the
+reference's order.  Host-only code behind the C ABI, so these run without a GPU.  The reference ships no fixtures for
+it; the checks are the analytic lattice counts and positions the generators must produce (shapes/*.cpp), the block
+layout of Init.cpp:298-475 and the consistency of the inlet tables."""
+import os
+
+import numpy as np
+import pytest
+
+from fjsph_b200 import _lib, cases, frontend
+
+DECKS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "decks")
+EPS = np.finfo(np.float64).eps
+
+
+def deck(name):
+    return os.path.join(DECKS, name)
+
+
+def write(tmp_path, name, text):
+    p = tmp_path / name
+    p.write_text(text)
+    return str(p)
+
+
+def test_sphere_block_is_the_culled_lattice():
+    """circle.cpp:131-189: lattice start = centre - R, ceil(2R/dx) points per axis, points with |x - c|^2 > R^2 culled,
+    x fastest; perturbation U(0, eps dx) per axis."""
+    c = frontend.read_case(deck("droplet3d.para"), 3)
+    ref = cases.droplet(dx=0.005, jitter="eps")
+    assert c["xi"].shape == ref["xi"].shape == (4166, 3)
+    assert np.abs(c["xi"] - ref["xi"]).max() <= 1e-16  # same lattice, same order, different eps stream
+    assert c["bound_points"] == 0 and len(c["blocks"]) == 1
+    b = c["blocks"][0]
+    assert (b["first"], b["second"], b["is_fluid"], b["block_type"]) == (0, 4166, 1, 2)
+    assert np.all(c["b"] == cases.FREE) and np.all(c["rho"] == 810.0)
+    assert np.allclose(c["m"], 810.0 * 0.005**3, rtol=1e-15) and np.all(c["p"] == 0.0)
+    assert np.array_equal(c["part_id"], np.arange(4166))
+    P = c["params"]
+    assert P.acase == 1 and tuple(P.v_inf) == (0.0, 21.55, 0.0) and P.solver_type == 0
+    assert abs(P.H - 2.0 * 0.005) < 1e-18 and P.sr == 4 * P.H * P.H
+
+
+def test_dam_2d_layout_and_hydrostatic_init():
+    c = frontend.read_case(deck("dam2d.para"), 2)
+    dx = 0.05
+    names = [b["name"] for b in c["blocks"]]
+    assert names == ["Left", "Bottom", "Water"]  # boundary blocks first, then fluid (Init.cpp:298-475)
+    left, bottom, water = c["blocks"]
+    # line.cpp: ni = ceil(|end - start| / dx) along the line, nk layers along (dy, -dx) of the direction
+    assert (left["first"], left["second"]) == (0, 41 * 4)
+    assert (bottom["first"], bottom["second"]) == (164, 164 + 81 * 4)
+    assert (water["first"], water["second"]) == (488, 488 + 40 * 20)
+    assert c["bound_points"] == 488
+    assert left["bound_solver"] == 1 and bottom["bound_solver"] == 2  # Pressure-Gradient, Ghost (the '#' line is cut)
+    assert np.all(c["b"][:488] == cases.BOUND) and np.all(c["b"][488:] == cases.FREE)
+    xl = c["xi"][:164]
+    # the Left wall runs downwards from (-0.05, 2): direction (0,-1), thickness normal (dy, -dx) = (-1, 0)
+    assert np.allclose(xl[0], (-0.05, 2.0), atol=1e-12) and np.allclose(xl[3], (-0.05 - 3 * dx, 2.0), atol=1e-12)
+    assert np.allclose(xl[4], (-0.05, 2.0 - dx), atol=1e-12)
+    xw = c["xi"][488:]
+    assert np.allclose(xw[0], (0, 0), atol=1e-12) and np.allclose(xw[1], (dx, 0), atol=1e-12)
+    assert np.allclose(xw[40], (0, dx), atol=1e-12)
+    # the perturbation is the reference's stream (square.cpp:103-104,135): std::default_random_engine = minstd_rand0
+    # from seed 1, uniform_real_distribution(0, eps dx) = generate_canonical over two draws, one value for all axes
+    x1 = 16807
+    x2 = 16807 * x1 % 2147483647
+    R = 2147483646.0
+    canon = ((x1 - 1) + (x2 - 1) * R) / (R * R)
+    assert xw[0, 0] == xw[0, 1] == canon * (EPS * dx)
+    # Init.cpp:480-493: p = max(0, -rho0 g_y (h - y)), rho = EOS^-1(p), for EVERY particle (walls too)
+    P = c["params"]
+    y = c["xi"][:, 1]
+    p = np.maximum(0.0, 1000.0 * 9.81 * (1.0 - y))
+    assert np.allclose(c["p"], p, rtol=1e-14)
+    assert np.allclose(c["rho"], cases.cole_density(p, 1000.0, 125.0), rtol=1e-14)
+    assert P.dim == 2 and abs(P.W_correc - 7.0 / (4.0 * np.pi * P.H**2)) < 1e-12 * P.W_correc
+
+
+def test_inlet_and_pipe_blocks():
+    """inlet.cpp (Circle sub-shape, lattice disks) + cylinder.cpp (Hollow), both rotated by "Rotation angles: 0,0,90";
+    Init.cpp:355-426 order: PIPE layers, the BACK row, then the BUFFER rows, with the back / buffer tables."""
+    c = frontend.read_case(deck("jet3d.para"), 3)
+    dx = 1e-4
+    pipe, fluid = c["blocks"]
+    assert pipe["name"] == "Pipe" and pipe["bound_solver"] == 2 and pipe["is_fluid"] == 0
+    assert fluid["name"] == "Fluid" and fluid["block_type"] == 6 and fluid["is_fluid"] == 1
+    nb = c["bound_points"]
+    # hollow cylinder: ni = ceil(2 pi R / dx) around, nj = ceil(L/dx) + 1 deep, nk = 2 layers
+    ni, nj, nk = int(np.ceil(2 * np.pi * 5.5e-4 / dx)), int(np.ceil(0.0008 / dx)) + 1, 2
+    assert nb == ni * nj * nk
+    xp = c["xi"][:nb]
+    r = np.hypot(xp[:, 0], xp[:, 2])  # rotated about z by 90 degrees: the axis is y, the pipe extends to -y
+    assert np.allclose(np.unique(np.round(r / dx, 6)), [5.5, 6.5])
+    assert xp[:, 1].max() < 1e-12 and abs(xp[:, 1].min() + (nj - 1) * dx) < 1e-12
+    # inlet: disk of the lattice points within R of the axis, nk = ceil(L/dx) PIPE layers, 1 BACK, 4 BUFFER
+    b = c["b"][nb:]
+    ndisk = len(fluid["back"])
+    assert np.array_equal(np.bincount(b, minlength=6)[[cases.BUFFER, cases.BACK, cases.PIPE]], [4 * ndisk, ndisk, 5 * ndisk])
+    assert np.all(b[: 5 * ndisk] == cases.PIPE) and np.all(b[5 * ndisk: 6 * ndisk] == cases.BACK)
+    assert np.array_equal(fluid["back"], nb + 5 * ndisk + np.arange(ndisk))
+    assert fluid["buffer"].shape == (ndisk, 4)
+    assert np.array_equal(fluid["buffer"][:, 0], nb + 6 * ndisk + np.arange(ndisk))
+    xf = c["xi"]
+    for k in range(ndisk):  # buffer particles sit straight behind their back particle, one spacing apart
+        col = np.concatenate([[fluid["back"][k]], fluid["buffer"][k]])
+        assert np.allclose(np.diff(xf[col, 1]), -dx, atol=1e-12) and np.allclose(xf[col, 0], xf[col[0], 0], atol=1e-12)
+    assert np.allclose(c["v"][nb:], (0.0, 33.63, 0.0), atol=1e-12)  # vmag * insert_norm, insert_norm = R e_x
+    assert np.allclose(fluid["insert_norm"], (0, 1, 0), atol=1e-15) and fluid["insconst"] == -0.0005
+    assert fluid["aero_norm"] == (0.0, 1.0, 0.0) and fluid["aeroconst"] == 0.0001
+    # PIPE particles carry the boundary mass (Init.cpp:364), BACK / BUFFER the fluid mass -- equal by Set_Values
+    assert np.allclose(c["m"], 997.0 * dx**3, rtol=1e-14)
+
+
+def test_intersecting_particles_are_removed(tmp_path):
+    """Check_Intersection (Init.cpp:61-225): fluid particles within 0.9 dx of a kept boundary particle go, and a fluid
+    block loses the particles a LATER fluid block overlaps."""
+    write(tmp_path, "b.bmap", """
+                       Name: Floor
+                      Shape: Plane
+           Start coordinate: 0,0,0
+           Right coordinate: 0.4,0,0
+             End coordinate: 0.4,0.4,0
+ Wall radial particle count: 2
+ block end
+""")
+    write(tmp_path, "f.bmap", """
+                       Name: A
+                      Shape: Cube
+           Start coordinate: 0,0,0
+             End coordinate: 0.4,0.4,0.4
+ block end
+                       Name: B
+                      Shape: Cube
+           Start coordinate: 0.2,0,0.2
+             End coordinate: 0.6,0.4,0.6
+ block end
+""")
+    para = write(tmp_path, "para", """
+ Input boundary definition filename: %s
+    Input fluid definition filename: %s
+               SPH initial spacing: 0.1
+           SPH frame time interval: 0.1
+""" % (tmp_path / "b.bmap", tmp_path / "f.bmap"))
+    c = frontend.read_case(para, 3)
+    floor, A, B = c["blocks"]
+    # plane: 4 x 4 points, 2 layers along normalized(dj x di) = -z ... the layer at z = 0 coincides with A's bottom layer
+    assert floor["second"] - floor["first"] == 32
+    # A: 4^3 lattice minus its z = 0 layer (on the floor) minus the 2 x 4 x 2 points B's lattice also holds
+    assert A["second"] - A["first"] == 64 - 16 - 16
+    assert B["second"] - B["first"] == 64
+    x = c["xi"]
+    from scipy.spatial import cKDTree
+
+    d, _ = cKDTree(x).query(x, k=2)
+    assert d[:, 1].min() > 0.09  # nothing closer than 0.9 dx survives
+
+
+def test_hcp_cube_spacing(tmp_path):
+    """square.cpp:109-131: HCP ordering puts every nearest neighbour one spacing away."""
+    write(tmp_path, "f.bmap", """
+                       Name: Block
+                      Shape: Cube
+ Particle ordering (0=grid,1=HCP): 1
+           Start coordinate: 0,0,0
+             End coordinate: 1,1,1
+ block end
+""")
+    para = write(tmp_path, "para", """
+    Input fluid definition filename: %s
+               SPH initial spacing: 0.1
+           SPH frame time interval: 0.1
+""" % (tmp_path / "f.bmap"))
+    c = frontend.read_case(para, 3)
+    ni, nj, nk = 10, int(np.ceil(1 / 0.1 / np.sqrt(3) * 2)), int(np.ceil(1 / 0.1 / np.sqrt(6) * 3))
+    assert c["xi"].shape[0] == ni * nj * nk
+    from scipy.spatial import cKDTree
+
+    d, _ = cKDTree(c["xi"]).query(c["xi"], k=2)
+    assert np.allclose(d[:, 1], 0.1, rtol=1e-12)
+
+
+def test_moving_wall_schedule_and_errors(tmp_path):
+    write(tmp_path, "b.bmap", """
+                       Name: Piston
+                      Shape: Line
+           Start coordinate: 0,0
+             End coordinate: 0,1
+ Wall radial particle count: 1
+ Time position data
+ 3
+ 0.0 0.0 0.0
+ 0.5 1.0 0.0
+ 1.5 1.0 2.0
+ block end
+""")
+    write(tmp_path, "f.bmap", """
+                       Name: W
+                      Shape: Square
+           Start coordinate: 0.2,0
+             End coordinate: 0.6,0.4
+ block end
+""")
+    para = write(tmp_path, "para", """
+ Input boundary definition filename: %s
+    Input fluid definition filename: %s
+               SPH initial spacing: 0.1
+           SPH frame time interval: 0.1
+""" % (tmp_path / "b.bmap", tmp_path / "f.bmap"))
+    c = frontend.read_case(para, 2)
+    piston = c["blocks"][0]
+    # get_boundary_velocity (Init.cpp:26-38): piecewise-constant velocities between the time stamps
+    assert np.array_equal(piston["times"], [0.0, 0.5, 1.5])
+    assert np.allclose(piston["vels"][:, :2], [[2.0, 0.0], [0.0, 2.0]])
+    # errors come back as FjsphError with the reference's diagnosis, never exit()
+    bad = write(tmp_path, "bad.bmap", "   Name: X\n  Shape: Blob\n block end\n")
+    para2 = write(tmp_path, "para2", " Input fluid definition filename: %s\n SPH initial spacing: 0.1\n SPH frame time interval: 1\n" % bad)
+    with pytest.raises(_lib.FjsphError, match="Unrecognised boundary shape"):
+        frontend.read_case(para2, 2)
+    with pytest.raises(_lib.FjsphError, match="file missing"):
+        frontend.read_case(write(tmp_path, "para3", " Input fluid definition filename: nope.bmap\n SPH initial spacing: 0.1\n"), 2)
+    nodx = write(tmp_path, "para4", " Input fluid definition filename: %s\n" % (tmp_path / "f.bmap"))
+    with pytest.raises(_lib.FjsphError, match="initial spacing"):
+        frontend.read_case(nodx, 2)
