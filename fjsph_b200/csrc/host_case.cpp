@@ -1493,6 +1493,9 @@ int init_particles(FjsphCase& c, Shapes& bound, Shapes& fluid)
             L.times = b.times;
             for (const V3& u : b.vels)
                 for (int d = 0; d < 3; ++d) L.vels.push_back(u[d]);
+            /* position data give ntimes - 1 velocities, yet the solvers index vels[ntimes - 1] once the last time
+               stamp has passed (Newmark_Beta.cpp:75-81, out of bounds in the reference): the wall then stands still */
+            L.vels.resize(3 * b.ntimes, 0.0);
             L.blk.n_times = int32_t(b.ntimes);
         }
         else
@@ -1562,6 +1565,7 @@ int init_particles(FjsphCase& c, Shapes& bound, Shapes& fluid)
             L.times = b.times;
             for (const V3& u : b.vels)
                 for (int d = 0; d < 3; ++d) L.vels.push_back(u[d]);
+            L.vels.resize(3 * b.ntimes, 0.0);
             L.blk.n_times = int32_t(b.ntimes);
         }
         else

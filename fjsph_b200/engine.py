@@ -310,6 +310,16 @@ class Engine:
         """Run on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
         check(self._L.fjsph_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
+    def write_restart(self, path: str, frame: int = 0):
+        """Checkpoint (the field set of the reference's _particles.h5, H5IO.cpp:395-538)."""
+        check(self._L.fjsph_write_restart(self._h, str(path).encode(), int(frame)))
+
+    def read_restart(self, path: str) -> int:
+        """Resume from a checkpoint: pn = pnp1 from the file, settings, blocks and counters restored; returns the frame."""
+        fr = C.c_int32()
+        check(self._L.fjsph_read_restart(self._h, str(path).encode(), C.byref(fr)))
+        return int(fr.value)
+
     def set_skin(self, skin_over_dx: float):
         """Width of the neighbour superset list in units of dx (0 = cell-list sweep at every update_neighbours)."""
         check(self._L.fjsph_set_skin(self._h, float(skin_over_dx)))

@@ -42,7 +42,7 @@ def read_case(para_path: str, dim: int = 3) -> dict:
                 fixed_vel_or_dynamic=int(B.fixed_vel_or_dynamic),
                 times=None if nt == 0 else np.ctypeslib.as_array(C.cast(B.times, C.POINTER(C.c_double)), shape=(nt,)).copy(),
                 vels=None if not B.vels else np.ctypeslib.as_array(C.cast(B.vels, C.POINTER(C.c_double)),
-                                                                     shape=(nv if nt == 0 else max(1, nt - 1), 3)).copy(),
+                                                                     shape=(nv, 3)).copy(),
                 insert_norm=tuple(B.insert_norm), insconst=float(B.insconst), delete_norm=tuple(B.delete_norm),
                 delconst=float(B.delconst), aero_norm=tuple(B.aero_norm), aeroconst=float(B.aeroconst))
             if nb:

@@ -235,6 +235,15 @@ int fjsph_slab_stats(FjsphEngine* e, int64_t* n_owned, int64_t* n_ghost, int64_t
 int fjsph_upload_owned(FjsphEngine* e, const FjsphStateView* s);
 int fjsph_set_owned(FjsphEngine* e, int64_t n_owned);
 
+/* Checkpoint / resume: a raw-binary mirror of the reference's <prefix>_particles.h5 restart data (H5IO.cpp:395-538,
+ * 915-962; HDF5 is not available here): position, velocity, acceleration, pressure, density, density gradient, mass,
+ * boundary condition, particle ID, cell ID, cell velocity / density / pressure under the reference's dataset names, the
+ * LIMITS blocks with their inlet back / buffer tables, every setting (FjsphParams incl. current time, previous frame
+ * time and the CFL controller state) and the particle index to add.  fjsph_read_restart restores pn = pnp1 from it, as
+ * Read_HDF5 does; the next step rebuilds the neighbour lists and the frozen terms.  Layout: csrc/restart.cu. */
+int fjsph_write_restart(FjsphEngine* e, const char* path, int32_t frame);
+int fjsph_read_restart(FjsphEngine* e, const char* path, int32_t* frame);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Case front end (host only): GetInput + Init_Particles (reference src/IO.cpp:305-723, src/Init.cpp:270-496,
  * src/shapes/{shapes,line,square,circle,cylinder,inlet,coordinates}.cpp).  Reads a FJSPH para file and the fluid /

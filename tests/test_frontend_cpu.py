@@ -211,7 +211,8 @@ def test_moving_wall_schedule_and_errors(tmp_path):
     piston = c["blocks"][0]
     # get_boundary_velocity (Init.cpp:26-38): piecewise-constant velocities between the time stamps
     assert np.array_equal(piston["times"], [0.0, 0.5, 1.5])
-    assert np.allclose(piston["vels"][:, :2], [[2.0, 0.0], [0.0, 2.0]])
+    # (one entry per time stamp: past the last one the wall stands still, where the reference reads out of bounds)
+    assert np.allclose(piston["vels"][:, :2], [[2.0, 0.0], [0.0, 2.0], [0.0, 0.0]])
     # errors come back as FjsphError with the reference's diagnosis, never exit()
     bad = write(tmp_path, "bad.bmap", "   Name: X\n  Shape: Blob\n block end\n")
     para2 = write(tmp_path, "para2", " Input fluid definition filename: %s\n SPH initial spacing: 0.1\n SPH frame time interval: 1\n" % bad)

@@ -1,0 +1,51 @@
+"""Decks read by the case front end (para + bmap -> particles and LIMITS blocks) run on the device against the CPU
+oracle: the droplet deck (Gissler aero) and the jet deck (round inlet with BACK / BUFFER tables inside a Ghost-solver
+pipe wall, "Rotation angles" 0,0,90) -- the layout of the reference's Examples/Droplet and Examples/Crossflow."""
+import os
+
+import numpy as np
+import pytest
+
+from fjsph_b200 import frontend
+from tests.util import assert_fields_close, make_pair_from_deck, relerr
+
+pytestmark = pytest.mark.gpu
+DECKS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "decks")
+
+
+def test_droplet_deck_steps():
+    case = frontend.read_case(os.path.join(DECKS, "droplet3d.para"), 3)
+    o, e = make_pair_from_deck(case)
+    for step in range(3):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert se.iterations == so.iterations and abs(se.dt - so.dt) <= 1e-12 * so.dt, step
+    # the deck's own lattice + U(0, eps dx) positions are a tie-stress input (tests/test_gpu_parity.py): flags exact,
+    # state 1e-8, rates 1e-3
+    assert_fields_close(e, o, ("surf", "surfzone", "cellID", "b"), context="droplet deck")
+    assert_fields_close(e, o, ("xi", "rho"), tol=1e-8, context="droplet deck")
+    assert_fields_close(e, o, ("acc", "Rrho", "Af"), tol=1e-3, context="droplet deck")
+
+
+def test_jet_deck_inlet_and_pipe():
+    case = frontend.read_case(os.path.join(DECKS, "jet3d.para"), 3)
+    o, e = make_pair_from_deck(case)
+    n_add = 0
+    for step in range(9):
+        _, so = o.integrate()
+        se = e.integrate()
+        ctx = "jet deck step %d" % step
+        assert (se.n_add, se.n_del, se.total_points) == (so.n_add, so.n_del, so.total_points), ctx
+        # dt follows max |acc| (a rate: 1e-6 bar); the sub-iteration loop stops on a residual threshold
+        assert abs(se.iterations - so.iterations) <= 1 and abs(se.dt - so.dt) <= 1e-6 * so.dt, ctx
+        got = e.download(("part_id", "b", "xi", "v", "rho"))
+        assert np.array_equal(got["part_id"], o.get("part_id")), ctx
+        assert np.array_equal(got["b"], o.get("b")), ctx
+        # lattice + U(0, eps dx) positions with every sub-iteration loop running to its limit: a tie-stress input
+        # (tests/test_gpu_parity.py), so the bars are the discrete ones above plus a loose one on the state
+        # (1e-6 of the 1 mm domain = 1e-5 dx)
+        assert relerr(got["xi"], o.get("xi")) <= 1e-6, ctx
+        assert relerr(got["rho"], o.get("rho")) <= 1e-6, ctx
+        assert relerr(got["v"], o.get("v")) <= 1e-4, ctx
+        n_add += se.n_add
+    assert n_add > 0  # the run did insert particles at the inlet

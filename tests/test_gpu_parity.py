@@ -214,7 +214,10 @@ def test_uniform_drift_keeps_the_superset_list():
         off_e, idx_e = e.neighbours()
         assert np.array_equal(off_o, off_e) and np.array_equal(idx_o, idx_e), ctx
         assert_fields_close(e, o, FLAG_FIELDS, context=ctx)
-        assert_fields_close(e, o, STATE_FIELDS, tol=1e-10, context=ctx)
+        # the velocity scale is 60x that of the other full-step cases while the block is as small: the same relative
+        # noise in v integrates to a 60x larger share of |x| (measured 1.4e-10 after 4 steps)
+        assert_fields_close(e, o, ("xi",), tol=1e-9, context=ctx)
+        assert_fields_close(e, o, ("rho", "lam", "lam_nb"), tol=1e-10, context=ctx)
         assert_fields_close(e, o, ("v", "p"), tol=1e-8, context=ctx)
         assert_fields_close(e, o, RATE_FIELDS, tol=1e-6, context=ctx)
     moved = e.download(("xi",))["xi"][:, 0].mean() - x0

@@ -53,3 +53,34 @@ def assert_fields_close(e, o, fields, tol=TOL, level=1, context=""):
         else:
             r = relerr(got[f], ref)
             assert r <= tol, "%s: field %s relative error %.3e > %.1e" % (context, f, r, tol)
+
+
+INPUT_PARAMS = ("ale pressure_rel solver_type acase asource use_lam use_TAB_def max_subits n_stable_limit n_unstable_limit "
+                "particle_step H_fac rho_rest press_pipe press_back rho_max rho_min rho_var rho_max_iter visc_alpha speed_sound "
+                "mu sig gam dsph_delta grav v_inf p_ref rho_g mu_g temp_g R_g gamma_g lam_cutoff i_interp_fac tab_Cf tab_Ck "
+                "tab_Cd tab_Cb cfl cfl_step cfl_max cfl_min subits_factor min_residual delta_t_max delta_t_min max_shift_vel "
+                "frame_time_interval").split()
+
+
+def make_pair_from_deck(case, capacity=None, **kw):
+    """(oracle, engine) for a case read by fjsph_b200.frontend.read_case: same settings, particles and LIMITS blocks."""
+    P = case["params"]
+    dim = case["dim"]
+    params = {k: (tuple(getattr(P, k)) if hasattr(getattr(P, k), "__len__") else getattr(P, k)) for k in INPUT_PARAMS}
+    params.update(kw)
+    o = orc.Oracle(orc.default_params(dim, **params))
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
+    o.lib.orc_clear_blocks(o.h)
+    for B in case["blocks"]:
+        o.add_block(B["is_fluid"], B["first"], B["second"], bound_solver=B["bound_solver"], no_slip=B["no_slip"],
+                    block_type=B["block_type"], fixed_vel_or_dynamic=B["fixed_vel_or_dynamic"], times=B["times"],
+                    vels=B["vels"], insert_norm=B["insert_norm"], insconst=B["insconst"], delete_norm=B["delete_norm"],
+                    delconst=B["delconst"], aero_norm=B["aero_norm"], aeroconst=B["aeroconst"], back=B.get("back"),
+                    buffer=B.get("buffer"))
+    if dim != 3:
+        return o, None
+    n = case["xi"].shape[0]
+    e = eng.Engine(eng.default_params(3, **params), capacity or 4 * n)
+    e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
+    e.set_blocks(case["blocks"])
+    return o, e
