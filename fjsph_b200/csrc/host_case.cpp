@@ -1403,6 +1403,9 @@ struct FjsphCase
     FjsphParams params;
     int init_hydro = 0;
     double hydro_height = -1.0;
+    int max_frames = -1;            /* "SPH frame count" (IO.cpp:375) */
+    long long max_points = -1;      /* "SPH maximum particle count" (IO.cpp:428) */
+    std::string output_prefix, restart_prefix; /* IO.cpp:373,355 */
     int64_t bound_points = 0;
     int n_bound_blocks = 0;
     std::vector<double> xi, v, rho, p, m;
@@ -1658,6 +1661,10 @@ extern "C" int fjsph_case_read(const char* para_path, int dim, FjsphCase** out)
             get_number(line, "Grid scale", scale);
             get_number(line, "Init hydrostatic pressure (0/1)", c->init_hydro);
             get_number(line, "Hydrostatic height", c->hydro_height);
+            get_number(line, "SPH frame count", c->max_frames);
+            get_number(line, "SPH maximum particle count", c->max_points);
+            get_string(line, "Output files prefix", c->output_prefix);
+            get_string(line, "SPH restart prefix", c->restart_prefix);
         }
     }
     st = fjsph_set_values(&c->params);
@@ -1704,6 +1711,22 @@ extern "C" int64_t fjsph_case_count(const FjsphCase* c) { return c ? int64_t(c->
 extern "C" int64_t fjsph_case_bound_points(const FjsphCase* c) { return c ? c->bound_points : 0; }
 extern "C" int32_t fjsph_case_num_blocks(const FjsphCase* c) { return c ? int32_t(c->limits.size()) : 0; }
 extern "C" int32_t fjsph_case_dim(const FjsphCase* c) { return c ? c->dim : 0; }
+// the run-control keys of GetInput the frame loop reads (FJSPH.cpp:262-330): frame count, particle capacity, prefixes
+extern "C" int fjsph_case_io(const FjsphCase* c, int32_t* max_frames, int64_t* max_points, char* output_prefix,
+                             char* restart_prefix, int32_t cap)
+{
+    if (!c)
+        return FJSPH_ERR_INVALID;
+    if (max_frames)
+        *max_frames = c->max_frames;
+    if (max_points)
+        *max_points = c->max_points;
+    if (output_prefix && cap > 0)
+        std::snprintf(output_prefix, size_t(cap), "%s", c->output_prefix.c_str());
+    if (restart_prefix && cap > 0)
+        std::snprintf(restart_prefix, size_t(cap), "%s", c->restart_prefix.c_str());
+    return FJSPH_OK;
+}
 extern "C" int fjsph_case_params(const FjsphCase* c, FjsphParams* out)
 {
     if (!c || !out)

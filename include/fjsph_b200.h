@@ -261,6 +261,10 @@ int64_t fjsph_case_bound_points(const FjsphCase* c);
 int32_t fjsph_case_num_blocks(const FjsphCase* c);
 int32_t fjsph_case_dim(const FjsphCase* c);
 int fjsph_case_params(const FjsphCase* c, FjsphParams* out);               /* after Set_Values */
+/* run control of the frame loop (FJSPH.cpp:262-330): "SPH frame count", "SPH maximum particle count" (-1 when the deck
+ * does not set them), "Output files prefix", "SPH restart prefix" */
+int fjsph_case_io(const FjsphCase* c, int32_t* max_frames, int64_t* max_points, char* output_prefix, char* restart_prefix,
+                  int32_t cap);
 int fjsph_case_block(const FjsphCase* c, int32_t i, FjsphBlock* out, char* name, int32_t name_cap); /* LIMITS[i]; the
                                                                               pointers live as long as the case */
 int fjsph_case_state(const FjsphCase* c, FjsphStateView* s);               /* fills xi, v, rho, p, m, b, part_id */

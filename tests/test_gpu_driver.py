@@ -1,0 +1,51 @@
+"""The command-line driver (csrc/fjsph_run.cpp = FJSPH's main(), FJSPH.cpp:29-356, on the C ABI): a deck runs through
+the frame loop, writes the frame table, the ASCII frames and the restart file, and a run resumed from the restart file
+ends where the uninterrupted one does."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "fjsph_b200", "bin", "fjsph_b200_run")
+
+
+def frame(path):
+    return np.loadtxt(path, skiprows=3)
+
+
+def test_driver_runs_a_deck_and_resumes(tmp_path):
+    if not os.path.exists(BIN):
+        pytest.fail("driver not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    for f in ("droplet3d.para", "droplet3d_fluid.bmap"):
+        shutil.copy(os.path.join(ROOT, "tests", "decks", f), tmp_path / f)
+    para = tmp_path / "droplet3d.para"
+    para.write_text(para.read_text().replace("SPH frame time interval: 0.001", "SPH frame time interval: 4e-5")
+                    + "\n SPH frame count: 4\n Output files prefix: full\n")
+    run = lambda *a: subprocess.run([BIN, str(para), "--quiet", *a], cwd=tmp_path, stdout=subprocess.PIPE,
+                                    stderr=subprocess.STDOUT, text=True, timeout=120)
+    out = run()
+    assert out.returncode == 0 and "Simulation complete!" in out.stdout, out.stdout[-2000:]
+    info = (tmp_path / "full_frame.info").read_text()
+    assert info.count("Frame:") == 4 and "Total Points: 4166 Boundary Points: 0 Fluid Points: 4166" in info
+    frames = sorted(p.name for p in tmp_path.glob("full_frame_*.dat"))
+    assert frames == ["full_frame_%05d.dat" % k for k in range(4)]
+    last = frame(tmp_path / "full_frame_00003.dat")
+    assert last.shape == (4166, 12) and np.isfinite(last).all()
+    # the droplet sits in a 21.55 m/s cross flow along +y: the Gissler drag has started to move it
+    assert last[:, 4].mean() > 0.0
+    # resume from the restart file written after frame 2 of a shorter run
+    out2 = run("--frames", "3", "--out", "part")
+    assert out2.returncode == 0, out2.stdout[-2000:]
+    out3 = run("--frames", "4", "--out", "part", "--restart", "part_particles.fjr")
+    assert out3.returncode == 0 and "Frame: 3" in out3.stdout, out3.stdout[-2000:]
+    resumed = frame(tmp_path / "part_frame_00003.dat")
+    assert np.array_equal(resumed[:, 11], last[:, 11])           # same particles, same order
+    assert np.abs(resumed[:, :3] - last[:, :3]).max() <= 1e-9 * 0.05  # positions, relative to the droplet radius
+    assert (tmp_path / "part_frame.info").read_text().count("Frame:") == 4
+    # errors are messages and exit codes, never a crash
+    bad = subprocess.run([BIN, str(tmp_path / "nope.para")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert bad.returncode == 1 and "could not open" in bad.stdout
