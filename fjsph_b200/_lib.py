@@ -127,6 +127,10 @@ def lib():
     L.fjsph_slab_comm_stream.argtypes = [vp, P(vp)]
     L.fjsph_slab_overlapped.argtypes = [vp, P(C.c_int64)]
     L.fjsph_slab_stats.argtypes = [vp, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)]
+    L.fjsph_foam_read.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, P(vp)]
+    L.fjsph_foam_view.argtypes = [vp, P(FjsphMesh)]
+    L.fjsph_foam_free.argtypes = [vp]
+    L.fjsph_foam_free.restype = None
     L.fjsph_write_restart.argtypes = [vp, C.c_char_p, C.c_int32]
     L.fjsph_read_restart.argtypes = [vp, C.c_char_p, P(C.c_int32)]
     L.fjsph_case_read.argtypes = [C.c_char_p, C.c_int, P(vp)]

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import FjsphBlock, FjsphParams, FjsphStateView, check
+from ._lib import FjsphBlock, FjsphMesh, FjsphParams, FjsphStateView, check
 
 
 def read_case(para_path: str, dim: int = 3) -> dict:
@@ -53,3 +53,33 @@ def read_case(para_path: str, dim: int = 3) -> dict:
         return out
     finally:
         L.fjsph_case_free(h)
+
+
+def read_foam(foam_dir: str, solution_dir: str | None = None, buoyant: bool = False, rho_fill: float = 1.29251) -> dict:
+    """FOAM::Read_FOAM (reference src/FOAMIO.cpp:943-953) for an ASCII OpenFOAM case: the mesh dict Engine.upload_mesh and
+    Oracle.set_mesh take (verts, face_ptr/face_vtx, leftright, cell_ptr/cell_faces, cCentre, cVel, cP, cRho)."""
+    L = _lib.lib()
+    h = C.c_void_p()
+    check(L.fjsph_foam_read(str(foam_dir).encode(), None if not solution_dir else str(solution_dir).encode(),
+                            int(bool(buoyant)), float(rho_fill), C.byref(h)))
+    try:
+        m = FjsphMesh()
+        check(L.fjsph_foam_view(h, C.byref(m)))
+        nv, nf, nc = int(m.n_verts), int(m.n_faces), int(m.n_cells)
+
+        def arr(ptr, ctype, shape):
+            n = int(np.prod(shape))
+            if n == 0:
+                return np.zeros(shape, dtype=np.dtype(ctype))
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).reshape(shape).copy()
+
+        face_ptr = arr(m.face_ptr, C.c_int64, (nf + 1,))
+        cell_ptr = arr(m.cell_ptr, C.c_int64, (nc + 1,))
+        return dict(verts=arr(m.verts, C.c_double, (nv, 3)), face_ptr=face_ptr,
+                    face_vtx=arr(m.face_vtx, C.c_int64, (int(face_ptr[-1]),)),
+                    leftright=arr(m.leftright, C.c_int32, (nf, 2)), cell_ptr=cell_ptr,
+                    cell_faces=arr(m.cell_faces, C.c_int64, (int(cell_ptr[-1]),)),
+                    cCentre=arr(m.cCentre, C.c_double, (nc, 3)), cVel=arr(m.cVel, C.c_double, (nc, 3)),
+                    cP=arr(m.cP, C.c_double, (nc,)), cRho=arr(m.cRho, C.c_double, (nc,)))
+    finally:
+        L.fjsph_foam_free(h)

@@ -235,6 +235,16 @@ int fjsph_slab_stats(FjsphEngine* e, int64_t* n_owned, int64_t* n_ghost, int64_t
 int fjsph_upload_owned(FjsphEngine* e, const FjsphStateView* s);
 int fjsph_set_owned(FjsphEngine* e, int64_t n_owned);
 
+/* OpenFOAM case ingestion (host only): FOAM::Read_FOAM for ASCII cases (reference src/FOAMIO.cpp:346-955) -- constant/
+ * polyMesh/{boundary,points,faces,owner,neighbour} and <solution_dir>/{p or p_rgh,U} -> the MESH arrays fjsph_upload_mesh
+ * takes: faces fanned into triangles, boundary markers -1 (wall patches) / -2 (other patches), the reference's cell
+ * centres.  The reference never fills cRho: it is set to rho_fill.  solution_dir NULL or "" = mesh only
+ * (zero velocity and pressure).  The view's pointers live as long as the FjsphFoamMesh. */
+typedef struct FjsphFoamMesh FjsphFoamMesh;
+int fjsph_foam_read(const char* foam_dir, const char* solution_dir, int buoyant, double rho_fill, FjsphFoamMesh** out);
+int fjsph_foam_view(const FjsphFoamMesh* m, FjsphMesh* view);
+void fjsph_foam_free(FjsphFoamMesh* m);
+
 /* Checkpoint / resume: a raw-binary mirror of the reference's <prefix>_particles.h5 restart data (H5IO.cpp:395-538,
  * 915-962; HDF5 is not available here): position, velocity, acceleration, pressure, density, density gradient, mass,
  * boundary condition, particle ID, cell ID, cell velocity / density / pressure under the reference's dataset names, the
