@@ -143,6 +143,7 @@ def lib():
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.c_int32
     L.fjsph_case_params.argtypes = [vp, P(FjsphParams)]
+    L.fjsph_case_foam.argtypes = [vp, C.c_char_p, C.c_char_p, P(C.c_int32), C.c_int32]
     L.fjsph_case_io.argtypes = [vp, P(C.c_int32), P(C.c_int64), C.c_char_p, C.c_char_p, C.c_int32]
     L.fjsph_case_block.argtypes = [vp, C.c_int32, P(FjsphBlock), C.c_char_p, C.c_int32]
     L.fjsph_case_state.argtypes = [vp, P(FjsphStateView)]

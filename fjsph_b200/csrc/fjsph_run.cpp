@@ -135,6 +135,21 @@ int main(int argc, char** argv)
     }
     else if (fjsph_read_restart(e, restart_file.c_str(), &frame))
         return fail("reading the restart file");
+    {
+        /* aero mesh named by the deck (FJSPH.cpp:70-100: FOAM::Read_FOAM), uploaded for the containment lookup */
+        char fdir[1024] = "", fsol[512] = "";
+        int32_t buoyant = 0;
+        fjsph_case_foam(c, fdir, fsol, &buoyant, 512);
+        if (fdir[0])
+        {
+            FjsphFoamMesh* fm = nullptr;
+            FjsphMesh view;
+            if (fjsph_foam_read(fdir, fsol, buoyant, P.rho_g, &fm) || fjsph_foam_view(fm, &view) || fjsph_upload_mesh(e, &view))
+                return fail("reading the OpenFOAM case");
+            std::printf("OpenFOAM mesh: %lld cells, %lld triangles\n", (long long)view.n_cells, (long long)view.n_faces);
+            fjsph_foam_free(fm);
+        }
+    }
     fjsph_get_params(e, &P);
     std::printf("Starting counts:\nBoundary: %lld  Sim: %lld\n\n", (long long)nb0, (long long)(fjsph_count(e) - nb0));
 

@@ -1406,6 +1406,8 @@ struct FjsphCase
     int max_frames = -1;            /* "SPH frame count" (IO.cpp:375) */
     long long max_points = -1;      /* "SPH maximum particle count" (IO.cpp:428) */
     std::string output_prefix, restart_prefix; /* IO.cpp:373,355 */
+    std::string foam_dir, foam_sol, tau_mesh;  /* IO.cpp:352,359-360 */
+    int foam_buoyant = 0;                      /* IO.cpp:364 */
     int64_t bound_points = 0;
     int n_bound_blocks = 0;
     std::vector<double> xi, v, rho, p, m;
@@ -1665,7 +1667,27 @@ extern "C" int fjsph_case_read(const char* para_path, int dim, FjsphCase** out)
             get_number(line, "SPH maximum particle count", c->max_points);
             get_string(line, "Output files prefix", c->output_prefix);
             get_string(line, "SPH restart prefix", c->restart_prefix);
+            get_string(line, "OpenFOAM input directory", c->foam_dir);
+            get_string(line, "OpenFOAM solution directory", c->foam_sol);
+            get_number(line, "OpenFOAM buoyant (0/1)", c->foam_buoyant);
+            get_string(line, "Primary grid face filename", c->tau_mesh);
         }
+    }
+    /* aero source, IO.cpp:464-499: a mesh named in the deck couples the aero model to it (meshInfl) */
+    if (!c->tau_mesh.empty())
+    {
+        fj_set_error("TAU NetCDF meshes (\"Primary grid face filename\") cannot be read here: NetCDF is not available; "
+                     "convert the case to OpenFOAM ascii or upload the mesh arrays with fjsph_upload_mesh");
+        return FJSPH_ERR_IO;
+    }
+    if (!c->foam_dir.empty())
+    {
+        if (c->foam_sol.empty())
+        {
+            fj_set_error("OpenFOAM solution directory not defined.");
+            return FJSPH_ERR_INVALID;
+        }
+        c->params.asource = 1;
     }
     st = fjsph_set_values(&c->params);
     if (st)
@@ -1725,6 +1747,19 @@ extern "C" int fjsph_case_io(const FjsphCase* c, int32_t* max_frames, int64_t* m
         std::snprintf(output_prefix, size_t(cap), "%s", c->output_prefix.c_str());
     if (restart_prefix && cap > 0)
         std::snprintf(restart_prefix, size_t(cap), "%s", c->restart_prefix.c_str());
+    return FJSPH_OK;
+}
+// the OpenFOAM case the deck couples to ("" when it names none): hand it to fjsph_foam_read, then fjsph_upload_mesh
+extern "C" int fjsph_case_foam(const FjsphCase* c, char* foam_dir, char* solution_dir, int32_t* buoyant, int32_t cap)
+{
+    if (!c)
+        return FJSPH_ERR_INVALID;
+    if (foam_dir && cap > 0)
+        std::snprintf(foam_dir, size_t(cap), "%s", c->foam_dir.c_str());
+    if (solution_dir && cap > 0)
+        std::snprintf(solution_dir, size_t(cap), "%s", c->foam_sol.c_str());
+    if (buoyant)
+        *buoyant = c->foam_buoyant;
     return FJSPH_OK;
 }
 extern "C" int fjsph_case_params(const FjsphCase* c, FjsphParams* out)

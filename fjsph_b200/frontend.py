@@ -49,7 +49,10 @@ def read_case(para_path: str, dim: int = 3) -> dict:
                 blk["back"] = np.ctypeslib.as_array(C.cast(B.back, C.POINTER(C.c_int64)), shape=(nb,)).copy()
                 blk["buffer"] = np.ctypeslib.as_array(C.cast(B.buffer, C.POINTER(C.c_int64)), shape=(nb, nf)).copy()
             blocks.append(blk)
-        out.update(bound_points=int(L.fjsph_case_bound_points(h)), params=params, blocks=blocks, dim=dim)
+        fdir, fsol, buoy = C.create_string_buffer(1024), C.create_string_buffer(1024), C.c_int32()
+        check(L.fjsph_case_foam(h, fdir, fsol, C.byref(buoy), 1024))
+        out.update(bound_points=int(L.fjsph_case_bound_points(h)), params=params, blocks=blocks, dim=dim,
+                   foam=(fdir.value.decode(), fsol.value.decode(), int(buoy.value)))
         return out
     finally:
         L.fjsph_case_free(h)

@@ -273,6 +273,9 @@ int32_t fjsph_case_dim(const FjsphCase* c);
 int fjsph_case_params(const FjsphCase* c, FjsphParams* out);               /* after Set_Values */
 /* run control of the frame loop (FJSPH.cpp:262-330): "SPH frame count", "SPH maximum particle count" (-1 when the deck
  * does not set them), "Output files prefix", "SPH restart prefix" */
+/* "OpenFOAM input directory" / "OpenFOAM solution directory" / "OpenFOAM buoyant (0/1)" of the deck ("" when it names
+ * no mesh; naming one sets params.asource = meshInfl, IO.cpp:464-499) */
+int fjsph_case_foam(const FjsphCase* c, char* foam_dir, char* solution_dir, int32_t* buoyant, int32_t cap);
 int fjsph_case_io(const FjsphCase* c, int32_t* max_frames, int64_t* max_points, char* output_prefix, char* restart_prefix,
                   int32_t cap);
 int fjsph_case_block(const FjsphCase* c, int32_t i, FjsphBlock* out, char* name, int32_t name_cap); /* LIMITS[i]; the

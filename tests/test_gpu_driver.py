@@ -46,6 +46,17 @@ def test_driver_runs_a_deck_and_resumes(tmp_path):
     assert np.array_equal(resumed[:, 11], last[:, 11])           # same particles, same order
     assert np.abs(resumed[:, :3] - last[:, :3]).max() <= 1e-9 * 0.05  # positions, relative to the droplet radius
     assert (tmp_path / "part_frame.info").read_text().count("Frame:") == 4
+    # the same deck coupled to an OpenFOAM case whose solution is the uniform free stream: the containment lookup
+    # (FindCell on the device) must hand every particle the free-stream values, i.e. the frames of the constant-velocity run
+    from tests.foam_case import write_case
+
+    write_case(tmp_path / "foam", (-0.1013, -0.1007, -0.1011), (0.1009, 0.1003, 0.1017), (6, 7, 5),
+               lambda c: (0.0, 21.55, 0.0), lambda c: 100000.0)
+    para.write_text(para.read_text() + " OpenFOAM input directory: foam\n OpenFOAM solution directory: 100\n")
+    out4 = run("--out", "mesh")
+    assert out4.returncode == 0 and "OpenFOAM mesh: 210 cells, 1474 triangles" in out4.stdout, out4.stdout[-2000:]
+    coupled = frame(tmp_path / "mesh_frame_00003.dat")
+    assert np.array_equal(coupled[:, 11], last[:, 11]) and np.abs(coupled[:, :6] - last[:, :6]).max() == 0.0
     # errors are messages and exit codes, never a crash
     bad = subprocess.run([BIN, str(tmp_path / "nope.para")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert bad.returncode == 1 and "could not open" in bad.stdout
