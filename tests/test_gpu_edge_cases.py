@@ -1,0 +1,107 @@
+"""Edge cases of the neighbour build and the step against the CPU oracle: isolated particles, pairs on the support
+edge (strict `<`, Neighbours.cpp:15-47), neighbour counts far above the default list capacity (both lists grow and the
+build retries), ragged cells, and a case with no fluid at all."""
+import numpy as np
+import pytest
+
+from fjsph_b200 import cases
+from tests.util import assert_fields_close, make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def tiny_case(xi, dx):
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    n = xi.shape[0]
+    return dict(xi=xi, v=np.zeros_like(xi), rho=np.full(n, 1000.0), p=np.zeros(n), m=np.full(n, 1000.0 * dx**3),
+                b=np.full(n, cases.FREE, dtype=np.int32), bound_points=0,
+                params=dict(particle_step=dx, rho_rest=1000.0, speed_sound=100.0, delta_t_min=1e-9))
+
+
+def same_lists(o, e):
+    off_o, idx_o, _ = o.neighbours()
+    off_e, idx_e = e.neighbours()
+    return np.array_equal(off_o, off_e) and np.array_equal(idx_o, idx_e)
+
+
+def test_single_particle_and_isolated_pair():
+    o, e, _ = make_pair(tiny_case([[0.0, 0.0, 0.0]], 1e-3))
+    o.update_neighbours()
+    e.update_neighbours()
+    assert same_lists(o, e) and e.neighbour_counts().tolist() == [1]  # the list of the reference holds the particle itself
+    so = o.integrate()[1]
+    se = e.integrate()
+    assert se.iterations == so.iterations and se.dt == so.dt
+    assert_fields_close(e, o, ("xi", "v", "rho", "acc", "Rrho", "lam", "surf"), context="single particle")
+    # two particles far outside each other's support: two lists of one
+    o, e, _ = make_pair(tiny_case([[0.0, 0.0, 0.0], [0.05, 0.0, 0.0]], 1e-3))
+    o.update_neighbours()
+    e.update_neighbours()
+    assert same_lists(o, e) and e.neighbour_counts().tolist() == [1, 1]
+
+
+def test_support_edge_is_exclusive():
+    """H = 2 dx = 1.0 exactly, sr = 4 H^2 = 4.0: a partner at distance exactly 2.0 is NOT a neighbour (d2 < sr), one ulp
+    closer is."""
+    dx = 0.5
+    for x1, expect in ((2.0, [1, 1]), (np.nextafter(2.0, 0.0), [2, 2]), (np.nextafter(2.0, 3.0), [1, 1])):
+        o, e, p = make_pair(tiny_case([[0.0, 0.0, 0.0], [x1, 0.0, 0.0]], dx))
+        assert p.sr == 4.0
+        o.update_neighbours()
+        e.update_neighbours()
+        assert same_lists(o, e), x1
+        assert e.neighbour_counts().tolist() == expect, x1
+
+
+def test_lists_grow_past_their_default_capacity():
+    """A block compressed to 0.62 of the nominal spacing holds ~1100 neighbours per particle, against a default exact-list
+    capacity of 288 and a superset capacity of ~416: both builds overflow, re-allocate and retry; the sets stay exact."""
+    dx = 1e-3
+    case = cases.synthetic_block((13, 12, 11), dx, jitter=0.1, seed=5)
+    case["xi"] = case["xi"] * 0.62
+    o, e, _ = make_pair(case)
+    o.update_neighbours()
+    e.update_neighbours()
+    counts = e.neighbour_counts()
+    assert counts.max() > 900
+    assert same_lists(o, e)
+    npd_o, npd_e = o.prestep(), e.dSPH_PreStep()
+    assert abs(npd_e - npd_o) <= 1e-10 * abs(npd_o)
+    assert_fields_close(e, o, ("L", "gradRho", "kernsum", "lam"), context="dense block prestep")
+    # ... and shrink back to ordinary lists when the particles spread out again
+    e.upload_level(1, xi=case["xi"] / 0.62)
+    o.set("xi", case["xi"] / 0.62)
+    o.update_neighbours()
+    e.update_neighbours()
+    assert same_lists(o, e) and e.neighbour_counts().max() < 300
+
+
+def test_ragged_cells_and_clusters():
+    """Three clusters of very different density far apart on a sparse cell grid, plus stragglers: empty cells, cells with
+    one particle and cells with a hundred and more."""
+    rng = np.random.default_rng(11)
+    dx = 1e-3
+    a = cases.lattice((9, 8, 7), dx, jitter=0.2, seed=1)
+    b = cases.lattice((6, 6, 6), 0.7 * dx, start=(0.05, 0.0, 0.01), jitter=0.2, seed=2)
+    c = cases.lattice((5, 4, 3), 1.6 * dx, start=(0.0, 0.04, 0.03), jitter=0.2, seed=3)
+    stray = rng.uniform(0.0, 0.06, size=(25, 3))
+    xi = np.concatenate([a, b, c, stray])
+    o, e, _ = make_pair(tiny_case(xi[rng.permutation(len(xi))], dx))
+    o.update_neighbours()
+    e.update_neighbours()
+    assert same_lists(o, e)
+    counts = e.neighbour_counts()
+    assert counts.min() == 1 and counts.max() > 200
+
+
+def test_walls_only_case_steps_without_fluid():
+    """No fluid particle at all: Integrator::integrate returns early (Integration.cpp:244-246); the engine must not
+    divide by the zero fluid count or launch empty grids."""
+    case = cases.box_with_walls(n=(5, 4, 4), dx=0.01, layers=2, jitter=0.05)
+    nb = case["bound_points"]
+    walls = {k: (v[:nb] if isinstance(v, np.ndarray) and v.shape[:1] == case["xi"].shape[:1] else v) for k, v in case.items()}
+    walls["bound_points"] = nb
+    o, e, _ = make_pair(walls)
+    se = e.integrate()
+    got = e.download(("xi", "v", "rho"))
+    assert np.array_equal(got["xi"], walls["xi"]) and np.isfinite(got["rho"]).all() and se.total_points == nb
