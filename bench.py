@@ -297,13 +297,21 @@ def main():
         traffic = float(tr["dram_bytes_per_particle"]) * n_fluid
     except (OSError, ValueError, KeyError):
         pass
+    fp64_peak, fp64_src = FP64_NOMINAL_TFLOPS, "nominal (148 SM x 64 DFMA/clk x 1.965 GHz)"
+    try:
+        fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["fp64_tflops"])
+        fp64_src = "measured (profiles/fp64_peak.json, tools/fp64_peak.cu)"
+    except (OSError, ValueError, KeyError):
+        pass
+    fp64_achieved = FORCE_FLOP_PER_PAIR * pairs / (force_ms * 1e-3) / 1e12 if force_ms > 0 else 0.0
     roofline = {
         "kernel": "k_force (get_acc_and_Rrho, Resid.cpp:243-469)", "bound": "hbm", "achieved": achieved,
         "peak": hbm_peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback", "unit": "GB/s",
         "frac": achieved / hbm_peak, "traffic": traffic, "ms_per_launch": force_ms,
         "algorithmic_bytes_per_launch": FORCE_BYTES_PER_PARTICLE * n_fluid,
-        "fp64": {"achieved_tflops": FORCE_FLOP_PER_PAIR * pairs / (force_ms * 1e-3) / 1e12 if force_ms > 0 else 0.0,
-                 "nominal_peak_tflops": FP64_NOMINAL_TFLOPS, "flop_per_pair": FORCE_FLOP_PER_PAIR, "pairs": pairs,
+        "fp64": {"achieved_tflops": fp64_achieved, "peak_tflops": fp64_peak, "peak_source": fp64_src,
+                 "frac": fp64_achieved / fp64_peak, "nominal_peak_tflops": FP64_NOMINAL_TFLOPS,
+                 "flop_per_pair": FORCE_FLOP_PER_PAIR, "pairs": pairs,
                  "note": "the pair sweeps are FP64-pipe bound (SURVEY.md 8d), the HBM figure is the yardstick north_star names"},
         "step_hbm_frac": (value / max(1, world)) * STEP_BYTES_PER_PARTICLE / 1e9 / hbm_peak,
     }
