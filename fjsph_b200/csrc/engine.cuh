@@ -104,6 +104,8 @@ struct Slab
     bool hold = false;        // set around the interior launches: KScope does not wait
     int64_t n_interior = 0;   // multiple of 32 (whole list warps)
     long long overlapped = 0; // exchanges that ran beside an interior sweep
+    // owned particles to drop at the next re-decomposition (escaped from the aero mesh): flags by CALLER index
+    const unsigned* del_by_caller = nullptr;
 };
 
 // aero mesh on the device (mesh.cu): per-face vertex coordinates, boundary markers, cell -> faces, cell centres and

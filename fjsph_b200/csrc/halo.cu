@@ -34,17 +34,20 @@ size_t level_bytes(size_t cnt)
     return off;
 }
 
+// del_by_caller (may be null): particles flagged there belong to no class and vanish with the re-decomposition
 __global__ void k_classify(const double4* __restrict__ P0, int n_owned, double x_lo, double x_hi,
+                           const unsigned* __restrict__ del_by_caller, const int* __restrict__ oidx,
                            unsigned* __restrict__ f_stay, unsigned* __restrict__ f_lo, unsigned* __restrict__ f_hi)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_owned)
         return;
     const double x = P0[i].x;
+    const unsigned keep = (del_by_caller && del_by_caller[oidx[i]]) ? 0u : 1u;
     const unsigned lo = x < x_lo, hi = !(x < x_hi);
-    f_lo[i] = lo;
-    f_hi[i] = hi && !lo;
-    f_stay[i] = !(lo || hi);
+    f_lo[i] = keep & lo;
+    f_hi[i] = keep & (hi && !lo);
+    f_stay[i] = keep & !(lo || hi);
 }
 
 __global__ void k_ghost_flags(const double4* __restrict__ P0, int n_owned, double x_ghost_lo, double x_ghost_hi,
@@ -338,7 +341,8 @@ int fj_redecompose(FjsphEngine* e)
     // ---- 1. classify the owned particles of pnp1 by slab, compact the three classes in slot order
     {
         KScope ks(e, "slab_classify", 8);
-        k_classify<<<fj_blocks(n0, TPB), TPB, 0, st_>>>(e->lv[1].P0, n0, S.x_lo, S.x_hi, S.flag[0], S.flag[1], S.flag[2]);
+        k_classify<<<fj_blocks(n0, TPB), TPB, 0, st_>>>(e->lv[1].P0, n0, S.x_lo, S.x_hi, S.del_by_caller, e->oidx, S.flag[0],
+                                                        S.flag[1], S.flag[2]);
         for (int c = 0; c < 3; ++c)
         {
             prim_exclusive_scan(st_, S.flag[c], S.scan[c], unsigned(n0), S.scan_tmp);
@@ -349,6 +353,7 @@ int fj_redecompose(FjsphEngine* e)
     for (int c = 0; c < 3; ++c)
         FJ_CUDA(cudaMemcpyAsync(&h_cnt[c], S.scan[c] + n0, sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
     FJ_CUDA(cudaStreamSynchronize(st_));
+    S.del_by_caller = nullptr; /* consumed */
     const int64_t n_stay = h_cnt[0];
     int64_t mig_send[2] = {has_lo ? int64_t(h_cnt[1]) : 0, has_hi ? int64_t(h_cnt[2]) : 0}, mig_recv[2];
     if ((!has_lo && h_cnt[1]) || (!has_hi && h_cnt[2]))

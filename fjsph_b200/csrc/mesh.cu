@@ -519,11 +519,7 @@ int fj_aero_velocity_mesh(FjsphEngine* e)
         fj_set_error("aero source meshInfl needs a mesh: call fjsph_upload_mesh first");
         return FJSPH_ERR_STATE;
     }
-    if (e->slab.on && e->slab.world > 1)
-    {
-        fj_set_error("mesh containment with slab decomposition is not available yet");
-        return FJSPH_ERR_INVALID;
-    }
+    const bool slabs = e->slab.on && e->slab.world > 1;
     const int n = int(e->n_owned);
     unsigned* d_del = reinterpret_cast<unsigned*>(e->key);
     FJ_CUDA(cudaMemsetAsync(d_del, 0, size_t(n) * sizeof(unsigned), e->stream));
@@ -537,6 +533,29 @@ int fj_aero_velocity_mesh(FjsphEngine* e)
     int h_cnt[4];
     FJ_CUDA(cudaMemcpyAsync(h_cnt, D.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     FJ_CUDA(cudaStreamSynchronize(e->stream));
+    if (slabs)
+    {
+        /* Slab decomposition (the mesh is replicated, every rank looks its own particles up): the ranks erase together.
+           The escaped particles are handed to the re-decomposition, which drops them while it re-makes the owned and
+           ghost sets and the global counts; then, as on one GPU, the lists and the prestep are redone. */
+        double any = double(h_cnt[0]);
+        int st = fj_allreduce(e, FJSPH_COMM_SUM, &any, 1);
+        if (st)
+            return st;
+        if (any > 0.0)
+        {
+            e->mesh_deleted += h_cnt[0];
+            e->slab.del_by_caller = d_del; /* e->key is not written again before fj_redecompose has read it */
+            e->skin_valid = false;
+            st = fj_build_neighbours(e);
+            if (st)
+                return st;
+            st = fj_prestep(e, nullptr); /* the caller exchanges the prestep's ghost fields next (frozen_terms) */
+            if (st)
+                return st;
+        }
+        return FJSPH_OK;
+    }
     if (h_cnt[0] > 0)
     {
         int n_del = 0;
@@ -562,6 +581,16 @@ int fj_pipe_outlet_mesh(FjsphEngine* e)
     {
         fj_set_error("aero source meshInfl needs a mesh: call fjsph_upload_mesh first");
         return FJSPH_ERR_STATE;
+    }
+    if (e->slab.on && e->slab.world > 1)
+    {
+        for (size_t bl = size_t(e->n_bound_blocks); bl < e->blocks.size(); ++bl)
+            if (e->blocks[bl].aeroconst != 9999999.0)
+            {
+                fj_set_error("pipe blocks with an aero entry plane are not available with slab decomposition yet");
+                return FJSPH_ERR_INVALID;
+            }
+        return FJSPH_OK;
     }
     const int n = int(e->n_owned);
     unsigned* d_del = reinterpret_cast<unsigned*>(e->key);
