@@ -191,7 +191,7 @@ namespace
 {
 constexpr int TPB = 256;
 
-__global__ void k_init_level(Level S, DevConst C, double cellRho, double cellP, int n)
+__global__ void k_init_level(Level S, const int* __restrict__ oidx, DevConst C, double cellRho, double cellP, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -211,7 +211,7 @@ __global__ void k_init_level(Level S, DevConst C, double cellRho, double cellP, 
     S.TH[i] = make_double4(0.0, 1.0, 0.0, cellRho);
     S.SC[i] = z;
     S.L0[i] = S.L1[i] = S.L2[i] = S.L3[i] = S.L4[i] = S.L5[i] = S.L6[i] = S.L7[i] = S.L8[i] = 0.0;
-    S.part_id[i] = i;
+    S.part_id[i] = oidx[i]; /* the caller's index of the particle in slot i */
     S.cellID[i] = -3; /* c_no_cell, VarDefs.h:197 */
     S.b[i] = 0;
     S.surfzone[i] = 0;
@@ -866,17 +866,26 @@ int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_po
     }
     const bool keep_blocks = !e->blocks.empty() && e->blocks.back().second == s->n && e->n == s->n &&
                              e->bound_points == bound_points;
+    /* A host that round-trips the SAME particle set every step (fjsph_step_host) keeps the engine's cell order and its
+       superset neighbour list: the uploaded values land in the slots the particles already occupy (slot_of), and the
+       next neighbour build decides from the displacements against the list's reference positions whether the list
+       still holds -- exactly as for device-resident state.  Anything else (another count, other blocks, slab mode, no
+       list yet) resets the slots to the caller's order and drops the list. */
+    const bool keep_order = keep_blocks && e->skin_valid && e->skin_n == s->n && e->n_owned == s->n && !e->slab.on;
     e->n = s->n;
     e->n_owned = s->n;
     e->bound_points = bound_points;
     e->list_valid = false;
-    e->skin_valid = false; /* slots are reset to the caller's order below */
     e->next_part_id = s->n;
     e->inlet_tables_dirty = true;
     const int n = int(e->n);
     e->launches += 2;
-    k_identity_index<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->oidx, e->slot_of, n);
-    k_init_level<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], e->C, e->P.rho_g, e->P.p_ref, n);
+    if (!keep_order)
+    {
+        e->skin_valid = false;
+        k_identity_index<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->oidx, e->slot_of, n);
+    }
+    k_init_level<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], e->oidx, e->C, e->P.rho_g, e->P.p_ref, n);
     FJ_CUDA(cudaGetLastError());
     int st = upload_fields(e, 1, s);
     if (st)
