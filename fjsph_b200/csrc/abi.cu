@@ -559,7 +559,9 @@ int stage_layout(FjsphEngine* e, const FjsphStateView* s, StageView* dv, std::ve
     return FJSPH_OK;
 }
 
-int upload_fields(FjsphEngine* e, int level, const FjsphStateView* s)
+// host arrays -> the device staging buffer (one H2D copy per field), then k_pack scatters them into the slots of a level.
+// both_levels: the same staged data go into pn and pnp1 (one trip over PCIe, two scatters on the device).
+int upload_fields(FjsphEngine* e, int level, const FjsphStateView* s, bool both_levels = false)
 {
     StageView dv;
     std::vector<std::pair<void*, void*>> copies;
@@ -570,8 +572,10 @@ int upload_fields(FjsphEngine* e, int level, const FjsphStateView* s)
     for (size_t k = 0; k < copies.size(); ++k)
         FJ_CUDA(cudaMemcpyAsync(copies[k].second, copies[k].first, sizes[k], cudaMemcpyHostToDevice, e->stream));
     const int n = int(s->n);
-    e->launches++;
+    e->launches += both_levels ? 2 : 1;
     k_pack<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[level], dv, e->slot_of, n);
+    if (both_levels)
+        k_pack<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1 - level], dv, e->slot_of, n);
     FJ_CUDA(cudaGetLastError());
     return FJSPH_OK;
 }
@@ -931,13 +935,10 @@ int fjsph_upload_owned(FjsphEngine* e, const FjsphStateView* s)
                      (long long)e->n_owned);
         return FJSPH_ERR_INVALID;
     }
-    for (int level = 0; level < 2; ++level)
-    {
-        int st = upload_fields(e, level, s);
-        if (st)
-            return st;
-        FJ_CUDA(cudaStreamSynchronize(e->stream)); /* the staging buffer is reused */
-    }
+    int st = upload_fields(e, 1, s, true);
+    if (st)
+        return st;
+    FJ_CUDA(cudaStreamSynchronize(e->stream)); /* the host arrays and the staging buffer are free again */
     e->list_valid = false;
     return fj_halo_exchange(e, 1, FJ_HX_P0 | FJ_HX_P1 | FJ_HX_P2 | FJ_HX_TH);
 }
