@@ -298,6 +298,8 @@ bool fj_has_inlets(FjsphEngine* e);
 int fj_inlet_motion(FjsphEngine* e, double dt, bool nb_solver, int* n_partials);
 int fj_update_data(FjsphEngine* e, int* n_add, int* n_del);
 int fj_delete_flagged(FjsphEngine* e, unsigned* d_del_by_caller, bool both_levels, int* n_del);
+/* slab re-decomposition: the inlet tables (caller indices) follow their particles into the compacted order */
+int fj_inlet_tables_remap(FjsphEngine* e, const unsigned* d_stay_flag, const unsigned* d_stay_scan);
 // aero-mesh containment (mesh.cu)
 int fj_aero_velocity_mesh(FjsphEngine* e);
 int fj_pipe_outlet_mesh(FjsphEngine* e);

@@ -354,6 +354,9 @@ int fj_redecompose(FjsphEngine* e)
         FJ_CUDA(cudaMemcpyAsync(&h_cnt[c], S.scan[c] + n0, sizeof(unsigned), cudaMemcpyDeviceToHost, st_));
     FJ_CUDA(cudaStreamSynchronize(st_));
     S.del_by_caller = nullptr; /* consumed */
+    st = fj_inlet_tables_remap(e, S.flag[0], S.scan[0]); /* inlet tables hold caller indices: they follow the stayers */
+    if (st)
+        return st;
     const int64_t n_stay = h_cnt[0];
     int64_t mig_send[2] = {has_lo ? int64_t(h_cnt[1]) : 0, has_hi ? int64_t(h_cnt[2]) : 0}, mig_recv[2];
     if ((!has_lo && h_cnt[1]) || (!has_hi && h_cnt[2]))
@@ -562,6 +565,12 @@ extern "C" int fjsph_set_slab(FjsphEngine* e, int32_t rank, int32_t world, doubl
         return st;
     S.n_fluid_global = v[0];
     S.n_total_global = v[1];
+    /* ids of particles an inlet adds later must be unique over all ranks: count from the global total */
+    double ids = double(e->next_part_id);
+    st = fj_allreduce(e, FJSPH_COMM_SUM, &ids, 1);
+    if (st)
+        return st;
+    e->next_part_id = (long long)ids;
     return FJSPH_OK;
 }
 

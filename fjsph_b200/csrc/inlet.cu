@@ -262,6 +262,28 @@ __global__ void k_map_callers(const unsigned* __restrict__ scan_by_caller, int* 
         idx[k] -= int(scan_by_caller[idx[k]]);
 }
 
+// re-decomposition: caller index -> slot -> position among the stayers (the new caller index); bad counts the
+// table entries whose particle is leaving the slab
+__global__ void k_remap_callers(const int* __restrict__ slot_of, const unsigned* __restrict__ stay_flag,
+                                const unsigned* __restrict__ stay_scan, int* __restrict__ idx, int cnt, int* __restrict__ bad)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt)
+        return;
+    const int s = slot_of[idx[k]];
+    if (!stay_flag[s])
+        atomicAdd(bad, 1);
+    idx[k] = int(stay_scan[s]);
+}
+__global__ void k_count_flags(const unsigned* __restrict__ f, int n, int* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned v = (i < n) ? f[i] : 0u;
+    const unsigned m = __ballot_sync(0xffffffffu, v != 0u);
+    if ((threadIdx.x & 31) == 0 && m)
+        atomicAdd(out, __popc(m));
+}
+
 struct InletTables
 {
     // device copies of back / buffer (caller indices) of every inlet block, refreshed when they change
@@ -295,6 +317,57 @@ static int upload_tables(FjsphEngine* e)
         FJ_CUDA(cudaStreamSynchronize(e->stream));
     }
     e->inlet_tables_dirty = false;
+    return FJSPH_OK;
+}
+
+static int download_tables(FjsphEngine* e, HostBlock& B)
+{
+    const int nb = int(B.back.size()), nf = int(B.buffer[0].size());
+    std::vector<int> hb(nb), hf(size_t(nb) * nf);
+    FJ_CUDA(cudaMemcpyAsync(hb.data(), B.d_back, nb * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaMemcpyAsync(hf.data(), B.d_buffer, size_t(nb) * nf * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < nb; ++i)
+    {
+        B.back[i] = hb[i];
+        for (int j = 0; j < nf; ++j) B.buffer[i][j] = hf[size_t(i) * nf + j];
+    }
+    return FJSPH_OK;
+}
+
+int fj_inlet_tables_remap(FjsphEngine* e, const unsigned* d_stay_flag, const unsigned* d_stay_scan)
+{
+    if (!fj_has_inlets(e))
+        return FJSPH_OK;
+    if (e->inlet_tables_dirty)
+    {
+        int st = upload_tables(e);
+        if (st)
+            return st;
+    }
+    FJ_CUDA(cudaMemsetAsync(e->d_flag + 1, 0, sizeof(int), e->stream));
+    for (size_t bl = size_t(e->n_bound_blocks); bl < e->blocks.size(); ++bl)
+    {
+        HostBlock& B = e->blocks[bl];
+        if (B.block_type != FJSPH_INLET_ZONE || B.back.empty())
+            continue;
+        const int nb = int(B.back.size()), nf = int(B.buffer[0].size());
+        k_remap_callers<<<fj_blocks(nb, TPB), TPB, 0, e->stream>>>(e->slot_of, d_stay_flag, d_stay_scan, B.d_back, nb, e->d_flag + 1);
+        k_remap_callers<<<fj_blocks(nb * nf, TPB), TPB, 0, e->stream>>>(e->slot_of, d_stay_flag, d_stay_scan, B.d_buffer, nb * nf,
+                                                                        e->d_flag + 1);
+        e->launches += 2;
+        int st = download_tables(e, B);
+        if (st)
+            return st;
+    }
+    FJ_CUDA(cudaMemcpyAsync(e->h_flag + 1, e->d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->h_flag[1] != 0)
+    {
+        fj_set_error("slab %d: %d BACK / BUFFER particle(s) of an inlet block crossed a slab face; an inlet's buffer region "
+                     "must lie inside one slab", e->slab.rank, e->h_flag[1]);
+        return FJSPH_ERR_STATE;
+    }
     return FJSPH_OK;
 }
 
@@ -445,13 +518,15 @@ int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
     cudaStream_t st_ = e->stream;
     bool any_delete_plane = false;
     for (size_t bl = size_t(nbb); bl < e->blocks.size(); ++bl) any_delete_plane |= e->blocks[bl].delconst != 9999999.0;
-    if (!fj_has_inlets(e) && !any_delete_plane)
+    /* Slab decomposition: every rank carries the same block list (the tables of an inlet block only on the rank that
+       holds its buffer region), so the ranks agree on whether this bookkeeping runs and meet at its all-reduces.  The
+       reference's particle ORDER has no meaning across ranks: new particles are appended behind the owned ones, the
+       ghosts are dropped, erased particles vanish with the forced re-decomposition that follows. */
+    const bool slabs = e->slab.on && e->slab.world > 1;
+    bool any_inlet_block = false;
+    for (size_t bl = size_t(nbb); bl < e->blocks.size(); ++bl) any_inlet_block |= e->blocks[bl].block_type == FJSPH_INLET_ZONE;
+    if (!(slabs ? any_inlet_block : fj_has_inlets(e)) && !any_delete_plane)
         return FJSPH_OK;
-    if (e->slab.on && e->slab.world > 1)
-    {
-        fj_set_error("inlet insertion / delete planes are not available with slab decomposition yet");
-        return FJSPH_ERR_INVALID;
-    }
     if (e->inlet_tables_dirty)
     {
         int st = upload_tables(e);
@@ -529,14 +604,24 @@ int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
             new_xyz.push_back(h_src[k].x - e->P.dx * B.insert_norm[0]);
             new_xyz.push_back(h_src[k].y - e->P.dx * B.insert_norm[1]);
             new_xyz.push_back(h_src[k].z - e->P.dx * B.insert_norm[2]);
-            new_caller.push_back(int(B.second));
             new_blk.push_back(int(bl));
+            if (slabs)
+            {
+                /* appended behind the owned particles; the ids come from the global counter below */
+                const int64_t c = e->n_owned + int64_t(new_caller.size());
+                new_caller.push_back(int(c));
+                B.buffer[ii].back() = c;
+                continue;
+            }
+            new_caller.push_back(int(B.second));
             new_pid.push_back(e->next_part_id++);
             B.buffer[ii].back() = B.second;
             B.second++;
             block_add++;
         }
         e->inlet_tables_dirty = true;
+        if (slabs)
+            continue;
         total_shift += block_add;
         if (shifts.n < 66)
         {
@@ -547,10 +632,32 @@ int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
         }
     }
     const int n_add = int(new_caller.size());
+    double n_add_global = n_add;
+    if (slabs)
+    {
+        /* globally unique particle ids: rank r takes [next + sum_{q<r} adds_q, ...) */
+        std::vector<double> adds(size_t(e->slab.world), 0.0);
+        adds[size_t(e->slab.rank)] = n_add;
+        int st = fj_allreduce(e, FJSPH_COMM_SUM, adds.data(), e->slab.world);
+        if (st)
+            return st;
+        long long before = 0, total = 0;
+        for (int r = 0; r < e->slab.world; ++r)
+        {
+            if (r < e->slab.rank)
+                before += (long long)adds[size_t(r)];
+            total += (long long)adds[size_t(r)];
+        }
+        for (int k = 0; k < n_add; ++k) new_pid.push_back(e->next_part_id + before + k);
+        e->next_part_id += total;
+        n_add_global = double(total);
+    }
     if (!to_pipe.empty())
     {
         KScope ks(e, "inlet_insert", 5);
-        const int n_old = int(e->n);
+        /* slab mode: the new particles take the slots behind the OWNED ones; this rank's ghosts are dropped, which is
+           safe because an insertion anywhere makes every rank re-decompose below */
+        const int n_old = slabs ? int(e->n_owned) : int(e->n);
         /* flags first (slot_of still in the old numbering) */
         int* d_a = reinterpret_cast<int*>(e->stage);
         const size_t m = to_pipe.size();
@@ -575,9 +682,10 @@ int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
             /* copy from the sources through the OLD slot_of, then renumber the callers */
             k_insert<<<fj_blocks(n_add, TPB), TPB, 0, st_>>>(S, e->oidx, e->blk, e->slot_of, d_src, d_xyz, d_newc, d_newb, d_pid,
                                                              n_old, n_add, e->C);
-            k_shift_oidx<<<fj_blocks(n_old, TPB), TPB, 0, st_>>>(e->oidx, n_old, shifts);
-            e->n += n_add;
+            if (!slabs)
+                k_shift_oidx<<<fj_blocks(n_old, TPB), TPB, 0, st_>>>(e->oidx, n_old, shifts);
             e->n_owned += n_add;
+            e->n = slabs ? e->n_owned : e->n + n_add;
             k_fill_slot_of<<<fj_blocks(e->n, TPB), TPB, 0, st_>>>(e->oidx, int(e->n), e->slot_of);
         }
         FJ_CUDA(cudaGetLastError());
@@ -600,18 +708,50 @@ int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
             T.nz[f] = B.delete_norm[2];
             T.c[f] = B.delconst;
         }
-        const int n = int(e->n);
+        const int n = slabs ? int(e->n_owned) : int(e->n);
         unsigned* d_del = reinterpret_cast<unsigned*>(e->key);       /* [cap] scratch, by caller index */
         unsigned* d_scan = e->rank_in_cell;                           /* [cap] */
         {
             KScope ks(e, "delete_plane", 4);
             k_fix_rho_and_flag_deleted<<<fj_blocks(n, TPB), TPB, 0, st_>>>(S, e->blk, e->oidx, n, T, e->C, d_del);
         }
-        if (any_delete_plane)
+        if (any_delete_plane && !slabs)
         {
             int st = fj_delete_flagged(e, d_del, false, &n_del); /* pn = pnp1 follows (Integration.cpp:220-223) */
             if (st)
                 return st;
+        }
+        if (slabs)
+        {
+            double dels = 0.0;
+            if (any_delete_plane)
+            {
+                FJ_CUDA(cudaMemsetAsync(e->d_flag + 1, 0, sizeof(int), st_));
+                k_count_flags<<<fj_blocks(n, TPB), TPB, 0, st_>>>(d_del, n, e->d_flag + 1);
+                e->launches++;
+                FJ_CUDA(cudaMemcpyAsync(e->h_flag + 1, e->d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st_));
+                FJ_CUDA(cudaStreamSynchronize(st_));
+                dels = double(e->h_flag[1]);
+            }
+            int st = fj_allreduce(e, FJSPH_COMM_SUM, &dels, 1);
+            if (st)
+                return st;
+            *n_add_out = int(n_add_global);
+            *n_del_out = int(dels);
+            if (n_add_global > 0.0 || dels > 0.0)
+            {
+                /* all ranks re-decompose together: erased particles belong to no class of its compaction, the ghost sets
+                   (dropped above) and the global counts are re-made */
+                if (dels > 0.0)
+                    e->slab.del_by_caller = d_del;
+                e->skin_valid = false;
+                e->list_valid = false;
+                st = fj_copy_level(e, 0, 1); /* pn = pnp1 before the particles move ranks (Integration.cpp:220-223) */
+                if (st)
+                    return st;
+                return fj_build_neighbours(e);
+            }
+            return FJSPH_OK;
         }
     }
     *n_add_out = n_add;

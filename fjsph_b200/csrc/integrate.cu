@@ -446,11 +446,6 @@ int check_supported(FjsphEngine* e)
         fj_set_error("more than 64 boundary blocks are not supported");
         return FJSPH_ERR_INVALID;
     }
-    if (e->slab.on && e->slab.world > 1 && fj_has_inlets(e))
-    {
-        fj_set_error("inlet blocks are not available with slab decomposition yet");
-        return FJSPH_ERR_INVALID;
-    }
     return FJSPH_OK;
 }
 

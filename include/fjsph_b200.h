@@ -215,6 +215,10 @@ int fjsph_set_skin(FjsphEngine* e, double skin_over_dx);
  *   op FJSPH_COMM_SENDRECV_DEV_ASYNC : the same on device pointers, but ordered on the engine's COMM stream
  *      (fjsph_slab_comm_stream) instead of its main stream: the forward halo exchanges run there while the main
  *      stream sweeps the interior particles.  The callback must not block the host on it.
+ * Blocks under slabs: every rank passes the SAME block list to fjsph_set_blocks with ranges over its own particles; an
+ * inlet block carries its back / buffer tables (local indices) only on the rank that holds its buffer region, which must
+ * lie inside one slab.  Insertions, delete planes and the erasures of the aero-mesh lookup then work as on one GPU, with
+ * globally unique particle ids; the particle ORDER is this rank's own.  A replicated aero mesh is uploaded on every rank.
  * The callback returns 0 on success.  fjsph_b200/slab.py implements it with NCCL send/recv over NVLink
  * (torch.distributed); upload the rank's own particles with fjsph_upload_state first, then call fjsph_set_slab. */
 enum { FJSPH_COMM_SUM = 0, FJSPH_COMM_MAX = 1, FJSPH_COMM_SENDRECV_DEV = 2, FJSPH_COMM_SENDRECV_HOST = 3,

@@ -25,45 +25,59 @@ def relerr(a, b):
     return 0.0 if d == 0 else (d / s if s > 0 else np.inf)
 
 
-def run(name, case, params, steps, rank, world, local_rank, mesh=None):
+def run(name, case, params, steps, rank, world, local_rank, mesh=None, block=None, bounds=None):
     n = case["xi"].shape[0]
     dx = case["params"]["particle_step"]
     xmin, xmax = case["xi"][:, 0].min() - 0.5 * dx, case["xi"][:, 0].max() + 0.5 * dx
-    lo, hi = slab.slab_bounds(xmin, xmax, world)
+    lo, hi = bounds if bounds is not None else slab.slab_bounds(xmin, xmax, world)
     own = slab.partition(case["xi"], lo[rank], hi[rank])
     sub = {k: (v[own] if isinstance(v, np.ndarray) and v.shape[:1] == (n,) else v) for k, v in case.items()}
     sub["bound_points"] = 0
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         e = slab.SlabEngine(eng.default_params(3, **params), sub, rank, world, lo[rank], hi[rank], device=local_rank,
-                            stream=stream, capacity=n + 1000, part_id=own)
+                            stream=stream, capacity=2 * n + 1000, part_id=own)
         if mesh is not None:
             e.upload_mesh(mesh)  # the aero mesh is replicated on every rank
+        if block is not None:
+            # every rank carries the block; its back / buffer tables (local indices) only where the buffer region lives
+            loc = -np.ones(n, dtype=np.int64)
+            loc[own] = np.arange(len(own))
+            mine = dict(block, first=0, second=len(own))
+            if (loc[block["back"]] >= 0).all() and (loc[block["buffer"]] >= 0).all():
+                mine.update(back=loc[block["back"]], buffer=loc[block["buffer"]])
+            else:
+                assert (loc[block["back"]] < 0).all() and (loc[block["buffer"]] < 0).all(), "buffer region split over ranks"
+                mine.pop("back"), mine.pop("buffer")
+            e.set_blocks([mine])
         its = []
         for _ in range(steps):
             s = e.integrate()
-            its.append((s.iterations, s.dt, s.npd, s.rms_error))
+            its.append((s.iterations, s.dt, s.npd, s.rms_error, s.n_add, s.n_del))
         got = e.download(FIELDS)
         stats = e.slab_stats()
     gathered = [None] * world
     dist.all_gather_object(gathered, (got, its, stats))
     ok = True
     if rank == 0:
-        ref = eng.Engine(eng.default_params(3, **params), n, device=local_rank)
+        ref = eng.Engine(eng.default_params(3, **params), 4 * n, device=local_rank)
         ref.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], 0)
         if mesh is not None:
             ref.upload_mesh(mesh)
+        if block is not None:
+            ref.set_blocks([block])
         rits = []
         for _ in range(steps):
             s = ref.integrate()
-            rits.append((s.iterations, s.dt, s.npd, s.rms_error))
+            rits.append((s.iterations, s.dt, s.npd, s.rms_error, s.n_add, s.n_del))
         want = ref.download(FIELDS)
         pid = np.concatenate([g[0]["part_id"] for g in gathered])
         n_left = want["part_id"].shape[0]  # the aero mesh erases the particles that escape it
         assert len(pid) == n_left and len(np.unique(pid)) == n_left and np.array_equal(np.sort(pid), np.sort(want["part_id"])), \
             "%s: particles lost or duplicated (%d of %d)" % (name, len(np.unique(pid)), n_left)
-        if n_left != n:
-            print("%s: %d of %d particles erased on both sides" % (name, n - n_left, n))
+        if n_left != n or sum(r[4] + r[5] for r in rits):
+            print("%s: %d particles at the start, %d inserted and %d erased on both sides, %d at the end" % (
+                name, n, sum(r[4] for r in rits), n + sum(r[4] for r in rits) - n_left, n_left))
         order = np.argsort(want["part_id"])
         pid = order[np.searchsorted(want["part_id"][order], pid)]  # rows of the reference download
         print("%s: owned per rank %s, ghosts %s, exchanges %s (beside an interior sweep: %s), redecomps %s" % (
@@ -72,7 +86,7 @@ def run(name, case, params, steps, rank, world, local_rank, mesh=None):
             [g[2]["redecomps"] for g in gathered]))
         for r, g in enumerate(gathered):
             for a, b in zip(g[1], rits):
-                if a[0] != b[0] or abs(a[1] - b[1]) > 1e-12 * b[1] or abs(a[2] - b[2]) > 1e-10 * abs(b[2]):
+                if a[0] != b[0] or abs(a[1] - b[1]) > 1e-12 * b[1] or abs(a[2] - b[2]) > 1e-10 * abs(b[2]) or a[4:] != b[4:]:
                     print("  rank %d step stats differ: %s vs %s" % (r, a, b))
                     ok = False
         for f in FIELDS[1:]:
@@ -115,6 +129,13 @@ def main():
     ok &= run("block in an aero mesh", case, dict(case["params"], delta_t_min=1e-9, acase=1, asource=1, lam_cutoff=1e9,
                                                   v_inf=(20.0, 5.0, 0.0), p_ref=100000.0, rho_g=1.2), 3, rank, world,
               local_rank, mesh=mesh)
+    # 5. an inlet on rank 0 feeding a jet that crosses into the next slab and ends at a delete plane there: insertions
+    #    (update_buffer_region) on one rank, migration of PIPE / FREE particles, erasures on another, ids unique over ranks
+    if world == 2:
+        jet = cases.inlet_jet(n=(5, 5, 8), fixed=1, delete_x=2.5, jitter=0.03)
+        dxj = jet["params"]["particle_step"]
+        ok &= run("inlet jet", jet, dict(jet["params"], delta_t_min=1e-9), 14, rank, world, local_rank, block=jet["block"],
+                  bounds=([-1e300, -3.5 * dxj], [-3.5 * dxj, 1e300]))
     dist.destroy_process_group()
     if rank == 0:
         print("SLAB PARITY %s" % ("OK" if ok else "FAILED"))
