@@ -7,9 +7,17 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this library.  The product (fjsph_b200/) never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests/golden vectors for this path and cannot be compiled
- * here (Eigen, nanoflann, TECIO, NetCDF, HDF5 are un-vendored), so this restatement is pinned only by
- * analytic checks (tests/test_oracle_*.py), not by reference outputs.
+ * PARITY: the reference ships no tests or golden vectors for this path, and its build as shipped cannot run here
+ * (Eigen, nanoflann, TECIO, NetCDF, HDF5 are un-vendored).  What can be done is done: FJSPH's OWN time-step translation
+ * units (Neighbours, Shifting, Resid, Geometry, Containment, Newmark_Beta, Runge_Kutta, Integration, shapes/inlet .cpp)
+ * compile unmodified against stand-in headers for the two header-only libraries (oracle/shim/, oracle/Makefile.ref ->
+ * oracle/_ref/liborc_ref{3d,3d_dsph,2d}.so, same orc_* ABI through oracle/ref_harness.cpp).  This restatement is pinned
+ * against them: live in tests/test_oracle_vs_reference.py and through the committed vectors of tests/golden/
+ * (tests/test_golden_reference.py) -- every stage and full NB / RK4 steps, walls, aero models, inlets, mesh containment,
+ * 2D: same flags, counts and sub-iterations, FP64 fields <= 1e-11.  STILL UNPINNED: the arithmetic INSIDE Eigen and
+ * nanoflann (ColPivHouseholderQR, computeDirect, 4x4 determinant, dot/norm summation order, KD-tree result order), which
+ * both this file and the stand-ins restate from the published algorithms; and the one path where the reference is
+ * undefined (erasing escaped particles by FindCell's duplicated index list), where the contract below stands alone.
  */
 #ifndef FJSPH_ORACLE_H
 #define FJSPH_ORACLE_H

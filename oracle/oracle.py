@@ -51,16 +51,51 @@ def build(fast: bool = False) -> None:
     subprocess.check_call(["make", "-s", "-C", _HERE] + (["fast"] if fast else []))
 
 
+def build_ref() -> None:
+    """Compile FJSPH's own sources from /root/reference into oracle/_ref/ (no-op where the reference is absent)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "-f", "Makefile.ref"])
+
+
+def have_ref(kind: str = "ref3d") -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "liborc_%s.so" % kind))
+
+
+def ref_set_values(p: "OrcParams", kind: str = "ref3d") -> "OrcParams":
+    """The derived constants of Set_Values through the reference's own inline functions (ref_harness.cpp)."""
+    q = OrcParams.from_buffer_copy(p)
+    _load(kind).orc_ref_set_values(C.byref(q))
+    return q
+
+
 def _load(kind: str):
     if kind in _LIBS:
         return _LIBS[kind]
-    path = os.path.join(_HERE, "lib", "liborc%s.so" % kind)
-    if not os.path.exists(path):
-        build(fast="fast" in kind)
+    if kind.startswith("ref"):
+        # FJSPH's own sources compiled against the stand-in headers (oracle/Makefile.ref, ref_harness.cpp): the same
+        # orc_* ABI, minus the parameter defaults and the small-matrix unit entry points
+        path = os.path.join(_HERE, "_ref", "liborc_%s.so" % kind)
+        if not os.path.exists(path):
+            build_ref()
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+    else:
+        path = os.path.join(_HERE, "lib", "liborc%s.so" % kind)
+        if not os.path.exists(path):
+            build(fast="fast" in kind)
     lib = C.CDLL(path)
     P = C.POINTER
-    lib.orc_default_params.argtypes = [P(OrcParams), C.c_int]
-    lib.orc_set_values.argtypes = [P(OrcParams)]
+    if kind.startswith("ref"):
+        lib.orc_ref_set_values.argtypes = [P(OrcParams)]
+        lib.orc_ref_pressure.argtypes = [P(OrcParams), C.c_double]
+        lib.orc_ref_pressure.restype = C.c_double
+        lib.orc_ref_density.argtypes = [P(OrcParams), C.c_double]
+        lib.orc_ref_density.restype = C.c_double
+    else:
+        lib.orc_default_params.argtypes = [P(OrcParams), C.c_int]
+        lib.orc_set_values.argtypes = [P(OrcParams)]
+        lib.orc_qr_inverse.argtypes = [C.c_void_p, C.c_void_p]
+        lib.orc_min_eigenvalue.argtypes = [C.c_void_p]
+        lib.orc_min_eigenvalue.restype = C.c_double
     lib.orc_create.argtypes = [P(OrcParams)]
     lib.orc_create.restype = C.c_void_p
     lib.orc_destroy.argtypes = [C.c_void_p]
@@ -99,9 +134,6 @@ def _load(kind: str):
     lib.orc_integrate_no_update.restype = C.c_double
     lib.orc_integrate.argtypes = [C.c_void_p, P(OrcStepStats)]
     lib.orc_integrate.restype = C.c_double
-    lib.orc_qr_inverse.argtypes = [C.c_void_p, C.c_void_p]
-    lib.orc_min_eigenvalue.argtypes = [C.c_void_p]
-    lib.orc_min_eigenvalue.restype = C.c_double
     lib.orc_kernel.argtypes = [C.c_double] * 3
     lib.orc_kernel.restype = C.c_double
     lib.orc_get_n_full.argtypes = [C.c_double] * 2

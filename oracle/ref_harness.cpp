@@ -1,0 +1,697 @@
+/* ref_harness.cpp — TEST INFRASTRUCTURE ONLY.
+ *
+ * The orc_* C ABI of fjsph_oracle.h on top of FJSPH's OWN time-step sources, compiled unmodified from where they lie
+ * under /root/reference/src (Neighbours, Shifting, Resid, Geometry, Containment, Newmark_Beta, Runge_Kutta, Integration,
+ * shapes/inlet .cpp; recipe: oracle/Makefile.ref, output: oracle/_ref/liborc_ref*.so).  The two header-only libraries
+ * the reference does not vendor (Eigen, nanoflann) are replaced by the stand-ins of oracle/shim/, so:
+ *   - what this library pins is FJSPH's arithmetic and control flow (pair loops, surface logic, boundary treatment,
+ *     aero coupling, containment, integrators, inlet bookkeeping) -- the oracle restatement is checked against it in
+ *     tests/test_oracle_vs_reference.py and through the fixtures of tests/golden/;
+ *   - Eigen's / nanoflann's own arithmetic (QR inverse, direct eigenvalues, 4x4 determinant, search order) is the
+ *     shim's restatement of the published algorithms and stays unpinned.
+ * Nothing in fjsph_b200/ links or loads this.  Functions of the reference that the path links but never runs here
+ * (IPT::Integrate, VLM::getVelocity, the ShapeBlock front end) are stubs that abort.
+ *
+ * OpenMP: the reference's loops keep their pragmas; the harness pins one thread so that reductions are deterministic
+ * and the npd data race cannot occur.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include <chrono>
+#include <set>
+
+#include "Var.h"
+#define private public /* Integrator keeps find_timestep and the step maxima private (Integration.h:30-75) */
+#include "Integration.h"
+#undef private
+#include "Containment.h"
+#include "Geometry.h"
+#include "Kernel.h"
+#include "Neighbours.h"
+#include "Newmark_Beta.h"
+#include "Resid.h"
+#include "Runge_Kutta.h"
+#include "Shifting.h"
+#include "shapes/inlet.h"
+
+#include "fjsph_oracle.h"
+
+/* ---- out-of-path symbols the objects reference ------------------------------------------------ */
+static void not_on_path(const char* what)
+{
+    std::fprintf(stderr, "ref_harness: %s is outside the time-step path and is not compiled\n", what);
+    std::abort();
+}
+namespace IPT
+{
+void Integrate(SIM&, MESH const&, size_t const&, IPTPart&, IPTPart&, IPTPart&, vector<SURF>&, vector<IPTState>&)
+{
+    not_on_path("IPT::Integrate");
+}
+} // namespace IPT
+#if SIMDIM == 3
+StateVecD VLM::getVelocity(StateVecD const&) const
+{
+    not_on_path("VLM::getVelocity");
+    return StateVecD::Zero();
+}
+#endif
+void ShapeBlock::check_input(SIM const&, real&, int&) { not_on_path("ShapeBlock::check_input"); }
+void ShapeBlock::check_input_post(real&) { not_on_path("ShapeBlock::check_input_post"); }
+void ShapeBlock::generate_points(real const&) { not_on_path("ShapeBlock::generate_points"); }
+
+/* ---- the handle ----------------------------------------------------------------------------- */
+struct Orc
+{
+    OrcParams P;
+    SIM svar;
+    LIMITS limits;
+    OUTL outlist;
+    MESH cells;
+    SURFS surf_marks;
+    SPHState pn, pnp1;
+    vector<IPTState> iptdata;
+    Sim_Tree* sph_tree = nullptr;
+    Vec_Tree* cell_tree = nullptr;
+    Integrator* integ = nullptr;
+    ~Orc()
+    {
+        delete sph_tree;
+        delete cell_tree;
+        delete integ;
+    }
+};
+
+static StateVecD vec_from(const double* p)
+{
+    StateVecD v = StateVecD::Zero();
+    if (p)
+        for (int d = 0; d < SIMDIM; ++d) v[d] = p[d];
+    return v;
+}
+
+/* OrcParams (inputs and the derived constants) -> SIM.  Field by field: Var.h INTEG_SETT / FLUID / AERO / SIM. */
+static void params_to_sim(const OrcParams& P, SIM& s)
+{
+    s.integrator.solver_type = uint(P.solver_type);
+    s.integrator.max_subits = uint(P.max_subits);
+    s.integrator.n_stable = uint(P.n_stable);
+    s.integrator.n_stable_limit = uint(P.n_stable_limit);
+    s.integrator.n_unstable = uint(P.n_unstable);
+    s.integrator.n_unstable_limit = uint(P.n_unstable_limit);
+    s.integrator.subits_factor = P.subits_factor;
+    s.integrator.cfl = P.cfl;
+    s.integrator.cfl_step = P.cfl_step;
+    s.integrator.cfl_max = P.cfl_max;
+    s.integrator.cfl_min = P.cfl_min;
+    s.integrator.current_time = P.current_time;
+    s.integrator.last_frame_time = P.last_frame_time;
+    s.integrator.frame_time_interval = P.frame_time_interval;
+    s.integrator.min_residual = P.min_residual;
+    s.integrator.delta_t = P.delta_t;
+    s.integrator.delta_t_max = P.delta_t_max;
+    s.integrator.delta_t_min = P.delta_t_min;
+    s.integrator.nb_beta = P.nb_beta;
+    s.integrator.nb_gamma = P.nb_gamma;
+    s.integrator.max_shift_vel = P.max_shift_vel;
+
+    FLUID& f = s.fluid;
+    f.pressure_rel = uint(P.pressure_rel);
+    f.H = P.H;
+    f.H_sq = P.H_sq;
+    f.sr = P.sr;
+    f.H_fac = P.H_fac;
+    f.W_dx = P.W_dx;
+    f.rho_rest = P.rho_rest;
+    f.rho_pipe = P.rho_pipe;
+    f.press_pipe = P.press_pipe;
+    f.press_back = P.press_back;
+    f.rho_max = P.rho_max;
+    f.rho_min = P.rho_min;
+    f.rho_var = P.rho_var;
+    f.rho_max_iter = P.rho_max_iter;
+    f.sim_mass = P.sim_mass;
+    f.bnd_mass = P.bnd_mass;
+    f.W_correc = P.W_correc;
+    f.visc_alpha = P.visc_alpha;
+    f.speed_sound = P.speed_sound;
+    f.mu = P.mu;
+    f.nu = P.nu;
+    f.sig = P.sig;
+    f.gam = P.gam;
+    f.B = P.B;
+    f.dsph_delta = P.dsph_delta;
+    f.dsph_cont = P.dsph_cont;
+    f.dsph_mom = 2.0 * (SIMDIM + 2.0); /* IO.cpp:80 */
+
+    AERO& a = s.air;
+    a.v_inf = vec_from(P.v_inf);
+    a.L = P.aero_L;
+    a.td = P.td;
+    a.omega = P.omega;
+    a.tmax = P.tmax;
+    a.ycoef = P.ycoef;
+    a.Cf = P.tab_Cf;
+    a.Ck = P.tab_Ck;
+    a.Cd = P.tab_Cd;
+    a.Cb = P.tab_Cb;
+    a.Cdef = P.Cdef;
+    a.A_sphere = P.A_sphere;
+    a.A_plate = P.A_plate;
+    a.p_ref = P.p_ref;
+    a.rho_g = P.rho_g;
+    a.mu_g = P.mu_g;
+    a.temp_g = P.temp_g;
+    a.R_g = P.R_g;
+    a.gamma = P.gamma_g;
+    a.sos = P.sos;
+    a.i_sos_sq = 1.0 / (P.sos * P.sos); /* IO.cpp:56 */
+    a.lam_cutoff = P.lam_cutoff;
+    a.interp_fac = P.interp_fac;
+    a.i_interp_fac = P.i_interp_fac;
+    a.n_full = P.n_full;
+    a.i_n_full = P.i_n_full;
+    a.acase = P.acase;
+    a.use_lam = P.use_lam;
+    a.use_TAB_def = P.use_TAB_def;
+
+    s.particle_step = P.particle_step;
+    s.dx = P.dx;
+    s.grav = vec_from(P.grav);
+    s.Asource = P.asource;
+    s.ipt.using_ipt = 0;
+    s.numThreads = 1;
+}
+
+static void sim_to_params(const SIM& s, OrcParams& P)
+{
+    P.n_stable = int(s.integrator.n_stable);
+    P.n_unstable = int(s.integrator.n_unstable);
+    P.cfl = s.integrator.cfl;
+    P.current_time = s.integrator.current_time;
+    P.delta_t = s.integrator.delta_t;
+}
+
+extern "C" {
+
+int orc_compiled_dim(void) { return SIMDIM; }
+
+/* Set_Values (IO.cpp:26-128) cannot be compiled (IO.cpp needs TECIO/HDF5 headers); this walks the same assignments
+ * through the reference's OWN inline pieces -- FLUID::get_density (Var.h:220-236), Kernel (Kernel.h:37-45),
+ * AERO::GetYcoef (Var.h:244-266), get_n_full (Geometry.cpp:282-308) -- so the derived constants of the restatement can
+ * be checked against them. */
+void orc_ref_set_values(OrcParams* p)
+{
+    SIM s;
+    params_to_sim(*p, s);
+    s.fluid.B = s.fluid.rho_rest * pow(s.fluid.speed_sound, 2) / s.fluid.gam;
+    s.fluid.rho_pipe = s.fluid.get_density(s.fluid.press_pipe);
+    if (s.fluid.rho_max == 1500 && s.fluid.rho_min == 500)
+    {
+        s.fluid.rho_max = s.fluid.rho_rest * (1.0 + s.fluid.rho_var * 0.01);
+        s.fluid.rho_min = s.fluid.rho_rest * (1.0 - s.fluid.rho_var * 0.01);
+    }
+    s.dx = s.particle_step * pow(s.fluid.rho_pipe / s.fluid.rho_rest, 1.0 / SIMDIM);
+    s.fluid.sim_mass = s.fluid.rho_rest * pow(s.particle_step, SIMDIM);
+    s.fluid.bnd_mass = s.fluid.sim_mass;
+    s.air.sos = sqrt(s.air.temp_g * s.air.R_g * s.air.gamma);
+    s.fluid.H = s.fluid.H_fac * s.particle_step;
+    s.fluid.H_sq = s.fluid.H * s.fluid.H;
+    s.fluid.sr = 4 * s.fluid.H_sq;
+    s.fluid.dsph_cont = 2.0 * s.fluid.dsph_delta * s.fluid.H * s.fluid.speed_sound;
+    s.fluid.nu = s.fluid.mu / s.fluid.rho_rest;
+#if SIMDIM == 2
+    s.fluid.W_correc = 7.0 / (4.0 * M_PI * s.fluid.H * s.fluid.H);
+#else
+    s.fluid.W_correc = (21 / (16 * M_PI * s.fluid.H * s.fluid.H * s.fluid.H));
+#endif
+    s.fluid.W_dx = Kernel(s.particle_step, s.fluid.H, s.fluid.W_correc);
+    s.air.GetYcoef(s.fluid, s.particle_step);
+    s.air.n_full = get_n_full(s.particle_step, s.fluid.H);
+    s.air.i_n_full = 1.0 / s.air.n_full;
+    s.air.interp_fac = 1.0 / s.air.i_interp_fac;
+#if SIMDIM == 3
+    s.air.A_plate = s.particle_step * s.particle_step;
+#else
+    s.air.A_plate = s.particle_step;
+#endif
+    p->B = s.fluid.B;
+    p->rho_pipe = s.fluid.rho_pipe;
+    p->rho_max = s.fluid.rho_max;
+    p->rho_min = s.fluid.rho_min;
+    p->dx = s.dx;
+    p->sim_mass = s.fluid.sim_mass;
+    p->bnd_mass = s.fluid.bnd_mass;
+    p->H = s.fluid.H;
+    p->H_sq = s.fluid.H_sq;
+    p->sr = s.fluid.sr;
+    p->dsph_cont = s.fluid.dsph_cont;
+    p->nu = s.fluid.nu;
+    p->W_correc = s.fluid.W_correc;
+    p->W_dx = s.fluid.W_dx;
+    p->nb_beta = 0.25;
+    p->nb_gamma = 0.5;
+    p->aero_L = s.air.L;
+    p->A_sphere = s.air.A_sphere;
+    p->A_plate = s.air.A_plate;
+    p->td = s.air.td;
+    p->omega = s.air.omega;
+    p->tmax = s.air.tmax;
+    p->Cdef = s.air.Cdef;
+    p->ycoef = s.air.ycoef;
+    p->n_full = s.air.n_full;
+    p->i_n_full = s.air.i_n_full;
+    p->interp_fac = s.air.interp_fac;
+    p->sos = s.air.sos;
+}
+
+/* the reference's EOS and kernel, for the unit tests */
+double orc_ref_pressure(const OrcParams* p, double rho)
+{
+    SIM s;
+    params_to_sim(*p, s);
+    return s.fluid.get_pressure(rho);
+}
+double orc_ref_density(const OrcParams* p, double press)
+{
+    SIM s;
+    params_to_sim(*p, s);
+    return s.fluid.get_density(press);
+}
+double orc_kernel(double r, double H, double Wc) { return Kernel(r, H, Wc); }
+double orc_get_n_full(double dx, double H) { return get_n_full(dx, H); }
+
+Orc* orc_create(const OrcParams* p)
+{
+    if (p->dim != SIMDIM)
+    {
+        std::fprintf(stderr, "orc_create(ref): params.dim=%d but library compiled with SIMDIM=%d\n", p->dim, SIMDIM);
+        return nullptr;
+    }
+#ifdef ALE
+    const int ale = 1;
+#else
+    const int ale = 0;
+#endif
+    if (p->ale != ale)
+    {
+        std::fprintf(stderr, "orc_create(ref): params.ale=%d but this is the %s binary\n", p->ale, ale ? "-DALE" : "delta-SPH");
+        return nullptr;
+    }
+    omp_set_num_threads(1);
+    Orc* o = new Orc();
+    o->P = *p;
+    params_to_sim(o->P, o->svar);
+    return o;
+}
+void orc_destroy(Orc* o) { delete o; }
+void orc_get_params(Orc* o, OrcParams* out)
+{
+    sim_to_params(o->svar, o->P);
+    *out = o->P;
+}
+void orc_set_params(Orc* o, const OrcParams* in)
+{
+    o->P = *in;
+    params_to_sim(o->P, o->svar);
+}
+
+int orc_add_block(Orc* o, int is_fluid, int64_t first, int64_t second, int bound_solver, int no_slip, int block_type,
+                  int fixed_vel_or_dynamic, int ntimes, const double* times, const double* vels, const double* insert_norm,
+                  double insconst, const double* delete_norm, double delconst, const double* aero_norm, double aeroconst,
+                  int nback, const int64_t* back, int nbuf, const int64_t* buffer)
+{
+    size_t const i0 = size_t(first), i1 = size_t(second);
+    bound_block B(i0, i1);
+    B.bound_solver = bound_solver;
+    B.no_slip = no_slip;
+    B.block_type = block_type;
+    B.fixed_vel_or_dynamic = fixed_vel_or_dynamic;
+    B.nTimes = size_t(ntimes);
+    for (int t = 0; t < ntimes; ++t) B.times.push_back(times[t]);
+    int const nv = std::max(1, ntimes);
+    for (int t = 0; t < nv; ++t) B.vels.push_back(vels ? vec_from(vels + 3 * t) : StateVecD::Zero());
+    if (insert_norm)
+        B.insert_norm = vec_from(insert_norm);
+    if (delete_norm)
+        B.delete_norm = vec_from(delete_norm);
+    if (aero_norm)
+        B.aero_norm = vec_from(aero_norm);
+    B.insconst = insconst;
+    B.delconst = delconst;
+    B.aeroconst = aeroconst;
+    for (int i = 0; i < nback; ++i)
+    {
+        B.back.push_back(size_t(back[i]));
+        std::vector<size_t> buf;
+        for (int j = 0; j < nbuf; ++j) buf.push_back(size_t(buffer[size_t(i) * nbuf + j]));
+        B.buffer.push_back(buf);
+    }
+    if (is_fluid)
+        o->svar.n_fluid_blocks++;
+    else
+    {
+        if (o->svar.n_fluid_blocks != 0)
+            return -1;
+        o->svar.n_bound_blocks++;
+    }
+    o->limits.push_back(B);
+    return int(o->limits.size()) - 1;
+}
+void orc_clear_blocks(Orc* o)
+{
+    o->limits.clear();
+    o->svar.n_bound_blocks = o->svar.n_fluid_blocks = 0;
+}
+int orc_get_block_range(Orc* o, int block, int64_t* first, int64_t* second)
+{
+    if (block < 0 || size_t(block) >= o->limits.size())
+        return -1;
+    *first = int64_t(o->limits[block].index.first);
+    *second = int64_t(o->limits[block].index.second);
+    return 0;
+}
+
+int orc_set_particles(Orc* o, int64_t n, int64_t bound_points, const double* xi, const double* v, const double* rho,
+                      const double* p, const double* m, const int32_t* b, const int64_t* part_id)
+{
+    SIM& svar = o->svar;
+    delete o->sph_tree;
+    o->sph_tree = nullptr;
+    o->pn.clear();
+    o->pnp1.clear();
+    /* FJSPH.cpp:98-99: the vectors never reallocate under the tree's reference */
+    o->pn.reserve(size_t(n) * 4 + 1024);
+    o->pnp1.reserve(size_t(n) * 4 + 1024);
+    size_t maxid = 0;
+    for (size_t i = 0; i < size_t(n); ++i)
+    {
+        const size_t id = part_id ? size_t(part_id[i]) : i;
+        SPHPart part(vec_from(xi + i * SIMDIM), v ? vec_from(v + i * SIMDIM) : StateVecD::Zero(), rho[i], m[i], p[i], b[i],
+                     uint(id));
+        /* FJSPH.cpp:115-126 (Asource != meshInfl) */
+        part.cellRho = svar.air.rho_g;
+        part.cellP = svar.air.p_ref;
+        part.cellV = svar.air.v_inf;
+        o->pnp1.push_back(part);
+        maxid = std::max(maxid, id);
+    }
+    o->pn = o->pnp1;
+    svar.bound_points = size_t(bound_points);
+    svar.total_points = size_t(n);
+    svar.fluid_points = size_t(n - bound_points);
+    svar.part_id = maxid + 1;
+    svar.delete_count = 0;
+    svar.internal_count = 0;
+    if (o->limits.empty())
+    {
+        double z[3] = {0, 0, 0};
+        if (bound_points > 0)
+            orc_add_block(o, 0, 0, bound_points, pressure_G, 0, 0, 0, 0, nullptr, z, nullptr, default_val, nullptr,
+                          default_val, nullptr, default_val, 0, nullptr, 0, nullptr);
+        orc_add_block(o, 1, bound_points, n, 0, 0, 0, 0, 0, nullptr, z, nullptr, default_val, nullptr, default_val,
+                      nullptr, default_val, 0, nullptr, 0, nullptr);
+    }
+    o->sph_tree = new Sim_Tree(SIMDIM, o->pnp1, 20); /* FJSPH.cpp:145 */
+    if (!o->cell_tree)
+    {
+        if (o->cells.cCentre.size() == 0)
+            o->cells.cCentre.emplace_back(StateVecD::Zero()); /* FJSPH.cpp:137-139 */
+        o->cell_tree = new Vec_Tree(SIMDIM, o->cells.cCentre, 10);
+        o->cell_tree->index->buildIndex();
+    }
+    delete o->integ;
+    o->integ = new Integrator(int(svar.integrator.solver_type));
+    o->outlist.clear();
+    return 0;
+}
+int64_t orc_count(Orc* o) { return int64_t(o->pnp1.size()); }
+int64_t orc_bound_points(Orc* o) { return int64_t(o->svar.bound_points); }
+
+static StateVecD* find_vec(SPHPart& p, std::string const& n)
+{
+    if (n == "xi") return &p.xi;
+    if (n == "v") return &p.v;
+    if (n == "acc") return &p.acc;
+    if (n == "Af") return &p.Af;
+    if (n == "aVisc") return &p.aVisc;
+    if (n == "cellV") return &p.cellV;
+    if (n == "gradRho") return &p.gradRho;
+    if (n == "norm") return &p.norm;
+    if (n == "bNorm") return &p.bNorm;
+    if (n == "vPert") return &p.vPert;
+    return nullptr;
+}
+static real* find_scalar(SPHPart& p, std::string const& n)
+{
+    if (n == "Rrho") return &p.Rrho;
+    if (n == "rho") return &p.rho;
+    if (n == "p") return &p.p;
+    if (n == "m") return &p.m;
+    if (n == "curve") return &p.curve;
+    if (n == "norm_curve") return &p.norm_curve;
+    if (n == "woccl") return &p.woccl;
+    if (n == "pDist") return &p.pDist;
+    if (n == "deltaD") return &p.deltaD;
+    if (n == "cellP") return &p.cellP;
+    if (n == "cellRho") return &p.cellRho;
+    if (n == "colourG") return &p.colourG;
+    if (n == "colour") return &p.colour;
+    if (n == "lam") return &p.lam;
+    if (n == "lam_nb") return &p.lam_nb;
+    if (n == "kernsum") return &p.kernsum;
+    if (n == "y") return &p.y;
+    return nullptr;
+}
+
+static int access_f64(Orc* o, int level, const char* name, double* out, const double* in)
+{
+    SPHState& S = level == 0 ? o->pn : o->pnp1;
+    const std::string n(name);
+    if (S.empty())
+        return 0;
+    if (n == "L")
+    {
+        for (size_t i = 0; i < S.size(); ++i)
+            for (int r = 0; r < SIMDIM; ++r)
+                for (int c = 0; c < SIMDIM; ++c)
+                {
+                    if (out)
+                        out[i * SIMDIM * SIMDIM + r * SIMDIM + c] = S[i].L(r, c);
+                    else
+                        S[i].L(r, c) = in[i * SIMDIM * SIMDIM + r * SIMDIM + c];
+                }
+        return SIMDIM * SIMDIM;
+    }
+    if (find_vec(S[0], n))
+    {
+        for (size_t i = 0; i < S.size(); ++i)
+        {
+            StateVecD& v = *find_vec(S[i], n);
+            for (int d = 0; d < SIMDIM; ++d)
+            {
+                if (out)
+                    out[i * SIMDIM + d] = v[d];
+                else
+                    v[d] = in[i * SIMDIM + d];
+            }
+        }
+        return SIMDIM;
+    }
+    if (find_scalar(S[0], n))
+    {
+        for (size_t i = 0; i < S.size(); ++i)
+        {
+            real& s = *find_scalar(S[i], n);
+            if (out)
+                out[i] = s;
+            else
+                s = in[i];
+        }
+        return 1;
+    }
+    return -1;
+}
+int orc_get_f64(Orc* o, int level, const char* name, double* out) { return access_f64(o, level, name, out, nullptr); }
+int orc_set_f64(Orc* o, int level, const char* name, const double* in) { return access_f64(o, level, name, nullptr, in); }
+
+static int access_i64(Orc* o, int level, const char* name, int64_t* out, const int64_t* in)
+{
+    SPHState& S = level == 0 ? o->pn : o->pnp1;
+    const std::string n(name);
+    for (size_t i = 0; i < S.size(); ++i)
+    {
+        SPHPart& p = S[i];
+#define FJ_INT_FIELD(F, T)                 \
+    if (n == #F)                           \
+    {                                      \
+        if (out)                           \
+            out[i] = int64_t(p.F);         \
+        else                               \
+            p.F = T(in[i]);                \
+        continue;                          \
+    }
+        FJ_INT_FIELD(part_id, size_t)
+        FJ_INT_FIELD(cellID, long)
+        FJ_INT_FIELD(b, uint)
+        FJ_INT_FIELD(surf, uint)
+        FJ_INT_FIELD(surfzone, uint)
+        FJ_INT_FIELD(internal, uint)
+        FJ_INT_FIELD(ipt_n_failed, uint)
+#undef FJ_INT_FIELD
+        return -1;
+    }
+    return 1;
+}
+int orc_get_i64(Orc* o, int level, const char* name, int64_t* out) { return access_i64(o, level, name, out, nullptr); }
+int orc_set_i64(Orc* o, int level, const char* name, const int64_t* in) { return access_i64(o, level, name, nullptr, in); }
+
+/* ---- stages: the reference's functions, called as integrate_no_update calls them (Integration.cpp:27-107) ---- */
+void orc_update_neighbours(Orc* o) { o->outlist = update_neighbours(o->svar.fluid, *o->sph_tree, o->pnp1); }
+int64_t orc_neighbour_total(Orc* o)
+{
+    int64_t t = 0;
+    for (auto const& l : o->outlist) t += int64_t(l.size());
+    return t;
+}
+void orc_get_neighbours(Orc* o, int64_t* offsets, int64_t* idx, double* d2)
+{
+    int64_t k = 0;
+    offsets[0] = 0;
+    for (size_t i = 0; i < o->outlist.size(); ++i)
+    {
+        /* ascending j, as the oracle reports them (the shim's scan already returns them so) */
+        std::vector<neighbour_index> l = o->outlist[i];
+        std::sort(l.begin(), l.end(), [](neighbour_index const& a, neighbour_index const& b) { return a.first < b.first; });
+        for (auto const& e : l)
+        {
+            idx[k] = int64_t(e.first);
+            d2[k] = e.second;
+            ++k;
+        }
+        offsets[i + 1] = k;
+    }
+}
+double orc_prestep(Orc* o)
+{
+    real npd = 1.0;
+    dSPH_PreStep(o->svar.fluid, o->svar.total_points, o->pnp1, o->outlist, npd);
+    return npd;
+}
+void orc_aero_velocity(Orc* o)
+{
+    size_t const start = o->svar.bound_points;
+    size_t end = o->svar.total_points;
+    real npd = 1.0;
+    get_aero_velocity(*o->sph_tree, *o->cell_tree, o->svar, o->cells, start, end, o->outlist, o->limits, o->pn, o->pnp1, npd);
+}
+void orc_set_mesh(Orc* o, int64_t n_verts, const double* verts, int64_t n_faces, const int64_t* face_ptr,
+                  const int64_t* face_vtx, const int32_t* leftright, int64_t n_cells, const int64_t* cell_ptr,
+                  const int64_t* cell_faces, const double* cCentre, const double* cVel, const double* cP, const double* cRho)
+{
+    delete o->cell_tree;
+    o->cell_tree = nullptr;
+    MESH& M = o->cells;
+    M = MESH();
+    M.nPnts = size_t(n_verts);
+    M.nElem = size_t(n_cells);
+    M.nFace = size_t(n_faces);
+    M.verts.resize(size_t(n_verts));
+    for (int64_t i = 0; i < n_verts; ++i) M.verts[size_t(i)] = vec_from(verts + i * SIMDIM);
+    M.faces.resize(size_t(n_faces));
+    M.leftright.resize(size_t(n_faces));
+    for (int64_t f = 0; f < n_faces; ++f)
+    {
+        M.faces[size_t(f)].assign(face_vtx + face_ptr[f], face_vtx + face_ptr[f + 1]);
+        M.leftright[size_t(f)] = std::make_pair(int(leftright[2 * f]), int(leftright[2 * f + 1]));
+    }
+    M.cFaces.resize(size_t(n_cells));
+    M.cCentre.resize(size_t(n_cells));
+    M.cVel.resize(size_t(n_cells));
+    M.cP.assign(cP, cP + n_cells);
+    M.cRho.assign(cRho, cRho + n_cells);
+    for (int64_t c = 0; c < n_cells; ++c)
+    {
+        M.cFaces[size_t(c)].assign(cell_faces + cell_ptr[c], cell_faces + cell_ptr[c + 1]);
+        M.cCentre[size_t(c)] = vec_from(cCentre + c * SIMDIM);
+        M.cVel[size_t(c)] = vec_from(cVel + c * SIMDIM);
+    }
+    o->cell_tree = new Vec_Tree(SIMDIM, o->cells.cCentre, 10); /* FJSPH.cpp:148-149 */
+    o->cell_tree->index->buildIndex();
+}
+int orc_first_cell_errors(Orc*) { return 0; } /* the reference exits instead */
+void orc_detect_surface(Orc* o)
+{
+    Detect_Surface(o->svar, o->svar.bound_points, o->svar.total_points, o->outlist, o->cells, o->pnp1);
+}
+void orc_dissipation(Orc* o)
+{
+    dissipation_terms(o->svar.fluid, o->svar.bound_points, o->svar.total_points, o->outlist, o->pnp1);
+}
+void orc_particle_shift(Orc* o)
+{
+#ifdef ALE
+    particle_shift(o->svar, o->svar.bound_points, o->svar.total_points, o->outlist, o->pnp1);
+#else
+    (void)o;
+#endif
+}
+void orc_forces(Orc* o, double npd) { get_acc_and_Rrho(o->svar, o->cells, o->outlist, npd, o->pnp1); }
+void orc_nb_iter(Orc* o, double npd)
+{
+    size_t const start = o->svar.bound_points;
+    size_t end = o->svar.total_points;
+    Newmark_Beta::Do_NB_Iter(*o->cell_tree, o->svar, start, end, npd, o->cells, o->limits, o->outlist, o->pn, o->pnp1);
+}
+double orc_find_timestep(Orc* o)
+{
+    return o->integ->find_timestep(o->svar, o->cells, o->pnp1, o->svar.bound_points, o->svar.total_points);
+}
+static void fill_stats(Orc* o, OrcStepStats* s, double e)
+{
+    if (!s)
+        return;
+    s->dt = o->svar.integrator.delta_t;
+    s->rms_error = e;
+    s->safe_dt = o->integ->safe_dt;
+    s->cfl_ratio = o->svar.integrator.delta_t / o->integ->safe_dt;
+    s->maxRho_pc = o->integ->maxRho_pc;
+    s->maxf = o->integ->maxf;
+    s->maxAf = o->integ->maxAf;
+#ifdef ALE
+    s->maxShift = o->integ->maxShift;
+#endif
+    s->iterations = int(o->integ->iteration);
+    s->total_points = int(o->pnp1.size());
+}
+double orc_integrate_no_update(Orc* o, OrcStepStats* s)
+{
+    if (s)
+        std::memset(s, 0, sizeof(*s));
+    o->integ->solver_method = int(o->svar.integrator.solver_type);
+    real const e = o->integ->integrate_no_update(*o->sph_tree, *o->cell_tree, o->svar, o->cells, o->limits, o->outlist,
+                                                 o->pn, o->pnp1);
+    fill_stats(o, s, e);
+    return e;
+}
+double orc_integrate(Orc* o, OrcStepStats* s)
+{
+    if (s)
+        std::memset(s, 0, sizeof(*s));
+    o->integ->solver_method = int(o->svar.integrator.solver_type);
+    size_t const total0 = o->svar.total_points, del0 = o->svar.delete_count;
+    real const e = o->integ->integrate(*o->sph_tree, *o->cell_tree, o->svar, o->cells, o->surf_marks, o->limits, o->outlist,
+                                       o->pn, o->pnp1, o->iptdata);
+    fill_stats(o, s, e);
+    if (s)
+    {
+        s->n_del = int(o->svar.delete_count - del0);
+        s->n_add = int(o->svar.total_points + size_t(s->n_del) - total0);
+    }
+    return e;
+}
+
+} /* extern "C" */

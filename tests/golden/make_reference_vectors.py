@@ -1,0 +1,130 @@
+"""Generates tests/golden/ref_*.npz: outputs of FJSPH's OWN time-step sources (compiled unmodified from /root/reference/src
+into oracle/_ref/ by oracle/Makefile.ref, against the stand-in Eigen / nanoflann headers of oracle/shim/) on small seeded
+cases.  Run here, where /root/reference exists; the fixtures travel, the reference does not:
+
+    python tests/golden/make_reference_vectors.py
+
+Each file holds the inputs (state arrays, settings as JSON, LIMITS blocks, mesh) and, after `steps` calls of
+Integrator::integrate, the per-step table (sub-iterations, dt, rms error, maxima, insertions / deletions) and every
+SPHPart field of pnp1.  tests/test_golden_reference.py replays the inputs through the CPU oracle (CPU suite) and through
+the CUDA engine's C ABI (GPU suite) and compares.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from fjsph_b200 import cases  # noqa: E402  (host-side input generation only)
+from oracle import oracle as orc  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FLOATS = orc._VEC_FIELDS + ("L",) + tuple(orc._SCALAR_FIELDS)
+INTS = ("part_id", "cellID", "b", "surf", "surfzone", "internal")
+STATS = ("dt", "cfl_ratio", "rms_error", "maxRho_pc", "maxf", "maxAf", "maxShift", "safe_dt")
+ISTATS = ("iterations", "n_add", "n_del", "total_points")
+BLOCK_KEYS = ("first", "second", "is_fluid", "block_type", "fixed_vel_or_dynamic", "insert_norm", "insconst", "delete_norm",
+              "delconst", "aero_norm", "aeroconst", "back", "buffer")
+
+
+def golden_cases():
+    """name -> (case, kind of reference binary, dim, steps, extra settings, mesh or None, initial cellID or None)"""
+    out = {}
+    blk = cases.synthetic_block(n=(9, 8, 7), jitter=0.1)
+    out["block_nb_ale"] = (blk, "ref3d", 3, 3, dict(ale=1), None, None)
+    out["block_rk4_ale"] = (blk, "ref3d", 3, 3, dict(ale=1, solver_type=1), None, None)
+    out["block_nb_dsph"] = (blk, "ref3d_dsph", 3, 3, dict(ale=0), None, None)
+    out["block_nb_ale_ties"] = (cases.synthetic_block(n=(9, 8, 7), jitter="eps"), "ref3d", 3, 2, dict(ale=1), None, None)
+    drop = cases.droplet(dx=0.008, jitter=0.05)
+    out["droplet_gissler"] = (drop, "ref3d", 3, 3, dict(ale=1), None, None)
+    out["droplet_gissler_tab_nolam"] = (drop, "ref3d", 3, 2, dict(ale=1, use_TAB_def=1, use_lam=0), None, None)
+    out["droplet_induced_pressure"] = (drop, "ref3d", 3, 2, dict(ale=1, acase=2), None, None)
+    out["droplet_skin_friction"] = (drop, "ref3d", 3, 2, dict(ale=1, acase=3), None, None)
+    out["droplet_dsph"] = (drop, "ref3d_dsph", 3, 2, dict(ale=0), None, None)
+    tank = cases.box_with_walls(n=(7, 6, 6), jitter=0.05)
+    out["tank_adami_nb"] = (tank, "ref3d", 3, 3, dict(ale=1), None, None)
+    out["tank_adami_rk4"] = (tank, "ref3d", 3, 3, dict(ale=1, solver_type=1), None, None)
+    out["tank_iso_eos"] = (tank, "ref3d", 3, 2, dict(ale=1, pressure_rel=1), None, None)
+    out["dam_2d"] = (cases.dam_2d(dx=0.05), "ref2d", 2, 3, dict(ale=1), None, None)
+    for fixed in (0, 1):
+        jet = cases.inlet_jet(delete_x=2.5, fixed=fixed, jitter=0.02)
+        out["inlet_jet_fixed%d" % fixed] = (jet, "ref3d", 3, 14, dict(ale=1), None, None)
+    dm = cases.droplet(dx=0.0125, jitter=0.05)
+    sheared = cases.hex_mesh((-0.1013, -0.1007, -0.1011), (0.1009, 0.1003, 0.1017), (6, 7, 5),
+                             vel=lambda c: np.stack([5 + 20 * c[:, 1], 21.55 + 0 * c[:, 0], 3 * c[:, 2]], 1), p=100000.0,
+                             rho=1.1025)
+    # FindCell reads cells.cFaces[cellID] before anything else (Containment.cpp:592-600): the reference needs a valid
+    # cell id on every FREE particle, so the fixture starts all of them in cell 0
+    out["droplet_sheared_mesh"] = (dm, "ref3d", 3, 3, dict(ale=1, asource=1, delta_t_min=1e-9), sheared, 0)
+    wall = cases.hex_mesh((-0.1013, -0.1007, -0.03), (0.1009, 0.1003, 0.1017), (6, 7, 5), vel=(0.0, 21.55, 0.0), p=100000.0,
+                          rho=1.1025, outer_marker=-1)
+    out["droplet_inner_wall_mesh"] = (dm, "ref3d", 3, 3, dict(ale=1, asource=1, delta_t_min=1e-9), wall, 0)
+    return out
+
+
+def make_sim(case, kind, dim, extra, mesh, cell0):
+    """One simulation on `kind` (None / '2d' = the oracle restatement, 'ref*' = the compiled reference)."""
+    P = orc.default_params(dim, **dict(case["params"], **extra))
+    o = orc.Oracle(P, kind=kind)
+    if mesh is not None:
+        o.set_mesh(mesh)
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case.get("bound_points", 0))
+    B = case.get("block")
+    if B is not None:
+        o.lib.orc_clear_blocks(o.h)
+        o.add_block(1, B["first"], B["second"], block_type=B["block_type"], fixed_vel_or_dynamic=B["fixed_vel_or_dynamic"],
+                    insert_norm=B["insert_norm"], insconst=B["insconst"], delete_norm=B.get("delete_norm"),
+                    delconst=B.get("delconst", 9999999.0), aero_norm=B["aero_norm"], aeroconst=B["aeroconst"], back=B["back"],
+                    buffer=B["buffer"])
+    if cell0 is not None:
+        for lvl in (0, 1):
+            o.set("cellID", np.full(o.n, cell0, dtype=np.int64), lvl)
+    return o
+
+
+def run(o, steps):
+    table = {k: [] for k in STATS + ISTATS}
+    for _ in range(steps):
+        _, s = o.integrate()
+        for k in STATS + ISTATS:
+            table[k].append(getattr(s, k))
+    return table
+
+
+def main():
+    if not orc.have_ref():
+        orc.build_ref()
+    for name, (case, kind, dim, steps, extra, mesh, cell0) in golden_cases().items():
+        o = make_sim(case, kind, dim, extra, mesh, cell0)
+        # stdout of the reference's step table is noise here
+        table = run(o, steps)
+        data = {"in_" + k: np.asarray(case[k]) for k in ("xi", "v", "rho", "p", "m", "b")}
+        meta = dict(name=name, kind=kind, dim=dim, steps=steps, bound_points=int(case.get("bound_points", 0)),
+                    params={k: (list(v) if hasattr(v, "__len__") else v) for k, v in dict(case["params"], **extra).items()},
+                    cell0=cell0)
+        if case.get("block") is not None:
+            B = case["block"]
+            meta["block"] = {k: (np.asarray(B[k]).tolist() if hasattr(B[k], "__len__") else B[k]) for k in BLOCK_KEYS if k in B}
+        if mesh is not None:
+            for k, v in mesh.items():
+                data["mesh_" + k] = np.asarray(v)
+        for k in STATS:
+            data["step_" + k] = np.asarray(table[k], dtype=np.float64)
+        for k in ISTATS:
+            data["step_" + k] = np.asarray(table[k], dtype=np.int64)
+        for f in FLOATS + INTS:
+            data["out_" + f] = o.get(f, 1)
+        data["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        path = os.path.join(HERE, "ref_%s.npz" % name)
+        np.savez_compressed(path, **data)
+        print("%-28s %5d particles, %2d steps, sub-iterations %s, %6.1f kB" % (
+            name, o.n, steps, table["iterations"], os.path.getsize(path) / 1024.0))
+
+
+if __name__ == "__main__":
+    main()

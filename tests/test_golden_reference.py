@@ -1,0 +1,119 @@
+"""Golden vectors from FJSPH's own sources.
+
+tests/golden/ref_*.npz were produced by tests/golden/make_reference_vectors.py from oracle/_ref/ -- the reference's
+Neighbours / Shifting / Resid / Geometry / Containment / Newmark_Beta / Runge_Kutta / Integration / shapes/inlet .cpp compiled
+unmodified against stand-in Eigen / nanoflann headers (oracle/Makefile.ref).  They pin FJSPH's arithmetic and control flow:
+
+  * CPU suite: the oracle restatement replays every fixture and must land on the reference's numbers
+    (same sub-iteration counts, insertions, deletions and flags; dt 1e-12; every FP64 field 1e-9 normwise -- measured
+    <= 1e-11, the difference being the summation order inside dot()/norm());
+  * GPU suite: the CUDA engine replays the 3D fixtures through the C ABI with the bars of tests/test_gpu_parity.py
+    (state 1e-10, velocity and pressure 1e-8, rates 1e-6, flags and counts exact; tie-stress inputs looser, as there).
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.util import relerr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_*.npz")))
+FLOATS = orc._VEC_FIELDS + ("L",) + tuple(orc._SCALAR_FIELDS)
+INTS = ("part_id", "cellID", "b", "surf", "surfzone", "internal")
+
+
+def load(path):
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    case = {k: z["in_" + k] for k in ("xi", "v", "rho", "p", "m", "b")}
+    case["bound_points"] = meta["bound_points"]
+    case["params"] = {k: (tuple(v) if isinstance(v, list) else v) for k, v in meta["params"].items()}
+    mesh = {k[5:]: z[k] for k in z.files if k.startswith("mesh_")} or None
+    block = meta.get("block")
+    if block is not None:
+        block = dict(block, back=np.asarray(block["back"], dtype=np.int64), buffer=np.asarray(block["buffer"], dtype=np.int64))
+    return z, meta, case, mesh, block
+
+
+def test_fixtures_present():
+    assert len(FIXTURES) >= 15, "tests/golden/ref_*.npz missing: run tests/golden/make_reference_vectors.py where /root/reference exists"
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[4:-4] for p in FIXTURES])
+def test_oracle_reproduces_reference_vectors(path):
+    z, meta, case, mesh, block = load(path)
+    dim = meta["dim"]
+    o = orc.Oracle(orc.default_params(dim, **case["params"]))
+    if mesh is not None:
+        o.set_mesh(mesh)
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
+    if block is not None:
+        o.lib.orc_clear_blocks(o.h)
+        o.add_block(1, block["first"], block["second"], block_type=block["block_type"],
+                    fixed_vel_or_dynamic=block["fixed_vel_or_dynamic"], insert_norm=block["insert_norm"],
+                    insconst=block["insconst"], delete_norm=block.get("delete_norm"), delconst=block.get("delconst", 9999999.0),
+                    aero_norm=block["aero_norm"], aeroconst=block["aeroconst"], back=block["back"], buffer=block["buffer"])
+    if meta["cell0"] is not None:
+        for lvl in (0, 1):
+            o.set("cellID", np.full(o.n, meta["cell0"], dtype=np.int64), lvl)
+    for step in range(meta["steps"]):
+        _, s = o.integrate()
+        ctx = "%s step %d" % (meta["name"], step)
+        for k in ("iterations", "n_add", "n_del", "total_points"):
+            assert getattr(s, k) == int(z["step_" + k][step]), (ctx, k, getattr(s, k), int(z["step_" + k][step]))
+        assert abs(s.dt - z["step_dt"][step]) <= 1e-12 * z["step_dt"][step], ctx
+        for k in ("maxf", "maxAf", "maxRho_pc", "safe_dt"):
+            assert abs(getattr(s, k) - z["step_" + k][step]) <= 1e-9 * max(abs(z["step_" + k][step]), 1e-300), (ctx, k)
+        if np.isfinite(z["step_rms_error"][step]):
+            assert abs(s.rms_error - z["step_rms_error"][step]) <= 1e-6, ctx
+    for f in INTS:
+        assert np.array_equal(o.get(f), z["out_" + f]), (meta["name"], f)
+    for f in FLOATS:
+        r = relerr(o.get(f), z["out_" + f])
+        assert r <= 1e-9, "%s: field %s differs from the reference by %.3e" % (meta["name"], f, r)
+
+
+# ---------------------------------------------------------------------------------------------------- GPU
+GPU_FIXTURES = [p for p in FIXTURES if "_2d" not in os.path.basename(p)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GPU_FIXTURES, ids=[os.path.basename(p)[4:-4] for p in GPU_FIXTURES])
+def test_engine_reproduces_reference_vectors(path):
+    from fjsph_b200 import engine as eng
+
+    z, meta, case, mesh, block = load(path)
+    ties = "ties" in meta["name"]
+    n = case["xi"].shape[0]
+    e = eng.Engine(eng.default_params(3, **case["params"]), 4 * n)
+    e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
+    if block is not None:
+        e.set_blocks([block])
+    if mesh is not None:
+        e.upload_mesh(mesh)
+    if meta["cell0"] is not None:
+        for lvl in (0, 1):
+            e.upload_level(lvl, cellID=np.full(n, meta["cell0"], dtype=np.int64))
+    for step in range(meta["steps"]):
+        s = e.integrate()
+        ctx = "%s step %d" % (meta["name"], step)
+        assert s.iterations == int(z["step_iterations"][step]), (ctx, s.iterations, int(z["step_iterations"][step]))
+        assert s.total_points == int(z["step_total_points"][step]), ctx
+        assert s.n_add == int(z["step_n_add"][step]) and s.n_del == int(z["step_n_del"][step]), ctx
+        assert abs(s.dt - z["step_dt"][step]) <= (1e-9 if ties else 1e-12) * z["step_dt"][step], ctx
+    got = e.download(FLOATS + INTS)
+    for f in INTS:
+        assert np.array_equal(got[f], z["out_" + f]), (meta["name"], f)
+    if ties:
+        bars = dict(xi=1e-8, rho=1e-8, v=1e-3, acc=1e-3, Rrho=1e-3, vPert=1e-3)
+    else:
+        bars = dict(xi=1e-10, rho=1e-10, lam=1e-10, lam_nb=1e-10, v=1e-8, p=1e-8, acc=1e-6, Af=1e-6, Rrho=1e-6, aVisc=1e-6,
+                    deltaD=1e-6, vPert=1e-6, cellV=1e-10, cellP=1e-10, cellRho=1e-10, norm=1e-8, curve=1e-6, woccl=1e-8,
+                    gradRho=1e-6, L=1e-8, kernsum=1e-8, colour=1e-8)
+    for f, tol in bars.items():
+        r = relerr(got[f], z["out_" + f])
+        assert r <= tol, "%s: field %s differs from the reference by %.3e (bar %.0e)" % (meta["name"], f, r, tol)
