@@ -15,10 +15,11 @@ sub-iterations (max_subits = 3, min_residual = -30), so one step holds 5 force e
 One JSON line on stdout (rank 0).  `value` times K steps on device-resident state with CUDA events on the
 engine's stream; `e2e` times the same K steps through fjsph_step_host with pinned HOST buffers (upload of
 x, v, acc, rho, Rrho, p, m, b and download of x, v, acc, rho, Rrho, p inside the timed region).  `roofline`
-is the force kernel (get_acc_and_Rrho), `cpu_baseline` the CPU restatement of the reference (oracle/, built
-with the reference's own flags, makefile:16) on this box's host cores.  `--impl reference` times that CPU
-restatement alone: the reference itself cannot be compiled here (Eigen, nanoflann, TECIO, NetCDF and HDF5
-are un-vendored).
+is the force kernel (get_acc_and_Rrho), `cpu_baseline` the reference's CPU path on this box's host cores: FJSPH's own
+time-step sources compiled unmodified with the reference's flags (makefile:16) against stand-in Eigen / nanoflann
+headers (oracle/_ref/liborc_ref3d_fast.so, built where /root/reference exists by oracle/Makefile.ref; kind
+"reference"), or, where that library is absent, the CPU restatement under oracle/ built the same way (kind "port").
+`--impl reference` times that arm alone.
 """
 from __future__ import annotations
 
@@ -142,12 +143,37 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+class quiet_fd1:
+    """FJSPH prints its step table with printf (Integration.cpp:250-265); bench.py prints ONE JSON line.  Routes the C
+    level stdout to /dev/null while the reference's own code runs."""
+
+    def __enter__(self):
+        import ctypes
+
+        self.libc = ctypes.CDLL(None)
+        sys.stdout.flush()
+        self.libc.fflush(None)
+        self.saved = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        os.close(devnull)
+
+    def __exit__(self, *exc):
+        self.libc.fflush(None)
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_reference(args, steps, warmup, sample_cells):
-    """Times the CPU restatement of the reference step (oracle/, the reference's flags + OpenMP) on a bounded
-    sample of the same workload.  Returns (particle-steps/s, cores, description)."""
+    """Times the reference's CPU implementation of the step on a bounded sample of the same workload, with every host
+    thread.  oracle/_ref/liborc_ref3d_fast.so when it is there -- FJSPH's OWN sources compiled with the reference's flags
+    (oracle/Makefile.ref; kind "reference") -- else the CPU restatement built the same way (kind "port").
+    Returns (particle-steps/s, cores, description, ms per step, kind)."""
     from oracle import oracle as orc  # bench.py's CPU-baseline leg: the checker timed as the baseline
 
-    subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "lib/liborc3d_fast.so"])
+    use_ref = orc.have_ref("ref3d_fast")
+    if not use_ref:
+        subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "lib/liborc3d_fast.so"])
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; the baseline gets every host core
     try:
@@ -165,37 +191,42 @@ def cpu_reference(args, steps, warmup, sample_cells):
     else:
         case = make_case(args)
     params = step_params(args, case["params"])
-    o = orc.Oracle(orc.default_params(3, kind="3d_fast", **params), kind="3d_fast")
+    kind = "ref3d_fast" if use_ref else "3d_fast"
+    o = orc.Oracle(orc.default_params(3, **params), kind=kind)
     o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
     n = case["xi"].shape[0] - case["bound_points"]
     its = 0
-    for _ in range(warmup):
-        o.integrate()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        _, st = o.integrate()
-        its = st.iterations
-    dt = time.perf_counter() - t0
-    desc = ("oracle/fjsph_oracle.cpp (-O3 -ffast-math -funroll-loops -fopenmp -march=native), %d threads, %d steps "
-            "after %d warm-up on %s, %d particles, %d sub-iterations" % (
-                cores, steps, warmup, "a %s lattice of the block workload" % sample_cells
-                if args.workload == "block" else ("a 64-column, R=32dx cylinder of the jet workload"
-                                                  if args.workload == "jet" else "the droplet"), n, its))
-    return n * steps / dt, cores, desc, dt / steps * 1e3
+    with quiet_fd1():
+        for _ in range(warmup):
+            o.integrate()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, st = o.integrate()
+            its = st.iterations
+        dt = time.perf_counter() - t0
+    what = ("FJSPH's own sources (Neighbours, Shifting, Resid, Geometry, Containment, Newmark_Beta, Integration .cpp compiled "
+            "unmodified, -O3 -ffast-math -funroll-loops -fopenmp -march=x86-64-v3; stand-in Eigen / nanoflann headers, a "
+            "uniform-grid radius search in place of the KD-tree)" if use_ref else
+            "oracle/fjsph_oracle.cpp (-O3 -ffast-math -funroll-loops -fopenmp -march=native)")
+    desc = ("%s, %d threads, %d steps after %d warm-up on %s, %d particles, %d sub-iterations" % (
+        what, cores, steps, warmup, "a %s lattice of the block workload" % sample_cells
+        if args.workload == "block" else ("a 64-column, R=32dx cylinder of the jet workload"
+                                          if args.workload == "jet" else "the droplet"), n, its))
+    return n * steps / dt, cores, desc, dt / steps * 1e3, ("reference" if use_ref else "port")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    value, cores, desc, ms = cpu_reference(args, max(1, args.steps), max(1, min(args.warmup, 1)), args.cpu_sample)
+    value, cores, desc, ms, kind = cpu_reference(args, max(1, args.steps), max(1, min(args.warmup, 1)), args.cpu_sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, world), "solver": args.solver,
                    "force_evals_per_step": 1 + K_SUBITS if args.solver == "newmark_beta" else 4,
-                   "note": "CPU restatement of the reference path on host cores; each step is a bounded sample"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+                   "note": "the reference's CPU path on host cores; each step is a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -378,8 +409,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, desc, _ = cpu_reference(args, 2, 1, args.cpu_sample)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        v, cores, desc, _, kind = cpu_reference(args, 2, 1, args.cpu_sample)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
 
     if rank == 0:
         line = {

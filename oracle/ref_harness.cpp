@@ -301,7 +301,13 @@ Orc* orc_create(const OrcParams* p)
         std::fprintf(stderr, "orc_create(ref): params.ale=%d but this is the %s binary\n", p->ale, ale ? "-DALE" : "delta-SPH");
         return nullptr;
     }
+#ifdef ORC_REF_THREADS
+    /* timing flavour (bench.py's reference arm): every thread OMP_NUM_THREADS grants, as FJSPH's main() does
+       (FJSPH.cpp:62); results are then as reproducible as the reference's own (reduction order, the npd race) */
+    omp_set_num_threads(std::getenv("OMP_NUM_THREADS") ? std::max(atoi(std::getenv("OMP_NUM_THREADS")), 1) : omp_get_num_procs());
+#else
     omp_set_num_threads(1);
+#endif
     Orc* o = new Orc();
     o->P = *p;
     params_to_sim(o->P, o->svar);
