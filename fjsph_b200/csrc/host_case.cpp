@@ -239,17 +239,17 @@ void get_vector(const std::string& line, const char* key, V3& out, int dim)
         return;
     std::istringstream iss(v);
     std::string item;
-    V3 r = out; /* a component that fails to parse keeps its old value (the reference leaves it uninitialised) */
+    /* IOFunctions.h:133-218: SIMDIM tokens; a missing token leaves the previous token's text in place (getline on an
+       exhausted stream does not touch its string) and is read again; text that is not a number reads as 0 */
     for (int d = 0; d < dim; ++d)
     {
-        if (!std::getline(iss, item, ','))
-            break;
+        std::getline(iss, item, ',');
         std::istringstream is2(item);
-        double t;
-        if (is2 >> t)
-            r[d] = t;
+        double t = 0.0;
+        if (!(is2 >> t))
+            t = 0.0;
+        out[d] = t;
     }
-    out = r;
 }
 
 int shape_type_of(const std::string& shape, int dim)
@@ -1456,12 +1456,8 @@ void fill_common(FjsphCase::Limit& L, const Block& b, int dim, bool is_fluid)
     L.blk.no_slip = b.no_slip ? 1 : 0;
     L.blk.block_type = b.bound_type;
     L.blk.fixed_vel_or_dynamic = b.fixed_vel_or_dynamic;
-    for (int d = 0; d < 3; ++d)
-    {
-        L.blk.insert_norm[d] = d == 0 ? 1.0 : 0.0;
-        L.blk.delete_norm[d] = d == 0 ? 1.0 : 0.0;
-        L.blk.aero_norm[d] = d == 0 ? 1.0 : 0.0;
-    }
+    /* bound_block's constructor (Var.h:781-815): planes unset; only fluid blocks get theirs copied (Init.cpp:455-461) */
+    for (int d = 0; d < 3; ++d) L.blk.insert_norm[d] = L.blk.delete_norm[d] = L.blk.aero_norm[d] = DEFV;
     L.blk.insconst = L.blk.delconst = L.blk.aeroconst = DEFV;
     (void)dim;
 }
@@ -1703,7 +1699,14 @@ extern "C" int fjsph_case_read(const char* para_path, int dim, FjsphCase** out)
     Shapes bound, fluid;
     std::string err;
     double gs = P.dx; /* Init_Particles passes a local copy of svar.dx the checks may raise (Init.cpp:272-290) */
-    if (bound_file[0] && !read_bmap(resolve(bound_file, pdir), C, gs, bound, err))
+    if (!bound_file[0])
+    {
+        /* the reference insists on both block files (IO.cpp:572-585); a case without walls names an empty one, as
+           Examples/Droplet does */
+        fj_set_error("Input boundary definition filename is not set in \"%s\"", para_path);
+        return FJSPH_ERR_IO;
+    }
+    if (!read_bmap(resolve(bound_file, pdir), C, gs, bound, err))
     {
         fj_set_error("boundary blocks: %s", err.c_str());
         return FJSPH_ERR_IO;

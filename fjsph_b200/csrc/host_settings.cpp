@@ -269,7 +269,6 @@ extern "C" int fjsph_read_para(const char* path, FjsphParams* p, char* fluid_fil
         return FJSPH_ERR_IO;
     }
     std::string solver_name, aero_case, line;
-    bool aero_seen = false;
     while (std::getline(fin, line))
     {
         const size_t hash = line.find('#');
@@ -285,7 +284,6 @@ extern "C" int fjsph_read_para(const char* path, FjsphParams* p, char* fluid_fil
         else if (key == "SPH aerodynamic case")
         {
             aero_case = val;
-            aero_seen = true;
         }
         else if (key == "Input fluid definition filename" && fluid_file)
             std::snprintf(fluid_file, size_t(name_cap), "%s", val.c_str());
@@ -311,16 +309,18 @@ extern "C" int fjsph_read_para(const char* path, FjsphParams* p, char* fluid_fil
             }
             else
             {
-                /* comma separated components (IOFunctions.h Get_Vector) */
+                /* comma separated components, exactly as IOFunctions.h:133-218 reads them: SIMDIM tokens; a token that
+                   is missing leaves the previous token's text in place (getline on an exhausted stream does not touch
+                   its string), so "0,0" in a 3D deck reads as (0, 0, 0); text that is not a number reads as 0 */
                 std::string item;
-                int d = 0;
-                while (d < 3 && std::getline(iss, item, ','))
+                for (int d = 0; d < (p->dim == 2 ? 2 : 3); ++d)
                 {
+                    std::getline(iss, item, ',');
                     std::istringstream is2(item);
-                    double v;
-                    if (is2 >> v)
-                        ((double*)dst)[d] = v;
-                    d++;
+                    double v = 0.0;
+                    if (!(is2 >> v))
+                        v = 0.0;
+                    ((double*)dst)[d] = v;
                 }
             }
         }
@@ -337,7 +337,8 @@ extern "C" int fjsph_read_para(const char* path, FjsphParams* p, char* fluid_fil
             return FJSPH_ERR_INVALID;
         }
     }
-    if (aero_seen)
+    /* AERO::aero_case starts empty and GetInput rejects anything but the four names (IO.cpp:606-627): a deck must
+       name its aerodynamic case, "(none)" included */
     {
         if (aero_case == "(none)")
             p->acase = 0;

@@ -53,7 +53,7 @@ def build(fast: bool = False) -> None:
 
 def build_ref() -> None:
     """Compile FJSPH's own sources from /root/reference into oracle/_ref/ (no-op where the reference is absent)."""
-    subprocess.check_call(["make", "-s", "-C", _HERE, "-f", "Makefile.ref"])
+    subprocess.check_call(["make", "-s", "-j4", "-C", _HERE, "-f", "Makefile.ref"])
 
 
 def have_ref(kind: str = "ref3d") -> bool:
@@ -350,6 +350,70 @@ class Oracle:
         s = OrcStepStats()
         e = self.lib.orc_integrate(self.h, C.byref(s))
         return float(e), s
+
+
+# ---- FJSPH's own front end (reference libraries only): GetInput + Init_Particles, the LIMITS blocks, FOAM::Read_FOAM
+def ref_read_case(para_path: str, kind: str = "ref3d") -> "Oracle":
+    """The deck through the reference's GetInput (IO.cpp:305-723) and Init_Particles (Init.cpp:270-496); the result is
+    a simulation handle like any other (get(), params, integrate(), ...).  A bad deck ends the process: the reference
+    calls exit()."""
+    lib = _load(kind)
+    lib.orc_ref_read_case.restype = C.c_void_p
+    lib.orc_ref_read_case.argtypes = [C.c_char_p]
+    o = Oracle.__new__(Oracle)
+    o.dim = 2 if "2d" in kind else 3
+    o.kind, o.lib = kind, lib
+    o.h = lib.orc_ref_read_case(os.fsencode(para_path))
+    return o
+
+
+def ref_blocks(o: "Oracle") -> list:
+    """The LIMITS vector (Var.h:779-859) of a reference handle as dicts with the keys Engine.set_blocks takes."""
+    lib = o.lib
+    lib.orc_ref_block_info.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+    lib.orc_ref_block_arrays.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    nb = int(lib.orc_ref_num_bound_blocks(C.c_void_p(o.h)))
+    out = []
+    for i in range(int(lib.orc_ref_num_blocks(C.c_void_p(o.h)))):
+        rng, ints = np.zeros(2, dtype=np.int64), np.zeros(8, dtype=np.int32)
+        norms, consts, name = np.zeros(9), np.zeros(3), C.create_string_buffer(256)
+        assert lib.orc_ref_block_info(o.h, i, _ptr(rng), _ptr(ints), _ptr(norms), _ptr(consts), name, 256) == 0
+        nt, nback, nbuf = int(ints[0]), int(ints[1]), int(ints[2])
+        times, vels = np.zeros(max(nt, 1)), np.zeros((max(nt, 1) + 1, 3))
+        back, buf = np.zeros(max(nback, 1), dtype=np.int64), np.zeros((max(nback, 1), max(nbuf, 1)), dtype=np.int64)
+        nv = lib.orc_ref_block_arrays(o.h, i, _ptr(times), _ptr(vels), _ptr(back), _ptr(buf))
+        out.append(dict(name=name.value.decode(), first=int(rng[0]), second=int(rng[1]), is_fluid=int(i >= nb), n_times=nt,
+                        bound_solver=int(ints[3]), no_slip=int(ints[4]), block_type=int(ints[5]),
+                        fixed_vel_or_dynamic=int(ints[6]), particle_order=int(ints[7]), times=times[:nt], vels=vels[:nv],
+                        insert_norm=tuple(norms[0:3]), delete_norm=tuple(norms[3:6]), aero_norm=tuple(norms[6:9]),
+                        insconst=float(consts[0]), delconst=float(consts[1]), aeroconst=float(consts[2]),
+                        back=back[:nback], buffer=buf[:nback, :nbuf]))
+    return out
+
+
+def ref_mesh(o: "Oracle") -> dict:
+    """The MESH of a reference handle (Var.h:396-451) in the layout of fjsph_b200.cases.hex_mesh."""
+    lib = o.lib
+    lib.orc_ref_mesh_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    lib.orc_ref_mesh_arrays.argtypes = [C.c_void_p] * 11
+    sz = np.zeros(5, dtype=np.int64)
+    lib.orc_ref_mesh_sizes(o.h, _ptr(sz))
+    nv, nf, nc, nfv, ncf = (int(k) for k in sz)
+    d = o.dim
+    m = dict(verts=np.zeros((nv, d)), face_ptr=np.zeros(nf + 1, dtype=np.int64), face_vtx=np.zeros(nfv, dtype=np.int64),
+             leftright=np.zeros((nf, 2), dtype=np.int32), cell_ptr=np.zeros(nc + 1, dtype=np.int64),
+             cell_faces=np.zeros(ncf, dtype=np.int64), cCentre=np.zeros((nc, d)), cVel=np.zeros((nc, d)), cP=np.zeros(nc),
+             cRho=np.zeros(nc))
+    lib.orc_ref_mesh_arrays(o.h, *[_ptr(m[k]) for k in ("verts", "face_ptr", "face_vtx", "leftright", "cell_ptr",
+                                                        "cell_faces", "cCentre", "cVel", "cP", "cRho")])
+    return m
+
+
+def ref_read_foam(o: "Oracle", foam_dir: str, foam_sol: str, buoyant: bool = False) -> dict:
+    """FOAM::Read_FOAM (FOAMIO.cpp:538-955) on an ASCII case; returns the mesh it built."""
+    o.lib.orc_ref_read_foam.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int]
+    o.lib.orc_ref_read_foam(o.h, os.fsencode(foam_dir), os.fsencode(foam_sol), int(buoyant))
+    return ref_mesh(o)
 
 
 def qr_inverse(a: np.ndarray):

@@ -1,8 +1,10 @@
 /* ref_harness.cpp — TEST INFRASTRUCTURE ONLY.
  *
- * The orc_* C ABI of fjsph_oracle.h on top of FJSPH's OWN time-step sources, compiled unmodified from where they lie
- * under /root/reference/src (Neighbours, Shifting, Resid, Geometry, Containment, Newmark_Beta, Runge_Kutta, Integration,
- * shapes/inlet .cpp; recipe: oracle/Makefile.ref, output: oracle/_ref/liborc_ref*.so).  The two header-only libraries
+ * The orc_* C ABI of fjsph_oracle.h on top of FJSPH's OWN sources, compiled unmodified from where they lie under
+ * /root/reference/src: the time step (Neighbours, Shifting, Resid, Geometry, Containment, Newmark_Beta, Runge_Kutta,
+ * Integration .cpp) and the callers either side of it (IO.cpp: GetInput / Set_Values; Init.cpp: Init_Particles;
+ * shapes/{shapes,square,circle,cylinder,line,coordinates,inlet}.cpp: the bmap reader and the generators; FOAMIO.cpp: the
+ * OpenFOAM reader).  Recipe: oracle/Makefile.ref, output: oracle/_ref/liborc_ref*.so.  The two header-only libraries
  * the reference does not vendor (Eigen, nanoflann) are replaced by the stand-ins of oracle/shim/, so:
  *   - what this library pins is FJSPH's arithmetic and control flow (pair loops, surface logic, boundary treatment,
  *     aero coupling, containment, integrators, inlet bookkeeping) -- the oracle restatement is checked against it in
@@ -10,7 +12,7 @@
  *   - Eigen's / nanoflann's own arithmetic (QR inverse, direct eigenvalues, 4x4 determinant, search order) is the
  *     shim's restatement of the published algorithms and stays unpinned.
  * Nothing in fjsph_b200/ links or loads this.  Functions of the reference that the path links but never runs here
- * (IPT::Integrate, VLM::getVelocity, the ShapeBlock front end) are stubs that abort.
+ * (IPT::Integrate, the VLM, the Tecplot-binary and h5part writers, Arc blocks) are stubs that abort.
  *
  * OpenMP: the reference's loops keep their pragmas; the harness pins one thread so that reductions are deterministic
  * and the npd data race cannot occur.
@@ -35,7 +37,16 @@
 #include "Resid.h"
 #include "Runge_Kutta.h"
 #include "Shifting.h"
+#include "BinaryIO.h"
+#include "FOAMIO.h"
+#include "H5IO.h"
+#include "IO.h"
+#include "Init.h"
+#include "shapes/arc.h"
 #include "shapes/inlet.h"
+
+#include <filesystem>
+#include <unistd.h>
 
 #include "fjsph_oracle.h"
 
@@ -58,10 +69,24 @@ StateVecD VLM::getVelocity(StateVecD const&) const
     not_on_path("VLM::getVelocity");
     return StateVecD::Zero();
 }
+void VLM::Init(std::string) { not_on_path("VLM::Init"); }
+void VLM::GetGamma(StateVecD) { not_on_path("VLM::GetGamma"); }
+void VLM::write_VLM_Panels(std::string&) { not_on_path("VLM::write_VLM_Panels"); }
+void VLM::Plot_Streamlines(std::string&) { not_on_path("VLM::Plot_Streamlines"); }
 #endif
-void ShapeBlock::check_input(SIM const&, real&, int&) { not_on_path("ShapeBlock::check_input"); }
-void ShapeBlock::check_input_post(real&) { not_on_path("ShapeBlock::check_input_post"); }
-void ShapeBlock::generate_points(real const&) { not_on_path("ShapeBlock::generate_points"); }
+void ArcShape::check_input(SIM const&, real&, int&) { not_on_path("ArcShape::check_input"); }
+void ArcShape::generate_points(real const&) { not_on_path("ArcShape::generate_points"); }
+/* TECIO / HDF5 writers (BinaryIO.cpp, H5IO.cpp need the absent libraries) */
+void Write_Binary_Timestep(SIM const&, real const&, SPHState const&, bound_block const&, char const*, int32_t const&,
+                           void* const&)
+{
+    not_on_path("Write_Binary_Timestep");
+}
+void Init_Binary_PLT(SIM&, std::string const&, std::string const&, std::string const&, void*&) { not_on_path("Init_Binary_PLT"); }
+void close_file(void*) { not_on_path("close_file"); }
+void open_h5part_files(SIM&, string const&) { not_on_path("open_h5part_files"); }
+void close_h5part_files(SIM&) { not_on_path("close_h5part_files"); }
+void write_h5part_data(SIM&, SPHState const&) { not_on_path("write_h5part_data"); }
 
 /* ---- the handle ----------------------------------------------------------------------------- */
 struct Orc
@@ -184,6 +209,98 @@ static void params_to_sim(const OrcParams& P, SIM& s)
     s.Asource = P.asource;
     s.ipt.using_ipt = 0;
     s.numThreads = 1;
+}
+
+/* SIM -> OrcParams, every field (after the reference's own GetInput + Set_Values) */
+static void sim_to_params_full(const SIM& s, OrcParams& P)
+{
+    std::memset(&P, 0, sizeof(P));
+    P.dim = SIMDIM;
+#ifdef ALE
+    P.ale = 1;
+#endif
+    P.pressure_rel = int(s.fluid.pressure_rel);
+    P.solver_type = int(s.integrator.solver_type);
+    P.acase = s.air.acase;
+    P.asource = s.Asource;
+    P.use_lam = s.air.use_lam;
+    P.use_TAB_def = s.air.use_TAB_def;
+    P.max_subits = int(s.integrator.max_subits);
+    P.n_stable = int(s.integrator.n_stable);
+    P.n_stable_limit = int(s.integrator.n_stable_limit);
+    P.n_unstable = int(s.integrator.n_unstable);
+    P.n_unstable_limit = int(s.integrator.n_unstable_limit);
+    P.particle_step = s.particle_step;
+    P.H_fac = s.fluid.H_fac;
+    P.rho_rest = s.fluid.rho_rest;
+    P.press_pipe = s.fluid.press_pipe;
+    P.press_back = s.fluid.press_back;
+    P.rho_max = s.fluid.rho_max;
+    P.rho_min = s.fluid.rho_min;
+    P.rho_var = s.fluid.rho_var;
+    P.rho_max_iter = s.fluid.rho_max_iter;
+    P.visc_alpha = s.fluid.visc_alpha;
+    P.speed_sound = s.fluid.speed_sound;
+    P.mu = s.fluid.mu;
+    P.sig = s.fluid.sig;
+    P.gam = s.fluid.gam;
+    P.dsph_delta = s.fluid.dsph_delta;
+    for (int d = 0; d < SIMDIM; ++d)
+    {
+        P.grav[d] = s.grav[d];
+        P.v_inf[d] = s.air.v_inf[d];
+    }
+    P.p_ref = s.air.p_ref;
+    P.rho_g = s.air.rho_g;
+    P.mu_g = s.air.mu_g;
+    P.temp_g = s.air.temp_g;
+    P.R_g = s.air.R_g;
+    P.gamma_g = s.air.gamma;
+    P.lam_cutoff = s.air.lam_cutoff;
+    P.i_interp_fac = s.air.i_interp_fac;
+    P.tab_Cf = s.air.Cf;
+    P.tab_Ck = s.air.Ck;
+    P.tab_Cd = s.air.Cd;
+    P.tab_Cb = s.air.Cb;
+    P.cfl = s.integrator.cfl;
+    P.cfl_step = s.integrator.cfl_step;
+    P.cfl_max = s.integrator.cfl_max;
+    P.cfl_min = s.integrator.cfl_min;
+    P.subits_factor = s.integrator.subits_factor;
+    P.min_residual = s.integrator.min_residual;
+    P.delta_t = s.integrator.delta_t;
+    P.delta_t_max = s.integrator.delta_t_max;
+    P.delta_t_min = s.integrator.delta_t_min;
+    P.max_shift_vel = s.integrator.max_shift_vel;
+    P.current_time = s.integrator.current_time;
+    P.last_frame_time = s.integrator.last_frame_time;
+    P.frame_time_interval = s.integrator.frame_time_interval;
+    P.B = s.fluid.B;
+    P.rho_pipe = s.fluid.rho_pipe;
+    P.dx = s.dx;
+    P.sim_mass = s.fluid.sim_mass;
+    P.bnd_mass = s.fluid.bnd_mass;
+    P.H = s.fluid.H;
+    P.H_sq = s.fluid.H_sq;
+    P.sr = s.fluid.sr;
+    P.dsph_cont = s.fluid.dsph_cont;
+    P.nu = s.fluid.nu;
+    P.W_correc = s.fluid.W_correc;
+    P.W_dx = s.fluid.W_dx;
+    P.nb_beta = s.integrator.nb_beta;
+    P.nb_gamma = s.integrator.nb_gamma;
+    P.aero_L = s.air.L;
+    P.A_sphere = s.air.A_sphere;
+    P.A_plate = s.air.A_plate;
+    P.td = s.air.td;
+    P.omega = s.air.omega;
+    P.tmax = s.air.tmax;
+    P.Cdef = s.air.Cdef;
+    P.ycoef = s.air.ycoef;
+    P.n_full = s.air.n_full;
+    P.i_n_full = s.air.i_n_full;
+    P.interp_fac = s.air.interp_fac;
+    P.sos = s.air.sos;
 }
 
 static void sim_to_params(const SIM& s, OrcParams& P)
@@ -372,6 +489,163 @@ void orc_clear_blocks(Orc* o)
     o->limits.clear();
     o->svar.n_bound_blocks = o->svar.n_fluid_blocks = 0;
 }
+/* ---- the callers either side of the path: FJSPH's own front end ------------------------------------------------ */
+
+/* GetInput (IO.cpp:305-723, with its Set_Values) + Init_Particles (Init.cpp:270-496) on a para deck, run from the deck's
+ * directory as FJSPH is.  The reference exits the process on a bad deck. */
+Orc* orc_ref_read_case(const char* para_path)
+{
+    namespace fs = std::filesystem;
+    omp_set_num_threads(1);
+    Orc* o = new Orc();
+    fs::path const para = fs::absolute(para_path);
+    fs::path const cwd = fs::current_path();
+    fs::current_path(para.parent_path());
+    std::string name = para.filename().string();
+    char prog[] = "FJSPH";
+    char* argv[2] = {prog, name.data()};
+    GetInput(2, argv, o->svar);
+    o->pn.reserve(o->svar.max_points); /* FJSPH.cpp:98-99 */
+    o->pnp1.reserve(o->svar.max_points);
+    Init_Particles(o->svar, o->pn, o->pnp1, o->limits);
+    if (o->svar.Asource != meshInfl)
+    { /* FJSPH.cpp:113-126 */
+        for (size_t ii = 0; ii < o->pnp1.size(); ++ii)
+        {
+            o->pn[ii].cellRho = o->pnp1[ii].cellRho = o->svar.air.rho_g;
+            o->pn[ii].cellP = o->pnp1[ii].cellP = o->svar.air.p_ref;
+            o->pn[ii].cellV = o->pnp1[ii].cellV = o->svar.air.v_inf;
+        }
+    }
+    fs::current_path(cwd);
+    sim_to_params_full(o->svar, o->P);
+    o->svar.numThreads = 1;
+    o->sph_tree = new Sim_Tree(SIMDIM, o->pnp1, 20);
+    if (o->cells.cCentre.size() == 0)
+        o->cells.cCentre.emplace_back(StateVecD::Zero());
+    o->cell_tree = new Vec_Tree(SIMDIM, o->cells.cCentre, 10);
+    o->cell_tree->index->buildIndex();
+    o->integ = new Integrator(int(o->svar.integrator.solver_type));
+    return o;
+}
+int orc_ref_num_blocks(Orc* o) { return int(o->limits.size()); }
+int orc_ref_num_bound_blocks(Orc* o) { return int(o->svar.n_bound_blocks); }
+/* sizes first (ints: nTimes, n_back, n_buf, bound_solver, no_slip, block_type, fixed_vel_or_dynamic, particle_order),
+ * then the arrays into caller buffers of those sizes (any may be NULL) */
+int orc_ref_block_info(Orc* o, int block, int64_t* range, int32_t* ints, double* norms /* 3 x 3 */, double* consts /* 3 */,
+                       char* name, int name_cap)
+{
+    if (block < 0 || size_t(block) >= o->limits.size())
+        return -1;
+    bound_block const& B = o->limits[size_t(block)];
+    range[0] = int64_t(B.index.first);
+    range[1] = int64_t(B.index.second);
+    ints[0] = int32_t(B.nTimes);
+    ints[1] = int32_t(B.back.size());
+    ints[2] = int32_t(B.buffer.empty() ? 0 : B.buffer[0].size());
+    ints[3] = B.bound_solver;
+    ints[4] = B.no_slip;
+    ints[5] = B.block_type;
+    ints[6] = B.fixed_vel_or_dynamic;
+    ints[7] = B.particle_order;
+    for (int d = 0; d < 3; ++d)
+    {
+        norms[d] = d < SIMDIM ? B.insert_norm[d] : 0.0;
+        norms[3 + d] = d < SIMDIM ? B.delete_norm[d] : 0.0;
+        norms[6 + d] = d < SIMDIM ? B.aero_norm[d] : 0.0;
+    }
+    consts[0] = B.insconst;
+    consts[1] = B.delconst;
+    consts[2] = B.aeroconst;
+    if (name && name_cap > 0)
+    {
+        std::strncpy(name, B.name.c_str(), size_t(name_cap) - 1);
+        name[name_cap - 1] = 0;
+    }
+    return 0;
+}
+int orc_ref_block_arrays(Orc* o, int block, double* times, double* vels /* max(1,nTimes) x 3 */, int64_t* back, int64_t* buffer)
+{
+    if (block < 0 || size_t(block) >= o->limits.size())
+        return -1;
+    bound_block const& B = o->limits[size_t(block)];
+    if (times)
+        for (size_t t = 0; t < B.times.size(); ++t) times[t] = B.times[t];
+    if (vels)
+        for (size_t t = 0; t < B.vels.size(); ++t)
+            for (int d = 0; d < 3; ++d) vels[3 * t + d] = d < SIMDIM ? B.vels[t][d] : 0.0;
+    if (back)
+        for (size_t i = 0; i < B.back.size(); ++i) back[i] = int64_t(B.back[i]);
+    if (buffer)
+        for (size_t i = 0; i < B.buffer.size(); ++i)
+            for (size_t j = 0; j < B.buffer[i].size(); ++j) buffer[i * B.buffer[i].size() + j] = int64_t(B.buffer[i][j]);
+    return int(B.vels.size());
+}
+
+#if SIMDIM == 3
+/* FOAM::Read_FOAM (FOAMIO.cpp:538-955) on an ASCII case directory; the mesh goes into the handle (and can be read back
+ * with orc_ref_mesh_sizes / orc_ref_mesh_arrays) */
+int orc_ref_read_foam(Orc* o, const char* foam_dir, const char* foam_sol, int buoyant)
+{
+    o->svar.io.foam_dir = foam_dir;
+    o->svar.io.foam_sol = foam_sol;
+    o->svar.io.foam_is_binary = false;
+    o->svar.io.foam_buoyant_sim = buoyant != 0;
+    o->svar.io.mesh_source = OpenFOAM;
+    o->svar.Asource = meshInfl;
+    delete o->cell_tree;
+    o->cell_tree = nullptr;
+    o->cells = MESH();
+    FOAM::Read_FOAM(o->svar, o->cells);
+    o->cell_tree = new Vec_Tree(SIMDIM, o->cells.cCentre, 10);
+    o->cell_tree->index->buildIndex();
+    return 0;
+}
+#endif
+void orc_ref_mesh_sizes(Orc* o, int64_t* out /* verts, faces, cells, face_vtx total, cell_faces total */)
+{
+    MESH const& M = o->cells;
+    out[0] = int64_t(M.verts.size());
+    out[1] = int64_t(M.faces.size());
+    out[2] = int64_t(M.cFaces.size());
+    int64_t t = 0;
+    for (auto const& f : M.faces) t += int64_t(f.size());
+    out[3] = t;
+    t = 0;
+    for (auto const& c : M.cFaces) t += int64_t(c.size());
+    out[4] = t;
+}
+void orc_ref_mesh_arrays(Orc* o, double* verts, int64_t* face_ptr, int64_t* face_vtx, int32_t* leftright, int64_t* cell_ptr,
+                         int64_t* cell_faces, double* cCentre, double* cVel, double* cP, double* cRho)
+{
+    MESH const& M = o->cells;
+    for (size_t i = 0; i < M.verts.size(); ++i)
+        for (int d = 0; d < SIMDIM; ++d) verts[i * SIMDIM + d] = M.verts[i][d];
+    int64_t k = 0;
+    face_ptr[0] = 0;
+    for (size_t f = 0; f < M.faces.size(); ++f)
+    {
+        for (size_t v : M.faces[f]) face_vtx[k++] = int64_t(v);
+        face_ptr[f + 1] = k;
+        leftright[2 * f] = M.leftright[f].first;
+        leftright[2 * f + 1] = M.leftright[f].second;
+    }
+    k = 0;
+    cell_ptr[0] = 0;
+    for (size_t c = 0; c < M.cFaces.size(); ++c)
+    {
+        for (size_t f : M.cFaces[c]) cell_faces[k++] = int64_t(f);
+        cell_ptr[c + 1] = k;
+        for (int d = 0; d < SIMDIM; ++d)
+        {
+            cCentre[c * SIMDIM + d] = M.cCentre[c][d];
+            cVel[c * SIMDIM + d] = M.cVel[c][d];
+        }
+        cP[c] = M.cP[c];
+        cRho[c] = c < M.cRho.size() ? M.cRho[c] : 0.0;
+    }
+}
+
 int orc_get_block_range(Orc* o, int block, int64_t* first, int64_t* second)
 {
     if (block < 0 || size_t(block) >= o->limits.size())

@@ -17,6 +17,10 @@ def deck(name):
     return os.path.join(DECKS, name)
 
 
+# a case without walls names an empty boundary file, as the reference's Examples/Droplet does
+NO_WALLS = " -----------------------------------------------------\n BOUNDARY MAPPING\n -----------------------------------------------------\n"
+
+
 def write(tmp_path, name, text):
     p = tmp_path / name
     p.write_text(text)
@@ -140,6 +144,7 @@ def test_intersecting_particles_are_removed(tmp_path):
  Input boundary definition filename: %s
     Input fluid definition filename: %s
                SPH initial spacing: 0.1
+              SPH aerodynamic case: (none)
            SPH frame time interval: 0.1
 """ % (tmp_path / "b.bmap", tmp_path / "f.bmap"))
     c = frontend.read_case(para, 3)
@@ -167,10 +172,12 @@ def test_hcp_cube_spacing(tmp_path):
  block end
 """)
     para = write(tmp_path, "para", """
+ Input boundary definition filename: %s
     Input fluid definition filename: %s
                SPH initial spacing: 0.1
+              SPH aerodynamic case: (none)
            SPH frame time interval: 0.1
-""" % (tmp_path / "f.bmap"))
+""" % (write(tmp_path, "none.bmap", NO_WALLS), tmp_path / "f.bmap"))
     c = frontend.read_case(para, 3)
     ni, nj, nk = 10, int(np.ceil(1 / 0.1 / np.sqrt(3) * 2)), int(np.ceil(1 / 0.1 / np.sqrt(6) * 3))
     assert c["xi"].shape[0] == ni * nj * nk
@@ -205,6 +212,7 @@ def test_moving_wall_schedule_and_errors(tmp_path):
  Input boundary definition filename: %s
     Input fluid definition filename: %s
                SPH initial spacing: 0.1
+              SPH aerodynamic case: (none)
            SPH frame time interval: 0.1
 """ % (tmp_path / "b.bmap", tmp_path / "f.bmap"))
     c = frontend.read_case(para, 2)
@@ -215,11 +223,18 @@ def test_moving_wall_schedule_and_errors(tmp_path):
     assert np.allclose(piston["vels"][:, :2], [[2.0, 0.0], [0.0, 2.0], [0.0, 0.0]])
     # errors come back as FjsphError with the reference's diagnosis, never exit()
     bad = write(tmp_path, "bad.bmap", "   Name: X\n  Shape: Blob\n block end\n")
-    para2 = write(tmp_path, "para2", " Input fluid definition filename: %s\n SPH initial spacing: 0.1\n SPH frame time interval: 1\n" % bad)
+    none = " Input boundary definition filename: %s\n" % write(tmp_path, "none.bmap", NO_WALLS)
+    para2 = write(tmp_path, "para2", none + " Input fluid definition filename: %s\n SPH initial spacing: 0.1\n SPH aerodynamic case: (none)\n SPH frame time interval: 1\n" % bad)
     with pytest.raises(_lib.FjsphError, match="Unrecognised boundary shape"):
         frontend.read_case(para2, 2)
     with pytest.raises(_lib.FjsphError, match="file missing"):
-        frontend.read_case(write(tmp_path, "para3", " Input fluid definition filename: nope.bmap\n SPH initial spacing: 0.1\n"), 2)
-    nodx = write(tmp_path, "para4", " Input fluid definition filename: %s\n" % (tmp_path / "f.bmap"))
+        frontend.read_case(write(tmp_path, "para3", none + " Input fluid definition filename: nope.bmap\n SPH initial spacing: 0.1\n SPH aerodynamic case: (none)\n"), 2)
+    # the reference insists on both block files (IO.cpp:555-585)
+    with pytest.raises(_lib.FjsphError, match="boundary definition filename"):
+        frontend.read_case(write(tmp_path, "para5", " Input fluid definition filename: %s\n SPH initial spacing: 0.1\n SPH aerodynamic case: (none)\n" % (tmp_path / "f.bmap")), 2)
+    nodx = write(tmp_path, "para4", none + " Input fluid definition filename: %s\n SPH aerodynamic case: (none)\n" % (tmp_path / "f.bmap"))
+    with pytest.raises(_lib.FjsphError, match="Aerodynamic coupling model"):   # IO.cpp:606-627: the case must be named
+        frontend.read_case(write(tmp_path, "para6", none + " Input fluid definition filename: %s\n SPH initial spacing: 0.1\n"
+                                 .replace(" SPH aerodynamic case: (none)\n", "") % (tmp_path / "f.bmap")), 2)
     with pytest.raises(_lib.FjsphError, match="initial spacing"):
         frontend.read_case(nodx, 2)

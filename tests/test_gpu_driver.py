@@ -20,7 +20,7 @@ def frame(path):
 def test_driver_runs_a_deck_and_resumes(tmp_path):
     if not os.path.exists(BIN):
         pytest.fail("driver not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
-    for f in ("droplet3d.para", "droplet3d_fluid.bmap"):
+    for f in ("droplet3d.para", "droplet3d_fluid.bmap", "droplet3d_boundary.bmap"):
         shutil.copy(os.path.join(ROOT, "tests", "decks", f), tmp_path / f)
     para = tmp_path / "droplet3d.para"
     para.write_text(para.read_text().replace("SPH frame time interval: 0.001", "SPH frame time interval: 4e-5")
