@@ -689,6 +689,8 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
     FJ_CUDA(cudaMalloc(&e->scount, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->xref, cap * sizeof(double4)));
     e->skin = 0.4 * e->P.particle_step; /* default skin: 0.4 dx = 5 % of the support radius at H_fac = 2 */
+    if (const char* order = std::getenv("FJSPH_B200_CELL_ORDER")) /* "morton" | "pencil" (default), engine.cuh */
+        e->pencil_order = std::string(order) != "morton";
     FJ_CUDA(cudaMalloc(&e->near_inlet, cap * sizeof(int)));
     FJ_CUDA(cudaMemset(e->near_inlet, 0, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->rk_sum_v, cap * sizeof(double4)));

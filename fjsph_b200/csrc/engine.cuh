@@ -58,10 +58,13 @@ struct DevConst
 
 struct Grid
 {
-    double ox, oy, oz, inv_cell;
-    int nx, ny, nz;           // cells per axis
-    int bx, by, bz;           // Morton bits per axis
-    unsigned int n_keys;      // 2^(bx+by+bz)
+    double ox, oy, oz, inv_cell; // inv_cell: 1 / cell edge along x (>= 2H + skin: reach 1)
+    double inv_cy, inv_cz;       // 1 / cell edge along y and z (pencil order: ~ one particle spacing; else = inv_cell)
+    double pw2, r_skin2;         // (cell edge along y, z)^2 and (2H + skin)^2, to cull pencils outside the disc
+    int ry, rz;                  // cells to visit either side along y and z (1 for cubic cells)
+    int nx, ny, nz;              // cells per axis
+    int bx, by, bz;              // key bits per axis
+    unsigned int n_keys;         // 2^(bx+by+bz)
 };
 
 // X(name): the double4 record arrays of a level, in halo-mask bit order
@@ -202,6 +205,12 @@ struct FjsphEngine
     int nb_cap = 0;
     size_t nlist_words = 0;
     bool list_valid = false;
+    // Memory order of the particles (decided at fjsph_create from FJSPH_B200_CELL_ORDER, default "pencil"):
+    //   pencil: cells are R x dx x dx bricks keyed lexicographically (x fastest), so consecutive particles run along x
+    //           inside a one-spacing-wide pencil and the 32 lanes of a warp walk translated copies of each other's
+    //           neighbourhoods -- slot s of their lists lands in ~14 cache lines instead of ~24 on lattice-born fluids;
+    //   morton: cubic cells of edge 2H + skin in Morton order.
+    bool pencil_order = true;
 
     // reductions / scalars
     double* red = nullptr;              // device scratch for block partials

@@ -7,7 +7,8 @@
 // count+1).
 //
 // Pipeline per build (all on e->stream):
-//   bounds -> Morton key + warp-aggregated histogram -> block prefix scan -> scatter
+//   bounds -> cell key (pencil cells, x fastest, by default; Morton keys for cubic cells: engine.cuh pencil_order)
+//   + warp-aggregated histogram -> block prefix scan -> scatter
 //   -> per-cell ordering by caller index (determinism) -> permute both time levels into cell order
 //   -> neighbour list in a warp-transposed ELL layout (entry (warp w, slot s, lane l) at
 //      ((w*nb_cap)+s)*32+l, so a warp reads slot s of its 32 particles with one 128-byte load).
@@ -94,8 +95,8 @@ __global__ void k_bounds_final(const double* __restrict__ partial, int nblocks, 
 __device__ __forceinline__ void cell_of(const Grid& g, double x, double y, double z, int& cx, int& cy, int& cz)
 {
     cx = min(max(int(floor((x - g.ox) * g.inv_cell)), 0), g.nx - 1);
-    cy = min(max(int(floor((y - g.oy) * g.inv_cell)), 0), g.ny - 1);
-    cz = min(max(int(floor((z - g.oz) * g.inv_cell)), 0), g.nz - 1);
+    cy = min(max(int(floor((y - g.oy) * g.inv_cy)), 0), g.ny - 1);
+    cz = min(max(int(floor((z - g.oz) * g.inv_cz)), 0), g.nz - 1);
 }
 
 // Slab mode sorts three classes one behind the other (key offsets 0, n_keys, 2 n_keys): INTERIOR owned particles
@@ -213,16 +214,22 @@ __global__ void __launch_bounds__(TPB)
     uint4* __restrict__ dst = reinterpret_cast<uint4*>(slist) + (size_t(i >> 5) * size_t(scap >> 2)) * 32u + (i & 31);
     unsigned eb0 = unsigned(i), eb1 = unsigned(i), eb2 = unsigned(i);
     int cnt = 0;
-    for (int dz = -1; dz <= 1; ++dz)
+    /* cells in ascending key order (z, then y, then x), so the list comes out sorted by index */
+    for (int dz = -g.rz; dz <= g.rz; ++dz)
     {
         const int z = cz + dz;
         if (z < 0 || z >= g.nz)
             continue;
         const unsigned kz = mz[z];
-        for (int dy = -1; dy <= 1; ++dy)
+        const int gz = max(abs(dz) - 1, 0);
+        for (int dy = -g.ry; dy <= g.ry; ++dy)
         {
             const int y = cy + dy;
             if (y < 0 || y >= g.ny)
+                continue;
+            /* narrow cells: a pencil whose cross-section lies wholly outside the disc of radius 2H + skin holds nobody */
+            const int gy = max(abs(dy) - 1, 0);
+            if (double(gy * gy + gz * gz) * g.pw2 > g.r_skin2)
                 continue;
             const unsigned kyz = kz | my[y];
             for (int dx = -1; dx <= 1; ++dx)
@@ -452,23 +459,40 @@ static int rebuild_skin(FjsphEngine* e)
             fj_set_error("build_neighbours: non-finite particle positions");
             return FJSPH_ERR_STATE;
         }
-    // grid: cell edge a hair above the skin radius 2H + skin so +-1 cell always covers it
+    // grid: cell edge along x a hair above the skin radius 2H + skin so +-1 cell always covers it.  Pencil order
+    // narrows the cells along y and z to about one particle spacing (and visits +-ry, +-rz of them), with the origin half
+    // a cell below the lowest particle so that the rows of a lattice-born fluid sit in the middle of their pencils.
     Grid g;
     const double r_skin = std::sqrt(e->P.sr) + e->skin;
     const double cell = r_skin * (1.0 + 1e-7);
-    g.inv_cell = 1.0 / cell;
-    g.ox = lo[0];
-    g.oy = lo[1];
-    g.oz = lo[2];
-    g.nx = int(std::floor((hi[0] - lo[0]) * g.inv_cell)) + 1;
-    g.ny = int(std::floor((hi[1] - lo[1]) * g.inv_cell)) + 1;
-    g.nz = int(std::floor((hi[2] - lo[2]) * g.inv_cell)) + 1;
-    g.bx = bits_for(g.nx);
-    g.by = bits_for(g.ny);
-    g.bz = bits_for(g.nz);
+    double pw = cell;
+    if (e->pencil_order && e->P.particle_step > 0.0)
+        pw = std::min(cell, std::max(e->P.particle_step, cell / 8.0));
+    for (;;)
+    {
+        const bool narrow = pw < cell;
+        g.inv_cell = 1.0 / cell;
+        g.inv_cy = g.inv_cz = 1.0 / pw;
+        g.pw2 = pw * pw;
+        g.r_skin2 = r_skin * r_skin;
+        g.ry = g.rz = narrow ? int(std::ceil(cell / pw)) : 1;
+        g.ox = lo[0];
+        g.oy = lo[1] - (narrow ? 0.5 * pw : 0.0);
+        g.oz = lo[2] - (narrow ? 0.5 * pw : 0.0);
+        g.nx = int(std::floor((hi[0] - g.ox) * g.inv_cell)) + 1;
+        g.ny = int(std::floor((hi[1] - g.oy) * g.inv_cy)) + 1;
+        g.nz = int(std::floor((hi[2] - g.oz) * g.inv_cz)) + 1;
+        g.bx = bits_for(g.nx);
+        g.by = bits_for(g.ny);
+        g.bz = bits_for(g.nz);
+        /* the key tables (count + start per class) stay below ~1 GB: wider pencils for very large cross-sections */
+        if (!narrow || g.bx + g.by + g.bz <= 25)
+            break;
+        pw = std::min(cell, 2.0 * pw);
+    }
     if (g.bx + g.by + g.bz > 29)
     {
-        fj_set_error("cell grid %d x %d x %d needs more than 2^29 Morton keys", g.nx, g.ny, g.nz);
+        fj_set_error("cell grid %d x %d x %d needs more than 2^29 keys", g.nx, g.ny, g.nz);
         return FJSPH_ERR_CAPACITY;
     }
     g.n_keys = 1u << (g.bx + g.by + g.bz);
@@ -482,7 +506,8 @@ static int rebuild_skin(FjsphEngine* e)
     int st = ensure_key_capacity(e, n_tab);
     if (st)
         return st;
-    // Morton spread tables: bit l of each axis is placed round-robin x,y,z among the axes that still have bits
+    // key tables, one per axis, OR-ed together: lexicographic fields (pencil order) or Morton spreading (bit l of each
+    // axis placed round-robin x,y,z among the axes that still have bits)
     {
         const int need = std::max(g.nx, std::max(g.ny, g.nz));
         if (need > e->mtab_cap)
@@ -499,10 +524,16 @@ static int rebuild_skin(FjsphEngine* e)
         int pos[3][32];
         int out = 0;
         const int bits[3] = {g.bx, g.by, g.bz};
-        for (int l = 0; l < 32; ++l)
+        if (e->pencil_order)
+        { /* lexicographic: x in the low bits, then y, then z -- consecutive keys run along x */
             for (int a = 0; a < 3; ++a)
-                if (l < bits[a])
-                    pos[a][l] = out++;
+                for (int l = 0; l < bits[a]; ++l) pos[a][l] = out++;
+        }
+        else
+            for (int l = 0; l < 32; ++l)
+                for (int a = 0; a < 3; ++a)
+                    if (l < bits[a])
+                        pos[a][l] = out++;
         std::vector<unsigned> tab(size_t(3) * e->mtab_cap, 0u);
         const int dims[3] = {g.nx, g.ny, g.nz};
         for (int a = 0; a < 3; ++a)
@@ -520,7 +551,7 @@ static int rebuild_skin(FjsphEngine* e)
     }
     e->grid = g;
 
-    // counting sort by Morton key
+    // counting sort by cell key
     Level& S = e->lv[1];
     {
         KScope ks(e, "nb_sort", 7);
