@@ -211,6 +211,12 @@ struct FjsphEngine
     //           neighbourhoods -- slot s of their lists lands in ~14 cache lines instead of ~24 on lattice-born fluids;
     //   morton: cubic cells of edge 2H + skin in Morton order.
     bool pencil_order = true;
+    // Order inside each chunk of four list entries (FJSPH_B200_LIST_ORDER = "index" (default) | "columns"): see chunk_slot
+    // in neighbours.cu -- with "columns", element e of a chunk of lane l holds a neighbour with index & 3 == (l + e) & 3
+    // where that element is free, so the four lanes of a group tend to gather from four different 32-byte columns, which
+    // the L1 data pipe serves in one wavefront.  Measured: force sweep -3 %, the other sweeps +1..2 %, the step +0.7 %
+    // (within noise), so it is off by default.
+    bool column_order = false;
 
     // reductions / scalars
     double* red = nullptr;              // device scratch for block partials

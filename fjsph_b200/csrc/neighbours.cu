@@ -196,6 +196,32 @@ __device__ __forceinline__ double4 ldg256(const double4* __restrict__ base, unsi
     return v;
 }
 
+// ---------------------------------------------------------------- column-aware order inside a chunk
+// The L1 data pipe serves a warp-wide 256-bit gather four lanes at a time: each group of four consecutive lanes costs
+// as many wavefronts as lanes of the group collide in the same 32-byte COLUMN of a 128-byte line (address bits 6:5,
+// i.e. record index & 3) on different sectors, and one wavefront when the four records sit in four different columns
+// -- whatever lines they are in (tools/l1_gather_probe.cu under ncu: 32 random lines cost 8.3 wavefronts with the
+// columns arranged so, 16.4 with random columns, 32 in one column).  A lane may visit the four neighbours of a chunk
+// in any order, so a neighbour with  index & 3 == (lane + e) & 3  goes to element e of its chunk where that element is
+// still free: the four lanes of a group then gather from four different columns at that slot.  The walk
+// through memory stays the ascending one (dealing whole lists out by column was measured too: the data-pipe wavefronts
+// fall further, but the four column streams of a lane drift apart, the L1 hit rate collapses and L2 -> L1 traffic
+// doubles; profiles/r5_*).
+// Online form: an accepted neighbour takes element (index - lane) & 3 of the chunk being filled if that element is
+// still free, else the lowest free one; the chunk is stored when its four elements are taken.
+template <bool COLS>
+__device__ __forceinline__ int chunk_slot(int lane, unsigned ent, unsigned freemask)
+{
+    if (COLS)
+    {
+        const int want = int((ent - unsigned(lane)) & 3u);
+        if ((freemask >> want) & 1u)
+            return want;
+    }
+    return __ffs(int(freemask)) - 1;
+}
+
+template <bool COLS>
 __global__ void __launch_bounds__(TPB)
     k_build_skin(const double4* __restrict__ P0, const int* __restrict__ b, int n, int n_owned, Grid g,
                  const unsigned* __restrict__ mx, const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
@@ -212,7 +238,8 @@ __global__ void __launch_bounds__(TPB)
     int cx, cy, cz;
     cell_of(g, a.x, a.y, a.z, cx, cy, cz);
     uint4* __restrict__ dst = reinterpret_cast<uint4*>(slist) + (size_t(i >> 5) * size_t(scap >> 2)) * 32u + (i & 31);
-    unsigned eb0 = unsigned(i), eb1 = unsigned(i), eb2 = unsigned(i);
+    unsigned eb0 = unsigned(i), eb1 = unsigned(i), eb2 = unsigned(i), eb3 = unsigned(i);
+    unsigned freemask = 15u; /* free elements of the chunk being filled */
     int cnt = 0;
     /* cells in ascending key order (z, then y, then x), so the list comes out sorted by index */
     for (int dz = -g.rz; dz <= g.rz; ++dz)
@@ -254,15 +281,22 @@ __global__ void __launch_bounds__(TPB)
                             ent |= FJ_NB_FLUID;
                         if (bj == FJSPH_BOUND)
                             ent |= FJ_NB_BOUND;
-                        const int kk = cnt & 3;
+                        const int kk = chunk_slot<COLS>(i & 31, ent, freemask);
                         if (kk == 0)
                             eb0 = ent;
                         else if (kk == 1)
                             eb1 = ent;
                         else if (kk == 2)
                             eb2 = ent;
-                        else if (cnt < scap)
-                            dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, eb1, eb2, ent);
+                        else
+                            eb3 = ent;
+                        freemask &= ~(1u << kk);
+                        if (freemask == 0u)
+                        {
+                            if (cnt < scap)
+                                dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, eb1, eb2, eb3);
+                            freemask = 15u;
+                        }
                         cnt++;
                     }
                 }
@@ -271,14 +305,29 @@ __global__ void __launch_bounds__(TPB)
         }
     }
     if ((cnt & 3) && cnt < scap)
-        dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, (cnt & 3) > 1 ? eb1 : unsigned(i), (cnt & 3) > 2 ? eb2 : unsigned(i),
-                                                 unsigned(i));
+    {
+        /* partial last chunk: its entries move to the front (consumers read `left` elements), the rest hold i itself */
+        unsigned v[4] = {eb0, eb1, eb2, eb3}, o[4] = {unsigned(i), unsigned(i), unsigned(i), unsigned(i)};
+        int k = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (!((freemask >> m) & 1u))
+            {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (t == k)
+                        o[t] = v[m];
+                k++;
+            }
+        dst[size_t(cnt >> 2) * 32u] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
     scount[i] = cnt;
     if (cnt > scap)
         atomicMax(flag, cnt);
 }
 
 // exact list from the skin list: list_i = { j in skin_i : ((xi-xj)^2 + (yi-yj)^2) + (zi-zj)^2 < sr }
+template <bool COLS>
 __global__ void __launch_bounds__(TPB)
     k_exact_from_skin(const double4* __restrict__ P0, int n, const unsigned* __restrict__ slist,
                       const int* __restrict__ scount, int scap, double sr, int nb_cap, unsigned* __restrict__ nlist,
@@ -295,8 +344,9 @@ __global__ void __launch_bounds__(TPB)
     double4* __restrict__ rdst = reinterpret_cast<double4*>(nr) + base;
     const int sc = scount[i];
     const int nchunk = (sc + 3) >> 2;
-    unsigned eb0 = unsigned(i), eb1 = unsigned(i), eb2 = unsigned(i);
-    double rb0 = 0.0, rb1 = 0.0, rb2 = 0.0;
+    unsigned eb0 = unsigned(i), eb1 = unsigned(i), eb2 = unsigned(i), eb3 = unsigned(i);
+    double rb0 = 0.0, rb1 = 0.0, rb2 = 0.0, rb3 = 0.0;
+    unsigned freemask = 15u; /* free elements of the chunk being filled */
     int cnt = 0;
     auto test = [&](const unsigned ent, const double4 q, const bool valid) {
         // nanoflann metric_L2_Simple order, no fma contraction (bit-exact sets)
@@ -305,7 +355,7 @@ __global__ void __launch_bounds__(TPB)
         if (valid && d2 < sr)
         {
             const double rv = sqrt(d2); /* r = sqrt(jj.second), as every pair loop takes it */
-            const int kk = cnt & 3;
+            const int kk = chunk_slot<COLS>(i & 31, ent, freemask);
             if (kk == 0)
             {
                 eb0 = ent;
@@ -321,10 +371,20 @@ __global__ void __launch_bounds__(TPB)
                 eb2 = ent;
                 rb2 = rv;
             }
-            else if (cnt < nb_cap)
+            else
             {
-                dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, eb1, eb2, ent);
-                rdst[size_t(cnt >> 2) * 32u] = make_double4(rb0, rb1, rb2, rv);
+                eb3 = ent;
+                rb3 = rv;
+            }
+            freemask &= ~(1u << kk);
+            if (freemask == 0u)
+            {
+                if (cnt < nb_cap)
+                {
+                    dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, eb1, eb2, eb3);
+                    rdst[size_t(cnt >> 2) * 32u] = make_double4(rb0, rb1, rb2, rb3);
+                }
+                freemask = 15u;
             }
             cnt++;
         }
@@ -352,10 +412,26 @@ __global__ void __launch_bounds__(TPB)
     }
     if ((cnt & 3) && cnt < nb_cap)
     {
-        /* partial last chunk; unused slots hold i itself (safe to gather) and are never consumed */
-        const int kk = cnt & 3;
-        dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, kk > 1 ? eb1 : unsigned(i), kk > 2 ? eb2 : unsigned(i), unsigned(i));
-        rdst[size_t(cnt >> 2) * 32u] = make_double4(rb0, kk > 1 ? rb1 : 0.0, kk > 2 ? rb2 : 0.0, 0.0);
+        /* partial last chunk: its entries move to the front (consumers read `left` elements); unused slots hold i itself
+           (safe to gather) and are never consumed */
+        unsigned v[4] = {eb0, eb1, eb2, eb3}, o[4] = {unsigned(i), unsigned(i), unsigned(i), unsigned(i)};
+        double vr[4] = {rb0, rb1, rb2, rb3}, orr[4] = {0.0, 0.0, 0.0, 0.0};
+        int k = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (!((freemask >> m) & 1u))
+            {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (t == k)
+                    {
+                        o[t] = v[m];
+                        orr[t] = vr[m];
+                    }
+                k++;
+            }
+        dst[size_t(cnt >> 2) * 32u] = make_uint4(o[0], o[1], o[2], o[3]);
+        rdst[size_t(cnt >> 2) * 32u] = make_double4(orr[0], orr[1], orr[2], orr[3]);
     }
     ncount[i] = cnt;
     if (cnt > nb_cap)
@@ -585,9 +661,14 @@ static int rebuild_skin(FjsphEngine* e)
         FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
         {
             KScope ks(e, "nb_skin", 1);
-            k_build_skin<<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, int(e->n_owned), g, e->mtab_x, e->mtab_y, e->mtab_z,
-                                                    e->cell_start, r_skin * r_skin, e->scap, e->slist, e->scount,
-                                                    e->xref, e->d_flag, n_class);
+            if (e->column_order) /* column_order_chunk above */
+                k_build_skin<true><<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, int(e->n_owned), g, e->mtab_x, e->mtab_y,
+                                                              e->mtab_z, e->cell_start, r_skin * r_skin, e->scap, e->slist,
+                                                              e->scount, e->xref, e->d_flag, n_class);
+            else
+                k_build_skin<false><<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, int(e->n_owned), g, e->mtab_x, e->mtab_y,
+                                                               e->mtab_z, e->cell_start, r_skin * r_skin, e->scap, e->slist,
+                                                               e->scount, e->xref, e->d_flag, n_class);
         }
         FJ_CUDA(cudaGetLastError());
         FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -687,8 +768,14 @@ int fj_build_neighbours(FjsphEngine* e)
         FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
         {
             KScope ks(e, "nb_list", 1);
-            k_exact_from_skin<<<fj_blocks(e->n_owned, TPB), TPB, 0, e->stream>>>(e->lv[1].P0, int(e->n_owned), e->slist, e->scount, e->scap, e->P.sr,
-                                                         e->nb_cap, e->nlist, e->nr, e->ncount, e->d_flag);
+            if (e->column_order)
+                k_exact_from_skin<true><<<fj_blocks(e->n_owned, TPB), TPB, 0, e->stream>>>(
+                    e->lv[1].P0, int(e->n_owned), e->slist, e->scount, e->scap, e->P.sr, e->nb_cap, e->nlist, e->nr, e->ncount,
+                    e->d_flag);
+            else
+                k_exact_from_skin<false><<<fj_blocks(e->n_owned, TPB), TPB, 0, e->stream>>>(
+                    e->lv[1].P0, int(e->n_owned), e->slist, e->scount, e->scap, e->P.sr, e->nb_cap, e->nlist, e->nr, e->ncount,
+                    e->d_flag);
         }
         FJ_CUDA(cudaGetLastError());
         FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
