@@ -691,6 +691,8 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
     e->skin = 0.4 * e->P.particle_step; /* default skin: 0.4 dx = 5 % of the support radius at H_fac = 2 */
     if (const char* order = std::getenv("FJSPH_B200_CELL_ORDER")) /* "morton" | "pencil" (default), engine.cuh */
         e->pencil_order = std::string(order) != "morton";
+    if (const char* tile = std::getenv("FJSPH_B200_PENCIL_TILE"))
+        std::sscanf(tile, "%d,%d", &e->pencil_tile_x, &e->pencil_tile_y);
     if (const char* order = std::getenv("FJSPH_B200_LIST_ORDER")) /* "index" (default) | "columns", engine.cuh */
         e->column_order = std::string(order) == "columns";
     FJ_CUDA(cudaMalloc(&e->near_inlet, cap * sizeof(int)));

@@ -211,6 +211,8 @@ struct FjsphEngine
     //           neighbourhoods -- slot s of their lists lands in ~14 cache lines instead of ~24 on lattice-born fluids;
     //   morton: cubic cells of edge 2H + skin in Morton order.
     bool pencil_order = true;
+    // pencil tiles (FJSPH_B200_PENCIL_TILE = "tx,ty", key bits; "0,0" = plain pencils): see the key tables in neighbours.cu
+    int pencil_tile_x = 3, pencil_tile_y = 3; /* measured: block 343.0 -> 337.3 ms per step (profiles/r9_tile_sweep.txt) */
     // Order inside each chunk of four list entries (FJSPH_B200_LIST_ORDER = "index" (default) | "columns"): see chunk_slot
     // in neighbours.cu -- with "columns", element e of a chunk of lane l holds a neighbour with index & 3 == (l + e) & 3
     // where that element is free, so the four lanes of a group tend to gather from four different 32-byte columns, which

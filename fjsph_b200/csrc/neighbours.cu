@@ -601,9 +601,18 @@ static int rebuild_skin(FjsphEngine* e)
         int out = 0;
         const int bits[3] = {g.bx, g.by, g.bz};
         if (e->pencil_order)
-        { /* lexicographic: x in the low bits, then y, then z -- consecutive keys run along x */
-            for (int a = 0; a < 3; ++a)
-                for (int l = 0; l < bits[a]; ++l) pos[a][l] = out++;
+        {
+            /* x in the low bits, then y, then z -- consecutive keys run along x.  With tiles (pencil_tile_y > 0) the
+               lowest TX bits of x come first, then the lowest TY bits of y, then the rest of x: memory then runs through
+               ~one warp's worth of a pencil (2^TX cells), then through the same stretch of the next pencil, ..., so the
+               warps of a block sit in ADJACENT pencils and walk nearly the same neighbour rows one row apart -- what
+               one warp pulls into L1 the next one finds there. */
+            const int tx = std::min(e->pencil_tile_x, bits[0]), ty = std::min(e->pencil_tile_y, bits[1]);
+            for (int l = 0; l < tx; ++l) pos[0][l] = out++;
+            for (int l = 0; l < ty; ++l) pos[1][l] = out++;
+            for (int l = tx; l < bits[0]; ++l) pos[0][l] = out++;
+            for (int l = ty; l < bits[1]; ++l) pos[1][l] = out++;
+            for (int l = 0; l < bits[2]; ++l) pos[2][l] = out++;
         }
         else
             for (int l = 0; l < 32; ++l)
