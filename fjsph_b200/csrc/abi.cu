@@ -534,11 +534,11 @@ constexpr size_t kStageBytesPerParticle = 8 * 2 + 4 * 4 + 24 * 10 + 72 + 8 * 17;
 
 // lays the non-null host fields out in the staging buffer; returns the device-side view
 int stage_layout(FjsphEngine* e, const FjsphStateView* s, StageView* dv, std::vector<std::pair<void*, void*>>* copies,
-                 std::vector<size_t>* sizes)
+                 std::vector<size_t>* sizes, size_t* stage_off = nullptr)
 {
     std::memset(dv, 0, sizeof(*dv));
     const size_t n = size_t(s->n);
-    size_t off = 0;
+    size_t off = stage_off ? *stage_off : 0;
     for (const FieldSpec& f : kFields)
     {
         void* hp = *(void* const*)((const char*)s + f.host_off);
@@ -556,17 +556,19 @@ int stage_layout(FjsphEngine* e, const FjsphStateView* s, StageView* dv, std::ve
         sizes->push_back(bytes);
         off += (bytes + 255) & ~size_t(255);
     }
+    if (stage_off)
+        *stage_off = off;
     return FJSPH_OK;
 }
 
 // host arrays -> the device staging buffer (one H2D copy per field), then k_pack scatters them into the slots of a level.
 // both_levels: the same staged data go into pn and pnp1 (one trip over PCIe, two scatters on the device).
-int upload_fields(FjsphEngine* e, int level, const FjsphStateView* s, bool both_levels = false)
+int upload_fields(FjsphEngine* e, int level, const FjsphStateView* s, bool both_levels = false, size_t* stage_off = nullptr)
 {
     StageView dv;
     std::vector<std::pair<void*, void*>> copies;
     std::vector<size_t> sizes;
-    int st = stage_layout(e, s, &dv, &copies, &sizes);
+    int st = stage_layout(e, s, &dv, &copies, &sizes, stage_off);
     if (st)
         return st;
     for (size_t k = 0; k < copies.size(); ++k)
@@ -749,6 +751,13 @@ int fjsph_destroy(FjsphEngine* e)
     cudaEventDestroy(e->ev1);
     fj_timers_flush(e);
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->upload_stream)
+    {
+        cudaStreamSynchronize(e->upload_stream);
+        cudaStreamDestroy(e->upload_stream);
+        cudaEventDestroy(e->ev_upload_x);
+        cudaEventDestroy(e->ev_upload);
+    }
     if (e->slab.comm_stream)
     {
         cudaStreamSynchronize(e->slab.comm_stream);
@@ -910,6 +919,65 @@ int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_po
         return st;
     e->maxShift = 0.0;
     FJ_CUDA(cudaStreamSynchronize(e->stream));
+    return FJSPH_OK;
+}
+
+// fjsph_upload_state for a host that round-trips the SAME particle set (fjsph_step_host): positions cross PCIe first, on
+// the engine's stream, and the neighbour build of the step that follows needs nothing else; the other fields follow on a
+// second stream beside it.  Returns with that second half in flight (e->upload_pending).  Falls back to the plain
+// upload whenever the cell order cannot be kept.
+static int upload_state_split(FjsphEngine* e, const FjsphStateView* s, int64_t bound_points)
+{
+    const bool keep = s && s->xi && s->rho && s->p && s->m && s->b && !e->blocks.empty() && e->blocks.back().second == s->n &&
+                      e->n == s->n && e->bound_points == bound_points && e->skin_valid && e->skin_n == s->n &&
+                      e->n_owned == s->n && !e->slab.on;
+    if (!keep)
+        return fjsph_upload_state(e, s, bound_points);
+    cudaSetDevice(e->device);
+    if (!e->upload_stream)
+    {
+        FJ_CUDA(cudaStreamCreateWithFlags(&e->upload_stream, cudaStreamNonBlocking));
+        FJ_CUDA(cudaEventCreateWithFlags(&e->ev_upload_x, cudaEventDisableTiming));
+        FJ_CUDA(cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming));
+    }
+    e->list_valid = false;
+    e->next_part_id = s->n;
+    e->inlet_tables_dirty = true;
+    e->maxShift = 0.0;
+    const int n = int(e->n);
+    e->launches += 1;
+    k_init_level<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], e->oidx, e->C, e->P.rho_g, e->P.p_ref, n);
+    FJ_CUDA(cudaGetLastError());
+    /* first half: positions */
+    FjsphStateView xs;
+    std::memset(&xs, 0, sizeof(xs));
+    xs.n = s->n;
+    xs.xi = s->xi;
+    size_t stage_off = 0;
+    int st = upload_fields(e, 1, &xs, false, &stage_off);
+    if (st)
+        return st;
+    FJ_CUDA(cudaEventRecord(e->ev_upload_x, e->stream));
+    /* second half: everything else, then pn = pnp1 (Init.cpp:496), on the upload stream behind the positions */
+    FjsphStateView rest = *s;
+    rest.xi = nullptr;
+    FJ_CUDA(cudaStreamWaitEvent(e->upload_stream, e->ev_upload_x, 0));
+    cudaStream_t main_stream = e->stream;
+    const bool timers = e->timers_on;
+    e->timers_on = false; /* the lazily resolved event timers belong to the engine's stream */
+    e->stream = e->upload_stream;
+    st = upload_fields(e, 1, &rest, false, &stage_off);
+    if (!st)
+        st = fj_copy_level(e, 0, 1);
+    e->stream = main_stream;
+    e->timers_on = timers;
+    if (st)
+    {
+        cudaStreamSynchronize(e->upload_stream);
+        return st;
+    }
+    FJ_CUDA(cudaEventRecord(e->ev_upload, e->upload_stream));
+    e->upload_pending = true;
     return FJSPH_OK;
 }
 
@@ -1134,15 +1202,22 @@ int fjsph_step(FjsphEngine* e, FjsphStepStats* s)
 int fjsph_step_host(FjsphEngine* e, const FjsphStateView* in, int64_t bound_points, int32_t n_steps,
                     FjsphStateView* out, FjsphStepStats* last)
 {
-    int st = fjsph_upload_state(e, in, bound_points);
+    int st = n_steps > 0 ? upload_state_split(e, in, bound_points) : fjsph_upload_state(e, in, bound_points);
     if (st)
         return st;
     for (int k = 0; k < n_steps; ++k)
     {
         st = fjsph_step(e, last);
         if (st)
-            return st;
+            break;
     }
+    if (e->upload_pending)
+    { /* a step that failed before it consumed the upload: the host arrays must be free again on return */
+        cudaStreamSynchronize(e->upload_stream);
+        e->upload_pending = false;
+    }
+    if (st)
+        return st;
     return fjsph_download_state(e, 1, out);
 }
 

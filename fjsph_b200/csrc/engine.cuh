@@ -205,6 +205,12 @@ struct FjsphEngine
     int nb_cap = 0;
     size_t nlist_words = 0;
     bool list_valid = false;
+    // fjsph_step_host overlaps the host -> device copy with the first neighbour build: positions go up first on the
+    // engine's stream, everything else on upload_stream; upload_pending tells fj_integrate_no_update to run the build
+    // ahead of find_timestep and to make the engine's stream wait for ev_upload before anything reads the other fields.
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t ev_upload_x = nullptr, ev_upload = nullptr;
+    bool upload_pending = false;
     // Memory order of the particles (decided at fjsph_create from FJSPH_B200_CELL_ORDER, default "pencil"):
     //   pencil: cells are R x dx x dx bricks keyed lexicographically (x fastest), so consecutive particles run along x
     //           inside a one-spacing-wide pencil and the 32 lanes of a warp walk translated copies of each other's
@@ -300,7 +306,8 @@ void fj_refresh_constants(FjsphEngine* e);
 void fj_timers_flush(FjsphEngine* e);
 // slab decomposition (halo.cu); all are no-ops / identities on a single rank
 int fj_halo_exchange(FjsphEngine* e, int level, unsigned mask); /* begin; completed by the next fj_halo_wait */
-int fj_halo_wait(FjsphEngine* e);                               /* main stream waits for the exchange in flight */
+int fj_halo_wait(FjsphEngine* e);
+int fj_upload_wait(FjsphEngine* e); /* engine stream waits for a split upload in flight (abi.cu) */                               /* main stream waits for the exchange in flight */
 /* true while an exchange is in flight that an interior/edge split sweep may run beside */
 static inline bool fj_halo_overlappable(const FjsphEngine* e)
 {

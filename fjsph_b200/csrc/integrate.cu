@@ -463,6 +463,17 @@ int fj_reduce_sum(FjsphEngine* e, int nblocks, int ncomp, double* out_host)
     return fj_allreduce(e, FJSPH_COMM_SUM, out_host, ncomp); /* slab decomposition: the sum over all ranks */
 }
 
+// The engine's stream waits for the second half of a split upload (upload_state_split, abi.cu).
+int fj_upload_wait(FjsphEngine* e)
+{
+    if (e->upload_pending)
+    {
+        FJ_CUDA(cudaStreamWaitEvent(e->stream, e->ev_upload, 0));
+        e->upload_pending = false;
+    }
+    return FJSPH_OK;
+}
+
 int fj_copy_level(FjsphEngine* e, int dst, int src)
 {
     const int n = int(e->n);
@@ -668,12 +679,29 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
      * keeps the global count), so it is read where it is used */
     #define nfluid fj_fluid_count(e)
 
-    st = fj_find_timestep(e, &e->P.delta_t);
-    if (st)
-        return st;
-    st = fj_build_neighbours(e);
-    if (st)
-        return st;
+    if (e->upload_pending)
+    {
+        /* fjsph_step_host: only the positions are on the device yet.  The list needs nothing else and the time step does
+           not depend on the list, so update_neighbours runs first, beside the rest of the upload */
+        st = fj_build_neighbours(e);
+        if (st)
+            return st;
+        st = fj_upload_wait(e);
+        if (st)
+            return st;
+        st = fj_find_timestep(e, &e->P.delta_t);
+        if (st)
+            return st;
+    }
+    else
+    {
+        st = fj_find_timestep(e, &e->P.delta_t);
+        if (st)
+            return st;
+        st = fj_build_neighbours(e);
+        if (st)
+            return st;
+    }
 
     if (e->P.solver_type == 1)
     {

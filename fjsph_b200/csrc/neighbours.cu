@@ -747,6 +747,10 @@ int fj_build_neighbours(FjsphEngine* e)
     double moved = valid ? 0.0 : 1.0;
     if (moved != 0.0)
     {
+        /* the re-sort moves every field of both time levels: a split upload (fjsph_step_host) has to land first */
+        int stw = fj_upload_wait(e);
+        if (stw)
+            return stw;
         if (e->slab.on && e->slab.world > 1)
         {
             int st = fj_redecompose(e); /* migration + new ghost sets; particle counts change */
