@@ -181,7 +181,10 @@ int fjsph_integrate_no_update(FjsphEngine* e, FjsphStepStats* s); /* Integration
 int fjsph_step(FjsphEngine* e, FjsphStepStats* s);              /* Integrator::integrate  Integration.h:20-23 */
 
 /* Convenience for hosts that keep particles on the host between steps (the end-to-end path):
- * upload -> n_steps x fjsph_step -> download, one call. */
+ * upload -> n_steps x fjsph_step -> download, one call.  When `in` holds the particle set the engine already has (same
+ * count and blocks), the cell order and the superset neighbour list are kept and the upload is split: positions first,
+ * the other fields beside the first update_neighbours of the step.  `in` must stay untouched until the call returns;
+ * `out` may alias `in`. */
 int fjsph_step_host(FjsphEngine* e, const FjsphStateView* in, int64_t bound_points, int32_t n_steps,
                     FjsphStateView* out, FjsphStepStats* last);
 
