@@ -258,8 +258,11 @@ __global__ void __launch_bounds__(TPB)
 template <bool ALE>
 __global__ void __launch_bounds__(TPB)
     k_rk_stage(Level Sn, Level S, const int* __restrict__ blk, BlockTable bt, const int* __restrict__ near_inlet,
-               DevConst C, double dt_s, int n, double* __restrict__ err_partial)
+               DevConst C, double dt_s, int n, double* __restrict__ err_partial, int part)
 {
+    /* part 0: the DBC / Ghost wall densities, BEFORE the stage's force evaluation (Runge_Kutta.cpp:76-131: the walls are
+       advanced with the Rrho the boundary treatment has just given them, and get_acc_and_Rrho sees the result);
+       part 1: the fluid, after it (Runge_Kutta.cpp:137-171) */
     __shared__ double sm[TPB / 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double err = 0.0;
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(TPB)
         if (bl < bt.n_bound_blocks)
         {
             const int solver = bt.solver[bl];
-            if (solver == FJSPH_DBC || solver == FJSPH_GHOST)
+            if (part == 0 && (solver == FJSPH_DBC || solver == FJSPH_GHOST))
             {
                 double4 acc = S.ACC[i];
                 const bool ni = (solver == FJSPH_GHOST) && near_inlet[i];
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(TPB)
                 }
             }
         }
-        else if (S.b[i] > FJSPH_BUFFER)
+        else if (part == 1 && S.b[i] > FJSPH_BUFFER)
         {
             const double4 xn = Sn.P0[i], vn = Sn.P1[i];
             const double4 v = S.P1[i], a = S.ACC[i];
@@ -302,6 +305,8 @@ __global__ void __launch_bounds__(TPB)
             err = ex * ex + ey * ey + ez * ez;
         }
     }
+    if (part == 0)
+        return;
     const double tot = block_sum(err, sm);
     if (threadIdx.x == 0)
         err_partial[blockIdx.x] = tot;
@@ -359,8 +364,9 @@ __global__ void k_rk_accumulate(Level Sn, Level S, double4* __restrict__ sum_v, 
 __global__ void __launch_bounds__(TPB)
     k_rk_final(Level Sn, Level S, const int* __restrict__ blk, BlockTable bt, const int* __restrict__ near_inlet,
                const double4* __restrict__ sum_v, const double4* __restrict__ sum_a, DevConst C, double dt, int n,
-               double* __restrict__ err_partial)
+               double* __restrict__ err_partial, int part)
 {
+    /* part 0: wall densities before the last force evaluation (Runge_Kutta.cpp:276-349), part 1: the fluid after it */
     __shared__ double sm[TPB / 32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double err = 0.0;
@@ -371,7 +377,7 @@ __global__ void __launch_bounds__(TPB)
         if (bl < bt.n_bound_blocks)
         {
             const int solver = bt.solver[bl];
-            if (solver == FJSPH_DBC || solver == FJSPH_GHOST)
+            if (part == 0 && (solver == FJSPH_DBC || solver == FJSPH_GHOST))
             {
                 /* sum_v.w holds Rrho_n + 2 Rrho_1 + 2 Rrho_2 + Rrho_3 for walls as well */
                 double4 acc = S.ACC[i];
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(TPB)
                 }
             }
         }
-        else
+        else if (part == 1)
         {
             const int b = S.b[i];
             if (b > FJSPH_BUFFER && b != FJSPH_OUTLET)
@@ -415,6 +421,8 @@ __global__ void __launch_bounds__(TPB)
             }
         }
     }
+    if (part == 0)
+        return;
     const double tot = block_sum(err, sm);
     if (threadIdx.x == 0)
         err_partial[blockIdx.x] = tot;
@@ -605,11 +613,32 @@ static int frozen_terms(FjsphEngine* e, bool all)
     return fj_halo_exchange(e, 1, FJ_HX_P2 | FJ_HX_SURFZONE | FJ_HX_B); /* vPert_j; surfzone_j and b_j for the walls */
 }
 
+static bool has_density_walls(const FjsphEngine* e)
+{
+    for (int b = 0; b < e->n_bound_blocks; ++b)
+        if (e->blocks[b].bound_solver == FJSPH_DBC || e->blocks[b].bound_solver == FJSPH_GHOST)
+            return true;
+    return false;
+}
+
 static int rk_stage(FjsphEngine* e, double dt_s, double* errsum)
 {
     int st = fj_walls(e, 1, false);
     if (st)
         return st;
+    const int n = int(e->n_owned);
+    const int nb = fj_blocks(n, TPB);
+    auto update = [&](int part) {
+        KScope ks(e, "rk_update", 1);
+        if (e->P.ale)
+            k_rk_stage<true><<<nb, TPB, 0, e->stream>>>(e->lv[0], e->lv[1], e->blk, make_block_table(e), e->near_inlet,
+                                                        e->C, dt_s, n, e->red, part);
+        else
+            k_rk_stage<false><<<nb, TPB, 0, e->stream>>>(e->lv[0], e->lv[1], e->blk, make_block_table(e),
+                                                         e->near_inlet, e->C, dt_s, n, e->red, part);
+    };
+    if (has_density_walls(e))
+        update(0); /* DBC / Ghost wall densities move before the forces see them (Runge_Kutta.cpp:76-131) */
     if (e->n_bound_blocks > 0)
     {
         st = fj_halo_exchange(e, 1, FJ_HX_STATE);
@@ -619,17 +648,7 @@ static int rk_stage(FjsphEngine* e, double dt_s, double* errsum)
     st = fj_forces(e, 1, e->npd);
     if (st)
         return st;
-    const int n = int(e->n_owned);
-    const int nb = fj_blocks(n, TPB);
-    {
-        KScope ks(e, "rk_update", 1);
-        if (e->P.ale)
-            k_rk_stage<true><<<nb, TPB, 0, e->stream>>>(e->lv[0], e->lv[1], e->blk, make_block_table(e), e->near_inlet,
-                                                        e->C, dt_s, n, e->red);
-        else
-            k_rk_stage<false><<<nb, TPB, 0, e->stream>>>(e->lv[0], e->lv[1], e->blk, make_block_table(e),
-                                                         e->near_inlet, e->C, dt_s, n, e->red);
-    }
+    update(1);
     FJ_CUDA(cudaGetLastError());
     int nparts = nb;
     st = fj_inlet_motion(e, dt_s, false, &nparts); /* Runge_Kutta.cpp:175-228 */
@@ -746,6 +765,15 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
         st = fj_walls(e, 1, false);
         if (st)
             return st;
+        const int n = int(e->n_owned);
+        const int nb = fj_blocks(n, TPB);
+        auto final_update = [&](int part) {
+            KScope ks(e, "rk_update", 1);
+            k_rk_final<<<nb, TPB, 0, e->stream>>>(e->lv[0], e->lv[1], e->blk, make_block_table(e), e->near_inlet,
+                                                  e->rk_sum_v, e->rk_sum_a, e->C, e->P.delta_t, n, e->red, part);
+        };
+        if (has_density_walls(e))
+            final_update(0); /* Runge_Kutta.cpp:276-349: the walls' weighted density step precedes the last forces */
         if (e->n_bound_blocks > 0)
         {
             st = fj_halo_exchange(e, 1, FJ_HX_STATE);
@@ -755,13 +783,7 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
         st = fj_forces(e, 1, e->npd);
         if (st)
             return st;
-        const int n = int(e->n_owned);
-        const int nb = fj_blocks(n, TPB);
-        {
-            KScope ks(e, "rk_update", 1);
-            k_rk_final<<<nb, TPB, 0, e->stream>>>(e->lv[0], e->lv[1], e->blk, make_block_table(e), e->near_inlet,
-                                                  e->rk_sum_v, e->rk_sum_a, e->C, e->P.delta_t, n, e->red);
-        }
+        final_update(1);
         FJ_CUDA(cudaGetLastError());
         int nparts = nb;
         st = fj_inlet_motion(e, e->P.delta_t, false, &nparts); /* Runge_Kutta.cpp:397-452 */

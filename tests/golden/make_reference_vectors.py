@@ -54,6 +54,21 @@ def golden_cases():
     for fixed in (0, 1):
         jet = cases.inlet_jet(delete_x=2.5, fixed=fixed, jitter=0.02)
         out["inlet_jet_fixed%d" % fixed] = (jet, "ref3d", 3, 14, dict(ale=1), None, None)
+    # other wall treatments (Resid.cpp:122-186, Newmark_Beta.cpp:69-132): Ghost continuity, no-slip mirror velocities, a
+    # wall moving on a schedule.  (DBC walls cannot be pinned: Boundary_DBC sizes its scratch vector by the END of the
+    # wall block and then writes it at FLUID indices, Resid.cpp:84-107 -- heap corruption in the reference.)
+    nb, n = tank["bound_points"], tank["xi"].shape[0]
+
+    def walls(solver, no_slip, times=None, vels=None):
+        return dict(tank, blocks=[dict(is_fluid=0, first=0, second=nb, bound_solver=solver, no_slip=no_slip, times=times,
+                                       vels=vels, fixed_vel_or_dynamic=0),
+                                  dict(is_fluid=1, first=nb, second=n)])
+
+    out["tank_ghost_noslip"] = (walls(2, 1), "ref3d", 3, 3, dict(ale=1), None, None)
+    out["tank_adami_moving_wall"] = (walls(1, 0, [0.0, 0.004, 0.009], [[0.1, 0, 0], [0, 0.2, 0], [0, 0, 0]]), "ref3d", 3, 3,
+                                     dict(ale=1), None, None)
+    out["tank_ghost_rk4_moving"] = (walls(2, 1, [0.0, 0.004], [[0.1, 0, 0], [0, 0.2, 0]]), "ref3d", 3, 3,
+                                    dict(ale=1, solver_type=1), None, None)
     dm = cases.droplet(dx=0.0125, jitter=0.05)
     sheared = cases.hex_mesh((-0.1013, -0.1007, -0.1011), (0.1009, 0.1003, 0.1017), (6, 7, 5),
                              vel=lambda c: np.stack([5 + 20 * c[:, 1], 21.55 + 0 * c[:, 0], 3 * c[:, 2]], 1), p=100000.0,
@@ -81,6 +96,12 @@ def make_sim(case, kind, dim, extra, mesh, cell0):
                     insert_norm=B["insert_norm"], insconst=B["insconst"], delete_norm=B.get("delete_norm"),
                     delconst=B.get("delconst", 9999999.0), aero_norm=B["aero_norm"], aeroconst=B["aeroconst"], back=B["back"],
                     buffer=B["buffer"])
+    if case.get("blocks") is not None:
+        o.lib.orc_clear_blocks(o.h)
+        for Bk in case["blocks"]:
+            o.add_block(Bk["is_fluid"], Bk["first"], Bk["second"], bound_solver=Bk.get("bound_solver", 1),
+                        no_slip=Bk.get("no_slip", 0), fixed_vel_or_dynamic=Bk.get("fixed_vel_or_dynamic", 0),
+                        times=Bk.get("times"), vels=Bk.get("vels"))
     if cell0 is not None:
         for lvl in (0, 1):
             o.set("cellID", np.full(o.n, cell0, dtype=np.int64), lvl)
@@ -110,6 +131,8 @@ def main():
         if case.get("block") is not None:
             B = case["block"]
             meta["block"] = {k: (np.asarray(B[k]).tolist() if hasattr(B[k], "__len__") else B[k]) for k in BLOCK_KEYS if k in B}
+        if case.get("blocks") is not None:
+            meta["blocks"] = case["blocks"]
         if mesh is not None:
             for k, v in mesh.items():
                 data["mesh_" + k] = np.asarray(v)

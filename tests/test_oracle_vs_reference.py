@@ -161,6 +161,34 @@ def test_full_steps(name, case, kind, dim, kw):
     assert abs(pa.current_time - pr.current_time) <= 1e-12 * pr.current_time
 
 
+WALLS = [("ghost", 2, 0, None, None, {}), ("ghost_noslip", 2, 1, None, None, {}), ("adami_noslip", 1, 1, None, None, {}),
+         ("adami_moving", 1, 0, [0.0, 0.004, 0.009], [[0.1, 0, 0], [0, 0.2, 0], [0, 0, 0]], {}),
+         ("ghost_noslip_moving_rk4", 2, 1, [0.0, 0.004], [[0.1, 0, 0], [0, 0.2, 0]], dict(solver_type=1)),
+         ("adami_moving_rk4", 1, 0, [0.0, 0.004], [[0.1, 0, 0], [0, 0.2, 0]], dict(solver_type=1))]
+
+
+@pytest.mark.parametrize("name,solver,no_slip,times,vels,kw", WALLS, ids=[w[0] for w in WALLS])
+def test_wall_treatments(name, solver, no_slip, times, vels, kw):
+    """Boundary_Ghost, Set_No_Slip, Get_Boundary_Pressure and the wall-velocity schedules of Do_NB_Iter and of the RK
+    stages (Resid.cpp:21-186, Newmark_Beta.cpp:69-132, Runge_Kutta.cpp:36-131 with its own comparator and its wall
+    densities advanced BEFORE the stage's forces).  Boundary_DBC is not compared: it sizes its scratch vector by the end
+    of the WALL block and writes it at FLUID indices (Resid.cpp:84-107) -- heap corruption in the reference."""
+    tank = cases.box_with_walls(n=(8, 6, 7), jitter=0.05)
+    nb, n = tank["bound_points"], tank["xi"].shape[0]
+    a, r = pair(tank, "ref3d", ale=1, **kw)
+    for o in (a, r):
+        o.lib.orc_clear_blocks(o.h)
+        o.add_block(0, 0, nb, bound_solver=solver, no_slip=no_slip, times=times, vels=vels)
+        o.add_block(1, nb, n)
+    for step in range(3):
+        _, sa = a.integrate()
+        _, sr = r.integrate()
+        assert sa.iterations == sr.iterations and abs(sa.dt - sr.dt) <= 1e-12 * sr.dt, (name, step)
+    for level in (0, 1):
+        assert_same(a, r, INTS, 0.0, name, level)
+        assert_same(a, r, FLOATS, 1e-9, name, level)
+
+
 def _with_block(o, B):
     o.lib.orc_clear_blocks(o.h)
     o.add_block(1, B["first"], B["second"], block_type=6, fixed_vel_or_dynamic=B["fixed_vel_or_dynamic"],
