@@ -69,6 +69,11 @@ def golden_cases():
                                      dict(ale=1), None, None)
     out["tank_ghost_rk4_moving"] = (walls(2, 1, [0.0, 0.004], [[0.1, 0, 0], [0, 0.2, 0]]), "ref3d", 3, 3,
                                     dict(ale=1, solver_type=1), None, None)
+    # Runge-Kutta over the other ingredients (each has its own code path in Runge_Kutta.cpp)
+    out["droplet_gissler_rk4"] = (drop, "ref3d", 3, 3, dict(ale=1, solver_type=1), None, None)
+    out["block_rk4_dsph"] = (blk, "ref3d_dsph", 3, 3, dict(ale=0, solver_type=1), None, None)
+    out["inlet_jet_fixed1_rk4"] = (cases.inlet_jet(delete_x=2.5, fixed=1, jitter=0.02), "ref3d", 3, 14,
+                                   dict(ale=1, solver_type=1), None, None)
     dm = cases.droplet(dx=0.0125, jitter=0.05)
     sheared = cases.hex_mesh((-0.1013, -0.1007, -0.1011), (0.1009, 0.1003, 0.1017), (6, 7, 5),
                              vel=lambda c: np.stack([5 + 20 * c[:, 1], 21.55 + 0 * c[:, 0], 3 * c[:, 2]], 1), p=100000.0,
@@ -79,6 +84,7 @@ def golden_cases():
     wall = cases.hex_mesh((-0.1013, -0.1007, -0.03), (0.1009, 0.1003, 0.1017), (6, 7, 5), vel=(0.0, 21.55, 0.0), p=100000.0,
                           rho=1.1025, outer_marker=-1)
     out["droplet_inner_wall_mesh"] = (dm, "ref3d", 3, 3, dict(ale=1, asource=1, delta_t_min=1e-9), wall, 0)
+    out["droplet_sheared_mesh_rk4"] = (dm, "ref3d", 3, 3, dict(ale=1, asource=1, delta_t_min=1e-9, solver_type=1), sheared, 0)
     return out
 
 
