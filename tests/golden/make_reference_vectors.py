@@ -84,6 +84,13 @@ def golden_cases():
     wall = cases.hex_mesh((-0.1013, -0.1007, -0.03), (0.1009, 0.1003, 0.1017), (6, 7, 5), vel=(0.0, 21.55, 0.0), p=100000.0,
                           rho=1.1025, outer_marker=-1)
     out["droplet_inner_wall_mesh"] = (dm, "ref3d", 3, 3, dict(ale=1, asource=1, delta_t_min=1e-9), wall, 0)
+    # Check_Pipe_Outlet with a mesh (Containment.cpp:822-890): PIPE particles crossing the aero plane become FREE and take
+    # their first cell from the 150 nearest cell centres (FirstCell, Containment.cpp:425-470)
+    pj = cases.inlet_jet(n=(5, 5, 4), fixed=1, jitter=0.03, aero_x=0.5)
+    pj["params"] = dict(pj["params"], acase=1, v_inf=(0.0, 30.0, 0.0), p_ref=100000.0, rho_g=1.2)
+    pipe_mesh = cases.hex_mesh((-0.0123, -0.0031, -0.0029), (0.0117, 0.0073, 0.0071), (12, 5, 5), vel=(0.0, 30.0, 0.0),
+                               p=100000.0, rho=1.2)
+    out["inlet_jet_mesh_first_cell"] = (pj, "ref3d", 3, 6, dict(ale=1, asource=1), pipe_mesh, None)
     out["droplet_sheared_mesh_rk4"] = (dm, "ref3d", 3, 3, dict(ale=1, asource=1, delta_t_min=1e-9, solver_type=1), sheared, 0)
     return out
 
