@@ -64,6 +64,11 @@ def golden_cases():
                                        vels=vels, fixed_vel_or_dynamic=0),
                                   dict(is_fluid=1, first=nb, second=n)])
 
+    half, mid = nb // 2, (nb + n) // 2
+    multi = dict(tank, blocks=[dict(is_fluid=0, first=0, second=half, bound_solver=1, no_slip=0),
+                               dict(is_fluid=0, first=half, second=nb, bound_solver=2, no_slip=1),
+                               dict(is_fluid=1, first=nb, second=mid), dict(is_fluid=1, first=mid, second=n)])
+    out["tank_two_wall_blocks_two_fluid_blocks"] = (multi, "ref3d", 3, 3, dict(ale=1), None, None)
     out["tank_ghost_noslip"] = (walls(2, 1), "ref3d", 3, 3, dict(ale=1), None, None)
     out["tank_adami_moving_wall"] = (walls(1, 0, [0.0, 0.004, 0.009], [[0.1, 0, 0], [0, 0.2, 0], [0, 0, 0]]), "ref3d", 3, 3,
                                      dict(ale=1), None, None)
