@@ -262,6 +262,31 @@ def test_walls_nb_iteration_parity(ale):
         assert_fields_close(e, o, ("xi", "v", "rho", "p", "acc", "Rrho"), tol=1e-9, context="walls nb_iter %d" % it)
 
 
+@pytest.mark.parametrize("solver_type", [0, 1], ids=["newmark_beta", "rk4"])
+@pytest.mark.parametrize("bound_solver,no_slip", [(0, 0), (0, 1), (2, 0)], ids=["dbc", "dbc_noslip", "ghost"])
+def test_dbc_and_ghost_walls_full_steps(bound_solver, no_slip, solver_type):
+    """Three full steps with DBC / Ghost walls under both integrators.  The wall densities of these two treatments are
+    integrated -- after the forces in Newmark-Beta (Newmark_Beta.cpp:137-241), before them in every Runge-Kutta stage
+    (Runge_Kutta.cpp:76-131, 276-349).  DBC has no reference vector (Boundary_DBC writes out of bounds in the reference,
+    Resid.cpp:84-107; the contract is the oracle's: wall acc = 0), so the oracle is the yardstick here."""
+    case = cases.box_with_walls(n=(8, 6, 7), jitter=0.05)
+    nb, n = case["bound_points"], case["xi"].shape[0]
+    o, e, p = make_pair(case, solver_type=solver_type, delta_t_min=1e-9)
+    o.lib.orc_clear_blocks(o.h)
+    o.add_block(0, 0, nb, bound_solver=bound_solver, no_slip=no_slip)
+    o.add_block(1, nb, n)
+    e.set_blocks([dict(first=0, second=nb, is_fluid=0, bound_solver=bound_solver, no_slip=no_slip),
+                  dict(first=nb, second=n, is_fluid=1)])
+    for step in range(3):
+        _, so = o.integrate()
+        se = e.integrate()
+        ctx = "walls %d/%d solver %d step %d" % (bound_solver, no_slip, solver_type, step)
+        assert se.iterations == so.iterations and abs(se.dt - so.dt) <= 1e-9 * so.dt, ctx
+        assert_fields_close(e, o, ("xi", "rho"), tol=1e-9, context=ctx)
+        assert_fields_close(e, o, ("v", "p"), tol=1e-7, context=ctx)
+        assert_fields_close(e, o, ("acc", "Rrho"), tol=1e-5, context=ctx)
+
+
 @pytest.mark.parametrize("acase", [2, 3], ids=["induced_pressure", "skin_friction"])
 def test_other_aero_models(acase):
     """CalcAeroAcc's other two models (Aero.h:106-202 induced pressure, Aero.h:224-257 skin friction) on the droplet in
