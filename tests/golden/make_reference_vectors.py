@@ -96,8 +96,49 @@ def golden_cases():
     pipe_mesh = cases.hex_mesh((-0.0123, -0.0031, -0.0029), (0.0117, 0.0073, 0.0071), (12, 5, 5), vel=(0.0, 30.0, 0.0),
                                p=100000.0, rho=1.2)
     out["inlet_jet_mesh_first_cell"] = (pj, "ref3d", 3, 6, dict(ale=1, asource=1), pipe_mesh, None)
+    out["jet_deck_jittered"] = (jittered_jet_deck(), "ref3d", 3, 12, {}, None, None)
     out["droplet_sheared_mesh_rk4"] = (dm, "ref3d", 3, 3, dict(ale=1, asource=1, delta_t_min=1e-9, solver_type=1), sheared, 0)
     return out
+
+
+def add_full_block(o, B):
+    """One LIMITS entry with every field it may carry (wall treatment, schedule, inlet planes and tables)."""
+    o.add_block(B["is_fluid"], B["first"], B["second"], bound_solver=B.get("bound_solver", 1), no_slip=B.get("no_slip", 0),
+                block_type=B.get("block_type", 0), fixed_vel_or_dynamic=B.get("fixed_vel_or_dynamic", 0),
+                times=B.get("times"), vels=B.get("vels"), insert_norm=B.get("insert_norm"),
+                insconst=B.get("insconst", 9999999.0), delete_norm=B.get("delete_norm"), delconst=B.get("delconst", 9999999.0),
+                aero_norm=B.get("aero_norm"), aeroconst=B.get("aeroconst", 9999999.0),
+                back=None if B.get("back") is None else np.asarray(B["back"], dtype=np.int64),
+                buffer=None if B.get("buffer") is None else np.asarray(B["buffer"], dtype=np.int64))
+
+
+def jittered_jet_deck():
+    """tests/decks/jet3d.para through the product's front end (round dynamic inlet rotated into +y, hollow Ghost pipe, Gissler
+    cross flow), every particle moved off its lattice site by U(-0.03, 0.03) dx so that the case is a generic input and
+    not a tie-stress one.  12 steps: three bursts of insertions, PIPE -> FREE transitions, the pipe wall's near-inlet
+    logic."""
+    from fjsph_b200 import frontend
+    from tests.util import INPUT_PARAMS
+
+    c = frontend.read_case(os.path.join(ROOT, "tests", "decks", "jet3d.para"), 3)
+    P = c["params"]
+    params = {k: (tuple(getattr(P, k)) if hasattr(getattr(P, k), "__len__") else getattr(P, k)) for k in INPUT_PARAMS}
+    rng = np.random.default_rng(5)
+    xi = c["xi"] + rng.uniform(-0.03, 0.03, c["xi"].shape) * P.particle_step
+    blocks = []
+    for B in c["blocks"]:
+        Bk = {k: B[k] for k in ("is_fluid", "first", "second", "bound_solver", "no_slip", "block_type", "fixed_vel_or_dynamic",
+                                 "insconst", "delconst", "aeroconst")}
+        for k in ("insert_norm", "delete_norm", "aero_norm"):
+            Bk[k] = [float(x) for x in B[k]]
+        Bk["times"] = None if B["times"] is None else [float(t) for t in B["times"]]
+        Bk["vels"] = None if B["vels"] is None else np.asarray(B["vels"]).tolist()
+        if B.get("back") is not None:
+            Bk["back"] = np.asarray(B["back"]).tolist()
+            Bk["buffer"] = np.asarray(B["buffer"]).tolist()
+        blocks.append(Bk)
+    return dict(xi=xi, v=c["v"], rho=c["rho"], p=c["p"], m=c["m"], b=c["b"], bound_points=c["bound_points"], params=params,
+                blocks=blocks)
 
 
 def make_sim(case, kind, dim, extra, mesh, cell0):
@@ -117,9 +158,7 @@ def make_sim(case, kind, dim, extra, mesh, cell0):
     if case.get("blocks") is not None:
         o.lib.orc_clear_blocks(o.h)
         for Bk in case["blocks"]:
-            o.add_block(Bk["is_fluid"], Bk["first"], Bk["second"], bound_solver=Bk.get("bound_solver", 1),
-                        no_slip=Bk.get("no_slip", 0), fixed_vel_or_dynamic=Bk.get("fixed_vel_or_dynamic", 0),
-                        times=Bk.get("times"), vels=Bk.get("vels"))
+            add_full_block(o, Bk)
     if cell0 is not None:
         for lvl in (0, 1):
             o.set("cellID", np.full(o.n, cell0, dtype=np.int64), lvl)

@@ -63,11 +63,11 @@ def test_oracle_reproduces_reference_vectors(path):
                     insconst=block["insconst"], delete_norm=block.get("delete_norm"), delconst=block.get("delconst", 9999999.0),
                     aero_norm=block["aero_norm"], aeroconst=block["aeroconst"], back=block["back"], buffer=block["buffer"])
     if _blocks(meta):
+        from tests.golden.make_reference_vectors import add_full_block
+
         o.lib.orc_clear_blocks(o.h)
         for B in _blocks(meta):
-            o.add_block(B["is_fluid"], B["first"], B["second"], bound_solver=B.get("bound_solver", 1),
-                        no_slip=B.get("no_slip", 0), fixed_vel_or_dynamic=B.get("fixed_vel_or_dynamic", 0),
-                        times=B.get("times"), vels=B.get("vels"))
+            add_full_block(o, B)
     if meta["cell0"] is not None:
         for lvl in (0, 1):
             o.set("cellID", np.full(o.n, meta["cell0"], dtype=np.int64), lvl)
@@ -103,14 +103,24 @@ def test_engine_reproduces_reference_vectors(path):
     # (-grad p / rho against g), so summation-order noise is 1e3-1e4 times larger RELATIVE to max|acc|, max|v| than in
     # the other cases, and the time step (set by max|acc|) inherits it: measured dt 3e-8, v 4e-8, rho 5e-10, acc 2e-7
     driven = "moving" in meta["name"]
+    # the 12-step jet deck (c = 300 m/s, dt = 7.5e-7, accelerations of 1e7): its first five steps stop at the
+    # sub-iteration limit WITHOUT converging, and a fixed-point iteration that does not contract multiplies the 1e-15
+    # summation-order differences by ~2.5 per sub-iteration: after the first step the frozen terms (lam, normals, vPert,
+    # aVisc, deltaD) agree with the oracle to 1e-15 while x is at 3e-9 and acc at 9e-6.  Counts, flags, insertions and
+    # the PIPE -> FREE transitions stay exact through all 12 steps; the state is held to what that amplification leaves.
+    stiff = "jet_deck" in meta["name"]
     n = case["xi"].shape[0]
     e = eng.Engine(eng.default_params(3, **case["params"]), 4 * n)
     e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
     if block is not None:
         e.set_blocks([block])
     if _blocks(meta):
-        e.set_blocks([dict(B, times=(None if not B.get("times") else np.asarray(B["times"])),
-                           vels=(None if not B.get("vels") else np.asarray(B["vels"], dtype=np.float64))) for B in _blocks(meta)])
+        e.set_blocks([dict({k: v for k, v in B.items() if v is not None},
+                           times=(None if not B.get("times") else np.asarray(B["times"])),
+                           vels=(None if not B.get("vels") else np.asarray(B["vels"], dtype=np.float64)),
+                           **({} if B.get("back") is None else dict(back=np.asarray(B["back"], dtype=np.int64),
+                                                                    buffer=np.asarray(B["buffer"], dtype=np.int64))))
+                      for B in _blocks(meta)])
     if mesh is not None:
         e.upload_mesh(mesh)
     if meta["cell0"] is not None:
@@ -122,7 +132,7 @@ def test_engine_reproduces_reference_vectors(path):
         assert s.iterations == int(z["step_iterations"][step]), (ctx, s.iterations, int(z["step_iterations"][step]))
         assert s.total_points == int(z["step_total_points"][step]), ctx
         assert s.n_add == int(z["step_n_add"][step]) and s.n_del == int(z["step_n_del"][step]), ctx
-        assert abs(s.dt - z["step_dt"][step]) <= (1e-9 if ties else 1e-6 if driven else 1e-12) * z["step_dt"][step], ctx
+        assert abs(s.dt - z["step_dt"][step]) <= (1e-9 if ties else 1e-6 if (driven or stiff) else 1e-12) * z["step_dt"][step], ctx
     got = e.download(FLOATS + INTS)
     for f in INTS:
         assert np.array_equal(got[f], z["out_" + f]), (meta["name"], f)
@@ -134,6 +144,10 @@ def test_engine_reproduces_reference_vectors(path):
                     gradRho=1e-6, L=1e-8, kernsum=1e-8, colour=1e-8)
     if driven:
         bars = {f: min(1e-5, 100.0 * t) for f, t in bars.items()}
+    if stiff:
+        bars = dict(xi=2e-6, rho=2e-7, v=1e-5, p=2e-6, acc=1e-5, Af=1e-5, Rrho=1e-5, vPert=1e-5, lam=2e-6, lam_nb=2e-6)  # ~10 x measured
+    if os.environ.get("FJSPH_GOLDEN_REPORT"):
+        print(meta["name"], {f: "%.1e" % relerr(got[f], z["out_" + f]) for f in bars})
     for f, tol in bars.items():
         r = relerr(got[f], z["out_" + f])
         assert r <= tol, "%s: field %s differs from the reference by %.3e (bar %.0e)" % (meta["name"], f, r, tol)
