@@ -695,6 +695,8 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
         e->pencil_order = std::string(order) != "morton";
     if (const char* tile = std::getenv("FJSPH_B200_PENCIL_TILE"))
         std::sscanf(tile, "%d,%d", &e->pencil_tile_x, &e->pencil_tile_y);
+    if (const char* split = std::getenv("FJSPH_B200_SPLIT_SURFACE"))
+        e->split_surface_sweep = std::string(split) != "0";
     if (const char* order = std::getenv("FJSPH_B200_LIST_ORDER")) /* "index" (default) | "columns", engine.cuh */
         e->column_order = std::string(order) == "columns";
     FJ_CUDA(cudaMalloc(&e->near_inlet, cap * sizeof(int)));
@@ -707,6 +709,7 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
     FJ_CUDA(cudaMallocHost(&e->h_red, 16 * sizeof(double)));
     FJ_CUDA(cudaMalloc(&e->d_flag, 4 * sizeof(int)));
     FJ_CUDA(cudaMallocHost(&e->h_flag, 4 * sizeof(int)));
+    std::memset(e->h_flag, 0, 4 * sizeof(int));
     e->stage_bytes = cap * kStageBytesPerParticle + 64 * 256;
     FJ_CUDA(cudaMalloc(&e->stage, e->stage_bytes));
     *out = e;

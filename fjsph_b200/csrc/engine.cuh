@@ -225,6 +225,9 @@ struct FjsphEngine
     // the L1 data pipe serves in one wavefront.  Measured: force sweep -3 %, the other sweeps +1..2 %, the step +0.7 %
     // (within noise), so it is off by default.
     bool column_order = false;
+    // fused surface / shifting sweep in two launches (lean bulk + near-surface rest) when few warps are near a surface
+    // (sweeps.cu, k_surf23_shift CLASS; FJSPH_B200_SPLIT_SURFACE=0 keeps the single launch)
+    bool split_surface_sweep = true;
 
     // reductions / scalars
     double* red = nullptr;              // device scratch for block partials

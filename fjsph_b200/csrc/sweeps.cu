@@ -357,7 +357,8 @@ template <bool SURF, bool DISS>
 #define FJ_S1_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
-    k_surf1_diss(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n, int i0)
+    k_surf1_diss(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n, int i0,
+                 int* __restrict__ near_warps = nullptr)
 {
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; /* slots [i0, n) */
     if (i >= n || blk[i] < n_bound_blocks)
@@ -491,6 +492,16 @@ __global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
             out.z = tz * inv;
         }
         S.P4[i] = out;
+        if (near_warps)
+        {
+            /* how many warps hold a particle the lean surface / shifting sweep cannot take (k_surf23_shift, CLASS) */
+            const bool near = (out.x != 0.0 || out.y != 0.0 || out.z != 0.0) ||
+                              ((b_i == FJSPH_FREE) && (C.acase == 1) && (lam_nb < C.lam_cutoff));
+            const unsigned act = __activemask();
+            const unsigned m = __ballot_sync(act, near);
+            if (m && (threadIdx.x & 31) == unsigned(__ffs(int(act)) - 1))
+                atomicAdd(near_warps, 1);
+        }
         if (b_i < FJSPH_PIPE)
         {
             double4 th = S.TH[i];
@@ -527,8 +538,17 @@ struct RecS2
 #ifndef FJ_FUSE_SHIFT
 #define FJ_FUSE_SHIFT 1
 #endif
-template <bool SURF23, bool SHIFT>
-__global__ void __launch_bounds__(TPB, FJ_S23_MINBLOCKS)
+// CLASS splits the fused sweep by what a particle needs (0: everybody, the stage entry points):
+//   1 "lean": particles WITHOUT a loop-1 normal and without an occlusion to compute -- the bulk of a fluid.  Their
+//      curvature is 0, n_i . n_j is 0 for every j, and of neighbour j's P4 record only the surf flag matters (one
+//      8-byte load instead of the 32-byte gather); no L matrix, no occlusion, far fewer registers, more resident warps;
+//   2 the others (near a free surface), with the full body.
+// The two launches cover disjoint particles; a warp that holds both kinds runs in both.
+#ifndef FJ_S23_LEAN_MINBLOCKS
+#define FJ_S23_LEAN_MINBLOCKS 4
+#endif
+template <bool SURF23, bool SHIFT, int CLASS = 0>
+__global__ void __launch_bounds__(TPB, CLASS == 1 ? FJ_S23_LEAN_MINBLOCKS : FJ_S23_MINBLOCKS)
     k_surf23_shift(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n, int i0)
 {
     const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; /* slots [i0, n) */
@@ -539,7 +559,15 @@ __global__ void __launch_bounds__(TPB, FJ_S23_MINBLOCKS)
     const double4 ni = S.P4[i]; /* Detect_Surface loop-1 normal (unit or zero), surf */
     const int b_i = S.b[i];
     const double lam_nb = S.NP[i].w;
-    const bool ni_nz = (ni.x * ni.x + ni.y * ni.y + ni.z * ni.z) > 0.0;
+    const bool ni_nz_real = (ni.x * ni.x + ni.y * ni.y + ni.z * ni.z) > 0.0;
+    if (CLASS != 0)
+    {
+        const bool near = ni_nz_real || ((b_i == FJSPH_FREE) && (C.acase == 1) && (lam_nb < C.lam_cutoff));
+        if (near != (CLASS == 2))
+            return;
+    }
+    const bool ni_nz = (CLASS == 1) ? false : ni_nz_real;
+    bool has_fluid = false; /* lean: min_j n_i . n_j over fluid neighbours is 0 if there is one */
 
     // ---- Detect_Surface loop 2 set-up
     const bool occl = (b_i == FJSPH_FREE) && (C.acase == 1);
@@ -578,7 +606,7 @@ __global__ void __launch_bounds__(TPB, FJ_S23_MINBLOCKS)
     double curve = 0.0, woccl_ = 0.0;
     int zone = (ni.w != 0.0) ? 1 : 0; /* the list of the reference includes self */
     /* woccl is overwritten with 1 when lam_nb >= lam_cutoff, so the occlusion max is only needed below it */
-    const bool need_occl = SURF23 && occl && (lam_nb < C.lam_cutoff);
+    const bool need_occl = (CLASS != 1) && SURF23 && occl && (lam_nb < C.lam_cutoff);
 
     // ---- particle_shift set-up (Shifting.cpp:205-212)
     const bool do_shift = SHIFT && !(lam_nb < 0.55 || b_i == FJSPH_BUFFER);
@@ -594,7 +622,10 @@ __global__ void __launch_bounds__(TPB, FJ_S23_MINBLOCKS)
         [&](const unsigned ent) {
             const unsigned j = ent & FJ_IDX_MASK;
             RecS2 q;
-            q.n = gather(S.P4, j);
+            if (CLASS == 1)
+                q.n.w = __ldg(&S.P4[j].w); /* the surf flag is all a lean particle reads of n_j */
+            else
+                q.n = gather(S.P4, j);
             if (need_pos)
                 q.p = gather(S.P0, j);
             if (do_shift)
@@ -639,7 +670,9 @@ __global__ void __launch_bounds__(TPB, FJ_S23_MINBLOCKS)
                 dux += f * rx;
                 duy += f * ry;
                 duz += f * rz;
-                if (!known_bulk && (ent & FJ_NB_FLUID))
+                if (CLASS == 1)
+                    has_fluid = has_fluid || ((ent & FJ_NB_FLUID) != 0u);
+                else if (!known_bulk && (ent & FJ_NB_FLUID))
                 {
                     /* n_i and n_j are unit vectors or zero already (loop 1), normalized() is the identity */
                     const double c = ni.x * nj.x + ni.y * nj.y + ni.z * nj.z;
@@ -650,6 +683,8 @@ __global__ void __launch_bounds__(TPB, FJ_S23_MINBLOCKS)
                 maxU2 = fmax(maxU2, ux * ux + uy * uy + uz * uz);
             }
         });
+    if (CLASS == 1 && has_fluid)
+        min_c = 0.0;
 
     if (SURF23)
     {
@@ -1298,8 +1333,18 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
         KERNEL<<<fj_blocks(i1 - i0, TPB), TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, i1, i0); })
     if (do_surface && do_dissipation)
     {
-        SplitScope ks(e, "surf1+diss");
-        st = FJ_SWEEP((k_surf1_diss<true, true>));
+        /* count the warps holding near-surface particles for the split decision below; the count of THIS pass is read
+           at the next one (it has crossed PCIe by then: every pass ends in synchronising readbacks) */
+        FJ_CUDA(cudaMemsetAsync(e->d_flag + 2, 0, sizeof(int), e->stream));
+        {
+            SplitScope ks(e, "surf1+diss");
+            int* nw = e->d_flag + 2;
+            st = launch_split(e, n, [&](int i0, int i1) {
+                k_surf1_diss<true, true><<<fj_blocks(i1 - i0, TPB), TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks,
+                                                                                        e->C, i1, i0, nw);
+            });
+        }
+        FJ_CUDA(cudaMemcpyAsync(e->h_flag + 2, e->d_flag + 2, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     }
     else if (do_surface)
     {
@@ -1322,7 +1367,18 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
     if (do_surface && fuse_shift && e->P.ale && FJ_FUSE_SHIFT)
     {
         SplitScope ks(e, "surf2+3+shift");
-        st = FJ_SWEEP((k_surf23_shift<true, true>));
+        /* Two launches (lean bulk, then the near-surface rest) pay when few warps hold near-surface particles: with the
+           lean body at ~0.6 of the full one, below ~0.4 of the warps (block: 0.17, 70 -> 54 ms; a 1 M droplet: 0.5,
+           where one fused launch is faster).  The fraction is the one counted at the previous pass. */
+        const double near_frac = double(e->h_flag[2]) / double(std::max(1, (n + 31) / 32));
+        if (e->split_surface_sweep && near_frac < 0.35)
+        {
+            st = FJ_SWEEP((k_surf23_shift<true, true, 1>));
+            if (!st)
+                st = FJ_SWEEP((k_surf23_shift<true, true, 2>));
+        }
+        else
+            st = FJ_SWEEP((k_surf23_shift<true, true>));
     }
     else if (do_surface)
     {
