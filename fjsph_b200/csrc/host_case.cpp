@@ -12,8 +12,11 @@
 // std::uniform_real_distribution<double>(0, eps*dx), drawn in the reference's order, one engine per block.
 // Reference behaviour kept on purpose: the solid cylinder's inner loop never runs (`kk > nk`, cylinder.cpp:378,490),
 // local `rotmat` variables shadow the member so only "Rotation angles" rotates a block (cylinder.cpp:196-241,
-// inlet.cpp:141-213), the hydrostatic initialisation always measures height along y (Init.cpp:480-493).
-// Not restated: Arc/Arch blocks (rejected with an error), JSON block files (nlohmann/json is not vendored).
+// inlet.cpp:141-213), the hydrostatic initialisation always measures height along y (Init.cpp:480-493), an Arc / Arch
+// block's counts default to 0, not -1, so its thickness / length / spacing fallbacks never fire and the 2D generator walks
+// the block file's "i-direction count" (arc.cpp:446-495,546-554), the 3D centre + start + end form states a -90 degree arc
+// whatever the end point (arc.cpp:206-245) and so generates only its straights.
+// Not restated: JSON block files (nlohmann/json is not vendored).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -572,6 +575,318 @@ void circle_generate(Block& b, double gs)
             }
 }
 
+// ---------------------------------------------------------------- Arc / Arch (arc.cpp)
+// x of A x = b for a 2x2 A as Eigen's colPivHouseholderQr().solve() computes it (arc.cpp:73,230): the column of larger
+// norm first, one Householder reflection, back-substitution over the pivots above the rank threshold.
+void qr_solve2(const double A[2][2], const double rhs[2], double x[2])
+{
+    const double eps = std::numeric_limits<double>::epsilon();
+    double q[2][2] = {{A[0][0], A[0][1]}, {A[1][0], A[1][1]}};
+    double c[2] = {rhs[0], rhs[1]};
+    int perm[2] = {0, 1};
+    const double n0 = q[0][0] * q[0][0] + q[1][0] * q[1][0], n1 = q[0][1] * q[0][1] + q[1][1] * q[1][1];
+    const double maxcol = std::sqrt(std::max(n0, n1));
+    const double thr = (maxcol * eps / 2.0) * (maxcol * eps / 2.0);
+    int nzp = 2;
+    if (n1 > n0)
+    {
+        std::swap(q[0][0], q[0][1]);
+        std::swap(q[1][0], q[1][1]);
+        std::swap(perm[0], perm[1]);
+    }
+    if (std::max(n0, n1) < thr * 2.0)
+        nzp = 0;
+    /* reflection that zeroes q[1][0] */
+    const double c0 = q[0][0], tail = q[1][0] * q[1][0];
+    double beta = c0, tau = 0.0, ess = 0.0;
+    if (tail > (std::numeric_limits<double>::min)())
+    {
+        beta = std::sqrt(c0 * c0 + tail);
+        if (c0 >= 0.0)
+            beta = -beta;
+        ess = q[1][0] / (c0 - beta);
+        tau = (beta - c0) / beta;
+    }
+    q[0][0] = beta;
+    {
+        const double t = (q[0][1] + ess * q[1][1]) * tau;
+        q[0][1] -= t;
+        q[1][1] -= t * ess;
+    }
+    if (nzp == 2 && q[1][1] * q[1][1] < thr)
+        nzp = 1;
+    if (nzp > 0)
+    {
+        const double t = (c[0] + ess * c[1]) * tau;
+        c[0] -= t;
+        c[1] -= t * ess;
+    }
+    /* the second reflection of a 2x2 is the identity (no tail) */
+    double y[2] = {0.0, 0.0};
+    if (nzp == 2)
+    {
+        y[1] = c[1] / q[1][1];
+        y[0] = (c[0] - q[0][1] * y[1]) / q[0][0];
+    }
+    else if (nzp == 1)
+        y[0] = c[0] / q[0][0];
+    x[perm[0]] = y[0];
+    x[perm[1]] = y[1];
+}
+
+// get_arclength_centrepoint (arc.cpp:27-57 in 2D, 176-250 in 3D): radius and the two angles, in degrees
+bool arc_from_centre(Block& b, std::string& err)
+{
+    const V3 d1 = b.start - b.centre, d2 = b.end - b.centre;
+    const double r = dot(d1, d1);
+    if (std::fabs(dot(d2, d2) - r) > 0.001)
+    {
+        err += "Block \"" + b.name + "\": arc points are not correctly defined, the ending radius differs from the starting radius. ";
+        return false;
+    }
+    b.radius = std::sqrt(r);
+    if (b.dim == 2)
+    {
+        b.arc_start = std::atan2(d1[1], d1[0]) * 180 / M_PI;
+        b.arc_end = std::atan2(d2[1], d2[0]) * 180 / M_PI;
+        return true;
+    }
+    /* 3D: coordinates of the end point in the plane basis (d1, v).  As in the reference, the right-hand side of the
+       2x2 system is v itself (so the solution is (0, 1) whatever the end point), and it keeps its x and y components
+       when another pair of axes is chosen for the matrix: the stated angles are 90 and atan2(a, b) degrees. */
+    const V3 e1 = normalized(d1), e2 = normalized(d2);
+    const V3 w = normalized(cross(e2, e1));
+    const V3 v = normalized(cross(w, e1));
+    const double maxx = std::fabs(e1[0]) + std::fabs(v[0]), maxy = std::fabs(e1[1]) + std::fabs(v[1]),
+                 maxz = std::fabs(e1[2]) + std::fabs(v[2]);
+    double m[2][2] = {{e1[0], v[0]}, {e1[1], v[1]}};
+    const double rhs[2] = {v[0], v[1]};
+    if (maxx < maxy && maxx < maxz)
+    {
+        m[0][0] = e1[1], m[0][1] = v[1], m[1][0] = e1[2], m[1][1] = v[2];
+    }
+    else if (maxy < maxx && maxy < maxz)
+    {
+        m[0][0] = e1[0], m[0][1] = v[0], m[1][0] = e1[2], m[1][1] = v[2];
+    }
+    double ab[2];
+    qr_solve2(m, rhs, ab);
+    b.arc_start = std::atan2(1.0, 0.0) * 180 / M_PI;
+    b.arc_end = std::atan2(ab[0], ab[1]) * 180 / M_PI;
+    b.right = w;
+    return true;
+}
+
+void arc_check(Block& b, const Ctx& C, double& gs, std::string& err)
+{
+    common_check(b, C, err);
+    const int dim = b.dim;
+    bool has_config = false, arc_defined = false;
+    if (dim == 2 && b.defined(b.centre))
+    {
+        if (b.arc_start >= 0 && b.arc_end >= 0 && b.radius > 0)
+            has_config = true;
+        else if (b.arc_start >= 0 && b.ni > 0 && b.radius > 0)
+            has_config = true;
+        else if (b.arc_start >= 0 && b.arclength != DEFV && b.radius > 0)
+            has_config = arc_defined = true;
+    }
+    if (!has_config && b.defined(b.centre) && b.defined(b.start) && b.defined(b.end))
+    {
+        has_config = true;
+        if (!arc_from_centre(b, err))
+            return;
+    }
+    if (!has_config && dim == 3)
+    {
+        if (b.defined(b.centre) && b.defined(b.start) && b.defined(b.mid) && b.arclength != DEFV)
+            has_config = arc_defined = true;
+    }
+    else if (!has_config && b.defined(b.start) && b.defined(b.end) && b.defined(b.mid))
+    {
+        /* 2D, three points on the arc (get_arclength_midpoint, arc.cpp:59-78): the centre from the two chord equations */
+        has_config = true;
+        const V3 &s = b.start, &e = b.end, &mp = b.mid;
+        const V3 r1(s[0] * s[0], s[1] * s[1], 0), r2(mp[0] * mp[0], mp[1] * mp[1], 0), r3(e[0] * e[0], e[1] * e[1], 0);
+        double m[2][2] = {{(s[0] - e[0]), (s[1] - e[1])}, {(s[0] - mp[0]), (s[1] - mp[1])}};
+        const double rhs[2] = {r1[0] - r3[0] + r1[1] - r3[1], r1[0] - r2[0] + r1[1] - r2[1]};
+        for (auto& row : m)
+            for (double& a : row) a *= 2.0;
+        double cxy[2];
+        qr_solve2(m, rhs, cxy);
+        b.centre = V3(cxy[0], cxy[1], 0.0);
+        if (!arc_from_centre(b, err))
+            return;
+    }
+    if (!has_config && b.defined(b.centre) && b.defined(b.start) && b.arclength != DEFV)
+    {
+        if (dim == 2 || b.defined(b.right))
+            has_config = arc_defined = true;
+    }
+    if (!has_config)
+        err += "Block \"" + b.name + "\" arc geometry has not been sufficiently defined. ";
+    if (b.dx < 0)
+        b.dx = (b.ni < 0) ? gs : (2.0 * b.radius) / double(b.ni);
+    if (b.thickness < 0)
+    {
+        if (b.nk < 0)
+            err += "Block \"" + b.name + "\" arc thickness has not been correctly defined. ";
+    }
+    else if (b.nk < 0)
+        b.nk = b.particle_order ? ceil_i(b.thickness / gs / std::sqrt(3.0) * 2.0) : ceil_i(b.thickness / gs);
+    if (!err.empty())
+        return;
+
+    const double dtheta = gs / b.radius;
+    if (arc_defined)
+    {
+        if (dim == 3)
+        {
+            /* get_arc_end (arc.cpp:149-174): the radius from the start point; the start must lie in the arch plane */
+            const V3 u = b.start - b.centre;
+            b.radius = norm(u);
+            if (std::fabs(dot(b.right, b.start) - dot(b.right, b.centre)) > 1e-4)
+            {
+                err += "Block \"" + b.name + "\": points do not exist upon the plane defined by the provided normal. ";
+                return;
+            }
+            const V3 uu = u / b.radius, w = normalized(b.right);
+            const V3 v = normalized(cross(uu, w));
+            const double alen = b.arclength * M_PI / 180.0;
+            b.end = b.radius * (std::cos(alen) * uu + std::sin(alen) * v) + b.centre;
+        }
+    }
+    else
+    {
+        if (b.arc_end < 0 && b.ni > 0)
+            b.arc_end = 180.0 / M_PI * (b.arc_start * M_PI / 180 + double(b.ni) * dtheta);
+        b.arclength = b.arc_end - b.arc_start;
+    }
+    /* a local count: the member ni (what the 2D generator walks) stays what the block file gave (arc.cpp:493-495) */
+    int ni = ceil_i((std::fabs(b.arclength) * M_PI / 180) / dtheta);
+    ni = ni > 1 ? ni : 1;
+    const int smax = b.sstraight > 0 ? ceil_i(b.sstraight / gs) : 0;
+    const int emax = b.estraight > 0 ? ceil_i(b.estraight / gs) : 0;
+    long np = long(ni + smax + emax) * b.nk;
+    if (dim == 3)
+    {
+        if (b.length < 0)
+        {
+            if (b.nj < 0)
+            {
+                err += "Block \"" + b.name + "\" arch length has not been correctly defined. ";
+                return;
+            }
+        }
+        else if (b.nj < 0)
+        {
+            b.nj = b.particle_order ? ceil_i(b.length / gs / std::sqrt(6.0) * 3.0) : ceil_i(b.length / gs);
+            b.nj = b.nj > 1 ? b.nj : 1;
+        }
+        np *= b.nj;
+    }
+    b.npts = np > 0 ? size_t(np) : 0;
+    post_check(b, gs);
+}
+
+void arc_generate(Block& b, double gs)
+{
+    std::uniform_real_distribution<double> unif(0.0, MEPS * gs);
+    std::default_random_engine re;
+    const double dtheta = gs / b.radius;
+    const int smax = ceil_i(b.sstraight / gs), emax = ceil_i(b.estraight / gs);
+    if (b.dim == 2)
+    {
+        /* make_arc (arc.cpp:80-145): nk rings inwards from the radius, each a start straight, ni arc points, an end straight */
+        const double theta0 = b.arc_start * M_PI / 180.0;
+        const int ni = b.ni, nk = b.nk;
+        const V3 svec(std::cos(theta0), std::sin(theta0), 0.0), snormal(svec[1], -svec[0], 0.0);
+        const V3 evec(std::cos(theta0 + double(ni - 1) * dtheta), std::sin(theta0 + double(ni - 1) * dtheta), 0.0);
+        const V3 enormal(-evec[1], evec[0], 0.0);
+        for (int jj = 0; jj < nk; ++jj)
+        {
+            if (b.sstraight > 0)
+                for (int ii = smax; ii > 0; --ii)
+                {
+                    V3 p = svec * (b.radius - double(jj) * gs) + snormal * double(ii) * gs;
+                    p = p + (make2(unif(re), unif(re)) + b.centre);
+                    b.coords.push_back(p);
+                }
+            for (int ii = 0; ii < ni; ++ii)
+            {
+                double theta = theta0 + double(ii) * dtheta, r = b.radius;
+                if (b.particle_order)
+                {
+                    theta += 0.5 * dtheta * (jj % 2);
+                    r -= 0.5 * std::sqrt(3.0) * double(jj) * gs;
+                }
+                else
+                    r -= double(jj) * gs;
+                V3 p(std::cos(theta) * r, std::sin(theta) * r, 0.0);
+                p = p + make2(unif(re), unif(re));
+                p = p + b.centre;
+                b.coords.push_back(p);
+            }
+            if (b.estraight > 0)
+                for (int ii = 1; ii <= emax; ++ii)
+                {
+                    V3 p = evec * (b.radius - double(jj) * gs) + enormal * double(ii) * gs;
+                    p = p + (make2(unif(re), unif(re)) + b.centre);
+                    b.coords.push_back(p);
+                }
+        }
+        return;
+    }
+    /* make_arch (arc.cpp:280-384): plane basis (u, v) with u towards the start point, w along the archway; nj slices of
+       nk layers outwards from the radius.  The arc count comes from the signed arc length (arc.cpp:567-569). */
+    const int nrad = ceil_i((b.arclength * M_PI / 180.0) / dtheta), nthick = b.nk, nlong = b.nj;
+    const V3 u = normalized(b.start - b.centre), w = normalized(b.right);
+    const V3 v = normalized(cross(u, w));
+    const V3 evec = std::cos(double(nrad - 1) * dtheta) * u + std::sin(double(nrad - 1) * dtheta) * v;
+    const V3 enorm = cross(evec, w);
+    for (int kk = 0; kk < nlong; ++kk)
+        for (int jj = 0; jj < nthick; ++jj)
+        {
+            double r = b.radius, l = double(kk) * gs, doffset = 0;
+            if (b.particle_order)
+            {
+                r += 1.0 / 3.0 * std::sqrt(6.0) * double(jj) * gs;
+                l = 0.5 * std::sqrt(3.0) * (double(kk) + double(jj % 2) / 3.0) * gs;
+                doffset = 0.5 * dtheta * ((jj + kk) % 2);
+            }
+            else
+                r += double(jj) * gs;
+            if (b.sstraight > 0)
+                for (int ii = smax; ii > 0; --ii)
+                {
+                    const double dist = double(ii) * gs + doffset;
+                    V3 p = u * r - v * dist + l * w;
+                    p = p + (make3(unif(re), unif(re), unif(re)) + b.centre);
+                    b.coords.push_back(p);
+                }
+            for (int ii = 0; ii < nrad; ++ii)
+            {
+                double theta = double(ii) * dtheta;
+                const double la = double(kk) * gs; /* the arc keeps the grid offset along w in HCP order too (arc.cpp:352) */
+                if (b.particle_order)
+                    theta += doffset;
+                const double a = std::cos(theta) * r, bb = std::sin(theta) * r;
+                V3 p = a * u + bb * v + la * w;
+                p = p + make3(unif(re), unif(re), unif(re));
+                p = p + b.centre;
+                b.coords.push_back(p);
+            }
+            if (b.estraight > 0)
+                for (int ii = 1; ii <= emax; ++ii)
+                {
+                    const double dist = double(ii) * gs + doffset;
+                    V3 p = evec * r + enorm * dist + l * w;
+                    p = p + (make3(unif(re), unif(re), unif(re)) + b.centre);
+                    b.coords.push_back(p);
+                }
+        }
+}
+
 // ---------------------------------------------------------------- Cylinder (cylinder.cpp)
 void cylinder_check(Block& b, const Ctx& C, double& gs, std::string& err)
 {
@@ -1122,8 +1437,6 @@ bool read_bmap(const std::string& path, const Ctx& C, double& gs, Shapes& out, s
             b->bound_type = shape_type_of(shape_name, dim);
             if (b->bound_type < 0)
                 err += "Unrecognised boundary shape, \"" + shape_name + "\". ";
-            else if (b->bound_type == arcSection)
-                err += "Arc/Arch blocks are not restated by this front end. ";
             out.block.push_back(std::move(b));
             shape_name.clear();
         }
@@ -1232,6 +1545,7 @@ bool read_bmap(const std::string& path, const Ctx& C, double& gs, Shapes& out, s
         case linePlane: line_check(b, C, gs, e); break;
         case squareCube: square_check(b, C, gs, e); break;
         case circleSphere: circle_check(b, C, gs, e); break;
+        case arcSection: arc_check(b, C, gs, e); break;
         case cylinderT: cylinder_check(b, C, gs, e); break;
         case inletZone: inlet_check(b, C, gs, e); break;
         case coordDef: coord_check(b, C, gs, e); break;
@@ -1256,6 +1570,7 @@ void generate_points(Shapes& S, double gs, const Ctx& C)
         case linePlane: line_generate(b, gs); break;
         case squareCube: square_generate(b, gs); break;
         case circleSphere: circle_generate(b, gs); break;
+        case arcSection: arc_generate(b, gs); break;
         case cylinderT: cylinder_generate(b, gs); break;
         case inletZone: inlet_generate(b, gs); break;
         default: break;

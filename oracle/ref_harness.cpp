@@ -74,8 +74,6 @@ void VLM::GetGamma(StateVecD) { not_on_path("VLM::GetGamma"); }
 void VLM::write_VLM_Panels(std::string&) { not_on_path("VLM::write_VLM_Panels"); }
 void VLM::Plot_Streamlines(std::string&) { not_on_path("VLM::Plot_Streamlines"); }
 #endif
-void ArcShape::check_input(SIM const&, real&, int&) { not_on_path("ArcShape::check_input"); }
-void ArcShape::generate_points(real const&) { not_on_path("ArcShape::generate_points"); }
 /* TECIO / HDF5 writers (BinaryIO.cpp, H5IO.cpp need the absent libraries) */
 void Write_Binary_Timestep(SIM const&, real const&, SPHState const&, bound_block const&, char const*, int32_t const&,
                            void* const&)

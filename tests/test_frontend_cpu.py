@@ -238,3 +238,66 @@ def test_moving_wall_schedule_and_errors(tmp_path):
                                  .replace(" SPH aerodynamic case: (none)\n", "") % (tmp_path / "f.bmap")), 2)
     with pytest.raises(_lib.FjsphError, match="initial spacing"):
         frontend.read_case(nodx, 2)
+
+
+def test_arc_and_arch_blocks():
+    """arc.cpp: an Arc (2D) is nk rings inwards from the radius, each a start straight of ceil(s/dx) points, the block
+    file's i-direction count of arc points dtheta = dx/R apart, and an end straight; an Arch (3D) is nj slices along the
+    plane normal of nk layers OUTWARDS from the radius, ceil(arclength/dtheta) arc points each.  (The decks are compared
+    particle for particle with the reference's own generator in test_frontend_vs_reference.py.)"""
+    dx = 0.05
+    c = frontend.read_case(deck("arc2d.para"), 2)
+    names = [b["name"] for b in c["blocks"]]
+    assert names == ["Bowl", "Lid", "Hook", "Sweep", "Water"]
+    # the last wall block is clear of everything else, so no particle of it is culled: 2 rings of 21 points
+    sweep = c["blocks"][3]
+    x = c["xi"][sweep["first"]:sweep["second"]]
+    assert x.shape[0] == 2 * 21
+    rad = np.hypot(x[:, 0] - 7.0, x[:, 1] - 1.0)
+    assert np.allclose(rad[:21], 0.8, atol=1e-12) and np.allclose(rad[21:], 0.8 - dx, atol=1e-12)
+    ang = np.arctan2(x[:21, 1] - 1.0, x[:21, 0] - 7.0)
+    assert np.allclose(ang, np.deg2rad(10.0) + np.arange(21) * dx / 0.8, atol=1e-12)
+    # three points on an arc give the centre (5, 2) and the radius 1; the points start at the start point
+    hook = c["blocks"][2]
+    x = c["xi"][hook["first"]:hook["second"]]
+    assert np.allclose(np.hypot(x[:20, 0] - 5.0, x[:20, 1] - 2.0), 1.0, atol=1e-12)
+    assert np.allclose(x[0], (5.0, 1.0), atol=1e-12)
+
+    c = frontend.read_case(deck("arch3d.para"), 3)
+    assert [b["name"] for b in c["blocks"]] == ["Trough", "Vault", "Stub", "Water"]
+    tr = c["blocks"][0]
+    x = c["xi"][tr["first"]:tr["second"]]
+    nrad, smax, emax, nk, nj = int(np.ceil(np.pi / (dx / 0.8))), 4, 3, 3, 12
+    assert x.shape[0] == (nrad + smax + emax) * nk * nj
+    ring = x.reshape(nj, nk, smax + nrad + emax, 3)
+    for kk in range(nj):
+        assert np.allclose(ring[kk, :, :, 1], kk * dx, atol=1e-12)            # slices along the normal (0, 1, 0)
+        for jj in range(nk):
+            arc = ring[kk, jj, smax:smax + nrad]
+            assert np.allclose(np.hypot(arc[:, 0], arc[:, 2] - 1.0), 0.8 + jj * dx, atol=1e-12)
+    # the start straight leaves the start point (-0.8, 0, 1) against the direction of travel, u x w = (0, 0, -1)
+    assert np.allclose(ring[0, 0, :smax, 0], -0.8, atol=1e-12)
+    assert np.allclose(ring[0, 0, :smax, 2], 1.0 + dx * np.arange(smax, 0, -1), atol=1e-12)
+    # centre + start + end in 3D: the reference states a -90 degree arc whatever the end point, so only straights exist
+    stub = c["blocks"][2]
+    assert stub["second"] - stub["first"] == (4 + 4) * 2 * 3
+
+
+def test_arch_errors_are_reported(tmp_path):
+    """Where arc.cpp calls exit() (a start point off the plane of the stated normal, arc.cpp:162-166; end and start radii
+    that differ, :36-42) or flags a fault (nothing that defines an arc, :455-459) the product returns the diagnosis."""
+    fluid = write(tmp_path, "f.bmap", "   Name: W\n  Shape: Cube\n Start coordinate: 0,0,0\n End coordinate: 0.2,0.2,0.2\n block end\n")
+
+    def para_for(i, block):
+        wall = write(tmp_path, "b%d.bmap" % i, block)
+        return write(tmp_path, "para%d" % i, " Input boundary definition filename: %s\n Input fluid definition filename: %s\n"
+                     " SPH initial spacing: 0.1\n SPH aerodynamic case: (none)\n SPH frame time interval: 1\n" % (wall, fluid))
+
+    head = "   Name: A\n  Shape: Arch\n Particle spacing: 0.1\n Wall radial particle count: 1\n j-direction count: 1\n"
+    with pytest.raises(_lib.FjsphError, match="plane defined by the provided normal"):
+        frontend.read_case(para_for(0, head + " Centre coordinate: 0,0,2\n Start coordinate: 1,0,2.5\n Arch normal: 0,0,1\n"
+                                    " Arc length (degree): 90\n block end\n"), 3)
+    with pytest.raises(_lib.FjsphError, match="ending radius differs"):
+        frontend.read_case(para_for(1, head + " Centre coordinate: 0,0,2\n Start coordinate: 1,0,2\n End coordinate: 0,2,2\n block end\n"), 3)
+    with pytest.raises(_lib.FjsphError, match="not been sufficiently defined"):
+        frontend.read_case(para_for(2, head + " Centre coordinate: 0,0,2\n Radius: 1\n block end\n"), 3)

@@ -37,6 +37,8 @@ pytestmark = pytest.mark.skipif(not _have("ref3d"), reason="oracle/_ref not buil
 DECKS = [
     ("jet3d", os.path.join(HERE, "decks", "jet3d.para"), 3),          # round inlet, rotated, in a hollow Ghost cylinder
     ("dam2d", os.path.join(HERE, "decks", "dam2d.para"), 2),          # walls + hydrostatic initialisation
+    ("arc2d", os.path.join(HERE, "decks", "arc2d.para"), 2),          # Arc walls: every way arc.cpp takes of stating an arc
+    ("arch3d", os.path.join(HERE, "decks", "arch3d.para"), 3),        # Arch walls: straights, HCP, a tilted plane
     ("Dam_2D", EXAMPLES + "/Dam_2D/para", 2),
     ("Standing_Column", EXAMPLES + "/Standing_Column/para", 2),
     ("Poiseuille", EXAMPLES + "/Poiseuille/para", 2),
