@@ -192,3 +192,36 @@ def test_openfoam_case_reads_like_the_reference(tmp_path):
     for k in ("verts", "cCentre", "cVel", "cP"):
         assert np.array_equal(mine[k], theirs[k]), k
     assert np.all(mine["cRho"] == 1.2262)
+
+
+def test_arch_deck_steps_follow_the_reference():
+    """tests/decks/arch3d (water resting in a trough of Arch blocks, a Ghost vault, culled intersections) through the
+    product's front end, then three Integrator::integrate steps on the compiled reference and on the oracle: the same
+    sub-iterations and time steps, flags identical, state to 1e-12 (the engine is held to the oracle on the same deck in
+    tests/test_gpu_decks.py)."""
+    from tests.util import relerr, INPUT_PARAMS
+
+    mine = frontend.read_case(os.path.join(HERE, "decks", "arch3d.para"), 3)
+    P = mine["params"]
+    params = {k: (tuple(getattr(P, k)) if hasattr(getattr(P, k), "__len__") else getattr(P, k)) for k in INPUT_PARAMS}
+
+    def fed(**kind):
+        a = orc.Oracle(orc.default_params(3, **params), **kind)
+        a.set_particles(mine["xi"], mine["v"], mine["rho"], mine["p"], mine["m"], mine["b"], mine["bound_points"])
+        a.lib.orc_clear_blocks(a.h)
+        for B in mine["blocks"]:
+            a.add_block(B["is_fluid"], B["first"], B["second"], bound_solver=B["bound_solver"], no_slip=B["no_slip"],
+                        block_type=B["block_type"], fixed_vel_or_dynamic=B["fixed_vel_or_dynamic"], times=B["times"],
+                        vels=B["vels"], insert_norm=B["insert_norm"], insconst=B["insconst"], delete_norm=B["delete_norm"],
+                        delconst=B["delconst"], aero_norm=B["aero_norm"], aeroconst=B["aeroconst"])
+        return a
+
+    o, r = fed(), fed(kind="ref3d")
+    for step in range(3):
+        _, so = o.integrate()
+        _, sr = r.integrate()
+        assert so.iterations == sr.iterations and so.dt == sr.dt, step
+    for f in ("surf", "surfzone", "b"):
+        assert np.array_equal(o.get(f), r.get(f)), f
+    for f, tol in (("xi", 1e-14), ("rho", 1e-14), ("v", 1e-12), ("p", 1e-11), ("acc", 1e-11), ("Rrho", 1e-11)):
+        assert relerr(o.get(f), r.get(f)) <= tol, (f, relerr(o.get(f), r.get(f)))

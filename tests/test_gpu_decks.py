@@ -49,3 +49,22 @@ def test_jet_deck_inlet_and_pipe():
         assert relerr(got["v"], o.get("v")) <= 1e-4, ctx
         n_add += se.n_add
     assert n_add > 0  # the run did insert particles at the inlet
+
+
+def test_arch_deck_steps():
+    """Water resting in a trough of Arch blocks (arc.cpp in 3D: a Pressure-Gradient trough with straights, a Ghost vault
+    in HCP order on a tilted plane, a stub of straights), particles culled where the blocks intersect: four steps, every
+    one running its 20 sub-iterations out.  The oracle follows FJSPH's compiled sources on this deck to 1e-13
+    (tests/test_frontend_vs_reference.py); measured here: x 1e-15, v 3e-11, rates 4e-11 (profiles/r24_arch_probe.txt)."""
+    case = frontend.read_case(os.path.join(DECKS, "arch3d.para"), 3)
+    assert [b["name"] for b in case["blocks"]] == ["Trough", "Vault", "Stub", "Water"]
+    o, e = make_pair_from_deck(case)
+    for step in range(4):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert se.iterations == so.iterations and abs(se.dt - so.dt) <= 1e-12 * so.dt, step
+        assert se.total_points == so.total_points
+    assert_fields_close(e, o, ("surf", "surfzone", "b", "part_id"), context="arch deck")
+    assert_fields_close(e, o, ("xi", "rho", "p"), tol=1e-10, context="arch deck")
+    assert_fields_close(e, o, ("v",), tol=1e-8, context="arch deck")
+    assert_fields_close(e, o, ("acc", "Rrho"), tol=1e-6, context="arch deck")
