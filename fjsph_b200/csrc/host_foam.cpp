@@ -1,8 +1,9 @@
 // host_foam.cpp — OpenFOAM case ingestion for the aero-mesh containment lookup.
 //
-// Restates FOAM::Read_FOAM for ASCII cases (library free), feeding fjsph_upload_mesh:
+// Restates FOAM::Read_FOAM for ASCII and binary cases (library free), feeding fjsph_upload_mesh:
 //   Read_Header / Read_Preamble / Read_Patch / Read_Boundary   reference src/FOAMIO.cpp:346-536
 //   ascii::Read_{Label,Scalar,Vector,Face}_Data                reference src/FOAMIO.cpp:21-112
+//   binary::Read_{Label,Scalar,Vector,Face}_Data               reference src/FOAMIO.cpp:113-342
 //   Read_Points / Read_Faces / Read_Label_Field                reference src/FOAMIO.cpp:685-865
 //   Read_polyMesh / Post_Process                               reference src/FOAMIO.cpp:538-683,867-903
 //   Read_Solution                                              reference src/FOAMIO.cpp:905-941
@@ -13,9 +14,14 @@
 // tail still count.  It is only the seed of the k-nearest-centre search, so it is kept bit for bit.
 // Deviations, each where the reference is undefined: cells.cRho is never filled by the reference although FindCell reads
 // it (Q8) -> filled with the rho_fill argument; the cell count is taken from the owner AND the neighbour file (the
-// reference keeps only the neighbour file's maximum, which is 0 for a one-cell mesh); binary cases are rejected.
+// reference keeps only the neighbour file's maximum, which is 0 for a one-cell mesh).
+// Binary files: each file's own header says whether it is binary and how wide its labels and scalars are (`arch
+// "LSB;label=32;scalar=64"`; 32 / 64 when the header has no arch entry, which the reference leaves uninitialised); the raw
+// list starts one byte after the line holding its size (the opening bracket), faces are a faceCompactList (offsets, then
+// the vertex labels).  Little-endian only, like the reference, which reads the bytes as they are.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -42,8 +48,14 @@ struct FoamError
     std::string msg;
 };
 
+struct Format /* what Read_Header takes from a FoamFile dictionary */
+{
+    bool binary = false;
+    int label_bits = 32, scalar_bits = 64;
+};
+
 // FoamFile header + the element count that follows it (Read_Preamble)
-size_t preamble(std::ifstream& fin, const std::string& file, const char* exp_class, bool allow_compact = false)
+size_t preamble(std::ifstream& fin, const std::string& file, const char* exp_class, Format& fmt, const char* binary_class = nullptr)
 {
     if (!fin.is_open())
         throw FoamError{"cannot open " + file};
@@ -56,8 +68,18 @@ size_t preamble(std::ifstream& fin, const std::string& file, const char* exp_cla
     {
         if (!std::getline(fin, line))
             throw FoamError{file + ": unterminated FoamFile header"};
-        if (line.find("format") != std::string::npos && line.find("ascii") == std::string::npos)
-            throw FoamError{file + ": binary OpenFOAM files are not restated by this reader (write the case in ascii)"};
+        if (line.find("format") != std::string::npos)
+            fmt.binary = line.find("ascii") == std::string::npos;
+        if (line.find("arch") != std::string::npos)
+        {
+            const size_t p1 = line.find("label"), p2 = line.find("scalar");
+            if (p1 != std::string::npos && p1 + 8 <= line.size())
+                fmt.label_bits = std::atoi(line.substr(p1 + 6, 2).c_str());
+            if (p2 != std::string::npos && p2 + 9 <= line.size())
+                fmt.scalar_bits = std::atoi(line.substr(p2 + 7, 2).c_str());
+            if ((fmt.label_bits != 32 && fmt.label_bits != 64) || (fmt.scalar_bits != 32 && fmt.scalar_bits != 64))
+                throw FoamError{file + ": unsupported arch entry " + line};
+        }
         if (line.find("class") != std::string::npos)
         {
             std::istringstream iss(line);
@@ -67,8 +89,9 @@ size_t preamble(std::ifstream& fin, const std::string& file, const char* exp_cla
                 cls.pop_back();
         }
     }
-    if (cls != exp_class && !(allow_compact && cls == "faceCompactList"))
-        throw FoamError{"File " + file + " is class \"" + cls + "\" and should be \"" + exp_class + "\""};
+    const char* want = (fmt.binary && binary_class) ? binary_class : exp_class;
+    if (cls != want)
+        throw FoamError{"File " + file + " is class \"" + cls + "\" and should be \"" + want + "\""};
     if (!std::getline(fin, line))
         throw FoamError{file + ": no data"};
     while (line.find("//") == 0 || line.empty() || line.find("dimensions") != std::string::npos)
@@ -87,10 +110,52 @@ size_t preamble(std::ifstream& fin, const std::string& file, const char* exp_cla
     return n;
 }
 
+// the raw list of a binary file: reopened in binary mode one byte past the size line (FOAMIO.cpp:702-706)
+void reopen_binary(std::ifstream& fin, const std::string& file)
+{
+    const std::streamoff pos = fin.tellg();
+    fin.close();
+    fin.open(file, std::ifstream::binary);
+    fin.seekg(pos + 1);
+}
+template <typename Raw, typename Out>
+void read_raw(std::ifstream& fin, const std::string& file, size_t count, Out* dst)
+{
+    std::vector<Raw> buf(count);
+    fin.read(reinterpret_cast<char*>(buf.data()), std::streamsize(count * sizeof(Raw)));
+    if (size_t(fin.gcount()) != count * sizeof(Raw))
+        throw FoamError{file + ": binary list ends early"};
+    for (size_t i = 0; i < count; ++i) dst[i] = Out(buf[i]);
+}
+template <typename Out>
+void read_raw_scalars(std::ifstream& fin, const std::string& file, const Format& fmt, size_t count, Out* dst)
+{
+    if (fmt.scalar_bits == 32)
+        read_raw<float>(fin, file, count, dst);
+    else
+        read_raw<double>(fin, file, count, dst);
+}
+template <typename Out>
+void read_raw_labels(std::ifstream& fin, const std::string& file, const Format& fmt, size_t count, Out* dst)
+{
+    if (fmt.label_bits == 32)
+        read_raw<int32_t>(fin, file, count, dst);
+    else
+        read_raw<int64_t>(fin, file, count, dst);
+}
+
 void read_vectors(const std::string& file, const char* cls, std::vector<double>& out)
 {
     std::ifstream fin(file);
-    const size_t n = preamble(fin, file, cls);
+    Format fmt;
+    const size_t n = preamble(fin, file, cls, fmt);
+    if (fmt.binary)
+    {
+        reopen_binary(fin, file);
+        out.assign(3 * n, 0.0);
+        read_raw_scalars(fin, file, fmt, 3 * n, out.data());
+        return;
+    }
     std::string line;
     std::getline(fin, line); /* the opening bracket */
     out.assign(3 * n, 0.0);
@@ -107,7 +172,15 @@ void read_vectors(const std::string& file, const char* cls, std::vector<double>&
 void read_scalars(const std::string& file, std::vector<double>& out)
 {
     std::ifstream fin(file);
-    const size_t n = preamble(fin, file, "volScalarField");
+    Format fmt;
+    const size_t n = preamble(fin, file, "volScalarField", fmt);
+    if (fmt.binary)
+    {
+        reopen_binary(fin, file);
+        out.assign(n, 0.0);
+        read_raw_scalars(fin, file, fmt, n, out.data());
+        return;
+    }
     std::string line;
     std::getline(fin, line);
     out.assign(n, 0.0);
@@ -122,7 +195,18 @@ void read_scalars(const std::string& file, std::vector<double>& out)
 void read_labels(const std::string& file, std::vector<int>& out, size_t& n_cells)
 {
     std::ifstream fin(file);
-    const size_t n = preamble(fin, file, "labelList");
+    Format fmt;
+    const size_t n = preamble(fin, file, "labelList", fmt);
+    if (fmt.binary)
+    {
+        reopen_binary(fin, file);
+        out.assign(n, 0);
+        read_raw_labels(fin, file, fmt, n, out.data());
+        for (size_t i = 0; i < n; ++i)
+            if (out[i] + 1 > int(n_cells))
+                n_cells = size_t(out[i] + 1);
+        return;
+    }
     std::string line;
     std::getline(fin, line);
     out.assign(n, 0);
@@ -139,7 +223,39 @@ void read_labels(const std::string& file, std::vector<int>& out, size_t& n_cells
 void read_faces(const std::string& file, std::vector<std::vector<size_t>>& faces)
 {
     std::ifstream fin(file);
-    const size_t n = preamble(fin, file, "faceList");
+    Format fmt;
+    const size_t n = preamble(fin, file, "faceList", fmt, "faceCompactList");
+    if (fmt.binary)
+    {
+        /* faceCompactList (FOAMIO.cpp:225-340): n = faces + 1 offsets, then ")", the label count, "(" and the labels */
+        if (n == 0)
+            throw FoamError{file + ": empty offset list"};
+        reopen_binary(fin, file);
+        std::vector<int64_t> index(n);
+        read_raw_labels(fin, file, fmt, n, index.data());
+        std::string interim;
+        char ch = '0';
+        while (ch != '(')
+        {
+            if (!fin.get(ch))
+                throw FoamError{file + ": no vertex label list after the face offsets"};
+            interim.push_back(ch);
+        }
+        for (char drop : {'\n', '\r', '(', ')'}) interim.erase(std::remove(interim.begin(), interim.end(), drop), interim.end());
+        const long n_labels = std::atol(interim.c_str());
+        if (index[0] != 0 || index[n - 1] != n_labels)
+            throw FoamError{file + ": face offsets do not match the " + std::to_string(n_labels) + " vertex labels"};
+        std::vector<int64_t> labels(size_t(n_labels), 0);
+        read_raw_labels(fin, file, fmt, size_t(n_labels), labels.data());
+        faces.assign(n - 1, {});
+        for (size_t i = 0; i + 1 < n; ++i)
+        {
+            if (index[i + 1] < index[i] + 3 || index[i + 1] - index[i] > 64)
+                throw FoamError{file + ": malformed face " + std::to_string(i)};
+            for (int64_t k = index[i]; k < index[i + 1]; ++k) faces[i].push_back(size_t(labels[size_t(k)]));
+        }
+        return;
+    }
     std::string line;
     std::getline(fin, line);
     faces.assign(n, {});

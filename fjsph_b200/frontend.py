@@ -59,7 +59,7 @@ def read_case(para_path: str, dim: int = 3) -> dict:
 
 
 def read_foam(foam_dir: str, solution_dir: str | None = None, buoyant: bool = False, rho_fill: float = 1.29251) -> dict:
-    """FOAM::Read_FOAM (reference src/FOAMIO.cpp:943-953) for an ASCII OpenFOAM case: the mesh dict Engine.upload_mesh and
+    """FOAM::Read_FOAM (reference src/FOAMIO.cpp:943-953) for an OpenFOAM case (ASCII or binary): the mesh dict Engine.upload_mesh and
     Oracle.set_mesh take (verts, face_ptr/face_vtx, leftright, cell_ptr/cell_faces, cCentre, cVel, cP, cRho)."""
     L = _lib.lib()
     h = C.c_void_p()

@@ -242,7 +242,7 @@ int fjsph_slab_stats(FjsphEngine* e, int64_t* n_owned, int64_t* n_ghost, int64_t
 int fjsph_upload_owned(FjsphEngine* e, const FjsphStateView* s);
 int fjsph_set_owned(FjsphEngine* e, int64_t n_owned);
 
-/* OpenFOAM case ingestion (host only): FOAM::Read_FOAM for ASCII cases (reference src/FOAMIO.cpp:346-955) -- constant/
+/* OpenFOAM case ingestion (host only): FOAM::Read_FOAM for ASCII and binary cases (reference src/FOAMIO.cpp:21-342,346-955) -- constant/
  * polyMesh/{boundary,points,faces,owner,neighbour} and <solution_dir>/{p or p_rgh,U} -> the MESH arrays fjsph_upload_mesh
  * takes: faces fanned into triangles, boundary markers -1 (wall patches) / -2 (other patches), the reference's cell
  * centres.  The reference never fills cRho: it is set to rho_fill.  solution_dir NULL or "" = mesh only

@@ -76,9 +76,42 @@ def test_foam_errors(tmp_path):
         frontend.read_foam(tmp_path / "nowhere")
     write_case(tmp_path, LO, HI, (2, 2, 2), lambda c: (0.0, 0.0, 0.0), lambda c: 0.0)
     pts = tmp_path / "constant" / "polyMesh" / "points"
-    pts.write_text(pts.read_text().replace("ascii", "binary"))
-    with pytest.raises(_lib.FjsphError, match="binary"):
+    faces = tmp_path / "constant" / "polyMesh" / "faces"
+    text = faces.read_text()
+    faces.write_text(text.replace("ascii", "binary"))   # a binary face file is a faceCompactList (FOAMIO.cpp:826-836)
+    with pytest.raises(_lib.FjsphError, match="should be \"faceCompactList\""):
         frontend.read_foam(tmp_path, "100")
-    pts.write_text(pts.read_text().replace("binary", "ascii").replace("vectorField", "labelList"))
+    faces.write_text(text)
+    pts.write_text(pts.read_text().replace("vectorField", "labelList"))
     with pytest.raises(_lib.FjsphError, match="should be"):
         frontend.read_foam(tmp_path, "100")
+
+
+@pytest.mark.parametrize("label_bits,scalar_bits", [(32, 64), (64, 64), (32, 32), (64, 32)])
+def test_binary_case_reads_like_the_ascii_one(tmp_path, label_bits, scalar_bits):
+    """binary::Read_*_Data (FOAMIO.cpp:113-342): `format binary` files with the label and scalar widths of their own
+    `arch` entry, faces as a faceCompactList.  With 64-bit scalars the mesh arrays equal those of the same case written in
+    ASCII bit for bit; with 32-bit scalars they equal the float-rounded values."""
+    vel = lambda c: (1.0 + c[0], 2.0 * c[1], 3.0)
+    pr = lambda c: 1.0e5 + 10.0 * c[2]
+    a_dir, b_dir = tmp_path / "ascii", tmp_path / "binary"
+    a_dir.mkdir()
+    b_dir.mkdir()
+    write_case(a_dir, LO, HI, N, vel, pr, wall_patch=True)
+    nc, U, P = write_case(b_dir, LO, HI, N, vel, pr, wall_patch=True, binary=True, label_bits=label_bits, scalar_bits=scalar_bits)
+    a = frontend.read_foam(a_dir, "100", rho_fill=1.2262)
+    b = frontend.read_foam(b_dir, "100", rho_fill=1.2262)
+    for k in ("face_ptr", "face_vtx", "leftright", "cell_ptr", "cell_faces", "cRho"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(b["cVel"], U) and np.array_equal(b["cP"], P)
+    if scalar_bits == 64:
+        for k in ("verts", "cCentre", "cVel", "cP"):
+            assert np.array_equal(a[k], b[k]), k
+    else:
+        assert np.array_equal(b["verts"], a["verts"].astype(np.float32).astype(np.float64))
+        assert np.abs(b["cCentre"] - a["cCentre"]).max() < 1e-7
+    # a truncated binary file is an error, not a short mesh
+    owner = b_dir / "constant" / "polyMesh" / "owner"
+    owner.write_bytes(owner.read_bytes()[:-40])
+    with pytest.raises(_lib.FjsphError, match="binary list ends early"):
+        frontend.read_foam(b_dir, "100")

@@ -192,6 +192,18 @@ def test_openfoam_case_reads_like_the_reference(tmp_path):
     for k in ("verts", "cCentre", "cVel", "cP"):
         assert np.array_equal(mine[k], theirs[k]), k
     assert np.all(mine["cRho"] == 1.2262)
+    # the same case written in binary (binary::Read_*_Data, FOAMIO.cpp:113-342), in each width of label and scalar
+    for label_bits, scalar_bits in ((32, 64), (64, 64), (64, 32)):
+        raw = tmp_path / ("binary_%d_%d" % (label_bits, scalar_bits))
+        raw.mkdir()
+        write_case(raw, lo, hi, (5, 7, 6), vel, pr, wall_patch=True, binary=True, label_bits=label_bits, scalar_bits=scalar_bits)
+        mine_b = frontend.read_foam(raw, "100", rho_fill=1.2262)
+        ref_b = orc.Oracle(orc.default_params(3, ale=1, particle_step=1e-3), kind="ref3d")
+        theirs_b = orc.ref_read_foam(ref_b, str(raw), "100")
+        for k in ("face_ptr", "face_vtx", "leftright", "cell_ptr", "cell_faces", "verts", "cCentre", "cVel", "cP"):
+            assert np.array_equal(mine_b[k], theirs_b[k]), (label_bits, scalar_bits, k)
+        if scalar_bits == 64:
+            assert np.array_equal(mine_b["verts"], mine["verts"]) and np.array_equal(mine_b["cP"], mine["cP"])
 
 
 def test_arch_deck_steps_follow_the_reference():
