@@ -16,8 +16,11 @@
 // block's counts default to 0, not -1, so its thickness / length / spacing fallbacks never fire and the 2D generator walks
 // the block file's "i-direction count" (arc.cpp:446-495,546-554), the 3D centre + start + end form states a -90 degree arc
 // whatever the end point (arc.cpp:206-245) and so generates only its straights.
-// Not restated: JSON block files (nlohmann/json is not vendored).
+// JSON block files are read too (read_json below: the slice of nlohmann/json's behaviour shapes.cpp relies on).
 #include <algorithm>
+#include <iterator>
+#include <map>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -162,7 +165,7 @@ struct Block /* ShapeBlock, shapes.h:10-116 */
 {
     int dim = 3;
     bool write_data = false, no_slip = false, particle_order = false;
-    std::string name, shape, subshape, filename, position_filename, solver_name;
+    std::string name, shape, subshape, filename, position_filename, solver_name, inlet_bc_type;
     int bound_type = -1, sub_bound_type = -1, fixed_vel_or_dynamic = 0, bound_solver = FJSPH_PRESSURE_G;
     int ni = 0, nj = 0, nk = 0;
     size_t npts = 0, ntimes = 0;
@@ -304,6 +307,13 @@ bool common_check(Block& b, const Ctx& C, std::string& err)
         else if (b.solver_name == "Ghost")
             b.bound_solver = FJSPH_GHOST;
         /* anything else: the reference warns and keeps Pressure-Gradient */
+    }
+    if (!b.inlet_bc_type.empty()) /* only the JSON reader fills it (shapes.cpp:104-121,292); anything else keeps the default */
+    {
+        if (b.inlet_bc_type == "Fixed Velocity")
+            b.fixed_vel_or_dynamic = 0;
+        else if (b.inlet_bc_type == "Dynamic")
+            b.fixed_vel_or_dynamic = 1;
     }
     if (b.press != 0)
     {
@@ -1407,6 +1417,23 @@ void coord_check(Block& b, const Ctx& C, double& gs, std::string& err)
     post_check(b, gs);
 }
 
+void check_block(Block& b, const Ctx& C, double& gs, std::string& err)
+{
+    std::string e;
+    switch (b.bound_type)
+    {
+    case linePlane: line_check(b, C, gs, e); break;
+    case squareCube: square_check(b, C, gs, e); break;
+    case circleSphere: circle_check(b, C, gs, e); break;
+    case arcSection: arc_check(b, C, gs, e); break;
+    case cylinderT: cylinder_check(b, C, gs, e); break;
+    case inletZone: inlet_check(b, C, gs, e); break;
+    case coordDef: coord_check(b, C, gs, e); break;
+    default: e = "unsupported shape. ";
+    }
+    err += e;
+}
+
 // ---------------------------------------------------------------- block file (shapes.cpp:408-625)
 struct Shapes
 {
@@ -1536,27 +1563,383 @@ bool read_bmap(const std::string& path, const Ctx& C, double& gs, Shapes& out, s
         if (line.find("block end") != std::string::npos)
             ib++;
     }
-    for (auto& bp : out.block)
+    for (auto& bp : out.block) check_block(*bp, C, gs, err);
+    if (!err.empty())
+        return false;
+    for (auto& bp : out.block) out.total_points += bp->npts;
+    return true;
+}
+
+// ---------------------------------------------------------------- JSON block file (shapes.cpp:229-395)
+// The reference reads these with nlohmann/json; what it relies on is restated here: one object per file, its members the
+// blocks, visited in KEY ORDER (the library's object is a std::map, so blocks come sorted by name, not in file order), a
+// repeated key keeps its last value, and typed reads as strict as the library's -- a string only from a string, a bool
+// only from true / false, a number from a number or a boolean (integers and reals kept apart, converted by a cast), a
+// vector only from an array of exactly `dim` numbers -- where the reference exits on a mismatch this returns the error.
+struct JVal
+{
+    enum Kind
     {
-        Block& b = *bp;
-        std::string e;
-        switch (b.bound_type)
+        Null,
+        Bool,
+        Int,
+        Real,
+        Str,
+        Arr,
+        Obj
+    } kind = Null;
+    bool b = false;
+    long long i = 0;
+    double f = 0.0;
+    std::string s;
+    std::vector<JVal> arr;
+    std::map<std::string, JVal> obj;
+    const JVal* find(const char* key) const
+    {
+        const auto it = obj.find(key);
+        return it == obj.end() ? nullptr : &it->second;
+    }
+};
+struct JsonError
+{
+    std::string msg;
+};
+class JsonReader
+{
+  public:
+    explicit JsonReader(const std::string& text) : t(text) {}
+    JVal document()
+    {
+        JVal v = value();
+        space();
+        if (p != t.size())
+            bad("text after the document");
+        return v;
+    }
+
+  private:
+    const std::string& t;
+    size_t p = 0;
+    [[noreturn]] void bad(const char* what) const { throw JsonError{"JSON parse error at byte " + std::to_string(p) + ": " + what}; }
+    void space()
+    {
+        while (p < t.size() && std::strchr(" \t\n\r", t[p])) ++p;
+    }
+    bool take(char c)
+    {
+        space();
+        if (p < t.size() && t[p] == c)
         {
-        case linePlane: line_check(b, C, gs, e); break;
-        case squareCube: square_check(b, C, gs, e); break;
-        case circleSphere: circle_check(b, C, gs, e); break;
-        case arcSection: arc_check(b, C, gs, e); break;
-        case cylinderT: cylinder_check(b, C, gs, e); break;
-        case inletZone: inlet_check(b, C, gs, e); break;
-        case coordDef: coord_check(b, C, gs, e); break;
-        default: e = "unsupported shape. ";
+            ++p;
+            return true;
         }
-        err += e;
+        return false;
+    }
+    std::string quoted()
+    {
+        std::string out;
+        for (++p; p < t.size() && t[p] != '"'; ++p)
+        {
+            if (t[p] != '\\')
+            {
+                out.push_back(t[p]);
+                continue;
+            }
+            if (++p >= t.size())
+                break;
+            switch (t[p])
+            {
+            case 'n': out.push_back('\n'); break;
+            case 't': out.push_back('\t'); break;
+            case 'r': out.push_back('\r'); break;
+            case 'b': out.push_back('\b'); break;
+            case 'f': out.push_back('\f'); break;
+            case 'u': bad("\\u escapes are not supported");
+            default: out.push_back(t[p]);
+            }
+        }
+        if (p >= t.size())
+            bad("unterminated string");
+        ++p;
+        return out;
+    }
+    JVal number()
+    {
+        const size_t a = p;
+        bool integral = true;
+        if (t[p] == '-')
+            ++p;
+        const size_t first_digit = p;
+        while (p < t.size() && std::isdigit(static_cast<unsigned char>(t[p]))) ++p;
+        if (p == first_digit)
+            bad("invalid literal");
+        if (p < t.size() && t[p] == '.')
+        {
+            integral = false;
+            for (++p; p < t.size() && std::isdigit(static_cast<unsigned char>(t[p])); ++p) {}
+        }
+        if (p < t.size() && (t[p] == 'e' || t[p] == 'E'))
+        {
+            integral = false;
+            ++p;
+            if (p < t.size() && (t[p] == '+' || t[p] == '-'))
+                ++p;
+            while (p < t.size() && std::isdigit(static_cast<unsigned char>(t[p]))) ++p;
+        }
+        const std::string tok = t.substr(a, p - a);
+        JVal v;
+        v.kind = integral ? JVal::Int : JVal::Real;
+        if (integral)
+            v.i = std::strtoll(tok.c_str(), nullptr, 10);
+        else
+            v.f = std::strtod(tok.c_str(), nullptr);
+        return v;
+    }
+    JVal value()
+    {
+        space();
+        if (p >= t.size())
+            bad("unexpected end of input");
+        JVal v;
+        if (take('{'))
+        {
+            v.kind = JVal::Obj;
+            if (take('}'))
+                return v;
+            do
+            {
+                space();
+                if (p >= t.size() || t[p] != '"')
+                    bad("expected a member name");
+                const std::string key = quoted();
+                if (!take(':'))
+                    bad("expected ':'");
+                v.obj[key] = value();
+            } while (take(','));
+            if (!take('}'))
+                bad("expected ',' or '}'");
+            return v;
+        }
+        if (take('['))
+        {
+            v.kind = JVal::Arr;
+            if (take(']'))
+                return v;
+            do
+                v.arr.push_back(value());
+            while (take(','));
+            if (!take(']'))
+                bad("expected ',' or ']'");
+            return v;
+        }
+        if (t[p] == '"')
+        {
+            v.kind = JVal::Str;
+            v.s = quoted();
+            return v;
+        }
+        for (const char* word : {"true", "false", "null"})
+            if (t.compare(p, std::strlen(word), word) == 0)
+            {
+                p += std::strlen(word);
+                v.kind = word[0] == 'n' ? JVal::Null : JVal::Bool;
+                v.b = word[0] == 't';
+                return v;
+            }
+        return number();
+    }
+};
+
+struct JsonBlock /* typed reads of one block's members (get_var, shapes.cpp:229-282) */
+{
+    const JVal& o;
+    const std::string& file;
+    int dim;
+    [[noreturn]] void mismatch(const char* key, const char* want) const
+    {
+        throw JsonError{"An error occured trying to read a parameter from the JSON file. File: " + file + " Parameter: " + key +
+                        " Error: type must be " + want};
+    }
+    double as_real(const JVal& v, const char* key) const
+    {
+        if (v.kind == JVal::Int)
+            return static_cast<double>(v.i);
+        if (v.kind == JVal::Real)
+            return v.f;
+        if (v.kind == JVal::Bool)
+            return v.b ? 1.0 : 0.0;
+        mismatch(key, "number");
+    }
+    void get(const char* key, std::string& out) const
+    {
+        if (const JVal* v = o.find(key))
+        {
+            if (v->kind != JVal::Str)
+                mismatch(key, "string");
+            out = v->s;
+        }
+    }
+    void get(const char* key, bool& out) const
+    {
+        if (const JVal* v = o.find(key))
+        {
+            if (v->kind != JVal::Bool)
+                mismatch(key, "boolean");
+            out = v->b;
+        }
+    }
+    void get(const char* key, int& out) const
+    {
+        if (const JVal* v = o.find(key))
+            out = v->kind == JVal::Int ? static_cast<int>(v->i) : static_cast<int>(as_real(*v, key));
+    }
+    void get(const char* key, double& out) const
+    {
+        if (const JVal* v = o.find(key))
+            out = as_real(*v, key);
+    }
+    void get(const char* key, std::vector<double>& out) const
+    {
+        if (const JVal* v = o.find(key))
+        {
+            if (v->kind != JVal::Arr)
+                mismatch(key, "array");
+            out.clear();
+            for (const JVal& e : v->arr) out.push_back(as_real(e, key));
+        }
+    }
+    void get(const char* key, V3& out) const /* taken only when the array has exactly dim entries */
+    {
+        std::vector<double> tmp;
+        get(key, tmp);
+        if (int(tmp.size()) == dim)
+            for (int d = 0; d < dim; ++d) out[d] = tmp[size_t(d)];
+    }
+    void get(const char* key, std::vector<V3>& out) const /* rows are read as dim numbers each, as the reference does */
+    {
+        const JVal* v = o.find(key);
+        if (!v)
+            return;
+        if (v->kind != JVal::Arr)
+            mismatch(key, "array");
+        if (v->arr.empty())
+            return;
+        std::vector<V3> rows;
+        for (const JVal& r : v->arr)
+        {
+            if (r.kind != JVal::Arr)
+                mismatch(key, "array");
+            if (int(r.arr.size()) < dim)
+                throw JsonError{"JSON file " + file + ": a row of \"" + key + "\" has fewer than " + std::to_string(dim) + " numbers"};
+            V3 x;
+            for (int d = 0; d < dim; ++d) x[d] = as_real(r.arr[size_t(d)], key);
+            rows.push_back(x);
+        }
+        out = rows;
+    }
+};
+
+bool read_json(const std::string& path, const Ctx& C, double& gs, Shapes& out, std::string& err)
+{
+    std::ifstream fin(path);
+    if (!fin.is_open())
+    {
+        err = path + " file missing";
+        return false;
+    }
+    const std::string text((std::istreambuf_iterator<char>(fin)), std::istreambuf_iterator<char>());
+    const int dim = C.dim;
+    try
+    {
+        const JVal doc = JsonReader(text).document();
+        if (doc.kind != JVal::Obj)
+            throw JsonError{"JSON file " + path + ": the document must be an object of blocks"};
+        for (const auto& member : doc.obj) /* key order */
+        {
+            if (member.second.kind != JVal::Obj && member.second.kind != JVal::Null)
+                throw JsonError{"JSON file " + path + ": block \"" + member.first + "\" is not an object"};
+            const JsonBlock J{member.second, path, dim};
+            std::unique_ptr<Block> bp(new Block(dim));
+            Block& b = *bp;
+            std::string shape_name;
+            J.get("Shape", shape_name);
+            b.bound_type = shape_type_of(shape_name, dim);
+            if (b.bound_type < 0)
+                err += "Unrecognised boundary shape, \"" + shape_name + "\". ";
+            b.filename = path; /* shapes.cpp:379: the JSON file's own name, until "Coordinate filename" replaces it */
+            b.name = member.first;
+            J.get("Shape", b.shape);
+            J.get("Sub-shape", b.subshape);
+            J.get("Boundary solver", b.solver_name);
+            J.get("Fixed velocity or dynamic inlet BC", b.inlet_bc_type); /* "Fixed Velocity" or "Dynamic" */
+            J.get("Aerodynamic entry normal", b.aero_norm);
+            J.get("Deletion normal", b.delete_norm);
+            J.get("Insertion normal", b.insert_norm);
+            J.get("Aerodynamic entry plane constant", b.aeroconst);
+            J.get("Deletion plane constant", b.delconst);
+            J.get("Insertion plane constant", b.insconst);
+            J.get("Pipe depth", b.thickness);
+            J.get("i-direction count", b.ni);
+            J.get("j-direction count", b.nj);
+            J.get("k-direction count", b.nk);
+            J.get("Stretching factor", b.stretch);
+            J.get("Normal vector", b.normal);
+            J.get("Rotation angles (degree)", b.angles);
+            J.get("Rotation angle (degree)", b.angles[0]);
+            J.get("Start coordinates", b.start);
+            J.get("End coordinates", b.end);
+            J.get("Right coordinates", b.right);
+            J.get("Midpoint coordinates", b.mid);
+            J.get("Centre coordinates", b.centre);
+            J.get("Arch normal", b.right);
+            J.get("Radius", b.radius);
+            J.get("Length", b.length);
+            J.get("Arc start (degree)", b.arc_start);
+            J.get("Arc end (degree)", b.arc_end);
+            J.get("Arc length (degree)", b.arclength);
+            J.get("Start straight length", b.sstraight);
+            J.get("End straight length", b.estraight);
+            J.get("Particle spacing", b.dx);
+            J.get("Particle ordering (Grid/HCP)", b.particle_order);
+            J.get("Wall thickness", b.thickness);
+            J.get("Wall radial particle count", b.nk);
+            J.get("Wall is no-slip", b.no_slip);
+            J.get("Start velocity", b.vel);
+            J.get("Start jet velocity", b.vmag);
+            J.get("Start pressure", b.press);
+            J.get("Start density", b.dens);
+            J.get("Cole EOS gamma", b.gamma);
+            J.get("Speed of sound", b.speedOfSound);
+            J.get("Rest density", b.rho_rest);
+            J.get("Volume to target", b.renorm_vol);
+            J.get("Coordinate filename", b.filename);
+            J.get("Coordinate data", b.coords);
+            J.get("Time data filename", b.position_filename);
+            J.get("Time data", b.times);
+            J.get("Position data", b.pos);
+            if (b.bound_type >= 0)
+                check_block(b, C, gs, err); /* each block is checked as it is read (shapes.cpp:354) */
+            out.block.push_back(std::move(bp));
+        }
+    }
+    catch (const JsonError& e)
+    {
+        err = e.msg;
+        return false;
     }
     if (!err.empty())
         return false;
     for (auto& bp : out.block) out.total_points += bp->npts;
     return true;
+}
+
+// read_shapes_JSON for a file whose extension is ".json" in any case, read_shapes_bmap otherwise (Init.cpp:276-287)
+bool read_blocks(const std::string& path, const Ctx& C, double& gs, Shapes& out, std::string& err)
+{
+    const size_t dot = path.find_last_of("./");
+    std::string ext = (dot != std::string::npos && path[dot] == '.') ? path.substr(dot) : std::string();
+    for (char& c : ext) c = char(std::tolower(static_cast<unsigned char>(c)));
+    return ext == ".json" ? read_json(path, C, gs, out, err) : read_bmap(path, C, gs, out, err);
 }
 
 void generate_points(Shapes& S, double gs, const Ctx& C)
@@ -1565,6 +1948,8 @@ void generate_points(Shapes& S, double gs, const Ctx& C)
     for (auto& bp : S.block)
     {
         Block& b = *bp;
+        if (b.bound_type != coordDef)
+            b.coords.clear(); /* every generator assigns its points: coordinate data given to another shape is dropped */
         switch (b.bound_type)
         {
         case linePlane: line_generate(b, gs); break;
@@ -2021,7 +2406,7 @@ extern "C" int fjsph_case_read(const char* para_path, int dim, FjsphCase** out)
         fj_set_error("Input boundary definition filename is not set in \"%s\"", para_path);
         return FJSPH_ERR_IO;
     }
-    if (!read_bmap(resolve(bound_file, pdir), C, gs, bound, err))
+    if (!read_blocks(resolve(bound_file, pdir), C, gs, bound, err))
     {
         fj_set_error("boundary blocks: %s", err.c_str());
         return FJSPH_ERR_IO;
@@ -2031,7 +2416,7 @@ extern "C" int fjsph_case_read(const char* para_path, int dim, FjsphCase** out)
         fj_set_error("Input fluid definition filename is not set in \"%s\"", para_path);
         return FJSPH_ERR_IO;
     }
-    if (!read_bmap(resolve(fluid_file, pdir), C, gs, fluid, err))
+    if (!read_blocks(resolve(fluid_file, pdir), C, gs, fluid, err))
     {
         fj_set_error("fluid blocks: %s", err.c_str());
         return FJSPH_ERR_IO;

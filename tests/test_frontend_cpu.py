@@ -301,3 +301,48 @@ def test_arch_errors_are_reported(tmp_path):
         frontend.read_case(para_for(1, head + " Centre coordinate: 0,0,2\n Start coordinate: 1,0,2\n End coordinate: 0,2,2\n block end\n"), 3)
     with pytest.raises(_lib.FjsphError, match="not been sufficiently defined"):
         frontend.read_case(para_for(2, head + " Centre coordinate: 0,0,2\n Radius: 1\n block end\n"), 3)
+
+
+def test_json_block_files(tmp_path):
+    """read_shapes_JSON (shapes.cpp:229-395): block files with a .json extension (any case).  The same blocks give the
+    same particles as their bmap form; blocks come in the order of their names (the reference's JSON object is a
+    std::map), a repeated key keeps its last value, a vector is taken only from an array of exactly `dim` numbers, and
+    typed reads are as strict as nlohmann/json's -- where the reference exits, the product returns the diagnosis."""
+    a = frontend.read_case(deck("jet3d.para"), 3)
+    b = frontend.read_case(deck("jet3d_json.para"), 3)
+    for f in ("xi", "v", "rho", "p", "m", "b", "part_id"):
+        assert np.array_equal(a[f], b[f]), f
+    for A, B in zip(a["blocks"], b["blocks"]):
+        for k in ("name", "first", "second", "is_fluid", "bound_solver", "block_type", "fixed_vel_or_dynamic", "insconst", "aeroconst"):
+            assert A[k] == B[k], k
+    c = frontend.read_case(deck("tank2d_json.para"), 2)
+    assert [B["name"] for B in c["blocks"]] == ["Bottom", "Bowl", "Left", "Right", "Drop", "Water"]   # sorted, not file order
+    bottom, left = c["blocks"][0], c["blocks"][2]
+    # the repeated "Start coordinates" of Bottom: the last one counts (and a 3-entry array in a 2D deck is ignored)
+    x = c["xi"][bottom["first"]:bottom["second"]]
+    assert abs(x[:, 0].min() + 0.05) < 1e-12 and x.shape[0] == 4 * 81
+    assert left["no_slip"] == 1 and left["bound_solver"] == 0   # "Wall is no-slip": true, "Boundary solver": "DBC"
+    water = c["blocks"][5]
+    assert water["second"] - water["first"] == 40 * 20
+
+    def para_for(i, fluid_json):
+        f = write(tmp_path, "f%d.json" % i, fluid_json)
+        none = write(tmp_path, "none%d.bmap" % i, NO_WALLS)
+        return write(tmp_path, "para%d" % i, " Input boundary definition filename: %s\n Input fluid definition filename: %s\n"
+                     " SPH initial spacing: 0.1\n SPH aerodynamic case: (none)\n SPH frame time interval: 1\n" % (none, f))
+
+    ok = '{"W": {"Shape": "Square", "Start coordinates": [0, 0], "End coordinates": [0.4, 0.4]%s}}'
+    assert frontend.read_case(para_for(0, ok % ""), 2)["xi"].shape[0] == 16
+    # a dynamic inlet is named, not numbered, in JSON (shapes.cpp:104-121)
+    inlet = ('{"In": {"Shape": "Inlet", "Sub-shape": "Square", "Fixed velocity or dynamic inlet BC": "Dynamic", "Start jet velocity": 1.0,'
+             ' "Start coordinates": [0, 0], "End coordinates": [0, 0.4], "Length": 0.3, "Insertion plane constant": -0.3}}')
+    blk = frontend.read_case(para_for(1, inlet), 2)["blocks"][0]
+    assert blk["fixed_vel_or_dynamic"] == 1
+    with pytest.raises(_lib.FjsphError, match="Parameter: Radius Error: type must be number"):
+        frontend.read_case(para_for(2, ok % ', "Radius": "wide"'), 2)
+    with pytest.raises(_lib.FjsphError, match="Parameter: Wall is no-slip Error: type must be boolean"):
+        frontend.read_case(para_for(3, ok % ', "Wall is no-slip": 1'), 2)
+    with pytest.raises(_lib.FjsphError, match="JSON parse error"):
+        frontend.read_case(para_for(4, '{"W": {"Shape": "Square", }}'), 2)
+    with pytest.raises(_lib.FjsphError, match="Unrecognised boundary shape"):
+        frontend.read_case(para_for(5, '{"W": {"Shape": "Blob"}}'), 2)

@@ -39,6 +39,8 @@ DECKS = [
     ("dam2d", os.path.join(HERE, "decks", "dam2d.para"), 2),          # walls + hydrostatic initialisation
     ("arc2d", os.path.join(HERE, "decks", "arc2d.para"), 2),          # Arc walls: every way arc.cpp takes of stating an arc
     ("arch3d", os.path.join(HERE, "decks", "arch3d.para"), 3),        # Arch walls: straights, HCP, a tilted plane
+    ("jet3d_json", os.path.join(HERE, "decks", "jet3d_json.para"), 3),   # the jet deck with JSON block files
+    ("tank2d_json", os.path.join(HERE, "decks", "tank2d_json.para"), 2),  # JSON: blocks in key order, typed reads, a repeated key
     ("Dam_2D", EXAMPLES + "/Dam_2D/para", 2),
     ("Standing_Column", EXAMPLES + "/Standing_Column/para", 2),
     ("Poiseuille", EXAMPLES + "/Poiseuille/para", 2),
@@ -72,7 +74,7 @@ def test_deck_gives_the_reference_particles(name, para, dim):
     assert mine["xi"].shape[0] == ref.n and mine["bound_points"] == int(ref.lib.orc_bound_points(ref.h))
     # particles: a rotated block differs by the rounding of its rotation matrix (Eigen composes AngleAxis objects as
     # quaternions, the stand-in as matrices): 1 ulp of the block's extent; everything else is bit for bit
-    rotated = name in ("jet3d", "Crossflow_3D")
+    rotated = name in ("jet3d", "jet3d_json", "Crossflow_3D")
     for f in ("xi", "v"):
         assert close(mine[f], ref.get(f), 1e-15 if rotated else 0.0), (name, f)
     for f in ("rho", "p", "m"):
