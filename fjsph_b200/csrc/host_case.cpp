@@ -18,6 +18,7 @@
 // whatever the end point (arc.cpp:206-245) and so generates only its straights.
 // JSON block files are read too (read_json below: the slice of nlohmann/json's behaviour shapes.cpp relies on).
 #include <algorithm>
+#include <exception>
 #include <iterator>
 #include <map>
 #include <cctype>
@@ -2330,7 +2331,21 @@ std::string resolve(const std::string& name, const std::string& para_dir)
 } // namespace
 
 // GetInput (IO.cpp:305-723) for the keys the path reads + Init_Particles.  dim = the SIMDIM of the build the deck is for.
+static int case_read_impl(const char* para_path, int dim, FjsphCase** out);
+// nothing thrown inside (a block file asking for more memory than there is, say) crosses the C boundary
 extern "C" int fjsph_case_read(const char* para_path, int dim, FjsphCase** out)
+{
+    try
+    {
+        return case_read_impl(para_path, dim, out);
+    }
+    catch (const std::exception& e)
+    {
+        fj_set_error("case_read: %s", e.what());
+        return FJSPH_ERR_IO;
+    }
+}
+static int case_read_impl(const char* para_path, int dim, FjsphCase** out)
 {
     if (!para_path || !out || (dim != 2 && dim != 3))
     {

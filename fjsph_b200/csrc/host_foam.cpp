@@ -20,6 +20,7 @@
 // list starts one byte after the line holding its size (the opening bracket), faces are a faceCompactList (offsets, then
 // the vertex labels).  Little-endian only, like the reference, which reads the bytes as they are.
 #include <algorithm>
+#include <exception>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -427,6 +428,11 @@ extern "C" int fjsph_foam_read(const char* foam_dir, const char* solution_dir, i
     catch (const FoamError& e)
     {
         fj_set_error("foam_read: %s", e.msg.c_str());
+        return FJSPH_ERR_IO;
+    }
+    catch (const std::exception& e) /* e.g. a damaged binary header asking for more memory than there is */
+    {
+        fj_set_error("foam_read: %s", e.what());
         return FJSPH_ERR_IO;
     }
 }

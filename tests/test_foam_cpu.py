@@ -115,3 +115,14 @@ def test_binary_case_reads_like_the_ascii_one(tmp_path, label_bits, scalar_bits)
     owner.write_bytes(owner.read_bytes()[:-40])
     with pytest.raises(_lib.FjsphError, match="binary list ends early"):
         frontend.read_foam(b_dir, "100")
+
+
+def test_damaged_binary_size_is_an_error(tmp_path):
+    """A binary points file claiming 10^15 points: the reader reports it (allocation failure or short list), the process
+    lives -- nothing thrown inside the library crosses the C boundary."""
+    write_case(tmp_path, LO, HI, (2, 2, 2), lambda c: (0.0, 0.0, 0.0), lambda c: 0.0, binary=True)
+    pts = tmp_path / "constant" / "polyMesh" / "points"
+    raw = pts.read_bytes()
+    pts.write_bytes(raw.replace(b"\n27\n(", b"\n1000000000000000\n(", 1))
+    with pytest.raises(_lib.FjsphError, match="foam_read"):
+        frontend.read_foam(tmp_path, "100")
