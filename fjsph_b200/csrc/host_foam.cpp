@@ -34,13 +34,7 @@
 
 void fj_set_error(const char* fmt, ...);
 
-struct FjsphFoamMesh
-{
-    std::vector<double> verts, cCentre, cVel, cP, cRho;
-    std::vector<int64_t> face_ptr, face_vtx, cell_ptr, cell_faces;
-    std::vector<int32_t> leftright;
-    int64_t n_quads_split = 0;
-};
+#include "host_mesh.h"
 
 namespace
 {

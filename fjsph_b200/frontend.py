@@ -58,6 +58,17 @@ def read_case(para_path: str, dim: int = 3) -> dict:
         L.fjsph_case_free(h)
 
 
+def read_tau(mesh_file: str, solution_file: str | None = None, scale: float = 1.0) -> dict:
+    """TAU::Read_tau_mesh_FACE + TAU::Read_SOLUTION (reference src/CDFIO.cpp:1228-1356,655-822) on NetCDF-3 classic files, read
+    without the NetCDF library: the mesh dict Engine.upload_mesh and Oracle.set_mesh take."""
+    L = _lib.lib()
+    h = C.c_void_p()
+    L.fjsph_tau_read.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.POINTER(C.c_void_p)]
+    check(L.fjsph_tau_read(str(mesh_file).encode(), None if not solution_file else str(solution_file).encode(), float(scale),
+                           C.byref(h)))
+    return _mesh_dict(L, h)
+
+
 def read_foam(foam_dir: str, solution_dir: str | None = None, buoyant: bool = False, rho_fill: float = 1.29251) -> dict:
     """FOAM::Read_FOAM (reference src/FOAMIO.cpp:943-953) for an OpenFOAM case (ASCII or binary): the mesh dict Engine.upload_mesh and
     Oracle.set_mesh take (verts, face_ptr/face_vtx, leftright, cell_ptr/cell_faces, cCentre, cVel, cP, cRho)."""
@@ -65,6 +76,11 @@ def read_foam(foam_dir: str, solution_dir: str | None = None, buoyant: bool = Fa
     h = C.c_void_p()
     check(L.fjsph_foam_read(str(foam_dir).encode(), None if not solution_dir else str(solution_dir).encode(),
                             int(bool(buoyant)), float(rho_fill), C.byref(h)))
+    return _mesh_dict(L, h)
+
+
+def _mesh_dict(L, h) -> dict:
+    """The arrays of a mesh handle (fjsph_foam_view), copied out; frees the handle."""
     try:
         m = FjsphMesh()
         check(L.fjsph_foam_view(h, C.byref(m)))

@@ -249,6 +249,12 @@ int fjsph_set_owned(FjsphEngine* e, int64_t n_owned);
  * (zero velocity and pressure).  The view's pointers live as long as the FjsphFoamMesh. */
 typedef struct FjsphFoamMesh FjsphFoamMesh;
 int fjsph_foam_read(const char* foam_dir, const char* solution_dir, int buoyant, double rho_fill, FjsphFoamMesh** out);
+/* TAU case ingestion (host only, no NetCDF library): TAU::Read_tau_mesh_FACE + TAU::Read_SOLUTION (reference src/CDFIO.cpp:
+ * 1228-1356, 655-822; FJSPH.cpp:76-78) on the face-based mesh file FJSPH's Cell2Face writes and a TAU solution file, both
+ * NetCDF-3 classic (CDF-1 / CDF-2).  Faces = triangles then quadrilaterals (kept four-cornered), right cell < 0 = the file's
+ * boundary marker, cell values = Kahan-summed means of the point data over the cell's vertices; coordinates times `scale`
+ * ("Grid scale").  solution_file NULL or "" = mesh only.  Same handle type as fjsph_foam_read (view / free below). */
+int fjsph_tau_read(const char* mesh_file, const char* solution_file, double scale, FjsphFoamMesh** out);
 int fjsph_foam_view(const FjsphFoamMesh* m, FjsphMesh* view);
 void fjsph_foam_free(FjsphFoamMesh* m);
 

@@ -416,6 +416,13 @@ def ref_read_foam(o: "Oracle", foam_dir: str, foam_sol: str, buoyant: bool = Fal
     return ref_mesh(o)
 
 
+def ref_read_tau(o: "Oracle", mesh_file: str, sol_file: str, scale: float = 1.0) -> dict:
+    """TAU::Read_tau_mesh_FACE + TAU::Read_SOLUTION (CDFIO.cpp:1228-1356,655-822) on NetCDF-3 classic files; returns the mesh."""
+    o.lib.orc_ref_read_tau.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double]
+    o.lib.orc_ref_read_tau(o.h, os.fsencode(mesh_file), os.fsencode(sol_file), float(scale))
+    return ref_mesh(o)
+
+
 def qr_inverse(a: np.ndarray):
     a = np.ascontiguousarray(a, dtype=np.float64)
     d = a.shape[0]

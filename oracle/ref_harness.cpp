@@ -38,6 +38,7 @@
 #include "Runge_Kutta.h"
 #include "Shifting.h"
 #include "BinaryIO.h"
+#include "CDFIO.h"
 #include "FOAMIO.h"
 #include "H5IO.h"
 #include "IO.h"
@@ -595,6 +596,29 @@ int orc_ref_read_foam(Orc* o, const char* foam_dir, const char* foam_sol, int bu
     o->cell_tree = nullptr;
     o->cells = MESH();
     FOAM::Read_FOAM(o->svar, o->cells);
+    o->cell_tree = new Vec_Tree(SIMDIM, o->cells.cCentre, 10);
+    o->cell_tree->index->buildIndex();
+    return 0;
+}
+#endif
+#if SIMDIM == 3
+/* TAU::Read_tau_mesh_FACE + TAU::Read_SOLUTION (CDFIO.cpp:1228-1356,655-822; FJSPH.cpp:76-78) on a face-based NetCDF mesh
+ * and a solution file, through the stand-in netcdf.h of shim/; the mesh goes into the handle */
+int orc_ref_read_tau(Orc* o, const char* mesh_file, const char* sol_file, double scale)
+{
+    o->svar.io.tau_mesh = mesh_file;
+    o->svar.io.tau_sol = sol_file;
+    o->svar.scale = scale;
+    o->svar.io.mesh_source = TAU_CDF;
+    o->svar.Asource = meshInfl;
+    delete o->cell_tree;
+    o->cell_tree = nullptr;
+    o->cells = MESH();
+    o->cells.maxlength = 0.0;
+    o->cells.minlength = 1e300;
+    TAU::Read_tau_mesh_FACE(o->svar, o->cells);
+    vector<uint> empty;
+    TAU::Read_SOLUTION(o->svar, o->svar.io.offset_axis, o->cells, empty);
     o->cell_tree = new Vec_Tree(SIMDIM, o->cells.cCentre, 10);
     o->cell_tree->index->buildIndex();
     return 0;

@@ -239,3 +239,23 @@ def test_arch_deck_steps_follow_the_reference():
         assert np.array_equal(o.get(f), r.get(f)), f
     for f, tol in (("xi", 1e-14), ("rho", 1e-14), ("v", 1e-12), ("p", 1e-11), ("acc", 1e-11), ("Rrho", 1e-11)):
         assert relerr(o.get(f), r.get(f)) <= tol, (f, relerr(o.get(f), r.get(f)))
+
+
+@pytest.mark.parametrize("version,scale,float_solution", [(1, 1.0, False), (2, 0.5, False), (2, 1.0, True)])
+def test_tau_files_read_like_the_reference(tmp_path, version, scale, float_solution):
+    """TAU::Read_tau_mesh_FACE + TAU::Read_SOLUTION (CDFIO.cpp:1228-1356,655-822), compiled unmodified against the stand-in
+    netcdf.h of oracle/shim, and csrc/host_tau.cpp on the same NetCDF-3 classic files (CDF-1 and CDF-2, double and float
+    point data, a grid scale): vertices, faces (triangles then quadrilaterals), left / right cells, the cells' face lists
+    and the Kahan-summed cell centres, velocities, pressures and densities, all bit for bit."""
+    from tests.tau_case import write_tau
+
+    lo, hi = np.array([-0.1013, -0.1007, -0.1011]), np.array([0.1009, 0.1003, 0.1017])
+    vel = lambda x: (1.0 + x[0], 2.0 * x[1] + 0.1 * x[2], 3.0 - x[0] * x[1])
+    mesh, sol, *_ = write_tau(tmp_path, lo, hi, (5, 7, 6), vel, lambda x: 1.0e5 + 10.0 * x[2] + x[0], lambda x: 1.2 + 0.3 * x[1],
+                              version=version, float_solution=float_solution)
+    mine = frontend.read_tau(mesh, sol, scale=scale)
+    ref = orc.Oracle(orc.default_params(3, ale=1, particle_step=1e-3), kind="ref3d")
+    theirs = orc.ref_read_tau(ref, mesh, sol, scale)
+    for k in ("face_ptr", "face_vtx", "leftright", "cell_ptr", "cell_faces", "verts", "cCentre", "cVel", "cP", "cRho"):
+        assert np.array_equal(mine[k], theirs[k]), k
+    assert np.abs(mine["cVel"]).max() > 1.0 and mine["cP"].min() > 9.0e4

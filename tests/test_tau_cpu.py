@@ -1,0 +1,89 @@
+"""TAU ingestion without the NetCDF library (csrc/host_tau.cpp = TAU::Read_tau_mesh_FACE + TAU::Read_SOLUTION, reference
+src/CDFIO.cpp:1228-1356,655-822): a small box written here as a face-based TAU mesh + solution (NetCDF-3 classic, scipy)
+is read back into the MESH arrays; the containment lookup of the CPU oracle on it gives the analytic cells.  Host-only
+code: no GPU needed.  The same files through the reference's own CDFIO.cpp: tests/test_frontend_vs_reference.py."""
+import numpy as np
+import pytest
+
+from fjsph_b200 import _lib, cases, frontend
+from oracle import oracle as orc
+
+from tests.tau_case import write_tau
+
+LO, HI, N = np.array([-0.1013, -0.1007, -0.1011]), np.array([0.1009, 0.1003, 0.1017]), (6, 7, 5)
+VEL = lambda x: (1.0 + x[0], 2.0 * x[1] + 0.1 * x[2], 3.0 - x[0])
+PR = lambda x: 1.0e5 + 10.0 * x[2] + x[0]
+RHO = lambda x: 1.2 + 0.3 * x[1]
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_face_based_mesh_round_trip(tmp_path, version):
+    mesh, sol, pts, faces, left, right = write_tau(tmp_path, LO, HI, N, VEL, PR, RHO, version=version)
+    m = frontend.read_tau(mesh, sol, scale=0.5)
+    nx, ny, nz = N
+    nc = nx * ny * nz
+    assert np.array_equal(m["verts"], pts * 0.5)                              # "Grid scale" applied to the coordinates
+    n_tri = 2 * (nx + 1) * ny * nz
+    assert np.array_equal(np.diff(m["face_ptr"]), [3] * n_tri + [4] * (len(faces) - n_tri))   # triangles, then 4-gons kept
+    assert np.array_equal(m["face_vtx"], np.concatenate([np.asarray(f) for f in faces]))
+    assert np.array_equal(m["leftright"][:, 0], left) and np.array_equal(m["leftright"][:, 1], right)
+    assert (m["leftright"][:, 1] == -1).sum() == nx * ny                      # the file's markers are kept as written
+    assert np.array_equal(np.diff(m["cell_ptr"]), np.full(nc, 8))             # 4 triangles + 4 quadrilaterals per cell
+    for c in (0, nc // 2, nc - 1):                                            # a cell's faces come in face order
+        fl = m["cell_faces"][m["cell_ptr"][c]: m["cell_ptr"][c + 1]]
+        assert np.array_equal(fl, np.sort(fl)) and all(left[f] == c or right[f] == c for f in fl)
+    # cell values: means over the cell's 8 distinct vertices -- exact for linear fields: the value at the cell centre
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cid = ((k * ny + j) * nx + i).ravel()
+    centre = np.empty((nc, 3))
+    centre[cid] = np.stack([LO[d] + (np.stack([i, j, k])[d].ravel() + 0.5) * (HI[d] - LO[d]) / N[d] for d in range(3)], axis=1)
+    assert np.allclose(m["cCentre"], 0.5 * centre, rtol=0, atol=1e-15)
+    assert np.allclose(m["cVel"], np.array([VEL(x) for x in centre]), rtol=1e-14)
+    assert np.allclose(m["cP"], [PR(x) for x in centre], rtol=1e-14) and np.allclose(m["cRho"], [RHO(x) for x in centre], rtol=1e-14)
+    # a mesh without a solution carries zeros
+    bare = frontend.read_tau(mesh)
+    assert np.all(bare["cVel"] == 0) and np.all(bare["cP"] == 0) and np.array_equal(bare["verts"], pts)
+
+
+def test_containment_on_a_tau_mesh(tmp_path):
+    """FindCell on the oracle with the TAU-read mesh (quadrilateral faces tested the reference's way): every
+    FREE particle lands in its analytic cell, and the cell data reach the particles."""
+    mesh, sol, *_ = write_tau(tmp_path, LO, HI, N, lambda x: (0.0, 21.55, 0.0), lambda x: 100000.0, lambda x: 1.1025)
+    tau = frontend.read_tau(mesh, sol)
+    case = cases.droplet(dx=0.0125, jitter=0.05)
+    o = orc.Oracle(orc.default_params(3, asource=1, **dict(case["params"], lam_cutoff=1e9)))
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+    o.set_mesh(tau)
+    o.update_neighbours()
+    o.prestep()
+    o.aero_velocity()
+    ijk = np.floor((case["xi"] - LO) / ((HI - LO) / np.array(N))).astype(int)
+    assert np.array_equal(o.get("cellID"), (ijk[:, 2] * N[1] + ijk[:, 1]) * N[0] + ijk[:, 0])
+    assert np.allclose(o.get("cellV"), (0.0, 21.55, 0.0), rtol=1e-14)
+
+
+def test_tau_errors(tmp_path):
+    with pytest.raises(_lib.FjsphError, match="cannot open"):
+        frontend.read_tau(tmp_path / "nowhere.grid")
+    mesh, sol, *_ = write_tau(tmp_path, LO, HI, (2, 2, 2), VEL, PR, RHO)
+    hdf = tmp_path / "new.grid"
+    hdf.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(_lib.FjsphError, match="NetCDF-4"):
+        frontend.read_tau(hdf)
+    junk = tmp_path / "junk.grid"
+    junk.write_bytes(b"not a grid at all")
+    with pytest.raises(_lib.FjsphError, match="not a NetCDF-3 classic file"):
+        frontend.read_tau(junk)
+    with pytest.raises(_lib.FjsphError, match='no dimension "no_of_elements"'):
+        frontend.read_tau(sol)                                       # a solution file is not a mesh
+    with pytest.raises(_lib.FjsphError, match='no variable "density"'):
+        frontend.read_tau(mesh, mesh)
+    cut = tmp_path / "cut.grid"
+    cut.write_bytes(open(mesh, "rb").read()[:-200])
+    with pytest.raises(_lib.FjsphError, match="past the end of the file"):
+        frontend.read_tau(cut)
+    other = tmp_path / "other"
+    other.mkdir()
+    _, sol2, *_ = write_tau(other, LO, HI, (3, 2, 2), VEL, PR, RHO)
+    with pytest.raises(_lib.FjsphError, match="same number of vertices"):
+        frontend.read_tau(mesh, sol2)
