@@ -149,6 +149,19 @@ int main(int argc, char** argv)
             std::printf("OpenFOAM mesh: %lld cells, %lld triangles\n", (long long)view.n_cells, (long long)view.n_faces);
             fjsph_foam_free(fm);
         }
+        /* ... or the TAU mesh and solution (FJSPH.cpp:72-79: Read_BMAP is part of fjsph_case_read) */
+        char tmesh[1024] = "", tsol[1024] = "";
+        double tscale = 1.0;
+        fjsph_case_tau(c, tmesh, tsol, &tscale, 1024);
+        if (tmesh[0])
+        {
+            FjsphFoamMesh* fm = nullptr;
+            FjsphMesh view;
+            if (fjsph_tau_read(tmesh, tsol, tscale, &fm) || fjsph_foam_view(fm, &view) || fjsph_upload_mesh(e, &view))
+                return fail("reading the TAU mesh");
+            std::printf("TAU mesh: %lld cells, %lld faces\n", (long long)view.n_cells, (long long)view.n_faces);
+            fjsph_foam_free(fm);
+        }
     }
     fjsph_get_params(e, &P);
     std::printf("Starting counts:\nBoundary: %lld  Sim: %lld\n\n", (long long)nb0, (long long)(fjsph_count(e) - nb0));

@@ -2107,7 +2107,8 @@ struct FjsphCase
     int max_frames = -1;            /* "SPH frame count" (IO.cpp:375) */
     long long max_points = -1;      /* "SPH maximum particle count" (IO.cpp:428) */
     std::string output_prefix, restart_prefix; /* IO.cpp:373,355 */
-    std::string foam_dir, foam_sol, tau_mesh;  /* IO.cpp:352,359-360 */
+    std::string foam_dir, foam_sol, tau_mesh, tau_bmap, tau_sol; /* IO.cpp:352-354,359-360 */
+    double scale = 1.0, angle_alpha = 0.0;     /* IO.cpp:356-357 */
     int foam_buoyant = 0;                      /* IO.cpp:364 */
     int64_t bound_points = 0;
     int n_bound_blocks = 0;
@@ -2382,14 +2383,50 @@ static int case_read_impl(const char* para_path, int dim, FjsphCase** out)
             get_string(line, "OpenFOAM solution directory", c->foam_sol);
             get_number(line, "OpenFOAM buoyant (0/1)", c->foam_buoyant);
             get_string(line, "Primary grid face filename", c->tau_mesh);
+            get_string(line, "Boundary mapping filename", c->tau_bmap);
+            get_string(line, "Restart-data prefix", c->tau_sol);
+            get_number(line, "Angle alpha (degree)", c->angle_alpha);
         }
     }
     /* aero source, IO.cpp:464-499: a mesh named in the deck couples the aero model to it (meshInfl) */
+    c->scale = scale;
     if (!c->tau_mesh.empty())
     {
-        fj_set_error("TAU NetCDF meshes (\"Primary grid face filename\") cannot be read here: NetCDF is not available; "
-                     "convert the case to OpenFOAM ascii or upload the mesh arrays with fjsph_upload_mesh");
-        return FJSPH_ERR_IO;
+        /* a TAU mesh wins over an OpenFOAM case (IO.cpp:465-533); it needs its boundary map and its solution file */
+        if (c->tau_bmap.empty())
+        {
+            fj_set_error("Input TAU bmap file not defined.");
+            return FJSPH_ERR_INVALID;
+        }
+        if (c->tau_bmap == "(thisfile)")
+            c->tau_bmap = para_path;
+        if (c->tau_sol.empty())
+        {
+            fj_set_error("Input TAU solution file not defined.");
+            return FJSPH_ERR_INVALID;
+        }
+        /* TAU::Read_BMAP (CDFIO.cpp:234-315), the part the time step sees: the map may restate the angle of attack, and
+           gravity is turned by it -- g_z cos(alpha), and g_x = -g_Y sin(alpha) as the reference writes it in 3D too */
+        std::ifstream bm(c->tau_bmap);
+        if (!bm.is_open())
+        {
+            fj_set_error("Couldn't open the boundary map file. Attempted path: %s", c->tau_bmap.c_str());
+            return FJSPH_ERR_IO;
+        }
+        std::string line;
+        while (std::getline(bm, line))
+        {
+            line = ltrim(line);
+            if (!line.empty() && line[0] == '#')
+                continue;
+            get_number(line, "Angle alpha (degree)", c->angle_alpha);
+        }
+        const double alpha = c->angle_alpha * M_PI / 180.0;
+        const double g1 = c->params.grav[1];
+        c->params.grav[dim - 1] = c->params.grav[dim - 1] * std::cos(alpha);
+        c->params.grav[0] = -g1 * std::sin(alpha);
+        c->foam_dir.clear();
+        c->params.asource = 1;
     }
     if (!c->foam_dir.empty())
     {
@@ -2465,6 +2502,20 @@ extern "C" int fjsph_case_io(const FjsphCase* c, int32_t* max_frames, int64_t* m
         std::snprintf(output_prefix, size_t(cap), "%s", c->output_prefix.c_str());
     if (restart_prefix && cap > 0)
         std::snprintf(restart_prefix, size_t(cap), "%s", c->restart_prefix.c_str());
+    return FJSPH_OK;
+}
+// the TAU mesh and solution files the deck couples to ("" when it names none) and its "Grid scale": hand them to
+// fjsph_tau_read, then fjsph_upload_mesh
+extern "C" int fjsph_case_tau(const FjsphCase* c, char* mesh_file, char* solution_file, double* scale, int32_t cap)
+{
+    if (!c)
+        return FJSPH_ERR_INVALID;
+    if (mesh_file && cap > 0)
+        std::snprintf(mesh_file, size_t(cap), "%s", c->tau_mesh.c_str());
+    if (solution_file && cap > 0)
+        std::snprintf(solution_file, size_t(cap), "%s", c->tau_sol.c_str());
+    if (scale)
+        *scale = c->scale;
     return FJSPH_OK;
 }
 // the OpenFOAM case the deck couples to ("" when it names none): hand it to fjsph_foam_read, then fjsph_upload_mesh

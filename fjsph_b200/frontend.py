@@ -51,8 +51,12 @@ def read_case(para_path: str, dim: int = 3) -> dict:
             blocks.append(blk)
         fdir, fsol, buoy = C.create_string_buffer(1024), C.create_string_buffer(1024), C.c_int32()
         check(L.fjsph_case_foam(h, fdir, fsol, C.byref(buoy), 1024))
+        tmesh, tsol, tscale = C.create_string_buffer(1024), C.create_string_buffer(1024), C.c_double(1.0)
+        L.fjsph_case_tau.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_double), C.c_int32]
+        check(L.fjsph_case_tau(h, tmesh, tsol, C.byref(tscale), 1024))
         out.update(bound_points=int(L.fjsph_case_bound_points(h)), params=params, blocks=blocks, dim=dim,
-                   foam=(fdir.value.decode(), fsol.value.decode(), int(buoy.value)))
+                   foam=(fdir.value.decode(), fsol.value.decode(), int(buoy.value)),
+                   tau=(tmesh.value.decode(), tsol.value.decode(), float(tscale.value)))
         return out
     finally:
         L.fjsph_case_free(h)

@@ -289,6 +289,10 @@ int fjsph_case_params(const FjsphCase* c, FjsphParams* out);               /* af
 /* "OpenFOAM input directory" / "OpenFOAM solution directory" / "OpenFOAM buoyant (0/1)" of the deck ("" when it names
  * no mesh; naming one sets params.asource = meshInfl, IO.cpp:464-499) */
 int fjsph_case_foam(const FjsphCase* c, char* foam_dir, char* solution_dir, int32_t* buoyant, int32_t cap);
+/* "Primary grid face filename" / "Restart-data prefix" / "Grid scale" of the deck ("" when it names no TAU mesh; naming one
+ * sets params.asource = meshInfl, needs "Boundary mapping filename" (IO.cpp:494-533), and turns gravity by the angle of
+ * attack of the para or the boundary map as TAU::Read_BMAP does, CDFIO.cpp:234-315): for fjsph_tau_read */
+int fjsph_case_tau(const FjsphCase* c, char* mesh_file, char* solution_file, double* scale, int32_t cap);
 int fjsph_case_io(const FjsphCase* c, int32_t* max_frames, int64_t* max_points, char* output_prefix, char* restart_prefix,
                   int32_t cap);
 int fjsph_case_block(const FjsphCase* c, int32_t i, FjsphBlock* out, char* name, int32_t name_cap); /* LIMITS[i]; the

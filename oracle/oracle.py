@@ -416,6 +416,15 @@ def ref_read_foam(o: "Oracle", foam_dir: str, foam_sol: str, buoyant: bool = Fal
     return ref_mesh(o)
 
 
+def ref_read_bmap(o: "Oracle", bmap_file: str, alpha_deg: float, grav) -> np.ndarray:
+    """TAU::Read_BMAP (CDFIO.cpp:234-315): gravity after the boundary map has been read."""
+    g_in = np.ascontiguousarray(grav, dtype=np.float64)
+    g_out = np.zeros_like(g_in)
+    o.lib.orc_ref_read_bmap.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_void_p, C.c_void_p]
+    o.lib.orc_ref_read_bmap(o.h, os.fsencode(bmap_file), float(alpha_deg), _ptr(g_in), _ptr(g_out))
+    return g_out
+
+
 def ref_read_tau(o: "Oracle", mesh_file: str, sol_file: str, scale: float = 1.0) -> dict:
     """TAU::Read_tau_mesh_FACE + TAU::Read_SOLUTION (CDFIO.cpp:1228-1356,655-822) on NetCDF-3 classic files; returns the mesh."""
     o.lib.orc_ref_read_tau.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double]

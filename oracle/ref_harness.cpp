@@ -601,6 +601,21 @@ int orc_ref_read_foam(Orc* o, const char* foam_dir, const char* foam_sol, int bu
     return 0;
 }
 #endif
+/* TAU::Read_BMAP (CDFIO.cpp:234-315) on a boundary map: what it does to gravity, given the para's angle of attack (degrees) */
+int orc_ref_read_bmap(Orc* o, const char* bmap_file, double alpha_deg, const double* grav_in, double* grav_out)
+{
+    SIM& s = o->svar; /* not copyable (it owns streams): run in place and put gravity and the angle back */
+    const StateVecD grav_saved = s.grav;
+    const real alpha_saved = s.io.angle_alpha;
+    s.io.tau_bmap = bmap_file;
+    s.io.angle_alpha = alpha_deg;
+    for (int d = 0; d < SIMDIM; ++d) s.grav[d] = grav_in[d];
+    TAU::Read_BMAP(s);
+    for (int d = 0; d < SIMDIM; ++d) grav_out[d] = s.grav[d];
+    s.grav = grav_saved;
+    s.io.angle_alpha = alpha_saved;
+    return 0;
+}
 #if SIMDIM == 3
 /* TAU::Read_tau_mesh_FACE + TAU::Read_SOLUTION (CDFIO.cpp:1228-1356,655-822; FJSPH.cpp:76-78) on a face-based NetCDF mesh
  * and a solution file, through the stand-in netcdf.h of shim/; the mesh goes into the handle */

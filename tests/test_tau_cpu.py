@@ -87,3 +87,41 @@ def test_tau_errors(tmp_path):
     _, sol2, *_ = write_tau(other, LO, HI, (3, 2, 2), VEL, PR, RHO)
     with pytest.raises(_lib.FjsphError, match="same number of vertices"):
         frontend.read_tau(mesh, sol2)
+
+
+def test_deck_naming_a_tau_mesh(tmp_path):
+    """A para file with "Primary grid face filename" couples the aero model to that mesh (IO.cpp:494-533): it needs the
+    boundary map and the solution file, sets the aero source to the mesh, and TAU::Read_BMAP (CDFIO.cpp:234-315) turns
+    gravity by the angle of attack -- the para's, or the boundary map's when it restates it: g_z cos(alpha), and
+    g_x = -g_Y sin(alpha), as the reference writes it."""
+    mesh, sol, *_ = write_tau(tmp_path, LO, HI, (2, 2, 2), VEL, PR, RHO)
+    (tmp_path / "f.bmap").write_text("   Name: W\n  Shape: Sphere\n Centre coordinate: 0,0,0\n Radius: 0.03\n Particle spacing: 0.01\n block end\n")
+    (tmp_path / "none.bmap").write_text("\n")
+    (tmp_path / "tau.bmap").write_text(" block begin\n   Markers: 1\n   Type: farfield\n   Angle alpha (degree): 30\n block end\n")
+
+    def para(extra):
+        p = tmp_path / "para"
+        p.write_text(" Input boundary definition filename: %s\n Input fluid definition filename: %s\n SPH initial spacing: 0.01\n"
+                     " SPH aerodynamic case: Gissler\n SPH frame time interval: 1\n SPH gravity vector: 0.5,2.0,-9.81\n Grid scale: 0.5\n"
+                     " Angle alpha (degree): 10\n" % (tmp_path / "none.bmap", tmp_path / "f.bmap") + extra)
+        return str(p)
+
+    full = " Primary grid face filename: %s\n Boundary mapping filename: %s\n Restart-data prefix: %s\n" % (mesh, tmp_path / "tau.bmap", sol)
+    c = frontend.read_case(para(full), 3)
+    assert c["tau"] == (mesh, sol, 0.5) and c["params"].asource == 1
+    a = np.deg2rad(30.0)                                             # the boundary map's angle wins over the para's
+    assert np.allclose(list(c["params"].grav), [-2.0 * np.sin(a), 2.0, -9.81 * np.cos(a)], rtol=1e-15)
+    m = frontend.read_tau(*c["tau"][:2], scale=c["tau"][2])
+    assert m["cCentre"].shape == (8, 3)
+    if orc.have_ref("ref3d"):                                        # FJSPH's own Read_BMAP on the same map, where it is built
+        ref = orc.Oracle(orc.default_params(3, ale=1, particle_step=1e-3), kind="ref3d")
+        assert np.array_equal(orc.ref_read_bmap(ref, str(tmp_path / "tau.bmap"), 10.0, [0.5, 2.0, -9.81]), list(c["params"].grav))
+        (tmp_path / "plain.bmap").write_text(" block begin\n   Markers: 1\n   Type: farfield\n block end\n")
+        c10 = frontend.read_case(para(full.replace("tau.bmap", "plain.bmap")), 3)   # no angle in the map: the para's 10 degrees
+        assert np.array_equal(orc.ref_read_bmap(ref, str(tmp_path / "plain.bmap"), 10.0, [0.5, 2.0, -9.81]), list(c10["params"].grav))
+    plain = frontend.read_case(para(""), 3)
+    assert plain["tau"][0] == "" and plain["params"].asource == 0 and list(plain["params"].grav) == [0.5, 2.0, -9.81]
+    with pytest.raises(_lib.FjsphError, match="TAU bmap file not defined"):
+        frontend.read_case(para(" Primary grid face filename: %s\n" % mesh), 3)
+    with pytest.raises(_lib.FjsphError, match="TAU solution file not defined"):
+        frontend.read_case(para(" Primary grid face filename: %s\n Boundary mapping filename: %s\n" % (mesh, tmp_path / "tau.bmap")), 3)
