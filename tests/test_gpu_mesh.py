@@ -115,3 +115,35 @@ def test_pipe_outlet_takes_its_first_cell_from_the_mesh():
         assert relerr(got["xi"], o.get("xi")) <= 1e-10 and relerr(got["v"], o.get("v")) <= 1e-8
         freed = int((got["b"] == cases.FREE).sum())
     assert freed > 0 and o.first_cell_errors == 0
+
+
+def test_tau_mesh_with_quadrilateral_faces(tmp_path):
+    """A TAU face-based mesh + solution (NetCDF-3 classic, written with scipy, read by fjsph_tau_read without the NetCDF
+    library): triangles AND four-cornered faces, which Crossings3D tests the reference's way, a sheared
+    point solution averaged to the cells.  Two coupled steps against the oracle: cells identical, state 1e-10,
+    velocity 1e-8, rates 1e-6 (measured on the box: x 1e-16, v 1e-12, Af 1e-15, profiles/r27_tau_probe.txt)."""
+    from fjsph_b200 import frontend
+    from tests.tau_case import write_tau
+
+    lo, hi = np.array([-0.1013, -0.1007, -0.1011]), np.array([0.1009, 0.1003, 0.1017])
+    mesh_file, sol_file, *_ = write_tau(tmp_path, lo, hi, (8, 9, 7), lambda x: (1.0 + 40 * x[0], 21.55 - 30 * x[2], 5 * x[1]),
+                                        lambda x: 1.0e5 + 100 * x[1], lambda x: 1.1 + x[2])
+    tau = frontend.read_tau(mesh_file, sol_file)
+    assert set(np.diff(tau["face_ptr"])) == {3, 4}
+    case = cases.droplet(dx=0.01, jitter=0.05)
+    params = dict(case["params"], delta_t_min=1e-9)
+    o = orc.Oracle(orc.default_params(3, asource=1, **params))
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+    o.set_mesh(tau)
+    e = eng.Engine(eng.default_params(3, asource=1, **params), case["xi"].shape[0])
+    e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+    e.upload_mesh(tau)
+    for step in range(2):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert se.iterations == so.iterations, step
+        got = e.download(("cellID", "xi", "v", "rho", "Af", "acc"))
+        assert np.array_equal(got["cellID"], o.get("cellID")) and (got["cellID"] >= 0).sum() > 50, step
+        for f, tol in (("xi", 1e-10), ("rho", 1e-10), ("v", 1e-8), ("Af", 1e-6), ("acc", 1e-6)):
+            ref = o.get(f)
+            assert np.abs(got[f] - ref).max() <= tol * max(np.abs(ref).max(), 1e-300), (step, f)
