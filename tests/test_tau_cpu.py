@@ -125,3 +125,18 @@ def test_deck_naming_a_tau_mesh(tmp_path):
         frontend.read_case(para(" Primary grid face filename: %s\n" % mesh), 3)
     with pytest.raises(_lib.FjsphError, match="TAU solution file not defined"):
         frontend.read_case(para(" Primary grid face filename: %s\n Boundary mapping filename: %s\n" % (mesh, tmp_path / "tau.bmap")), 3)
+
+
+def test_headers_of_the_reference_s_own_tau_files():
+    """Examples/RAE2822 ships a TAU mesh (CDF-1) and solution (CDF-2) written by TAU itself, with global and variable
+    attributes: both are NetCDF-3 classic, and the header parser walks them to the dimension it then misses (they are the
+    2D edge-based layout, which the 3D path does not take)."""
+    import os
+
+    rae = "/root/reference/Examples/RAE2822"
+    if not os.path.exists(rae + "/mesh.grid.conf.edges"):
+        pytest.skip("the reference's Examples are not mounted here")
+    with pytest.raises(_lib.FjsphError, match='mesh.grid.conf.edges: no dimension "no_of_faces"'):
+        frontend.read_tau(rae + "/mesh.grid.conf.edges")
+    with pytest.raises(_lib.FjsphError, match='sol.pval.10000: no dimension "no_of_elements"'):
+        frontend.read_tau(rae + "/sol.pval.10000")
