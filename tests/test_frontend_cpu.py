@@ -316,13 +316,14 @@ def test_json_block_files(tmp_path):
         for k in ("name", "first", "second", "is_fluid", "bound_solver", "block_type", "fixed_vel_or_dynamic", "insconst", "aeroconst"):
             assert A[k] == B[k], k
     c = frontend.read_case(deck("tank2d_json.para"), 2)
-    assert [B["name"] for B in c["blocks"]] == ["Bottom", "Bowl", "Left", "Right", "Drop", "Water"]   # sorted, not file order
-    bottom, left = c["blocks"][0], c["blocks"][2]
+    assert [B["name"] for B in c["blocks"]] == ["Bottom", "Bowl", "Left", "Pegs", "Right", "Drop", "Water"]   # sorted, not file order
+    bottom, left, pegs = c["blocks"][0], c["blocks"][2], c["blocks"][3]
+    assert np.array_equal(c["xi"][pegs["first"]:pegs["second"]], [[3.5, 1.8], [3.55, 1.8], [3.6, 1.8], [3.5, 1.85]])   # "Coordinate data"
     # the repeated "Start coordinates" of Bottom: the last one counts (and a 3-entry array in a 2D deck is ignored)
     x = c["xi"][bottom["first"]:bottom["second"]]
     assert abs(x[:, 0].min() + 0.05) < 1e-12 and x.shape[0] == 4 * 81
     assert left["no_slip"] == 1 and left["bound_solver"] == 0   # "Wall is no-slip": true, "Boundary solver": "DBC"
-    water = c["blocks"][5]
+    water = c["blocks"][6]
     assert water["second"] - water["first"] == 40 * 20
 
     def para_for(i, fluid_json):
