@@ -308,6 +308,8 @@ extern "C" int fjsph_tau_read(const char* mesh_file, const char* solution_file, 
             M->cell_ptr.push_back(int64_t(M->cell_faces.size()));
             std::sort(elem.begin(), elem.end());
             elem.erase(std::unique(elem.begin(), elem.end()), elem.end());
+            if (elem.empty())
+                throw TauError{"cell " + std::to_string(c) + " has no faces"};
             const double nv = double(elem.size());
             Kahan s[8];
             for (size_t i : elem)
