@@ -104,6 +104,30 @@ int main(int argc, char** argv)
         std::fprintf(stderr, "ERROR: SPH frame count has not been defined (para key or --frames).\n");
         return 1;
     }
+    /* aero mesh named by the deck, read on the host before anything touches the device, as FJSPH.cpp:70-100 does
+       (FOAM::Read_FOAM, or TAU::Read_tau_mesh_FACE + Read_SOLUTION; Read_BMAP is part of fjsph_case_read); uploaded for
+       the containment lookup once the particles are on the device */
+    FjsphFoamMesh* aero_mesh = nullptr;
+    {
+        char fdir[1024] = "", fsol[1024] = "", tmesh[1024] = "", tsol[1024] = "";
+        int32_t buoyant = 0;
+        double tscale = 1.0;
+        FjsphMesh view;
+        fjsph_case_foam(c, fdir, fsol, &buoyant, 1024);
+        fjsph_case_tau(c, tmesh, tsol, &tscale, 1024);
+        if (tmesh[0])
+        {
+            if (fjsph_tau_read(tmesh, tsol, tscale, &aero_mesh) || fjsph_foam_view(aero_mesh, &view))
+                return fail("reading the TAU mesh");
+            std::printf("TAU mesh: %lld cells, %lld faces\n", (long long)view.n_cells, (long long)view.n_faces);
+        }
+        else if (fdir[0])
+        {
+            if (fjsph_foam_read(fdir, fsol, buoyant, P.rho_g, &aero_mesh) || fjsph_foam_view(aero_mesh, &view))
+                return fail("reading the OpenFOAM case");
+            std::printf("OpenFOAM mesh: %lld cells, %lld triangles\n", (long long)view.n_cells, (long long)view.n_faces);
+        }
+    }
     const int64_t n0 = fjsph_case_count(c), nb0 = fjsph_case_bound_points(c);
     const int64_t capacity = max_points > n0 ? max_points : 2 * n0 + 100000;
     FjsphEngine* e = nullptr;
@@ -135,33 +159,12 @@ int main(int argc, char** argv)
     }
     else if (fjsph_read_restart(e, restart_file.c_str(), &frame))
         return fail("reading the restart file");
+    if (aero_mesh)
     {
-        /* aero mesh named by the deck (FJSPH.cpp:70-100: FOAM::Read_FOAM), uploaded for the containment lookup */
-        char fdir[1024] = "", fsol[512] = "";
-        int32_t buoyant = 0;
-        fjsph_case_foam(c, fdir, fsol, &buoyant, 512);
-        if (fdir[0])
-        {
-            FjsphFoamMesh* fm = nullptr;
-            FjsphMesh view;
-            if (fjsph_foam_read(fdir, fsol, buoyant, P.rho_g, &fm) || fjsph_foam_view(fm, &view) || fjsph_upload_mesh(e, &view))
-                return fail("reading the OpenFOAM case");
-            std::printf("OpenFOAM mesh: %lld cells, %lld triangles\n", (long long)view.n_cells, (long long)view.n_faces);
-            fjsph_foam_free(fm);
-        }
-        /* ... or the TAU mesh and solution (FJSPH.cpp:72-79: Read_BMAP is part of fjsph_case_read) */
-        char tmesh[1024] = "", tsol[1024] = "";
-        double tscale = 1.0;
-        fjsph_case_tau(c, tmesh, tsol, &tscale, 1024);
-        if (tmesh[0])
-        {
-            FjsphFoamMesh* fm = nullptr;
-            FjsphMesh view;
-            if (fjsph_tau_read(tmesh, tsol, tscale, &fm) || fjsph_foam_view(fm, &view) || fjsph_upload_mesh(e, &view))
-                return fail("reading the TAU mesh");
-            std::printf("TAU mesh: %lld cells, %lld faces\n", (long long)view.n_cells, (long long)view.n_faces);
-            fjsph_foam_free(fm);
-        }
+        FjsphMesh view;
+        if (fjsph_foam_view(aero_mesh, &view) || fjsph_upload_mesh(e, &view))
+            return fail("uploading the aero mesh");
+        fjsph_foam_free(aero_mesh);
     }
     fjsph_get_params(e, &P);
     std::printf("Starting counts:\nBoundary: %lld  Sim: %lld\n\n", (long long)nb0, (long long)(fjsph_count(e) - nb0));

@@ -140,3 +140,24 @@ def test_headers_of_the_reference_s_own_tau_files():
         frontend.read_tau(rae + "/mesh.grid.conf.edges")
     with pytest.raises(_lib.FjsphError, match='sol.pval.10000: no dimension "no_of_elements"'):
         frontend.read_tau(rae + "/sol.pval.10000")
+
+
+def test_driver_reads_the_tau_mesh_before_it_needs_a_device(tmp_path):
+    """fjsph_b200_run on a deck naming a TAU mesh: the mesh and solution are read on the host first, as FJSPH.cpp:70-100
+    does, so this part of the driver runs without a GPU (an impossible device number stops it at fjsph_create)."""
+    import os
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fjsph_b200", "bin", "fjsph_b200_run")
+    mesh, sol, *_ = write_tau(tmp_path, LO, HI, (2, 3, 2), VEL, PR, RHO)
+    (tmp_path / "f.bmap").write_text("   Name: W\n  Shape: Sphere\n Centre coordinate: 0,0,0\n Radius: 0.03\n Particle spacing: 0.01\n block end\n")
+    (tmp_path / "none.bmap").write_text("\n")
+    (tmp_path / "tau.bmap").write_text(" block begin\n   Markers: 1\n   Type: farfield\n block end\n")
+    (tmp_path / "para").write_text(" Input boundary definition filename: none.bmap\n Input fluid definition filename: f.bmap\n"
+                                   " SPH initial spacing: 0.01\n SPH aerodynamic case: Gissler\n SPH frame time interval: 1e-4\n"
+                                   " Primary grid face filename: %s\n Boundary mapping filename: tau.bmap\n Restart-data prefix: %s\n" % (mesh, sol))
+    out = subprocess.run([exe, "para", "--frames", "1", "--device", "9999"], cwd=tmp_path, stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True)
+    n_faces = 2 * 3 * 3 * 2 + 2 * 4 * 2 + 2 * 3 * 3                  # split x-faces + y-faces + z-faces
+    assert "TAU mesh: 12 cells, %d faces" % n_faces in out.stdout, out.stdout[-2000:]
+    assert out.returncode == 1 and "creating the engine" in out.stdout, out.stdout[-2000:]
