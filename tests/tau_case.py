@@ -4,9 +4,10 @@ import numpy as np
 from scipy.io import netcdf_file
 
 
-def write_tau(root, lo, hi, n, vel, p, rho, version=2, wall_marker=-1, outer_marker=-2, float_solution=False):
-    """Box [lo, hi] of n = (nx, ny, nz) hexahedra.  The x-normal faces are split into two triangles each (so the file has
-    triangles AND quadrilaterals; triangles come first in the face numbering), the others stay quadrilaterals.  Cell ids
+def write_tau(root, lo, hi, n, vel, p, rho, version=2, wall_marker=-1, outer_marker=-2, float_solution=False, split="x"):
+    """Box [lo, hi] of n = (nx, ny, nz) hexahedra.  The x-normal faces (split="x"; the y-normal ones with split="y") are
+    split into two triangles each (so the file has triangles AND quadrilaterals; triangles come first in the face
+    numbering), the others stay quadrilaterals.  Cell ids
     are (k*ny + j)*nx + i.  right_element_of_faces of a boundary face is wall_marker on zmin, outer_marker elsewhere.
     Returns (mesh path, solution path, points, list of faces as vertex tuples, left, right)."""
     nx, ny, nz = n
@@ -25,8 +26,11 @@ def write_tau(root, lo, hi, n, vel, p, rho, version=2, wall_marker=-1, outer_mar
                     l, r = cid(nx - 1, j, k), outer_marker
                 else:
                     l, r = cid(i - 1, j, k), cid(i, j, k)
-                tris.append(((q[0], q[1], q[2]), l, r))
-                tris.append(((q[0], q[2], q[3]), l, r))
+                if split == "x":
+                    tris.append(((q[0], q[1], q[2]), l, r))
+                    tris.append(((q[0], q[2], q[3]), l, r))
+                else:
+                    quads.append((q, l, r))
     for k in range(nz):
         for j in range(ny + 1):
             for i in range(nx):
@@ -37,7 +41,11 @@ def write_tau(root, lo, hi, n, vel, p, rho, version=2, wall_marker=-1, outer_mar
                     l, r = cid(i, ny - 1, k), outer_marker
                 else:
                     l, r = cid(i, j - 1, k), cid(i, j, k)
-                quads.append((q, l, r))
+                if split == "y":
+                    tris.append(((q[0], q[1], q[2]), l, r))
+                    tris.append(((q[0], q[2], q[3]), l, r))
+                else:
+                    quads.append((q, l, r))
     for k in range(nz + 1):
         for j in range(ny):
             for i in range(nx):

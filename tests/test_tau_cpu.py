@@ -161,3 +161,38 @@ def test_driver_reads_the_tau_mesh_before_it_needs_a_device(tmp_path):
     n_faces = 2 * 3 * 3 * 2 + 2 * 4 * 2 + 2 * 3 * 3                  # split x-faces + y-faces + z-faces
     assert "TAU mesh: 12 cells, %d faces" % n_faces in out.stdout, out.stdout[-2000:]
     assert out.returncode == 1 and "creating the engine" in out.stdout, out.stdout[-2000:]
+
+
+def test_coupled_run_on_quadrilateral_faces_follows_the_reference(tmp_path):
+    """TAU quadrilaterals stay four-cornered and Crossings3D tests only the edges (3,0), (0,1), (1,2) of one, so
+    a +x ray that passes ABOVE an x-normal quadrilateral (beyond its untested edge) still counts as crossing it.  The
+    oracle and FJSPH's compiled sources, both coupled to the same TAU-read mesh whose x-normal faces are quadrilaterals,
+    every particle starting in the cell BELOW its own: that cell's far face is "crossed", so CheckCell keeps the particle
+    there -- on both sides alike.  Two steps: the same cells for every particle (the wrong ones included), state to 1e-12."""
+    if not orc.have_ref("ref3d"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    n = (8, 9, 7)
+    mesh_file, sol_file, *_ = write_tau(tmp_path, LO, HI, n, lambda x: (1.0 + 40 * x[0], 21.55 - 30 * x[2], 5 * x[1]),
+                                        lambda x: 1.0e5 + 100 * x[1], lambda x: 1.1 + x[2], split="y")
+    tau = frontend.read_tau(mesh_file, sol_file)
+    case = cases.droplet(dx=0.0125, jitter=0.05)
+    params = dict(case["params"], delta_t_min=1e-9)
+    ijk = np.floor((case["xi"] - LO) / ((HI - LO) / np.array(n))).astype(int)
+    own = (ijk[:, 2] * n[1] + ijk[:, 1]) * n[0] + ijk[:, 0]
+    below = np.where(ijk[:, 2] > 0, own - n[0] * n[1], own)
+    runs = []
+    for kind in (None, "ref3d"):
+        o = orc.Oracle(orc.default_params(3, asource=1, **params), **({"kind": kind} if kind else {}))
+        o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+        o.set_mesh(tau)
+        for lvl in (0, 1):   # (a valid starting cell is needed anyway: the reference indexes cFaces[-3] otherwise, SURVEY Q7)
+            o.set("cellID", below.astype(np.int64), lvl)
+        its = [o.integrate()[1].iterations for _ in range(2)]
+        runs.append((its, {f: o.get(f) for f in ("cellID", "xi", "v", "rho", "Af", "cellV", "cellP")}))
+    (its_a, a), (its_b, b) = runs
+    assert its_a == its_b and np.array_equal(a["cellID"], b["cellID"])
+    found = a["cellID"] >= 0
+    assert found.sum() > 50 and (a["cellID"][found] == below[found]).sum() > 0.9 * found.sum()   # Q6 at work: kept in the cell below
+    assert (a["cellID"][found] != own[found]).sum() > 0.5 * found.sum()
+    for f, tol in (("xi", 1e-13), ("rho", 1e-13), ("v", 1e-11), ("Af", 1e-11), ("cellV", 1e-14), ("cellP", 1e-14)):
+        assert np.abs(a[f] - b[f]).max() <= tol * max(np.abs(b[f]).max(), 1e-300), f
