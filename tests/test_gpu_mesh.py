@@ -147,3 +147,4 @@ def test_tau_mesh_with_quadrilateral_faces(tmp_path):
         for f, tol in (("xi", 1e-10), ("rho", 1e-10), ("v", 1e-8), ("Af", 1e-6), ("acc", 1e-6)):
             ref = o.get(f)
             assert np.abs(got[f] - ref).max() <= tol * max(np.abs(ref).max(), 1e-300), (step, f)
+
