@@ -259,3 +259,36 @@ def test_tau_files_read_like_the_reference(tmp_path, version, scale, float_solut
     for k in ("face_ptr", "face_vtx", "leftright", "cell_ptr", "cell_faces", "verts", "cCentre", "cVel", "cP", "cRho"):
         assert np.array_equal(mine[k], theirs[k]), k
     assert np.abs(mine["cVel"]).max() > 1.0 and mine["cP"].min() > 9.0e4
+
+
+def test_arc_deck_steps_follow_the_reference_in_2d():
+    """tests/decks/arc2d (water in a bowl of Arc rings, intersecting particles culled) through the product's front end, then
+    three Integrator::integrate steps on the 2D build of the compiled reference and on the 2D oracle: the same
+    sub-iterations and time steps, surface flags identical, state to 1e-13."""
+    from tests.util import relerr, INPUT_PARAMS
+
+    if not _have("ref2d"):
+        pytest.skip("ref2d")
+    mine = frontend.read_case(os.path.join(HERE, "decks", "arc2d.para"), 2)
+    P = mine["params"]
+    params = {k: (tuple(getattr(P, k)) if hasattr(getattr(P, k), "__len__") else getattr(P, k)) for k in INPUT_PARAMS}
+
+    def fed(**kind):
+        a = orc.Oracle(orc.default_params(2, **params), **kind)
+        a.set_particles(mine["xi"], mine["v"], mine["rho"], mine["p"], mine["m"], mine["b"], mine["bound_points"])
+        a.lib.orc_clear_blocks(a.h)
+        for B in mine["blocks"]:
+            a.add_block(B["is_fluid"], B["first"], B["second"], bound_solver=B["bound_solver"], no_slip=B["no_slip"],
+                        block_type=B["block_type"], fixed_vel_or_dynamic=B["fixed_vel_or_dynamic"], times=B["times"],
+                        vels=B["vels"], insert_norm=B["insert_norm"], insconst=B["insconst"], delete_norm=B["delete_norm"],
+                        delconst=B["delconst"], aero_norm=B["aero_norm"], aeroconst=B["aeroconst"])
+        return a
+
+    o, r = fed(), fed(kind="ref2d")
+    for step in range(3):
+        _, so = o.integrate()
+        _, sr = r.integrate()
+        assert so.iterations == sr.iterations and so.dt == sr.dt, step
+    assert np.array_equal(o.get("surf"), r.get("surf")) and np.array_equal(o.get("b"), r.get("b"))
+    for f, tol in (("xi", 1e-14), ("rho", 1e-14), ("v", 1e-13), ("p", 1e-13), ("acc", 1e-13), ("Rrho", 1e-13)):
+        assert relerr(o.get(f), r.get(f)) <= tol, (f, relerr(o.get(f), r.get(f)))
