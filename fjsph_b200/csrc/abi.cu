@@ -645,7 +645,7 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
     }
     if (capacity > int64_t(FJ_IDX_MASK))
     {
-        fj_set_error("capacity %lld exceeds the 2^28-1 particles one engine can index", (long long)capacity);
+        fj_set_error("capacity %lld exceeds the 2^27-1 particles one engine can index", (long long)capacity);
         return FJSPH_ERR_CAPACITY;
     }
     int st = validate_params(*p);
@@ -688,23 +688,26 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
     FJ_CUDA(cudaMalloc(&e->perm, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->perm2, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->ncount, cap * sizeof(int)));
-    FJ_CUDA(cudaMalloc(&e->scount, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->xref, cap * sizeof(double4)));
+    FJ_CUDA(cudaMalloc(&e->x0, cap * sizeof(double4)));
     e->skin = 0.4 * e->P.particle_step; /* default skin: 0.4 dx = 5 % of the support radius at H_fac = 2 */
-    if (const char* order = std::getenv("FJSPH_B200_CELL_ORDER")) /* "morton" | "pencil" (default), engine.cuh */
-        e->pencil_order = std::string(order) != "morton";
-    if (const char* tile = std::getenv("FJSPH_B200_PENCIL_TILE"))
-        std::sscanf(tile, "%d,%d", &e->pencil_tile_x, &e->pencil_tile_y);
+    if (const char* v = std::getenv("FJSPH_B200_ROW_AXIS")) /* neighbours.cu, rebuild_skin */
+        e->row_axis = std::atoi(v);
+    if (const char* v = std::getenv("FJSPH_B200_ROW_WIDTH"))
+        e->row_width_cells = std::atof(v);
+    if (const char* v = std::getenv("FJSPH_B200_MAX_KEY_BITS"))
+        e->max_key_bits = std::min(29, std::max(6, std::atoi(v)));
+    if (const char* v = std::getenv("FJSPH_B200_SWEEP_WARPS"))
+        e->sweep_warps = (std::atoi(v) == 4) ? 4 : 8;
     if (const char* split = std::getenv("FJSPH_B200_SPLIT_SURFACE"))
         e->split_surface_sweep = std::string(split) != "0";
-    if (const char* order = std::getenv("FJSPH_B200_LIST_ORDER")) /* "index" (default) | "columns", engine.cuh */
-        e->column_order = std::string(order) == "columns";
     FJ_CUDA(cudaMalloc(&e->near_inlet, cap * sizeof(int)));
     FJ_CUDA(cudaMemset(e->near_inlet, 0, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->rk_sum_v, cap * sizeof(double4)));
     FJ_CUDA(cudaMalloc(&e->rk_sum_a, cap * sizeof(double4)));
     const size_t red_n = std::max<size_t>((cap + 127) / 128 + 16, 2048 * 8);
     FJ_CUDA(cudaMalloc(&e->red, red_n * sizeof(double)));
+    e->red_cap = red_n;
     FJ_CUDA(cudaMalloc(&e->red_out, 16 * sizeof(double)));
     FJ_CUDA(cudaMallocHost(&e->h_red, 16 * sizeof(double)));
     FJ_CUDA(cudaMalloc(&e->d_flag, 4 * sizeof(int)));
@@ -741,8 +744,9 @@ int fjsph_destroy(FjsphEngine* e)
     fj_free_mesh(e);
     void* ptrs[] = {e->oidx,       e->oidx_tmp, e->slot_of,  e->blk,      e->blk_tmp,   e->key,     e->rank_in_cell,
                     e->perm,       e->perm2,    e->ncount,   e->near_inlet, e->rk_sum_v, e->rk_sum_a, e->red,
-                    e->red_out,    e->d_flag,   e->stage,    e->cell_count, e->cell_start, e->scan_tmp, e->mtab_x,
-                    e->nlist,      e->nr,       e->slist,    e->scount,     e->xref};
+                    e->red_out,    e->d_flag,   e->stage,    e->cell_count, e->cell_start, e->scan_tmp, e->mtab_y,
+                    e->erun,       e->erows,    e->srun,     e->srows,      e->xref,       e->x0,       e->warp_start,
+                    e->row_warps,  e->row_scan_tmp, e->row_off};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -1093,27 +1097,34 @@ int fjsph_get_neighbours(FjsphEngine* e, const int64_t* offsets, int64_t* idx)
         return FJSPH_ERR_STATE;
     }
     const size_t n = size_t(e->n_owned);
-    const size_t nw = (n + 31) / 32;
-    std::vector<int> cnt(n), oidx(n);
-    std::vector<unsigned> list(nw * size_t(e->nb_cap) * 32u);
-    FJ_CUDA(cudaMemcpyAsync(cnt.data(), e->ncount, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    FJ_CUDA(cudaMemcpyAsync(oidx.data(), e->oidx, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    FJ_CUDA(cudaMemcpyAsync(list.data(), e->nlist, list.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
-    FJ_CUDA(cudaStreamSynchronize(e->stream));
-    for (size_t i = 0; i < n; ++i)
+    const size_t total = size_t(offsets[n]);
+    long long *d_off = nullptr, *d_idx = nullptr;
+    int* d_bad = nullptr;
+    FJ_CUDA(cudaMalloc(&d_off, (n + 1) * sizeof(long long)));
+    FJ_CUDA(cudaMalloc(&d_idx, std::max<size_t>(total, 1) * sizeof(long long)));
+    FJ_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    FJ_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), e->stream));
+    FJ_CUDA(cudaMemcpyAsync(d_off, offsets, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    int st = fj_neighbours_to_csr(e, d_off, d_idx, d_bad);
+    int bad = 0;
+    if (!st)
     {
-        const int64_t c = oidx[i];
-        int64_t* dst = idx + offsets[c];
-        int k = 0;
-        for (; k < cnt[i]; ++k) dst[k] = oidx[list[FJ_LIST_WORD(i, k, e->nb_cap)] & FJ_IDX_MASK];
-        dst[k++] = c;
-        if (offsets[c + 1] - offsets[c] != k)
-        {
-            fj_set_error("get_neighbours: offsets do not match neighbour_counts");
-            return FJSPH_ERR_INVALID;
-        }
-        std::sort(dst, dst + k);
+        cudaMemcpyAsync(idx, d_idx, total * sizeof(long long), cudaMemcpyDeviceToHost, e->stream);
+        cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess)
+            st = fj_cuda_fail(cudaGetLastError(), "get_neighbours", __FILE__, __LINE__);
     }
+    cudaFree(d_off);
+    cudaFree(d_idx);
+    cudaFree(d_bad);
+    if (st)
+        return st;
+    if (bad)
+    {
+        fj_set_error("get_neighbours: offsets do not match neighbour_counts");
+        return FJSPH_ERR_INVALID;
+    }
+    for (size_t c = 0; c < n; ++c) std::sort(idx + offsets[c], idx + offsets[c + 1]);
     return FJSPH_OK;
 }
 

@@ -20,12 +20,9 @@
 
 #include "../../include/fjsph_b200.h"
 
-#define FJ_IDX_MASK 0x0FFFFFFFu
-#define FJ_NB_FLUID 0x80000000u /* neighbour j has b > PISTON (VarDefs.h:92-102) */
-#define FJ_NB_BOUND 0x40000000u /* neighbour j has b == BOUND */
-/* word index of slot s of particle i in the chunked ELL list (nb_cap slots per particle, a multiple of 4) */
-#define FJ_LIST_WORD(i, s, nb_cap) \
-    ((((size_t((i) >> 5) * size_t((nb_cap) >> 2) + size_t((s) >> 2)) * 32u + size_t((i)&31)) << 2) + size_t((s)&3))
+#define FJ_IDX_MASK 0x07FFFFFFu /* 2^27 - 1 particles per engine: a skin run packs first index + length in 32 bits */
+#define FJ_RUN_EMPTY 0xFFFFFFFFu
+#define FJ_ROW_WARPS 8 /* warps (= rows) of a CTA of the list builds: 4 rows along v x 2 rows along w */
 
 // X(type, name): every per-particle array of one time level
 #define FJ_LEVEL_FIELDS(X)                                                                                     \
@@ -56,16 +53,51 @@ struct DevConst
     int ale, pressure_rel, acase, asource, use_lam, use_TAB_def;
 };
 
+// Cell grid in ROW coordinates (u, v, w): u = the row axis (the longest extent of the particles' bounding box, component
+// ax0 of a position), v and w the transverse axes (components ax1, ax2).  A ROW is a pencil of cells one particle spacing
+// wide along v and w; its particles are contiguous in memory and sorted along u (key = row bits << bx | u-cell).
 struct Grid
 {
-    double ox, oy, oz, inv_cell; // inv_cell: 1 / cell edge along x (>= 2H + skin: reach 1)
-    double inv_cy, inv_cz;       // 1 / cell edge along y and z (pencil order: ~ one particle spacing; else = inv_cell)
-    double pw2, r_skin2;         // (cell edge along y, z)^2 and (2H + skin)^2, to cull pencils outside the disc
-    int ry, rz;                  // cells to visit either side along y and z (1 for cubic cells)
-    int nx, ny, nz;              // cells per axis
-    int bx, by, bz;              // key bits per axis
-    unsigned int n_keys;         // 2^(bx+by+bz)
+    double ox, oy, oz, inv_cell; // origin in (u, v, w); inv_cell: 1 / cell edge along u (>= 2H + skin: reach 1)
+    double inv_cy, inv_cz;       // 1 / cell edge along v and w (~ one particle spacing)
+    double pw2, r_skin2;         // (cell edge along v, w)^2 and (2H + skin)^2, to cull rows outside the disc
+    int ry, rz;                  // rows to visit either side along v and w
+    int nx, ny, nz;              // cells per axis (u, v, w)
+    int bx, by, bz;              // key bits per axis; the u bits are the low bx bits of a key
+    int ax0, ax1, ax2;           // position component (0 = x, 1 = y, 2 = z) of u, v, w
+    unsigned int n_keys;         // 2^(bx+by+bz) keys per class; 2^(by+bz) rows per class
 };
+
+// Work mapping of the row sweeps: CTA (group g, chunk c) holds WARPS warps (4, 8 or 16); warp w walks particles
+// [32 c, 32 c + 32) of row  row0 + g * WARPS + w.  Rows that are adjacent in v and w have adjacent ids (the low
+// row-id bits are v0, w0, v1, w1), so the warps of a CTA sweep the same stretch of a 2 x 2, 4 x 2 or 4 x 4 block of
+// neighbouring rows and share what they pull into L1.  warp_start[row] + c numbers the work warps; the run lists are
+// laid out by that number, whatever the CTA shape.
+struct RowMap
+{
+    const unsigned* __restrict__ cell_start;
+    const unsigned* __restrict__ warp_start;
+    unsigned row0, n_rows; // rows [row0, row0 + n_rows) of the table (n_rows a multiple of 16)
+    int bx;
+    int n_chunks;
+};
+#ifdef __CUDACC__
+// particle and work-warp number of this thread; false for lanes past the end of the row (the whole warp when the row
+// holds no chunk c).  i is a valid particle index whenever the WARP has work (clamped to the row's last particle).
+template <int WARPS = FJ_ROW_WARPS>
+__device__ __forceinline__ bool fj_row_thread(const RowMap& M, int& i, int& W, bool& warp_has_work)
+{
+    const unsigned chunk = blockIdx.x % unsigned(M.n_chunks), group = blockIdx.x / unsigned(M.n_chunks);
+    const unsigned row = M.row0 + group * WARPS + (threadIdx.x >> 5);
+    const unsigned s = M.cell_start[size_t(row) << M.bx], e = M.cell_start[size_t(row + 1u) << M.bx];
+    const unsigned first = s + chunk * 32u;
+    warp_has_work = first < e;
+    W = int(M.warp_start[row] + chunk);
+    const unsigned ii = first + (threadIdx.x & 31u);
+    i = int(warp_has_work ? (ii < e ? ii : e - 1u) : 0u);
+    return ii < e;
+}
+#endif
 
 // X(name): the double4 record arrays of a level, in halo-mask bit order
 #define FJ_D4_FIELDS(X) X(P0) X(P1) X(P2) X(P3) X(P4) X(ACC) X(AF) X(AV) X(CV) X(NP) X(BN) X(TH) X(SC)
@@ -183,27 +215,42 @@ struct FjsphEngine
     unsigned int* cell_start = nullptr; // [key_cap+1]
     unsigned int* scan_tmp = nullptr;
     size_t key_cap = 0;
-    unsigned int *mtab_x = nullptr, *mtab_y = nullptr, *mtab_z = nullptr; // Morton spread tables
+    unsigned int *mtab_y = nullptr, *mtab_z = nullptr; // key bits of a row's v and w cell coordinates
     int mtab_cap = 0;
-    // chunked warp-transposed ELL: slots come in chunks of 4 per lane; chunk c of lane l of warp w is element
-    // (w*nchunk + c)*32 + l of a uint4 array (indices + flag bits) and of a double4 array (frozen r), so a lane
-    // reads 4 slots with one 128-bit + one 256-bit load and a warp's loads are contiguous (512 B / 1 KB).
-    unsigned int* nlist = nullptr;      // slot s of particle i at FJ_LIST_WORD(i, s, nb_cap)
-    double* nr = nullptr;               // same layout: r = sqrt(d^2) at list-build time (OUTL's .second, frozen)
+    int row_axis = -1;                  // FJSPH_B200_ROW_AXIS: 0 | 1 | 2 pins the row axis (default: the longest extent)
+    double row_width_cells = 0.0;       // FJSPH_B200_ROW_WIDTH: row width along v, w in particle spacings (default 1)
+    int max_key_bits = 25;              // FJSPH_B200_MAX_KEY_BITS: rows widen until the cell table fits 2^bits keys
+    // Row-run neighbour lists (neighbours.cu).  A particle's neighbours inside one row are a window of consecutive
+    // indices (rows are sorted along u), so a list is one RUN per neighbouring row: {first index, 32-bit membership
+    // mask}.  Slot k of work warp W, lane l is element (W * cap + k) * 32 + l: the 32 lanes of a warp -- 32 consecutive
+    // particles of one row -- walk the same neighbouring row at the same time and gather consecutive records.
+    // Slots that are empty for every lane of a warp are squeezed out (erows / srows = slots in use per warp).
+    uint2* erun = nullptr;              // exact list (the reference's OUTL): {first, mask}, mask bit o <-> index first + o
+    int* erows = nullptr;               // [n_warp]
+    int ecap = 0;
     int* ncount = nullptr;              // [cap] neighbours excluding self
-    // skin list (superset with d < 2H + skin at its build time), same chunked layout, indices only
-    unsigned int* slist = nullptr;
-    int* scount = nullptr;
-    double4* xref = nullptr;            // positions at the skin build
+    double4* x0 = nullptr;              // positions the exact list was built on: r = |x0_j - x0_i| is the reference's
+                                        // sqrt(jj.second), frozen through the sub-iterations (Resid.cpp:289)
+    bool x_moved = true;                // level-1 positions differ from x0 (sweeps then take r from x0)
+    // skin list (superset with d < 2H + skin at its build time): {first | (length - 1) << 27}, FJ_RUN_EMPTY = none
+    unsigned int* srun = nullptr;
+    int* srows = nullptr;
     int scap = 0;
-    size_t slist_words = 0;
+    size_t run_warps_cap = 0;           // work warps the run arrays hold
+    unsigned* warp_start = nullptr;     // [rows + 1] exclusive scan of the 32-particle chunks per owned row
+    unsigned* row_warps = nullptr;
+    unsigned* row_scan_tmp = nullptr;
+    size_t row_cap = 0;
+    unsigned n_warp = 0;                // work warps of the owned rows
+    int n_chunks = 1;                   // ceil(longest owned row / 32)
+    int2* row_off = nullptr;            // device table of the neighbouring-row offsets (dv, dw) inside the disc
+    int n_row_off = 0;
+    double4* xref = nullptr;            // positions at the skin build
     bool skin_valid = false;
     int64_t skin_n = 0;
     double skin = 0.0;                  // skin width (m); 0 = rebuild the cell list at every update_neighbours
     long long skin_builds = 0;
     int* near_inlet = nullptr;          // [cap] Boundary_Ghost flag, valid within one sub-iteration
-    int nb_cap = 0;
-    size_t nlist_words = 0;
     bool list_valid = false;
     // fjsph_step_host overlaps the host -> device copy with the first neighbour build: positions go up first on the
     // engine's stream, everything else on upload_stream; upload_pending tells fj_integrate_no_update to run the build
@@ -211,26 +258,15 @@ struct FjsphEngine
     cudaStream_t upload_stream = nullptr;
     cudaEvent_t ev_upload_x = nullptr, ev_upload = nullptr;
     bool upload_pending = false;
-    // Memory order of the particles (decided at fjsph_create from FJSPH_B200_CELL_ORDER, default "pencil"):
-    //   pencil: cells are R x dx x dx bricks keyed lexicographically (x fastest), so consecutive particles run along x
-    //           inside a one-spacing-wide pencil and the 32 lanes of a warp walk translated copies of each other's
-    //           neighbourhoods -- slot s of their lists lands in ~14 cache lines instead of ~24 on lattice-born fluids;
-    //   morton: cubic cells of edge 2H + skin in Morton order.
-    bool pencil_order = true;
-    // pencil tiles (FJSPH_B200_PENCIL_TILE = "tx,ty", key bits; "0,0" = plain pencils): see the key tables in neighbours.cu
-    int pencil_tile_x = 3, pencil_tile_y = 3; /* measured: block 343.0 -> 337.3 ms per step (profiles/r9_tile_sweep.txt) */
-    // Order inside each chunk of four list entries (FJSPH_B200_LIST_ORDER = "index" (default) | "columns"): see chunk_slot
-    // in neighbours.cu -- with "columns", element e of a chunk of lane l holds a neighbour with index & 3 == (l + e) & 3
-    // where that element is free, so the four lanes of a group tend to gather from four different 32-byte columns, which
-    // the L1 data pipe serves in one wavefront.  Measured: force sweep -3 %, the other sweeps +1..2 %, the step +0.7 %
-    // (within noise), so it is off by default.
-    bool column_order = false;
     // fused surface / shifting sweep in two launches (lean bulk + near-surface rest) when few warps are near a surface
     // (sweeps.cu, k_surf23_shift CLASS; FJSPH_B200_SPLIT_SURFACE=0 keeps the single launch)
     bool split_surface_sweep = true;
+    int sweep_warps = 8;               // FJSPH_B200_SWEEP_WARPS: warps (rows) per CTA of the pair sweeps, 4 | 8
+    double split_surface_below = 0.35; // fraction of near-surface warps below which the two launches pay
 
     // reductions / scalars
     double* red = nullptr;              // device scratch for block partials
+    size_t red_cap = 0;
     double* red_out = nullptr;          // device [16]
     double* h_red = nullptr;            // pinned [16]
     int* d_flag = nullptr;              // device error / overflow flags [4]
@@ -291,6 +327,10 @@ static inline int fj_blocks(int64_t n, int threads) { return (int)((n + threads 
 
 // stage implementations (each returns FjsphStatus)
 int fj_build_neighbours(FjsphEngine* e);
+RowMap fj_row_map(const FjsphEngine* e, int first_class, int n_classes); /* rows of the slab classes [first, first + n) */
+unsigned fj_row_grid(const RowMap& M, int warps = FJ_ROW_WARPS);         /* CTAs of a row sweep over M */
+int fj_owned_classes(const FjsphEngine* e);                              /* 1, or 2 (interior, edge) under slabs */
+int fj_neighbours_to_csr(FjsphEngine* e, const long long* d_offsets, long long* d_idx, int* d_bad);
 int fj_prestep(FjsphEngine* e, double* npd);
 int fj_aero_velocity(FjsphEngine* e);
 int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipation, bool fuse_shift = false);

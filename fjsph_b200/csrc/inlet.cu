@@ -383,6 +383,7 @@ bool fj_has_inlets(FjsphEngine* e)
 // particles' |x - x_prev|^2 block partials behind the first `nb_partials` entries of e->red; returns the new count.
 int fj_inlet_motion(FjsphEngine* e, double dt, bool nb_solver, int* n_partials)
 {
+    e->x_moved = true;
     if (!fj_has_inlets(e))
         return FJSPH_OK;
     if (e->inlet_tables_dirty)

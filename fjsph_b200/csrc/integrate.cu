@@ -486,6 +486,8 @@ int fj_copy_level(FjsphEngine* e, int dst, int src)
 {
     const int n = int(e->n);
     KScope ks(e, "copy_level", 1);
+    if (dst == 1)
+        e->x_moved = true; /* pnp1's positions may differ from the ones the list was built on: pair sweeps take r from x0 */
     k_copy_level<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[src], e->lv[dst], n);
     FJ_CUDA(cudaGetLastError());
     return FJSPH_OK;
@@ -576,6 +578,7 @@ int fj_nb_iter(FjsphEngine* e, double npd, double* errsum)
                                                           e->P.nb_gamma, n, e->red);
     }
     FJ_CUDA(cudaGetLastError());
+    e->x_moved = true;
     int nparts = nb;
     st = fj_inlet_motion(e, e->P.delta_t, true, &nparts); /* BUFFER particles, Newmark_Beta.cpp:243-297 */
     if (st)
@@ -630,6 +633,7 @@ static int rk_stage(FjsphEngine* e, double dt_s, double* errsum)
     const int nb = fj_blocks(n, TPB);
     auto update = [&](int part) {
         KScope ks(e, "rk_update", 1);
+        e->x_moved = true;
         if (e->P.ale)
             k_rk_stage<true><<<nb, TPB, 0, e->stream>>>(e->lv[0], e->lv[1], e->blk, make_block_table(e), e->near_inlet,
                                                         e->C, dt_s, n, e->red, part);
@@ -769,6 +773,7 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
         const int nb = fj_blocks(n, TPB);
         auto final_update = [&](int part) {
             KScope ks(e, "rk_update", 1);
+            e->x_moved = true;
             k_rk_final<<<nb, TPB, 0, e->stream>>>(e->lv[0], e->lv[1], e->blk, make_block_table(e), e->near_inlet,
                                                   e->rk_sum_v, e->rk_sum_a, e->C, e->P.delta_t, n, e->red, part);
         };

@@ -576,6 +576,7 @@ int fj_aero_velocity_mesh(FjsphEngine* e)
 // Check_Pipe_Outlet with the mesh: one launch per fluid block that defines an aero plane
 int fj_pipe_outlet_mesh(FjsphEngine* e)
 {
+    e->x_moved = true; /* a particle reflected off an inner wall is put on the wall's plane (k_pipe_outlet_mesh) */
     DeviceMesh& D = e->mesh;
     if (!D.loaded)
     {

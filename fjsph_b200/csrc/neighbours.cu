@@ -1,4 +1,4 @@
-// neighbours.cu — uniform cell list replacing FJSPH's nanoflann KD-tree radius search.
+// neighbours.cu — uniform cell list + row-run neighbour lists replacing FJSPH's nanoflann KD-tree radius search.
 //
 // Replaces update_neighbours / find_neighbours / radius_search (reference src/Neighbours.cpp:7-47):
 //   list_i = { j : ((xi-xj)^2 + (yi-yj)^2) + (zi-zj)^2 < sr }, strict '<', evaluated WITHOUT fma
@@ -6,12 +6,18 @@
 // the CPU oracle.  Self is not stored (callers add the self terms explicitly; outlist[i].size() is
 // count+1).
 //
+// Layout: cells are (2H + skin) x dx x dx bricks along the ROW axis u (the longest extent of the
+// bounding box); a ROW is the pencil of cells with the same transverse coordinates, its particles contiguous in memory
+// and sorted along u.  The neighbours of particle i inside one neighbouring row are then a WINDOW of consecutive
+// indices, so a list is one run {first, 32-bit mask} per neighbouring row instead of one entry per neighbour: ~0.5 KB
+// per particle instead of 3.4 KB, and the 32 lanes of a warp (32 consecutive particles of a row) gather 32 consecutive
+// records at every step of a sweep.
+//
 // Pipeline per build (all on e->stream):
-//   bounds -> cell key (pencil cells, x fastest, by default; Morton keys for cubic cells: engine.cuh pencil_order)
-//   + warp-aggregated histogram -> block prefix scan -> scatter
-//   -> per-cell ordering by caller index (determinism) -> permute both time levels into cell order
-//   -> neighbour list in a warp-transposed ELL layout (entry (warp w, slot s, lane l) at
-//      ((w*nb_cap)+s)*32+l, so a warp reads slot s of its 32 particles with one 128-byte load).
+//   bounds -> cell key + warp-aggregated histogram -> block prefix scan -> scatter -> per-cell ordering along u
+//   (ties by caller index: deterministic) -> permute both time levels into cell order -> work-warp numbering of the rows
+//   -> SKIN runs (every j with d < 2H + skin; rebuilt only when a particle has moved more than skin / 2)
+//   -> EXACT runs (the reference's OUTL, filtered from the skin runs at every update_neighbours).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -92,20 +98,20 @@ __global__ void k_bounds_final(const double* __restrict__ partial, int nblocks, 
 }
 
 // ---------------------------------------------------------------- keys + histogram
-__device__ __forceinline__ void cell_of(const Grid& g, double x, double y, double z, int& cx, int& cy, int& cz)
+__device__ __forceinline__ double comp(const double4& a, int ax) { return ax == 0 ? a.x : (ax == 1 ? a.y : a.z); }
+__device__ __forceinline__ void cell_of(const Grid& g, const double4& a, int& cx, int& cy, int& cz)
 {
-    cx = min(max(int(floor((x - g.ox) * g.inv_cell)), 0), g.nx - 1);
-    cy = min(max(int(floor((y - g.oy) * g.inv_cy)), 0), g.ny - 1);
-    cz = min(max(int(floor((z - g.oz) * g.inv_cz)), 0), g.nz - 1);
+    cx = min(max(int(floor((comp(a, g.ax0) - g.ox) * g.inv_cell)), 0), g.nx - 1);
+    cy = min(max(int(floor((comp(a, g.ax1) - g.oy) * g.inv_cy)), 0), g.ny - 1);
+    cz = min(max(int(floor((comp(a, g.ax2) - g.oz) * g.inv_cz)), 0), g.nz - 1);
 }
 
 // Slab mode sorts three classes one behind the other (key offsets 0, n_keys, 2 n_keys): INTERIOR owned particles
 // (x in [x_edge_lo, x_edge_hi): farther than 2H + skin from every face with a neighbour rank, so no ghost can be
 // their neighbour), EDGE owned particles (the ones sent as ghosts, same predicate as k_ghost_flags) and GHOSTS.
-__global__ void k_key_hist(const double4* __restrict__ P0, int n, int n_owned, Grid g, const unsigned* __restrict__ mx,
-                           const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
-                           unsigned* __restrict__ key, unsigned* __restrict__ rank, unsigned* __restrict__ count,
-                           int n_class, double x_edge_lo, double x_edge_hi)
+__global__ void k_key_hist(const double4* __restrict__ P0, int n, int n_owned, Grid g, const unsigned* __restrict__ my,
+                           const unsigned* __restrict__ mz, unsigned* __restrict__ key, unsigned* __restrict__ rank,
+                           unsigned* __restrict__ count, int n_class, double x_edge_lo, double x_edge_hi)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
@@ -114,8 +120,8 @@ __global__ void k_key_hist(const double4* __restrict__ P0, int n, int n_owned, G
     {
         double4 a = P0[i];
         int cx, cy, cz;
-        cell_of(g, a.x, a.y, a.z, cx, cy, cz);
-        k = mx[cx] | my[cy] | mz[cz];
+        cell_of(g, a, cx, cy, cz);
+        k = unsigned(cx) | my[cy] | mz[cz];
         if (n_class == 3)
         {
             if (i >= n_owned)
@@ -145,11 +151,13 @@ __global__ void k_scatter(const unsigned* __restrict__ key, const unsigned* __re
         perm[cell_start[key[i]] + rank[i]] = i;
 }
 
-// One warp per occupied cell segment: order its members by caller index (rank sort).  The atomics above
-// leave an arbitrary order inside a cell; this makes the layout — and with it every FP64 summation
-// order downstream — reproducible run to run.
+// One warp per occupied cell: order its members along the row axis u, ties by caller index (rank sort).  The atomics
+// above leave an arbitrary order inside a cell; this makes the layout -- and with it every FP64 summation order
+// downstream -- reproducible run to run, and the rows sorted along u, which is what makes a particle's neighbours
+// inside a row a window of consecutive indices.
 __global__ void k_cell_order(const unsigned* __restrict__ cell_start, unsigned n_keys, const int* __restrict__ perm,
-                             const int* __restrict__ oidx, int* __restrict__ perm2)
+                             const int* __restrict__ oidx, const double4* __restrict__ P0, int ax0,
+                             int* __restrict__ perm2)
 {
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31;
@@ -163,8 +171,14 @@ __global__ void k_cell_order(const unsigned* __restrict__ cell_start, unsigned n
     {
         const int mine = perm[s + t];
         const int mo = oidx[mine];
+        const double mu = comp(P0[mine], ax0);
         unsigned r = 0;
-        for (unsigned u = 0; u < c; ++u) r += (oidx[perm[s + u]] < mo) ? 1u : 0u;
+        for (unsigned u = 0; u < c; ++u)
+        {
+            const int other = perm[s + u];
+            const double ou = comp(P0[other], ax0);
+            r += (ou < mu || (ou == mu && oidx[other] < mo)) ? 1u : 0u;
+        }
         perm2[s + r] = mine;
     }
 }
@@ -183,12 +197,29 @@ __global__ void k_permute_index(const int* __restrict__ oidx_in, const int* __re
     slot_of[o] = i;
 }
 
-// ---------------------------------------------------------------- skin list + exact list
-// Two-level neighbour build.  The SKIN list holds every j with d < 2H + skin at the time it was built (27-cell
-// sweep over the Morton cell list); it stays valid while no particle has moved more than skin/2 since.  The
-// EXACT list -- the reference's OUTL: { j : d2 < sr } with r = sqrt(d2), rebuilt at every update_neighbours --
-// is filtered from the skin list with the bit-exact nanoflann distance on the CURRENT positions, ~1.3 N_nb
-// candidates per particle instead of the 27-cell sweep's ~7 N_nb.  Both use the chunked ELL layout.
+// ---------------------------------------------------------------- work warps of the rows
+// row r spans cell keys [r << bx, (r + 1) << bx); owned rows (the first n_owned_rows of the table) are cut into
+// 32-particle chunks, one work warp each.  stats[0] = longest owned row.
+__global__ void k_row_warps(const unsigned* __restrict__ cell_start, int bx, unsigned n_rows, unsigned n_owned_rows,
+                            unsigned* __restrict__ row_warps, unsigned* __restrict__ stats)
+{
+    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows)
+        return;
+    const unsigned len = cell_start[size_t(r + 1u) << bx] - cell_start[size_t(r) << bx];
+    const bool owned = r < n_owned_rows;
+    row_warps[r] = owned ? (len + 31u) >> 5 : 0u;
+    if (owned && len > 0)
+        atomicMax(stats, len);
+}
+
+__global__ void k_snapshot(const double4* __restrict__ P0, double4* __restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = P0[i];
+}
+
 __device__ __forceinline__ double4 ldg256(const double4* __restrict__ base, unsigned j)
 {
     double4 v;
@@ -196,246 +227,173 @@ __device__ __forceinline__ double4 ldg256(const double4* __restrict__ base, unsi
     return v;
 }
 
-// ---------------------------------------------------------------- column-aware order inside a chunk
-// The L1 data pipe serves a warp-wide 256-bit gather four lanes at a time: each group of four consecutive lanes costs
-// as many wavefronts as lanes of the group collide in the same 32-byte COLUMN of a 128-byte line (address bits 6:5,
-// i.e. record index & 3) on different sectors, and one wavefront when the four records sit in four different columns
-// -- whatever lines they are in (tools/l1_gather_probe.cu under ncu: 32 random lines cost 8.3 wavefronts with the
-// columns arranged so, 16.4 with random columns, 32 in one column).  A lane may visit the four neighbours of a chunk
-// in any order, so a neighbour with  index & 3 == (lane + e) & 3  goes to element e of its chunk where that element is
-// still free: the four lanes of a group then gather from four different columns at that slot.  The walk
-// through memory stays the ascending one (dealing whole lists out by column was measured too: the data-pipe wavefronts
-// fall further, but the four column streams of a lane drift apart, the L1 hit rate collapses and L2 -> L1 traffic
-// doubles; profiles/r5_*).
-// Online form: an accepted neighbour takes element (index - lane) & 3 of the chunk being filled if that element is
-// still free, else the lowest free one; the chunk is stored when its four elements are taken.
-template <bool COLS>
-__device__ __forceinline__ int chunk_slot(int lane, unsigned ent, unsigned freemask)
+// ---------------------------------------------------------------- skin runs
+// For every neighbouring row inside the disc of radius 2H + skin (row_off, ascending w then v) and every class
+// segment of it, the lanes scan the u-cells cx-1 .. cx+1 of that row -- one contiguous index range -- and keep the
+// window [first, last] of the particles closer than 2H + skin.  The 32 lanes are consecutive particles of one row, so
+// their ranges overlap and the scan reads a few distinct records per step.  Windows longer than 32 take several slots.
+__global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
+    k_build_skin_runs(const double4* __restrict__ P0, RowMap M, Grid g, const unsigned* __restrict__ my,
+                      const unsigned* __restrict__ mz, const int2* __restrict__ row_off, int n_off, int n_seg,
+                      double sr_skin, int scap, unsigned* __restrict__ srun, int* __restrict__ srows,
+                      int* __restrict__ flag)
 {
-    if (COLS)
-    {
-        const int want = int((ent - unsigned(lane)) & 3u);
-        if ((freemask >> want) & 1u)
-            return want;
-    }
-    return __ffs(int(freemask)) - 1;
-}
-
-template <bool COLS>
-__global__ void __launch_bounds__(TPB)
-    k_build_skin(const double4* __restrict__ P0, const int* __restrict__ b, int n, int n_owned, Grid g,
-                 const unsigned* __restrict__ mx, const unsigned* __restrict__ my, const unsigned* __restrict__ mz,
-                 const unsigned* __restrict__ cell_start, double sr_skin, int scap, unsigned* __restrict__ slist,
-                 int* __restrict__ scount, double4* __restrict__ xref, int* __restrict__ flag, int n_seg)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
+    int i, W;
+    bool work;
+    const bool valid = fj_row_thread(M, i, W, work);
+    if (!work)
+        return; /* warp-uniform */
+    const unsigned lane = threadIdx.x & 31u;
     const double4 a = P0[i];
-    xref[i] = a;
-    if (i >= n_owned)
-        return; /* ghosts are neighbours only */
     int cx, cy, cz;
-    cell_of(g, a.x, a.y, a.z, cx, cy, cz);
-    uint4* __restrict__ dst = reinterpret_cast<uint4*>(slist) + (size_t(i >> 5) * size_t(scap >> 2)) * 32u + (i & 31);
-    unsigned eb0 = unsigned(i), eb1 = unsigned(i), eb2 = unsigned(i), eb3 = unsigned(i);
-    unsigned freemask = 15u; /* free elements of the chunk being filled */
-    int cnt = 0;
-    /* cells in ascending key order (z, then y, then x), so the list comes out sorted by index */
-    for (int dz = -g.rz; dz <= g.rz; ++dz)
+    cell_of(g, a, cx, cy, cz);
+    cy = __shfl_sync(0xffffffffu, cy, 0); /* the warp's row */
+    cz = __shfl_sync(0xffffffffu, cz, 0);
+    const unsigned cxl = unsigned(max(cx - 1, 0)), cxh = unsigned(min(cx + 1, g.nx - 1));
+    unsigned* __restrict__ dst = srun + (size_t(W) * size_t(scap)) * 32u + lane;
+    int kk = 0;
+    for (int k = 0; k < n_off; ++k)
     {
-        const int z = cz + dz;
-        if (z < 0 || z >= g.nz)
+        const int2 off = row_off[k];
+        const int y = cy + off.x, z = cz + off.y;
+        if (y < 0 || y >= g.ny || z < 0 || z >= g.nz)
             continue;
-        const unsigned kz = mz[z];
-        const int gz = max(abs(dz) - 1, 0);
-        for (int dy = -g.ry; dy <= g.ry; ++dy)
+        const unsigned rowkey = my[y] | mz[z];
+        for (int seg = 0; seg < n_seg; ++seg)
         {
-            const int y = cy + dy;
-            if (y < 0 || y >= g.ny)
-                continue;
-            /* narrow cells: a pencil whose cross-section lies wholly outside the disc of radius 2H + skin holds nobody */
-            const int gy = max(abs(dy) - 1, 0);
-            if (double(gy * gy + gz * gz) * g.pw2 > g.r_skin2)
-                continue;
-            const unsigned kyz = kz | my[y];
-            for (int dx = -1; dx <= 1; ++dx)
+            const unsigned base = rowkey + unsigned(seg) * g.n_keys;
+            const unsigned s = M.cell_start[base | cxl];
+            const unsigned e = valid ? M.cell_start[(base | cxh) + 1u] : s;
+            const int T = __reduce_max_sync(0xffffffffu, int(e - s));
+            unsigned first = 0xFFFFFFFFu, last = 0u;
+            for (int o = 0; o < T; ++o)
             {
-                const int x = cx + dx;
-                if (x < 0 || x >= g.nx)
-                    continue;
-                for (int seg = 0; seg < n_seg; ++seg)
+                const unsigned j = s + unsigned(o);
+                if (j < e)
                 {
-                const unsigned k = (kyz | mx[x]) + unsigned(seg) * g.n_keys;
-                const unsigned s = cell_start[k], e = cell_start[k + 1];
-                for (unsigned j = s; j < e; ++j)
-                {
-                    const double4 q = P0[j];
+                    const double4 q = ldg256(P0, j);
                     const double ddx = a.x - q.x, ddy = a.y - q.y, ddz = a.z - q.z;
                     const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
                     if (d2 < sr_skin && int(j) != i)
                     {
-                        const int bj = b[j];
-                        unsigned ent = j;
-                        if (bj > FJSPH_PISTON)
-                            ent |= FJ_NB_FLUID;
-                        if (bj == FJSPH_BOUND)
-                            ent |= FJ_NB_BOUND;
-                        const int kk = chunk_slot<COLS>(i & 31, ent, freemask);
-                        if (kk == 0)
-                            eb0 = ent;
-                        else if (kk == 1)
-                            eb1 = ent;
-                        else if (kk == 2)
-                            eb2 = ent;
-                        else
-                            eb3 = ent;
-                        freemask &= ~(1u << kk);
-                        if (freemask == 0u)
-                        {
-                            if (cnt < scap)
-                                dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, eb1, eb2, eb3);
-                            freemask = 15u;
-                        }
-                        cnt++;
+                        first = min(first, j);
+                        last = max(last, j);
                     }
                 }
-                }
+            }
+            const int len = (first != 0xFFFFFFFFu) ? int(last - first) + 1 : 0;
+            const int maxlen = __reduce_max_sync(0xffffffffu, len);
+            for (int p = 0; p < maxlen; p += 32)
+            {
+                const int pl = len - p;
+                if (kk < scap)
+                    dst[size_t(kk) * 32u] = (pl > 0) ? ((first + unsigned(p)) | (unsigned(min(pl, 32) - 1) << 27)) : FJ_RUN_EMPTY;
+                kk++;
             }
         }
     }
-    if ((cnt & 3) && cnt < scap)
+    if (lane == 0)
     {
-        /* partial last chunk: its entries move to the front (consumers read `left` elements), the rest hold i itself */
-        unsigned v[4] = {eb0, eb1, eb2, eb3}, o[4] = {unsigned(i), unsigned(i), unsigned(i), unsigned(i)};
-        int k = 0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-            if (!((freemask >> m) & 1u))
-            {
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (t == k)
-                        o[t] = v[m];
-                k++;
-            }
-        dst[size_t(cnt >> 2) * 32u] = make_uint4(o[0], o[1], o[2], o[3]);
+        srows[W] = min(kk, scap);
+        if (kk > scap)
+            atomicMax(flag, kk);
     }
-    scount[i] = cnt;
-    if (cnt > scap)
-        atomicMax(flag, cnt);
 }
 
-// exact list from the skin list: list_i = { j in skin_i : ((xi-xj)^2 + (yi-yj)^2) + (zi-zj)^2 < sr }
-template <bool COLS>
-__global__ void __launch_bounds__(TPB)
-    k_exact_from_skin(const double4* __restrict__ P0, int n, const unsigned* __restrict__ slist,
-                      const int* __restrict__ scount, int scap, double sr, int nb_cap, unsigned* __restrict__ nlist,
-                      double* __restrict__ nr, int* __restrict__ ncount, int* __restrict__ flag)
+// ---------------------------------------------------------------- exact runs
+// exact list from the skin runs: list_i = { j in skin_i : ((xi-xj)^2 + (yi-yj)^2) + (zi-zj)^2 < sr }, as run + mask
+__global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
+    k_exact_runs(const double4* __restrict__ P0, RowMap M, const unsigned* __restrict__ srun,
+                 const int* __restrict__ srows, int scap, double sr, int ecap, uint2* __restrict__ erun,
+                 int* __restrict__ erows, int* __restrict__ ncount)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
+    int i, W;
+    bool work;
+    const bool valid = fj_row_thread(M, i, W, work);
+    if (!work)
+        return; /* warp-uniform */
+    const unsigned lane = threadIdx.x & 31u;
     const double4 a = P0[i];
-    const uint4* __restrict__ sp =
-        reinterpret_cast<const uint4*>(slist) + (size_t(i >> 5) * size_t(scap >> 2)) * 32u + (i & 31);
-    const size_t base = (size_t(i >> 5) * size_t(nb_cap >> 2)) * 32u + (i & 31);
-    uint4* __restrict__ dst = reinterpret_cast<uint4*>(nlist) + base;
-    double4* __restrict__ rdst = reinterpret_cast<double4*>(nr) + base;
-    const int sc = scount[i];
-    const int nchunk = (sc + 3) >> 2;
-    unsigned eb0 = unsigned(i), eb1 = unsigned(i), eb2 = unsigned(i), eb3 = unsigned(i);
-    double rb0 = 0.0, rb1 = 0.0, rb2 = 0.0, rb3 = 0.0;
-    unsigned freemask = 15u; /* free elements of the chunk being filled */
-    int cnt = 0;
-    auto test = [&](const unsigned ent, const double4 q, const bool valid) {
+    const int nrow = srows[W];
+    const unsigned* __restrict__ sp = srun + (size_t(W) * size_t(scap)) * 32u + lane;
+    uint2* __restrict__ dst = erun + (size_t(W) * size_t(ecap)) * 32u + lane;
+    int kk = 0, cnt = 0;
+    auto test = [&](const unsigned j, const double4 q, const bool ok) -> bool {
         // nanoflann metric_L2_Simple order, no fma contraction (bit-exact sets)
         const double ddx = __dsub_rn(a.x, q.x), ddy = __dsub_rn(a.y, q.y), ddz = __dsub_rn(a.z, q.z);
         const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz));
-        if (valid && d2 < sr)
-        {
-            const double rv = sqrt(d2); /* r = sqrt(jj.second), as every pair loop takes it */
-            const int kk = chunk_slot<COLS>(i & 31, ent, freemask);
-            if (kk == 0)
-            {
-                eb0 = ent;
-                rb0 = rv;
-            }
-            else if (kk == 1)
-            {
-                eb1 = ent;
-                rb1 = rv;
-            }
-            else if (kk == 2)
-            {
-                eb2 = ent;
-                rb2 = rv;
-            }
-            else
-            {
-                eb3 = ent;
-                rb3 = rv;
-            }
-            freemask &= ~(1u << kk);
-            if (freemask == 0u)
-            {
-                if (cnt < nb_cap)
-                {
-                    dst[size_t(cnt >> 2) * 32u] = make_uint4(eb0, eb1, eb2, eb3);
-                    rdst[size_t(cnt >> 2) * 32u] = make_double4(rb0, rb1, rb2, rb3);
-                }
-                freemask = 15u;
-            }
-            cnt++;
-        }
+        return ok && d2 < sr && int(j) != i;
     };
-    if (nchunk > 0)
+    unsigned d = (nrow > 0) ? sp[0] : FJ_RUN_EMPTY;
+    for (int k = 0; k < nrow; ++k)
     {
-        uint4 id = sp[0];
-        for (int c = 0; c < nchunk; ++c)
+        const unsigned dn = (k + 1 < nrow) ? sp[size_t(k + 1) * 32u] : FJ_RUN_EMPTY;
+        if (!valid)
+            d = FJ_RUN_EMPTY;
+        const unsigned start = d & FJ_IDX_MASK;
+        const int len = (d == FJ_RUN_EMPTY) ? 0 : int(d >> 27) + 1;
+        const int T = __reduce_max_sync(0xffffffffu, len);
+        unsigned mask = 0u;
+        for (int o = 0; o < T; o += 2)
         {
-            uint4 idn = id;
-            if (c + 1 < nchunk)
-                idn = sp[size_t(c + 1) * 32u];
-            /* four independent gathers in flight (unused slots of the last chunk hold i itself) */
-            const double4 q0 = ldg256(P0, id.x & FJ_IDX_MASK);
-            const double4 q1 = ldg256(P0, id.y & FJ_IDX_MASK);
-            const double4 q2 = ldg256(P0, id.z & FJ_IDX_MASK);
-            const double4 q3 = ldg256(P0, id.w & FJ_IDX_MASK);
-            const int left = sc - (c << 2);
-            test(id.x, q0, true);
-            test(id.y, q1, left > 1);
-            test(id.z, q2, left > 2);
-            test(id.w, q3, left > 3);
-            id = idn;
+            /* two independent gathers in flight; lanes past their window re-read their own record */
+            const bool ok0 = o < len, ok1 = o + 1 < len;
+            const unsigned j0 = ok0 ? start + unsigned(o) : unsigned(i), j1 = ok1 ? start + unsigned(o) + 1u : unsigned(i);
+            const double4 q0 = ldg256(P0, j0);
+            const double4 q1 = ldg256(P0, j1);
+            if (test(j0, q0, ok0))
+                mask |= 1u << o;
+            if (test(j1, q1, ok1))
+                mask |= 2u << o;
         }
+        if (__ballot_sync(0xffffffffu, mask != 0u))
+        {
+            const int tz = mask ? __ffs(int(mask)) - 1 : 0;
+            dst[size_t(kk) * 32u] = mask ? make_uint2(start + unsigned(tz), mask >> tz) : make_uint2(0u, 0u);
+            kk++;
+        }
+        cnt += __popc(mask);
+        d = dn;
     }
-    if ((cnt & 3) && cnt < nb_cap)
+    if (lane == 0)
+        erows[W] = kk;
+    if (valid)
+        ncount[i] = cnt;
+}
+
+// debug / parity view: the runs of every owned particle written out as caller indices (fjsph_get_neighbours)
+__global__ void k_runs_to_csr(RowMap M, const uint2* __restrict__ erun, const int* __restrict__ erows, int ecap,
+                              const int* __restrict__ oidx, const long long* __restrict__ offsets,
+                              long long* __restrict__ idx, int* __restrict__ bad)
+{
+    int i, W;
+    bool work;
+    const bool valid = fj_row_thread(M, i, W, work);
+    if (!work || !valid)
+        return;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint2* __restrict__ dp = erun + (size_t(W) * size_t(ecap)) * 32u + lane;
+    const int nrow = erows[W];
+    const int c = oidx[i];
+    long long* dst = idx + offsets[c];
+    const long long room = offsets[c + 1] - offsets[c];
+    long long t = 0;
+    for (int k = 0; k < nrow; ++k)
     {
-        /* partial last chunk: its entries move to the front (consumers read `left` elements); unused slots hold i itself
-           (safe to gather) and are never consumed */
-        unsigned v[4] = {eb0, eb1, eb2, eb3}, o[4] = {unsigned(i), unsigned(i), unsigned(i), unsigned(i)};
-        double vr[4] = {rb0, rb1, rb2, rb3}, orr[4] = {0.0, 0.0, 0.0, 0.0};
-        int k = 0;
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-            if (!((freemask >> m) & 1u))
+        const uint2 d = dp[size_t(k) * 32u];
+        for (unsigned m = d.y, o = 0; m; m >>= 1, ++o)
+            if (m & 1u)
             {
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (t == k)
-                    {
-                        o[t] = v[m];
-                        orr[t] = vr[m];
-                    }
-                k++;
+                if (t < room)
+                    dst[t] = oidx[d.x + o];
+                t++;
             }
-        dst[size_t(cnt >> 2) * 32u] = make_uint4(o[0], o[1], o[2], o[3]);
-        rdst[size_t(cnt >> 2) * 32u] = make_double4(orr[0], orr[1], orr[2], orr[3]);
     }
-    ncount[i] = cnt;
-    if (cnt > nb_cap)
-        atomicMax(flag, cnt);
+    if (t < room)
+        dst[t] = c;
+    t++;
+    if (t != room)
+        atomicExch(bad, 1);
 }
 
 int bits_for(int n)
@@ -448,6 +406,21 @@ int bits_for(int n)
 } // namespace
 
 // ------------------------------------------------------------------ host orchestration
+RowMap fj_row_map(const FjsphEngine* e, int first_class, int n_classes)
+{
+    RowMap M;
+    const unsigned n_rowkeys = 1u << (e->grid.by + e->grid.bz);
+    M.cell_start = e->cell_start;
+    M.warp_start = e->warp_start;
+    M.row0 = unsigned(first_class) * n_rowkeys;
+    M.n_rows = unsigned(n_classes) * n_rowkeys;
+    M.bx = e->grid.bx;
+    M.n_chunks = e->n_chunks;
+    return M;
+}
+unsigned fj_row_grid(const RowMap& M, int warps) { return (M.n_rows / unsigned(warps)) * unsigned(M.n_chunks); }
+int fj_owned_classes(const FjsphEngine* e) { return (e->slab.on && e->slab.world > 1) ? 2 : 1; }
+
 int fj_permute_levels(FjsphEngine* e)
 {
     const int n = int(e->n);
@@ -472,7 +445,7 @@ static int ensure_key_capacity(FjsphEngine* e, size_t n_keys)
         return FJSPH_OK;
     if (n_keys > (size_t(1) << 29))
     {
-        fj_set_error("cell table needs %zu keys (> 2^29): domain too sparse for the dense Morton table", n_keys);
+        fj_set_error("cell table needs %zu keys (> 2^29): domain too sparse for the dense cell table", n_keys);
         return FJSPH_ERR_CAPACITY;
     }
     if (e->cell_count)
@@ -491,35 +464,67 @@ static int ensure_key_capacity(FjsphEngine* e, size_t n_keys)
     return FJSPH_OK;
 }
 
-static int ensure_list_capacity(FjsphEngine* e, int nb_cap)
+static int ensure_row_capacity(FjsphEngine* e, size_t n_rows)
 {
-    const size_t words = size_t((e->cap + 31) / 32) * size_t(nb_cap) * 32u;
-    if (nb_cap <= e->nb_cap && words <= e->nlist_words)
+    if (n_rows <= e->row_cap)
         return FJSPH_OK;
-    if (e->nlist)
-        cudaFree(e->nlist);
-    if (e->nr)
-        cudaFree(e->nr);
-    e->nlist = nullptr;
-    e->nr = nullptr;
-    FJ_CUDA(cudaMalloc(&e->nlist, words * sizeof(unsigned)));
-    FJ_CUDA(cudaMalloc(&e->nr, words * sizeof(double)));
-    e->nlist_words = words;
-    e->nb_cap = nb_cap;
+    if (e->row_warps)
+        cudaFree(e->row_warps);
+    if (e->warp_start)
+        cudaFree(e->warp_start);
+    if (e->row_scan_tmp)
+        cudaFree(e->row_scan_tmp);
+    e->row_warps = e->warp_start = e->row_scan_tmp = nullptr;
+    e->row_cap = 0;
+    FJ_CUDA(cudaMalloc(&e->row_warps, (n_rows + 4) * sizeof(unsigned))); /* + the longest-row statistic behind the rows */
+    FJ_CUDA(cudaMalloc(&e->warp_start, (n_rows + 1) * sizeof(unsigned)));
+    FJ_CUDA(cudaMalloc(&e->row_scan_tmp, (n_rows / SCAN_TILE + 2) * sizeof(unsigned)));
+    e->row_cap = n_rows;
     return FJSPH_OK;
 }
 
-static int ensure_skin_capacity(FjsphEngine* e, int scap)
+// run arrays for n_warp work warps with scap skin slots (and as many exact slots) per warp; the per-warp partials of the
+// prestep's npd sum live in e->red, which grows with the warps
+static int ensure_run_capacity(FjsphEngine* e, size_t n_warp, int scap)
 {
-    const size_t words = size_t((e->cap + 31) / 32) * size_t(scap) * 32u;
-    if (scap <= e->scap && words <= e->slist_words)
-        return FJSPH_OK;
-    if (e->slist)
-        cudaFree(e->slist);
-    e->slist = nullptr;
-    FJ_CUDA(cudaMalloc(&e->slist, words * sizeof(unsigned)));
-    e->slist_words = words;
-    e->scap = scap;
+    if (n_warp > e->run_warps_cap || scap > e->scap)
+    {
+        for (void* p : {(void*)e->srun, (void*)e->erun, (void*)e->srows, (void*)e->erows})
+            if (p)
+                cudaFree(p);
+        e->srun = nullptr;
+        e->erun = nullptr;
+        e->srows = e->erows = nullptr;
+        e->run_warps_cap = 0;
+        e->scap = e->ecap = 0;
+        const size_t nw = std::max(n_warp + n_warp / 16 + 64, e->run_warps_cap);
+        const size_t slots = nw * size_t(scap) * 32u;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (slots * 12u + (64u << 20) > free_b)
+        {
+            fj_set_error("neighbour runs need %.1f GB (%zu work warps x %d row slots) but %.1f GB are free: rows too short "
+                         "for this layout (a sheet of particles across the row axis?)",
+                         slots * 12.0 / 1e9, nw, scap, free_b / 1e9);
+            return FJSPH_ERR_CAPACITY;
+        }
+        FJ_CUDA(cudaMalloc(&e->srun, slots * sizeof(unsigned)));
+        FJ_CUDA(cudaMalloc(&e->erun, slots * sizeof(uint2)));
+        FJ_CUDA(cudaMalloc(&e->srows, nw * sizeof(int)));
+        FJ_CUDA(cudaMalloc(&e->erows, nw * sizeof(int)));
+        e->run_warps_cap = nw;
+        e->scap = e->ecap = scap;
+    }
+    if (n_warp + 16 > e->red_cap)
+    {
+        if (e->red)
+            cudaFree(e->red);
+        e->red = nullptr;
+        e->red_cap = 0;
+        const size_t want = n_warp + n_warp / 16 + 1024;
+        FJ_CUDA(cudaMalloc(&e->red, want * sizeof(double)));
+        e->red_cap = want;
+    }
     return FJSPH_OK;
 }
 
@@ -535,15 +540,29 @@ static int rebuild_skin(FjsphEngine* e)
             fj_set_error("build_neighbours: non-finite particle positions");
             return FJSPH_ERR_STATE;
         }
-    // grid: cell edge along x a hair above the skin radius 2H + skin so +-1 cell always covers it.  Pencil order
-    // narrows the cells along y and z to about one particle spacing (and visits +-ry, +-rz of them), with the origin half
-    // a cell below the lowest particle so that the rows of a lattice-born fluid sit in the middle of their pencils.
+    // Row axis u = the longest extent (long rows fill their 32-lane chunks; FJSPH_B200_ROW_AXIS = 0|1|2 pins it).  Cell
+    // edge along u a hair above the skin radius 2H + skin, so +-1 cell always covers it; along v and w about one
+    // particle spacing (visiting +-ry, +-rz rows), with the origin half a cell below the lowest particle so that the
+    // rows of a lattice-born fluid sit in the middle of their pencils.
     Grid g;
+    int ax0 = 0;
+    for (int d = 1; d < 3; ++d)
+        if (hi[d] - lo[d] > 1.0001 * (hi[ax0] - lo[ax0]))
+            ax0 = d;
+    if (e->row_axis >= 0 && e->row_axis < 3)
+        ax0 = e->row_axis;
+    g.ax0 = ax0;
+    g.ax1 = (ax0 + 1) % 3;
+    g.ax2 = (ax0 + 2) % 3;
+    if (g.ax1 > g.ax2)
+        std::swap(g.ax1, g.ax2);
     const double r_skin = std::sqrt(e->P.sr) + e->skin;
     const double cell = r_skin * (1.0 + 1e-7);
     double pw = cell;
-    if (e->pencil_order && e->P.particle_step > 0.0)
+    if (e->P.particle_step > 0.0)
         pw = std::min(cell, std::max(e->P.particle_step, cell / 8.0));
+    if (e->row_width_cells > 0.0)
+        pw = std::min(cell, std::max(e->row_width_cells * e->P.particle_step, cell / 8.0));
     for (;;)
     {
         const bool narrow = pw < cell;
@@ -552,17 +571,17 @@ static int rebuild_skin(FjsphEngine* e)
         g.pw2 = pw * pw;
         g.r_skin2 = r_skin * r_skin;
         g.ry = g.rz = narrow ? int(std::ceil(cell / pw)) : 1;
-        g.ox = lo[0];
-        g.oy = lo[1] - (narrow ? 0.5 * pw : 0.0);
-        g.oz = lo[2] - (narrow ? 0.5 * pw : 0.0);
-        g.nx = int(std::floor((hi[0] - g.ox) * g.inv_cell)) + 1;
-        g.ny = int(std::floor((hi[1] - g.oy) * g.inv_cy)) + 1;
-        g.nz = int(std::floor((hi[2] - g.oz) * g.inv_cz)) + 1;
+        g.ox = lo[g.ax0];
+        g.oy = lo[g.ax1] - (narrow ? 0.5 * pw : 0.0);
+        g.oz = lo[g.ax2] - (narrow ? 0.5 * pw : 0.0);
+        g.nx = int(std::floor((hi[g.ax0] - g.ox) * g.inv_cell)) + 1;
+        g.ny = int(std::floor((hi[g.ax1] - g.oy) * g.inv_cy)) + 1;
+        g.nz = int(std::floor((hi[g.ax2] - g.oz) * g.inv_cz)) + 1;
         g.bx = bits_for(g.nx);
-        g.by = bits_for(g.ny);
-        g.bz = bits_for(g.nz);
-        /* the key tables (count + start per class) stay below ~1 GB: wider pencils for very large cross-sections */
-        if (!narrow || g.bx + g.by + g.bz <= 25)
+        g.by = std::max(2, bits_for(g.ny)); /* at least 4 x 4 rows: a sweep CTA holds FJ_ROW_WARPS adjacent rows */
+        g.bz = std::max(2, bits_for(g.nz));
+        /* the key tables (count + start per class) stay below ~1 GB: wider rows for very large cross-sections */
+        if (!narrow || g.bx + g.by + g.bz <= e->max_key_bits)
             break;
         pw = std::min(cell, 2.0 * pw);
     }
@@ -582,46 +601,38 @@ static int rebuild_skin(FjsphEngine* e)
     int st = ensure_key_capacity(e, n_tab);
     if (st)
         return st;
-    // key tables, one per axis, OR-ed together: lexicographic fields (pencil order) or Morton spreading (bit l of each
-    // axis placed round-robin x,y,z among the axes that still have bits)
+    // key = row bits << bx | u-cell.  Row-id bit order: v0, w0, v1, w1 (the FJ_ROW_WARPS rows of a sweep CTA are the 4 x 2
+    // block of adjacent rows under the lowest three), then v2-4, w2-4 (consecutive CTAs stay inside a 32 x 32 block of
+    // rows, whose records L2 keeps), then the rest of v and of w.
     {
-        const int need = std::max(g.nx, std::max(g.ny, g.nz));
+        const int need = std::max(g.ny, g.nz);
         if (need > e->mtab_cap)
         {
-            if (e->mtab_x)
-                cudaFree(e->mtab_x);
+            if (e->mtab_y)
+                cudaFree(e->mtab_y);
             int cap = 64;
             while (cap < need) cap <<= 1;
-            FJ_CUDA(cudaMalloc(&e->mtab_x, size_t(3) * cap * sizeof(unsigned)));
-            e->mtab_y = e->mtab_x + cap;
+            FJ_CUDA(cudaMalloc(&e->mtab_y, size_t(2) * cap * sizeof(unsigned)));
             e->mtab_z = e->mtab_y + cap;
             e->mtab_cap = cap;
         }
-        int pos[3][32];
-        int out = 0;
-        const int bits[3] = {g.bx, g.by, g.bz};
-        if (e->pencil_order)
-        {
-            /* x in the low bits, then y, then z -- consecutive keys run along x.  With tiles (pencil_tile_y > 0) the
-               lowest TX bits of x come first, then the lowest TY bits of y, then the rest of x: memory then runs through
-               ~one warp's worth of a pencil (2^TX cells), then through the same stretch of the next pencil, ..., so the
-               warps of a block sit in ADJACENT pencils and walk nearly the same neighbour rows one row apart -- what
-               one warp pulls into L1 the next one finds there. */
-            const int tx = std::min(e->pencil_tile_x, bits[0]), ty = std::min(e->pencil_tile_y, bits[1]);
-            for (int l = 0; l < tx; ++l) pos[0][l] = out++;
-            for (int l = 0; l < ty; ++l) pos[1][l] = out++;
-            for (int l = tx; l < bits[0]; ++l) pos[0][l] = out++;
-            for (int l = ty; l < bits[1]; ++l) pos[1][l] = out++;
-            for (int l = 0; l < bits[2]; ++l) pos[2][l] = out++;
-        }
-        else
-            for (int l = 0; l < 32; ++l)
-                for (int a = 0; a < 3; ++a)
-                    if (l < bits[a])
-                        pos[a][l] = out++;
-        std::vector<unsigned> tab(size_t(3) * e->mtab_cap, 0u);
-        const int dims[3] = {g.nx, g.ny, g.nz};
-        for (int a = 0; a < 3; ++a)
+        int pos[2][32];
+        int out = g.bx;
+        const int bits[2] = {g.by, g.bz};
+        auto take = [&](int a, int l0, int l1) {
+            for (int l = l0; l < std::min(l1, bits[a]); ++l) pos[a][l] = out++;
+        };
+        take(0, 0, 1);
+        take(1, 0, 1);
+        take(0, 1, 2);
+        take(1, 1, 2);
+        take(0, 2, 5);
+        take(1, 2, 5);
+        take(0, 5, 32);
+        take(1, 5, 32);
+        std::vector<unsigned> tab(size_t(2) * e->mtab_cap, 0u);
+        const int dims[2] = {g.ny, g.nz};
+        for (int a = 0; a < 2; ++a)
             for (int c = 0; c < dims[a]; ++c)
             {
                 unsigned v = 0;
@@ -630,9 +641,24 @@ static int rebuild_skin(FjsphEngine* e)
                         v |= 1u << pos[a][l];
                 tab[size_t(a) * e->mtab_cap + c] = v;
             }
-        FJ_CUDA(cudaMemcpyAsync(e->mtab_x, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice,
+        FJ_CUDA(cudaMemcpyAsync(e->mtab_y, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice,
                                 e->stream));
-        FJ_CUDA(cudaStreamSynchronize(e->stream)); // tab is a stack-lifetime buffer
+        // neighbouring rows inside the disc of radius 2H + skin, ascending w then v: a row whose cross-section lies
+        // wholly outside the disc holds nobody
+        std::vector<int2> offs;
+        for (int dz = -g.rz; dz <= g.rz; ++dz)
+            for (int dy = -g.ry; dy <= g.ry; ++dy)
+            {
+                const int gy = std::max(std::abs(dy) - 1, 0), gz = std::max(std::abs(dz) - 1, 0);
+                if (double(gy * gy + gz * gz) * g.pw2 > g.r_skin2)
+                    continue;
+                offs.push_back(make_int2(dy, dz));
+            }
+        if (!e->row_off)
+            FJ_CUDA(cudaMalloc(&e->row_off, size_t(17 * 17) * sizeof(int2)));
+        e->n_row_off = int(offs.size());
+        FJ_CUDA(cudaMemcpyAsync(e->row_off, offs.data(), offs.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+        FJ_CUDA(cudaStreamSynchronize(e->stream)); // tab and offs are stack-lifetime buffers
     }
     e->grid = g;
 
@@ -641,12 +667,12 @@ static int rebuild_skin(FjsphEngine* e)
     {
         KScope ks(e, "nb_sort", 7);
         FJ_CUDA(cudaMemsetAsync(e->cell_count, 0, size_t(n_tab) * sizeof(unsigned), e->stream));
-        k_key_hist<<<nb, TPB, 0, e->stream>>>(S.P0, n, int(e->n_owned), g, e->mtab_x, e->mtab_y, e->mtab_z, e->key, e->rank_in_cell,
+        k_key_hist<<<nb, TPB, 0, e->stream>>>(S.P0, n, int(e->n_owned), g, e->mtab_y, e->mtab_z, e->key, e->rank_in_cell,
                                               e->cell_count, n_class, x_edge_lo, x_edge_hi);
         prim_exclusive_scan(e->stream, e->cell_count, e->cell_start, n_tab, e->scan_tmp);
         k_scatter<<<nb, TPB, 0, e->stream>>>(e->key, e->rank_in_cell, e->cell_start, n, e->perm2);
         k_cell_order<<<fj_blocks(int64_t(n_tab) * 32, TPB), TPB, 0, e->stream>>>(e->cell_start, n_tab, e->perm2, e->oidx,
-                                                                                 e->perm);
+                                                                                 S.P0, g.ax0, e->perm);
     }
     FJ_CUDA(cudaGetLastError());
 
@@ -655,37 +681,52 @@ static int rebuild_skin(FjsphEngine* e)
     if (st)
         return st;
 
-    // skin list (retry with a larger per-particle capacity on overflow)
-    if (e->scap == 0)
+    // work warps: 32-particle chunks of the owned rows
+    const unsigned n_rowkeys = 1u << (g.by + g.bz);
+    const unsigned n_rows = unsigned(n_class) * n_rowkeys, n_owned_rows = unsigned(three ? 2 : 1) * n_rowkeys;
+    st = ensure_row_capacity(e, n_rows);
+    if (st)
+        return st;
     {
-        /* expected count N_nb (1 + skin/2H)^3 with N_nb ~ 270, plus headroom */
-        const double f = r_skin / std::sqrt(e->P.sr);
-        const int want = ((int(300.0 * f * f * f) + 31) / 32) * 32;
-        st = ensure_skin_capacity(e, want);
-        if (st)
-            return st;
+        KScope ks(e, "nb_sort", 4);
+        unsigned* stats = e->row_warps + n_rows;
+        FJ_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned), e->stream));
+        k_row_warps<<<fj_blocks(n_rows, TPB), TPB, 0, e->stream>>>(e->cell_start, g.bx, n_rows, n_owned_rows, e->row_warps,
+                                                                   stats);
+        prim_exclusive_scan(e->stream, e->row_warps, e->warp_start, n_rows, e->row_scan_tmp);
+        FJ_CUDA(cudaMemcpyAsync(e->h_flag + 1, e->warp_start + n_rows, sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+        FJ_CUDA(cudaMemcpyAsync(e->h_flag + 3, stats, sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+        if (three) /* first slot of the edge class = number of interior particles */
+            FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->cell_start + g.n_keys, sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
     }
+    FJ_CUDA(cudaGetLastError());
+    FJ_CUDA(cudaStreamSynchronize(e->stream));
+    e->n_warp = unsigned(e->h_flag[1]);
+    e->n_chunks = std::max(1, (e->h_flag[3] + 31) / 32);
+    e->slab.n_interior = three ? int64_t(e->h_flag[0]) : 0;
+
+    // skin runs (retry with more row slots per warp on overflow)
+    {
+        KScope ks(e, "nb_skin", 1);
+        k_snapshot<<<nb, TPB, 0, e->stream>>>(S.P0, e->xref, n);
+    }
+    int scap = std::max(e->scap, e->n_row_off + (n_class > 1 ? 40 : 4));
     for (int attempt = 0; attempt < 4; ++attempt)
     {
+        st = ensure_run_capacity(e, e->n_warp, scap);
+        if (st)
+            return st;
         FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
+        const RowMap M = fj_row_map(e, 0, three ? 2 : 1);
         {
             KScope ks(e, "nb_skin", 1);
-            if (e->column_order) /* column_order_chunk above */
-                k_build_skin<true><<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, int(e->n_owned), g, e->mtab_x, e->mtab_y,
-                                                              e->mtab_z, e->cell_start, r_skin * r_skin, e->scap, e->slist,
-                                                              e->scount, e->xref, e->d_flag, n_class);
-            else
-                k_build_skin<false><<<nb, TPB, 0, e->stream>>>(e->lv[1].P0, e->lv[1].b, n, int(e->n_owned), g, e->mtab_x, e->mtab_y,
-                                                               e->mtab_z, e->cell_start, r_skin * r_skin, e->scap, e->slist,
-                                                               e->scount, e->xref, e->d_flag, n_class);
+            k_build_skin_runs<<<fj_row_grid(M), FJ_ROW_WARPS * 32, 0, e->stream>>>(
+                S.P0, M, g, e->mtab_y, e->mtab_z, e->row_off, e->n_row_off, n_class, r_skin * r_skin, e->scap, e->srun,
+                e->srows, e->d_flag);
         }
         FJ_CUDA(cudaGetLastError());
         FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-        if (three) /* first slot of the edge class = number of interior particles */
-            FJ_CUDA(cudaMemcpyAsync(e->h_flag + 1, e->cell_start + g.n_keys, sizeof(unsigned), cudaMemcpyDeviceToHost,
-                                    e->stream));
         FJ_CUDA(cudaStreamSynchronize(e->stream));
-        e->slab.n_interior = three ? int64_t(e->h_flag[1]) & ~int64_t(31) : 0;
         if (e->h_flag[0] == 0)
         {
             e->skin_valid = true;
@@ -693,11 +734,9 @@ static int rebuild_skin(FjsphEngine* e)
             e->skin_builds++;
             return FJSPH_OK;
         }
-        st = ensure_skin_capacity(e, ((e->h_flag[0] + 31) / 32) * 32 + 32);
-        if (st)
-            return st;
+        scap = e->h_flag[0] + 8;
     }
-    fj_set_error("skin list capacity could not be satisfied");
+    fj_set_error("skin run capacity could not be satisfied");
     return FJSPH_ERR_CAPACITY;
 }
 
@@ -769,41 +808,28 @@ int fj_build_neighbours(FjsphEngine* e)
             return st;
     }
 
-    // 2. exact list (retry with a larger per-particle capacity on overflow)
-    if (e->nb_cap == 0)
+    // 2. exact runs, and the positions they were built on (every pair loop takes r from them: frozen pair distances)
     {
-        int st = ensure_list_capacity(e, 288);
-        if (st)
-            return st;
+        KScope ks(e, "nb_list", 2);
+        const RowMap M = fj_row_map(e, 0, fj_owned_classes(e));
+        k_exact_runs<<<fj_row_grid(M), FJ_ROW_WARPS * 32, 0, e->stream>>>(e->lv[1].P0, M, e->srun, e->srows, e->scap, e->P.sr,
+                                                                         e->ecap, e->erun, e->erows, e->ncount);
+        k_snapshot<<<fj_blocks(int(e->n), TPB), TPB, 0, e->stream>>>(e->lv[1].P0, e->x0, int(e->n));
     }
-    for (int attempt = 0; attempt < 4; ++attempt)
-    {
-        FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
-        {
-            KScope ks(e, "nb_list", 1);
-            if (e->column_order)
-                k_exact_from_skin<true><<<fj_blocks(e->n_owned, TPB), TPB, 0, e->stream>>>(
-                    e->lv[1].P0, int(e->n_owned), e->slist, e->scount, e->scap, e->P.sr, e->nb_cap, e->nlist, e->nr, e->ncount,
-                    e->d_flag);
-            else
-                k_exact_from_skin<false><<<fj_blocks(e->n_owned, TPB), TPB, 0, e->stream>>>(
-                    e->lv[1].P0, int(e->n_owned), e->slist, e->scount, e->scap, e->P.sr, e->nb_cap, e->nlist, e->nr, e->ncount,
-                    e->d_flag);
-        }
-        FJ_CUDA(cudaGetLastError());
-        FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-        FJ_CUDA(cudaStreamSynchronize(e->stream));
-        if (e->h_flag[0] == 0)
-        {
-            e->list_valid = true;
-            e->nb_builds++;
-            return FJSPH_OK;
-        }
-        const int want = ((e->h_flag[0] + 31) / 32) * 32 + 32;
-        int st = ensure_list_capacity(e, want);
-        if (st)
-            return st;
-    }
-    fj_set_error("neighbour list capacity could not be satisfied");
-    return FJSPH_ERR_CAPACITY;
+    FJ_CUDA(cudaGetLastError());
+    e->x_moved = false;
+    e->list_valid = true;
+    e->nb_builds++;
+    return FJSPH_OK;
+}
+
+// debug / parity view of the exact list (fjsph_get_neighbours): d_offsets = exclusive prefix sum of count + 1 over
+// caller indices, d_idx receives the caller indices of the neighbours and of the particle itself (unsorted)
+int fj_neighbours_to_csr(FjsphEngine* e, const long long* d_offsets, long long* d_idx, int* d_bad)
+{
+    const RowMap M = fj_row_map(e, 0, fj_owned_classes(e));
+    k_runs_to_csr<<<fj_row_grid(M), FJ_ROW_WARPS * 32, 0, e->stream>>>(M, e->erun, e->erows, e->ecap, e->oidx, d_offsets,
+                                                                       d_idx, d_bad);
+    FJ_CUDA(cudaGetLastError());
+    return FJSPH_OK;
 }

@@ -1,5 +1,7 @@
-// sweeps.cu — the FP64 pair sweeps of the WCSPH step (one thread per particle, neighbour slots read
-// with one coalesced 128-byte load per warp, neighbour records gathered as 32-byte sectors through L1).
+// sweeps.cu — the FP64 pair sweeps of the WCSPH step.  One thread per particle; a warp is 32 consecutive particles of
+// one ROW (neighbours.cu) and walks the run lists row by row, so at every step its lanes gather 32 (nearly) consecutive
+// neighbour records: coalesced 256-bit loads instead of 32 scattered sectors.  The warps of a CTA sit in adjacent rows
+// over the same stretch of the row axis and share those records through L1.
 //
 // Replaces, with results within 1e-10 (normwise) of the CPU oracle:
 //   dSPH_PreStep        reference src/Shifting.cpp:12-123
@@ -12,6 +14,7 @@
 //
 // Sweep fusion: prestep | surface loop 1 + dissipation | surface loops 2+3 | shifting | force.
 #include <cmath>
+#include <type_traits>
 
 #include "engine.cuh"
 #include "small_matrix.cuh"
@@ -19,38 +22,34 @@
 namespace
 {
 
-#ifndef FJ_SWEEP_TPB
-#define FJ_SWEEP_TPB 128
-#endif
-constexpr int TPB = FJ_SWEEP_TPB;
+// CTA shapes of the pair sweeps: WARPS rows per CTA; resident CTAs per SM chosen so that the heaviest instantiation
+// keeps its registers (8 warps x 1 CTA: up to 255; 4 warps x 3 CTAs: up to 168; the lean bulk sweep twice that)
+constexpr int min_blocks(int warps, bool lean) { return warps == 8 ? (lean ? 2 : 1) : (lean ? 4 : 3); }
 #define FJ_PI 3.14159265358979323846
+#define FJ_FULL 0xffffffffu
 
-struct ListView
+struct RunView
 {
-    const unsigned* __restrict__ nlist;
-    const double* __restrict__ nr;
+    const uint2* __restrict__ erun;
+    const int* __restrict__ erows;
     const int* __restrict__ ncount;
-    int nb_cap;
+    const double4* __restrict__ x0;
+    int ecap;
 };
 
 // The reference carries d^2 in the neighbour list (OUTL = vector<vector<pair<idx, dist2>>>, Var.h:889-890) and
 // every pair loop reads r = sqrt(jj.second) from it, so r stays FROZEN at its list-build value while
-// Rji = xj - xi follows the positions through the Newmark-Beta sub-iterations / RK stages.  The list
-// therefore stores r next to the index, in chunks of 4 slots per lane (engine.cuh).
-__device__ __forceinline__ uint4 ld_list_idx(const uint4* p)
+// Rji = xj - xi follows the positions through the Newmark-Beta sub-iterations / RK stages.  The run lists store no
+// per-pair value: a sweep that runs on the positions the list was built on (FROZEN = false: prestep, surface,
+// shifting, the first force evaluation after a build) takes r from the positions it gathers anyway; once the
+// particles have moved (FROZEN = true) it gathers the build-time positions x0 as well and takes r from those.
+__device__ __forceinline__ uint2 ld_desc(const uint2* p)
 {
-    uint4 v;
-    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    uint2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
-__device__ __forceinline__ double4 ld_list_r(const double4* p)
-{
-    double4 v;
-    asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
-    return v;
-}
-// 32-byte record gather with ONE 256-bit load (LDG.E.256): half the L1 wavefronts of two 128-bit loads.
-// Only for arrays no thread writes during the kernel (read-only path).
+// 32-byte record gather with ONE 256-bit load (LDG.E.256).  Only for arrays no thread writes during the kernel.
 __device__ __forceinline__ double4 gather(const double4* __restrict__ base, unsigned j)
 {
     double4 v;
@@ -65,94 +64,88 @@ __device__ __forceinline__ double4 gather_rw(const double4* base, unsigned j)
     return v;
 }
 
-template <class Body>
-__device__ __forceinline__ void for_neighbours(const ListView& lv, int i, Body&& body)
+// Walks the runs of work warp W in lockstep: slot k holds, for every lane, the window {first, mask} of its neighbours
+// inside one neighbouring row; the warp steps o = 0 .. T-1 (T = the longest window of the slot) and lane l visits
+// neighbour first_l + o when bit o of its mask is set.  load(j, take) issues the record gathers of one neighbour (and
+// returns them; nothing is loaded when !take), body(j, rec) consumes them.  Software-pipelined: the gathers of step
+// s+1 are issued before the arithmetic of step s, the next slot's descriptors one slot ahead.  Every lane of the warp
+// must call this (the trip counts are warp votes); lanes with active == false visit nobody.
+template <class Load, class Body>
+__device__ __forceinline__ void for_neighbours(const RunView& L, int W, bool active, Load&& load, Body&& body)
 {
-    const size_t base = (size_t(i >> 5) * size_t(lv.nb_cap >> 2)) * 32u + (i & 31);
-    const uint4* __restrict__ lp = reinterpret_cast<const uint4*>(lv.nlist) + base;
-    const double4* __restrict__ rp = reinterpret_cast<const double4*>(lv.nr) + base;
-    const int cnt = lv.ncount[i];
-    const int nchunk = (cnt + 3) >> 2;
-    if (nchunk == 0)
+    const int nrow = L.erows[W];
+    const uint2* __restrict__ dp = L.erun + (size_t(W) * size_t(L.ecap)) * 32u + (threadIdx.x & 31u);
+    int k = 0, T = 0, o = 0;
+    uint2 d = make_uint2(0u, 0u), dn = make_uint2(0u, 0u);
+    if (nrow > 0)
+        dn = ld_desc(dp);
+    /* next slot with somebody in it: false at the end of the list (warp-uniform) */
+    auto next_slot = [&]() -> bool {
+        while (k < nrow)
+        {
+            d = dn;
+            if (!active)
+                d.y = 0u;
+            ++k;
+            if (k < nrow)
+                dn = ld_desc(dp + size_t(k) * 32u);
+            T = __reduce_max_sync(FJ_FULL, 32 - __clz(int(d.y)));
+            if (T > 0)
+                return true;
+        }
+        return false;
+    };
+    if (!next_slot())
         return;
-    uint4 id = ld_list_idx(lp);
-    double4 rr = ld_list_r(rp);
-    for (int c = 0; c < nchunk; ++c)
+    unsigned ja = d.x;
+    bool va = (d.y & 1u) != 0u;
+    auto ra = load(ja, va);
+    for (;;)
     {
-        /* next chunk in flight while this one is processed (the list streams from HBM) */
-        uint4 idn = id;
-        double4 rn = rr;
-        if (c + 1 < nchunk)
+        /* step B is prepared while A is consumed, and the other way round (two register sets, no moves) */
+        bool more = true;
+        if (++o >= T)
         {
-            idn = ld_list_idx(lp + size_t(c + 1) * 32u);
-            rn = ld_list_r(rp + size_t(c + 1) * 32u);
+            more = next_slot();
+            o = 0;
         }
-        const int left = cnt - (c << 2);
-        if (left >= 4)
+        const unsigned jb = d.x + unsigned(o);
+        const bool vb = more && ((d.y >> o) & 1u) != 0u;
+        auto rb = load(jb, vb);
+        if (va)
+            body(ja, ra);
+        if (!more)
+            break;
+        more = true;
+        if (++o >= T)
         {
-            body(id.x, rr.x);
-            body(id.y, rr.y);
-            body(id.z, rr.z);
-            body(id.w, rr.w);
+            more = next_slot();
+            o = 0;
         }
-        else
-        {
-            body(id.x, rr.x);
-            if (left > 1)
-                body(id.y, rr.y);
-            if (left > 2)
-                body(id.z, rr.z);
-        }
-        id = idn;
-        rr = rn;
+        ja = d.x + unsigned(o);
+        va = more && ((d.y >> o) & 1u) != 0u;
+        ra = load(ja, va);
+        if (vb)
+            body(jb, rb);
+        if (!more)
+            break;
     }
 }
-#define FJ_NEIGHBOURS_BEGIN(i, LV, ent, j, r)                          \
-    for_neighbours(LV, i, [&](const unsigned ent, const double r) {    \
-        const unsigned j = ent & FJ_IDX_MASK;
-#define FJ_NEIGHBOURS_END });
 
-// Software-pipelined form for the hot sweeps: load(ent) issues the record gathers of one neighbour and
-// returns them; body(ent, r, rec) consumes them.  The gathers of neighbour k+1 are issued before the
-// arithmetic of neighbour k, and the next list chunk one chunk ahead, so every warp always has one
-// neighbour's records and one chunk of the list in flight behind its FP64 work.  Unused slots of the
-// last chunk hold the particle's own index (safe to gather, never consumed).
-template <class Load, class Body>
-__device__ __forceinline__ void for_neighbours_pipelined(const ListView& lv, int i, Load&& load, Body&& body)
+// plain form for the wall treatments (few particles, short bodies): body(j)
+template <class Body>
+__device__ __forceinline__ void for_neighbours_simple(const RunView& L, int W, bool active, Body&& body)
 {
-    const size_t base = (size_t(i >> 5) * size_t(lv.nb_cap >> 2)) * 32u + (i & 31);
-    const uint4* __restrict__ lp = reinterpret_cast<const uint4*>(lv.nlist) + base;
-    const double4* __restrict__ rp = reinterpret_cast<const double4*>(lv.nr) + base;
-    const int cnt = lv.ncount[i];
-    const int nchunk = (cnt + 3) >> 2;
-    if (nchunk == 0)
+    const int nrow = L.erows[W];
+    const uint2* __restrict__ dp = L.erun + (size_t(W) * size_t(L.ecap)) * 32u + (threadIdx.x & 31u);
+    if (!active)
         return;
-    uint4 id = ld_list_idx(lp);
-    double4 rr = ld_list_r(rp);
-    auto cur = load(id.x);
-    for (int c = 0; c < nchunk; ++c)
+    for (int k = 0; k < nrow; ++k)
     {
-        uint4 idn = id;
-        double4 rn = rr;
-        if (c + 1 < nchunk)
-        {
-            idn = ld_list_idx(lp + size_t(c + 1) * 32u);
-            rn = ld_list_r(rp + size_t(c + 1) * 32u);
-        }
-        const int left = cnt - (c << 2);
-        auto nx = load(id.y);
-        body(id.x, rr.x, cur);
-        cur = load(id.z);
-        if (left > 1)
-            body(id.y, rr.y, nx);
-        nx = load(id.w);
-        if (left > 2)
-            body(id.z, rr.z, cur);
-        cur = load(idn.x);
-        if (left > 3)
-            body(id.w, rr.w, nx);
-        id = idn;
-        rr = rn;
+        const uint2 d = dp[size_t(k) * 32u];
+        for (unsigned m = d.y, j = d.x; m; m >>= 1, ++j)
+            if (m & 1u)
+                body(j);
     }
 }
 
@@ -179,6 +172,26 @@ __device__ __forceinline__ double fj_rsqrt(double x)
     return fma(y, e, y);
 }
 
+// r of a pair the way the reference takes it -- sqrt of the list's d^2, the distance at the list build -- with 1 / r
+// beside it: from the current separation when the particles have not moved since (FROZEN = false), else from the
+// build-time positions x0.  rr = d^2, r = d^2 * rsqrt(d^2) (~1 ulp; coincident particles give r = 0, not NaN);
+// r2c = |Rji|^2 of the CURRENT positions, which is what Rji . gradK carries (Kernel.h:262-269, Shifting.cpp:160-176).
+template <bool FROZEN>
+__device__ __forceinline__ void pair_dist(const double4& x0i, const double4& x0j, double rx, double ry, double rz,
+                                          double& rr, double& ir, double& r, double& r2c)
+{
+    r2c = fma(rz, rz, fma(ry, ry, rx * rx));
+    if (FROZEN)
+    {
+        const double ex = x0j.x - x0i.x, ey = x0j.y - x0i.y, ez = x0j.z - x0i.z;
+        rr = fma(ez, ez, fma(ey, ey, ex * ex));
+    }
+    else
+        rr = r2c;
+    ir = fj_rsqrt(fmax(rr, 1e-300));
+    r = rr * ir;
+}
+
 // Wendland C2 (Kernel.h:37-61).  t = 1 - q/2.  W = t^4 (2q+1) Wc ; GradK(R, r) = R * gk with
 // gk = 5 Wc/H^2 * t^3, and 0 when r/H < 1e-12.
 __device__ __forceinline__ double wend_t(const DevConst& C, double r) { return 1.0 - 0.5 * r * C.iH; }
@@ -192,57 +205,59 @@ __device__ __forceinline__ double wend_gk(const DevConst& C, double r, double t)
     return (r * C.iH < 1e-12) ? 0.0 : C.gk_fac * (t * t * t);
 }
 
-__device__ __forceinline__ double block_sum(double v, double* sm)
+__device__ __forceinline__ double warp_sum(double v)
 {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0)
-        sm[w] = v;
-    __syncthreads();
-    double r = 0.0;
-    if (threadIdx.x == 0)
-        for (int k = 0; k < (int(blockDim.x) >> 5); ++k) r += sm[k];
-    __syncthreads();
-    return r;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FJ_FULL, v, o);
+    return v;
 }
 
 // ================================================================= dSPH_PreStep
 struct RecPre
 {
-    double4 p;
+    double4 p, x0;
     double rho;
+    int b;
 };
 
-#ifndef FJ_PRESTEP_MINBLOCKS
-#define FJ_PRESTEP_MINBLOCKS 3
-#endif
-__global__ void __launch_bounds__(TPB, FJ_PRESTEP_MINBLOCKS)
-    k_prestep(Level S, ListView lv, DevConst C, int n, double* __restrict__ npd_partial)
+// npd_partial[W]: one partial per work warp (summed in a fixed order by fj_reduce_sum)
+template <bool FROZEN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
+    k_prestep(Level S, RunView lv, RowMap M, DevConst C, double* __restrict__ npd_partial)
 {
-    __shared__ double sm[TPB / 32];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i, W;
+    bool work;
+    const bool active = fj_row_thread<WARPS>(M, i, W, work);
+    if (!work)
+        return; /* warp-uniform */
     double npd_ = 0.0;
-    if (i < n)
     {
         const double4 pi = S.P0[i];
+        const double4 x0i = FROZEN ? lv.x0[i] : pi;
         const double rho_i = S.P1[i].w;
         double l00 = 0, l01 = 0, l02 = 0, l11 = 0, l12 = 0, l22 = 0;
         double n00 = 0, n01 = 0, n02 = 0, n11 = 0, n12 = 0, n22 = 0;
         double g0 = 0, g1 = 0, g2 = 0, m0 = 0, m1 = 0, m2 = 0;
         double kernsum = C.W_correc; /* self term, Shifting.cpp:39-45 */
         double colour = 0.0;
-        for_neighbours_pipelined(
-            lv, i,
-            [&](const unsigned ent) {
-                const unsigned j = ent & FJ_IDX_MASK;
+        for_neighbours(
+            lv, W, active,
+            [&](const unsigned j, const bool take) {
                 RecPre q;
-                q.p = gather(S.P0, j);
-                q.rho = __ldg(&S.P1[j].w);
+                if (take)
+                {
+                    q.p = gather(S.P0, j);
+                    q.rho = __ldg(&S.P1[j].w);
+                    q.b = __ldg(&S.b[j]);
+                    if (FROZEN)
+                        q.x0 = gather(lv.x0, j);
+                }
                 return q;
             },
-            [&](const unsigned ent, const double r, const RecPre& q) {
+            [&](const unsigned j, const RecPre& q) {
                 const double4 pj = q.p;
                 const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+                double rr, ir, r, r2c;
+                pair_dist<FROZEN>(x0i, q.x0, rx, ry, rz, rr, ir, r, r2c);
                 const double t = wend_t(C, r);
                 const double vg = pj.w * wend_gk(C, r, t); /* V_j * gk ; Grad = GradK(-Rji) = -Rji*gk */
                 const double ax = vg * rx, ay = vg * ry, az = vg * rz;
@@ -257,7 +272,7 @@ __global__ void __launch_bounds__(TPB, FJ_PRESTEP_MINBLOCKS)
                 g0 -= dr * ax;
                 g1 -= dr * ay;
                 g2 -= dr * az;
-                if (ent & FJ_NB_FLUID)
+                if (q.b > FJSPH_PISTON)
                 {
                     n00 += ax * rx;
                     n01 += ax * ry;
@@ -268,12 +283,14 @@ __global__ void __launch_bounds__(TPB, FJ_PRESTEP_MINBLOCKS)
                     m0 -= ax;
                     m1 -= ay;
                     m2 -= az;
-                    const double W = wend_W(C, r, t);
-                    kernsum += W;
-                    colour += pj.w * W;
-                    npd_ += W;
+                    const double W_ = wend_W(C, r, t);
+                    kernsum += W_;
+                    colour += pj.w * W_;
+                    npd_ += W_;
                 }
             });
+        if (active)
+        {
         double Lm[3][3] = {{l00, l01, l02}, {l01, l11, l12}, {l02, l12, l22}};
         double Li[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
         double tmp[3][3];
@@ -312,10 +329,11 @@ __global__ void __launch_bounds__(TPB, FJ_PRESTEP_MINBLOCKS)
         sc.y = colour;
         sc.z = kernsum;
         S.SC[i] = sc;
+        }
     }
-    const double tot = block_sum(npd_, sm);
-    if (threadIdx.x == 0)
-        npd_partial[blockIdx.x] = tot;
+    const double tot = warp_sum(npd_);
+    if ((threadIdx.x & 31u) == 0u)
+        npd_partial[W] = tot;
 }
 
 // ================================================================= get_aero_velocity (constVel)
@@ -349,20 +367,24 @@ __global__ void k_aero_velocity(Level S, const int* __restrict__ ncount, const i
 // ================================================================= Detect_Surface loop 1 + dissipation_terms
 struct RecS1
 {
-    double4 p, g, v;
+    double4 p, g, v, x0;
+    int b;
 };
 
-template <bool SURF, bool DISS>
-#ifndef FJ_S1_MINBLOCKS
-#define FJ_S1_MINBLOCKS 3
-#endif
-__global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
-    k_surf1_diss(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n, int i0,
+template <bool SURF, bool DISS, bool FROZEN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
+    k_surf1_diss(Level S, RunView lv, RowMap M, const int* __restrict__ blk, int n_bound_blocks, DevConst C,
                  int* __restrict__ near_warps = nullptr)
 {
-    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; /* slots [i0, n) */
-    if (i >= n || blk[i] < n_bound_blocks)
+    int i, W;
+    bool work;
+    const bool in_row = fj_row_thread<WARPS>(M, i, W, work);
+    if (!work)
+        return; /* warp-uniform */
+    const bool active = in_row && blk[i] >= n_bound_blocks;
+    if (!__any_sync(FJ_FULL, active))
         return;
+    const double4 x0i = FROZEN ? lv.x0[i] : make_double4(0, 0, 0, 0);
     const double4 pi = S.P0[i];
     const double4 vi = S.P1[i];
     const double4 gi = S.P3[i]; /* gradRho_i, lam_i */
@@ -406,22 +428,30 @@ __global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
     double avx = 0, avy = 0, avz = 0, Rrhod = 0;
     const double cos_pi4 = 0.70710678118654757;
 
-    for_neighbours_pipelined(
-        lv, i,
-        [&](const unsigned ent) {
-            const unsigned j = ent & FJ_IDX_MASK;
+    for_neighbours(
+        lv, W, active,
+        [&](const unsigned j, const bool take) {
             RecS1 q;
-            q.p = gather(S.P0, j);
-            q.g = gather(S.P3, j);
-            if (DISS)
-                q.v = gather(S.P1, j);
+            if (take)
+            {
+                q.p = gather(S.P0, j);
+                q.g = gather(S.P3, j);
+                if (DISS)
+                {
+                    q.v = gather(S.P1, j);
+                    q.b = __ldg(&S.b[j]);
+                }
+                if (FROZEN)
+                    q.x0 = gather(lv.x0, j);
+            }
             return q;
         },
-        [&](const unsigned ent, const double r, const RecS1& q) {
+        [&](const unsigned j, const RecS1& q) {
             const double4 pj = q.p;
             const double4 gj = q.g;
             const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-            const double rr = r * r;
+            double rr, ir, r, r2c;
+            pair_dist<FROZEN>(x0i, q.x0, rx, ry, rz, rr, ir, r, r2c);
             const double t = wend_t(C, r);
             const double gk = wend_gk(C, r, t);
             const double vg = pj.w * gk;
@@ -443,7 +473,7 @@ __global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
                     else
                     {
                         /* acos(nhat . (Rji/r)) < pi/4 ; acos is NaN outside [-1,1] so those never trigger */
-                        const double c = (nhx * rx + nhy * ry + nhz * rz) / r;
+                        const double c = (nhx * rx + nhy * ry + nhz * rz) * ir;
                         if (c > cos_pi4 && c <= 1.0)
                             surf = 0;
                     }
@@ -454,9 +484,9 @@ __global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
                 const double4 vj = q.v;
                 const double rho_j = vj.w;
                 const double idist2 = fj_rcp(rr + eps_d);
-                const double w = vg * (rr * idist2); /* V_j (Rji . gradK) idist2 */
+                const double w = vg * (r2c * idist2); /* V_j (Rji . gradK) idist2 */
                 const double drho = rho_j - rho_i;
-                if (ent & FJ_NB_FLUID)
+                if (q.b > FJSPH_PISTON)
                 {
                     const double vdotr = (vj.x - vi.x) * rx + (vj.y - vi.y) * ry + (vj.z - vi.z) * rz;
                     /* ArtVisc = 0 when Vji.Rji > 0 (select, no branch) */
@@ -491,25 +521,25 @@ __global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
             out.y = ty * inv;
             out.z = tz * inv;
         }
-        S.P4[i] = out;
+        if (active)
+            S.P4[i] = out;
         if (near_warps)
         {
             /* how many warps hold a particle the lean surface / shifting sweep cannot take (k_surf23_shift, CLASS) */
-            const bool near = (out.x != 0.0 || out.y != 0.0 || out.z != 0.0) ||
-                              ((b_i == FJSPH_FREE) && (C.acase == 1) && (lam_nb < C.lam_cutoff));
-            const unsigned act = __activemask();
-            const unsigned m = __ballot_sync(act, near);
-            if (m && (threadIdx.x & 31) == unsigned(__ffs(int(act)) - 1))
+            const bool near = active && ((out.x != 0.0 || out.y != 0.0 || out.z != 0.0) ||
+                                         ((b_i == FJSPH_FREE) && (C.acase == 1) && (lam_nb < C.lam_cutoff)));
+            const unsigned m = __ballot_sync(FJ_FULL, near);
+            if (m && (threadIdx.x & 31u) == 0u)
                 atomicAdd(near_warps, 1);
         }
-        if (b_i < FJSPH_PIPE)
+        if (active && b_i < FJSPH_PIPE)
         {
             double4 th = S.TH[i];
             th.z = 1.0; /* woccl = 1, Geometry.cpp:33-37 */
             S.TH[i] = th;
         }
     }
-    if (DISS)
+    if (DISS && active)
     {
         double4 av = S.AV[i];
         av.x = avx;
@@ -529,12 +559,10 @@ __global__ void __launch_bounds__(TPB, FJ_S1_MINBLOCKS)
 // (Shifting.cpp:189-290) share one pass over the list.  The stage entry points run the halves separately.
 struct RecS2
 {
-    double4 n, p, v;
+    double4 n, p, v, x0;
+    int b;
 };
 
-#ifndef FJ_S23_MINBLOCKS
-#define FJ_S23_MINBLOCKS 2
-#endif
 #ifndef FJ_FUSE_SHIFT
 #define FJ_FUSE_SHIFT 1
 #endif
@@ -544,17 +572,18 @@ struct RecS2
 //      8-byte load instead of the 32-byte gather); no L matrix, no occlusion, far fewer registers, more resident warps;
 //   2 the others (near a free surface), with the full body.
 // The two launches cover disjoint particles; a warp that holds both kinds runs in both.
-#ifndef FJ_S23_LEAN_MINBLOCKS
-#define FJ_S23_LEAN_MINBLOCKS 4
-#endif
-template <bool SURF23, bool SHIFT, int CLASS = 0>
-__global__ void __launch_bounds__(TPB, CLASS == 1 ? FJ_S23_LEAN_MINBLOCKS : FJ_S23_MINBLOCKS)
-    k_surf23_shift(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, int n, int i0)
+template <bool SURF23, bool SHIFT, int CLASS, bool FROZEN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
+    k_surf23_shift(Level S, RunView lv, RowMap M, const int* __restrict__ blk, int n_bound_blocks, DevConst C)
 {
-    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; /* slots [i0, n) */
-    if (i >= n || blk[i] < n_bound_blocks)
-        return;
+    int i, W;
+    bool work;
+    const bool in_row = fj_row_thread<WARPS>(M, i, W, work);
+    if (!work)
+        return; /* warp-uniform */
+    bool active = in_row && blk[i] >= n_bound_blocks;
     const double4 pi = S.P0[i];
+    const double4 x0i = FROZEN ? lv.x0[i] : make_double4(0, 0, 0, 0);
     const double4 vi = S.P1[i];
     const double4 ni = S.P4[i]; /* Detect_Surface loop-1 normal (unit or zero), surf */
     const int b_i = S.b[i];
@@ -564,8 +593,10 @@ __global__ void __launch_bounds__(TPB, CLASS == 1 ? FJ_S23_LEAN_MINBLOCKS : FJ_S
     {
         const bool near = ni_nz_real || ((b_i == FJSPH_FREE) && (C.acase == 1) && (lam_nb < C.lam_cutoff));
         if (near != (CLASS == 2))
-            return;
+            active = false;
     }
+    if (!__any_sync(FJ_FULL, active))
+        return;
     const bool ni_nz = (CLASS == 1) ? false : ni_nz_real;
     bool has_fluid = false; /* lean: min_j n_i . n_j over fluid neighbours is 0 if there is one */
 
@@ -617,22 +648,29 @@ __global__ void __launch_bounds__(TPB, CLASS == 1 ? FJ_S23_LEAN_MINBLOCKS : FJ_S
     double min_c = 2.0;
     const bool need_pos = (SURF23 && (ni_nz || need_occl)) || do_shift;
 
-    for_neighbours_pipelined(
-        lv, i,
-        [&](const unsigned ent) {
-            const unsigned j = ent & FJ_IDX_MASK;
+    for_neighbours(
+        lv, W, active,
+        [&](const unsigned j, const bool take) {
             RecS2 q;
-            if (CLASS == 1)
-                q.n.w = __ldg(&S.P4[j].w); /* the surf flag is all a lean particle reads of n_j */
-            else
-                q.n = gather(S.P4, j);
-            if (need_pos)
-                q.p = gather(S.P0, j);
-            if (do_shift)
-                q.v = gather(S.P1, j);
+            if (take)
+            {
+                if (CLASS == 1)
+                    q.n.w = __ldg(&S.P4[j].w); /* the surf flag is all a lean particle reads of n_j */
+                else
+                    q.n = gather(S.P4, j);
+                if (need_pos)
+                    q.p = gather(S.P0, j);
+                if (do_shift)
+                {
+                    q.v = gather(S.P1, j);
+                    q.b = __ldg(&S.b[j]);
+                }
+                if (FROZEN && need_pos)
+                    q.x0 = gather(lv.x0, j);
+            }
             return q;
         },
-        [&](const unsigned ent, const double r, const RecS2& q) {
+        [&](const unsigned j, const RecS2& q) {
             const double4 nj = q.n;
             if (nj.w != 0.0)
                 zone = 1;
@@ -640,6 +678,8 @@ __global__ void __launch_bounds__(TPB, CLASS == 1 ? FJ_S23_LEAN_MINBLOCKS : FJ_S
                 return;
             const double4 pj = q.p;
             const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
+            double rr, ir, r, r2c;
+            pair_dist<FROZEN>(x0i, q.x0, rx, ry, rz, rr, ir, r, r2c);
             const double t = wend_t(C, r);
             const double gk = wend_gk(C, r, t);
             if (SURF23)
@@ -655,7 +695,7 @@ __global__ void __launch_bounds__(TPB, CLASS == 1 ? FJ_S23_LEAN_MINBLOCKS : FJ_S
                 }
                 if (need_occl)
                 {
-                    const double frac = (rx * vdx + ry * vdy + rz * vdz) * mivdn * fj_rcp(r);
+                    const double frac = (rx * vdx + ry * vdy + rz * vdz) * mivdn * ir;
                     if (frac > woccl_)
                         woccl_ = frac;
                 }
@@ -671,8 +711,8 @@ __global__ void __launch_bounds__(TPB, CLASS == 1 ? FJ_S23_LEAN_MINBLOCKS : FJ_S
                 duy += f * ry;
                 duz += f * rz;
                 if (CLASS == 1)
-                    has_fluid = has_fluid || ((ent & FJ_NB_FLUID) != 0u);
-                else if (!known_bulk && (ent & FJ_NB_FLUID))
+                    has_fluid = has_fluid || (q.b > FJSPH_PISTON);
+                else if (!known_bulk && (q.b > FJSPH_PISTON))
                 {
                     /* n_i and n_j are unit vectors or zero already (loop 1), normalized() is the identity */
                     const double c = ni.x * nj.x + ni.y * nj.y + ni.z * nj.z;
@@ -685,6 +725,8 @@ __global__ void __launch_bounds__(TPB, CLASS == 1 ? FJ_S23_LEAN_MINBLOCKS : FJ_S
         });
     if (CLASS == 1 && has_fluid)
         min_c = 0.0;
+    if (!active)
+        return; /* the walk is over: nothing below votes */
 
     if (SURF23)
     {
@@ -902,28 +944,32 @@ __device__ void calc_aero_acc(const DevConst& C, double dx_, double dy_, double 
 
 struct RecF
 {
-    double4 p, v, q;
+    double4 p, v, q, x0;
+    int b;
 };
 
 // Pair algebra (V_j = m_j / rho_j, G = V_j gradK, Pi = p_i / rho_i^2, u = v_j - v_i, w = vPert):
 //   pressure    BasePos, Kernel.h:153-157          acc_     -= m_j (Pi + Pj) gradK         = rho_j (Pi + Pj) G
 //   viscosity   Kernel.h:262-269                   visc_    += m_j nu (rho_i + rho_j)/(rho_i rho_j) (Rji.gradK) idist2 u
-//                                                            = (nu + nu rho_j / rho_i) (V_j gk rr idist2) u
+//                                                            = (nu + nu rho_j / rho_i) (V_j gk |Rji|^2 idist2) u
 //   ALE moment. Kernel.h:179-185                   acc_ale_ += V_j [(v_j (w_j.gK) + v_i (w_i.gK)) - v_i ((w_j - w_i).gK)]
 //                                                            = u (w_j.G) + 2 v_i (w_i.G)
 //   continuity  Kernel.h:187-196                   Rrho_    -= V_j ((u + w_j - w_i).gK)     = -(u.G + w_j.G) + w_i.G
 //                                                  Rrhoc_   += V_j (rho_j w_j.gK + rho_i w_i.gK) = rho_j (w_j.G) + rho_i (w_i.G)
 // The w_i.G terms are linear in G, so sum_j G is accumulated once and w_i applied after the loop.
-#ifndef FJ_FORCE_MINBLOCKS
-#define FJ_FORCE_MINBLOCKS 3
-#endif
-template <bool ALE>
-__global__ void __launch_bounds__(TPB, FJ_FORCE_MINBLOCKS)
-    k_force(Level S, ListView lv, const int* __restrict__ blk, int n_bound_blocks, DevConst C, double npdm2, int n, int i0)
+template <bool ALE, bool FROZEN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
+    k_force(Level S, RunView lv, RowMap M, const int* __restrict__ blk, int n_bound_blocks, DevConst C, double npdm2)
 {
-    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x; /* slots [i0, n) */
-    if (i >= n || blk[i] < n_bound_blocks)
+    int i, W;
+    bool work;
+    const bool in_row = fj_row_thread<WARPS>(M, i, W, work);
+    if (!work)
+        return; /* warp-uniform */
+    const bool active = in_row && blk[i] >= n_bound_blocks;
+    if (!__any_sync(FJ_FULL, active))
         return;
+    const double4 x0i = FROZEN ? lv.x0[i] : make_double4(0, 0, 0, 0);
     const double4 pi = S.P0[i];
     const double4 vi = S.P1[i];
     const double4 qi = S.P2[i]; /* vPert_i, p_i/rho_i^2 */
@@ -964,23 +1010,30 @@ __global__ void __launch_bounds__(TPB, FJ_FORCE_MINBLOCKS)
         }
     }
 
-    for_neighbours_pipelined(
-        lv, i,
-        [&](const unsigned ent) {
-            const unsigned j = ent & FJ_IDX_MASK;
+    for_neighbours(
+        lv, W, active,
+        [&](const unsigned j, const bool take) {
             RecF q;
-            q.p = gather(S.P0, j);
-            q.v = gather(S.P1, j);
-            q.q = gather(S.P2, j);
+            if (take)
+            {
+                q.p = gather(S.P0, j);
+                q.v = gather(S.P1, j);
+                q.q = gather(S.P2, j);
+                if (do_st)
+                    q.b = __ldg(&S.b[j]);
+                if (FROZEN)
+                    q.x0 = gather(lv.x0, j);
+            }
             return q;
         },
-        [&](const unsigned ent, const double r, const RecF& q) {
+        [&](const unsigned j, const RecF& q) {
             const double4 pj = q.p;
             const double4 vj = q.v;
             const double4 qj = q.q;
             const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
             const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
-            const double rr = r * r;
+            double rr, ir, r, r2c;
+            pair_dist<FROZEN>(x0i, q.x0, rx, ry, rz, rr, ir, r, r2c);
             const double idist2 = fj_rcp(rr + eps_f);
             const double t = wend_t(C, r);
             const double rho_j = vj.w;
@@ -990,15 +1043,15 @@ __global__ void __launch_bounds__(TPB, FJ_FORCE_MINBLOCKS)
             ax -= pf * Gx;
             ay -= pf * Gy;
             az -= pf * Gz;
-            const double vf = fma(nu_irho_i, rho_j, C.nu) * ((s * rr) * idist2);
+            const double vf = fma(nu_irho_i, rho_j, C.nu) * ((s * r2c) * idist2);
             vx += vf * ux;
             vy += vf * uy;
             vz += vf * uz;
             /* pairwise surface tension, Kernel.h:101-113 */
             if (do_st)
             {
-                const double fac = (b_i == FJSPH_BOUND || (ent & FJ_NB_BOUND)) ? st_bound_fac : 1.0;
-                const double sf = -npdm2 * fac * cospi(q_st * r) * fj_rcp(r);
+                const double fac = (b_i == FJSPH_BOUND || q.b == FJSPH_BOUND) ? st_bound_fac : 1.0;
+                const double sf = -npdm2 * fac * cospi(q_st * r) * ir;
                 sx += sf * rx;
                 sy += sf * ry;
                 sz += sf * rz;
@@ -1048,6 +1101,8 @@ __global__ void __launch_bounds__(TPB, FJ_FORCE_MINBLOCKS)
         ay += f * bn.y;
         az += f * bn.z;
     }
+    if (!active)
+        return; /* the walk is over: nothing below votes */
     const double4 av = S.AV[i];
     const double im = 1.0 / th.y;
     double4 acc;
@@ -1072,26 +1127,36 @@ __global__ void k_wall_velocity(Level S, const int* __restrict__ blk, int block,
     S.P1[i] = v;
 }
 
-// Set_No_Slip: v_i = 2 v_i - sum(v_j W)/sum(W) over fluid neighbours
-__global__ void k_wall_no_slip(Level S, ListView lv, const int* __restrict__ blk, int block, DevConst C, int n)
+// r of a pair for the wall treatments (they run with the particles moved: the build-time positions give the frozen r)
+__device__ __forceinline__ double wall_pair_r(const double4* __restrict__ x0, const double4& x0i, unsigned j)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || blk[i] != block)
+    const double4 q = x0[j];
+    const double ex = q.x - x0i.x, ey = q.y - x0i.y, ez = q.z - x0i.z;
+    return sqrt(fma(ez, ez, fma(ey, ey, ex * ex)));
+}
+
+// Set_No_Slip: v_i = 2 v_i - sum(v_j W)/sum(W) over fluid neighbours
+__global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
+    k_wall_no_slip(Level S, RunView lv, RowMap M, const int* __restrict__ blk, int block, DevConst C)
+{
+    int i, W;
+    bool work;
+    const bool in_row = fj_row_thread(M, i, W, work);
+    if (!work || !in_row || blk[i] != block)
         return;
-    const double4 pi = S.P0[i];
+    const double4 x0i = lv.x0[i];
     double sxx = 0, syy = 0, szz = 0, ks = 0;
-    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
-        if (!(ent & FJ_NB_FLUID))
+    for_neighbours_simple(lv, W, true, [&](const unsigned j) {
+        if (!(S.b[j] > FJSPH_PISTON))
             return;
-        const double4 pj = gather_rw(S.P0, j);
+        const double r = wall_pair_r(lv.x0, x0i, j);
         const double4 vj = gather_rw(S.P1, j);
-        const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-        const double W = wend_W(C, r, wend_t(C, r));
-        ks += W;
-        sxx += vj.x * W;
-        syy += vj.y * W;
-        szz += vj.z * W;
-    FJ_NEIGHBOURS_END
+        const double W_ = wend_W(C, r, wend_t(C, r));
+        ks += W_;
+        sxx += vj.x * W_;
+        syy += vj.y * W_;
+        szz += vj.z * W_;
+    });
     if (ks > 0.0)
     {
         double4 v = S.P1[i];
@@ -1132,18 +1197,23 @@ __device__ __forceinline__ void store_thermo(Level& S, int i, double rho, double
 }
 
 // Get_Boundary_Pressure (Adami et al. 2012): walls read fluid records only, so in-place update is race free
-__global__ void k_wall_pressure(Level S, ListView lv, const int* __restrict__ blk, int block, DevConst C, int n)
+__global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
+    k_wall_pressure(Level S, RunView lv, RowMap M, const int* __restrict__ blk, int block, DevConst C)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || blk[i] != block)
+    int i, W;
+    bool work;
+    const bool in_row = fj_row_thread(M, i, W, work);
+    if (!work || !in_row || blk[i] != block)
         return;
     const double4 pi = S.P0[i];
+    const double4 x0i = lv.x0[i];
     const double4 acc = S.ACC[i];
     double ks = 0, pk = 0, akx = 0, aky = 0, akz = 0;
     int near_surface = 0;
-    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
-        if (!(ent & FJ_NB_FLUID))
+    for_neighbours_simple(lv, W, true, [&](const unsigned j) {
+        if (!(S.b[j] > FJSPH_PISTON))
             return;
+        const double r = wall_pair_r(lv.x0, x0i, j);
         const double4 pj = gather_rw(S.P0, j);
         const double rho_j = S.P1[j].w;
         const double p_j = S.TH[j].x;
@@ -1157,7 +1227,7 @@ __global__ void k_wall_pressure(Level S, ListView lv, const int* __restrict__ bl
         akz += kr * rz;
         if (S.surfzone[j])
             near_surface = 1;
-    FJ_NEIGHBOURS_END
+    });
     double p = 0.0;
     if (ks > 0.0)
     {
@@ -1169,26 +1239,31 @@ __global__ void k_wall_pressure(Level S, ListView lv, const int* __restrict__ bl
 }
 
 // Boundary_Ghost: Rrho_i = -rho_i sum V_j Vji.gradK over all neighbours; near_inlet = no PIPE/FREE neighbour.
-__global__ void k_wall_ghost(Level S, ListView lv, const int* __restrict__ blk, int block, DevConst C, int n,
-                             int* __restrict__ near_inlet_out)
+__global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
+    k_wall_ghost(Level S, RunView lv, RowMap M, const int* __restrict__ blk, int block, DevConst C,
+                 int* __restrict__ near_inlet_out)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || blk[i] != block)
+    int i, W;
+    bool work;
+    const bool in_row = fj_row_thread(M, i, W, work);
+    if (!work || !in_row || blk[i] != block)
         return;
     const double4 pi = S.P0[i];
+    const double4 x0i = lv.x0[i];
     const double4 vi = S.P1[i];
     double Rrhoi = 0.0;
     int near_inlet = 1;
-    FJ_NEIGHBOURS_BEGIN(i, lv, ent, j, r)
+    for_neighbours_simple(lv, W, true, [&](const unsigned j) {
         const int bj = S.b[j];
         if (bj == FJSPH_PIPE || bj == FJSPH_FREE)
             near_inlet = 0;
+        const double r = wall_pair_r(lv.x0, x0i, j);
         const double4 pj = gather_rw(S.P0, j);
         const double4 vj = gather_rw(S.P1, j);
         const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
         const double gk = wend_gk(C, r, wend_t(C, r));
         Rrhoi -= pj.w * gk * ((vj.x - vi.x) * rx + (vj.y - vi.y) * ry + (vj.z - vi.z) * rz);
-    FJ_NEIGHBOURS_END
+    });
     double4 acc = S.ACC[i];
     acc.w = Rrhoi * vi.w;
     S.ACC[i] = acc;
@@ -1221,31 +1296,31 @@ __global__ void k_pipe_outlet(Level S, const int* __restrict__ blk, int block, d
     }
 }
 
-ListView list_view(FjsphEngine* e)
+RunView run_view(FjsphEngine* e)
 {
-    ListView v;
-    v.nlist = e->nlist;
-    v.nr = e->nr;
+    RunView v;
+    v.erun = e->erun;
+    v.erows = e->erows;
     v.ncount = e->ncount;
-    v.nb_cap = e->nb_cap;
+    v.x0 = e->x0;
+    v.ecap = e->ecap;
     return v;
 }
 
-// Launches a sweep over the owned slots [0, n).  Slab mode, with a forward exchange in flight on the comm stream:
-// the INTERIOR slots first (none of their neighbours is a ghost, so they run beside the exchange), then -- once the
-// main stream has waited for the ghosts -- the EDGE slots.  launch(i0, i1) must queue the kernel for slots [i0, i1).
-// Call with e->slab.hold set while the KScope of the sweep is constructed (SplitScope below).
+// Launches a sweep over the owned rows.  Slab mode, with a forward exchange in flight on the comm stream: the rows of
+// the INTERIOR class first (none of their neighbours is a ghost, so they run beside the exchange), then -- once the
+// main stream has waited for the ghosts -- the rows of the EDGE class.  launch(M) must queue the kernel for the rows
+// of M.  Call with e->slab.hold set while the KScope of the sweep is constructed (SplitScope below).
 template <class F>
-int launch_split(FjsphEngine* e, int n, F&& launch)
+int launch_split(FjsphEngine* e, F&& launch)
 {
     if (fj_halo_overlappable(e))
     {
-        const int ni = int(e->slab.n_interior);
-        launch(0, ni);
+        launch(fj_row_map(e, 0, 1));
         int st = fj_halo_wait(e);
         if (st)
             return st;
-        launch(ni, n);
+        launch(fj_row_map(e, 1, 1));
         e->slab.overlapped++;
     }
     else
@@ -1253,7 +1328,7 @@ int launch_split(FjsphEngine* e, int n, F&& launch)
         int st = fj_halo_wait(e);
         if (st)
             return st;
-        launch(0, n);
+        launch(fj_row_map(e, 0, fj_owned_classes(e)));
     }
     return FJSPH_OK;
 }
@@ -1281,6 +1356,55 @@ int need_list(FjsphEngine* e, const char* who)
     return FJSPH_OK;
 }
 
+// picks the instantiation of a sweep: FROZEN once the level-1 positions differ from the ones the list was built on,
+// WARPS = rows per CTA (e->sweep_warps).  f(FROZEN, WARPS) receives both as integral constants.
+template <class F>
+void by_shape(const FjsphEngine* e, bool frozen, F&& f)
+{
+    using std::integral_constant;
+    if (e->sweep_warps == 4)
+    {
+        if (frozen)
+            f(integral_constant<bool, true>{}, integral_constant<int, 4>{});
+        else
+            f(integral_constant<bool, false>{}, integral_constant<int, 4>{});
+    }
+    else
+    {
+        if (frozen)
+            f(integral_constant<bool, true>{}, integral_constant<int, 8>{});
+        else
+            f(integral_constant<bool, false>{}, integral_constant<int, 8>{});
+    }
+}
+
+template <bool SURF, bool DISS>
+int sweep_surf1(FjsphEngine* e, int* near_warps)
+{
+    const RunView lv = run_view(e);
+    return launch_split(e, [&](const RowMap& M) {
+        by_shape(e, e->x_moved, [&](auto fr, auto wp) {
+            constexpr bool FR = decltype(fr)::value;
+            constexpr int WP = decltype(wp)::value;
+            k_surf1_diss<SURF, DISS, FR, WP><<<fj_row_grid(M, WP), WP * 32, 0, e->stream>>>(e->lv[1], lv, M, e->blk,
+                                                                                           e->n_bound_blocks, e->C, near_warps);
+        });
+    });
+}
+template <bool SURF23, bool SHIFT, int CLASS>
+int sweep_surf23(FjsphEngine* e)
+{
+    const RunView lv = run_view(e);
+    return launch_split(e, [&](const RowMap& M) {
+        by_shape(e, e->x_moved, [&](auto fr, auto wp) {
+            constexpr bool FR = decltype(fr)::value;
+            constexpr int WP = decltype(wp)::value;
+            k_surf23_shift<SURF23, SHIFT, CLASS, FR, WP><<<fj_row_grid(M, WP), WP * 32, 0, e->stream>>>(
+                e->lv[1], lv, M, e->blk, e->n_bound_blocks, e->C);
+        });
+    });
+}
+
 } // namespace
 
 // ------------------------------------------------------------------ host wrappers
@@ -1289,15 +1413,18 @@ int fj_prestep(FjsphEngine* e, double* npd)
     int st = need_list(e, "prestep");
     if (st)
         return st;
-    const int n = int(e->n_owned);
-    const int nb = fj_blocks(n, TPB);
+    const RowMap M = fj_row_map(e, 0, fj_owned_classes(e));
     {
         KScope ks(e, "prestep", 1);
-        k_prestep<<<nb, TPB, 0, e->stream>>>(e->lv[1], list_view(e), e->C, n, e->red);
+        by_shape(e, e->x_moved, [&](auto fr, auto wp) {
+            constexpr bool FR = decltype(fr)::value;
+            constexpr int WP = decltype(wp)::value;
+            k_prestep<FR, WP><<<fj_row_grid(M, WP), WP * 32, 0, e->stream>>>(e->lv[1], run_view(e), M, e->C, e->red);
+        });
     }
     FJ_CUDA(cudaGetLastError());
     double sum = 0.0;
-    st = fj_reduce_sum(e, nb, 1, &sum);
+    st = fj_reduce_sum(e, int(e->n_warp), 1, &sum);
     if (st)
         return st;
     /* npd = npd_ / end (Shifting.cpp:121); Q4: the race-free sum */
@@ -1326,11 +1453,6 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
     int st = need_list(e, "detect_surface/dissipation");
     if (st)
         return st;
-    const int n = int(e->n_owned);
-    ListView lv = list_view(e);
-#define FJ_SWEEP(KERNEL) \
-    launch_split(e, n, [&](int i0, int i1) { \
-        KERNEL<<<fj_blocks(i1 - i0, TPB), TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks, e->C, i1, i0); })
     if (do_surface && do_dissipation)
     {
         /* count the warps holding near-surface particles for the split decision below; the count of THIS pass is read
@@ -1339,22 +1461,19 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
         {
             SplitScope ks(e, "surf1+diss");
             int* nw = e->d_flag + 2;
-            st = launch_split(e, n, [&](int i0, int i1) {
-                k_surf1_diss<true, true><<<fj_blocks(i1 - i0, TPB), TPB, 0, e->stream>>>(e->lv[1], lv, e->blk, e->n_bound_blocks,
-                                                                                        e->C, i1, i0, nw);
-            });
+            st = sweep_surf1<true, true>(e, nw);
         }
         FJ_CUDA(cudaMemcpyAsync(e->h_flag + 2, e->d_flag + 2, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     }
     else if (do_surface)
     {
         SplitScope ks(e, "surf1");
-        st = FJ_SWEEP((k_surf1_diss<true, false>));
+        st = sweep_surf1<true, false>(e, nullptr);
     }
     else if (do_dissipation)
     {
         SplitScope ks(e, "diss");
-        st = FJ_SWEEP((k_surf1_diss<false, true>));
+        st = sweep_surf1<false, true>(e, nullptr);
     }
     if (st)
         return st;
@@ -1368,23 +1487,23 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
     {
         SplitScope ks(e, "surf2+3+shift");
         /* Two launches (lean bulk, then the near-surface rest) pay when few warps hold near-surface particles: with the
-           lean body at ~0.6 of the full one, below ~0.4 of the warps (block: 0.17, 70 -> 54 ms; a 1 M droplet: 0.5,
-           where one fused launch is faster).  The fraction is the one counted at the previous pass. */
-        const double near_frac = double(e->h_flag[2]) / double(std::max(1, (n + 31) / 32));
-        if (e->split_surface_sweep && near_frac < 0.35)
+           lean body at ~0.6 of the full one, below ~0.4 of the warps (block: 0.17; a 1 M droplet: 0.5, where one fused
+           launch is faster).  The fraction is the one counted at the previous pass. */
+        const double near_frac = double(e->h_flag[2]) / double(std::max(1u, e->n_warp));
+        if (e->split_surface_sweep && near_frac < e->split_surface_below)
         {
-            st = FJ_SWEEP((k_surf23_shift<true, true, 1>));
+            st = sweep_surf23<true, true, 1>(e);
             if (!st)
-                st = FJ_SWEEP((k_surf23_shift<true, true, 2>));
+                st = sweep_surf23<true, true, 2>(e);
         }
         else
-            st = FJ_SWEEP((k_surf23_shift<true, true>));
+            st = sweep_surf23<true, true, 0>(e);
     }
     else if (do_surface)
     {
         {
             SplitScope ks(e, "surf2+3");
-            st = FJ_SWEEP((k_surf23_shift<true, false>));
+            st = sweep_surf23<true, false, 0>(e);
         }
         if (st)
             return st;
@@ -1407,10 +1526,14 @@ int fj_shift(FjsphEngine* e)
         return st;
     if (!e->P.ale)
         return FJSPH_OK;
-    const int n = int(e->n_owned);
+    const RowMap M = fj_row_map(e, 0, fj_owned_classes(e));
     KScope ks(e, "shift", 1);
-    k_surf23_shift<false, true><<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], list_view(e), e->blk,
-                                                                          e->n_bound_blocks, e->C, n, 0);
+    by_shape(e, e->x_moved, [&](auto fr, auto wp) {
+        constexpr bool FR = decltype(fr)::value;
+        constexpr int WP = decltype(wp)::value;
+        k_surf23_shift<false, true, 0, FR, WP><<<fj_row_grid(M, WP), WP * 32, 0, e->stream>>>(e->lv[1], run_view(e), M, e->blk,
+                                                                                             e->n_bound_blocks, e->C);
+    });
     FJ_CUDA(cudaGetLastError());
     return FJSPH_OK;
 }
@@ -1438,21 +1561,26 @@ int fj_forces(FjsphEngine* e, int level_idx, double npd)
     int st = need_list(e, "forces");
     if (st)
         return st;
-    const int n = int(e->n_owned);
     /* Resid.cpp:437-448 */
     const double lam = (6.0 / 81.0 * std::pow((2.0 * e->P.H), 3.0) / std::pow(FJ_PI, 4.0) *
                         (9.0 / 4.0 * std::pow(FJ_PI, 3.0) - 6.0 * FJ_PI - 4.0));
     const double npdm2 = (0.5 * e->P.sig / lam) / (npd * npd);
+    /* the list was built on level 1's positions: any other level, or level 1 after a move, takes r from x0 */
+    const bool frozen = e->x_moved || level_idx != 1;
     {
         SplitScope ks(e, "force");
-        ListView lv = list_view(e);
-        st = launch_split(e, n, [&](int i0, int i1) {
-            if (e->P.ale)
-                k_force<true><<<fj_blocks(i1 - i0, TPB), TPB, 0, e->stream>>>(e->lv[level_idx], lv, e->blk, e->n_bound_blocks,
-                                                                               e->C, npdm2, i1, i0);
-            else
-                k_force<false><<<fj_blocks(i1 - i0, TPB), TPB, 0, e->stream>>>(e->lv[level_idx], lv, e->blk, e->n_bound_blocks,
-                                                                                e->C, npdm2, i1, i0);
+        RunView lv = run_view(e);
+        st = launch_split(e, [&](const RowMap& M) {
+            by_shape(e, frozen, [&](auto fr, auto wp) {
+                constexpr bool FR = decltype(fr)::value;
+                constexpr int WP = decltype(wp)::value;
+                if (e->P.ale)
+                    k_force<true, FR, WP><<<fj_row_grid(M, WP), WP * 32, 0, e->stream>>>(e->lv[level_idx], lv, M, e->blk,
+                                                                                        e->n_bound_blocks, e->C, npdm2);
+                else
+                    k_force<false, FR, WP><<<fj_row_grid(M, WP), WP * 32, 0, e->stream>>>(e->lv[level_idx], lv, M, e->blk,
+                                                                                         e->n_bound_blocks, e->C, npdm2);
+            });
         });
         if (st)
             return st;
@@ -1472,8 +1600,10 @@ int fj_walls(FjsphEngine* e, int level_idx, bool nb_comparator)
     if (st)
         return st;
     const int n = int(e->n_owned);
-    const int nb = fj_blocks(n, TPB);
-    ListView lv = list_view(e);
+    const int nb = fj_blocks(n, 256);
+    RunView lv = run_view(e);
+    const RowMap M = fj_row_map(e, 0, fj_owned_classes(e));
+    const unsigned grid = fj_row_grid(M);
     Level& S = e->lv[level_idx];
     for (int bl = 0; bl < e->n_bound_blocks; ++bl)
     {
@@ -1490,14 +1620,14 @@ int fj_walls(FjsphEngine* e, int level_idx, bool nb_comparator)
             }
         }
         KScope ks(e, "walls", 3);
-        k_wall_velocity<<<nb, TPB, 0, e->stream>>>(S, e->blk, bl, vel[0], vel[1], vel[2], n);
+        k_wall_velocity<<<nb, 256, 0, e->stream>>>(S, e->blk, bl, vel[0], vel[1], vel[2], n);
         if (B.no_slip)
-            k_wall_no_slip<<<nb, TPB, 0, e->stream>>>(S, lv, e->blk, bl, e->C, n);
+            k_wall_no_slip<<<grid, FJ_ROW_WARPS * 32, 0, e->stream>>>(S, lv, M, e->blk, bl, e->C);
         switch (B.bound_solver)
         {
-        case FJSPH_DBC: k_wall_dbc<<<nb, TPB, 0, e->stream>>>(S, e->blk, bl, n); break;
-        case FJSPH_PRESSURE_G: k_wall_pressure<<<nb, TPB, 0, e->stream>>>(S, lv, e->blk, bl, e->C, n); break;
-        case FJSPH_GHOST: k_wall_ghost<<<nb, TPB, 0, e->stream>>>(S, lv, e->blk, bl, e->C, n, e->near_inlet); break;
+        case FJSPH_DBC: k_wall_dbc<<<nb, 256, 0, e->stream>>>(S, e->blk, bl, n); break;
+        case FJSPH_PRESSURE_G: k_wall_pressure<<<grid, FJ_ROW_WARPS * 32, 0, e->stream>>>(S, lv, M, e->blk, bl, e->C); break;
+        case FJSPH_GHOST: k_wall_ghost<<<grid, FJ_ROW_WARPS * 32, 0, e->stream>>>(S, lv, M, e->blk, bl, e->C, e->near_inlet); break;
         default: break;
         }
     }
