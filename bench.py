@@ -58,7 +58,10 @@ def parse_args():
     ap.add_argument("--cells", default="500,250,100", help="block lattice per GPU (x,y,z)")
     ap.add_argument("--droplet-dx", type=float, default=0.0008)
     ap.add_argument("--solver", default="newmark_beta", choices=["newmark_beta", "runge_kutta"])
-    ap.add_argument("--cpu-sample", default="64,56,56", help="lattice of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", default="64,64,64", help="lattice of the bounded CPU-baseline sample (block workload)")
+    ap.add_argument("--check", action="store_true",
+                    help="before the timed steps: 2 steps of the slab engine on a ~1 M-particle block against the 1-GPU engine "
+                         "(N > 1; rank 0 reports the differences in `slab_parity`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -164,16 +167,31 @@ class quiet_fd1:
         os.close(self.saved)
 
 
-def cpu_reference(args, steps, warmup, sample_cells):
+def cpu_sample_case(args, sample_cells):
+    """The bounded sample of the workload the CPU arm steps: same generator, same spacing, jitter and fields, fewer
+    particles (the reference's list layout needs ~4.2 KB per particle, and a step of 12.5 M particles takes minutes)."""
+    from fjsph_b200 import cases
+
+    if args.workload == "block":
+        return make_case(args, 0, cells=sample_cells), "%s lattice of the block workload" % sample_cells.replace(",", "x")
+    if args.workload == "jet":
+        return (cases.synthetic_jet(nx=64, radius_cells=32, dx=1e-3, jitter=0.1, seed=1234),
+                "64-column, R=32dx cylinder of the jet workload")
+    return make_case(args), "the droplet itself"
+
+
+def cpu_reference(args, steps, warmup, sample_cells, kind_pref="reference"):
     """Times the reference's CPU implementation of the step on a bounded sample of the same workload, with every host
-    thread.  oracle/_ref/liborc_ref3d_fast.so when it is there -- FJSPH's OWN sources compiled with the reference's flags
-    (oracle/Makefile.ref; kind "reference") -- else the CPU restatement built the same way (kind "port").
-    Returns (particle-steps/s, cores, description, ms per step, kind)."""
+    thread: exactly `warmup` untimed steps, then `steps` timed ones; the value is particles / MEDIAN step time.
+    kind_pref "reference": oracle/_ref/liborc_ref3d_fast.so -- FJSPH's OWN sources compiled with the reference's flags
+    (oracle/Makefile.ref), dissipation_terms serial as the reference has it (Shifting.cpp:126-186 carries no OpenMP
+    pragma) -- falling back to the port where that library is absent; "port": the CPU restatement built the same way,
+    every loop threaded.  Returns a dict (value, cores, kind, sample, ms_per_step, n, step_ms)."""
     from oracle import oracle as orc  # bench.py's CPU-baseline leg: the checker timed as the baseline
 
-    use_ref = orc.have_ref("ref3d_fast")
+    use_ref = kind_pref == "reference" and orc.have_ref("ref3d_fast")
     if not use_ref:
-        subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "lib/liborc3d_fast.so"])
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "lib/liborc3d_fast.so"])
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; the baseline gets every host core
     try:
@@ -182,52 +200,63 @@ def cpu_reference(args, steps, warmup, sample_cells):
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)  # in case libgomp was initialised before
     except OSError:
         pass
-    if args.workload == "block":
-        case = make_case(args, 0, cells=sample_cells)
-    elif args.workload == "jet":
-        from fjsph_b200 import cases
-
-        case = cases.synthetic_jet(nx=64, radius_cells=32, dx=1e-3, jitter=0.1, seed=1234)
-    else:
-        case = make_case(args)
+    case, what_sample = cpu_sample_case(args, sample_cells)
     params = step_params(args, case["params"])
     kind = "ref3d_fast" if use_ref else "3d_fast"
     o = orc.Oracle(orc.default_params(3, **params), kind=kind)
     o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
     n = case["xi"].shape[0] - case["bound_points"]
     its = 0
+    step_s = []
     with quiet_fd1():
         for _ in range(warmup):
             o.integrate()
-        t0 = time.perf_counter()
         for _ in range(steps):
+            t0 = time.perf_counter()
             _, st = o.integrate()
+            step_s.append(time.perf_counter() - t0)
             its = st.iterations
-        dt = time.perf_counter() - t0
+    med = float(np.median(step_s))
     what = ("FJSPH's own sources (Neighbours, Shifting, Resid, Geometry, Containment, Newmark_Beta, Integration .cpp compiled "
             "unmodified, -O3 -ffast-math -funroll-loops -fopenmp -march=x86-64-v3; stand-in Eigen / nanoflann headers, a "
-            "uniform-grid radius search in place of the KD-tree)" if use_ref else
-            "oracle/fjsph_oracle.cpp (-O3 -ffast-math -funroll-loops -fopenmp -march=native)")
-    desc = ("%s, %d threads, %d steps after %d warm-up on %s, %d particles, %d sub-iterations" % (
-        what, cores, steps, warmup, "a %s lattice of the block workload" % sample_cells
-        if args.workload == "block" else ("a 64-column, R=32dx cylinder of the jet workload"
-                                          if args.workload == "jet" else "the droplet"), n, its))
-    return n * steps / dt, cores, desc, dt / steps * 1e3, ("reference" if use_ref else "port")
+            "uniform-grid radius search in place of the KD-tree; dissipation_terms serial as in the reference)" if use_ref else
+            "oracle/fjsph_oracle.cpp, the CPU restatement, every loop threaded (-O3 -ffast-math -funroll-loops -fopenmp "
+            "-march=native)")
+    desc = "%s, %d threads, median of %d timed steps after %d warm-up on a %s, %d particles, %d sub-iterations" % (
+        what, cores, steps, warmup, what_sample, n, its)
+    return {"value": n / med, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port", "sample": desc,
+            "ms_per_step": med * 1e3, "n": int(n), "what_sample": what_sample,
+            "step_ms_min_max": [float(min(step_s)) * 1e3, float(max(step_s)) * 1e3]}
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the step, alone.  It runs what it says: `warmup`
+    untimed and `steps` timed steps of a bounded SAMPLE of the workload (named in config.workload with its particle
+    count -- the 12.5 M-particle configuration itself would need ~50 GB of the reference's list and minutes per step)."""
     if rank != 0:
         return
-    value, cores, desc, ms, kind = cpu_reference(args, max(1, args.steps), max(1, min(args.warmup, 1)), args.cpu_sample)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    r = cpu_reference(args, steps, warmup, args.cpu_sample)
+    port = None
+    if r["kind"] == "reference":
+        # BASELINE.md 3, line (a): the restatement with every loop threaded, on the same sample (a short run: it is the
+        # side line; the headline is the reference's own code above)
+        p = cpu_reference(args, 3, 1, args.cpu_sample, kind_pref="port")
+        port = {k: p[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, world), "solver": args.solver,
+        "config": {"workload": "%s -- CPU arm: a bounded sample of it, %s, %d particles" % (
+                       workload_name(args, world), r["what_sample"], r["n"]),
+                   "particles_total": r["n"], "solver": args.solver,
                    "force_evals_per_step": 1 + K_SUBITS if args.solver == "newmark_beta" else 4,
-                   "note": "the reference's CPU path on host cores; each step is a bounded sample"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   "same_config": False,
+                   "note": "the reference's CPU path on host cores; every step is one step of the sample named in workload; "
+                           "value = particles / median step time; step_ms_min_max shows the spread"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_port": port, "step_ms_min_max": r["step_ms_min_max"],
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
@@ -428,8 +457,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, desc, _, kind = cpu_reference(args, 2, 1, args.cpu_sample)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+        r = cpu_reference(args, 4, 1, args.cpu_sample)  # ~25 s of CPU work: 1 warm-up + 4 timed steps, median
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         line = {

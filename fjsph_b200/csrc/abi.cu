@@ -697,6 +697,8 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
         e->row_width_cells = std::atof(v);
     if (const char* v = std::getenv("FJSPH_B200_MAX_KEY_BITS"))
         e->max_key_bits = std::min(29, std::max(6, std::atoi(v)));
+    if (const char* v = std::getenv("FJSPH_B200_LIST_STATS"))
+        e->list_stats = std::atoi(v) != 0;
     if (const char* v = std::getenv("FJSPH_B200_SWEEP_WARPS"))
         e->sweep_warps = (std::atoi(v) == 4) ? 4 : 8;
     if (const char* split = std::getenv("FJSPH_B200_SPLIT_SURFACE"))
@@ -902,7 +904,14 @@ int fjsph_upload_state(FjsphEngine* e, const FjsphStateView* s, int64_t bound_po
     e->n_owned = s->n;
     e->bound_points = bound_points;
     e->list_valid = false;
-    e->next_part_id = s->n;
+    /* FJSPH's id counter only grows (Init.cpp:283, inlet.cpp:610): a host that hands its ids back after erasures and
+       insertions must not see them reused */
+    {
+        int64_t next = s->n;
+        if (s->part_id)
+            for (int64_t k = 0; k < s->n; ++k) next = std::max(next, s->part_id[k] + 1);
+        e->next_part_id = (keep_blocks && s->part_id) ? std::max(e->next_part_id, next) : next;
+    }
     e->inlet_tables_dirty = true;
     const int n = int(e->n);
     e->launches += 2;
@@ -948,7 +957,12 @@ static int upload_state_split(FjsphEngine* e, const FjsphStateView* s, int64_t b
         FJ_CUDA(cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming));
     }
     e->list_valid = false;
-    e->next_part_id = s->n;
+    {
+        int64_t next = s->n;
+        if (s->part_id)
+            for (int64_t k = 0; k < s->n; ++k) next = std::max(next, s->part_id[k] + 1);
+        e->next_part_id = s->part_id ? std::max(e->next_part_id, next) : next; /* ids handed back: the counter only grows */
+    }
     e->inlet_tables_dirty = true;
     e->maxShift = 0.0;
     const int n = int(e->n);

@@ -219,6 +219,7 @@ struct FjsphEngine
     int mtab_cap = 0;
     int row_axis = -1;                  // FJSPH_B200_ROW_AXIS: 0 | 1 | 2 pins the row axis (default: the longest extent)
     double row_width_cells = 0.0;       // FJSPH_B200_ROW_WIDTH: row width along v, w in particle spacings (default 1)
+    bool list_stats = false;            // FJSPH_B200_LIST_STATS=1: print the fill of the lockstep walk after every build
     int max_key_bits = 25;              // FJSPH_B200_MAX_KEY_BITS: rows widen until the cell table fits 2^bits keys
     // Row-run neighbour lists (neighbours.cu).  A particle's neighbours inside one row are a window of consecutive
     // indices (rows are sorted along u), so a list is one RUN per neighbouring row: {first index, 32-bit membership

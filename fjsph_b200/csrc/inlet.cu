@@ -624,7 +624,12 @@ int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
         if (slabs)
             continue;
         total_shift += block_add;
-        if (shifts.n < 66)
+        if (shifts.n >= 66)
+        {
+            /* the index-shift table is full: later blocks would be remapped wrongly -- an error, not a silent drop */
+            fj_set_error("update_data: more than 66 inlet blocks insert particles in one step (index-shift table full)");
+            return FJSPH_ERR_CAPACITY;
+        }
         {
             /* callers at or after this block's OLD end (in the pre-insertion numbering) move by total_shift */
             shifts.first[shifts.n] = int(B.second - block_add - (total_shift - block_add));

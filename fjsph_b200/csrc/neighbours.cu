@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
 __global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
     k_exact_runs(const double4* __restrict__ P0, RowMap M, const unsigned* __restrict__ srun,
                  const int* __restrict__ srows, int scap, double sr, int ecap, uint2* __restrict__ erun,
-                 int* __restrict__ erows, int* __restrict__ ncount)
+                 int* __restrict__ erows, int* __restrict__ ncount, unsigned long long* __restrict__ stats)
 {
     int i, W;
     bool work;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
     const int nrow = srows[W];
     const unsigned* __restrict__ sp = srun + (size_t(W) * size_t(scap)) * 32u + lane;
     uint2* __restrict__ dst = erun + (size_t(W) * size_t(ecap)) * 32u + lane;
-    int kk = 0, cnt = 0;
+    int kk = 0, cnt = 0, steps = 0;
     auto test = [&](const unsigned j, const double4 q, const bool ok) -> bool {
         // nanoflann metric_L2_Simple order, no fma contraction (bit-exact sets)
         const double ddx = __dsub_rn(a.x, q.x), ddy = __dsub_rn(a.y, q.y), ddz = __dsub_rn(a.z, q.z);
@@ -351,6 +351,8 @@ __global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
             const int tz = mask ? __ffs(int(mask)) - 1 : 0;
             dst[size_t(kk) * 32u] = mask ? make_uint2(start + unsigned(tz), mask >> tz) : make_uint2(0u, 0u);
             kk++;
+            if (stats) /* lockstep steps a sweep spends on this slot: the longest trimmed window */
+                steps += __reduce_max_sync(0xffffffffu, mask ? 32 - __clz(int(mask >> tz)) : 0);
         }
         cnt += __popc(mask);
         d = dn;
@@ -359,6 +361,18 @@ __global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
         erows[W] = kk;
     if (valid)
         ncount[i] = cnt;
+    if (stats)
+    {
+        /* [0] lane-steps a sweep walks (32 x steps per warp), [1] pairs, [2] slots, [3] work warps */
+        const int pairs = __reduce_add_sync(0xffffffffu, valid ? cnt : 0);
+        if (lane == 0)
+        {
+            atomicAdd(&stats[0], 32ull * unsigned(steps));
+            atomicAdd(&stats[1], (unsigned long long)pairs);
+            atomicAdd(&stats[2], (unsigned long long)kk);
+            atomicAdd(&stats[3], 1ull);
+        }
+    }
 }
 
 // debug / parity view: the runs of every owned particle written out as caller indices (fjsph_get_neighbours)
@@ -812,11 +826,32 @@ int fj_build_neighbours(FjsphEngine* e)
     {
         KScope ks(e, "nb_list", 2);
         const RowMap M = fj_row_map(e, 0, fj_owned_classes(e));
+        unsigned long long* stats = nullptr;
+        if (e->list_stats)
+        {
+            stats = reinterpret_cast<unsigned long long*>(e->red_out) + 8; /* red_out holds 16 doubles: the upper half */
+            FJ_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long), e->stream));
+        }
         k_exact_runs<<<fj_row_grid(M), FJ_ROW_WARPS * 32, 0, e->stream>>>(e->lv[1].P0, M, e->srun, e->srows, e->scap, e->P.sr,
-                                                                         e->ecap, e->erun, e->erows, e->ncount);
+                                                                         e->ecap, e->erun, e->erows, e->ncount, stats);
         k_snapshot<<<fj_blocks(int(e->n), TPB), TPB, 0, e->stream>>>(e->lv[1].P0, e->x0, int(e->n));
     }
     FJ_CUDA(cudaGetLastError());
+    if (e->list_stats)
+    {
+        /* FJSPH_B200_LIST_STATS=1: how well the lockstep walk is filled (diagnostic, synchronises) */
+        unsigned long long h[4];
+        FJ_CUDA(cudaMemcpyAsync(h, reinterpret_cast<unsigned long long*>(e->red_out) + 8, sizeof(h), cudaMemcpyDeviceToHost,
+                                e->stream));
+        FJ_CUDA(cudaStreamSynchronize(e->stream));
+        std::fprintf(stderr,
+                     "[fjsph_b200] list: %llu pairs in %llu lane-steps (fill %.3f), %.1f slots and %.1f steps per warp, %llu work "
+                     "warps for %lld particles (lane use %.3f), row axis %d, %d x %d x %d cells, %d row offsets\n",
+                     h[1], h[0], h[0] ? double(h[1]) / double(h[0]) : 0.0, h[3] ? double(h[2]) / double(h[3]) : 0.0,
+                     h[3] ? double(h[0]) / 32.0 / double(h[3]) : 0.0, h[3], (long long)e->n_owned,
+                     h[3] ? double(e->n_owned) / (32.0 * double(h[3])) : 0.0, e->grid.ax0, e->grid.nx, e->grid.ny, e->grid.nz,
+                     e->n_row_off);
+    }
     e->x_moved = false;
     e->list_valid = true;
     e->nb_builds++;

@@ -16,8 +16,10 @@
 //   dataset = u32 name_len | name | u32 type (0 f64, 1 i32, 2 i64) | u64 count | data
 // One dataset beyond the reference's set: "Curvature" (SPHPart::curve), which find_timestep reads for the surface-tension
 // limit before the first resumed step has recomputed it (Integration.cpp:393-396); a reader may ignore it.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -110,10 +112,12 @@ extern "C" int fjsph_write_restart(FjsphEngine* e, const char* path, int32_t fra
     int st = fjsph_download_state(e, 1, &s);
     if (st)
         return st;
-    FILE* f = fopen(path, "wb");
+    /* written beside the target and renamed over it: a crash mid-write never damages the checkpoint that is there */
+    const std::string tmp_path = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp_path.c_str(), "wb");
     if (!f)
     {
-        fj_set_error("write_restart: cannot open \"%s\"", path);
+        fj_set_error("write_restart: cannot open \"%s\"", tmp_path.c_str());
         return FJSPH_ERR_IO;
     }
     Writer w{f};
@@ -168,20 +172,42 @@ extern "C" int fjsph_write_restart(FjsphEngine* e, const char* path, int32_t fra
     w.dataset("Cell density", 0, cellRho);
     w.dataset("Cell pressure", 0, cellP);
     w.dataset("Curvature", 0, curve);
-    const bool ok = w.ok && fclose(f) == 0;
-    if (!ok)
+    const bool ok = w.ok && fflush(f) == 0;
+    const bool closed = fclose(f) == 0;
+    if (!ok || !closed || std::rename(tmp_path.c_str(), path) != 0)
     {
+        std::remove(tmp_path.c_str());
         fj_set_error("write_restart: short write to \"%s\"", path);
         return FJSPH_ERR_IO;
     }
     return FJSPH_OK;
 }
 
+static int read_restart_impl(FjsphEngine* e, const char* path, int32_t* frame, FILE*& f);
+
+// A damaged or truncated file is an error return, never an exception across the C boundary (the driver overwrites its
+// only checkpoint every frame: every length read from the file is bounded before anything is sized by it).
 extern "C" int fjsph_read_restart(FjsphEngine* e, const char* path, int32_t* frame)
+{
+    FILE* f = nullptr;
+    try
+    {
+        return read_restart_impl(e, path, frame, f);
+    }
+    catch (const std::exception& ex)
+    {
+        if (f)
+            fclose(f);
+        fj_set_error("read_restart: \"%s\" could not be read (%s)", path ? path : "(null)", ex.what());
+        return FJSPH_ERR_IO;
+    }
+}
+
+static int read_restart_impl(FjsphEngine* e, const char* path, int32_t* frame, FILE*& f)
 {
     cudaSetDevice(e->device);
     fj_halo_wait(e);
-    FILE* f = path ? fopen(path, "rb") : nullptr;
+    f = path ? fopen(path, "rb") : nullptr;
     if (!f)
     {
         fj_set_error("read_restart: cannot open \"%s\"", path ? path : "(null)");
@@ -194,15 +220,17 @@ extern "C" int fjsph_read_restart(FjsphEngine* e, const char* path, int32_t* fra
     if (!r.ok || std::memcmp(magic, kMagic, 8) != 0 || version != kVersion || dim != 3)
     {
         fclose(f);
+        f = nullptr;
         fj_set_error("read_restart: \"%s\" is not a version-%u 3D restart file of this engine", path, kVersion);
         return FJSPH_ERR_IO;
     }
     const int64_t n = r.get<int64_t>(), bound_points = r.get<int64_t>(), next_part_id = r.get<int64_t>();
     const int32_t fr = r.get<int32_t>();
     const uint32_t n_blocks = r.get<uint32_t>(), psize = r.get<uint32_t>();
-    if (!r.ok || psize != sizeof(FjsphParams) || n <= 0 || n > e->cap)
+    if (!r.ok || psize != sizeof(FjsphParams) || n <= 0 || n > e->cap || n_blocks > 4096u)
     {
         fclose(f);
+        f = nullptr;
         fj_set_error("read_restart: %lld particles / a %u-byte parameter block do not fit this engine (capacity %lld, %zu bytes)",
                      (long long)n, psize, (long long)e->cap, sizeof(FjsphParams));
         return FJSPH_ERR_CAPACITY;
@@ -225,9 +253,21 @@ extern "C" int fjsph_read_restart(FjsphEngine* e, const char* path, int32_t* fra
         B.b.no_slip = r.get<int32_t>();
         B.b.block_type = r.get<int32_t>();
         B.b.fixed_vel_or_dynamic = r.get<int32_t>();
-        B.times.resize(r.get<uint32_t>());
+        const uint32_t n_times = r.get<uint32_t>();
+        if (!r.ok || n_times > 65536u)
+        {
+            r.ok = false;
+            break;
+        }
+        B.times.resize(n_times);
         r.raw(B.times.data(), B.times.size() * sizeof(double));
-        B.vels.resize(r.get<uint32_t>());
+        const uint32_t n_vels = r.get<uint32_t>();
+        if (!r.ok || n_vels != 3u * std::max(1u, n_times)) /* one velocity per time stamp, or the single constant one */
+        {
+            r.ok = false;
+            break;
+        }
+        B.vels.resize(n_vels);
         r.raw(B.vels.data(), B.vels.size() * sizeof(double));
         r.raw(B.b.insert_norm, sizeof(B.b.insert_norm));
         B.b.insconst = r.get<double>();
@@ -258,7 +298,9 @@ extern "C" int fjsph_read_restart(FjsphEngine* e, const char* path, int32_t* fra
         curve(N, 0.0);
     std::vector<int32_t> b(N);
     std::vector<int64_t> pid(N), cid(N);
-    unsigned seen = 0;
+    /* one bit per required dataset: a file holding one dataset twice and lacking another is not complete */
+    uint32_t seen_bits = 0;
+    enum { D_XI = 0, D_V = 3, D_ACC = 6, D_CELLV = 9, D_P = 12, D_RHO, D_RRHO, D_M, D_CRHO, D_CP, D_B, D_PID, D_CID, D_COUNT };
     const uint32_t nds = r.ok ? r.get<uint32_t>() : 0u;
     for (uint32_t k = 0; k < nds && r.ok; ++k)
     {
@@ -278,31 +320,31 @@ extern "C" int fjsph_read_restart(FjsphEngine* e, const char* path, int32_t* fra
             break;
         }
         std::vector<double> tmp;
-        auto vec_comp = [&](std::vector<double>& dst, const char* prefix) {
+        auto vec_comp = [&](std::vector<double>& dst, const char* prefix, int bit0) {
             for (int d = 0; d < 3; ++d)
                 if (name == std::string(prefix) + kAxis[d] && type == 0)
                 {
                     tmp.resize(N);
                     r.raw(tmp.data(), N * sizeof(double));
                     for (size_t i = 0; i < N; ++i) dst[3 * i + size_t(d)] = tmp[i];
-                    seen++;
+                    seen_bits |= 1u << (bit0 + d);
                     return true;
                 }
             return false;
         };
-        auto scalar = [&](std::vector<double>& dst, const char* nm) {
+        auto scalar = [&](std::vector<double>& dst, const char* nm, int bit) {
             if (name == nm && type == 0)
             {
                 r.raw(dst.data(), N * sizeof(double));
-                seen++;
+                seen_bits |= 1u << bit;
                 return true;
             }
             return false;
         };
-        if (vec_comp(xi, "Position coordinate ") || vec_comp(v, "Velocity ") || vec_comp(acc, "Acceleration ") ||
-            vec_comp(cellV, "Cell velocity ") || scalar(p, "Pressure") || scalar(rho, "Density") ||
-            scalar(Rrho, "Density gradient") || scalar(m, "Mass") || scalar(cellRho, "Cell density") ||
-            scalar(cellP, "Cell pressure"))
+        if (vec_comp(xi, "Position coordinate ", D_XI) || vec_comp(v, "Velocity ", D_V) || vec_comp(acc, "Acceleration ", D_ACC) ||
+            vec_comp(cellV, "Cell velocity ", D_CELLV) || scalar(p, "Pressure", D_P) || scalar(rho, "Density", D_RHO) ||
+            scalar(Rrho, "Density gradient", D_RRHO) || scalar(m, "Mass", D_M) || scalar(cellRho, "Cell density", D_CRHO) ||
+            scalar(cellP, "Cell pressure", D_CP))
             continue;
         if (name == "Curvature" && type == 0)
         {
@@ -312,25 +354,27 @@ extern "C" int fjsph_read_restart(FjsphEngine* e, const char* path, int32_t* fra
         if (name == "Boundary condition" && type == 1)
         {
             r.raw(b.data(), N * sizeof(int32_t));
-            seen++;
+            seen_bits |= 1u << D_B;
         }
         else if (name == "Particle ID" && type == 2)
         {
             r.raw(pid.data(), N * sizeof(int64_t));
-            seen++;
+            seen_bits |= 1u << D_PID;
         }
         else if (name == "Cell ID" && type == 2)
         {
             r.raw(cid.data(), N * sizeof(int64_t));
-            seen++;
+            seen_bits |= 1u << D_CID;
         }
-        else /* unknown dataset: skip it */
-            fseek(f, long(count * (type == 1 ? 4u : 8u)), SEEK_CUR);
+        else if (type > 2u || fseek(f, long(count * (type == 1 ? 4u : 8u)), SEEK_CUR) != 0) /* unknown dataset: skip it */
+            r.ok = false;
     }
     fclose(f);
-    if (!r.ok || seen != 21)
+    f = nullptr;
+    if (!r.ok || seen_bits != (1u << D_COUNT) - 1u)
     {
-        fj_set_error("read_restart: \"%s\" is truncated or lacks datasets (%u of 21 found)", path, seen);
+        fj_set_error("read_restart: \"%s\" is truncated or lacks datasets (%d of %d found)", path, __builtin_popcount(seen_bits),
+                     int(D_COUNT));
         return FJSPH_ERR_IO;
     }
     int st = fjsph_set_params(e, &P);

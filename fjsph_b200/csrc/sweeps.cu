@@ -64,31 +64,49 @@ __device__ __forceinline__ double4 gather_rw(const double4* base, unsigned j)
     return v;
 }
 
+#ifndef FJ_PREFETCH
+#define FJ_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Walks the runs of work warp W in lockstep: slot k holds, for every lane, the window {first, mask} of its neighbours
 // inside one neighbouring row; the warp steps o = 0 .. T-1 (T = the longest window of the slot) and lane l visits
 // neighbour first_l + o when bit o of its mask is set.  load(j, take) issues the record gathers of one neighbour (and
-// returns them; nothing is loaded when !take), body(j, rec) consumes them.  Software-pipelined: the gathers of step
-// s+1 are issued before the arithmetic of step s, the next slot's descriptors one slot ahead.  Every lane of the warp
-// must call this (the trip counts are warp votes); lanes with active == false visit nobody.
-template <class Load, class Body>
-__device__ __forceinline__ void for_neighbours(const RunView& L, int W, bool active, Load&& load, Body&& body)
+// returns them; nothing is loaded when !take), body(j, rec) consumes them, prefetch(j) touches the records of
+// neighbour j.  Software-pipelined: the gathers of step s+1 are issued before the arithmetic of step s; the
+// descriptors run two slots ahead, and on entering a slot every lane prefetches the first and the last record of its
+// window in the NEXT slot into L1 -- between them the lanes of a warp cover the whole stretch of the next row (their
+// windows are shifted copies of each other), so the gathers of a fresh row find their lines on the way instead of
+// stalling the warp on an L2 round trip at every row.  Every lane of the warp must call this (the trip counts are warp
+// votes); lanes with active == false visit nobody.
+template <class Load, class Body, class Prefetch>
+__device__ __forceinline__ void for_neighbours(const RunView& L, int W, bool active, Load&& load, Body&& body,
+                                               Prefetch&& prefetch)
 {
     const int nrow = L.erows[W];
     const uint2* __restrict__ dp = L.erun + (size_t(W) * size_t(L.ecap)) * 32u + (threadIdx.x & 31u);
     int k = 0, T = 0, o = 0;
-    uint2 d = make_uint2(0u, 0u), dn = make_uint2(0u, 0u);
+    uint2 d = make_uint2(0u, 0u), dn = make_uint2(0u, 0u), dnn = make_uint2(0u, 0u);
     if (nrow > 0)
         dn = ld_desc(dp);
+    if (nrow > 1)
+        dnn = ld_desc(dp + 32u);
     /* next slot with somebody in it: false at the end of the list (warp-uniform) */
     auto next_slot = [&]() -> bool {
         while (k < nrow)
         {
             d = dn;
+            dn = dnn;
             if (!active)
                 d.y = 0u;
             ++k;
-            if (k < nrow)
-                dn = ld_desc(dp + size_t(k) * 32u);
+            if (k + 1 < nrow)
+                dnn = ld_desc(dp + size_t(k + 1) * 32u);
+            if (FJ_PREFETCH && k < nrow && active && dn.y != 0u)
+            {
+                prefetch(dn.x);
+                prefetch(dn.x + unsigned(31 - __clz(int(dn.y))));
+            }
             T = __reduce_max_sync(FJ_FULL, 32 - __clz(int(d.y)));
             if (T > 0)
                 return true;
@@ -288,6 +306,12 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
                     colour += pj.w * W_;
                     npd_ += W_;
                 }
+            },
+            [&](const unsigned j) {
+                prefetch_l1(S.P0 + j);
+                prefetch_l1(S.P1 + j);
+                if (FROZEN)
+                    prefetch_l1(lv.x0 + j);
             });
         if (active)
         {
@@ -506,6 +530,14 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
                     Rrhod += drho * w;
                 }
             }
+        },
+        [&](const unsigned j) {
+            prefetch_l1(S.P0 + j);
+            prefetch_l1(S.P3 + j);
+            if (DISS)
+                prefetch_l1(S.P1 + j);
+            if (FROZEN)
+                prefetch_l1(lv.x0 + j);
         });
     if (SURF)
     {
@@ -722,6 +754,15 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
                 const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
                 maxU2 = fmax(maxU2, ux * ux + uy * uy + uz * uz);
             }
+        },
+        [&](const unsigned j) {
+            prefetch_l1(S.P4 + j);
+            if (need_pos)
+                prefetch_l1(S.P0 + j);
+            if (do_shift)
+                prefetch_l1(S.P1 + j);
+            if (FROZEN && need_pos)
+                prefetch_l1(lv.x0 + j);
         });
     if (CLASS == 1 && has_fluid)
         min_c = 0.0;
@@ -1073,6 +1114,13 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
             {
                 Rrho_ -= ug;
             }
+        },
+        [&](const unsigned j) {
+            prefetch_l1(S.P0 + j);
+            prefetch_l1(S.P1 + j);
+            prefetch_l1(S.P2 + j);
+            if (FROZEN)
+                prefetch_l1(lv.x0 + j);
         });
     if (ALE)
     {

@@ -98,6 +98,12 @@ def golden_cases():
     out["inlet_jet_mesh_first_cell"] = (pj, "ref3d", 3, 6, dict(ale=1, asource=1), pipe_mesh, None)
     out["jet_deck_jittered"] = (jittered_jet_deck(), "ref3d", 3, 12, {}, None, None)
     out["droplet_sheared_mesh_rk4"] = (dm, "ref3d", 3, 3, dict(ale=1, asource=1, delta_t_min=1e-9, solver_type=1), sheared, 0)
+    # Check_Error's unstable-step branch (Newmark_Beta.cpp:32-48): a CFL number of 6 makes the sub-iterations diverge, so
+    # pnp1 = pn, the list is rebuilt, dt halves and the step starts over -- once at step 0, twice at the steps after it
+    # (dt = cfl * safe_dt / 2^k shows k); with walls the rebuild happens between two wall treatments
+    unstable = dict(ale=1, cfl=6.0, cfl_max=6.0, max_subits=2, delta_t_max=1.0, delta_t_min=1e-12)
+    out["block_nb_unstable_restart"] = (cases.synthetic_block(n=(10, 9, 8), jitter=0.1), "ref3d", 3, 3, unstable, None, None)
+    out["tank_nb_unstable_restart"] = (tank, "ref3d", 3, 3, dict(unstable, cfl=8.0, cfl_max=8.0), None, None)
     return out
 
 
@@ -177,7 +183,10 @@ def run(o, steps):
 def main():
     if not orc.have_ref():
         orc.build_ref()
+    only = set(sys.argv[1:])  # optional: names of the vectors to (re)make
     for name, (case, kind, dim, steps, extra, mesh, cell0) in golden_cases().items():
+        if only and name not in only:
+            continue
         o = make_sim(case, kind, dim, extra, mesh, cell0)
         # stdout of the reference's step table is noise here
         table = run(o, steps)

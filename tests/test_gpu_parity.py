@@ -195,6 +195,37 @@ def test_full_step_parity(which, solver):
     assert pe.cfl == po.cfl and pe.n_stable == po.n_stable and pe.n_unstable == po.n_unstable
 
 
+@pytest.mark.parametrize("which,cfl", [("block", 6.0), ("walls", 8.0)])
+def test_unstable_step_restart_parity(which, cfl):
+    """Check_Error's unstable-step branch (Newmark_Beta.cpp:32-48; engine: integrate.cu, fj_integrate_no_update): a CFL
+    number this large makes the sub-iterations diverge, so pnp1 = pn (every frozen-term array restored), the list is
+    rebuilt mid-step -- with walls, between two wall treatments --, dt halves and the iteration counter restarts.  The
+    engine and the oracle (itself pinned on this branch against the compiled reference, tests/test_oracle_vs_reference.py::
+    test_unstable_step_restarts, and by tests/golden/ref_*_unstable_restart.npz) take the same number of halvings and
+    land on the same state.  A diverging fixed-point iteration amplifies summation-order noise ~2.5x per sub-iteration, so
+    the rate bars are those of the stiff jet deck (tests/test_golden_reference.py)."""
+    case = full_step_case(which)
+    o, e, p = make_pair(case, cfl=cfl, cfl_max=cfl, max_subits=2, delta_t_max=1.0, delta_t_min=1e-12)
+    halvings = []
+    for step in range(3):
+        cfl_now = o.params.cfl
+        err_o, so = o.integrate()
+        se = e.integrate()
+        ctx = "%s unstable step %d" % (which, step)
+        assert se.iterations == so.iterations, ctx
+        assert abs(se.dt - so.dt) <= 1e-9 * so.dt, ctx
+        assert se.neighbour_builds >= 2, ctx
+        halvings.append(np.log2(cfl_now * so.safe_dt / so.dt))
+        assert_fields_close(e, o, FLAG_FIELDS, context=ctx)
+        assert_fields_close(e, o, ("xi", "rho"), tol=1e-8, context=ctx)
+        assert_fields_close(e, o, ("v", "p"), tol=1e-6, context=ctx)
+        assert_fields_close(e, o, ("acc", "Rrho"), tol=1e-4, context=ctx)
+        assert_fields_close(e, o, ("xi", "rho"), tol=1e-8, level=0, context=ctx + " pn")
+    assert max(halvings) >= 0.99, halvings  # at least one step was halved
+    pe, po = e.params, o.params
+    assert pe.cfl == po.cfl and pe.n_stable == po.n_stable and pe.n_unstable == po.n_unstable
+
+
 def test_uniform_drift_keeps_the_superset_list():
     """A block drifting at 30 m/s moves every particle by more than skin/2 per step but no pair apart: the superset
     (skin) list must survive (no cell-list sweep after the first step), and the exact lists filtered from it must

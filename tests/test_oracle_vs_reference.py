@@ -178,6 +178,31 @@ def test_eighty_steps_track_the_reference():
     assert_same(a, r, ("acc", "Rrho", "vPert"), 1e-8, "80 steps")
 
 
+@pytest.mark.parametrize("which,cfl,subits", [("block", 6.0, 2), ("block", 12.0, 4), ("tank", 8.0, 2)])
+def test_unstable_step_restarts(which, cfl, subits):
+    """Check_Error's unstable-step branch (Newmark_Beta.cpp:32-48), part of the integrator contract: with a CFL
+    number this large the sub-iterations diverge (rms_error > 0 past max_subits), so pnp1 = pn, the list is rebuilt, dt
+    halves, the iteration counter restarts -- as often as it takes.  dt = cfl * safe_dt / 2^k shows k >= 1 halvings; the
+    restatement and the reference agree on k, on the restored state and on the CFL controller's reaction."""
+    case = cases.synthetic_block(n=(10, 9, 8), jitter=0.1) if which == "block" else cases.box_with_walls(n=(7, 6, 6), jitter=0.05)
+    a, r = pair(case, "ref3d", ale=1, cfl=cfl, cfl_max=cfl, max_subits=subits, delta_t_max=1.0, delta_t_min=1e-12)
+    halvings = []
+    for step in range(3):
+        cfl_now = r.params.cfl
+        _, sa = a.integrate()
+        _, sr = r.integrate()
+        ctx = "%s step %d" % (which, step)
+        assert sa.iterations == sr.iterations and abs(sa.dt - sr.dt) <= 1e-12 * sr.dt, ctx
+        assert abs(sa.rms_error - sr.rms_error) <= 1e-6, ctx
+        halvings.append(np.log2(cfl_now * sr.safe_dt / sr.dt))
+    assert max(halvings) >= 0.99 and all(abs(h - round(h)) < 1e-6 for h in halvings), halvings
+    pa, pr = a.params, r.params
+    assert pa.cfl == pr.cfl and pa.n_stable == pr.n_stable and pa.n_unstable == pr.n_unstable
+    for level in (0, 1):
+        assert_same(a, r, INTS, 0.0, which, level)
+        assert_same(a, r, FLOATS, 1e-9, which, level)
+
+
 WALLS = [("ghost", 2, 0, None, None, {}), ("ghost_noslip", 2, 1, None, None, {}), ("adami_noslip", 1, 1, None, None, {}),
          ("adami_moving", 1, 0, [0.0, 0.004, 0.009], [[0.1, 0, 0], [0, 0.2, 0], [0, 0, 0]], {}),
          ("ghost_noslip_moving_rk4", 2, 1, [0.0, 0.004], [[0.1, 0, 0], [0, 0.2, 0]], dict(solver_type=1)),
