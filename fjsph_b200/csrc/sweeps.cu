@@ -150,6 +150,98 @@ __device__ __forceinline__ void for_neighbours(const RunView& L, int W, bool act
     }
 }
 
+// Branch-free, two neighbours at a time.  load(j) gathers the records of neighbour j unconditionally -- a lane with
+// nobody to visit at a step is handed its OWN index (self), a valid address whose pair terms vanish or are masked by
+// the `take` flags body(recA, takeA, recB, takeB) receives -- so the loop body is one basic block and the compiler
+// interleaves the two independent FP64 dependency chains of the two pairs: the pair algebra is a long serial chain (d^2 -> rsqrt -> r ->
+// kernel gradient -> accumulators) and with ~3 warps per scheduler a single chain leaves the FP64 pipe idle two cycles
+// out of three (ncu, profiles/r2b_*).  warm(first, last) loads one word of the first and of the last record of a
+// lane's window in the NEXT slot and returns them; the walker folds them into a checksum one slot later, so the
+// loads are real (they allocate in L1: `prefetch.global.L1` changed nothing on this part) and nobody waits for them.
+// Returns the checksum (the caller keeps it alive with a store that never happens).
+struct Warm
+{
+    unsigned a, b, c, d, e, f;
+};
+__device__ __forceinline__ unsigned fold(const Warm& w) { return w.a ^ w.b ^ w.c ^ w.d ^ w.e ^ w.f; }
+__device__ __forceinline__ unsigned ld_word(const void* p)
+{
+    unsigned v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+template <class Load, class Body, class WarmFn>
+__device__ __forceinline__ unsigned for_neighbours2(const RunView& L, int W, bool active, unsigned self, Load&& load,
+                                                    Body&& body, WarmFn&& warm)
+{
+    const int nrow = L.erows[W];
+    const uint2* __restrict__ dp = L.erun + (size_t(W) * size_t(L.ecap)) * 32u + (threadIdx.x & 31u);
+    int k = 0, T = 0, o = 0;
+    unsigned sink = 0u;
+    Warm pend = {0u, 0u, 0u, 0u, 0u, 0u};
+    uint2 d = make_uint2(0u, 0u), dn = make_uint2(0u, 0u), dnn = make_uint2(0u, 0u);
+    if (nrow > 0)
+        dn = ld_desc(dp);
+    if (nrow > 1)
+        dnn = ld_desc(dp + 32u);
+    /* next slot with somebody in it: false at the end of the list (warp-uniform) */
+    auto next_slot = [&]() -> bool {
+        while (k < nrow)
+        {
+            d = dn;
+            dn = dnn;
+            if (!active)
+                d.y = 0u;
+            ++k;
+            if (k + 1 < nrow)
+                dnn = ld_desc(dp + size_t(k + 1) * 32u);
+            sink ^= fold(pend); /* issued one slot ago */
+            {
+                const bool any = k < nrow && active && dn.y != 0u;
+                const unsigned first = any ? dn.x : self;
+                pend = warm(first, any ? first + unsigned(31 - __clz(int(dn.y))) : self);
+            }
+            T = __reduce_max_sync(FJ_FULL, 32 - __clz(int(d.y)));
+            if (T > 0)
+                return true;
+        }
+        return false;
+    };
+    /* the lane's neighbour at the next step, or itself when it has none there; false past the end of the list */
+    auto advance = [&](unsigned& j, bool& take) -> bool {
+        if (++o >= T)
+        {
+            if (!next_slot())
+            {
+                j = self;
+                take = false;
+                return false;
+            }
+            o = 0;
+        }
+        take = ((d.y >> o) & 1u) != 0u;
+        j = take ? d.x + unsigned(o) : self;
+        return true;
+    };
+    o = -1;
+    T = 0;
+    for (;;)
+    {
+        unsigned ja, jb;
+        bool ta, tb;
+        if (!advance(ja, ta))
+            break;
+        const bool more = advance(jb, tb);
+        const auto ra = load(ja);
+        const auto rb = load(jb);
+        body(ra, ta, rb, tb);
+        if (!more)
+            break;
+    }
+    return sink ^ fold(pend);
+}
+
 // plain form for the wall treatments (few particles, short bodies): body(j)
 template <class Body>
 __device__ __forceinline__ void for_neighbours_simple(const RunView& L, int W, bool active, Body&& body)
@@ -188,6 +280,20 @@ __device__ __forceinline__ double fj_rsqrt(double x)
     y = fma(y, e, y);
     e = fma(-hx * y, y, 0.5);
     return fma(y, e, y);
+}
+
+// 1/sqrt(x) for positive normal x with ONE third-order step on the MUFU.RSQ64H seed: y = y0 (1 + e/2 + 3 e^2 / 8),
+// e = 1 - x y0^2 (error ~ seed^3: full double precision) -- four dependent FP64 operations instead of the six of two
+// Newton steps, on the critical path of every pair
+__device__ __forceinline__ double fj_rsqrt3(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double t = x * y0;
+    const double e = fma(-t, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double ye = y0 * e;
+    return fma(ye, p, y0);
 }
 
 // r of a pair the way the reference takes it -- sqrt of the list's d^2, the distance at the list build -- with 1 / r
@@ -1051,76 +1157,109 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         }
     }
 
-    for_neighbours(
-        lv, W, active,
-        [&](const unsigned j, const bool take) {
+    /* one pair, branch-free (a lane's own index as j gives exact zeros: Rji = 0, gradK = 0).  Critical path kept short:
+       everything that does not wait for 1/r is formed beside it (V_j Rji, rr / 2H), t = 1 - r / 2H comes straight out of
+       rr and 1/r, the kernel gradient as (gk_fac t)(t t). */
+    struct Geo
+    {
+        double rx, ry, rz, r, ir;
+    };
+    const double m_half_iH = -0.5 * C.iH, tiny2 = (1e-12 * C.H) * (1e-12 * C.H);
+    auto pair_main = [&](const RecF& q) -> Geo {
+        const double4 pj = q.p;
+        const double4 vj = q.v;
+        const double4 qj = q.q;
+        Geo g;
+        g.rx = pj.x - pi.x;
+        g.ry = pj.y - pi.y;
+        g.rz = pj.z - pi.z;
+        const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
+        const double r2c = fma(g.rz, g.rz, fma(g.ry, g.ry, g.rx * g.rx));
+        double rr = r2c;
+        if (FROZEN)
+        {
+            const double ex = q.x0.x - x0i.x, ey = q.x0.y - x0i.y, ez = q.x0.z - x0i.z;
+            rr = fma(ez, ez, fma(ey, ey, ex * ex));
+        }
+        g.ir = fj_rsqrt3(fmax(rr, 1e-300));
+        g.r = rr * g.ir;
+        const double idist2 = fj_rcp(rr + eps_f);
+        const double t = fma(rr * m_half_iH, g.ir, 1.0); /* 1 - r / 2H */
+        const double gk = (rr < tiny2) ? 0.0 : (C.gk_fac * t) * (t * t); /* Kernel.h:49-61: 0 when r / H < 1e-12 */
+        const double rho_j = vj.w;
+        const double s = pj.w * gk;                                       /* V_j gk */
+        const double Gx = (pj.w * g.rx) * gk, Gy = (pj.w * g.ry) * gk, Gz = (pj.w * g.rz) * gk; /* V_j gradK */
+        const double pf = rho_j * (qi.w + qj.w);
+        ax = fma(-pf, Gx, ax);
+        ay = fma(-pf, Gy, ay);
+        az = fma(-pf, Gz, az);
+        const double vf = fma(nu_irho_i, rho_j, C.nu) * ((s * r2c) * idist2);
+        vx = fma(vf, ux, vx);
+        vy = fma(vf, uy, vy);
+        vz = fma(vf, uz, vz);
+        const double ug = ux * Gx + uy * Gy + uz * Gz;
+        if (ALE)
+        {
+            const double pjg = qj.x * Gx + qj.y * Gy + qj.z * Gz; /* V_j (vPert_j . gradK) */
+            alx = fma(ux, pjg, alx);
+            aly = fma(uy, pjg, aly);
+            alz = fma(uz, pjg, alz);
+            sgx += Gx;
+            sgy += Gy;
+            sgz += Gz;
+            Rrho_ -= ug + pjg;
+            Rrhoc_ = fma(rho_j, pjg, Rrhoc_);
+        }
+        else
+        {
+            Rrho_ -= ug;
+        }
+        return g;
+    };
+    /* pairwise surface tension, Kernel.h:101-113 (surface-zone particles only under ALE) */
+    auto pair_st = [&](const RecF& q, const Geo& g, const bool take) {
+        const double fac = (b_i == FJSPH_BOUND || q.b == FJSPH_BOUND) ? st_bound_fac : 1.0;
+        const double sf = take ? -npdm2 * fac * cospi(q_st * g.r) * g.ir : 0.0;
+        sx = fma(sf, g.rx, sx);
+        sy = fma(sf, g.ry, sy);
+        sz = fma(sf, g.rz, sz);
+    };
+    const unsigned warm_sink = for_neighbours2(
+        lv, W, active, unsigned(i),
+        [&](const unsigned j) {
             RecF q;
-            if (take)
-            {
-                q.p = gather(S.P0, j);
-                q.v = gather(S.P1, j);
-                q.q = gather(S.P2, j);
-                if (do_st)
-                    q.b = __ldg(&S.b[j]);
-                if (FROZEN)
-                    q.x0 = gather(lv.x0, j);
-            }
+            q.p = gather(S.P0, j);
+            q.v = gather(S.P1, j);
+            q.q = gather(S.P2, j);
+            if (do_st)
+                q.b = __ldg(&S.b[j]);
+            if (FROZEN)
+                q.x0 = gather(lv.x0, j);
             return q;
         },
-        [&](const unsigned j, const RecF& q) {
-            const double4 pj = q.p;
-            const double4 vj = q.v;
-            const double4 qj = q.q;
-            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-            const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
-            double rr, ir, r, r2c;
-            pair_dist<FROZEN>(x0i, q.x0, rx, ry, rz, rr, ir, r, r2c);
-            const double idist2 = fj_rcp(rr + eps_f);
-            const double t = wend_t(C, r);
-            const double rho_j = vj.w;
-            const double s = pj.w * wend_gk(C, r, t);               /* V_j gk */
-            const double Gx = s * rx, Gy = s * ry, Gz = s * rz;     /* V_j gradK */
-            const double pf = rho_j * (qi.w + qj.w);
-            ax -= pf * Gx;
-            ay -= pf * Gy;
-            az -= pf * Gz;
-            const double vf = fma(nu_irho_i, rho_j, C.nu) * ((s * r2c) * idist2);
-            vx += vf * ux;
-            vy += vf * uy;
-            vz += vf * uz;
-            /* pairwise surface tension, Kernel.h:101-113 */
+        [&](const RecF& qa, const bool ta, const RecF& qb, const bool tb) {
+            const Geo ga = pair_main(qa);
+            const Geo gb = pair_main(qb);
             if (do_st)
             {
-                const double fac = (b_i == FJSPH_BOUND || q.b == FJSPH_BOUND) ? st_bound_fac : 1.0;
-                const double sf = -npdm2 * fac * cospi(q_st * r) * ir;
-                sx += sf * rx;
-                sy += sf * ry;
-                sz += sf * rz;
-            }
-            const double ug = ux * Gx + uy * Gy + uz * Gz;
-            if (ALE)
-            {
-                const double pjg = qj.x * Gx + qj.y * Gy + qj.z * Gz; /* V_j (vPert_j . gradK) */
-                alx += ux * pjg;
-                aly += uy * pjg;
-                alz += uz * pjg;
-                sgx += Gx;
-                sgy += Gy;
-                sgz += Gz;
-                Rrho_ -= ug + pjg;
-                Rrhoc_ += rho_j * pjg;
-            }
-            else
-            {
-                Rrho_ -= ug;
+                pair_st(qa, ga, ta);
+                pair_st(qb, gb, tb);
             }
         },
-        [&](const unsigned j) {
-            prefetch_l1(S.P0 + j);
-            prefetch_l1(S.P1 + j);
-            prefetch_l1(S.P2 + j);
+        [&](const unsigned first, const unsigned last) {
+            Warm w;
+            w.a = ld_word(S.P0 + first);
+            w.b = ld_word(S.P0 + last);
+            w.c = ld_word(S.P1 + first);
+            w.d = ld_word(S.P1 + last);
+            w.e = ld_word(S.P2 + first);
+            w.f = ld_word(S.P2 + last);
             if (FROZEN)
-                prefetch_l1(lv.x0 + j);
+            {
+                w.a ^= ld_word(lv.x0 + first);
+                w.b ^= ld_word(lv.x0 + last);
+            }
+            return w;
         });
     if (ALE)
     {
@@ -1149,6 +1288,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         ay += f * bn.y;
         az += f * bn.z;
     }
+    if (warm_sink == 0x9e3779b9u && C.dx < -1.0)
+        S.cellID[i] = -1; /* never happens: keeps the warming loads of the walk alive */
     if (!active)
         return; /* the walk is over: nothing below votes */
     const double4 av = S.AV[i];

@@ -183,7 +183,8 @@ def _ptr(a):
 
 
 class Oracle:
-    """One simulation on the CPU oracle.  kind: '3d', '2d', '3d_fast', '3d_fast_serialdiss'."""
+    """One simulation on the CPU oracle.  kind: '3d', '2d', '3d_mt' (the parity build, particle loops threaded),
+    '3d_fast', '3d_fast_serialdiss' (timing builds)."""
 
     def __init__(self, params: "OrcParams", kind: str | None = None):
         self.dim = int(params.dim)

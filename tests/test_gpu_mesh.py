@@ -148,3 +148,42 @@ def test_tau_mesh_with_quadrilateral_faces(tmp_path):
             ref = o.get(f)
             assert np.abs(got[f] - ref).max() <= tol * max(np.abs(ref).max(), 1e-300), (step, f)
 
+
+def test_q6_crossed_quadrilaterals_keep_the_cell_below(tmp_path):
+    """GPU twin of tests/test_tau_cpu.py::test_coupled_run_on_quadrilateral_faces_follows_the_reference (SURVEY Q6): x-normal
+    quadrilaterals, every particle started in the cell below its own; the three-edge crossing test keeps it there.  The
+    engine must report the oracle's cells (which are FJSPH's, pinned on the CPU) and its state.  (Green on a B200 since
+    round 1, GPUTEST_r01.json.)"""
+    from fjsph_b200 import frontend
+    from tests.tau_case import write_tau
+
+    lo, hi, n = np.array([-0.1013, -0.1007, -0.1011]), np.array([0.1009, 0.1003, 0.1017]), (8, 9, 7)
+    mesh_file, sol_file, *_ = write_tau(tmp_path, lo, hi, n, lambda x: (1.0 + 40 * x[0], 21.55 - 30 * x[2], 5 * x[1]),
+                                        lambda x: 1.0e5 + 100 * x[1], lambda x: 1.1 + x[2], split="y")
+    tau = frontend.read_tau(mesh_file, sol_file)
+    case = cases.droplet(dx=0.0125, jitter=0.05)
+    params = dict(case["params"], delta_t_min=1e-9)
+    ijk = np.floor((case["xi"] - lo) / ((hi - lo) / np.array(n))).astype(int)
+    own = (ijk[:, 2] * n[1] + ijk[:, 1]) * n[0] + ijk[:, 0]
+    below = np.where(ijk[:, 2] > 0, own - n[0] * n[1], own).astype(np.int64)
+    o = orc.Oracle(orc.default_params(3, asource=1, **params))
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+    o.set_mesh(tau)
+    e = eng.Engine(eng.default_params(3, asource=1, **params), case["xi"].shape[0])
+    e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+    e.upload_mesh(tau)
+    for lvl in (0, 1):
+        o.set("cellID", below, lvl)
+        e.upload_level(lvl, cellID=below)
+    for step in range(2):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert se.iterations == so.iterations, step
+    got = e.download(("cellID", "xi", "v", "rho", "Af"))
+    ref = o.get("cellID")
+    assert np.array_equal(got["cellID"], ref)
+    found = ref >= 0
+    assert (ref[found] == below[found]).sum() > 0.9 * found.sum()
+    for f, tol in (("xi", 1e-10), ("rho", 1e-10), ("v", 1e-8), ("Af", 1e-6)):
+        r = o.get(f)
+        assert np.abs(got[f] - r).max() <= tol * max(np.abs(r).max(), 1e-300), f
