@@ -703,6 +703,8 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
         e->sweep_warps = (std::atoi(v) == 4) ? 4 : 8;
     if (const char* split = std::getenv("FJSPH_B200_SPLIT_SURFACE"))
         e->split_surface_sweep = std::string(split) != "0";
+    if (const char* v = std::getenv("FJSPH_B200_SPLIT_BELOW")) /* near-surface warp fraction below which the sweep splits */
+        e->split_surface_below = std::atof(v);
     FJ_CUDA(cudaMalloc(&e->near_inlet, cap * sizeof(int)));
     FJ_CUDA(cudaMemset(e->near_inlet, 0, cap * sizeof(int)));
     FJ_CUDA(cudaMalloc(&e->rk_sum_v, cap * sizeof(double4)));

@@ -46,7 +46,7 @@ struct RunView
 __device__ __forceinline__ uint2 ld_desc(const uint2* p)
 {
     uint2 v;
-    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    asm("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
 // 32-byte record gather with ONE 256-bit load (LDG.E.256).  Only for arrays no thread writes during the kernel.
@@ -153,56 +153,51 @@ __device__ __forceinline__ void for_neighbours(const RunView& L, int W, bool act
 // Branch-free, two neighbours at a time.  load(j) gathers the records of neighbour j unconditionally -- a lane with
 // nobody to visit at a step is handed its OWN index (self), a valid address whose pair terms vanish or are masked by
 // the `take` flags body(recA, takeA, recB, takeB) receives -- so the loop body is one basic block and the compiler
-// interleaves the two independent FP64 dependency chains of the two pairs: the pair algebra is a long serial chain (d^2 -> rsqrt -> r ->
-// kernel gradient -> accumulators) and with ~3 warps per scheduler a single chain leaves the FP64 pipe idle two cycles
-// out of three (ncu, profiles/r2b_*).  warm(first, last) loads one word of the first and of the last record of a
-// lane's window in the NEXT slot and returns them; the walker folds them into a checksum one slot later, so the
-// loads are real (they allocate in L1: `prefetch.global.L1` changed nothing on this part) and nobody waits for them.
-// Returns the checksum (the caller keeps it alive with a store that never happens).
-struct Warm
+// interleaves the two independent FP64 dependency chains of the two pairs: the pair algebra is a long serial chain
+// (d^2 -> rsqrt -> r -> kernel gradient -> accumulators) and with ~3 warps per scheduler a single chain leaves the FP64
+// pipe idle two cycles out of three (ncu, profiles/r2b_*).
+//
+// L1 staging: on entering a slot every lane queues `cp.async.ca` copies (LDGSTS: global -> L1 -> a scratch word of shared
+// memory nobody reads) of the first and the last record of its window in the NEXT slot, and of its descriptor four slots
+// on.  The copies cost no register and no scoreboard entry, nobody ever waits for them, and they pull the stretch of the
+// next row the warp is about to walk (the lanes' windows are shifted copies of each other: firsts and lasts cover it) into
+// L1, so the gathers of a fresh row and of its leading edge are L1 hits instead of one L2 round trip per step.
+// (`prefetch.global.L1` changed nothing on this part; plain loads into registers consumed a slot later stalled on the
+// register moves the compiler put behind them -- profiles/r2c_*.)
+__device__ __forceinline__ void stage_l1(const void* gptr)
 {
-    unsigned a, b, c, d, e, f;
-};
-__device__ __forceinline__ unsigned fold(const Warm& w) { return w.a ^ w.b ^ w.c ^ w.d ^ w.e ^ w.f; }
-__device__ __forceinline__ unsigned ld_word(const void* p)
-{
-    unsigned v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
+    __shared__ unsigned scratch[16 * 32];
+    const unsigned saddr = unsigned(__cvta_generic_to_shared(&scratch[threadIdx.x & 511u]));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr) : "memory");
 }
+__device__ __forceinline__ void stage_l1_drain() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <class Load, class Body, class WarmFn>
-__device__ __forceinline__ unsigned for_neighbours2(const RunView& L, int W, bool active, unsigned self, Load&& load,
-                                                    Body&& body, WarmFn&& warm)
+template <class Load, class Body, class StageFn>
+__device__ __forceinline__ void for_neighbours2(const RunView& L, int W, bool active, unsigned self, Load&& load,
+                                                Body&& body, StageFn&& stage)
 {
     const int nrow = L.erows[W];
     const uint2* __restrict__ dp = L.erun + (size_t(W) * size_t(L.ecap)) * 32u + (threadIdx.x & 31u);
     int k = 0, T = 0, o = 0;
-    unsigned sink = 0u;
-    Warm pend = {0u, 0u, 0u, 0u, 0u, 0u};
-    uint2 d = make_uint2(0u, 0u), dn = make_uint2(0u, 0u), dnn = make_uint2(0u, 0u);
+    uint2 d = make_uint2(0u, 0u), dn = make_uint2(0u, 0u);
+    for (int a = 1; a < 4 && a < nrow; ++a) stage_l1(dp + size_t(a) * 32u);
     if (nrow > 0)
         dn = ld_desc(dp);
-    if (nrow > 1)
-        dnn = ld_desc(dp + 32u);
     /* next slot with somebody in it: false at the end of the list (warp-uniform) */
     auto next_slot = [&]() -> bool {
         while (k < nrow)
         {
             d = dn;
-            dn = dnn;
             if (!active)
                 d.y = 0u;
             ++k;
-            if (k + 1 < nrow)
-                dnn = ld_desc(dp + size_t(k + 1) * 32u);
-            sink ^= fold(pend); /* issued one slot ago */
-            {
-                const bool any = k < nrow && active && dn.y != 0u;
-                const unsigned first = any ? dn.x : self;
-                pend = warm(first, any ? first + unsigned(31 - __clz(int(dn.y))) : self);
-            }
+            if (k + 3 < nrow)
+                stage_l1(dp + size_t(k + 3) * 32u);
+            if (k < nrow)
+                dn = ld_desc(dp + size_t(k) * 32u); /* an L1 hit: staged three slots ago */
             T = __reduce_max_sync(FJ_FULL, 32 - __clz(int(d.y)));
+            if (k < nrow && active && dn.y != 0u) /* the records of the slot after this one */
+                stage(dn.x, dn.x + unsigned(31 - __clz(int(dn.y))));
             if (T > 0)
                 return true;
         }
@@ -239,7 +234,7 @@ __device__ __forceinline__ unsigned for_neighbours2(const RunView& L, int W, boo
         if (!more)
             break;
     }
-    return sink ^ fold(pend);
+    stage_l1_drain();
 }
 
 // plain form for the wall treatments (few particles, short bodies): body(j)
@@ -1224,7 +1219,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         sy = fma(sf, g.ry, sy);
         sz = fma(sf, g.rz, sz);
     };
-    const unsigned warm_sink = for_neighbours2(
+    for_neighbours2(
         lv, W, active, unsigned(i),
         [&](const unsigned j) {
             RecF q;
@@ -1247,19 +1242,17 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
             }
         },
         [&](const unsigned first, const unsigned last) {
-            Warm w;
-            w.a = ld_word(S.P0 + first);
-            w.b = ld_word(S.P0 + last);
-            w.c = ld_word(S.P1 + first);
-            w.d = ld_word(S.P1 + last);
-            w.e = ld_word(S.P2 + first);
-            w.f = ld_word(S.P2 + last);
+            stage_l1(S.P0 + first);
+            stage_l1(S.P0 + last);
+            stage_l1(S.P1 + first);
+            stage_l1(S.P1 + last);
+            stage_l1(S.P2 + first);
+            stage_l1(S.P2 + last);
             if (FROZEN)
             {
-                w.a ^= ld_word(lv.x0 + first);
-                w.b ^= ld_word(lv.x0 + last);
+                stage_l1(lv.x0 + first);
+                stage_l1(lv.x0 + last);
             }
-            return w;
         });
     if (ALE)
     {
@@ -1288,8 +1281,6 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         ay += f * bn.y;
         az += f * bn.z;
     }
-    if (warm_sink == 0x9e3779b9u && C.dx < -1.0)
-        S.cellID[i] = -1; /* never happens: keeps the warming loads of the walk alive */
     if (!active)
         return; /* the walk is over: nothing below votes */
     const double4 av = S.AV[i];

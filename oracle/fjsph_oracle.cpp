@@ -2727,6 +2727,11 @@ void orc_get_neighbours(Orc* o, int64_t* offsets, int64_t* idx, double* d2)
         d2[k] = o->nb_d2[k];
     }
 }
+/* list lengths (self included, as outlist[i].size()): the full-size parity tests compare these without copying the lists */
+void orc_neighbour_counts(Orc* o, int64_t* counts)
+{
+    for (size_t i = 0; i + 1 < o->nb_off.size(); ++i) counts[i] = int64_t(o->nb_off[i + 1] - o->nb_off[i]);
+}
 static void set_range(Orc* o)
 {
     o->start_index = o->bound_points;

@@ -109,6 +109,7 @@ int orc_set_i64(Orc* o, int level, const char* name, const int64_t* in);
 void orc_update_neighbours(Orc* o);                       /* Neighbours.cpp:7-31 on pnp1 */
 int64_t orc_neighbour_total(Orc* o);
 void orc_get_neighbours(Orc* o, int64_t* offsets /* n+1 */, int64_t* idx, double* d2); /* ascending j */
+void orc_neighbour_counts(Orc* o, int64_t* counts /* n */);                            /* restatement builds only */
 double orc_prestep(Orc* o);                               /* Shifting.cpp:12-123; returns npd */
 void orc_aero_velocity(Orc* o);                           /* Resid.cpp:471-612 (constVel) */
 void orc_set_mesh(Orc* o, int64_t n_verts, const double* verts, int64_t n_faces, const int64_t* face_ptr,

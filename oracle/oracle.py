@@ -318,6 +318,16 @@ class Oracle:
         self.lib.orc_get_neighbours(self.h, _ptr(off), _ptr(idx), _ptr(d2))
         return off, idx, d2
 
+    def neighbour_counts(self) -> np.ndarray:
+        """List lengths, self included (outlist[i].size())."""
+        if hasattr(self.lib, "orc_neighbour_counts"):
+            out = np.empty(self.n, dtype=np.int64)
+            self.lib.orc_neighbour_counts.argtypes = [C.c_void_p, C.c_void_p]
+            self.lib.orc_neighbour_counts.restype = None
+            self.lib.orc_neighbour_counts(self.h, _ptr(out))
+            return out
+        return np.diff(self.neighbours()[0])
+
     def prestep(self) -> float:
         return float(self.lib.orc_prestep(self.h))
 
