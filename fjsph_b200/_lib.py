@@ -47,6 +47,7 @@ FjsphBlock = struct_from_header("FjsphBlock")
 FjsphStateView = struct_from_header("FjsphStateView")
 FjsphStepStats = struct_from_header("FjsphStepStats")
 FjsphMesh = struct_from_header("FjsphMesh")
+FjsphDeleted = struct_from_header("FjsphDeleted")
 
 
 # FjsphCommFn, include/fjsph_b200.h
@@ -126,6 +127,7 @@ def lib():
     L.fjsph_set_slab.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_double, COMM_FN, vp]
     L.fjsph_slab_comm_stream.argtypes = [vp, P(vp)]
     L.fjsph_slab_overlapped.argtypes = [vp, P(C.c_int64)]
+    L.fjsph_take_deleted.argtypes = [vp, vp, C.c_int64, P(C.c_int64)]
     L.fjsph_slab_stats.argtypes = [vp, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)]
     L.fjsph_foam_read.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, P(vp)]
     L.fjsph_foam_view.argtypes = [vp, P(FjsphMesh)]

@@ -700,7 +700,7 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
     if (const char* v = std::getenv("FJSPH_B200_LIST_STATS"))
         e->list_stats = std::atoi(v) != 0;
     if (const char* v = std::getenv("FJSPH_B200_SWEEP_WARPS"))
-        e->sweep_warps = (std::atoi(v) == 4) ? 4 : 8;
+        e->sweep_warps = (std::atoi(v) == 8) ? 8 : 4;
     if (const char* split = std::getenv("FJSPH_B200_SPLIT_SURFACE"))
         e->split_surface_sweep = std::string(split) != "0";
     if (const char* v = std::getenv("FJSPH_B200_SPLIT_BELOW")) /* near-surface warp fraction below which the sweep splits */
@@ -779,6 +779,26 @@ int fjsph_destroy(FjsphEngine* e)
     if (e->own_stream)
         cudaStreamDestroy(e->stream);
     delete e;
+    return FJSPH_OK;
+}
+
+int fjsph_take_deleted(FjsphEngine* e, FjsphDeleted* out, int64_t capacity, int64_t* n_out)
+{
+    if (!e || !n_out || (out && capacity < 0))
+    {
+        fj_set_error("take_deleted: bad arguments");
+        return FJSPH_ERR_INVALID;
+    }
+    if (!out)
+    {
+        *n_out = int64_t(e->deleted.size());
+        return FJSPH_OK;
+    }
+    const size_t n = std::min<size_t>(e->deleted.size(), size_t(capacity));
+    if (n)
+        std::memcpy(out, e->deleted.data(), n * sizeof(FjsphDeleted));
+    e->deleted.erase(e->deleted.begin(), e->deleted.begin() + std::ptrdiff_t(n));
+    *n_out = int64_t(n);
     return FJSPH_OK;
 }
 

@@ -262,7 +262,7 @@ struct FjsphEngine
     // fused surface / shifting sweep in two launches (lean bulk + near-surface rest) when few warps are near a surface
     // (sweeps.cu, k_surf23_shift CLASS; FJSPH_B200_SPLIT_SURFACE=0 keeps the single launch)
     bool split_surface_sweep = true;
-    int sweep_warps = 8;               // FJSPH_B200_SWEEP_WARPS: warps (rows) per CTA of the pair sweeps, 4 | 8
+    int sweep_warps = 4;               // FJSPH_B200_SWEEP_WARPS: warps (rows) per CTA of the pair sweeps, 4 (2 x 2 rows) | 8 (4 x 2)
     double split_surface_below = 0.35; // fraction of near-surface warps below which the two launches pay
 
     // reductions / scalars
@@ -288,6 +288,7 @@ struct FjsphEngine
     Slab slab;
     DeviceMesh mesh;
     long long mesh_deleted = 0;
+    std::vector<FjsphDeleted> deleted;  // particles erased at a delete plane since the last fjsph_take_deleted (IPT hand-off)
 
     // Integrator members, Integration.h:53-68
     double safe_dt = 0.0, maxf = 0.0, maxAf = 0.0, maxRho_pc = 0.0, maxRhoi = 0.0, maxdrho = 0.0, minST = 0.0,
@@ -365,7 +366,7 @@ double fj_total_count(FjsphEngine* e);
 bool fj_has_inlets(FjsphEngine* e);
 int fj_inlet_motion(FjsphEngine* e, double dt, bool nb_solver, int* n_partials);
 int fj_update_data(FjsphEngine* e, int* n_add, int* n_del);
-int fj_delete_flagged(FjsphEngine* e, unsigned* d_del_by_caller, bool both_levels, int* n_del);
+int fj_delete_flagged(FjsphEngine* e, unsigned* d_del_by_caller, bool both_levels, int* n_del, bool hand_off = false);
 /* slab re-decomposition: the inlet tables (caller indices) follow their particles into the compacted order */
 int fj_inlet_tables_remap(FjsphEngine* e, const unsigned* d_stay_flag, const unsigned* d_stay_scan);
 // aero-mesh containment (mesh.cu)

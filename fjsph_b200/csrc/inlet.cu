@@ -419,10 +419,60 @@ int fj_inlet_motion(FjsphEngine* e, double dt, bool nb_solver, int* n_partials)
     return FJSPH_OK;
 }
 
+// IPT hand-off (Integration.cpp:151-169, Var.h:733-763): a particle past its block's delete plane is "downstream enough
+// to convert to IPT" -- the reference builds an IPTPart from it (id, time, position, velocity, mass, cell id, cell velocity and
+// density; diameter and area come from the IPT settings) before it erases the SPH particle.  The engine keeps those
+// records, in the reference's order (ascending caller index), for the host to collect with fjsph_take_deleted.
+__global__ void k_capture_deleted(Level S, const unsigned* __restrict__ del_by_caller, const unsigned* __restrict__ scan_by_caller,
+                                  const int* __restrict__ oidx, int n, double t, FjsphDeleted* __restrict__ out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n)
+        return;
+    const int c = oidx[s];
+    if (!del_by_caller[c])
+        return;
+    FjsphDeleted d;
+    const double4 x = S.P0[s], v = S.P1[s], cv = S.CV[s], th = S.TH[s];
+    d.part_id = S.part_id[s];
+    d.cellID = S.cellID[s];
+    d.t = t;
+    d.xi[0] = x.x, d.xi[1] = x.y, d.xi[2] = x.z;
+    d.v[0] = v.x, d.v[1] = v.y, d.v[2] = v.z;
+    d.mass = th.y;
+    d.cellV[0] = cv.x, d.cellV[1] = cv.y, d.cellV[2] = cv.z;
+    d.cellRho = th.w;
+    out[scan_by_caller[c]] = d;
+}
+
+// appends the particles flagged in d_del (by caller index, n_flagged of them, exclusive scan in d_scan) to e->deleted
+static int capture_deleted(FjsphEngine* e, const unsigned* d_del, const unsigned* d_scan, int n, int n_flagged)
+{
+    if (n_flagged <= 0)
+        return FJSPH_OK;
+    FjsphDeleted* d_out = nullptr;
+    FJ_CUDA(cudaMalloc(&d_out, size_t(n_flagged) * sizeof(FjsphDeleted)));
+    k_capture_deleted<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], d_del, d_scan, e->oidx, n, e->P.current_time, d_out);
+    e->launches++;
+    const size_t at = e->deleted.size();
+    e->deleted.resize(at + size_t(n_flagged));
+    cudaError_t ce = cudaMemcpyAsync(e->deleted.data() + at, d_out, size_t(n_flagged) * sizeof(FjsphDeleted),
+                                     cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess)
+        ce = cudaStreamSynchronize(e->stream);
+    cudaFree(d_out);
+    if (ce != cudaSuccess)
+    {
+        e->deleted.resize(at);
+        return fj_cuda_fail(ce, "capture_deleted", __FILE__, __LINE__);
+    }
+    return FJSPH_OK;
+}
+
 // Erase the particles flagged in d_del (one unsigned per CALLER index, the key scratch array) from pnp1 -- and from pn
 // when both_levels -- keeping the reference's order: later indices shift down, block ranges and the inlet tables
 // follow (Integration.cpp:171-205, Resid.cpp:483-523).  The neighbour lists become invalid.
-int fj_delete_flagged(FjsphEngine* e, unsigned* d_del, bool both_levels, int* n_del_out)
+int fj_delete_flagged(FjsphEngine* e, unsigned* d_del, bool both_levels, int* n_del_out, bool hand_off)
 {
     cudaStream_t st_ = e->stream;
     const int n = int(e->n);
@@ -443,6 +493,12 @@ int fj_delete_flagged(FjsphEngine* e, unsigned* d_del, bool both_levels, int* n_
     const int n_del = int(h_tail[0] + h_tail[1]);
     if (n_del == 0)
         return FJSPH_OK;
+    if (hand_off)
+    {
+        int st = capture_deleted(e, d_del, d_scan, n, n_del);
+        if (st)
+            return st;
+    }
     KScope ks(e, "delete_particles", 8);
     /* survivors in slot order; their new caller index = old - (#deleted before it) */
     unsigned* d_keep = reinterpret_cast<unsigned*>(e->perm);
@@ -723,7 +779,7 @@ int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
         }
         if (any_delete_plane && !slabs)
         {
-            int st = fj_delete_flagged(e, d_del, false, &n_del); /* pn = pnp1 follows (Integration.cpp:220-223) */
+            int st = fj_delete_flagged(e, d_del, false, &n_del, true); /* pn = pnp1 follows (Integration.cpp:220-223) */
             if (st)
                 return st;
         }
@@ -738,6 +794,16 @@ int fj_update_data(FjsphEngine* e, int* n_add_out, int* n_del_out)
                 FJ_CUDA(cudaMemcpyAsync(e->h_flag + 1, e->d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st_));
                 FJ_CUDA(cudaStreamSynchronize(st_));
                 dels = double(e->h_flag[1]);
+                if (e->h_flag[1] > 0)
+                {
+                    /* this rank's erased particles, for the IPT hand-off (order: ascending caller index on this rank) */
+                    if (!e->scan_particles)
+                        FJ_CUDA(cudaMalloc(&e->scan_particles, (size_t(e->cap) / SCAN_TILE + 2) * sizeof(unsigned)));
+                    prim_exclusive_scan(st_, d_del, d_scan, unsigned(n), e->scan_particles);
+                    int stc = capture_deleted(e, d_del, d_scan, n, e->h_flag[1]);
+                    if (stc)
+                        return stc;
+                }
             }
             int st = fj_allreduce(e, FJSPH_COMM_SUM, &dels, 1);
             if (st)

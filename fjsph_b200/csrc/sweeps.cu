@@ -64,92 +64,6 @@ __device__ __forceinline__ double4 gather_rw(const double4* base, unsigned j)
     return v;
 }
 
-#ifndef FJ_PREFETCH
-#define FJ_PREFETCH 1
-#endif
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// Walks the runs of work warp W in lockstep: slot k holds, for every lane, the window {first, mask} of its neighbours
-// inside one neighbouring row; the warp steps o = 0 .. T-1 (T = the longest window of the slot) and lane l visits
-// neighbour first_l + o when bit o of its mask is set.  load(j, take) issues the record gathers of one neighbour (and
-// returns them; nothing is loaded when !take), body(j, rec) consumes them, prefetch(j) touches the records of
-// neighbour j.  Software-pipelined: the gathers of step s+1 are issued before the arithmetic of step s; the
-// descriptors run two slots ahead, and on entering a slot every lane prefetches the first and the last record of its
-// window in the NEXT slot into L1 -- between them the lanes of a warp cover the whole stretch of the next row (their
-// windows are shifted copies of each other), so the gathers of a fresh row find their lines on the way instead of
-// stalling the warp on an L2 round trip at every row.  Every lane of the warp must call this (the trip counts are warp
-// votes); lanes with active == false visit nobody.
-template <class Load, class Body, class Prefetch>
-__device__ __forceinline__ void for_neighbours(const RunView& L, int W, bool active, Load&& load, Body&& body,
-                                               Prefetch&& prefetch)
-{
-    const int nrow = L.erows[W];
-    const uint2* __restrict__ dp = L.erun + (size_t(W) * size_t(L.ecap)) * 32u + (threadIdx.x & 31u);
-    int k = 0, T = 0, o = 0;
-    uint2 d = make_uint2(0u, 0u), dn = make_uint2(0u, 0u), dnn = make_uint2(0u, 0u);
-    if (nrow > 0)
-        dn = ld_desc(dp);
-    if (nrow > 1)
-        dnn = ld_desc(dp + 32u);
-    /* next slot with somebody in it: false at the end of the list (warp-uniform) */
-    auto next_slot = [&]() -> bool {
-        while (k < nrow)
-        {
-            d = dn;
-            dn = dnn;
-            if (!active)
-                d.y = 0u;
-            ++k;
-            if (k + 1 < nrow)
-                dnn = ld_desc(dp + size_t(k + 1) * 32u);
-            if (FJ_PREFETCH && k < nrow && active && dn.y != 0u)
-            {
-                prefetch(dn.x);
-                prefetch(dn.x + unsigned(31 - __clz(int(dn.y))));
-            }
-            T = __reduce_max_sync(FJ_FULL, 32 - __clz(int(d.y)));
-            if (T > 0)
-                return true;
-        }
-        return false;
-    };
-    if (!next_slot())
-        return;
-    unsigned ja = d.x;
-    bool va = (d.y & 1u) != 0u;
-    auto ra = load(ja, va);
-    for (;;)
-    {
-        /* step B is prepared while A is consumed, and the other way round (two register sets, no moves) */
-        bool more = true;
-        if (++o >= T)
-        {
-            more = next_slot();
-            o = 0;
-        }
-        const unsigned jb = d.x + unsigned(o);
-        const bool vb = more && ((d.y >> o) & 1u) != 0u;
-        auto rb = load(jb, vb);
-        if (va)
-            body(ja, ra);
-        if (!more)
-            break;
-        more = true;
-        if (++o >= T)
-        {
-            more = next_slot();
-            o = 0;
-        }
-        ja = d.x + unsigned(o);
-        va = more && ((d.y >> o) & 1u) != 0u;
-        ra = load(ja, va);
-        if (vb)
-            body(jb, rb);
-        if (!more)
-            break;
-    }
-}
-
 // Branch-free, two neighbours at a time.  load(j) gathers the records of neighbour j unconditionally -- a lane with
 // nobody to visit at a step is handed its OWN index (self), a valid address whose pair terms vanish or are masked by
 // the `take` flags body(recA, takeA, recB, takeB) receives -- so the loop body is one basic block and the compiler
@@ -179,22 +93,26 @@ __device__ __forceinline__ void for_neighbours2(const RunView& L, int W, bool ac
     const int nrow = L.erows[W];
     const uint2* __restrict__ dp = L.erun + (size_t(W) * size_t(L.ecap)) * 32u + (threadIdx.x & 31u);
     int k = 0, T = 0, o = 0;
-    uint2 d = make_uint2(0u, 0u), dn = make_uint2(0u, 0u);
-    for (int a = 1; a < 4 && a < nrow; ++a) stage_l1(dp + size_t(a) * 32u);
+    uint2 d = make_uint2(0u, 0u), dn = make_uint2(0u, 0u), dnn = make_uint2(0u, 0u);
+    for (int a = 2; a < 6 && a < nrow; ++a) stage_l1(dp + size_t(a) * 32u);
     if (nrow > 0)
         dn = ld_desc(dp);
-    /* next slot with somebody in it: false at the end of the list (warp-uniform) */
+    if (nrow > 1)
+        dnn = ld_desc(dp + 32u);
+    /* next slot with somebody in it: false at the end of the list (warp-uniform).  Descriptors run two slots ahead in
+       registers (dnn was issued a slot ago: the move below does not wait) and six slots ahead in L1. */
     auto next_slot = [&]() -> bool {
         while (k < nrow)
         {
             d = dn;
+            dn = dnn;
             if (!active)
                 d.y = 0u;
             ++k;
-            if (k + 3 < nrow)
-                stage_l1(dp + size_t(k + 3) * 32u);
-            if (k < nrow)
-                dn = ld_desc(dp + size_t(k) * 32u); /* an L1 hit: staged three slots ago */
+            if (k + 5 < nrow)
+                stage_l1(dp + size_t(k + 5) * 32u);
+            if (k + 1 < nrow)
+                dnn = ld_desc(dp + size_t(k + 1) * 32u);
             T = __reduce_max_sync(FJ_FULL, 32 - __clz(int(d.y)));
             if (k < nrow && active && dn.y != 0u) /* the records of the slot after this one */
                 stage(dn.x, dn.x + unsigned(31 - __clz(int(dn.y))));
@@ -291,24 +209,49 @@ __device__ __forceinline__ double fj_rsqrt3(double x)
     return fma(ye, p, y0);
 }
 
-// r of a pair the way the reference takes it -- sqrt of the list's d^2, the distance at the list build -- with 1 / r
-// beside it: from the current separation when the particles have not moved since (FROZEN = false), else from the
-// build-time positions x0.  rr = d^2, r = d^2 * rsqrt(d^2) (~1 ulp; coincident particles give r = 0, not NaN);
-// r2c = |Rji|^2 of the CURRENT positions, which is what Rji . gradK carries (Kernel.h:262-269, Shifting.cpp:160-176).
-template <bool FROZEN>
-__device__ __forceinline__ void pair_dist(const double4& x0i, const double4& x0j, double rx, double ry, double rz,
-                                          double& rr, double& ir, double& r, double& r2c)
+// Geometry of one pair, branch-free and with a short dependency chain: Rji (current positions), rr = the list's d^2
+// (current separation, or the build-time one under FROZEN), 1 / r, t = 1 - r / 2H formed straight from rr and 1 / r, and
+// the Wendland C2 gradient factor gk = 5 Wc / H^2 t^3, 0 when r / H < 1e-12 (Kernel.h:37-61).  W = t^4 (2 r / H + 1) Wc
+// = t^4 (5 - 4 t) Wc.  A lane that has nobody to visit at a step is handed its own index: rr = 0, gk = 0 exactly, 1 / r
+// and t not finite -- every use of those is a select on the `take` flag, never a product.
+struct PairGeo
 {
-    r2c = fma(rz, rz, fma(ry, ry, rx * rx));
+    double rx, ry, rz, rr, r2c, ir, t, gk;
+};
+template <bool FROZEN>
+__device__ __forceinline__ PairGeo pair_geo(const DevConst& C, const double4& pi, const double4& x0i, const double4& pj,
+                                            const double4& x0j)
+{
+    PairGeo g;
+    g.rx = pj.x - pi.x;
+    g.ry = pj.y - pi.y;
+    g.rz = pj.z - pi.z;
+    g.r2c = fma(g.rz, g.rz, fma(g.ry, g.ry, g.rx * g.rx));
+    g.rr = g.r2c;
     if (FROZEN)
     {
         const double ex = x0j.x - x0i.x, ey = x0j.y - x0i.y, ez = x0j.z - x0i.z;
-        rr = fma(ez, ez, fma(ey, ey, ex * ex));
+        g.rr = fma(ez, ez, fma(ey, ey, ex * ex));
     }
-    else
-        rr = r2c;
-    ir = fj_rsqrt(fmax(rr, 1e-300));
-    r = rr * ir;
+    g.ir = fj_rsqrt3(g.rr);
+    g.t = fma(g.rr * (-0.5 * C.iH), g.ir, 1.0);
+    const double tiny = 1e-12 * C.H;
+    g.gk = (g.rr < tiny * tiny) ? 0.0 : (C.gk_fac * g.t) * (g.t * g.t);
+    return g;
+}
+__device__ __forceinline__ double wend_W_t(const DevConst& C, double t)
+{
+    const double t2 = t * t;
+    return (t2 * t2) * (fma(-4.0, t, 5.0) * C.W_correc);
+}
+// 1 / x with ONE Newton step on the MUFU.RCP64H seed (~1e-12 relative): for the 1 / (r^2 + eps h^2) of the viscous and
+// density-diffusion terms, which are small corrections of the sums they enter
+__device__ __forceinline__ double fj_rcp1(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, e, y);
 }
 
 // Wendland C2 (Kernel.h:37-61).  t = 1 - q/2.  W = t^4 (2q+1) Wc ; GradK(R, r) = R * gk with
@@ -358,61 +301,66 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
         double g0 = 0, g1 = 0, g2 = 0, m0 = 0, m1 = 0, m2 = 0;
         double kernsum = C.W_correc; /* self term, Shifting.cpp:39-45 */
         double colour = 0.0;
-        for_neighbours(
-            lv, W, active,
-            [&](const unsigned j, const bool take) {
+        auto pair = [&](const RecPre& q, const bool take) {
+            const double4 pj = q.p;
+            const PairGeo g = pair_geo<FROZEN>(C, pi, x0i, pj, q.x0);
+            const double vg = pj.w * g.gk; /* V_j * gk ; Grad = GradK(-Rji) = -Rji*gk; 0 for a lane's own index */
+            const double ax = vg * g.rx, ay = vg * g.ry, az = vg * g.rz;
+            /* Lmat -= V Rji (x) Grad  ==  += V gk Rji (x) Rji */
+            l00 = fma(ax, g.rx, l00);
+            l01 = fma(ax, g.ry, l01);
+            l02 = fma(ax, g.rz, l02);
+            l11 = fma(ay, g.ry, l11);
+            l12 = fma(ay, g.rz, l12);
+            l22 = fma(az, g.rz, l22);
+            const double dr = q.rho - rho_i;
+            g0 = fma(-dr, ax, g0);
+            g1 = fma(-dr, ay, g1);
+            g2 = fma(-dr, az, g2);
+            /* fluid neighbours only (b > PISTON): selects, not branches */
+            const bool fl = take && q.b > FJSPH_PISTON;
+            const double fx = fl ? ax : 0.0, fy = fl ? ay : 0.0, fz = fl ? az : 0.0;
+            n00 = fma(fx, g.rx, n00);
+            n01 = fma(fx, g.ry, n01);
+            n02 = fma(fx, g.rz, n02);
+            n11 = fma(fy, g.ry, n11);
+            n12 = fma(fy, g.rz, n12);
+            n22 = fma(fz, g.rz, n22);
+            m0 -= fx;
+            m1 -= fy;
+            m2 -= fz;
+            const double W_ = fl ? wend_W_t(C, g.t) : 0.0;
+            kernsum += W_;
+            colour = fma(pj.w, W_, colour);
+            npd_ += W_;
+        };
+        for_neighbours2(
+            lv, W, active, unsigned(i),
+            [&](const unsigned j) {
                 RecPre q;
-                if (take)
-                {
-                    q.p = gather(S.P0, j);
-                    q.rho = __ldg(&S.P1[j].w);
-                    q.b = __ldg(&S.b[j]);
-                    if (FROZEN)
-                        q.x0 = gather(lv.x0, j);
-                }
+                q.p = gather(S.P0, j);
+                q.rho = __ldg(&S.P1[j].w);
+                q.b = __ldg(&S.b[j]);
+                if (FROZEN)
+                    q.x0 = gather(lv.x0, j);
                 return q;
             },
-            [&](const unsigned j, const RecPre& q) {
-                const double4 pj = q.p;
-                const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-                double rr, ir, r, r2c;
-                pair_dist<FROZEN>(x0i, q.x0, rx, ry, rz, rr, ir, r, r2c);
-                const double t = wend_t(C, r);
-                const double vg = pj.w * wend_gk(C, r, t); /* V_j * gk ; Grad = GradK(-Rji) = -Rji*gk */
-                const double ax = vg * rx, ay = vg * ry, az = vg * rz;
-                /* Lmat -= V Rji (x) Grad  ==  += V gk Rji (x) Rji */
-                l00 += ax * rx;
-                l01 += ax * ry;
-                l02 += ax * rz;
-                l11 += ay * ry;
-                l12 += ay * rz;
-                l22 += az * rz;
-                const double dr = q.rho - rho_i;
-                g0 -= dr * ax;
-                g1 -= dr * ay;
-                g2 -= dr * az;
-                if (q.b > FJSPH_PISTON)
-                {
-                    n00 += ax * rx;
-                    n01 += ax * ry;
-                    n02 += ax * rz;
-                    n11 += ay * ry;
-                    n12 += ay * rz;
-                    n22 += az * rz;
-                    m0 -= ax;
-                    m1 -= ay;
-                    m2 -= az;
-                    const double W_ = wend_W(C, r, t);
-                    kernsum += W_;
-                    colour += pj.w * W_;
-                    npd_ += W_;
-                }
+            [&](const RecPre& qa, const bool ta, const RecPre& qb, const bool tb) {
+                pair(qa, ta);
+                pair(qb, tb);
             },
-            [&](const unsigned j) {
-                prefetch_l1(S.P0 + j);
-                prefetch_l1(S.P1 + j);
+            [&](const unsigned first, const unsigned last) {
+                stage_l1(S.P0 + first);
+                stage_l1(S.P0 + last);
+                stage_l1(S.P1 + first);
+                stage_l1(S.P1 + last);
+                stage_l1(S.b + first);
+                stage_l1(S.b + last);
                 if (FROZEN)
-                    prefetch_l1(lv.x0 + j);
+                {
+                    stage_l1(lv.x0 + first);
+                    stage_l1(lv.x0 + last);
+                }
             });
         if (active)
         {
@@ -553,92 +501,104 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
     double avx = 0, avy = 0, avz = 0, Rrhod = 0;
     const double cos_pi4 = 0.70710678118654757;
 
-    for_neighbours(
-        lv, W, active,
-        [&](const unsigned j, const bool take) {
+    /* main part of one pair, branch-free */
+    auto pair = [&](const RecS1& q, const bool take, PairGeo& g) {
+        const double4 pj = q.p;
+        const double4 gj = q.g;
+        g = pair_geo<FROZEN>(C, pi, x0i, pj, q.x0);
+        const double vg = pj.w * g.gk; /* 0 for a lane's own index */
+        if (SURF)
+        {
+            /* normal from the eigenvalue gradient, GradK(Rij = xi - xj) = -Rji*gk (Geometry.cpp:109-137) */
+            const double sn = -vg * (gj.w - lam_ref);
+            nx = fma(sn, g.rx, nx);
+            ny = fma(sn, g.ry, ny);
+            nz = fma(sn, g.rz, nz);
+        }
+        if (DISS)
+        {
+            const double4 vj = q.v;
+            const double rho_j = vj.w;
+            const double idist2 = fj_rcp1(g.rr + eps_d);
+            const double w = vg * (g.r2c * idist2); /* V_j (Rji . gradK) idist2 */
+            const double drho = rho_j - rho_i;
+            const bool fl = q.b > FJSPH_PISTON;
+            const double vdotr = (vj.x - vi.x) * g.rx + (vj.y - vi.y) * g.ry + (vj.z - vi.z) * g.rz;
+            /* ArtVisc = 0 when Vji.Rji > 0, and for a non-fluid neighbour (selects, no branches) */
+            const double muij = C.H * vdotr * idist2;
+            const double cbar = 0.5 * (cs_i + sqrt_Bgam * fj_rsqrt3(rho_j));
+            /* m_j gk alpha cbar mu / rhobar, m_j = rho_j V_j, rhobar = (rho_i + rho_j)/2 */
+            double f = (rho_j * vg) * (C.visc_alpha * cbar) * muij * fj_rcp1(0.5 * (rho_i + rho_j));
+            f = (vdotr > 0.0 || !fl) ? 0.0 : f;
+            avx = fma(f, g.rx, avx);
+            avy = fma(f, g.ry, avy);
+            avz = fma(f, g.rz, avz);
+            const double gdot = (gi.x + gj.x) * g.rx + (gi.y + gj.y) * g.ry + (gi.z + gj.z) * g.rz;
+            Rrhod = fma(drho + (fl ? 0.5 * gdot : 0.0), w, Rrhod);
+        }
+    };
+    /* Detect_Surface's cone test (Geometry.cpp:60-103): only particles with 0.2 <= lam_nb < 0.75 */
+    auto cone = [&](const RecS1& q, const bool take, const PairGeo& g) {
+        if (!take)
+            return;
+        const double4 pj = q.p;
+        const double r = g.rr * g.ir;
+        if (r >= sqrt2h)
+        {
+            const double ex = pj.x - Tx, ey = pj.y - Ty, ez = pj.z - Tz;
+            if (sqrt(ex * ex + ey * ey + ez * ez) < h)
+                surf = 0;
+        }
+        else
+        {
+            /* acos(nhat . (Rji/r)) < pi/4 ; acos is NaN outside [-1,1] so those never trigger */
+            const double c = (nhx * g.rx + nhy * g.ry + nhz * g.rz) * g.ir;
+            if (c > cos_pi4 && c <= 1.0)
+                surf = 0;
+        }
+    };
+    for_neighbours2(
+        lv, W, active, unsigned(i),
+        [&](const unsigned j) {
             RecS1 q;
-            if (take)
+            q.p = gather(S.P0, j);
+            q.g = gather(S.P3, j);
+            if (DISS)
             {
-                q.p = gather(S.P0, j);
-                q.g = gather(S.P3, j);
-                if (DISS)
-                {
-                    q.v = gather(S.P1, j);
-                    q.b = __ldg(&S.b[j]);
-                }
-                if (FROZEN)
-                    q.x0 = gather(lv.x0, j);
+                q.v = gather(S.P1, j);
+                q.b = __ldg(&S.b[j]);
             }
+            if (FROZEN)
+                q.x0 = gather(lv.x0, j);
             return q;
         },
-        [&](const unsigned j, const RecS1& q) {
-            const double4 pj = q.p;
-            const double4 gj = q.g;
-            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-            double rr, ir, r, r2c;
-            pair_dist<FROZEN>(x0i, q.x0, rx, ry, rz, rr, ir, r, r2c);
-            const double t = wend_t(C, r);
-            const double gk = wend_gk(C, r, t);
-            const double vg = pj.w * gk;
-            if (SURF)
+        [&](const RecS1& qa, const bool ta, const RecS1& qb, const bool tb) {
+            PairGeo ga, gb;
+            pair(qa, ta, ga);
+            pair(qb, tb, gb);
+            if (SURF && need_test)
             {
-                /* normal from the eigenvalue gradient, GradK(Rij = xi - xj) = -Rji*gk (Geometry.cpp:109-137) */
-                const double s = -vg * (gj.w - lam_ref);
-                nx += s * rx;
-                ny += s * ry;
-                nz += s * rz;
-                if (need_test)
-                {
-                    if (r >= sqrt2h)
-                    {
-                        const double ex = pj.x - Tx, ey = pj.y - Ty, ez = pj.z - Tz;
-                        if (sqrt(ex * ex + ey * ey + ez * ez) < h)
-                            surf = 0;
-                    }
-                    else
-                    {
-                        /* acos(nhat . (Rji/r)) < pi/4 ; acos is NaN outside [-1,1] so those never trigger */
-                        const double c = (nhx * rx + nhy * ry + nhz * rz) * ir;
-                        if (c > cos_pi4 && c <= 1.0)
-                            surf = 0;
-                    }
-                }
-            }
-            if (DISS)
-            {
-                const double4 vj = q.v;
-                const double rho_j = vj.w;
-                const double idist2 = fj_rcp(rr + eps_d);
-                const double w = vg * (r2c * idist2); /* V_j (Rji . gradK) idist2 */
-                const double drho = rho_j - rho_i;
-                if (q.b > FJSPH_PISTON)
-                {
-                    const double vdotr = (vj.x - vi.x) * rx + (vj.y - vi.y) * ry + (vj.z - vi.z) * rz;
-                    /* ArtVisc = 0 when Vji.Rji > 0 (select, no branch) */
-                    const double muij = C.H * vdotr * idist2;
-                    const double cbar = 0.5 * (cs_i + sqrt_Bgam * fj_rsqrt(rho_j));
-                    /* m_j gk alpha cbar mu / rhobar, m_j = rho_j V_j, rhobar = (rho_i + rho_j)/2 */
-                    double f = (rho_j * vg) * (C.visc_alpha * cbar) * muij * fj_rcp(0.5 * (rho_i + rho_j));
-                    f = (vdotr > 0.0) ? 0.0 : f;
-                    avx += f * rx;
-                    avy += f * ry;
-                    avz += f * rz;
-                    const double gdot = (gi.x + gj.x) * rx + (gi.y + gj.y) * ry + (gi.z + gj.z) * rz;
-                    Rrhod += (drho + 0.5 * gdot) * w;
-                }
-                else
-                {
-                    Rrhod += drho * w;
-                }
+                cone(qa, ta, ga);
+                cone(qb, tb, gb);
             }
         },
-        [&](const unsigned j) {
-            prefetch_l1(S.P0 + j);
-            prefetch_l1(S.P3 + j);
+        [&](const unsigned first, const unsigned last) {
+            stage_l1(S.P0 + first);
+            stage_l1(S.P0 + last);
+            stage_l1(S.P3 + first);
+            stage_l1(S.P3 + last);
             if (DISS)
-                prefetch_l1(S.P1 + j);
+            {
+                stage_l1(S.P1 + first);
+                stage_l1(S.P1 + last);
+                stage_l1(S.b + first);
+                stage_l1(S.b + last);
+            }
             if (FROZEN)
-                prefetch_l1(lv.x0 + j);
+            {
+                stage_l1(lv.x0 + first);
+                stage_l1(lv.x0 + last);
+            }
         });
     if (SURF)
     {
@@ -781,89 +741,90 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
     double min_c = 2.0;
     const bool need_pos = (SURF23 && (ni_nz || need_occl)) || do_shift;
 
-    for_neighbours(
-        lv, W, active,
-        [&](const unsigned j, const bool take) {
-            RecS2 q;
-            if (take)
+    /* one pair, branch-free: what a particle does not need is computed and dropped by a select */
+    auto pair = [&](const RecS2& q, const bool take) {
+        const double4 nj = q.n;
+        zone |= (take && nj.w != 0.0) ? 1 : 0;
+        const double4 pj = q.p;
+        const PairGeo g = pair_geo<FROZEN>(C, pi, x0i, pj, q.x0);
+        if (SURF23)
+        {
+            if (CLASS != 1)
             {
-                if (CLASS == 1)
-                    q.n.w = __ldg(&S.P4[j].w); /* the surf flag is all a lean particle reads of n_j */
-                else
-                    q.n = gather(S.P4, j);
-                if (need_pos)
-                    q.p = gather(S.P0, j);
-                if (do_shift)
-                {
-                    q.v = gather(S.P1, j);
-                    q.b = __ldg(&S.b[j]);
-                }
-                if (FROZEN && need_pos)
-                    q.x0 = gather(lv.x0, j);
+                /* curvature (Geometry.cpp:187-213): L is zero unless particle i has a loop-1 normal */
+                const double vg = pj.w * g.gk;
+                const double dx_ = nj.x - ni.x, dy_ = nj.y - ni.y, dz_ = nj.z - ni.z;
+                const double lx = L0 * dx_ + L1 * dy_ + L2 * dz_;
+                const double ly = L3 * dx_ + L4 * dy_ + L5 * dz_;
+                const double lz = L6 * dx_ + L7 * dy_ + L8 * dz_;
+                const double term = vg * (lx * g.rx + ly * g.ry + lz * g.rz);
+                curve += (ni_nz && (nj.x * nj.x + nj.y * nj.y + nj.z * nj.z) > 0.0) ? term : 0.0;
+                const double frac = (g.rx * vdx + g.ry * vdy + g.rz * vdz) * mivdn * g.ir;
+                woccl_ = (need_occl && take && frac > woccl_) ? frac : woccl_;
             }
+        }
+        if (SHIFT)
+        {
+            const double4 vj = q.v;
+            const double W_ = wend_W_t(C, g.t);
+            const double kq = W_ * C.iW_dx;
+            const double kq2 = kq * kq;
+            const double f = take ? fma(0.2, kq2 * kq2, 1.0) * g.gk * pj.w : 0.0;
+            dux = fma(f, g.rx, dux);
+            duy = fma(f, g.ry, duy);
+            duz = fma(f, g.rz, duz);
+            const bool fl = take && q.b > FJSPH_PISTON;
+            if (CLASS == 1)
+                has_fluid = has_fluid || fl;
+            else
+            {
+                /* n_i and n_j are unit vectors or zero already (loop 1), normalized() is the identity */
+                const double c = ni.x * nj.x + ni.y * nj.y + ni.z * nj.z;
+                min_c = (fl && !known_bulk && c >= -1.0 && c <= 1.0) ? fmin(min_c, c) : min_c;
+            }
+            const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
+            maxU2 = fmax(maxU2, fma(uz, uz, fma(uy, uy, ux * ux)));
+        }
+    };
+    for_neighbours2(
+        lv, W, active, unsigned(i),
+        [&](const unsigned j) {
+            RecS2 q;
+            if (CLASS == 1)
+                q.n.w = __ldg(&S.P4[j].w); /* the surf flag is all a lean particle reads of n_j */
+            else
+                q.n = gather(S.P4, j);
+            q.p = gather(S.P0, j);
+            if (SHIFT)
+            {
+                q.v = gather(S.P1, j);
+                q.b = __ldg(&S.b[j]);
+            }
+            if (FROZEN)
+                q.x0 = gather(lv.x0, j);
             return q;
         },
-        [&](const unsigned j, const RecS2& q) {
-            const double4 nj = q.n;
-            if (nj.w != 0.0)
-                zone = 1;
-            if (!need_pos)
-                return;
-            const double4 pj = q.p;
-            const double rx = pj.x - pi.x, ry = pj.y - pi.y, rz = pj.z - pi.z;
-            double rr, ir, r, r2c;
-            pair_dist<FROZEN>(x0i, q.x0, rx, ry, rz, rr, ir, r, r2c);
-            const double t = wend_t(C, r);
-            const double gk = wend_gk(C, r, t);
-            if (SURF23)
-            {
-                if (ni_nz && ((nj.x * nj.x + nj.y * nj.y + nj.z * nj.z) > 0.0))
-                {
-                    const double vg = pj.w * gk;
-                    const double dx_ = nj.x - ni.x, dy_ = nj.y - ni.y, dz_ = nj.z - ni.z;
-                    const double lx = L0 * dx_ + L1 * dy_ + L2 * dz_;
-                    const double ly = L3 * dx_ + L4 * dy_ + L5 * dz_;
-                    const double lz = L6 * dx_ + L7 * dy_ + L8 * dz_;
-                    curve += vg * (lx * rx + ly * ry + lz * rz);
-                }
-                if (need_occl)
-                {
-                    const double frac = (rx * vdx + ry * vdy + rz * vdz) * mivdn * ir;
-                    if (frac > woccl_)
-                        woccl_ = frac;
-                }
-            }
-            if (do_shift)
-            {
-                const double4 vj = q.v;
-                const double W = wend_W(C, r, t);
-                const double kq = W * C.iW_dx;
-                const double kq2 = kq * kq;
-                const double f = (1.0 + 0.2 * (kq2 * kq2)) * gk * pj.w;
-                dux += f * rx;
-                duy += f * ry;
-                duz += f * rz;
-                if (CLASS == 1)
-                    has_fluid = has_fluid || (q.b > FJSPH_PISTON);
-                else if (!known_bulk && (q.b > FJSPH_PISTON))
-                {
-                    /* n_i and n_j are unit vectors or zero already (loop 1), normalized() is the identity */
-                    const double c = ni.x * nj.x + ni.y * nj.y + ni.z * nj.z;
-                    if (c >= -1.0 && c <= 1.0)
-                        min_c = fmin(min_c, c);
-                }
-                const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
-                maxU2 = fmax(maxU2, ux * ux + uy * uy + uz * uz);
-            }
+        [&](const RecS2& qa, const bool ta, const RecS2& qb, const bool tb) {
+            pair(qa, ta);
+            pair(qb, tb);
         },
-        [&](const unsigned j) {
-            prefetch_l1(S.P4 + j);
-            if (need_pos)
-                prefetch_l1(S.P0 + j);
-            if (do_shift)
-                prefetch_l1(S.P1 + j);
-            if (FROZEN && need_pos)
-                prefetch_l1(lv.x0 + j);
+        [&](const unsigned first, const unsigned last) {
+            stage_l1(S.P4 + first);
+            stage_l1(S.P4 + last);
+            stage_l1(S.P0 + first);
+            stage_l1(S.P0 + last);
+            if (SHIFT)
+            {
+                stage_l1(S.P1 + first);
+                stage_l1(S.P1 + last);
+                stage_l1(S.b + first);
+                stage_l1(S.b + last);
+            }
+            if (FROZEN)
+            {
+                stage_l1(lv.x0 + first);
+                stage_l1(lv.x0 + last);
+            }
         });
     if (CLASS == 1 && has_fluid)
         min_c = 0.0;
@@ -1152,43 +1113,22 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         }
     }
 
-    /* one pair, branch-free (a lane's own index as j gives exact zeros: Rji = 0, gradK = 0).  Critical path kept short:
-       everything that does not wait for 1/r is formed beside it (V_j Rji, rr / 2H), t = 1 - r / 2H comes straight out of
-       rr and 1/r, the kernel gradient as (gk_fac t)(t t). */
-    struct Geo
-    {
-        double rx, ry, rz, r, ir;
-    };
-    const double m_half_iH = -0.5 * C.iH, tiny2 = (1e-12 * C.H) * (1e-12 * C.H);
-    auto pair_main = [&](const RecF& q) -> Geo {
+    /* one pair, branch-free (a lane's own index as j gives exact zeros: Rji = 0, gradK = 0) */
+    auto pair_main = [&](const RecF& q, PairGeo& g) {
         const double4 pj = q.p;
         const double4 vj = q.v;
         const double4 qj = q.q;
-        Geo g;
-        g.rx = pj.x - pi.x;
-        g.ry = pj.y - pi.y;
-        g.rz = pj.z - pi.z;
+        g = pair_geo<FROZEN>(C, pi, x0i, pj, q.x0);
         const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
-        const double r2c = fma(g.rz, g.rz, fma(g.ry, g.ry, g.rx * g.rx));
-        double rr = r2c;
-        if (FROZEN)
-        {
-            const double ex = q.x0.x - x0i.x, ey = q.x0.y - x0i.y, ez = q.x0.z - x0i.z;
-            rr = fma(ez, ez, fma(ey, ey, ex * ex));
-        }
-        g.ir = fj_rsqrt3(fmax(rr, 1e-300));
-        g.r = rr * g.ir;
-        const double idist2 = fj_rcp(rr + eps_f);
-        const double t = fma(rr * m_half_iH, g.ir, 1.0); /* 1 - r / 2H */
-        const double gk = (rr < tiny2) ? 0.0 : (C.gk_fac * t) * (t * t); /* Kernel.h:49-61: 0 when r / H < 1e-12 */
+        const double idist2 = fj_rcp1(g.rr + eps_f);
         const double rho_j = vj.w;
-        const double s = pj.w * gk;                                       /* V_j gk */
-        const double Gx = (pj.w * g.rx) * gk, Gy = (pj.w * g.ry) * gk, Gz = (pj.w * g.rz) * gk; /* V_j gradK */
+        const double s = pj.w * g.gk;                                                               /* V_j gk */
+        const double Gx = (pj.w * g.rx) * g.gk, Gy = (pj.w * g.ry) * g.gk, Gz = (pj.w * g.rz) * g.gk; /* V_j gradK */
         const double pf = rho_j * (qi.w + qj.w);
         ax = fma(-pf, Gx, ax);
         ay = fma(-pf, Gy, ay);
         az = fma(-pf, Gz, az);
-        const double vf = fma(nu_irho_i, rho_j, C.nu) * ((s * r2c) * idist2);
+        const double vf = fma(nu_irho_i, rho_j, C.nu) * ((s * g.r2c) * idist2);
         vx = fma(vf, ux, vx);
         vy = fma(vf, uy, vy);
         vz = fma(vf, uz, vz);
@@ -1209,12 +1149,11 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         {
             Rrho_ -= ug;
         }
-        return g;
     };
     /* pairwise surface tension, Kernel.h:101-113 (surface-zone particles only under ALE) */
-    auto pair_st = [&](const RecF& q, const Geo& g, const bool take) {
+    auto pair_st = [&](const RecF& q, const PairGeo& g, const bool take) {
         const double fac = (b_i == FJSPH_BOUND || q.b == FJSPH_BOUND) ? st_bound_fac : 1.0;
-        const double sf = take ? -npdm2 * fac * cospi(q_st * g.r) * g.ir : 0.0;
+        const double sf = take ? -npdm2 * fac * cospi(q_st * (g.rr * g.ir)) * g.ir : 0.0;
         sx = fma(sf, g.rx, sx);
         sy = fma(sf, g.ry, sy);
         sz = fma(sf, g.rz, sz);
@@ -1233,8 +1172,9 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
             return q;
         },
         [&](const RecF& qa, const bool ta, const RecF& qb, const bool tb) {
-            const Geo ga = pair_main(qa);
-            const Geo gb = pair_main(qb);
+            PairGeo ga, gb;
+            pair_main(qa, ga);
+            pair_main(qb, gb);
             if (do_st)
             {
                 pair_st(qa, ga, ta);
@@ -1248,6 +1188,11 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
             stage_l1(S.P1 + last);
             stage_l1(S.P2 + first);
             stage_l1(S.P2 + last);
+            if (do_st)
+            {
+                stage_l1(S.b + first);
+                stage_l1(S.b + last);
+            }
             if (FROZEN)
             {
                 stage_l1(lv.x0 + first);

@@ -320,6 +320,23 @@ class Engine:
         check(self._L.fjsph_read_restart(self._h, str(path).encode(), C.byref(fr)))
         return int(fr.value)
 
+    def take_deleted(self):
+        """IPT hand-off (Integration.cpp:151-169): the particles erased at a delete plane since the last call, as a dict of
+        arrays (part_id, cellID, t, xi, v, mass, cellV, cellRho) in the reference's order; the engine's queue is emptied."""
+        n = C.c_int64(0)
+        check(self._L.fjsph_take_deleted(self._h, None, 0, C.byref(n)))
+        buf = (_lib.FjsphDeleted * max(1, n.value))()
+        got = C.c_int64(0)
+        check(self._L.fjsph_take_deleted(self._h, C.cast(buf, C.c_void_p), n.value, C.byref(got)))
+        k = got.value
+        return dict(part_id=np.array([buf[i].part_id for i in range(k)], dtype=np.int64),
+                    cellID=np.array([buf[i].cellID for i in range(k)], dtype=np.int64),
+                    t=np.array([buf[i].t for i in range(k)]), mass=np.array([buf[i].mass for i in range(k)]),
+                    cellRho=np.array([buf[i].cellRho for i in range(k)]),
+                    xi=np.array([list(buf[i].xi) for i in range(k)]).reshape(k, 3),
+                    v=np.array([list(buf[i].v) for i in range(k)]).reshape(k, 3),
+                    cellV=np.array([list(buf[i].cellV) for i in range(k)]).reshape(k, 3))
+
     def set_skin(self, skin_over_dx: float):
         """Width of the neighbour superset list in units of dx (0 = cell-list sweep at every update_neighbours)."""
         check(self._L.fjsph_set_skin(self._h, float(skin_over_dx)))

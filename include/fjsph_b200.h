@@ -111,6 +111,18 @@ typedef struct FjsphStepStats
     int32_t skin_builds; /* cell-list sweeps behind those neighbour builds (the rest were filtered from the skin list) */
 } FjsphStepStats;
 
+/* What the reference hands to its particle tracker when a particle passes its block's delete plane: the fields
+ * IPTPart(SPHPart const&, time, diam, area) copies (Var.h:733-763; Integration.cpp:151-169).  Diameter and area are IPT
+ * settings of the host (ipt_diam, ipt_area). */
+typedef struct FjsphDeleted
+{
+    int64_t part_id, cellID;
+    double t;        /* integrator.current_time at the hand-off */
+    double xi[3], v[3];
+    double mass;
+    double cellV[3], cellRho;
+} FjsphDeleted;
+
 /* The reference's MESH (Var.h:396-451) as plain arrays: vertices, faces as vertex lists (CSR), leftright (owner cell,
  * neighbour cell or boundary marker: -1 inner wall, -2 outer boundary), cell -> faces (CSR), cell centres and the
  * cell-averaged CFD solution.  What TAU::Read_* (CDFIO.cpp:1103-1356) or FOAM::Read_FOAM (FOAMIO.cpp:538-955) fill. */
@@ -179,6 +191,12 @@ int fjsph_nb_iter(FjsphEngine* e, double npd, double* errsum);  /* Newmark_Beta:
 int fjsph_find_timestep(FjsphEngine* e, double* dt);            /* Integrator::find_timestep */
 int fjsph_integrate_no_update(FjsphEngine* e, FjsphStepStats* s); /* Integration.h:25-28 */
 int fjsph_step(FjsphEngine* e, FjsphStepStats* s);              /* Integrator::integrate  Integration.h:20-23 */
+
+/* IPT hand-off: the particles erased at a delete plane (Integration.cpp:127-169) since the last call, in the reference's
+ * order (ascending index within a step, steps in sequence) -- what update_data turns into IPTPart objects before it
+ * erases them.  Copies up to `capacity` records into `out` and drops them from the engine's queue; with out == NULL it
+ * only reports how many are waiting.  Under slab decomposition every rank holds the particles erased on it. */
+int fjsph_take_deleted(FjsphEngine* e, FjsphDeleted* out, int64_t capacity, int64_t* n_out);
 
 /* Convenience for hosts that keep particles on the host between steps (the end-to-end path):
  * upload -> n_steps x fjsph_step -> download, one call.  When `in` holds the particle set the engine already has (same

@@ -51,6 +51,33 @@ def test_inlet_insertion_and_delete_plane(fixed, solver):
     assert n_add >= 50 and n_del >= 25   # the run did insert columns and did erase particles
 
 
+def test_deleted_particles_are_handed_off():
+    """IPT hand-off (Integration.cpp:151-169, Var.h:733-763): every particle past the delete plane is erased from the SPH
+    state and handed to the host with what IPTPart(SPHPart, time, ...) copies -- id, time, position, velocity, mass, cell
+    id, cell velocity and density -- in the reference's order (ascending index, step after step).  Checked against the
+    oracle: the ids that leave its particle set at a step are the ids handed off at that step, with the state the
+    oracle's particles had when they crossed the plane."""
+    case = cases.inlet_jet(n=(5, 5, 4), fixed=1, delete_x=2.5, jitter=0.03)
+    o, e = make_inlet_pair(case)
+    handed = 0
+    for step in range(14):
+        _, so = o.integrate()
+        t_before = e.params.current_time
+        se = e.integrate()
+        d = e.take_deleted()
+        assert d["part_id"].shape[0] == se.n_del == so.n_del, step
+        if se.n_del == 0:
+            continue
+        handed += se.n_del
+        alive = set(o.get("part_id").tolist())
+        assert not (set(d["part_id"].tolist()) & alive), step          # gone from the SPH set ...
+        assert np.all(d["xi"][:, 0] > 2.5 * case["params"]["particle_step"]), step   # ... because past the plane
+        assert np.all(np.diff(d["part_id"]) != 0) and np.allclose(d["t"], t_before), step
+        assert np.allclose(d["mass"], case["m"][0]) and np.all(d["v"][:, 0] > 0.0), step
+    assert handed >= 25
+    assert e.take_deleted()["part_id"].shape[0] == 0                    # the queue was emptied
+
+
 def test_runge_kutta_dynamic_inlet_is_rejected():
     from fjsph_b200._lib import FjsphError
 
