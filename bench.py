@@ -59,9 +59,11 @@ def parse_args():
     ap.add_argument("--droplet-dx", type=float, default=0.0008)
     ap.add_argument("--solver", default="newmark_beta", choices=["newmark_beta", "runge_kutta"])
     ap.add_argument("--cpu-sample", default="64,64,64", help="lattice of the bounded CPU-baseline sample (block workload)")
-    ap.add_argument("--check", action="store_true",
-                    help="before the timed steps: 2 steps of the slab engine on a ~1 M-particle block against the 1-GPU engine "
-                         "(N > 1; rank 0 reports the differences in `slab_parity`)")
+    ap.add_argument("--no-check", action="store_true",
+                    help="N > 1: skip the slab parity check (2 steps of the slab engines on a ~1 M-particle block against one "
+                         "engine, reported as `slab_parity`)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="N > 1: skip the side lines (`workloads.jet`: the 12.5 M-per-GPU jet; `strong`: 12.5 M particles in total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -266,6 +268,85 @@ def run_reference(args, rank, world):
 _RESULT_FD = None
 
 
+def slab_parity(rank, world, local_rank):
+    """2 steps of the slab engines (x-slabs over all ranks, ghosts and migration over NCCL) against ONE engine on rank 0, on a
+    ~1 M-particle block of the bench workload: every particle compared by id (tools/slab_check.py).  Carries the multi-GPU
+    parity into the scaling run itself."""
+    import io
+    from contextlib import redirect_stdout
+
+    from fjsph_b200 import cases
+    from tools import slab_check
+
+    case = cases.synthetic_block((208, 70, 70), 1e-3, jitter=0.1, seed=77)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        ok = slab_check.run("bench block", case, dict(case["params"], delta_t_min=1e-9, max_subits=K_SUBITS - 1,
+                                                      min_residual=-30.0), 2, rank, world, local_rank)
+    errs = {}
+    for line in buf.getvalue().splitlines():
+        t = line.split()
+        if len(t) >= 3 and t[1] == "relerr":
+            errs[t[0]] = float(t[2])
+        elif len(t) >= 4 and t[1] == "differing":
+            errs[t[0] + "_flags_differing"] = int(t[3])
+    return {"ok": bool(ok), "particles": int(case["xi"].shape[0]), "steps": 2, "world": world,
+            "what": "slab engines vs one engine on rank 0, particle by particle (normwise relative errors; flags: count)",
+            "errors": errs}
+
+
+def time_slab_workload(args, rank, world, local_rank, workload, cells, steps, warmup):
+    """A side measurement at N > 1: K steps of another workload / decomposition, device-resident, max over ranks."""
+    import argparse
+
+    import torch
+    import torch.distributed as dist
+
+    from fjsph_b200 import engine as eng, slab
+
+    a = argparse.Namespace(**vars(args))
+    a.workload = workload
+    if workload == "jet":
+        a.jet_columns = int(cells)
+        nx = a.jet_columns
+        case = make_case(a, rank, cells=str(nx))
+    else:
+        a.cells = cells
+        nx = int(cells.split(",")[0])
+        case = make_case(a, rank)
+    params = step_params(a, case["params"])
+    n = case["xi"].shape[0]
+    dx = case["params"]["particle_step"]
+    x_lo = -1e300 if rank == 0 else (rank * nx - 0.5) * dx
+    x_hi = 1e300 if rank == world - 1 else ((rank + 1) * nx - 0.5) * dx
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        e = slab.SlabEngine(eng.default_params(3, **params), case, rank, world, x_lo, x_hi, device=local_rank, stream=stream,
+                            part_id=np.arange(n, dtype=np.int64) + rank * n)
+        for _ in range(warmup):
+            e.integrate()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for _ in range(steps):
+            e.integrate()
+        ev1.record(stream)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(n - case["bound_points"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    e.close()
+    del e
+    torch.cuda.empty_cache()
+    total = float(cnt.item())
+    return {"value": total * steps / (float(t.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t.item()) / steps,
+            "particles_total": int(total), "steps": steps, "warmup": warmup, "workload": workload_name(a, world)}
+
+
 def emit(line: dict) -> None:
     """The ONE JSON line of the contract, on the process's real stdout."""
     data = (json.dumps(line) + "\n").encode()
@@ -301,6 +382,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    parity = None
+    if world > 1 and not args.no_check:
+        parity = slab_parity(rank, world, local_rank)
 
     case = make_case(args, rank)
     params = step_params(args, case["params"])
@@ -455,10 +539,25 @@ def main():
         e2e = {"value": total_fluid * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt / args.steps * 1e3, "note": "bytes are per rank"}
 
+    slab_stats = e.slab_stats() if world > 1 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference(args, 4, 1, args.cpu_sample)  # ~25 s of CPU work: 1 warm-up + 4 timed steps, median
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    extras = {}
+    if world > 1 and not args.no_extras:
+        e.close()
+        del e
+        torch.cuda.empty_cache()
+        n_cells = [int(k) for k in args.cells.split(",")]
+        if args.workload != "jet":
+            # north_star's 100 M-particle jet: 12.5 M particles per GPU, Gissler aero in a cross flow
+            extras["workloads"] = {"jet": time_slab_workload(args, rank, world, local_rank, "jet", str(args.jet_columns), 3, 2)}
+        # strong scaling: the single-GPU workload (12.5 M particles in total) cut over the N GPUs
+        sx = max(16, n_cells[0] // world)
+        extras["strong"] = dict(time_slab_workload(args, rank, world, local_rank, "block", "%d,%d,%d" % (sx, n_cells[1], n_cells[2]),
+                                                   5, 3), scaling="strong")
 
     if rank == 0:
         line = {
@@ -475,7 +574,9 @@ def main():
             "clocks": clocks, "kernels": kernels,
         }
         if world > 1:
-            line["slab"] = e.slab_stats()
+            line["slab"] = slab_stats
+            line["slab_parity"] = parity
+            line.update(extras)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -127,6 +127,8 @@ def lib():
     L.fjsph_set_slab.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_double, COMM_FN, vp]
     L.fjsph_slab_comm_stream.argtypes = [vp, P(vp)]
     L.fjsph_slab_overlapped.argtypes = [vp, P(C.c_int64)]
+    L.fjsph_get_stream.argtypes = [vp, P(vp)]
+    L.fjsph_slab_device_reductions.argtypes = [vp, C.c_int32]
     L.fjsph_take_deleted.argtypes = [vp, vp, C.c_int64, P(C.c_int64)]
     L.fjsph_slab_stats.argtypes = [vp, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)]
     L.fjsph_foam_read.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, P(vp)]
@@ -151,6 +153,33 @@ def lib():
     L.fjsph_case_state.argtypes = [vp, P(FjsphStateView)]
     _lib = L
     return L
+
+
+NCCL_LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libfjsph_b200_nccl.so")
+_nccl = None
+
+
+def nccl_lib():
+    """libfjsph_b200_nccl.so: the slab transport natively on NCCL (include/fjsph_b200_nccl.h).  None where it is not built."""
+    global _nccl
+    if _nccl is not None:
+        return _nccl
+    if not os.path.exists(NCCL_LIB_PATH):
+        return None
+    lib()  # libfjsph_b200.so first: the transport library links against it
+    N = C.CDLL(NCCL_LIB_PATH)
+    vp, P = C.c_void_p, C.POINTER
+    N.fjsph_nccl_unique_id.argtypes = [C.c_char_p]
+    N.fjsph_nccl_create.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, P(vp)]
+    N.fjsph_nccl_attach.argtypes = [vp, vp, C.c_double, C.c_double]
+    N.fjsph_nccl_allreduce_host.argtypes = [vp, vp, C.c_int64, C.c_int32]
+    N.fjsph_nccl_barrier.argtypes = [vp]
+    N.fjsph_nccl_calls.argtypes = [vp, C.c_int32]
+    N.fjsph_nccl_calls.restype = C.c_int64
+    N.fjsph_nccl_last_error.restype = C.c_char_p
+    N.fjsph_nccl_destroy.argtypes = [vp]
+    _nccl = N
+    return N
 
 
 class FjsphError(RuntimeError):

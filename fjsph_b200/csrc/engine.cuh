@@ -134,6 +134,7 @@ struct Slab
     // swept after the main stream has waited for ev_done.  Every other kernel family waits first (KScope).
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    bool dev_reduce = false;  // the callback implements FJSPH_COMM_SUM_DEV / MAX_DEV (fjsph_slab_device_reductions)
     bool overlap = true;      // FJSPH_SLAB_OVERLAP=0 in the environment: exchanges complete before the next launch
     bool pending = false;     // an exchange is in flight on comm_stream
     bool hold = false;        // set around the interior launches: KScope does not wait
@@ -359,6 +360,8 @@ static inline bool fj_halo_overlappable(const FjsphEngine* e)
     return e->slab.on && e->slab.pending && e->slab.n_interior > 0 && e->slab.n_interior < e->n_owned;
 }
 int fj_allreduce(FjsphEngine* e, int op, double* v, int n);
+/* in place on a DEVICE array, ordered on e->stream; returns FJSPH_OK with *done = false when the transport cannot */
+int fj_allreduce_dev(FjsphEngine* e, int op, double* d_v, int n, bool* done);
 int fj_redecompose(FjsphEngine* e);
 double fj_fluid_count(FjsphEngine* e);
 double fj_total_count(FjsphEngine* e);

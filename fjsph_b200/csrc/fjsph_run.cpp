@@ -1,12 +1,21 @@
 // fjsph_run.cpp — command-line driver: FJSPH's main() (reference src/FJSPH.cpp:29-356) on top of the C ABI.
 //
-//   fjsph_b200_run <para file> [--frames N] [--device K] [--restart file.fjr] [--out prefix] [--quiet]
+//   fjsph_b200_run <para file> [--frames N] [--device K] [--restart file.fjr] [--out prefix] [--quiet] [--ranks N]
+//
+// --ranks N (N > 1): one process per GPU (forked here; rank r on device r), the case cut into N x-slabs of equal
+// particle count, ghosts and migration over NCCL send/recv, the step's scalars by NCCL all-reduce on device buffers
+// (comm_nccl.cu, include/fjsph_b200_nccl.h).  Every rank writes its own frame files (<prefix>_r<rank>_frame_*.dat); rank 0
+// writes <prefix>_frame.info with the global counts.  Decks with inlet tables and restart files are single-GPU for now.
 //
 // GetInput + Init_Particles (fjsph_case_read) -> engine -> integrate_no_update at t = 0 (FJSPH.cpp:183) -> the frame
 // loop `while (stept + 0.1 dt_min < frame_dt) integrate` (FJSPH.cpp:262-283) with the reference's per-step table
 // (Integration.cpp:250-265), `<prefix>_frame.info` (FJSPH.cpp:228-243,286-300), one ASCII Tecplot zone file per frame
 // (the fallback of AsciiIO.cpp; TECIO / HDF5 are not available here) and a restart file after every frame
 // (csrc/restart.cu).  Everything numerical happens behind fjsph_step; this file is host bookkeeping only.
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +24,7 @@
 #include <vector>
 
 #include "../../include/fjsph_b200.h"
+#include "../../include/fjsph_b200_nccl.h"
 
 static int fail(const char* what)
 {
@@ -57,13 +67,80 @@ static int write_frame(FjsphEngine* e, const std::string& prefix, int frame, dou
     return 0;
 }
 
+static int run(int argc, char** argv, int rank, int world, const char* nccl_id);
+
 int main(int argc, char** argv)
 {
     if (argc < 2)
     {
-        std::fprintf(stderr, "usage: %s <para file> [--frames N] [--device K] [--restart file] [--out prefix] [--quiet]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s <para file> [--frames N] [--device K] [--restart file] [--out prefix] [--quiet] [--ranks N]\n",
+                     argv[0]);
         return 2;
     }
+    int ranks = 1;
+    for (int a = 2; a + 1 < argc; ++a)
+        if (std::string(argv[a]) == "--ranks")
+            ranks = std::atoi(argv[a + 1]);
+    if (ranks <= 1)
+        return run(argc, argv, 0, 1, nullptr);
+    /* one process per GPU.  Rank 0 makes the NCCL id AFTER the fork (ncclGetUniqueId starts a bootstrap thread, which a
+       fork would not carry over) and hands it to the others through pipes made before it. */
+    std::vector<int> rd(size_t(ranks), -1), wr(size_t(ranks), -1);
+    for (int r = 1; r < ranks; ++r)
+    {
+        int fd[2];
+        if (pipe(fd) != 0)
+        {
+            std::perror("pipe");
+            return 1;
+        }
+        rd[size_t(r)] = fd[0];
+        wr[size_t(r)] = fd[1];
+    }
+    std::vector<pid_t> kids;
+    for (int r = 0; r < ranks; ++r)
+    {
+        const pid_t pid = fork();
+        if (pid < 0)
+        {
+            std::perror("fork");
+            return 1;
+        }
+        if (pid == 0)
+        {
+            char id[FJSPH_NCCL_ID_BYTES];
+            if (r == 0)
+            {
+                if (fjsph_nccl_unique_id(id))
+                {
+                    std::fprintf(stderr, "ERROR: %s\n", fjsph_nccl_last_error());
+                    _exit(1);
+                }
+                for (int q = 1; q < ranks; ++q)
+                    if (write(wr[size_t(q)], id, sizeof(id)) != ssize_t(sizeof(id)))
+                        _exit(1);
+            }
+            else if (read(rd[size_t(r)], id, sizeof(id)) != ssize_t(sizeof(id)))
+                _exit(1);
+            const int rc = run(argc, argv, r, ranks, id);
+            std::fflush(nullptr);
+            _exit(rc);
+        }
+        kids.push_back(pid);
+    }
+    int worst = 0;
+    for (pid_t k : kids)
+    {
+        int status = 0;
+        waitpid(k, &status, 0);
+        const int rc = WIFEXITED(status) ? WEXITSTATUS(status) : 1;
+        worst = std::max(worst, rc);
+    }
+    return worst;
+}
+
+static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
+{
     const char* para = argv[1];
     int frames_cli = -1, device = 0;
     bool quiet = false;
@@ -81,6 +158,8 @@ int main(int argc, char** argv)
             restart_file = argv[++a];
         else if (a + 1 < argc && k == "--out")
             prefix_cli = argv[++a];
+        else if (a + 1 < argc && k == "--ranks")
+            ++a;
         else
         {
             std::fprintf(stderr, "unknown argument %s\n", k.c_str());
@@ -128,20 +207,34 @@ int main(int argc, char** argv)
             std::printf("OpenFOAM mesh: %lld cells, %lld triangles\n", (long long)view.n_cells, (long long)view.n_faces);
         }
     }
-    const int64_t n0 = fjsph_case_count(c), nb0 = fjsph_case_bound_points(c);
-    const int64_t capacity = max_points > n0 ? max_points : 2 * n0 + 100000;
+    const int64_t n_case = fjsph_case_count(c), nb_case = fjsph_case_bound_points(c);
+    int64_t n0 = n_case, nb0 = nb_case;
+    FjsphNcclComm* comm = nullptr;
+    if (world > 1)
+    {
+        device = rank; /* one process per GPU */
+        if (!restart_file.empty())
+        {
+            std::fprintf(stderr, "ERROR: --restart is single-GPU (gather the slabs first)\n");
+            return 1;
+        }
+        if (fjsph_nccl_create(nccl_id, rank, world, device, &comm))
+        {
+            std::fprintf(stderr, "ERROR: %s\n", fjsph_nccl_last_error());
+            return 1;
+        }
+        prefix += "_r" + std::to_string(rank);
+    }
     FjsphEngine* e = nullptr;
-    if (fjsph_create(&P, device, capacity, &e))
-        return fail("creating the engine");
     int32_t frame = 0;
     if (restart_file.empty())
     {
-        std::vector<double> xi(3 * n0), v(3 * n0), rho(n0), p(n0), m(n0);
-        std::vector<int32_t> b(n0);
-        std::vector<int64_t> pid(n0);
+        std::vector<double> xi(3 * n_case), v(3 * n_case), rho(n_case), p(n_case), m(n_case);
+        std::vector<int32_t> b(n_case);
+        std::vector<int64_t> pid(n_case);
         FjsphStateView s;
         std::memset(&s, 0, sizeof(s));
-        s.n = n0;
+        s.n = n_case;
         s.xi = xi.data();
         s.v = v.data();
         s.rho = rho.data();
@@ -149,16 +242,99 @@ int main(int argc, char** argv)
         s.m = m.data();
         s.b = b.data();
         s.part_id = pid.data();
-        if (fjsph_case_state(c, &s) || fjsph_upload_state(e, &s, nb0))
-            return fail("uploading the particles");
+        if (fjsph_case_state(c, &s))
+            return fail("reading the particles of the case");
         const int32_t nblk = fjsph_case_num_blocks(c);
         std::vector<FjsphBlock> blocks(nblk);
         for (int32_t i = 0; i < nblk; ++i) fjsph_case_block(c, i, &blocks[i], nullptr, 0);
+        double x_lo = -1e300, x_hi = 1e300;
+        if (world > 1)
+        {
+            /* x-slabs of equal particle count: cuts at the quantiles of x, half-way between the two particles either side;
+               every rank keeps its particles in the case's order, so every block stays one contiguous range */
+            for (const FjsphBlock& B : blocks)
+                if (B.n_back > 0)
+                {
+                    std::fprintf(stderr, "ERROR: decks with inlet tables run on one GPU with this driver (--ranks 1)\n");
+                    return 1;
+                }
+            std::vector<double> xs(static_cast<size_t>(n_case), 0.0);
+            for (int64_t i = 0; i < n_case; ++i) xs[size_t(i)] = xi[3 * size_t(i)];
+            std::sort(xs.begin(), xs.end());
+            auto cut = [&](int r) {
+                const size_t k = size_t(n_case) * size_t(r) / size_t(world);
+                return 0.5 * (xs[k - 1] + xs[k]);
+            };
+            if (rank > 0)
+                x_lo = cut(rank);
+            if (rank < world - 1)
+                x_hi = cut(rank + 1);
+            std::vector<int64_t> keep;
+            for (int64_t i = 0; i < n_case; ++i)
+                if (xi[3 * size_t(i)] >= x_lo && xi[3 * size_t(i)] < x_hi)
+                    keep.push_back(i);
+            std::vector<int64_t> before(static_cast<size_t>(n_case) + 1, 0); /* kept particles with a smaller case index */
+            {
+                size_t k = 0;
+                for (int64_t i = 0; i <= n_case; ++i)
+                {
+                    while (k < keep.size() && keep[k] < i) ++k;
+                    before[size_t(i)] = int64_t(k);
+                }
+            }
+            for (FjsphBlock& B : blocks)
+            {
+                B.first = before[size_t(B.first)];
+                B.second = before[size_t(B.second)];
+            }
+            n0 = int64_t(keep.size());
+            nb0 = before[size_t(nb_case)];
+            for (size_t k = 0; k < keep.size(); ++k)
+            {
+                const size_t i = size_t(keep[k]);
+                for (int d = 0; d < 3; ++d)
+                {
+                    xi[3 * k + size_t(d)] = xi[3 * i + size_t(d)];
+                    v[3 * k + size_t(d)] = v[3 * i + size_t(d)];
+                }
+                rho[k] = rho[i];
+                p[k] = p[i];
+                m[k] = m[i];
+                b[k] = b[i];
+                pid[k] = pid[i];
+            }
+            s.n = n0;
+        }
+        const int64_t capacity = (world == 1 && max_points > n0) ? max_points : 2 * n0 + 100000;
+        if (fjsph_create(&P, device, capacity, &e))
+            return fail("creating the engine");
+        if (fjsph_upload_state(e, &s, nb0))
+            return fail("uploading the particles");
         if (nblk && fjsph_set_blocks(e, nblk, blocks.data()))
             return fail("setting the blocks");
+        if (world > 1 && fjsph_nccl_attach(comm, e, x_lo, x_hi))
+        {
+            std::fprintf(stderr, "ERROR: %s\n", fjsph_nccl_last_error());
+            return 1;
+        }
     }
-    else if (fjsph_read_restart(e, restart_file.c_str(), &frame))
-        return fail("reading the restart file");
+    else
+    {
+        const int64_t capacity = max_points > n0 ? max_points : 2 * n0 + 100000;
+        if (fjsph_create(&P, device, capacity, &e))
+            return fail("creating the engine");
+        if (fjsph_read_restart(e, restart_file.c_str(), &frame))
+            return fail("reading the restart file");
+    }
+    /* particle counts of the whole domain for the frame table (a rank's own counts change with migration) */
+    auto global_counts = [&](long long& n_all, long long& n_bound) -> int {
+        double cnt[2] = {double(fjsph_count(e)), double(nb0)};
+        if (comm && fjsph_nccl_allreduce_host(comm, cnt, 2, FJSPH_COMM_SUM))
+            return 1;
+        n_all = (long long)cnt[0];
+        n_bound = (long long)cnt[1];
+        return 0;
+    };
     if (aero_mesh)
     {
         FjsphMesh view;
@@ -167,7 +343,13 @@ int main(int argc, char** argv)
         fjsph_foam_free(aero_mesh);
     }
     fjsph_get_params(e, &P);
-    std::printf("Starting counts:\nBoundary: %lld  Sim: %lld\n\n", (long long)nb0, (long long)(fjsph_count(e) - nb0));
+    long long n_all = 0, n_bound = 0;
+    if (global_counts(n_all, n_bound))
+        return 1;
+    if (rank == 0)
+        std::printf("Starting counts:\nBoundary: %lld  Sim: %lld%s\n\n", n_bound, n_all - n_bound,
+                    world > 1 ? (" (" + std::to_string(world) + " x-slabs, one GPU each)").c_str() : "");
+    quiet = quiet || rank != 0;
 
     const std::string info_name = prefix + "_frame.info";
     FILE* info = std::fopen(info_name.c_str(), restart_file.empty() ? "w" : "a");
@@ -187,8 +369,8 @@ int main(int argc, char** argv)
             return fail("writing frame 0");
         if (fjsph_integrate_no_update(e, &st)) /* populate the force vectors, FJSPH.cpp:183 */
             return fail("first integrate_no_update");
-        std::fprintf(info, "Frame: %u\nTotal Points: %lld Boundary Points: %lld Fluid Points: %lld\n", 0u,
-                     (long long)fjsph_count(e), (long long)nb0, (long long)(fjsph_count(e) - nb0));
+        std::fprintf(info, "Frame: %u\nTotal Points: %lld Boundary Points: %lld Fluid Points: %lld\n", 0u, n_all, n_bound,
+                     n_all - n_bound);
         std::fprintf(info, "Sim Time:  %.7g Comp Time: %.6e Error: %.6f Sub-iterations: %d\n", P.current_time, seconds(), 0.0, 0);
         std::fprintf(info, "Deleted particles: %lld Internal collisions: %d\n", deleted, 0);
     }
@@ -214,15 +396,20 @@ int main(int argc, char** argv)
             stept += st.dt;
             ++stepits;
         }
-        const int64_t n = fjsph_count(e);
-        std::fprintf(info, "\nFrame: %u\nTotal Points: %lld Boundary Points: %lld Fluid Points: %lld\n", unsigned(fr), (long long)n,
-                     (long long)nb0, (long long)(n - nb0));
+        if (global_counts(n_all, n_bound))
+            return 1;
+        const long long n = n_all;
+        std::fprintf(info, "\nFrame: %u\nTotal Points: %lld Boundary Points: %lld Fluid Points: %lld\n", unsigned(fr), n, n_bound,
+                     n - n_bound);
         std::fprintf(info, "Sim Time:  %.7g Comp Time: %.6e Error: %.6f Sub-iterations: %d\n", P.current_time, seconds(), error, stepits);
         std::fprintf(info, "Deleted particles: %lld Internal collisions: %d\n", deleted, 0);
         std::fflush(info);
-        std::printf("Frame: %d  Sim Time: %.7g  Compute Time: %.3f  Error: %.5f\n", fr, P.current_time, seconds(), error);
-        std::printf("Boundary particles:  %lld Sim particles: %lld Deleted particles: %lld\n", (long long)nb0, (long long)(n - nb0), deleted);
-        if (n - nb0 == 0)
+        if (rank == 0)
+        {
+            std::printf("Frame: %d  Sim Time: %.7g  Compute Time: %.3f  Error: %.5f\n", fr, P.current_time, seconds(), error);
+            std::printf("Boundary particles:  %lld Sim particles: %lld Deleted particles: %lld\n", n_bound, n - n_bound, deleted);
+        }
+        if (n - n_bound == 0)
         {
             std::printf("No more points in the simulation space. Ending....\n");
             break;
@@ -234,12 +421,21 @@ int main(int argc, char** argv)
         P.last_frame_time += P.frame_time_interval;
         if (fjsph_set_params(e, &P))
             return fail("set_params");
-        if (fjsph_write_restart(e, (prefix + "_particles.fjr").c_str(), fr))
+        if (world == 1 && fjsph_write_restart(e, (prefix + "_particles.fjr").c_str(), fr))
             return fail("writing the restart file");
     }
     std::fclose(info);
-    std::printf("Simulation complete!\nTime taken:\t%.3f seconds\nTotal simulation time:\t%.7g seconds\n", seconds(), P.current_time);
+    if (rank == 0)
+        std::printf("Simulation complete!\nTime taken:\t%.3f seconds\nTotal simulation time:\t%.7g seconds\n", seconds(), P.current_time);
+    if (comm && rank == 0)
+        std::printf("NCCL transport: %lld device all-reduces, %lld host all-reduces, %lld + %lld neighbour exchanges\n",
+                    (long long)(fjsph_nccl_calls(comm, FJSPH_COMM_SUM_DEV) + fjsph_nccl_calls(comm, FJSPH_COMM_MAX_DEV)),
+                    (long long)(fjsph_nccl_calls(comm, FJSPH_COMM_SUM) + fjsph_nccl_calls(comm, FJSPH_COMM_MAX)),
+                    (long long)fjsph_nccl_calls(comm, FJSPH_COMM_SENDRECV_DEV_ASYNC),
+                    (long long)fjsph_nccl_calls(comm, FJSPH_COMM_SENDRECV_DEV));
     fjsph_destroy(e);
+    if (comm)
+        fjsph_nccl_destroy(comm);
     fjsph_case_free(c);
     return 0;
 }

@@ -249,6 +249,24 @@ int fj_allreduce(FjsphEngine* e, int op, double* v, int n)
     return comm(e, op, v, int64_t(n) * 8, nullptr, 0, nullptr, 0, nullptr, 0);
 }
 
+int fj_allreduce_dev(FjsphEngine* e, int op, double* d_v, int n, bool* done)
+{
+    *done = false;
+    if (!e->slab.on || e->slab.world == 1)
+    {
+        *done = true; /* nothing to reduce over */
+        return FJSPH_OK;
+    }
+    if (!e->slab.dev_reduce)
+        return FJSPH_OK;
+    int st = comm(e, op == FJSPH_COMM_SUM ? FJSPH_COMM_SUM_DEV : FJSPH_COMM_MAX_DEV, d_v, int64_t(n) * 8, nullptr, 0, nullptr, 0,
+                  nullptr, 0);
+    if (st)
+        return st;
+    *done = true;
+    return FJSPH_OK;
+}
+
 double fj_fluid_count(FjsphEngine* e)
 {
     return e->slab.on ? e->slab.n_fluid_global : double(e->n_owned - e->bound_points);
@@ -571,6 +589,17 @@ extern "C" int fjsph_set_slab(FjsphEngine* e, int32_t rank, int32_t world, doubl
     if (st)
         return st;
     e->next_part_id = (long long)ids;
+    return FJSPH_OK;
+}
+
+extern "C" int fjsph_get_stream(FjsphEngine* e, void** stream)
+{
+    *stream = (void*)e->stream;
+    return FJSPH_OK;
+}
+extern "C" int fjsph_slab_device_reductions(FjsphEngine* e, int32_t on)
+{
+    e->slab.dev_reduce = on != 0;
     return FJSPH_OK;
 }
 

@@ -116,7 +116,8 @@ __global__ void k_timestep_partials(Level S, const int* __restrict__ blk, int n_
         partial[blockIdx.x * 7 + c] = x;
     }
 }
-__global__ void k_timestep_final(const double* __restrict__ partial, int nblocks, double* __restrict__ out)
+__global__ void k_timestep_final(const double* __restrict__ partial, int nblocks, double* __restrict__ out,
+                                 bool negate_min = false)
 {
     // one warp per component, lanes stride the block partials
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,7 +135,7 @@ __global__ void k_timestep_final(const double* __restrict__ partial, int nblocks
         x = (c == 4) ? fmin(x, y) : fmax(x, y);
     }
     if (lane == 0)
-        out[c] = x;
+        out[c] = (negate_min && c == 4) ? -x : x; /* min as -max(-x): one MAX all-reduce serves all seven */
 }
 
 // keeps V = m/rho and p/rho^2 consistent with (rho, p)
@@ -465,10 +466,15 @@ int fj_reduce_sum(FjsphEngine* e, int nblocks, int ncomp, double* out_host)
     k_reduce_sum<<<1, TPB, 0, e->stream>>>(e->red, nblocks, ncomp, e->red_out);
     e->launches++;
     FJ_CUDA(cudaGetLastError());
+    /* slab decomposition: the sum over all ranks -- on the device, ahead of the one readback, when the transport can */
+    bool reduced = false;
+    int st = fj_allreduce_dev(e, FJSPH_COMM_SUM, e->red_out, ncomp, &reduced);
+    if (st)
+        return st;
     FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, ncomp * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     FJ_CUDA(cudaStreamSynchronize(e->stream));
     for (int c = 0; c < ncomp; ++c) out_host[c] = e->h_red[c];
-    return fj_allreduce(e, FJSPH_COMM_SUM, out_host, ncomp); /* slab decomposition: the sum over all ranks */
+    return reduced ? FJSPH_OK : fj_allreduce(e, FJSPH_COMM_SUM, out_host, ncomp);
 }
 
 // The engine's stream waits for the second half of a split upload (upload_state_split, abi.cu).
@@ -501,12 +507,22 @@ int fj_find_timestep(FjsphEngine* e, double* dt_out)
     {
         KScope ks(e, "timestep", 2);
         k_timestep_partials<<<nb, TPB, 0, e->stream>>>(e->lv[1], e->blk, e->n_bound_blocks, e->C, n, e->red);
-        k_timestep_final<<<1, 7 * 32, 0, e->stream>>>(e->red, nb, e->red_out);
+        k_timestep_final<<<1, 7 * 32, 0, e->stream>>>(e->red, nb, e->red_out, e->slab.on && e->slab.dev_reduce);
     }
     FJ_CUDA(cudaGetLastError());
+    /* slabs: max over all ranks (the minimum, component 4, travels negated) on the device when the transport can */
+    bool reduced = false;
+    if (e->slab.on && e->slab.dev_reduce)
+    {
+        int st = fj_allreduce_dev(e, FJSPH_COMM_MAX, e->red_out, 7, &reduced);
+        if (st)
+            return st;
+    }
     FJ_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, 7 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     FJ_CUDA(cudaStreamSynchronize(e->stream));
-    if (e->slab.on)
+    if (e->slab.on && e->slab.dev_reduce)
+        e->h_red[4] = -e->h_red[4];
+    if (e->slab.on && !reduced)
     {
         double v[7];
         for (int c = 0; c < 7; ++c) v[c] = (c == 4) ? -e->h_red[c] : e->h_red[c]; /* min as -max(-x) */

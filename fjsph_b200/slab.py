@@ -17,6 +17,7 @@ from . import _lib, engine as eng
 from ._lib import check
 
 COMM_SUM, COMM_MAX, COMM_SENDRECV_DEV, COMM_SENDRECV_HOST, COMM_SENDRECV_DEV_ASYNC = 0, 1, 2, 3, 4
+COMM_SUM_DEV, COMM_MAX_DEV = 5, 6
 COMM_FN = _lib.COMM_FN
 
 
@@ -59,12 +60,17 @@ class Transport:
         self.calls = {COMM_SUM: 0, COMM_MAX: 0, COMM_SENDRECV_DEV: 0, COMM_SENDRECV_HOST: 0, COMM_SENDRECV_DEV_ASYNC: 0}
         self.error = None
         self.comm_stream = None  # torch view of the engine's comm stream (set_comm_stream), for the ASYNC exchanges
+        self.main_stream = None  # torch view of the engine's main stream (set_main_stream), for the device reductions
         self.fn = COMM_FN(self._callback)  # keep alive as long as the engine uses it
 
     def set_comm_stream(self, cuda_stream_ptr: int):
         """The engine's comm stream (fjsph_slab_comm_stream): FJSPH_COMM_SENDRECV_DEV_ASYNC exchanges are ordered on it,
         so that they run beside the interior sweeps the engine queues on its main stream."""
         self.comm_stream = self.torch.cuda.ExternalStream(int(cuda_stream_ptr), device=self.device)
+
+    def set_main_stream(self, cuda_stream_ptr: int):
+        """The engine's main stream (fjsph_get_stream): FJSPH_COMM_SUM_DEV / MAX_DEV all-reduce device arrays in place on it."""
+        self.main_stream = self.torch.cuda.ExternalStream(int(cuda_stream_ptr), device=self.device)
 
     # -- pieces
     def _host_array(self, ptr, nbytes, dtype):
@@ -100,6 +106,12 @@ class Transport:
             torch = self.torch
             if op in (COMM_SUM, COMM_MAX):
                 self.allreduce(a, na, op)
+            elif op in (COMM_SUM_DEV, COMM_MAX_DEV):
+                # in place on the engine's device array, ordered on its main stream: no host round trip
+                t = torch.as_tensor(_DevBuf(a, na), device=self.device).view(torch.float64)
+                with torch.cuda.stream(self.main_stream):
+                    self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == COMM_SUM_DEV else self.dist.ReduceOp.MAX,
+                                         group=self.group)
             elif op in (COMM_SENDRECV_DEV, COMM_SENDRECV_DEV_ASYNC):
                 t = [torch.as_tensor(_DevBuf(p, n), device=self.device) if (p and n > 0) else None
                      for p, n in ((a, na), (b, nb), (c, nc), (d, nd))]
@@ -132,7 +144,10 @@ class SlabEngine(eng.Engine):
     """One rank of a slab-decomposed simulation.  `case` holds THIS rank's particles (see partition())."""
 
     def __init__(self, params, case, rank, world, x_lo, x_hi, device=0, stream=None, capacity=None, group=None,
-                 part_id=None):
+                 part_id=None, transport="auto"):
+        """transport: "native" = libfjsph_b200_nccl.so (ncclSend / ncclRecv / ncclAllReduce straight from C++, the NCCL id
+        handed round through torch.distributed once), "torch" = the callback below on torch.distributed, "auto" = native on
+        the nccl backend when the library is built."""
         n = case["xi"].shape[0]
         # room for ghosts on both faces and for migration imbalance
         super().__init__(params, int(capacity or (n * 1.25 + 400_000)), device=device)
@@ -142,11 +157,43 @@ class SlabEngine(eng.Engine):
         extra = {} if part_id is None else {"part_id": np.ascontiguousarray(part_id, dtype=np.int64)}
         self.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"], **extra)
         self.transport = Transport(group=group)
+        self.native = None
+        N = _lib.nccl_lib() if transport in ("auto", "native") and self.transport.backend == "nccl" and world > 1 else None
+        if transport == "native" and N is None:
+            raise RuntimeError("native NCCL transport requested but libfjsph_b200_nccl.so is not built / backend is not nccl")
+        if N is not None:
+            import torch
+            import torch.distributed as dist
+
+            ident = torch.zeros(128, dtype=torch.uint8, device=self.transport.device)
+            if rank == 0:
+                buf = C.create_string_buffer(128)
+                if N.fjsph_nccl_unique_id(buf):
+                    raise RuntimeError(N.fjsph_nccl_last_error().decode())
+                ident.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+            dist.broadcast(ident, src=0, group=group)
+            comm = C.c_void_p()
+            if N.fjsph_nccl_create(bytes(ident.cpu().numpy().tobytes()), rank, world, int(device), C.byref(comm)):
+                raise RuntimeError(N.fjsph_nccl_last_error().decode())
+            if N.fjsph_nccl_attach(comm, self._h, float(x_lo), float(x_hi)):
+                raise RuntimeError(N.fjsph_nccl_last_error().decode())
+            self.native, self._N = comm, N
+            return
         check(self._L.fjsph_set_slab(self._h, rank, world, float(x_lo), float(x_hi), self.transport.fn, None))
         if self.transport.backend == "nccl":
             cs = C.c_void_p()
             check(self._L.fjsph_slab_comm_stream(self._h, C.byref(cs)))
             self.transport.set_comm_stream(cs.value)
+            ms = C.c_void_p()
+            check(self._L.fjsph_get_stream(self._h, C.byref(ms)))
+            self.transport.set_main_stream(ms.value)
+            check(self._L.fjsph_slab_device_reductions(self._h, 1))
+
+    def close(self):
+        super().close()
+        if getattr(self, "native", None):
+            self._N.fjsph_nccl_destroy(self.native)
+            self.native = None
 
     def _raise_transport_error(self):
         if self.transport.error is not None:
@@ -174,6 +221,12 @@ class SlabEngine(eng.Engine):
         ov = C.c_int64()
         check(self._L.fjsph_slab_overlapped(self._h, C.byref(ov)))
         out["overlapped"] = int(ov.value)
+        out["transport"] = "native NCCL (libfjsph_b200_nccl.so)" if self.native else "torch.distributed " + self.transport.backend
+        if self.native:
+            out["device_allreduces"] = int(self._N.fjsph_nccl_calls(self.native, COMM_SUM_DEV)
+                                           + self._N.fjsph_nccl_calls(self.native, COMM_MAX_DEV))
+            out["host_allreduces"] = int(self._N.fjsph_nccl_calls(self.native, COMM_SUM)
+                                         + self._N.fjsph_nccl_calls(self.native, COMM_MAX))
         return out
 
     def pair_count(self) -> float:

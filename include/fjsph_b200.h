@@ -243,12 +243,20 @@ int fjsph_set_skin(FjsphEngine* e, double skin_over_dx);
  * The callback returns 0 on success.  fjsph_b200/slab.py implements it with NCCL send/recv over NVLink
  * (torch.distributed); upload the rank's own particles with fjsph_upload_state first, then call fjsph_set_slab. */
 enum { FJSPH_COMM_SUM = 0, FJSPH_COMM_MAX = 1, FJSPH_COMM_SENDRECV_DEV = 2, FJSPH_COMM_SENDRECV_HOST = 3,
-       FJSPH_COMM_SENDRECV_DEV_ASYNC = 4 };
+       FJSPH_COMM_SENDRECV_DEV_ASYNC = 4,
+       /* all-reduce of the DEVICE array a (na/8 doubles) in place, ordered on the engine's MAIN stream (fjsph_get_stream):
+          used for the per-sub-iteration residual, npd and the time-step maxima when fjsph_slab_device_reductions is on --
+          the scalar then crosses PCIe once, after the all-reduce, instead of host -> device -> NCCL -> host */
+       FJSPH_COMM_SUM_DEV = 5, FJSPH_COMM_MAX_DEV = 6 };
 typedef int (*FjsphCommFn)(void* user, int32_t op, void* a, int64_t na, void* b, int64_t nb, void* c, int64_t nc,
                            void* d, int64_t nd);
 int fjsph_set_slab(FjsphEngine* e, int32_t rank, int32_t world, double x_lo, double x_hi, FjsphCommFn fn, void* user);
 /* the cudaStream_t FJSPH_COMM_SENDRECV_DEV_ASYNC exchanges must be ordered on (valid after fjsph_set_slab) */
 int fjsph_slab_comm_stream(FjsphEngine* e, void** stream);
+/* the engine's main stream (its own, or the one given to fjsph_set_stream): FJSPH_COMM_*_DEV reductions are ordered on it */
+int fjsph_get_stream(FjsphEngine* e, void** stream);
+/* tell the engine that the callback implements FJSPH_COMM_SUM_DEV / MAX_DEV (off by default: host-array reductions) */
+int fjsph_slab_device_reductions(FjsphEngine* e, int32_t on);
 /* forward exchanges that ran beside an interior sweep since fjsph_set_slab */
 int fjsph_slab_overlapped(FjsphEngine* e, int64_t* n);
 /* owned / ghost particle counts, halo exchanges, re-decompositions and bytes sent since fjsph_set_slab */

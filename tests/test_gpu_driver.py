@@ -60,3 +60,36 @@ def test_driver_runs_a_deck_and_resumes(tmp_path):
     # errors are messages and exit codes, never a crash
     bad = subprocess.run([BIN, str(tmp_path / "nope.para")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert bad.returncode == 1 and "could not open" in bad.stdout
+
+
+def test_driver_two_ranks_native_nccl(tmp_path):
+    """fjsph_b200_run --ranks 2: one process per GPU forked by the driver, the case cut into two x-slabs, ghosts and
+    migration by ncclSend / ncclRecv, the step's scalars by ncclAllReduce on device buffers (csrc/comm_nccl.cu) -- no Python
+    anywhere.  The particles of the two slabs, put together by id, are the single-GPU run's.  Needs two visible GPUs."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    for f in ("droplet3d.para", "droplet3d_fluid.bmap", "droplet3d_boundary.bmap"):
+        shutil.copy(os.path.join(ROOT, "tests", "decks", f), tmp_path / f)
+    para = tmp_path / "droplet3d.para"
+    para.write_text(para.read_text().replace("SPH frame time interval: 0.001", "SPH frame time interval: 4e-5")
+                    + "\n SPH frame count: 3\n")
+    run = lambda *a: subprocess.run([BIN, str(para), "--quiet", *a], cwd=tmp_path, stdout=subprocess.PIPE,
+                                    stderr=subprocess.STDOUT, text=True, timeout=300)
+    one = run("--out", "one")
+    assert one.returncode == 0, one.stdout[-2000:]
+    two = run("--out", "two", "--ranks", "2")
+    assert two.returncode == 0 and "NCCL transport:" in two.stdout, two.stdout[-3000:]
+    assert " 0 device all-reduces" not in two.stdout  # the residual was reduced on the device
+    ref = frame(tmp_path / "one_frame_00002.dat")
+    parts = np.concatenate([frame(tmp_path / ("two_r%d_frame_00002.dat" % r)) for r in (0, 1)])
+    assert parts.shape == ref.shape
+    parts = parts[np.argsort(parts[:, 11])]
+    ref = ref[np.argsort(ref[:, 11])]
+    assert np.array_equal(parts[:, 11], ref[:, 11])
+    # frames are printed with 8 significant digits; the slabs differ from one engine by summation order only
+    assert np.abs(parts[:, :3] - ref[:, :3]).max() <= 2e-7 * 0.05
+    assert np.abs(parts[:, 3:6] - ref[:, 3:6]).max() <= 1e-5 * max(np.abs(ref[:, 3:6]).max(), 1e-12)
+    info = (tmp_path / "two_r0_frame.info").read_text()
+    assert info.count("Frame:") == 3 and "Total Points: 4166 Boundary Points: 0 Fluid Points: 4166" in info

@@ -62,13 +62,14 @@ INPUT_PARAMS = ("ale pressure_rel solver_type acase asource use_lam use_TAB_def 
                 "frame_time_interval").split()
 
 
-def make_pair_from_deck(case, capacity=None, **kw):
-    """(oracle, engine) for a case read by fjsph_b200.frontend.read_case: same settings, particles and LIMITS blocks."""
+def make_pair_from_deck(case, capacity=None, kind=None, **kw):
+    """(oracle, engine) for a case read by fjsph_b200.frontend.read_case: same settings, particles and LIMITS blocks.
+    kind: the oracle build (None = the serial parity build, "3d_mt" = the same with its particle loops threaded)."""
     P = case["params"]
     dim = case["dim"]
     params = {k: (tuple(getattr(P, k)) if hasattr(getattr(P, k), "__len__") else getattr(P, k)) for k in INPUT_PARAMS}
     params.update(kw)
-    o = orc.Oracle(orc.default_params(dim, **params))
+    o = orc.Oracle(orc.default_params(dim, **params), kind=kind)
     o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
     o.lib.orc_clear_blocks(o.h)
     for B in case["blocks"]:
