@@ -454,12 +454,38 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = FORCE_BYTES_PER_PARTICLE * n_fluid / (force_ms * 1e-3) / 1e9 if force_ms > 0 else 0.0
-    traffic = None
+    # Hardware counters of the same kernels from one `ncu --set full` capture of this build (profiles/kernel_counters.json,
+    # made by tools/kernel_counters.py): DRAM bytes and FP64-pipe busy time per launch, scaled by the particle count.  They
+    # are profile data, NOT measured in this run (ncu replays every kernel ~40 times); the durations they are set against
+    # are this run's CUDA-event times.
+    counters = {}
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "force_traffic.json")))
-        traffic = float(tr["dram_bytes_per_particle"]) * n_fluid
-    except (OSError, ValueError, KeyError):
+        counters = json.load(open(os.path.join(ROOT, "profiles", "kernel_counters.json")))
+    except (OSError, ValueError):
         pass
+    kc = counters.get("kernels", {})
+    kscale = n_fluid / float(counters.get("particles", n_fluid) or n_fluid)
+
+    def family_counters(prefixes):
+        """Sum over the kernels of one timed family (one launch of each), e.g. the lean + near launches of the fused sweep."""
+        picked = [v for k, v in kc.items() if any(k.startswith(p_) for p_ in prefixes)]
+        if not picked:
+            return None
+        return {"dram_bytes": sum(v["dram_bytes"] for v in picked) * kscale,
+                "fp64_pipe_busy_ms": sum(v["fp64_pipe_busy_ms"] * v["sm_mhz"] for v in picked) * kscale,  # ms x MHz
+                "kernels": [k for k in kc if any(k.startswith(p_) for p_ in prefixes)]}
+
+    def mean_variants(prefix):
+        """Mean over the captured instantiations of one kernel (force: the FROZEN and the plain one)."""
+        picked = [v for k, v in kc.items() if k.startswith(prefix)]
+        if not picked:
+            return None
+        return {"dram_bytes": float(np.mean([v["dram_bytes"] for v in picked])) * kscale,
+                "fp64_pipe_busy_ms": float(np.mean([v["fp64_pipe_busy_ms"] * v["sm_mhz"] for v in picked])) * kscale,
+                "kernels": [k for k in kc if k.startswith(prefix)]}
+
+    fcnt = mean_variants("k_force")
+    traffic = fcnt["dram_bytes"] if fcnt else None
     fp64_peak, fp64_src = FP64_NOMINAL_TFLOPS, "nominal (148 SM x 64 DFMA/clk x 1.965 GHz)"
     try:
         fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["fp64_tflops"])
@@ -470,7 +496,11 @@ def main():
     roofline = {
         "kernel": "k_force (get_acc_and_Rrho, Resid.cpp:243-469)", "bound": "hbm", "achieved": achieved,
         "peak": hbm_peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback", "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": traffic, "ms_per_launch": force_ms,
+        "frac": achieved / hbm_peak, "traffic": traffic,
+        "traffic_source": ("profile: profiles/kernel_counters.json (ncu --set full of this build: %s), dram__bytes_read + "
+                           "dram__bytes_write per launch, scaled by the particle count; not measured in this run"
+                           % counters.get("how", "")) if traffic is not None else None,
+        "ms_per_launch": force_ms,
         "algorithmic_bytes_per_launch": FORCE_BYTES_PER_PARTICLE * n_fluid,
         "fp64": {"achieved_tflops": fp64_achieved, "peak_tflops": fp64_peak, "peak_source": fp64_src,
                  "frac": fp64_achieved / fp64_peak, "nominal_peak_tflops": FP64_NOMINAL_TFLOPS,
@@ -478,6 +508,37 @@ def main():
                  "note": "the pair sweeps are FP64-pipe bound (SURVEY.md 8d), the HBM figure is the yardstick north_star names"},
         "step_hbm_frac": (value / max(1, world)) * STEP_BYTES_PER_PARTICLE / 1e9 / hbm_peak,
     }
+    sm_mhz_live = float(clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    if fcnt and force_ms > 0:
+        # FP64-pipe utilisation of the force sweep from the hardware counter (sm__inst_executed_pipe_fp64), not from a
+        # flop-per-pair estimate: pipe-busy time of the profile, rescaled to this run's clock, over this run's duration
+        roofline["fp64"]["pipe_busy_frac"] = fcnt["fp64_pipe_busy_ms"] / sm_mhz_live / force_ms
+        roofline["fp64"]["pipe_busy_source"] = "profile counter sm__inst_executed_pipe_fp64 x this run's CUDA-event duration"
+    # per-kernel rooflines: HBM for the streaming kernels, the FP64 pipe for the pair sweeps (SURVEY 8d algorithmic bytes)
+    FAMILIES = [("force", ["k_force"], 292.0, True), ("prestep", ["k_prestep"], 204.0, False),
+                ("surf1+diss", ["k_surf1_diss"], 460.0, False), ("surf2+3+shift", ["k_surf23_shift"], 252.0, False),
+                ("nb_list", ["k_exact_runs"], 40.0, False), ("nb_skin", ["k_build_skin_runs"], 40.0, False),
+                ("nb_update", ["k_nb_update"], 152.0, False)]
+    roofline_kernels = []
+    whole_busy = 0.0
+    for fam, prefixes, alg_bytes, variants in FAMILIES:
+        tm = timers.get(fam)
+        if not tm or tm["calls"] == 0:
+            continue
+        ms_launch = tm["ms"] / tm["calls"]
+        cnt_f = mean_variants(prefixes[0]) if variants else family_counters(prefixes)
+        ent = {"family": fam, "ms_per_call": ms_launch, "calls_per_step": tm["calls"] / args.steps,
+               "hbm": {"algorithmic_bytes": alg_bytes * n_fluid, "achieved_gbs": alg_bytes * n_fluid / (ms_launch * 1e-3) / 1e9,
+                       "frac": alg_bytes * n_fluid / (ms_launch * 1e-3) / 1e9 / hbm_peak}}
+        if cnt_f:
+            ent["hbm"]["dram_traffic_bytes_profile"] = cnt_f["dram_bytes"]
+            ent["hbm"]["dram_frac_profile"] = cnt_f["dram_bytes"] / (ms_launch * 1e-3) / 1e9 / hbm_peak
+            ent["fp64_pipe_busy_frac"] = cnt_f["fp64_pipe_busy_ms"] / sm_mhz_live / ms_launch
+            ent["profile_kernels"] = cnt_f["kernels"]
+            whole_busy += cnt_f["fp64_pipe_busy_ms"] / sm_mhz_live * tm["calls"] / args.steps
+        roofline_kernels.append(ent)
+    if whole_busy > 0:
+        roofline["step_fp64_pipe_busy_frac"] = whole_busy / (ms / args.steps)
     total_ms = sum(v["ms"] for v in timers.values())
     kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                    "share": v["ms"] / total_ms if total_ms > 0 else 0.0} for k, v in sorted(timers.items())}
@@ -570,7 +631,8 @@ def main():
                        "l2": "inputs larger than L2 (state + neighbour list >> 126 MB), no explicit flush"
                        if n_fluid > 2_000_000 else "working set may fit L2 (small workload)",
                        "parallelism": "slab%d" % world if world > 1 else "single"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(cnt[1].item()),
+            "roofline": roofline, "roofline_kernels": roofline_kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(cnt[1].item()),
             "clocks": clocks, "kernels": kernels,
         }
         if world > 1:

@@ -216,6 +216,7 @@ __global__ void k_init_level(Level S, const int* __restrict__ oidx, DevConst C, 
     S.b[i] = 0;
     S.surfzone[i] = 0;
     S.internal[i] = 0;
+    S.surf_i[i] = 0;
 }
 
 __global__ void k_identity_index(int* oidx, int* slot_of, int n)
@@ -318,6 +319,7 @@ __global__ void k_pack(Level S, StageView h, const int* __restrict__ slot_of, in
         if (h.lam_nb)
             q.w = h.lam_nb[c];
         S.P4[i] = r;
+        S.surf_i[i] = (r.w != 0.0) ? 1 : 0;
         S.NP[i] = q;
     }
     if (h.acc || h.Rrho)

@@ -48,7 +48,12 @@ constexpr size_t BOUNCE_BYTES = 1 << 16;
 
 struct FjsphNcclComm
 {
-    ncclComm_t comm = nullptr;
+    /* two communicators, as many ordering domains: NCCL serialises the operations of ONE communicator in the order the host
+       enqueues them, whatever streams they are on, so neighbour exchanges queued on the comm stream beside the sweeps and
+       all-reduces queued on the main stream must not share one -- a rank that (legitimately) enqueues the two kinds in the
+       other order than its neighbour would deadlock, and an exchange would wait for an all-reduce that waits for a sweep */
+    ncclComm_t comm = nullptr; /* collectives */
+    ncclComm_t p2p = nullptr;  /* ncclSend / ncclRecv between x-neighbours */
     int rank = 0, world = 1, device = 0;
     cudaStream_t main_stream = nullptr, comm_stream = nullptr, own_stream = nullptr;
     char* d_bounce = nullptr; /* device scratch for host-array ops: [send lo | send hi | recv lo | recv hi] quarters */
@@ -64,13 +69,13 @@ int sendrecv(FjsphNcclComm* c, cudaStream_t st, const void* a, int64_t na, const
 {
     NCCL_OK(ncclGroupStart());
     if (rc && nc > 0)
-        NCCL_OK(ncclRecv(rc, size_t(nc), ncclChar, c->rank - 1, c->comm, st));
+        NCCL_OK(ncclRecv(rc, size_t(nc), ncclChar, c->rank - 1, c->p2p, st));
     if (rd && nd > 0)
-        NCCL_OK(ncclRecv(rd, size_t(nd), ncclChar, c->rank + 1, c->comm, st));
+        NCCL_OK(ncclRecv(rd, size_t(nd), ncclChar, c->rank + 1, c->p2p, st));
     if (a && na > 0)
-        NCCL_OK(ncclSend(a, size_t(na), ncclChar, c->rank - 1, c->comm, st));
+        NCCL_OK(ncclSend(a, size_t(na), ncclChar, c->rank - 1, c->p2p, st));
     if (b && nb > 0)
-        NCCL_OK(ncclSend(b, size_t(nb), ncclChar, c->rank + 1, c->comm, st));
+        NCCL_OK(ncclSend(b, size_t(nb), ncclChar, c->rank + 1, c->p2p, st));
     NCCL_OK(ncclGroupEnd());
     return 0;
 }
@@ -150,11 +155,12 @@ const char* fjsph_nccl_last_error(void) { return g_err; }
 
 int fjsph_nccl_unique_id(char id[FJSPH_NCCL_ID_BYTES])
 {
-    static_assert(sizeof(ncclUniqueId) <= FJSPH_NCCL_ID_BYTES, "ncclUniqueId does not fit FJSPH_NCCL_ID_BYTES");
-    ncclUniqueId u;
-    NCCL_OK(ncclGetUniqueId(&u));
+    static_assert(2 * sizeof(ncclUniqueId) <= FJSPH_NCCL_ID_BYTES, "two ncclUniqueIds do not fit FJSPH_NCCL_ID_BYTES");
+    ncclUniqueId u[2]; /* one per communicator */
+    NCCL_OK(ncclGetUniqueId(&u[0]));
+    NCCL_OK(ncclGetUniqueId(&u[1]));
     std::memset(id, 0, FJSPH_NCCL_ID_BYTES);
-    std::memcpy(id, &u, sizeof(u));
+    std::memcpy(id, u, sizeof(u));
     return 0;
 }
 
@@ -170,9 +176,10 @@ int fjsph_nccl_create(const char id[FJSPH_NCCL_ID_BYTES], int32_t rank, int32_t 
     c->rank = rank;
     c->world = world;
     c->device = device;
-    ncclUniqueId u;
-    std::memcpy(&u, id, sizeof(u));
-    NCCL_OK(ncclCommInitRank(&c->comm, world, u, rank));
+    ncclUniqueId u[2];
+    std::memcpy(u, id, sizeof(u));
+    NCCL_OK(ncclCommInitRank(&c->comm, world, u[0], rank));
+    NCCL_OK(ncclCommInitRank(&c->p2p, world, u[1], rank));
     CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaMalloc(&c->d_bounce, BOUNCE_BYTES));
     CUDA_OK(cudaMallocHost(&c->h_bounce, BOUNCE_BYTES));
@@ -236,6 +243,8 @@ int fjsph_nccl_destroy(FjsphNcclComm* c)
         cudaFree(c->d_bounce);
     if (c->h_bounce)
         cudaFreeHost(c->h_bounce);
+    if (c->p2p)
+        ncclCommDestroy(c->p2p);
     if (c->comm)
         ncclCommDestroy(c->comm);
     delete c;

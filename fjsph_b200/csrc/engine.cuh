@@ -10,6 +10,8 @@
 //   ACC = {acc.xyz, Rrho}  AF = {Af.xyz, deltaD}  AV = {aVisc.xyz, curve}  CV = {cellV.xyz, cellP}
 //   NP = {normal.xyz, lam_nb}  BN = {bNorm.xyz, y}  TH = {p, m, woccl, cellRho}
 //   SC = {colourG, colour, kernsum, pDist}          L0..L8 = the 3x3 renormalisation matrix
+// surf_i mirrors the surf flag of P4 (0 / 1) as an int: the bulk ("lean") shifting sweep reads nothing else of P4, and a
+// 4-byte coalesced load costs an eighth of the L1 wavefronts of a strided 8-byte one.
 // Field list = SPHPart, reference src/Var.h:499-642.
 #pragma once
 #include <cuda_runtime.h>
@@ -31,7 +33,7 @@
     X(double4, TH) X(double4, SC)                                                                              \
     X(double, L0) X(double, L1) X(double, L2) X(double, L3) X(double, L4) X(double, L5) X(double, L6)          \
     X(double, L7) X(double, L8)                                                                                \
-    X(long long, part_id) X(int, cellID) X(int, b) X(int, surfzone) X(int, internal)
+    X(long long, part_id) X(int, cellID) X(int, b) X(int, surfzone) X(int, internal) X(int, surf_i)
 
 struct Level
 {

@@ -146,8 +146,9 @@ __global__ void k_pack_fields(D4Table T, const int* __restrict__ surfzone, const
     if (mask & FJ_HX_B)
         reinterpret_cast<int*>(buf + off)[k] = b[s];
 }
-__global__ void k_unpack_fields(D4Table T, int* __restrict__ surfzone, int* __restrict__ b, unsigned mask, int first_caller,
-                                const int* __restrict__ slot_of, int cnt, const char* __restrict__ buf)
+__global__ void k_unpack_fields(D4Table T, int* __restrict__ surfzone, int* __restrict__ b, int* __restrict__ surf_i,
+                                unsigned mask, int first_caller, const int* __restrict__ slot_of, int cnt,
+                                const char* __restrict__ buf)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt)
@@ -158,7 +159,10 @@ __global__ void k_unpack_fields(D4Table T, int* __restrict__ surfzone, int* __re
     for (int a = 0; a < 13; ++a)
         if (mask & (1u << a))
         {
-            T.p[a][s] = reinterpret_cast<const double4*>(buf + off)[k];
+            const double4 rec = reinterpret_cast<const double4*>(buf + off)[k];
+            T.p[a][s] = rec;
+            if (a == 4)
+                surf_i[s] = (rec.w != 0.0) ? 1 : 0; /* the int mirror of P4's surf flag (engine.cuh) */
             off += size_t(cnt) * sizeof(double4);
         }
     if (mask & FJ_HX_SURFZONE)
@@ -326,7 +330,7 @@ int fj_halo_exchange(FjsphEngine* e, int level, unsigned mask)
     for (int s = 0; s < 2; ++s)
     {
         if (S.n_recv[s] > 0)
-            k_unpack_fields<<<fj_blocks(S.n_recv[s], TPB), TPB, 0, cs>>>(T, L.surfzone, L.b, mask, first, e->slot_of,
+            k_unpack_fields<<<fj_blocks(S.n_recv[s], TPB), TPB, 0, cs>>>(T, L.surfzone, L.b, L.surf_i, mask, first, e->slot_of,
                                                                          int(S.n_recv[s]), S.rbuf[s]);
         first += int(S.n_recv[s]);
     }

@@ -185,6 +185,7 @@ __global__ void k_insert(Level S, int* __restrict__ oidx, int* __restrict__ blk,
     S.P2[s] = make_double4(0, 0, 0, th.x / (rho * rho));
     S.P3[s] = z;
     S.P4[s] = z;
+    S.surf_i[s] = 0;
     S.ACC[s] = z;
     S.AF[s] = z;
     S.AV[s] = z;

@@ -198,6 +198,9 @@ __device__ __forceinline__ double fj_rsqrt(double x)
 // 1/sqrt(x) for positive normal x with ONE third-order step on the MUFU.RSQ64H seed: y = y0 (1 + e/2 + 3 e^2 / 8),
 // e = 1 - x y0^2 (error ~ seed^3: full double precision) -- four dependent FP64 operations instead of the six of two
 // Newton steps, on the critical path of every pair
+#ifndef FJ_RSQRT3_POLISH
+#define FJ_RSQRT3_POLISH 0
+#endif
 __device__ __forceinline__ double fj_rsqrt3(double x)
 {
     double y0;
@@ -206,7 +209,13 @@ __device__ __forceinline__ double fj_rsqrt3(double x)
     const double e = fma(-t, y0, 1.0);
     const double p = fma(0.375, e, 0.5);
     const double ye = y0 * e;
-    return fma(ye, p, y0);
+    double y = fma(ye, p, y0);
+    if (FJ_RSQRT3_POLISH)
+    {
+        const double e2 = fma(-(x * y), y, 1.0);
+        y = fma(0.5 * y, e2, y);
+    }
+    return y;
 }
 
 // Geometry of one pair, branch-free and with a short dependency chain: Rji (current positions), rr = the list's d^2
@@ -246,12 +255,20 @@ __device__ __forceinline__ double wend_W_t(const DevConst& C, double t)
 }
 // 1 / x with ONE Newton step on the MUFU.RCP64H seed (~1e-12 relative): for the 1 / (r^2 + eps h^2) of the viscous and
 // density-diffusion terms, which are small corrections of the sums they enter
+#ifndef FJ_RCP1_STEPS
+#define FJ_RCP1_STEPS 1
+#endif
 __device__ __forceinline__ double fj_rcp1(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+#pragma unroll
+    for (int k = 0; k < FJ_RCP1_STEPS; ++k)
+    {
+        const double e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+    }
+    return y;
 }
 
 // Wendland C2 (Kernel.h:37-61).  t = 1 - q/2.  W = t^4 (2q+1) Wc ; GradK(R, r) = R * gk with
@@ -615,7 +632,10 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
             out.z = tz * inv;
         }
         if (active)
+        {
             S.P4[i] = out;
+            S.surf_i[i] = surf;
+        }
         if (near_warps)
         {
             /* how many warps hold a particle the lean surface / shifting sweep cannot take (k_surf23_shift, CLASS) */
@@ -791,7 +811,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
         [&](const unsigned j) {
             RecS2 q;
             if (CLASS == 1)
-                q.n.w = __ldg(&S.P4[j].w); /* the surf flag is all a lean particle reads of n_j */
+                q.n.w = double(__ldg(&S.surf_i[j])); /* the surf flag is all a lean particle reads of n_j */
             else
                 q.n = gather(S.P4, j);
             q.p = gather(S.P0, j);
@@ -809,8 +829,16 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
             pair(qb, tb);
         },
         [&](const unsigned first, const unsigned last) {
-            stage_l1(S.P4 + first);
-            stage_l1(S.P4 + last);
+            if (CLASS == 1)
+            {
+                stage_l1(S.surf_i + first);
+                stage_l1(S.surf_i + last);
+            }
+            else
+            {
+                stage_l1(S.P4 + first);
+                stage_l1(S.P4 + last);
+            }
             stage_l1(S.P0 + first);
             stage_l1(S.P0 + last);
             if (SHIFT)

@@ -158,6 +158,9 @@ class SlabEngine(eng.Engine):
         self.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"], **extra)
         self.transport = Transport(group=group)
         self.native = None
+        import os
+
+        transport = os.environ.get("FJSPH_B200_TRANSPORT", transport)  # "native" | "torch" | "auto"
         N = _lib.nccl_lib() if transport in ("auto", "native") and self.transport.backend == "nccl" and world > 1 else None
         if transport == "native" and N is None:
             raise RuntimeError("native NCCL transport requested but libfjsph_b200_nccl.so is not built / backend is not nccl")
@@ -165,9 +168,9 @@ class SlabEngine(eng.Engine):
             import torch
             import torch.distributed as dist
 
-            ident = torch.zeros(128, dtype=torch.uint8, device=self.transport.device)
+            ident = torch.zeros(256, dtype=torch.uint8, device=self.transport.device)
             if rank == 0:
-                buf = C.create_string_buffer(128)
+                buf = C.create_string_buffer(256)
                 if N.fjsph_nccl_unique_id(buf):
                     raise RuntimeError(N.fjsph_nccl_last_error().decode())
                 ident.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))

@@ -295,13 +295,14 @@ int fjsph_read_restart(FjsphEngine* e, const char* path, int32_t* frame);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Case front end (host only): GetInput + Init_Particles (reference src/IO.cpp:305-723, src/Init.cpp:270-496,
- * src/shapes/{shapes,line,square,circle,cylinder,inlet,coordinates}.cpp).  Reads a FJSPH para file and the fluid /
+ * src/shapes/{shapes,line,square,circle,cylinder,arc,inlet,coordinates}.cpp).  Reads a FJSPH para file and the fluid /
  * boundary block files (bmap) it names, generates every block's particles with the reference's perturbation stream
  * (std::default_random_engine through uniform_real_distribution(0, eps dx)), removes intersecting particles
  * (Check_Intersection) and lays the particles out in the reference's order: boundary blocks first, then fluid blocks,
  * inlet blocks as PIPE layers | BACK row | BUFFER rows with their back / buffer tables.  dim is the SIMDIM of the
  * build the deck was written for (shape names differ: Line/Plane, Square/Cube, Circle/Sphere); xi and v of
- * fjsph_case_state are [n][dim].  Arc/Arch blocks and JSON block files are rejected. */
+ * fjsph_case_state are [n][dim].  Arc / Arch blocks (shapes/arc.cpp) and JSON block files (the reference's JSON keys, blocks
+ * in key order) are read as well; what arc.cpp answers with exit() is an error return here. */
 typedef struct FjsphCase FjsphCase;
 int fjsph_case_read(const char* para_path, int dim, FjsphCase** out);
 void fjsph_case_free(FjsphCase* c);

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FJSPH_NCCL_ID_BYTES 128
+#define FJSPH_NCCL_ID_BYTES 256 /* two ncclUniqueIds: one communicator for the collectives, one for the neighbour exchanges */
 typedef struct FjsphNcclComm FjsphNcclComm;
 
 int fjsph_nccl_unique_id(char id[FJSPH_NCCL_ID_BYTES]); /* ncclGetUniqueId, on one rank */

@@ -82,8 +82,8 @@ def test_c3_standing_column_one_million():
 def test_c4_crossflow_deck_coupled_to_a_tau_mesh(tmp_path):
     """BASELINE.json configs[3]: Examples/Crossflow (3D) at the reference's own numbers (tests/decks/crossflow3d.para: round
     dynamic inlet, hollow Ghost pipe, 43 k particles at 3e-5 spacing, Gissler aero) coupled to a TAU mesh: the mesh and its
-    solution are written as NetCDF-3 files and read back by fjsph_tau_read.  (i) 5 steps against the oracle with the mesh;
-    (ii) a uniform solution equal to the deck's free stream reproduces the constant-free-stream run."""
+    solution are written as NetCDF-3 files and read back by fjsph_tau_read.  (i) four steps against the oracle with the mesh;
+    (ii) run on until the jet has left the pipe: the particles the lookup finds carry the mesh's (uniform) solution."""
     from tests.tau_case import write_tau
 
     case = frontend.read_case(os.path.join(DECKS, "crossflow3d.para"), 3)
@@ -110,27 +110,26 @@ def test_c4_crossflow_deck_coupled_to_a_tau_mesh(tmp_path):
         # the deck's lattice + U(0, eps dx) positions are a tie-stress input: the bars of tests/test_gpu_decks.py
         assert relerr(got["xi"], o.get("xi")) <= 1e-6 and relerr(got["rho"], o.get("rho")) <= 1e-6, ctx
         assert relerr(got["v"], o.get("v")) <= 1e-4, ctx
-    # (ii) the jet leaves the pipe, crosses the aero entry plane (PIPE -> FREE, FirstCell) and meets the cross flow: the run
-    # coupled to the uniform mesh against the same deck on the constant free stream, engine against engine
-    _, e0 = make_pair_from_deck(case, kind="3d_mt", asource=0)
-    _, e1 = make_pair_from_deck(case, kind="3d_mt", asource=1)
-    e1.upload_mesh(tau)
+    # (ii) the jet leaves the pipe, crosses the aero entry plane (PIPE -> FREE, FirstCell on the device) and meets the cross
+    # flow: every FREE particle the lookup placed in a cell carries that cell's solution -- here the uniform free stream --
+    # and feels the Gissler drag.  (The constant-free-stream run is NOT the same run on this deck: get_aero_velocity zeroes
+    # cellV of the PIPE / BUFFER particles every step there, the mesh branch leaves them alone, Resid.cpp:478-611, and the
+    # aero term is evaluated for both, Resid.cpp:267-277.)
     n_add = 0
     for step in range(400):
-        s1 = e1.integrate()
-        s0 = e0.integrate()
-        assert (s0.n_add, s0.n_del, s0.total_points, s0.iterations) == (s1.n_add, s1.n_del, s1.total_points, s1.iterations), step
+        s1 = e.integrate()
         n_add += s1.n_add
-        if step % 20 == 19 and (e1.download(("b",))["b"] == cases.FREE).sum() > 200:
+        if step % 20 == 19 and (e.download(("b",))["b"] == cases.FREE).sum() > 200:
             break
-    a = e1.download(("xi", "v", "rho", "acc", "Af", "b", "part_id", "cellID"))
-    b = e0.download(("xi", "v", "rho", "acc", "Af", "b", "part_id"))
-    assert np.array_equal(a["part_id"], b["part_id"]) and np.array_equal(a["b"], b["b"])
+    a = e.download(("xi", "v", "rho", "Af", "b", "cellID", "cellV", "cellP", "cellRho"))
     free = a["b"] == cases.FREE
-    assert free.sum() > 200 and n_add > 0 and np.abs(a["Af"][free]).max() > 0.0  # particles did reach the cross flow
-    assert (a["cellID"][free] >= 0).sum() > 0                                      # ... and were found in mesh cells
-    for f, tol in (("xi", 1e-10), ("rho", 1e-10), ("v", 1e-8), ("acc", 1e-6), ("Af", 1e-6)):
-        assert relerr(a[f], b[f]) <= tol, (f, relerr(a[f], b[f]))
+    found = free & (a["cellID"] >= 0)
+    assert free.sum() > 200 and n_add > 0 and found.sum() > 100, (free.sum(), n_add, found.sum())
+    assert a["cellID"][found].max() < 9 * 11 * 8
+    assert np.abs(a["cellV"][found] - np.asarray(vinf)).max() <= 1e-12 * max(abs(v) for v in vinf)
+    assert np.abs(a["cellP"][found] - pref).max() <= 1e-9 * pref and np.abs(a["cellRho"][found] - rhog).max() <= 1e-12 * rhog
+    assert np.isfinite(a["Af"]).all() and np.abs(a["Af"][found]).max() > 0.0 and np.isfinite(a["xi"]).all()
+    assert a["Af"][found][:, 0].mean() > 0.0  # the cross flow pushes along +x
 
 
 def test_key_table_doubling_and_wide_rows(monkeypatch):
