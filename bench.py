@@ -382,10 +382,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    parity = None
-    if world > 1 and not args.no_check:
-        parity = slab_parity(rank, world, local_rank)
-
     case = make_case(args, rank)
     params = step_params(args, case["params"])
     n = case["xi"].shape[0]
@@ -619,6 +615,16 @@ def main():
         sx = max(16, n_cells[0] // world)
         extras["strong"] = dict(time_slab_workload(args, rank, world, local_rank, "block", "%d,%d,%d" % (sx, n_cells[1], n_cells[2]),
                                                    5, 3), scaling="strong")
+
+    parity = None
+    if world > 1 and not args.no_check:
+        # after every timed region: the check builds and frees several engines, and a measurement taken after it ran 2.3x
+        # slower (profiles/r2e_bench_n2_after_check.json) -- fragmented device memory is the suspect
+        if not extras:
+            e.close()
+            del e
+            torch.cuda.empty_cache()
+        parity = slab_parity(rank, world, local_rank)
 
     if rank == 0:
         line = {

@@ -587,12 +587,14 @@ extern "C" int fjsph_set_slab(FjsphEngine* e, int32_t rank, int32_t world, doubl
         return st;
     S.n_fluid_global = v[0];
     S.n_total_global = v[1];
-    /* ids of particles an inlet adds later must be unique over all ranks: count from the global total */
+    /* ids of particles an inlet adds later must be unique over all ranks, and the ones a single engine would hand out:
+       count from the global total, or from one past the highest id any rank holds if the host supplied ids beyond it
+       (fjsph_upload_state keeps next_part_id = max(n, max id + 1): the reference's counter only grows) */
     double ids = double(e->next_part_id);
-    st = fj_allreduce(e, FJSPH_COMM_SUM, &ids, 1);
+    st = fj_allreduce(e, FJSPH_COMM_MAX, &ids, 1);
     if (st)
         return st;
-    e->next_part_id = (long long)ids;
+    e->next_part_id = std::max((long long)ids, (long long)S.n_total_global);
     return FJSPH_OK;
 }
 

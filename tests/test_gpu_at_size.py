@@ -115,16 +115,19 @@ def test_c4_crossflow_deck_coupled_to_a_tau_mesh(tmp_path):
     # and feels the Gissler drag.  (The constant-free-stream run is NOT the same run on this deck: get_aero_velocity zeroes
     # cellV of the PIPE / BUFFER particles every step there, the mesh branch leaves them alone, Resid.cpp:478-611, and the
     # aero term is evaluated for both, Resid.cpp:267-277.)
-    n_add = 0
-    for step in range(400):
+    n_add, t_sim = 0, 0.0
+    for step in range(1500):
         s1 = e.integrate()
         n_add += s1.n_add
+        t_sim += s1.dt
         if step % 20 == 19 and (e.download(("b",))["b"] == cases.FREE).sum() > 200:
             break
     a = e.download(("xi", "v", "rho", "Af", "b", "cellID", "cellV", "cellP", "cellRho"))
     free = a["b"] == cases.FREE
     found = free & (a["cellID"] >= 0)
-    assert free.sum() > 200 and n_add > 0 and found.sum() > 100, (free.sum(), n_add, found.sum())
+    diag = dict(steps=step + 1, t=t_sim, dt=s1.dt, free=int(free.sum()), found=int(found.sum()), n_add=n_add,
+                ymax=float(a["xi"][:, 1].max()), cell_ids=np.unique(a["cellID"])[:8].tolist())
+    assert free.sum() > 200 and n_add > 0 and found.sum() > 100, diag
     assert a["cellID"][found].max() < 9 * 11 * 8
     assert np.abs(a["cellV"][found] - np.asarray(vinf)).max() <= 1e-12 * max(abs(v) for v in vinf)
     assert np.abs(a["cellP"][found] - pref).max() <= 1e-9 * pref and np.abs(a["cellRho"][found] - rhog).max() <= 1e-12 * rhog
