@@ -115,17 +115,28 @@ def test_c4_crossflow_deck_coupled_to_a_tau_mesh(tmp_path):
     # and feels the Gissler drag.  (The constant-free-stream run is NOT the same run on this deck: get_aero_velocity zeroes
     # cellV of the PIPE / BUFFER particles every step there, the mesh branch leaves them alone, Resid.cpp:478-611, and the
     # aero term is evaluated for both, Resid.cpp:267-277.)
-    n_add, t_sim = 0, 0.0
-    for step in range(1500):
-        s1 = e.integrate()
-        n_add += s1.n_add
-        t_sim += s1.dt
-        if step % 20 == 19 and (e.download(("b",))["b"] == cases.FREE).sum() > 200:
+    # The deck's frame interval (1e-6 s) is a few steps long and find_timestep clamps dt to what is left of the frame
+    # (Integration.cpp:433-440), so the host marches the frames as FJSPH's main does (FJSPH.cpp:262-330): step until the
+    # frame is full, then last_frame_time += frame_time_interval.
+    n_add, t_sim, step = 0, 0.0, 0
+    dt_min, frame_dt = e.params.delta_t_min, e.params.frame_time_interval
+    stept = e.params.current_time - e.params.last_frame_time  # part (i) ran inside the first frame
+    for frame in range(60):
+        while stept + 0.1 * dt_min < frame_dt:
+            s1 = e.integrate()
+            n_add += s1.n_add
+            stept += s1.dt
+            step += 1
+            assert s1.dt > 0.0 and step < 1500, (frame, step, s1.dt)
+        t_sim += stept
+        stept = 0.0
+        e.set_params(last_frame_time=e.params.last_frame_time + frame_dt)
+        if (e.download(("b",))["b"] == cases.FREE).sum() > 200:
             break
     a = e.download(("xi", "v", "rho", "Af", "b", "cellID", "cellV", "cellP", "cellRho"))
     free = a["b"] == cases.FREE
     found = free & (a["cellID"] >= 0)
-    diag = dict(steps=step + 1, t=t_sim, dt=s1.dt, free=int(free.sum()), found=int(found.sum()), n_add=n_add,
+    diag = dict(steps=step, frames=frame + 1, t=t_sim, dt=s1.dt, free=int(free.sum()), found=int(found.sum()), n_add=n_add,
                 ymax=float(a["xi"][:, 1].max()), cell_ids=np.unique(a["cellID"])[:8].tolist())
     assert free.sum() > 200 and n_add > 0 and found.sum() > 100, diag
     assert a["cellID"][found].max() < 9 * 11 * 8

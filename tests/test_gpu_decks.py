@@ -68,8 +68,10 @@ def test_arch_deck_steps():
     input: lam, the smallest eigenvalue of L, is a repeated eigenvalue for edge and face particles there, where Eigen's
     closed form takes the square root of an exact cancellation, so a last-bit difference in L (the engine sums its
     neighbours row by row, the reference in KD-tree order) moves lam by sqrt(eps) ~ 1.5e-8 (tests/test_gpu_parity.py,
-    TOL_EIGEN_DEGENERATE), and lam feeds the surface normals and the shifting velocity.  Flags, counts and dt exact; state
-    to 1e-8, rates to 1e-4.  The same deck on generic positions holds the tight bars: next test."""
+    TOL_EIGEN_DEGENERATE), and lam feeds the surface normals and the shifting velocity.  Measured on a B200
+    (profiles/r2h_arch_probe.txt, tools/arch_probe.py): lam 1.8e-8, xi 3.7e-10, rho 9.8e-8, p 6e-5 (the stiff EOS on rho),
+    v 9e-6, rates 1.3e-4 after 4 x 20 sub-iterations; every flag, count and dt exact.  Bars one decade above that.  The same
+    deck on generic positions holds the tight bars (xi 3e-17, rho 2e-16, rates 6e-13 measured): next test."""
     o, e = _arch_pair(0.0)
     for step in range(4):
         _, so = o.integrate()
@@ -77,9 +79,12 @@ def test_arch_deck_steps():
         assert se.iterations == so.iterations and abs(se.dt - so.dt) <= 1e-12 * so.dt, step
         assert se.total_points == so.total_points
     assert_fields_close(e, o, ("surf", "surfzone", "b", "part_id"), context="arch deck")
-    assert_fields_close(e, o, ("xi", "rho", "p"), tol=1e-8, context="arch deck")
-    assert_fields_close(e, o, ("v",), tol=1e-6, context="arch deck")
-    assert_fields_close(e, o, ("acc", "Rrho"), tol=1e-4, context="arch deck")
+    assert_fields_close(e, o, ("lam",), tol=2e-7, context="arch deck")
+    assert_fields_close(e, o, ("xi",), tol=1e-8, context="arch deck")
+    assert_fields_close(e, o, ("rho",), tol=1e-6, context="arch deck")
+    assert_fields_close(e, o, ("p",), tol=1e-3, context="arch deck")
+    assert_fields_close(e, o, ("v",), tol=1e-4, context="arch deck")
+    assert_fields_close(e, o, ("acc", "Rrho"), tol=2e-3, context="arch deck")
 
 
 def test_arch_deck_steps_generic_positions():

@@ -143,4 +143,16 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:
+        # a failed check on one rank must not leave the others waiting in a collective until the watchdog fires:
+        # leave at once, without the interpreter's teardown (which joins NCCL), and let the launcher stop the rest
+        import traceback
+
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
