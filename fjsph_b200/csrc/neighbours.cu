@@ -563,6 +563,15 @@ static int rebuild_skin(FjsphEngine* e)
     for (int d = 1; d < 3; ++d)
         if (hi[d] - lo[d] > 1.0001 * (hi[ax0] - lo[ax0]))
             ax0 = d;
+    /* slab mode cuts the fluid along x into interior | edge | ghost classes, each with rows of its own: rows along x would
+       be a handful of particles long in the edge and ghost classes (2H + skin wide), leaving most lanes of their warps
+       idle, so the rows run along the longer transverse axis whenever that is long enough to fill warps */
+    if (e->slab.on && e->slab.world > 1)
+    {
+        const int t = (hi[2] - lo[2] > 1.0001 * (hi[1] - lo[1])) ? 2 : 1;
+        if (e->P.particle_step > 0.0 && hi[t] - lo[t] >= 64.0 * e->P.particle_step)
+            ax0 = t;
+    }
     if (e->row_axis >= 0 && e->row_axis < 3)
         ax0 = e->row_axis;
     g.ax0 = ax0;

@@ -85,8 +85,31 @@ __device__ __forceinline__ void stage_l1(const void* gptr)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void stage_l1_drain() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// What a warp stages of one record array for the slot after the current one.  FJ_STAGE_MODE 1 (default): every lane the
+// first and the last record of its own window.  2: first / last are the WARP's bounds and lane l touches the l-th 128-byte
+// line of the stretch between them (one copy per line instead of two per lane).  0: nothing.  Measured (profiles/
+// r2k_sweep_variants.txt): 1 beats 0 by 7 % and 2 by 10 % on the whole step.
+#ifndef FJ_STAGE_MODE
+#define FJ_STAGE_MODE 1
+#endif
+template <class T>
+__device__ __forceinline__ void stage_span(const T* base, unsigned first, unsigned last)
+{
+#if FJ_STAGE_MODE == 1
+    stage_l1(base + first);
+    stage_l1(base + last);
+#elif FJ_STAGE_MODE == 2
+    const unsigned long long a0 = (unsigned long long)(base + first) & ~127ull;
+    const unsigned long long p = a0 + (threadIdx.x & 31u) * 128ull;
+    if (p < (unsigned long long)(base + last + 1u))
+        stage_l1((const void*)p);
+#endif
+}
 
-template <class Load, class Body, class StageFn>
+// CLAMP: a lane with nobody to visit at a step of a slot it has a window in re-reads the LAST record of that window (a line
+// its neighbouring lanes read at the same step) instead of its own record; the body must then mask the pair by `take`
+// (own-index zeros no longer do it).
+template <bool CLAMP = false, class Load, class Body, class StageFn>
 __device__ __forceinline__ void for_neighbours2(const RunView& L, int W, bool active, unsigned self, Load&& load,
                                                 Body&& body, StageFn&& stage)
 {
@@ -114,8 +137,19 @@ __device__ __forceinline__ void for_neighbours2(const RunView& L, int W, bool ac
             if (k + 1 < nrow)
                 dnn = ld_desc(dp + size_t(k + 1) * 32u);
             T = __reduce_max_sync(FJ_FULL, 32 - __clz(int(d.y)));
+#if FJ_STAGE_MODE == 2
+            if (k < nrow)
+            {
+                const bool any = active && dn.y != 0u;
+                const unsigned lo = __reduce_min_sync(FJ_FULL, any ? dn.x : 0xFFFFFFFFu);
+                const unsigned hi = __reduce_max_sync(FJ_FULL, any ? dn.x + unsigned(31 - __clz(int(dn.y))) : 0u);
+                if (lo <= hi)
+                    stage(lo, hi);
+            }
+#else
             if (k < nrow && active && dn.y != 0u) /* the records of the slot after this one */
                 stage(dn.x, dn.x + unsigned(31 - __clz(int(dn.y))));
+#endif
             if (T > 0)
                 return true;
         }
@@ -134,7 +168,10 @@ __device__ __forceinline__ void for_neighbours2(const RunView& L, int W, bool ac
             o = 0;
         }
         take = ((d.y >> o) & 1u) != 0u;
-        j = take ? d.x + unsigned(o) : self;
+        if (CLAMP)
+            j = d.y != 0u ? d.x + min(unsigned(o), unsigned(31 - __clz(int(d.y)))) : self;
+        else
+            j = take ? d.x + unsigned(o) : self;
         return true;
     };
     o = -1;
@@ -367,16 +404,12 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
                 pair(qb, tb);
             },
             [&](const unsigned first, const unsigned last) {
-                stage_l1(S.P0 + first);
-                stage_l1(S.P0 + last);
-                stage_l1(S.P1 + first);
-                stage_l1(S.P1 + last);
-                stage_l1(S.b + first);
-                stage_l1(S.b + last);
+                stage_span(S.P0, first, last);
+                stage_span(S.P1, first, last);
+                stage_span(S.b, first, last);
                 if (FROZEN)
                 {
-                    stage_l1(lv.x0 + first);
-                    stage_l1(lv.x0 + last);
+                    stage_span(lv.x0, first, last);
                 }
             });
         if (active)
@@ -600,21 +633,16 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
             }
         },
         [&](const unsigned first, const unsigned last) {
-            stage_l1(S.P0 + first);
-            stage_l1(S.P0 + last);
-            stage_l1(S.P3 + first);
-            stage_l1(S.P3 + last);
+            stage_span(S.P0, first, last);
+            stage_span(S.P3, first, last);
             if (DISS)
             {
-                stage_l1(S.P1 + first);
-                stage_l1(S.P1 + last);
-                stage_l1(S.b + first);
-                stage_l1(S.b + last);
+                stage_span(S.P1, first, last);
+                stage_span(S.b, first, last);
             }
             if (FROZEN)
             {
-                stage_l1(lv.x0 + first);
-                stage_l1(lv.x0 + last);
+                stage_span(lv.x0, first, last);
             }
         });
     if (SURF)
@@ -831,27 +859,21 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
         [&](const unsigned first, const unsigned last) {
             if (CLASS == 1)
             {
-                stage_l1(S.surf_i + first);
-                stage_l1(S.surf_i + last);
+                stage_span(S.surf_i, first, last);
             }
             else
             {
-                stage_l1(S.P4 + first);
-                stage_l1(S.P4 + last);
+                stage_span(S.P4, first, last);
             }
-            stage_l1(S.P0 + first);
-            stage_l1(S.P0 + last);
+            stage_span(S.P0, first, last);
             if (SHIFT)
             {
-                stage_l1(S.P1 + first);
-                stage_l1(S.P1 + last);
-                stage_l1(S.b + first);
-                stage_l1(S.b + last);
+                stage_span(S.P1, first, last);
+                stage_span(S.b, first, last);
             }
             if (FROZEN)
             {
-                stage_l1(lv.x0 + first);
-                stage_l1(lv.x0 + last);
+                stage_span(lv.x0, first, last);
             }
         });
     if (CLASS == 1 && has_fluid)
@@ -1088,8 +1110,15 @@ struct RecF
 //   continuity  Kernel.h:187-196                   Rrho_    -= V_j ((u + w_j - w_i).gK)     = -(u.G + w_j.G) + w_i.G
 //                                                  Rrhoc_   += V_j (rho_j w_j.gK + rho_i w_i.gK) = rho_j (w_j.G) + rho_i (w_i.G)
 // The w_i.G terms are linear in G, so sum_j G is accumulated once and w_i applied after the loop.
+// experiment knobs of the force sweep, both measured and left off (profiles/r2k_sweep_variants.txt)
+#ifndef FJ_FORCE_CLAMP
+#define FJ_FORCE_CLAMP 0
+#endif
+#ifndef FJ_FORCE_MINB
+#define FJ_FORCE_MINB min_blocks(WARPS, false)
+#endif
 template <bool ALE, bool FROZEN, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
+__global__ void __launch_bounds__(WARPS * 32, FJ_FORCE_MINB)
     k_force(Level S, RunView lv, RowMap M, const int* __restrict__ blk, int n_bound_blocks, DevConst C, double npdm2)
 {
     int i, W;
@@ -1142,11 +1171,13 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
     }
 
     /* one pair, branch-free (a lane's own index as j gives exact zeros: Rji = 0, gradK = 0) */
-    auto pair_main = [&](const RecF& q, PairGeo& g) {
+    auto pair_main = [&](const RecF& q, PairGeo& g, const bool take) {
         const double4 pj = q.p;
         const double4 vj = q.v;
         const double4 qj = q.q;
         g = pair_geo<FROZEN>(C, pi, x0i, pj, q.x0);
+        if (FJ_FORCE_CLAMP && !take)
+            g.gk = 0.0; /* every term below carries gk */
         const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
         const double idist2 = fj_rcp1(g.rr + eps_f);
         const double rho_j = vj.w;
@@ -1186,7 +1217,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         sy = fma(sf, g.ry, sy);
         sz = fma(sf, g.rz, sz);
     };
-    for_neighbours2(
+    for_neighbours2<FJ_FORCE_CLAMP != 0>(
         lv, W, active, unsigned(i),
         [&](const unsigned j) {
             RecF q;
@@ -1201,8 +1232,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         },
         [&](const RecF& qa, const bool ta, const RecF& qb, const bool tb) {
             PairGeo ga, gb;
-            pair_main(qa, ga);
-            pair_main(qb, gb);
+            pair_main(qa, ga, ta);
+            pair_main(qb, gb, tb);
             if (do_st)
             {
                 pair_st(qa, ga, ta);
@@ -1210,21 +1241,16 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
             }
         },
         [&](const unsigned first, const unsigned last) {
-            stage_l1(S.P0 + first);
-            stage_l1(S.P0 + last);
-            stage_l1(S.P1 + first);
-            stage_l1(S.P1 + last);
-            stage_l1(S.P2 + first);
-            stage_l1(S.P2 + last);
+            stage_span(S.P0, first, last);
+            stage_span(S.P1, first, last);
+            stage_span(S.P2, first, last);
             if (do_st)
             {
-                stage_l1(S.b + first);
-                stage_l1(S.b + last);
+                stage_span(S.b, first, last);
             }
             if (FROZEN)
             {
-                stage_l1(lv.x0 + first);
-                stage_l1(lv.x0 + last);
+                stage_span(lv.x0, first, last);
             }
         });
     if (ALE)
