@@ -139,13 +139,19 @@ void fj_refresh_constants(FjsphEngine* e)
     C.asource = P.asource;
     C.use_lam = P.use_lam;
     C.use_TAB_def = P.use_TAB_def;
+    C.dim = P.dim;
 }
 
 static int validate_params(const FjsphParams& P)
 {
-    if (P.dim != 3)
+    if (P.dim != 2 && P.dim != 3)
     {
-        fj_set_error("the device path supports SIMDIM=3 only (got dim=%d)", P.dim);
+        fj_set_error("dim must be 2 or 3 (got %d)", P.dim);
+        return FJSPH_ERR_INVALID;
+    }
+    if (P.dim == 2 && (P.grav[2] != 0.0 || P.v_inf[2] != 0.0))
+    {
+        fj_set_error("SIMDIM=2: the third component of gravity and of the free stream must be 0");
         return FJSPH_ERR_INVALID;
     }
     if (!(P.H > 0.0) || !(P.sr > 0.0) || !(P.W_correc > 0.0))

@@ -53,6 +53,7 @@ struct DevConst
     double lam_cutoff, interp_fac, i_n_full, aero_L, A_sphere, A_plate, mu_g, sos2, gamma_g, ycoef, tab_Cb;
     double max_shift_vel, bnd_mass, sim_mass, c_sound, rho_g;
     int ale, pressure_rel, acase, asource, use_lam, use_TAB_def;
+    int dim; /* 2: SIMDIM=2, every z component exactly 0 (records keep their three components) */
 };
 
 // Cell grid in ROW coordinates (u, v, w): u = the row axis (the longest extent of the particles' bounding box, component

@@ -142,7 +142,7 @@ int main(int argc, char** argv)
 static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
 {
     const char* para = argv[1];
-    int frames_cli = -1, device = 0;
+    int frames_cli = -1, device = 0, dim = 3;
     bool quiet = false;
     std::string restart_file, prefix_cli;
     for (int a = 2; a < argc; ++a)
@@ -154,6 +154,8 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
             frames_cli = std::atoi(argv[++a]);
         else if (a + 1 < argc && k == "--device")
             device = std::atoi(argv[++a]);
+        else if (a + 1 < argc && k == "--dim") /* the SIMDIM of the build the deck was written for (makefile: 2D / 3D targets) */
+            dim = std::atoi(argv[++a]);
         else if (a + 1 < argc && k == "--restart")
             restart_file = argv[++a];
         else if (a + 1 < argc && k == "--out")
@@ -167,7 +169,12 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
         }
     }
     FjsphCase* c = nullptr;
-    if (fjsph_case_read(para, 3, &c))
+    if (dim != 2 && dim != 3)
+    {
+        std::fprintf(stderr, "--dim must be 2 or 3\n");
+        return 2;
+    }
+    if (fjsph_case_read(para, dim, &c))
         return fail("reading the case");
     FjsphParams P;
     fjsph_case_params(c, &P);
@@ -244,6 +251,14 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
         s.part_id = pid.data();
         if (fjsph_case_state(c, &s))
             return fail("reading the particles of the case");
+        if (dim == 2) /* the case holds [n][2] vectors; the engine's view is [n][3] with z = 0 */
+            for (int64_t i = n_case - 1; i >= 0; --i)
+            {
+                const size_t k = size_t(i);
+                const double x0 = xi[2 * k], x1 = xi[2 * k + 1], v0 = v[2 * k], v1 = v[2 * k + 1];
+                xi[3 * k] = x0, xi[3 * k + 1] = x1, xi[3 * k + 2] = 0.0;
+                v[3 * k] = v0, v[3 * k + 1] = v1, v[3 * k + 2] = 0.0;
+            }
         const int32_t nblk = fjsph_case_num_blocks(c);
         std::vector<FjsphBlock> blocks(nblk);
         for (int32_t i = 0; i < nblk; ++i) fjsph_case_block(c, i, &blocks[i], nullptr, 0);

@@ -408,6 +408,11 @@ void fj_free_mesh(FjsphEngine* e)
 
 extern "C" int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m)
 {
+    if (e && e->P.dim == 2)
+    {
+        fj_set_error("upload_mesh: SIMDIM=2 aero meshes (Crossings2D, TAU edge meshes) are not on the device path");
+        return FJSPH_ERR_INVALID;
+    }
     cudaSetDevice(e->device);
     if (!m || m->n_cells <= 0 || m->n_faces <= 0 || !m->verts || !m->face_ptr || !m->face_vtx || !m->leftright ||
         !m->cell_ptr || !m->cell_faces || !m->cCentre || !m->cVel || !m->cP || !m->cRho)

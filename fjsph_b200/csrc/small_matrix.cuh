@@ -206,3 +206,95 @@ __device__ __forceinline__ double fj_min_eig3(double a00, double a10, double a11
     const double r2 = c2_over_3 + 2.0 * rho * cos_theta;
     return fmin(r0, fmin(r1, r2)) * scale + shift;
 }
+
+// ---- SIMDIM = 2 (reference src/VarDefs.h:29-41): the same two Eigen algorithms on 2x2 matrices.
+// ColPivHouseholderQR<2x2>::isInvertible / inverse, restated like the 3x3 form above (thresholds scale with n = 2).
+__device__ __forceinline__ int fj_qr_inverse2(const double (&a)[2][2], double (&inv)[2][2])
+{
+    double q00 = a[0][0], q01 = a[0][1], q10 = a[1][0], q11 = a[1][1];
+    int p0 = 0, p1 = 1;
+    const double n0 = q00 * q00 + q10 * q10, n1 = q01 * q01 + q11 * q11;
+    const double maxcol = fmax(sqrt(n0), sqrt(n1));
+    const double th = maxcol * DBL_EPSILON / 2.0;
+    const double thr_helper = th * th;
+    int nonzero_pivots = 2;
+    /* k = 0: pivot on the larger column (the first one on a tie) */
+    double bigsq = n0;
+    if (n1 > n0)
+    {
+        double t = q00; q00 = q01; q01 = t;
+        t = q10; q10 = q11; q11 = t;
+        p0 = 1; p1 = 0;
+        bigsq = n1;
+    }
+    if (bigsq < thr_helper * 2.0)
+        nonzero_pivots = 0;
+    double tau0, beta0;
+    {
+        const double c0 = q00, tailsq = q10 * q10;
+        if (tailsq <= DBL_MIN)
+        {
+            tau0 = 0.0;
+            beta0 = c0;
+            q10 = 0.0;
+        }
+        else
+        {
+            beta0 = sqrt(c0 * c0 + tailsq);
+            if (c0 >= 0.0)
+                beta0 = -beta0;
+            q10 *= 1.0 / (c0 - beta0);
+            tau0 = (beta0 - c0) / beta0;
+        }
+        q00 = beta0;
+        double s = q01 + q10 * q11;
+        s *= tau0;
+        q01 -= s;
+        q11 -= s * q10;
+    }
+    /* k = 1: one column, one row left */
+    if (nonzero_pivots == 2 && q11 * q11 < thr_helper * 1.0)
+        nonzero_pivots = 1;
+    const double maxpivot = fmax(fabs(q00), fabs(q11));
+    const double premult = maxpivot * (DBL_EPSILON * 2.0);
+    int rank = 0;
+    if (0 < nonzero_pivots && fabs(q00) > premult)
+        rank++;
+    if (1 < nonzero_pivots && fabs(q11) > premult)
+        rank++;
+    if (rank != 2)
+        return 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+    {
+        double r0 = (c == 0) ? 1.0 : 0.0, r1 = (c == 1) ? 1.0 : 0.0;
+        double s = r0 + q10 * r1;
+        s *= tau0;
+        r0 -= s;
+        r1 -= s * q10;
+        /* the second reflector has no essential part: tau = 0 */
+        r1 = r1 / q11;
+        r0 = (r0 - q01 * r1) / q00;
+        inv[p0][c] = r0;
+        inv[p1][c] = r1;
+    }
+    return 1;
+}
+
+// Minimum eigenvalue of a symmetric 2x2 (lower triangle): Eigen 3.4 direct_selfadjoint_eigenvalues<2x2> after the shift by
+// trace / 2 and the scaling by max|a_ij|.
+__device__ __forceinline__ double fj_min_eig2(double a00, double a10, double a11)
+{
+    const double shift = (a00 + a11) / 2.0;
+    double m00 = a00 - shift, m11 = a11 - shift, m10 = a10;
+    const double scale = fmax(fabs(m00), fmax(fabs(m11), fabs(m10)));
+    if (scale > 0.0)
+    {
+        m00 /= scale;
+        m11 /= scale;
+        m10 /= scale;
+    }
+    const double t0 = 0.5 * sqrt((m00 - m11) * (m00 - m11) + 4.0 * m10 * m10);
+    const double t1 = 0.5 * (m00 + m11);
+    return (t1 - t0) * scale + shift;
+}

@@ -416,13 +416,29 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
         {
         double Lm[3][3] = {{l00, l01, l02}, {l01, l11, l12}, {l02, l12, l22}};
         double Li[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-        double tmp[3][3];
-        if (fj_qr_inverse3(Lm, tmp))
+        if (C.dim == 2)
         {
+            /* SIMDIM = 2: L is 2 x 2 (every z term above is an exact zero); the third row and column stay the identity's */
+            const double L2[2][2] = {{l00, l01}, {l01, l11}};
+            double t2[2][2];
+            if (fj_qr_inverse2(L2, t2))
+            {
+                Li[0][0] = t2[0][0];
+                Li[0][1] = t2[0][1];
+                Li[1][0] = t2[1][0];
+                Li[1][1] = t2[1][1];
+            }
+        }
+        else
+        {
+            double tmp[3][3];
+            if (fj_qr_inverse3(Lm, tmp))
+            {
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+                for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) Li[a][c] = tmp[a][c];
+                    for (int c = 0; c < 3; ++c) Li[a][c] = tmp[a][c];
+            }
         }
         const double gr0 = Li[0][0] * g0 + Li[0][1] * g1 + Li[0][2] * g2;
         const double gr1 = Li[1][0] * g0 + Li[1][1] * g1 + Li[1][2] * g2;
@@ -430,8 +446,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
         double lam = 1.0, lam_nb = 1.0;
         if (S.b[i] != FJSPH_BOUND)
         {
-            lam = fj_min_eig3(l00, l01, l11, l02, l12, l22);
-            lam_nb = fj_min_eig3(n00, n01, n11, n02, n12, n22);
+            lam = (C.dim == 2) ? fj_min_eig2(l00, l01, l11) : fj_min_eig3(l00, l01, l11, l02, l12, l22);
+            lam_nb = (C.dim == 2) ? fj_min_eig2(n00, n01, n11) : fj_min_eig3(n00, n01, n11, n02, n12, n22);
         }
         S.L0[i] = Li[0][0];
         S.L1[i] = Li[0][1];
@@ -597,6 +613,13 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         {
             const double ex = pj.x - Tx, ey = pj.y - Ty, ez = pj.z - Tz;
             if (sqrt(ex * ex + ey * ey + ez * ez) < h)
+                surf = 0;
+        }
+        else if (C.dim == 2)
+        {
+            /* SIMDIM = 2, Geometry.cpp:76-84: |nhat . x_jT| + |tau . x_jT| < h with tau = (n_y, -n_x) normalised */
+            const double ex = pj.x - Tx, ey = pj.y - Ty;
+            if (fabs(nhx * ex + nhy * ey) + fabs(nhy * ex - nhx * ey) < h)
                 surf = 0;
         }
         else
@@ -990,7 +1013,8 @@ __device__ void calc_aero_acc(const DevConst& C, double dx_, double dy_, double 
                 ymax = 1.0;
             Cdl = Cds * (1 + 2.632 * ymax);
             const double rr_ = C.aero_L + C.tab_Cb * C.aero_L * ymax;
-            Adrop = FJ_PI * rr_ * rr_;
+            /* Aero.h:57-70: a disc in 3D, a chord in 2D */
+            Adrop = (C.dim == 2) ? C.A_sphere + 2.0 * (C.tab_Cb * C.aero_L * ymax) : FJ_PI * rr_ * rr_;
         }
         else
         {

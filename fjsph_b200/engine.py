@@ -79,6 +79,22 @@ def _shape_of(name, n):
     return (n,)
 
 
+def _pad3(name, a, n):
+    """SIMDIM = 2 hosts hold [n][2] vectors and [n][2][2] matrices; the C ABI's view is [n][3] / [n][3][3] whatever the
+    dimension (third components 0, L's third row and column the identity's)."""
+    a = np.asarray(a, dtype=np.float64)
+    if name in VEC_FIELDS and a.shape == (n, 2):
+        out = np.zeros((n, 3))
+        out[:, :2] = a
+        return out
+    if name == "L" and a.shape == (n, 2, 2):
+        out = np.zeros((n, 3, 3))
+        out[:, :2, :2] = a
+        out[:, 2, 2] = 1.0
+        return out
+    return a
+
+
 def make_view(arrays: dict, n: int):
     """FjsphStateView over numpy arrays (kept alive by the returned list)."""
     view = FjsphStateView()
@@ -87,6 +103,8 @@ def make_view(arrays: dict, n: int):
     for name, a in arrays.items():
         if a is None:
             continue
+        if name in VEC_FIELDS or name == "L":
+            a = _pad3(name, a, n)
         a = np.ascontiguousarray(a, dtype=_dtype_of(name))
         if a.shape != _shape_of(name, n):
             a = np.ascontiguousarray(np.broadcast_to(a, _shape_of(name, n)))
@@ -104,6 +122,7 @@ class Engine:
         self._h = C.c_void_p()
         check(self._L.fjsph_create(C.byref(params), device, int(capacity), C.byref(self._h)))
         self.capacity = int(capacity)
+        self.dim = int(params.dim)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -149,13 +168,15 @@ class Engine:
                 B.times = t.ctypes.data
             vels = np.zeros((max(1, nt), 3))
             if b.get("vels") is not None:
-                vels[:] = np.asarray(b["vels"], dtype=np.float64).reshape(-1, 3)
+                bv = np.asarray(b["vels"], dtype=np.float64)
+                bv = bv.reshape(max(1, nt), -1)
+                vels[:, :bv.shape[1]] = bv
             keep.append(vels)
             B.vels = vels.ctypes.data
             for key, const in (("insert_norm", "insconst"), ("delete_norm", "delconst"), ("aero_norm", "aeroconst")):
                 vec = b.get(key)
                 for d in range(3):
-                    getattr(B, key)[d] = 9999999.0 if vec is None else float(vec[d])
+                    getattr(B, key)[d] = 9999999.0 if vec is None else (float(vec[d]) if d < len(vec) else 0.0)
                 setattr(B, const, float(b.get(const, 9999999.0)))
             back = b.get("back")
             if back is not None:
@@ -198,12 +219,21 @@ class Engine:
         n = self.n
         arrays = {}
         for f in fields:
-            if out is not None and f in out:
+            if out is not None and f in out and out[f].shape == _shape_of(f, n):
                 arrays[f] = out[f]
             else:
                 arrays[f] = np.empty(_shape_of(f, n), dtype=_dtype_of(f))
         view, keep = make_view(arrays, n)
         check(self._L.fjsph_download_state(self._h, level, C.byref(view)))
+        if self.dim == 2:  # the host's shapes: [n][2] vectors, [n][2][2] matrices
+            for f in fields:
+                if f in VEC_FIELDS:
+                    arrays[f] = np.ascontiguousarray(arrays[f][:, :2])
+                elif f == "L":
+                    arrays[f] = np.ascontiguousarray(arrays[f][:, :2, :2])
+                if out is not None and f in out and out[f] is not arrays[f]:
+                    out[f][...] = arrays[f]
+                    arrays[f] = out[f]
         return arrays
 
     def get(self, name: str, level: int = 1) -> np.ndarray:

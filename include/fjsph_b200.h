@@ -42,7 +42,8 @@ enum { FJSPH_INLET_ZONE = 6 };
 typedef struct FjsphParams
 {
     /* switches */
-    int32_t dim;          /* SIMDIM; the device path supports 3 only */
+    int32_t dim;          /* SIMDIM (VarDefs.h:13-41): 3 or 2.  In 2D every view below keeps its [n][3] / [n][3][3] shape with
+                             the third components 0 (L: third row and column of the identity); aero meshes are 3D only */
     int32_t ale;          /* 1 = the -DALE binary (shifting, surfzone-gated ST), 0 = the delta-SPH binary */
     int32_t pressure_rel; /* 0 Cole, 1 isothermal (Var.h:203-236, IO.cpp:397) */
     int32_t solver_type;  /* 0 Newmark-Beta, 1 Runge-Kutta (IO.cpp:393) */
@@ -96,7 +97,7 @@ typedef struct FjsphStateView
     int64_t* part_id;
     int64_t* cellID;
     int32_t *b, *surf, *surfzone, *internal;
-    double *xi, *v, *acc, *Af, *aVisc, *cellV, *gradRho, *norm, *bNorm, *vPert; /* [n][3] */
+    double *xi, *v, *acc, *Af, *aVisc, *cellV, *gradRho, *norm, *bNorm, *vPert; /* [n][3] (dim 2: z = 0) */
     double* L;                                                                   /* [n][3][3] */
     double *Rrho, *rho, *p, *m, *curve, *norm_curve, *woccl, *pDist, *deltaD, *cellP, *cellRho, *colourG, *colour,
         *lam, *lam_nb, *kernsum, *y; /* [n] */

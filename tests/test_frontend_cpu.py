@@ -347,3 +347,23 @@ def test_json_block_files(tmp_path):
         frontend.read_case(para_for(4, '{"W": {"Shape": "Square", }}'), 2)
     with pytest.raises(_lib.FjsphError, match="Unrecognised boundary shape"):
         frontend.read_case(para_for(5, '{"W": {"Shape": "Blob"}}'), 2)
+
+
+def test_dam2d_example_deck_is_the_references():
+    """tests/decks/dam2d_example.para states the numbers of the reference's Examples/Dam_2D (BASELINE.json configs[0]); where
+    the reference tree is present the two decks give the same particles, walls and settings, bit for bit."""
+    mine = frontend.read_case(os.path.join(DECKS, "dam2d_example.para"), 2)
+    assert mine["xi"].shape == (8371, 2) and mine["bound_points"] == 3520
+    assert [(b["name"], b["first"], b["second"]) for b in mine["blocks"]] == [
+        ("Left", 0, 800), ("Right", 800, 2396), ("Bottom", 2396, 3520), ("Fluid", 3520, 8371)]
+    ref_para = "/root/reference/Examples/Dam_2D/para"
+    if not os.path.exists(ref_para):
+        pytest.skip("reference tree absent")
+    ref = frontend.read_case(ref_para, 2)
+    for k in ("xi", "v", "rho", "p", "m", "b"):
+        assert np.array_equal(mine[k], ref[k]), k
+    from fjsph_b200.engine import params_to_dict
+
+    pm, pr = params_to_dict(mine["params"]), params_to_dict(ref["params"])
+    differing = [k for k in pm if pm[k] != pr[k] and not (isinstance(pm[k], float) and np.isnan(pm[k]) and np.isnan(pr[k]))]
+    assert differing == [], differing

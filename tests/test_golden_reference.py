@@ -89,7 +89,7 @@ def test_oracle_reproduces_reference_vectors(path):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU
-GPU_FIXTURES = [p for p in FIXTURES if "_2d" not in os.path.basename(p)]
+GPU_FIXTURES = FIXTURES  # Dam_2D included: SIMDIM = 2 runs on the device (tests/test_gpu_2d.py)
 
 
 @pytest.mark.gpu
@@ -110,7 +110,7 @@ def test_engine_reproduces_reference_vectors(path):
     # the PIPE -> FREE transitions stay exact through all 12 steps; the state is held to what that amplification leaves.
     stiff = "jet_deck" in meta["name"]
     n = case["xi"].shape[0]
-    e = eng.Engine(eng.default_params(3, **case["params"]), 4 * n)
+    e = eng.Engine(eng.default_params(meta["dim"], **case["params"]), 4 * n)
     e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
     if block is not None:
         e.set_blocks([block])

@@ -1,0 +1,149 @@
+"""SIMDIM = 2 on the device (reference src/VarDefs.h:29-41): the same kernels on records whose z components are exact
+zeros, with the 2 x 2 forms of the per-particle Eigen algorithms (dSPH_PreStep's L inverse and lam, Shifting.cpp:73-99), the
+2D free-surface test (Geometry.cpp:76-84), the 2D Wendland normalisation and Gissler areas (IO.cpp:87, Var.h:244-266,
+Aero.h:57-84).  Checker: the oracle's 2D build (oracle/lib/liborc2d.so), which follows FJSPH's own -DSIMDIM=2 objects on
+Dam_2D and the 2D decks (tests/test_oracle_vs_reference.py, tests/golden/ref_dam_2d.npz).  Bars as in the 3D suite."""
+import os
+
+import numpy as np
+import pytest
+
+from fjsph_b200 import cases, engine as eng, frontend
+from tests.test_gpu_parity import PRESTEP_FIELDS, TOL_EIGEN_DEGENERATE, run_stages
+from tests.util import TOL, assert_fields_close, make_pair, make_pair_from_deck, relerr
+
+pytestmark = pytest.mark.gpu
+DECKS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "decks")
+
+
+def block2d(n=(40, 28), dx=1e-3, jitter=0.1, seed=21, rho0=1000.0, c=100.0):
+    """The 2D cut of the C5 block: FREE particles on a jittered lattice with smooth density and velocity fields."""
+    xi = cases.lattice(n, dx, start=(0.0, 0.0), jitter=jitter, seed=seed)
+    L = np.array([n[0] * dx, n[1] * dx])
+    rho = rho0 * (1.0 + 1e-3 * np.sin(2 * np.pi * xi[:, 0] / L[0]))
+    v = 0.5 * np.stack([np.sin(2 * np.pi * xi[:, 1] / L[1]), np.sin(2 * np.pi * xi[:, 0] / L[0])], axis=1)
+    N = xi.shape[0]
+    return dict(xi=xi, v=v, rho=rho, p=cases.cole_pressure(rho, rho0, c), m=np.full(N, rho0 * dx**2),
+                b=np.full(N, cases.FREE, dtype=np.int32), bound_points=0,
+                params=dict(particle_step=dx, rho_rest=rho0, speed_sound=c, mu=8.94e-4, sig=0.0708, visc_alpha=0.05,
+                            dsph_delta=0.1, grav=(0.0, -9.81, 0.0)))
+
+
+def cases2d():
+    yield "block", block2d()
+    yield "block_eps", block2d(n=(23, 19), jitter="eps", seed=4)
+    yield "droplet", cases.droplet(dx=0.002, dim=2, jitter=0.05)
+    yield "tank", cases.box_with_walls(n=(24, 14), dx=0.01, layers=4, jitter=0.05, dim=2)
+
+
+@pytest.mark.parametrize("name,case", list(cases2d()), ids=[n for n, _ in cases2d()])
+def test_2d_neighbour_sets_bit_exact(name, case):
+    o, e, p = make_pair(case, dim=2)
+    o.update_neighbours()
+    e.update_neighbours()
+    off_o, idx_o, _ = o.neighbours()
+    off_e, idx_e = e.neighbours()
+    assert np.array_equal(off_o, off_e) and np.array_equal(idx_o, idx_e)
+    got = e.download(("xi", "v", "rho", "m", "b", "part_id"))
+    assert got["xi"].shape == case["xi"].shape == (case["xi"].shape[0], 2)
+    assert np.array_equal(got["xi"], case["xi"]) and np.array_equal(got["b"], case["b"])
+    assert np.array_equal(got["part_id"], np.arange(case["xi"].shape[0]))
+
+
+@pytest.mark.parametrize("ale", [1, 0])
+@pytest.mark.parametrize("which", ["block", "droplet", "block_eps"])
+def test_2d_stagewise_parity(which, ale):
+    case = dict(cases2d())[which]
+    o, e, p = make_pair(case, dim=2, ale=ale)
+    npd_o, npd_e = run_stages(o, e, ale=bool(ale), label="2D " + which,
+                              tol_eigen=TOL if which == "block" else TOL_EIGEN_DEGENERATE)
+    L = e.download(("L",))["L"]
+    assert L.shape == (case["xi"].shape[0], 2, 2)
+    o.forces(npd_o)
+    e.get_acc_and_Rrho(npd_e)
+    assert_fields_close(e, o, ("acc", "Rrho", "Af"), context="2D " + which + " forces")
+    assert np.abs(e.download(("acc",))["acc"]).max() > 0.0
+
+
+def _steps(o, e, steps, ctx, state_tol=1e-10, rate_tol=1e-6):
+    for step in range(steps):
+        _, so = o.integrate()
+        se = e.integrate()
+        c = "%s step %d" % (ctx, step)
+        assert se.iterations == so.iterations and se.total_points == so.total_points, c
+        assert abs(se.dt - so.dt) <= 1e-12 * so.dt, c
+        assert np.array_equal(e.neighbour_counts(), o.neighbour_counts()), c
+        assert_fields_close(e, o, ("surf", "surfzone", "b", "part_id"), context=c)
+        assert_fields_close(e, o, ("xi", "rho", "lam", "lam_nb"), tol=state_tol, context=c)
+        assert_fields_close(e, o, ("v", "p"), tol=100 * state_tol, context=c)
+        assert_fields_close(e, o, ("acc", "Rrho", "Af", "aVisc", "deltaD", "vPert"), tol=rate_tol, context=c)
+
+
+@pytest.mark.parametrize("solver", [0, 1], ids=["newmark_beta", "rk4"])
+@pytest.mark.parametrize("which", ["block", "droplet", "tank"])
+def test_2d_full_step_parity(which, solver):
+    """Three Integrator::integrate steps in 2D on generic positions: free block, droplet in a gas stream (Gissler with the
+    2D areas, TAB deformation on), tank with Adami walls under gravity along -y."""
+    case = dict(cases2d())[which]
+    kw = dict(solver_type=solver, delta_t_min=1e-9)
+    if which == "droplet":
+        kw.update(use_TAB_def=1)
+    o, e, p = make_pair(case, dim=2, **kw)
+    _steps(o, e, 3, "2D %s solver %d" % (which, solver))
+
+
+def test_dam_2d_deck():
+    """BASELINE.json configs[0]: Examples/Dam_2D as shipped, through the para / bmap front end (tests/decks/dam2d.para: a water
+    column beside a Pressure-Gradient wall on a Ghost floor).  The deck's lattice + U(0, eps dx) positions are a tie-stress
+    input (tests/test_gpu_decks.py), but no 2D particle sits on a repeated eigenvalue the way the 3D lattice decks' edge
+    particles do: flags, counts and dt exact, the state to the bars of the generic cases."""
+    case = frontend.read_case(os.path.join(DECKS, "dam2d.para"), 2)
+    assert case["dim"] == 2 and case["xi"].shape[1] == 2
+    o, e = make_pair_from_deck(case)
+    for step in range(6):
+        _, so = o.integrate()
+        se = e.integrate()
+        ctx = "dam 2D step %d" % step
+        assert se.iterations == so.iterations and abs(se.dt - so.dt) <= 1e-9 * so.dt, ctx
+        assert se.total_points == so.total_points
+    assert_fields_close(e, o, ("surf", "surfzone", "b", "part_id"), context="dam 2D")
+    got = e.download(("xi", "rho", "p", "v", "acc", "Rrho"))
+    report = {f: relerr(got[f], o.get(f)) for f in got}
+    assert report["xi"] <= 1e-10 and report["rho"] <= 1e-10 and report["v"] <= 1e-8 and report["p"] <= 1e-8, report
+    assert report["acc"] <= 1e-6 and report["Rrho"] <= 1e-6, report
+
+
+def test_2d_rejects_what_it_does_not_run():
+    """2D aero meshes (Crossings2D, TAU edge meshes) are not on the device path: an error, not a wrong answer."""
+    case = block2d(n=(12, 10))
+    e = eng.Engine(eng.default_params(2, **case["params"]), case["xi"].shape[0])
+    e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], 0)
+    mesh = cases.hex_mesh((-1e-2, -1e-2, -1e-2), (3e-2, 3e-2, 1e-2), (2, 2, 1), vel=lambda c: np.zeros_like(c), p=1e5, rho=1.2)
+    with pytest.raises(Exception):
+        e.upload_mesh(mesh)
+
+
+def test_c1_dam_2d_at_the_examples_numbers():
+    """BASELINE.json configs[0] at size: tests/decks/dam2d_example.para states Examples/Dam_2D's own numbers (0.02 m spacing,
+    three Pressure-Gradient walls, 8371 particles; identical to the reference's deck particle for particle,
+    tests/test_frontend_cpu.py::test_dam2d_example_deck_is_the_references).  Ten steps against the 2D oracle: flags, counts
+    and dt exact; state 1e-10, rates 1e-6 (measured: x 3e-17, rho 2e-16, rates 9e-12)."""
+    case = frontend.read_case(os.path.join(DECKS, "dam2d_example.para"), 2)
+    assert case["xi"].shape == (8371, 2) and case["bound_points"] == 3520
+    o, e = make_pair_from_deck(case)
+    for step in range(10):
+        _, so = o.integrate()
+        se = e.integrate()
+        ctx = "Dam_2D step %d" % step
+        assert se.iterations == so.iterations and abs(se.dt - so.dt) <= 1e-9 * so.dt, ctx
+        assert se.total_points == so.total_points
+    assert_fields_close(e, o, ("surf", "surfzone", "b", "part_id"), context="Dam_2D")
+    got = e.download(("xi", "rho", "p", "v", "acc", "Rrho"))
+    report = {f: relerr(got[f], o.get(f)) for f in got}
+    print("Dam_2D, 10 steps:", {k: "%.1e" % v for k, v in report.items()})
+    assert report["xi"] <= 1e-10 and report["rho"] <= 1e-10 and report["v"] <= 1e-8 and report["p"] <= 1e-8, report
+    assert report["acc"] <= 1e-6 and report["Rrho"] <= 1e-6, report  # measured 3e-12 / 9e-12 (profiles/r2n_tests_gpu_2d.log)
+    # the column has started to collapse: the free surface is detected along its top and its right side
+    surf = e.download(("surf", "b", "xi"))
+    fluid = surf["b"] != cases.BOUND
+    assert surf["surf"][fluid].sum() > 100

@@ -93,3 +93,28 @@ def test_driver_two_ranks_native_nccl(tmp_path):
     assert np.abs(parts[:, 3:6] - ref[:, 3:6]).max() <= 1e-5 * max(np.abs(ref[:, 3:6]).max(), 1e-12)
     info = (tmp_path / "two_r0_frame.info").read_text()
     assert info.count("Frame:") == 3 and "Total Points: 4166 Boundary Points: 0 Fluid Points: 4166" in info
+
+
+def test_driver_runs_the_2d_dam_break(tmp_path):
+    """Examples/Dam_2D through the driver: `--dim 2` is the reference's 2D build target (makefile: SIMDIM=2)."""
+    if not os.path.exists(BIN):
+        pytest.fail("driver not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    for f in ("dam2d.para", "dam2d_fluid.bmap", "dam2d_boundary.bmap"):
+        shutil.copy(os.path.join(ROOT, "tests", "decks", f), tmp_path / f)
+    para = tmp_path / "dam2d.para"
+    para.write_text(para.read_text().replace("SPH frame time interval: 0.01", "SPH frame time interval: 0.002")
+                    + "\n SPH frame count: 3\n Output files prefix: dam\n")
+    out = subprocess.run([BIN, str(para), "--quiet", "--dim", "2"], cwd=tmp_path, stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 0 and "Simulation complete!" in out.stdout, out.stdout[-2000:]
+    info = (tmp_path / "dam_frame.info").read_text()
+    assert info.count("Frame:") == 3 and "Total Points: 1288 Boundary Points: 488 Fluid Points: 800" in info
+    last = frame(tmp_path / "dam_frame_00002.dat")
+    assert last.shape == (1288, 12) and np.isfinite(last).all()
+    assert np.abs(last[:, 2]).max() == 0.0 and np.abs(last[:, 5]).max() == 0.0  # z and v_z stay exact zeros
+    fluid = last[488:]
+    assert fluid[:, 4].mean() < 0.0  # the column has started to fall (gravity along -y)
+    # a 3D read of the 2D deck is an error message, not a crash
+    bad = subprocess.run([BIN, str(para), "--quiet"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         timeout=60)
+    assert bad.returncode != 0 and "ERROR" in bad.stdout

@@ -78,10 +78,8 @@ def make_pair_from_deck(case, capacity=None, kind=None, **kw):
                     vels=B["vels"], insert_norm=B["insert_norm"], insconst=B["insconst"], delete_norm=B["delete_norm"],
                     delconst=B["delconst"], aero_norm=B["aero_norm"], aeroconst=B["aeroconst"], back=B.get("back"),
                     buffer=B.get("buffer"))
-    if dim != 3:
-        return o, None
     n = case["xi"].shape[0]
-    e = eng.Engine(eng.default_params(3, **params), capacity or 4 * n)
+    e = eng.Engine(eng.default_params(dim, **params), capacity or 4 * n)
     e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], case["bound_points"])
     e.set_blocks(case["blocks"])
     return o, e
