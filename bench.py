@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true",
                     help="N > 1: skip the side lines (`workloads.jet`: the 12.5 M-per-GPU jet; `strong`: 12.5 M particles in total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-port", action="store_true", help="--impl reference: skip the `cpu_port` side line")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -231,6 +232,28 @@ def cpu_reference(args, steps, warmup, sample_cells, kind_pref="reference"):
             "step_ms_min_max": [float(min(step_s)) * 1e3, float(max(step_s)) * 1e3]}
 
 
+def cpu_baseline_leg(args):
+    """The `cpu_baseline` leg of the GPU arm: the reference arm itself (`--impl reference`, 2 warm-up + 4 timed steps, ~30 s)
+    in a FRESH process, so that the CPU code runs under the conditions of the reference arm -- inside this process, beside
+    an initialised CUDA context, its runtime threads and 2.5 GB of pinned buffers, the same 16-thread run measured 37 k
+    particle-steps/s against 58 k alone (profiles/r2j_bench_12.5M.json vs r2j_bench_reference_arm.json)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4", "--warmup", "2",
+           "--workload", args.workload, "--cpu-sample", args.cpu_sample, "--solver", args.solver, "--no-cpu-port"]
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)
+    try:
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=env)
+        line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+        cpu = dict(line["cpu_baseline"])
+        cpu["step_ms_min_max"] = line.get("step_ms_min_max")
+        cpu["how"] = "bench.py --impl reference --steps 4 --warmup 2 in a fresh process"
+        return cpu
+    except (subprocess.SubprocessError, ValueError, IndexError, KeyError) as ex:
+        print("cpu_baseline: the fresh-process run failed (%s); timing in this process instead" % ex, file=sys.stderr)
+        r = cpu_reference(args, 4, 1, args.cpu_sample)
+        return {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+
 def run_reference(args, rank, world):
     """`--impl reference`: the reference's own CPU implementation of the step, alone.  It runs what it says: `warmup`
     untimed and `steps` timed steps of a bounded SAMPLE of the workload (named in config.workload with its particle
@@ -240,7 +263,7 @@ def run_reference(args, rank, world):
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     r = cpu_reference(args, steps, warmup, args.cpu_sample)
     port = None
-    if r["kind"] == "reference":
+    if r["kind"] == "reference" and not args.no_cpu_port:
         # BASELINE.md 3, line (a): the restatement with every loop threaded, on the same sample (a short run: it is the
         # side line; the headline is the reference's own code above)
         p = cpu_reference(args, 3, 1, args.cpu_sample, kind_pref="port")
@@ -599,8 +622,7 @@ def main():
     slab_stats = e.slab_stats() if world > 1 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(args, 4, 1, args.cpu_sample)  # ~25 s of CPU work: 1 warm-up + 4 timed steps, median
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = cpu_baseline_leg(args)
 
     extras = {}
     if world > 1 and not args.no_extras:
