@@ -264,7 +264,9 @@ struct PairGeo
 {
     double rx, ry, rz, rr, r2c, ir, t, gk;
 };
-template <bool FROZEN>
+// RAW: gk = t^3 without the constant 5 Wc / H^2 -- for a sweep whose pair sums are all linear in gk and which applies the
+// constant once per particle after the walk (one FP64 multiplication less per pair).
+template <bool FROZEN, bool RAW = false>
 __device__ __forceinline__ PairGeo pair_geo(const DevConst& C, const double4& pi, const double4& x0i, const double4& pj,
                                             const double4& x0j)
 {
@@ -282,7 +284,7 @@ __device__ __forceinline__ PairGeo pair_geo(const DevConst& C, const double4& pi
     g.ir = fj_rsqrt3(g.rr);
     g.t = fma(g.rr * (-0.5 * C.iH), g.ir, 1.0);
     const double tiny = 1e-12 * C.H;
-    g.gk = (g.rr < tiny * tiny) ? 0.0 : (C.gk_fac * g.t) * (g.t * g.t);
+    g.gk = (g.rr < tiny * tiny) ? 0.0 : (RAW ? (g.t * g.t) * g.t : (C.gk_fac * g.t) * (g.t * g.t));
     return g;
 }
 __device__ __forceinline__ double wend_W_t(const DevConst& C, double t)
@@ -1134,6 +1136,11 @@ struct RecF
 //   continuity  Kernel.h:187-196                   Rrho_    -= V_j ((u + w_j - w_i).gK)     = -(u.G + w_j.G) + w_i.G
 //                                                  Rrhoc_   += V_j (rho_j w_j.gK + rho_i w_i.gK) = rho_j (w_j.G) + rho_i (w_i.G)
 // The w_i.G terms are linear in G, so sum_j G is accumulated once and w_i applied after the loop.
+// FP64 instructions per pair are what the sweep costs (profiles/r2k_sweep_variants.txt: 16 warps per SM run no faster than 12,
+// fewer instructions do), so: pressure, viscosity and ALE momentum share ONE accumulator (they are only ever summed; the
+// viscous and the ALE factor of u are added first: a += u (vf + w_j.G)), u.G is accumulated by its own FMAs, every pair sum
+// is taken with gk = t^3 and the constant 5 Wc / H^2 applied once after the walk, G = (V_j t^3) Rji, and what is needed after
+// the walk only (vPert_i, Af, the mass) is re-read there instead of held in registers through it (168 -> 152 registers).
 // experiment knobs of the force sweep, both measured and left off (profiles/r2k_sweep_variants.txt)
 #ifndef FJ_FORCE_CLAMP
 #define FJ_FORCE_CLAMP 0
@@ -1156,9 +1163,8 @@ __global__ void __launch_bounds__(WARPS * 32, FJ_FORCE_MINB)
     const double4 x0i = FROZEN ? lv.x0[i] : make_double4(0, 0, 0, 0);
     const double4 pi = S.P0[i];
     const double4 vi = S.P1[i];
-    const double4 qi = S.P2[i]; /* vPert_i, p_i/rho_i^2 */
+    const double Pi = S.P2[i].w; /* p_i/rho_i^2; vPert_i is re-read after the walk */
     const double rho_i = vi.w, irho_i = 1.0 / rho_i;
-    const double4 th = S.TH[i]; /* p, m, woccl, cellRho */
     const int b_i = S.b[i];
     const bool do_st = ALE ? (S.surfzone[i] == 1) : true;
     const double st_bound_fac = 1.0 + 0.5 * cos(0.5 * FJ_PI * 7.0 / 9.0);
@@ -1166,32 +1172,32 @@ __global__ void __launch_bounds__(WARPS * 32, FJ_FORCE_MINB)
     const double nu_irho_i = C.nu * irho_i;
     const double q_st = 0.75 * C.iH; /* cos(3 pi/4 r/H) = cospi(0.75 r/H) */
 
-    double ax = 0, ay = 0, az = 0;       /* acc_ (aero + pressure + wall repulsion) */
-    double alx = 0, aly = 0, alz = 0;    /* acc_ale_ */
-    double vx = 0, vy = 0, vz = 0;       /* visc_ */
-    double sx = 0, sy = 0, sz = 0;       /* surf_t_ */
+    /* pair sums, all in units of 5 Wc / H^2 (applied after the walk) */
+    double ax = 0, ay = 0, az = 0;       /* acc_ (pressure) + visc_ + the pair part of acc_ale_ */
+    double sx = 0, sy = 0, sz = 0;       /* surf_t_ (no kernel gradient in it: true units) */
     double sgx = 0, sgy = 0, sgz = 0;    /* sum_j G */
-    double Rrho_ = 0.0, Rrhoc_ = 0.0;
-    double4 af = S.AF[i];                /* Af, deltaD */
+    double Ug = 0.0, Pg = 0.0, Rrhoc_ = 0.0; /* sum_j u.G, sum_j w_j.G, sum_j rho_j w_j.G */
 
-    /* aero term, Resid.cpp:267-277 (Q1: evaluated whenever cellID != -1) */
-    if (S.cellID[i] != -1)
+    /* aero term, Resid.cpp:267-277 (Q1: evaluated whenever cellID != -1): written to AF now, added to acc after the walk */
+    const bool aero_on = S.cellID[i] != -1;
+    if (aero_on)
     {
+        double4 af = S.AF[i]; /* Af, deltaD */
         af.x = af.y = af.z = 0.0; /* CalcAeroAcc returns zero for NoAero */
         if (C.acase != 0)
         {
             const double4 cv = S.CV[i];
             const double4 np = S.NP[i]; /* surface normal, lam_nb */
+            const double4 th = S.TH[i]; /* p, m, woccl, cellRho */
             double a3[3];
             calc_aero_acc(C, cv.x - vi.x, cv.y - vi.y, cv.z - vi.z, np, th, cv.w, S.AV[i].w * C.dx,
                           double(lv.ncount[i] + 1), a3);
             af.x = a3[0];
             af.y = a3[1];
             af.z = a3[2];
-            ax += af.x;
-            ay += af.y;
-            az += af.z;
         }
+        if (active)
+            S.AF[i] = af;
     }
 
     /* one pair, branch-free (a lane's own index as j gives exact zeros: Rji = 0, gradK = 0) */
@@ -1199,38 +1205,38 @@ __global__ void __launch_bounds__(WARPS * 32, FJ_FORCE_MINB)
         const double4 pj = q.p;
         const double4 vj = q.v;
         const double4 qj = q.q;
-        g = pair_geo<FROZEN>(C, pi, x0i, pj, q.x0);
+        g = pair_geo<FROZEN, true>(C, pi, x0i, pj, q.x0);
         if (FJ_FORCE_CLAMP && !take)
             g.gk = 0.0; /* every term below carries gk */
         const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
         const double idist2 = fj_rcp1(g.rr + eps_f);
         const double rho_j = vj.w;
-        const double s = pj.w * g.gk;                                                               /* V_j gk */
-        const double Gx = (pj.w * g.rx) * g.gk, Gy = (pj.w * g.ry) * g.gk, Gz = (pj.w * g.rz) * g.gk; /* V_j gradK */
-        const double pf = rho_j * (qi.w + qj.w);
+        const double s = pj.w * g.gk;                              /* V_j t^3 */
+        const double Gx = s * g.rx, Gy = s * g.ry, Gz = s * g.rz; /* V_j gradK / (5 Wc / H^2) */
+        const double pf = rho_j * (Pi + qj.w);
         ax = fma(-pf, Gx, ax);
         ay = fma(-pf, Gy, ay);
         az = fma(-pf, Gz, az);
         const double vf = fma(nu_irho_i, rho_j, C.nu) * ((s * g.r2c) * idist2);
-        vx = fma(vf, ux, vx);
-        vy = fma(vf, uy, vy);
-        vz = fma(vf, uz, vz);
-        const double ug = ux * Gx + uy * Gy + uz * Gz;
+        Ug = fma(uz, Gz, fma(uy, Gy, fma(ux, Gx, Ug)));
         if (ALE)
         {
             const double pjg = qj.x * Gx + qj.y * Gy + qj.z * Gz; /* V_j (vPert_j . gradK) */
-            alx = fma(ux, pjg, alx);
-            aly = fma(uy, pjg, aly);
-            alz = fma(uz, pjg, alz);
+            const double wv = vf + pjg;                           /* viscosity and ALE momentum both multiply u */
+            ax = fma(ux, wv, ax);
+            ay = fma(uy, wv, ay);
+            az = fma(uz, wv, az);
             sgx += Gx;
             sgy += Gy;
             sgz += Gz;
-            Rrho_ -= ug + pjg;
+            Pg += pjg;
             Rrhoc_ = fma(rho_j, pjg, Rrhoc_);
         }
         else
         {
-            Rrho_ -= ug;
+            ax = fma(ux, vf, ax);
+            ay = fma(uy, vf, ay);
+            az = fma(uz, vf, az);
         }
     };
     /* pairwise surface tension, Kernel.h:101-113 (surface-zone particles only under ALE) */
@@ -1277,14 +1283,28 @@ __global__ void __launch_bounds__(WARPS * 32, FJ_FORCE_MINB)
                 stage_span(lv.x0, first, last);
             }
         });
+    double Rrho_ = -Ug; /* Rrho_ -= V_j ((u + w_j - w_i) . gK) */
     if (ALE)
     {
-        const double pig = qi.x * sgx + qi.y * sgy + qi.z * sgz; /* vPert_i . sum_j G */
-        alx += 2.0 * vi.x * pig;
-        aly += 2.0 * vi.y * pig;
-        alz += 2.0 * vi.z * pig;
-        Rrho_ += pig;
+        const double4 wi = gather_rw(S.P2, unsigned(i));
+        const double pig = wi.x * sgx + wi.y * sgy + wi.z * sgz; /* vPert_i . sum_j G */
+        ax += 2.0 * vi.x * pig;
+        ay += 2.0 * vi.y * pig;
+        az += 2.0 * vi.z * pig;
+        Rrho_ += pig - Pg;
         Rrhoc_ += rho_i * pig;
+    }
+    /* the constant of the kernel gradient, once per particle */
+    ax *= C.gk_fac;
+    ay *= C.gk_fac;
+    az *= C.gk_fac;
+    const double Rrho_pairs = (Rrho_ * rho_i + Rrhoc_) * C.gk_fac;
+    const double4 af = gather_rw(S.AF, unsigned(i));
+    if (aero_on)
+    {
+        ax += af.x;
+        ay += af.y;
+        az += af.z;
     }
     if ((S.internal[i] & 0xFF) == 1)
     {
@@ -1307,14 +1327,13 @@ __global__ void __launch_bounds__(WARPS * 32, FJ_FORCE_MINB)
     if (!active)
         return; /* the walk is over: nothing below votes */
     const double4 av = S.AV[i];
-    const double im = 1.0 / th.y;
+    const double im = 1.0 / gather_rw(S.TH, unsigned(i)).y;
     double4 acc;
-    acc.x = ax + alx + av.x + vx + sx * im + C.gx;
-    acc.y = ay + aly + av.y + vy + sy * im + C.gy;
-    acc.z = az + alz + av.z + vz + sz * im + C.gz;
-    acc.w = Rrho_ * rho_i + Rrhoc_ + af.w;
+    acc.x = ax + av.x + sx * im + C.gx;
+    acc.y = ay + av.y + sy * im + C.gy;
+    acc.z = az + av.z + sz * im + C.gz;
+    acc.w = Rrho_pairs + af.w;
     S.ACC[i] = acc;
-    S.AF[i] = af;
 }
 
 // ================================================================= walls (Resid.cpp:21-186)

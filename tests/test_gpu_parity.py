@@ -370,4 +370,8 @@ def test_engine_errors_are_reported_not_fatal():
     with pytest.raises(FjsphError):
         e.get_acc_and_Rrho(1.0)  # list not built
     with pytest.raises(FjsphError):
-        eng.Engine(eng.default_params(2, particle_step=1e-3), 10)  # 2D is oracle-only
+        eng.default_params(4, particle_step=1e-3)  # SIMDIM is 2 or 3
+    p2 = eng.default_params(2, particle_step=1e-3)
+    p2.grav[2] = -9.81  # a third gravity component in a 2D build
+    with pytest.raises(FjsphError):
+        eng.Engine(p2, 10)
