@@ -62,6 +62,19 @@ def synthetic_block(n=(500, 250, 100), dx=1e-3, jitter=0.1, seed=1234, rho0=1000
     )
 
 
+def synthetic_block_2d(n=(40, 28), dx=1e-3, jitter=0.1, seed=21, rho0=1000.0, c=100.0):
+    """The 2D cut of the C5 block: FREE particles on a jittered lattice with smooth density and velocity fields."""
+    xi = lattice(n, dx, start=(0.0, 0.0), jitter=jitter, seed=seed)
+    L = np.array([n[0] * dx, n[1] * dx])
+    rho = rho0 * (1.0 + 1e-3 * np.sin(2 * np.pi * xi[:, 0] / L[0]))
+    v = 0.5 * np.stack([np.sin(2 * np.pi * xi[:, 1] / L[1]), np.sin(2 * np.pi * xi[:, 0] / L[0])], axis=1)
+    N = xi.shape[0]
+    return dict(xi=xi, v=v, rho=rho, p=cole_pressure(rho, rho0, c), m=np.full(N, rho0 * dx**2),
+                b=np.full(N, FREE, dtype=np.int32), bound_points=0,
+                params=dict(particle_step=dx, rho_rest=rho0, speed_sound=c, mu=8.94e-4, sig=0.0708, visc_alpha=0.05,
+                            dsph_delta=0.1, grav=(0.0, -9.81, 0.0)))
+
+
 def synthetic_jet(nx=255, radius_cells=125, dx=1e-3, jitter=0.1, seed=1234, rho0=1000.0, c=100.0, x_offset_cells=0,
                   v_jet=30.0, v_inf=(0.0, 100.0, 0.0)):
     """Config C5, "jet" flavour: a liquid cylinder of radius radius_cells*dx along x moving at

@@ -98,6 +98,10 @@ __device__ __forceinline__ void stage_span(const T* base, unsigned first, unsign
 #if FJ_STAGE_MODE == 1
     stage_l1(base + first);
     stage_l1(base + last);
+#elif FJ_STAGE_MODE == 3 /* the lanes' first records only (the trailing few records of the stretch are demand-loaded) */
+    stage_l1(base + first);
+#elif FJ_STAGE_MODE == 4 /* the lanes' last records only */
+    stage_l1(base + last);
 #elif FJ_STAGE_MODE == 2
     const unsigned long long a0 = (unsigned long long)(base + first) & ~127ull;
     const unsigned long long p = a0 + (threadIdx.x & 31u) * 128ull;

@@ -16,17 +16,7 @@ pytestmark = pytest.mark.gpu
 DECKS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "decks")
 
 
-def block2d(n=(40, 28), dx=1e-3, jitter=0.1, seed=21, rho0=1000.0, c=100.0):
-    """The 2D cut of the C5 block: FREE particles on a jittered lattice with smooth density and velocity fields."""
-    xi = cases.lattice(n, dx, start=(0.0, 0.0), jitter=jitter, seed=seed)
-    L = np.array([n[0] * dx, n[1] * dx])
-    rho = rho0 * (1.0 + 1e-3 * np.sin(2 * np.pi * xi[:, 0] / L[0]))
-    v = 0.5 * np.stack([np.sin(2 * np.pi * xi[:, 1] / L[1]), np.sin(2 * np.pi * xi[:, 0] / L[0])], axis=1)
-    N = xi.shape[0]
-    return dict(xi=xi, v=v, rho=rho, p=cases.cole_pressure(rho, rho0, c), m=np.full(N, rho0 * dx**2),
-                b=np.full(N, cases.FREE, dtype=np.int32), bound_points=0,
-                params=dict(particle_step=dx, rho_rest=rho0, speed_sound=c, mu=8.94e-4, sig=0.0708, visc_alpha=0.05,
-                            dsph_delta=0.1, grav=(0.0, -9.81, 0.0)))
+block2d = cases.synthetic_block_2d
 
 
 def cases2d():
@@ -147,3 +137,22 @@ def test_c1_dam_2d_at_the_examples_numbers():
     surf = e.download(("surf", "b", "xi"))
     fluid = surf["b"] != cases.BOUND
     assert surf["surf"][fluid].sum() > 100
+
+
+def test_2d_state_after_500_steps():
+    """The 3D suite's long run (tests/test_gpu_parity.py::test_state_after_1000_steps) in 2D: 500 Integrator::integrate
+    calls on the jittered 2D block with free surfaces on all four sides; sub-iteration count and dt of every step and every
+    surface flag agree, positions to 1e-8 of the domain, density 1e-10, velocity 1e-7."""
+    case = block2d(n=(24, 18), seed=5)
+    o, e, p = make_pair(case, dim=2, delta_t_min=1e-9)
+    for step in range(500):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert se.iterations == so.iterations, step
+        assert abs(se.dt - so.dt) <= 1e-9 * so.dt, step
+    assert_fields_close(e, o, ("surf", "surfzone", "b"), context="2D 500 steps")
+    got = e.download(("xi", "rho", "v"))
+    report = {f: relerr(got[f], o.get(f)) for f in got}
+    print("2D, 500 steps:", {k: "%.1e" % v for k, v in report.items()})
+    assert report["xi"] <= 1e-8 and report["rho"] <= 1e-10 and report["v"] <= 1e-7, report
+    assert np.abs(o.get("xi") - case["xi"]).max() > 2e-3  # the block really moved

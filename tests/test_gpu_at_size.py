@@ -186,3 +186,16 @@ def test_lean_and_near_surface_launches_agree(monkeypatch, below):
     case = cases.synthetic_block((70, 18, 16), 1e-3, jitter=0.1, seed=5)
     o, e = pair_mt(case, max_subits=3, delta_t_min=1e-9)
     step_and_compare(o, e, 2, "split below " + below)
+
+
+@pytest.mark.parametrize("flavour", ["rk4", "dsph"])
+def test_quarter_million_block_other_solvers(flavour):
+    """The C5 block workload at 262 144 particles (the CPU arm's sample, bench.py) through the two paths the million-particle
+    cases above do not take: Runge-Kutta 4 (Runge_Kutta.cpp:462-476: four force evaluations on FROZEN pair distances, the
+    stage accumulators) and the delta-SPH build without ALE shifting (ALE = 0: no vPert terms in the force sweep, the plain
+    continuity equation).  One step against the threaded parity oracle."""
+    case = cases.synthetic_block((64, 64, 64), 1e-3, jitter=0.1, seed=1234)
+    kw = dict(delta_t_min=1e-9, max_subits=3)
+    kw.update(dict(solver_type=1) if flavour == "rk4" else dict(ale=0))
+    o, e = pair_mt(case, **kw)
+    step_and_compare(o, e, 1, "block 64^3 " + flavour)

@@ -25,7 +25,7 @@ def relerr(a, b):
     return 0.0 if d == 0 else (d / s if s > 0 else np.inf)
 
 
-def run(name, case, params, steps, rank, world, local_rank, mesh=None, block=None, bounds=None):
+def run(name, case, params, steps, rank, world, local_rank, mesh=None, block=None, bounds=None, dim=3):
     n = case["xi"].shape[0]
     dx = case["params"]["particle_step"]
     xmin, xmax = case["xi"][:, 0].min() - 0.5 * dx, case["xi"][:, 0].max() + 0.5 * dx
@@ -35,7 +35,7 @@ def run(name, case, params, steps, rank, world, local_rank, mesh=None, block=Non
     sub["bound_points"] = 0
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        e = slab.SlabEngine(eng.default_params(3, **params), sub, rank, world, lo[rank], hi[rank], device=local_rank,
+        e = slab.SlabEngine(eng.default_params(dim, **params), sub, rank, world, lo[rank], hi[rank], device=local_rank,
                             stream=stream, capacity=2 * n + 1000, part_id=own)
         if mesh is not None:
             e.upload_mesh(mesh)  # the aero mesh is replicated on every rank
@@ -60,7 +60,7 @@ def run(name, case, params, steps, rank, world, local_rank, mesh=None, block=Non
     dist.all_gather_object(gathered, (got, its, stats))
     ok = True
     if rank == 0:
-        ref = eng.Engine(eng.default_params(3, **params), 4 * n, device=local_rank)
+        ref = eng.Engine(eng.default_params(dim, **params), 4 * n, device=local_rank)
         ref.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], 0)
         if mesh is not None:
             ref.upload_mesh(mesh)
@@ -136,6 +136,10 @@ def main():
         dxj = jet["params"]["particle_step"]
         ok &= run("inlet jet", jet, dict(jet["params"], delta_t_min=1e-9), 14, rank, world, local_rank, block=jet["block"],
                   bounds=([-1e300, -3.5 * dxj], [-3.5 * dxj, 1e300]))
+    # 6. the 2D build: x-slabs of a 2D block (rows run along y, z = 0 throughout), with migration
+    case6 = cases.synthetic_block_2d((48 * world, 80), 1e-3, jitter=0.1, seed=6)
+    case6["v"] = case6["v"] + np.array([20.0, 0.0])
+    ok &= run("2D drifting block", case6, dict(case6["params"], delta_t_min=1e-9), 5, rank, world, local_rank, dim=2)
     dist.destroy_process_group()
     if rank == 0:
         print("SLAB PARITY %s" % ("OK" if ok else "FAILED"))
