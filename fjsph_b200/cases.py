@@ -178,13 +178,17 @@ def dam_2d(dx=0.02):
 
 
 def inlet_jet(n=(5, 5, 4), dx=1e-3, v_jet=10.0, fixed=0, n_buf=4, aero_x=1.5, delete_x=None, rho0=1000.0, c=100.0,
-              jitter="eps", seed=21):
+              jitter="eps", seed=21, dim=3):
     """A square inlet block along +x (the squareCube branch of InletShape::generate_points, shapes/inlet.cpp:455-520,
     without rotation): nk PIPE layers at x = -k dx, one BACK layer at x = -nk dx and n_buf BUFFER layers behind
     it; insertion plane normal (1,0,0) with insconst = -(nk - 0.01) dx (inlet.cpp:207-210), aero entry plane at
     aero_x*dx (PIPE -> FREE, Containment.cpp:822-847), optional delete plane at delete_x*dx (Integration.cpp:127-205).
     Returns the case plus the bound_block fields of its single fluid block."""
-    ni, nj, nk = n
+    if dim == 2:  # n = (ni, nk): a line inlet, the 2D build's square inlet
+        ni, nk = n
+        nj = 1
+    else:
+        ni, nj, nk = n
     rng = np.random.default_rng(seed)
     pts, b = [], []
     layers = list(range(nk)) + [nk] + list(range(nk + 1, nk + 1 + n_buf))
@@ -194,7 +198,7 @@ def inlet_jet(n=(5, 5, 4), dx=1e-3, v_jet=10.0, fixed=0, n_buf=4, aero_x=1.5, de
             for ii in range(ni):
                 pts.append((-kk * dx, ii * dx, jj * dx))
                 b.append(kind)
-    xi = np.asarray(pts, dtype=np.float64)
+    xi = np.asarray(pts, dtype=np.float64)[:, :dim]
     if jitter == "eps":
         xi = xi + rng.uniform(0.0, EPS * dx, size=xi.shape)
     elif jitter is not None:
@@ -210,7 +214,7 @@ def inlet_jet(n=(5, 5, 4), dx=1e-3, v_jet=10.0, fixed=0, n_buf=4, aero_x=1.5, de
     if delete_x is not None:
         block.update(delete_norm=(1.0, 0.0, 0.0), delconst=delete_x * dx)
     return dict(
-        xi=xi, v=v, rho=np.full(N, rho0), p=np.zeros(N), m=np.full(N, rho0 * dx**3), b=np.asarray(b, dtype=np.int32),
+        xi=xi, v=v, rho=np.full(N, rho0), p=np.zeros(N), m=np.full(N, rho0 * dx**dim), b=np.asarray(b, dtype=np.int32),
         bound_points=0, block=block,
         params=dict(particle_step=dx, rho_rest=rho0, speed_sound=c, mu=8.94e-4, sig=0.0708, visc_alpha=0.05,
                     delta_t_min=1e-9, frame_time_interval=1e9),
@@ -285,4 +289,60 @@ def hex_mesh(lo, hi, n, vel=(0.0, 0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-
         cell_ptr=np.concatenate([[0], np.cumsum([len(c) for c in cfaces])]).astype(np.int64),
         cell_faces=np.concatenate([np.asarray(c, dtype=np.int64) for c in cfaces]),
         cCentre=centre, cVel=ev(vel, (nc, 3)), cP=ev(p, (nc,)), cRho=ev(rho, (nc,)),
+    )
+
+
+def quad_mesh(lo, hi, n, vel=(0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-2):
+    """2D counterpart of hex_mesh: uniform mesh of the rectangle [lo, hi] with n = (nx, ny) quadrilateral cells in the
+    layout of the reference's 2D MESH (what TAU::Read_tau_mesh_EDGE fills, CDFIO.cpp:1103-1227): verts [nv,2], faces =
+    EDGES (two vertices each), leftright = (left cell, right cell or the boundary marker: -2 outer, -1 inner wall),
+    cell -> edges, cell centres and the cell solution.  vel / p / rho may be constants or callables of the centres [nc,2]."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    nx, ny = (int(k) for k in n)
+    xs = [np.linspace(lo[d], hi[d], k + 1) for d, k in enumerate((nx, ny))]
+    vid = lambda i, j: j * (nx + 1) + i
+    cid = lambda i, j: j * nx + i
+    gi, gj = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
+    verts = np.zeros(((nx + 1) * (ny + 1), 2))
+    verts[vid(gi, gj).ravel()] = np.stack([xs[0][gi.ravel()], xs[1][gj.ravel()]], axis=1)
+    faces, leftright, cfaces = [], [], [[] for _ in range(nx * ny)]
+
+    def add_edge(e, left, right):
+        f = len(faces)
+        faces.append(e)
+        leftright.append((left, right))
+        cfaces[left].append(f)
+        if right >= 0:
+            cfaces[right].append(f)
+
+    for j in range(ny):
+        for i in range(nx + 1):   # x-normal edges
+            e = (vid(i, j), vid(i, j + 1))
+            if i == 0:
+                add_edge(e, cid(0, j), outer_marker)
+            elif i == nx:
+                add_edge(e, cid(nx - 1, j), outer_marker)
+            else:
+                add_edge(e, cid(i - 1, j), cid(i, j))
+    for j in range(ny + 1):
+        for i in range(nx):       # y-normal edges
+            e = (vid(i + 1, j), vid(i, j))
+            if j == 0:
+                add_edge(e, cid(i, 0), outer_marker)
+            elif j == ny:
+                add_edge(e, cid(i, ny - 1), outer_marker)
+            else:
+                add_edge(e, cid(i, j - 1), cid(i, j))
+    ci, cj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    centre = np.zeros((nx * ny, 2))
+    mid = [0.5 * (x[1:] + x[:-1]) for x in xs]
+    centre[cid(ci, cj).ravel()] = np.stack([mid[0][ci.ravel()], mid[1][cj.ravel()]], axis=1)
+    nc = centre.shape[0]
+    ev = lambda f, shape: (np.asarray(f(centre), float) if callable(f) else np.broadcast_to(np.asarray(f, float), shape)).copy()
+    return dict(
+        verts=verts, face_ptr=np.arange(0, 2 * len(faces) + 1, 2, dtype=np.int64),
+        face_vtx=np.asarray(faces, dtype=np.int64).ravel(), leftright=np.asarray(leftright, dtype=np.int32),
+        cell_ptr=np.concatenate([[0], np.cumsum([len(c) for c in cfaces])]).astype(np.int64),
+        cell_faces=np.concatenate([np.asarray(c, dtype=np.int64) for c in cfaces]),
+        cCentre=centre, cVel=ev(vel, (nc, 2)), cP=ev(p, (nc,)), cRho=ev(rho, (nc,)),
     )

@@ -152,6 +152,7 @@ struct Slab
 struct DeviceMesh
 {
     bool loaded = false;
+    int dim = 3;
     int n_cells = 0, n_faces = 0;
     double4* fx = nullptr;
     int* fmark = nullptr;

@@ -5,7 +5,11 @@
 //   CheckCell        reference src/Containment.cpp:385-420 crossing parity of a +x ray over the cell's faces
 //   FindCell         reference src/Containment.cpp:579-820 previous cell, then the 5 / 500 nearest cell centres,
 //                                                          then boundary faces (inner wall / outer boundary / lost)
-//   FirstCell        reference src/Containment.cpp:425-573 PIPE -> FREE transition (150 nearest cell centres)
+//   FirstCell        reference src/Containment.cpp:425-573 PIPE -> FREE transition (150 nearest cell centres; 20 in 2D)
+// and in the 2D build (-DSIMDIM=2: faces are EDGES of two vertices, z = 0 throughout):
+//   Crossings2D      reference src/Geometry.cpp:354-399   the +x ray of the crossings test against one edge
+//   get_line_intersection reference src/Geometry.cpp:312-341 segment point -> cell centre against a boundary edge (its
+//                                                          denominator test is one-sided, as in the reference)
 // The reference finds nearest cell centres with a second nanoflann KD-tree (FJSPH.cpp:148); here the centres are
 // binned into a uniform grid on the host once per mesh and a thread walks Chebyshev shells of bins around its
 // particle.  "The first of the k nearest centres whose cell contains the point" is evaluated as: the containing
@@ -26,6 +30,7 @@ constexpr int TPB = 128;
 struct MeshView
 {
     int n_cells;
+    int dim;                          // 3, or 2 (edges: v0 and v1 only)
     const double4* __restrict__ fx;   // 3 per face: {v0.xyz, v1.x} {v1.yz, v2.xy} {v2.z, vlast.xyz}
     const int* __restrict__ fmark;    // leftright.second: neighbour cell, -1 inner wall, -2 outer boundary
     const int* __restrict__ cell_ptr;
@@ -73,14 +78,55 @@ __device__ int crossings3d(const MeshView& M, int f, const V3& testp, const V3& 
     return 1;
 }
 
+// Crossings2D (Geometry.cpp:354-399), products rounded one by one as the CPU evaluates them
+__device__ int crossings2d(const MeshView& M, int f, const V3& p)
+{
+    const double4 a = M.fx[3 * f], b = M.fx[3 * f + 1];
+    const double v0x = a.x, v0y = a.y, v1x = a.w, v1y = b.x;
+    const int yflag0 = (v0y >= p.y), yflag1 = (v1y >= p.y);
+    if (yflag0 == yflag1)
+        return 0;
+    const double lhs = __dmul_rn(__dsub_rn(v1y, p.y), __dsub_rn(v1x, v0x));
+    const double rhs = __dmul_rn(__dsub_rn(v1x, p.x), __dsub_rn(v1y, v0y));
+    return (int(lhs >= rhs) == yflag1) ? 1 : 0;
+}
+
+// get_line_intersection (Geometry.cpp:312-341): segment p -> c against the edge of face f
+__device__ int line_intersection2d(const MeshView& M, int f, const V3& p, const V3& c)
+{
+    const double4 a = M.fx[3 * f], b = M.fx[3 * f + 1];
+    const double e1x = a.x, e1y = a.y, e2x = a.w, e2y = b.x;
+    const double sx = __dsub_rn(c.x, p.x), sy = __dsub_rn(c.y, p.y);
+    const double rx = __dsub_rn(e2x, e1x), ry = __dsub_rn(e2y, e1y);
+    const double denom = __dadd_rn(__dmul_rn(-rx, sy), __dmul_rn(sx, ry));
+    if (denom < 2.220446049250313e-16) /* MEPSILON: collinear, or any negative denominator */
+        return 0;
+    const double dx = __dsub_rn(p.x, e1x), dy = __dsub_rn(p.y, e1y);
+    const double u = __ddiv_rn(__dadd_rn(__dmul_rn(-sy, dx), __dmul_rn(sx, dy)), denom);
+    const double t = __ddiv_rn(__dsub_rn(__dmul_rn(rx, dy), __dmul_rn(ry, dx)), denom);
+    return (u > 0.0 && u < 1.0 && t > 0.0 && t < 1.0) ? 1 : 0;
+}
+
+// the containment test of one face (ray along +x from the point) and the boundary test (segment point -> cell centre)
+__device__ __forceinline__ int face_contains_ray(const MeshView& M, int f, const V3& p)
+{
+    if (M.dim == 2)
+        return crossings2d(M, f, p);
+    const V3 rayp = {p.x + 1e+5, p.y, p.z};
+    return crossings3d(M, f, p, rayp);
+}
+__device__ __forceinline__ int face_cut_by_segment(const MeshView& M, int f, const V3& p, const V3& rayp)
+{
+    return (M.dim == 2) ? line_intersection2d(M, f, p, rayp) : crossings3d(M, f, p, rayp);
+}
+
 __device__ bool check_cell(const MeshView& M, int cell, const V3& p)
 {
     if (cell < 0 || cell >= M.n_cells) /* Q7 */
         return false;
-    const V3 rayp = {p.x + 1e+5, p.y, p.z};
     unsigned line_flag = 0, inside = 0;
     for (int k = M.cell_ptr[cell]; k < M.cell_ptr[cell + 1]; ++k)
-        if (crossings3d(M, M.cell_faces[k], p, rayp))
+        if (face_contains_ray(M, M.cell_faces[k], p))
         {
             inside = !inside;
             if (line_flag)
@@ -243,7 +289,7 @@ __global__ void __launch_bounds__(TPB)
         {
             const int f = M.cell_faces[k];
             const int mark = M.fmark[f];
-            if (mark < 0 && crossings3d(M, f, p, rayp))
+            if (mark < 0 && face_cut_by_segment(M, f, p, rayp))
             {
                 cross = !cross;
                 if (mark == -1)
@@ -291,7 +337,8 @@ __global__ void __launch_bounds__(TPB)
         return;
     const V3 p = {x.x, x.y, x.z};
     Search S;
-    const int cell = find_containing(M, p, 150, S);
+    const int k_first = (M.dim == 2) ? 20 : 150; /* Containment.cpp:431-436 */
+    const int cell = find_containing(M, p, k_first, S);
     if (cell >= 0)
     {
         take_cell(L, i, M, cell);
@@ -302,7 +349,7 @@ __global__ void __launch_bounds__(TPB)
     double last_d2 = -1.0;
     int last = -1;
     double4 v = L.P1[i];
-    for (int t = 0; t < 150; ++t)
+    for (int t = 0; t < k_first; ++t)
     {
         last = next_nearest(M, S, p, last_d2, last);
         if (last < 0)
@@ -313,7 +360,7 @@ __global__ void __launch_bounds__(TPB)
         {
             const int f = M.cell_faces[k];
             const int mark = M.fmark[f];
-            if (mark < 0 && crossings3d(M, f, p, rayp))
+            if (mark < 0 && face_cut_by_segment(M, f, p, rayp))
             {
                 cross = !cross;
                 if (mark == -1)
@@ -323,6 +370,12 @@ __global__ void __launch_bounds__(TPB)
                     const double r1x = a.w - a.x, r1y = b.x - a.y, r1z = b.y - a.z;
                     const double r2x = b.z - a.x, r2y = b.w - a.y, r2z = cc.x - a.z;
                     double qx = r1y * r2z - r1z * r2y, qy = r1z * r2x - r1x * r2z, qz = r1x * r2y - r1y * r2x;
+                    if (M.dim == 2) /* Containment.cpp:540-544: norm = (-r1.y, r1.x) */
+                    {
+                        qx = -r1y;
+                        qy = r1x;
+                        qz = 0.0;
+                    }
                     const double qq = qx * qx + qy * qy + qz * qz;
                     if (qq > 0.0)
                     {
@@ -360,6 +413,7 @@ __global__ void __launch_bounds__(TPB)
 MeshView view_of(const DeviceMesh& D)
 {
     MeshView M;
+    M.dim = D.dim;
     M.n_cells = D.n_cells;
     M.fx = D.fx;
     M.fmark = D.fmark;
@@ -408,11 +462,7 @@ void fj_free_mesh(FjsphEngine* e)
 
 extern "C" int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m)
 {
-    if (e && e->P.dim == 2)
-    {
-        fj_set_error("upload_mesh: SIMDIM=2 aero meshes (Crossings2D, TAU edge meshes) are not on the device path");
-        return FJSPH_ERR_INVALID;
-    }
+    const int dim = e->P.dim; /* 2: faces are edges, every z of verts / cCentre / cVel must be 0 */
     cudaSetDevice(e->device);
     if (!m || m->n_cells <= 0 || m->n_faces <= 0 || !m->verts || !m->face_ptr || !m->face_vtx || !m->leftright ||
         !m->cell_ptr || !m->cell_faces || !m->cCentre || !m->cVel || !m->cP || !m->cRho)
@@ -431,12 +481,12 @@ extern "C" int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m)
     for (size_t f = 0; f < nf; ++f)
     {
         const int64_t a = m->face_ptr[f], b = m->face_ptr[f + 1];
-        if (b - a < 3)
+        if (b - a < dim)
         {
-            fj_set_error("upload_mesh: face %zu has fewer than 3 vertices", f);
+            fj_set_error("upload_mesh: face %zu has fewer than %d vertices", f, dim);
             return FJSPH_ERR_INVALID;
         }
-        const int64_t id[4] = {m->face_vtx[a], m->face_vtx[a + 1], m->face_vtx[a + 2], m->face_vtx[b - 1]};
+        const int64_t id[4] = {m->face_vtx[a], m->face_vtx[a + 1], m->face_vtx[dim == 2 ? a + 1 : a + 2], m->face_vtx[b - 1]};
         double v[4][3];
         for (int k = 0; k < 4; ++k)
         {
@@ -446,6 +496,11 @@ extern "C" int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m)
                 return FJSPH_ERR_INVALID;
             }
             for (int d = 0; d < 3; ++d) v[k][d] = m->verts[3 * id[k] + d];
+            if (dim == 2 && v[k][2] != 0.0)
+            {
+                fj_set_error("upload_mesh: SIMDIM=2 mesh with a non-zero z coordinate (vertex %lld)", (long long)id[k]);
+                return FJSPH_ERR_INVALID;
+            }
         }
         fx[3 * f] = make_double4(v[0][0], v[0][1], v[0][2], v[1][0]);
         fx[3 * f + 1] = make_double4(v[1][1], v[1][2], v[2][0], v[2][1]);
@@ -470,7 +525,7 @@ extern "C" int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m)
     // bins over the cell centres: about 4 centres per bin
     DeviceMesh& D = e->mesh;
     const double ext[3] = {std::max(hi[0] - lo[0], 1e-300), std::max(hi[1] - lo[1], 1e-300), std::max(hi[2] - lo[2], 1e-300)};
-    double bin = std::cbrt(ext[0] * ext[1] * ext[2] / double(nc) * 4.0);
+    double bin = dim == 2 ? std::sqrt(ext[0] * ext[1] / double(nc) * 4.0) : std::cbrt(ext[0] * ext[1] * ext[2] / double(nc) * 4.0);
     if (!(bin > 0.0) || !std::isfinite(bin))
         bin = std::max(ext[0], std::max(ext[1], ext[2]));
     int nb[3];
@@ -498,6 +553,7 @@ extern "C" int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m)
         return st;
     if (!D.counters)
         FJ_CUDA(cudaMalloc(&D.counters, 4 * sizeof(int)));
+    D.dim = dim;
     D.n_cells = int(nc);
     D.n_faces = int(nf);
     D.ox = lo[0];

@@ -189,11 +189,15 @@ class Engine:
 
     def upload_mesh(self, mesh: dict):
         """The reference's MESH (Var.h:396-451) for aero source meshInfl: verts [nv,3], face_ptr/face_vtx (CSR),
-        leftright [nf,2], cell_ptr/cell_faces (CSR), cCentre [nc,3], cVel [nc,3], cP [nc], cRho [nc]."""
+        leftright [nf,2], cell_ptr/cell_faces (CSR), cCentre [nc,3], cVel [nc,3], cP [nc], cRho [nc]; in a 2D engine the
+        faces are edges of two vertices and the vector arrays may be [n,2]."""
         m = FjsphMesh()
         keep = {}
         for k in ("verts", "cCentre", "cVel", "cP", "cRho"):
-            keep[k] = np.ascontiguousarray(mesh[k], dtype=np.float64)
+            a = np.asarray(mesh[k], dtype=np.float64)
+            if a.ndim == 2 and a.shape[1] == 2:  # a 2D mesh (faces are edges): the ABI's [n][3] with z = 0
+                a = np.concatenate([a, np.zeros((a.shape[0], 1))], axis=1)
+            keep[k] = np.ascontiguousarray(a)
         for k in ("face_ptr", "face_vtx", "cell_ptr", "cell_faces"):
             keep[k] = np.ascontiguousarray(mesh[k], dtype=np.int64)
         keep["leftright"] = np.ascontiguousarray(mesh["leftright"], dtype=np.int32)

@@ -1552,16 +1552,60 @@ static int Crossings3D(Mesh const& M, std::vector<long> const& face, Vec const& 
     }
     return 0;
 }
+/* the containment test of one face (ray along +x from the point) and the boundary test (segment point -> cell centre) */
+static inline int face_contains_ray(Mesh const& M, std::vector<long> const& face, Vec const& testp)
+{
+    Vec rayp = testp;
+    rayp[0] += 1e+5; /* Containment.cpp:388-390 */
+    return Crossings3D(M, face, testp, rayp);
+}
+static inline int face_cut_by_segment(Mesh const& M, std::vector<long> const& face, Vec const& testp, Vec const& rayp)
+{
+    return Crossings3D(M, face, testp, rayp);
+}
+#else
+/* Crossings2D, Geometry.cpp:354-399: does the +x ray from the point cross this edge (Haines' crossings test, one edge) */
+static int Crossings2D(Mesh const& M, std::vector<long> const& edge, Vec const& point)
+{
+    real const tx = point[0], ty = point[1];
+    Vec const &vtx0 = M.verts[edge[0]], &vtx1 = M.verts[edge[1]];
+    int const yflag0 = (vtx0[1] >= ty), yflag1 = (vtx1[1] >= ty);
+    int inside_flag = 0;
+    if (yflag0 != yflag1)
+        if (((vtx1[1] - ty) * (vtx1[0] - vtx0[0]) >= (vtx1[0] - tx) * (vtx1[1] - vtx0[1])) == yflag1)
+            inside_flag = !inside_flag;
+    return inside_flag;
+}
+/* get_line_intersection, Geometry.cpp:312-341: segment p1 -> cellC against the edge; a denominator below MEPSILON --
+ * collinear, or any NEGATIVE one -- is "no intersection", as in the reference */
+static int get_line_intersection(Mesh const& M, std::vector<long> const& edge, Vec const& p1, Vec const& cellC)
+{
+    Vec const &e1 = M.verts[edge[0]], &e2 = M.verts[edge[1]];
+    Vec const s_ = cellC - p1, r = e2 - e1;
+    real const denom = (-r[0] * s_[1] + s_[0] * r[1]);
+    if (denom < MEPS)
+        return 0;
+    real const u = (-s_[1] * (p1[0] - e1[0]) + s_[0] * (p1[1] - e1[1])) / denom;
+    real const t = (r[0] * (p1[1] - e1[1]) - r[1] * (p1[0] - e1[0])) / denom;
+    return (u > 0 && u < 1 && t > 0 && t < 1) ? 1 : 0;
+}
+static inline int face_contains_ray(Mesh const& M, std::vector<long> const& face, Vec const& testp)
+{
+    return Crossings2D(M, face, testp);
+}
+static inline int face_cut_by_segment(Mesh const& M, std::vector<long> const& face, Vec const& testp, Vec const& rayp)
+{
+    return get_line_intersection(M, face, testp, rayp);
+}
+#endif
 /* Containment.cpp:385-420; Q7: a negative (or out of range) cell is "not contained" */
 static unsigned CheckCell(Mesh const& M, long cell, Vec const& testp)
 {
     if (cell < 0 || size_t(cell) >= M.size())
         return 0;
-    Vec rayp = testp;
-    rayp[0] += 1e+5;
     unsigned line_flag = 0, inside_flag = 0;
     for (long f : M.cFaces[size_t(cell)])
-        if (Crossings3D(M, M.faces[size_t(f)], testp, rayp))
+        if (face_contains_ray(M, M.faces[size_t(f)], testp))
         {
             inside_flag = !inside_flag;
             if (line_flag)
@@ -1640,7 +1684,7 @@ static std::vector<size_t> FindCell(Orc& o, State& pnp1)
             Vec const rayp = M.cCentre[size_t(index)];
             for (long findex : M.cFaces[size_t(index)])
                 if (M.leftright[size_t(findex)].second < 0)
-                    if (Crossings3D(M, M.faces[size_t(findex)], testp, rayp))
+                    if (face_cut_by_segment(M, M.faces[size_t(findex)], testp, rayp))
                     {
                         cross = !cross;
                         if (M.leftright[size_t(findex)].second == -1)
@@ -1672,7 +1716,7 @@ static void FirstCell(Orc& o, State& S, size_t ii, unsigned& to_del)
 {
     Mesh const& M = o.cells;
     Vec const testp = S.xi[ii];
-    std::vector<long> const ret = nearest_cells(M, testp, 150);
+    std::vector<long> const ret = nearest_cells(M, testp, DIM == 3 ? 150 : 20); /* Containment.cpp:431-436 */
     for (long cell : ret)
         if (CheckCell(M, cell, testp))
         {
@@ -1687,13 +1731,21 @@ static void FirstCell(Orc& o, State& S, size_t ii, unsigned& to_del)
             if (M.leftright[size_t(findex)].second < 0)
             {
                 std::vector<long> const& face = M.faces[size_t(findex)];
-                if (Crossings3D(M, face, testp, rayp))
+                if (face_cut_by_segment(M, face, testp, rayp))
                 {
                     cross = !cross;
                     if (M.leftright[size_t(findex)].second == -1)
                     {
+#if DIM == 3
                         Vec const r1 = M.verts[face[1]] - M.verts[face[0]], r2 = M.verts[face[2]] - M.verts[face[0]];
                         Vec nrm = normalized(cross3(r1, r2));
+#else
+                        Vec const r1 = M.verts[face[1]] - M.verts[face[0]]; /* Containment.cpp:540-544 */
+                        Vec nrm;
+                        nrm[0] = -r1[1];
+                        nrm[1] = r1[0];
+                        nrm = normalized(nrm);
+#endif
                         S.v[ii] = S.v[ii] - (2 * dot(S.v[ii], nrm)) * nrm;
                         real const plane = dot(nrm, M.verts[face[1]]);
                         real const dist = (plane - dot(S.xi[ii], nrm)) / dot(nrm, nrm);
@@ -1707,7 +1759,6 @@ static void FirstCell(Orc& o, State& S, size_t ii, unsigned& to_del)
     if (cross == 0)
         o.first_cell_errors++; /* the reference prints and calls exit(-1) here */
 }
-#endif
 
 static void dSPH_PreStep(Orc& o, size_t end, State& S, real& npd);
 static void update_neighbours(Orc& o, State const& S);
@@ -1716,7 +1767,6 @@ static void update_neighbours(Orc& o, State const& S);
  * the prestep are redone. */
 static void get_aero_velocity_mesh(Orc& o, State& pn, State& pnp1, real& npd)
 {
-#if DIM == 3
     std::vector<size_t> toDelete = FindCell(o, pnp1);
     if (toDelete.empty())
         return;
@@ -1749,9 +1799,6 @@ static void get_aero_velocity_mesh(Orc& o, State& pn, State& pnp1, real& npd)
     o.end_index -= nDel;
     update_neighbours(o, pnp1);
     dSPH_PreStep(o, o.total_points, pnp1, npd);
-#else
-    (void)o; (void)pn; (void)pnp1; (void)npd;
-#endif
 }
 
 static void get_aero_velocity(Orc& o, size_t start, size_t end, State& S)
@@ -1790,7 +1837,6 @@ static void Check_Pipe_Outlet(Orc& o, State& S)
                 if (dot(S.xi[ii], B.aero_norm) > B.aeroconst)
                 {
                     S.b[ii] = ORC_FREE;
-#if DIM == 3
                     if (S.lam_nb[ii] < o.P.lam_cutoff && o.P.asource == meshInfl)
                     {
                         unsigned to_del = 0;
@@ -1798,7 +1844,6 @@ static void Check_Pipe_Outlet(Orc& o, State& S)
                         if (to_del)
                             o.pipe_outlet_del.push_back(size_t(ii));
                     }
-#endif
                 }
     }
     /* Containment.cpp:849-890: erase the particles that left through an outer boundary (pnp1 only) */

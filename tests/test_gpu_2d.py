@@ -103,8 +103,108 @@ def test_dam_2d_deck():
     assert report["acc"] <= 1e-6 and report["Rrho"] <= 1e-6, report
 
 
-def test_2d_rejects_what_it_does_not_run():
-    """2D aero meshes (Crossings2D, TAU edge meshes) are not on the device path: an error, not a wrong answer."""
+def pair_with_mesh_2d(case, mesh, **kw):
+    from oracle import oracle as orc
+
+    params = dict(case["params"], delta_t_min=1e-9, asource=1, **kw)
+    o = orc.Oracle(orc.default_params(2, **params), kind="2d")
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+    o.set_mesh(mesh)
+    e = eng.Engine(eng.default_params(2, **params), case["xi"].shape[0])
+    e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+    e.upload_mesh(mesh)
+    return o, e
+
+
+def test_2d_mesh_sheared_solution_against_oracle():
+    """2D aero mesh (faces are edges): CheckCell on Crossings2D (Geometry.cpp:354-399), FindCell's nearest-centre search;
+    the oracle's 2D containment follows FJSPH's -DSIMDIM=2 objects (tests/test_oracle_vs_reference.py::
+    test_mesh_containment_2d).  Cells identical, then three coupled steps."""
+    case = cases.droplet(dx=0.002, dim=2, jitter=0.05)
+    vel = lambda c: np.stack([21.55 * (1.0 + 4.0 * c[:, 1]), 2.0 * c[:, 0]], axis=1)
+    mesh = cases.quad_mesh((-0.1013, -0.1007), (0.1009, 0.1003), (11, 9), vel=vel, p=lambda c: 100000.0 + 500.0 * c[:, 1],
+                           rho=lambda c: 1.1025 + 0.1 * c[:, 0])
+    o, e = pair_with_mesh_2d(case, mesh)
+    o.update_neighbours(); e.update_neighbours()
+    o.prestep(); e.dSPH_PreStep()
+    o.aero_velocity(); e.get_aero_velocity()
+    got = e.download(("cellID", "cellV", "cellP", "cellRho"))
+    assert np.array_equal(got["cellID"], o.get("cellID"))
+    hit = got["cellID"] >= 0
+    assert hit.sum() > 50 and len(np.unique(got["cellID"][hit])) > 8
+    for f in ("cellV", "cellP", "cellRho"):
+        assert np.array_equal(got[f][hit], o.get(f)[hit]), f
+    for step in range(3):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert se.iterations == so.iterations and abs(se.dt - so.dt) <= 1e-12 * so.dt
+        got = e.download(("cellID", "xi", "v", "rho", "Af", "acc"))
+        assert np.array_equal(got["cellID"], o.get("cellID")), step
+        assert relerr(got["xi"], o.get("xi")) <= 1e-10 and relerr(got["rho"], o.get("rho")) <= 1e-10
+        assert relerr(got["v"], o.get("v")) <= 1e-8
+        assert relerr(got["Af"], o.get("Af")) <= 1e-6 and relerr(got["acc"], o.get("acc")) <= 1e-6
+    assert np.abs(got["Af"]).max() > 1.0
+
+
+@pytest.mark.parametrize("marker", [-2, -1], ids=["outer_boundary", "inner_wall"])
+def test_2d_mesh_boundaries(marker):
+    """A 2D mesh that does not cover the droplet's lower part: the free-surface particles out there are tested against the
+    boundary edges with get_line_intersection (Geometry.cpp:312-341, one-sided denominator test) -- erased across an outer
+    boundary (-2), flagged `internal` across an inner wall (-1) -- as in the oracle."""
+    case = cases.droplet(dx=0.002, dim=2, jitter=0.05)
+    mesh = cases.quad_mesh((-0.1013, -0.0303), (0.1009, 0.1003), (8, 6), vel=(21.55, 0.0), p=100000.0, rho=1.1025,
+                           outer_marker=marker)
+    o, e = pair_with_mesh_2d(case, mesh)
+    n0 = e.n
+    for step in range(3):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert e.n == o.n, step
+        got = e.download(("part_id", "cellID", "internal", "xi", "rho"))
+        assert np.array_equal(got["part_id"], o.get("part_id")), step
+        assert np.array_equal(got["cellID"], o.get("cellID")), step
+        assert np.array_equal(got["internal"], o.get("internal")), step
+        assert relerr(got["xi"], o.get("xi")) <= 1e-10 and relerr(got["rho"], o.get("rho")) <= 1e-10
+    if marker == -2:
+        assert e.n < n0  # something was erased
+    else:
+        assert got["internal"].sum() > 0
+
+
+def test_2d_pipe_outlet_takes_its_first_cell_from_the_mesh():
+    """Check_Pipe_Outlet with a 2D mesh (Containment.cpp:822-847): a PIPE particle crossing the aero plane becomes FREE and
+    FirstCell assigns its cell from the 20 nearest cell centres (150 in 3D)."""
+    from oracle import oracle as orc
+
+    case = cases.inlet_jet(n=(7, 4), fixed=1, jitter=0.03, aero_x=0.5, dim=2)
+    mesh = cases.quad_mesh((-0.0123, -0.0031), (0.0117, 0.0093), (12, 6), vel=(0.0, 30.0), p=100000.0, rho=1.2)
+    params = dict(case["params"], asource=1, acase=1, v_inf=(0.0, 30.0, 0.0), p_ref=100000.0, rho_g=1.2)
+    B = case["block"]
+    o = orc.Oracle(orc.default_params(2, **params), kind="2d")
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], 0)
+    o.lib.orc_clear_blocks(o.h)
+    o.add_block(1, B["first"], B["second"], block_type=6, fixed_vel_or_dynamic=1, insert_norm=B["insert_norm"],
+                insconst=B["insconst"], aero_norm=B["aero_norm"], aeroconst=B["aeroconst"], back=B["back"], buffer=B["buffer"])
+    o.set_mesh(mesh)
+    e = eng.Engine(eng.default_params(2, **params), 4 * case["xi"].shape[0])
+    e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], 0)
+    e.set_blocks([B])
+    e.upload_mesh(mesh)
+    freed = 0
+    for step in range(6):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert (se.n_add, se.total_points, se.iterations) == (so.n_add, so.total_points, so.iterations), step
+        got = e.download(("part_id", "b", "cellID", "xi", "v"))
+        assert np.array_equal(got["part_id"], o.get("part_id")) and np.array_equal(got["b"], o.get("b")), step
+        assert np.array_equal(got["cellID"], o.get("cellID")), step
+        assert relerr(got["xi"], o.get("xi")) <= 1e-10 and relerr(got["v"], o.get("v")) <= 1e-8
+        freed = int((got["b"] == cases.FREE).sum())
+    assert freed > 0 and o.first_cell_errors == 0
+
+
+def test_2d_mesh_must_be_flat():
+    """A 2D engine takes 2D meshes only: a vertex off the z = 0 plane is an error, not a wrong answer."""
     case = block2d(n=(12, 10))
     e = eng.Engine(eng.default_params(2, **case["params"]), case["xi"].shape[0])
     e.upload_state(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"], 0)

@@ -293,3 +293,40 @@ def test_mesh_containment(which):
         assert r.get("internal").sum() > 0
     assert_same(a, r, INTS, 0.0, which)
     assert_same(a, r, FLOATS, 1e-9, which)
+
+
+@pytest.mark.parametrize("which", ["sheared", "inner_wall"])
+def test_mesh_containment_2d(which):
+    """The 2D build's containment: FindCell / CheckCell on Crossings2D (Geometry.cpp:354-399), the boundary test on
+    get_line_intersection (Geometry.cpp:312-341, with its one-sided denominator test), on a quadrilateral mesh whose faces
+    are edges -- a 2D droplet in a sheared stream, and the same droplet cut by an inner wall.  Same cells, `internal` flags,
+    failure counters and aero force as FJSPH's own -DSIMDIM=2 objects."""
+    if not _have("ref2d"):
+        pytest.skip("ref2d")
+    case = cases.droplet(dx=0.004, dim=2, jitter=0.05)
+    if which == "sheared":
+        mesh = cases.quad_mesh((-0.1013, -0.1007), (0.1009, 0.1003), (6, 7), p=100000.0, rho=1.1025,
+                               vel=lambda c: np.stack([21.55 + 0 * c[:, 0], 5 + 20 * c[:, 0]], 1))
+    else:
+        mesh = cases.quad_mesh((-0.1013, -0.03), (0.1009, 0.1003), (6, 5), vel=(21.55, 0.0), p=100000.0, rho=1.1025,
+                               outer_marker=-1)
+    sims = []
+    for kind in ("2d", "ref2d"):
+        o = orc.Oracle(orc.default_params(2, ale=1, asource=1, **dict(case["params"], delta_t_min=1e-9)), kind=kind)
+        o.set_mesh(mesh)
+        o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+        for lvl in (0, 1):
+            o.set("cellID", np.zeros(o.n, dtype=np.int64), lvl)
+        sims.append(o)
+    a, r = sims
+    for step in range(3):
+        _, sa = a.integrate()
+        _, sr = r.integrate()
+        assert (sa.iterations, a.n) == (sr.iterations, r.n), step
+        assert_same(a, r, ("cellID", "internal", "ipt_n_failed"), 0.0, "2D mesh step %d" % step)
+    assert (r.get("cellID") >= 0).sum() > 20 and np.abs(r.get("Af")).max() > 1.0
+    assert len(np.unique(r.get("cellID"))) > 4
+    if which == "inner_wall":
+        assert r.get("internal").sum() > 0
+    assert_same(a, r, INTS, 0.0, "2D " + which)
+    assert_same(a, r, FLOATS, 1e-9, "2D " + which)
