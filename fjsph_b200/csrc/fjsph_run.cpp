@@ -203,7 +203,10 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
         fjsph_case_tau(c, tmesh, tsol, &tscale, 1024);
         if (tmesh[0])
         {
-            if (fjsph_tau_read(tmesh, tsol, tscale, &aero_mesh) || fjsph_foam_view(aero_mesh, &view))
+            /* FJSPH.cpp:72-91: the face-based mesh in 3D, the edge-based one in 2D */
+            if ((dim == 2 ? fjsph_tau_read_edge(tmesh, tsol, tscale, fjsph_case_offset_axis(c), &aero_mesh)
+                          : fjsph_tau_read(tmesh, tsol, tscale, &aero_mesh)) ||
+                fjsph_foam_view(aero_mesh, &view))
                 return fail("reading the TAU mesh");
             std::printf("TAU mesh: %lld cells, %lld faces\n", (long long)view.n_cells, (long long)view.n_faces);
         }

@@ -2110,6 +2110,7 @@ struct FjsphCase
     std::string foam_dir, foam_sol, tau_mesh, tau_bmap, tau_sol; /* IO.cpp:352-354,359-360 */
     double scale = 1.0, angle_alpha = 0.0;     /* IO.cpp:356-357 */
     int foam_buoyant = 0;                      /* IO.cpp:364 */
+    int offset_axis = -1;                      /* IO.cpp:358; -1 = not in the deck: Var.h:99-103 (0 in 3D, 2 in 2D) */
     int64_t bound_points = 0;
     int n_bound_blocks = 0;
     std::vector<double> xi, v, rho, p, m;
@@ -2386,7 +2387,17 @@ static int case_read_impl(const char* para_path, int dim, FjsphCase** out)
             get_string(line, "Boundary mapping filename", c->tau_bmap);
             get_string(line, "Restart-data prefix", c->tau_sol);
             get_number(line, "Angle alpha (degree)", c->angle_alpha);
+            get_number(line, "2D offset vector (0 / x=1,y=2,z=3)", c->offset_axis);
         }
+    }
+    if (c->offset_axis < 0)
+        c->offset_axis = dim == 2 ? 2 : 0;
+    if (dim == 3)
+        c->offset_axis = 0; /* IO.cpp:686-692: a 3D build ignores the 2D setting */
+    else if (c->offset_axis < 1 || c->offset_axis > 3)
+    {
+        fj_set_error(c->offset_axis == 0 ? "Offset axis has not been defined." : "2D offset axis option out of bounds");
+        return FJSPH_ERR_INVALID; /* IO.cpp:694-705 */
     }
     /* aero source, IO.cpp:464-499: a mesh named in the deck couples the aero model to it (meshInfl) */
     c->scale = scale;
@@ -2488,6 +2499,9 @@ extern "C" int64_t fjsph_case_count(const FjsphCase* c) { return c ? int64_t(c->
 extern "C" int64_t fjsph_case_bound_points(const FjsphCase* c) { return c ? c->bound_points : 0; }
 extern "C" int32_t fjsph_case_num_blocks(const FjsphCase* c) { return c ? int32_t(c->limits.size()) : 0; }
 extern "C" int32_t fjsph_case_dim(const FjsphCase* c) { return c ? c->dim : 0; }
+// the para's "2D offset vector" (IO.cpp:358): which axis a 2D case ignores -- picks the velocity components of a TAU
+// solution (fjsph_tau_read_edge); 0 in a 3D case
+extern "C" int32_t fjsph_case_offset_axis(const FjsphCase* c) { return c ? c->offset_axis : 0; }
 // the run-control keys of GetInput the frame loop reads (FJSPH.cpp:262-330): frame count, particle capacity, prefixes
 extern "C" int fjsph_case_io(const FjsphCase* c, int32_t* max_frames, int64_t* max_points, char* output_prefix,
                              char* restart_prefix, int32_t cap)

@@ -101,6 +101,13 @@ class ClassicFile
             throw TauError{path + ": no dimension \"" + name + "\""};
         return len;
     }
+    bool has_variable(const char* name) const
+    {
+        for (const Var& v : vars)
+            if (v.name == name)
+                return true;
+        return false;
+    }
     // a whole variable, converted to T as the library's nc_get_var_<type> does
     template <typename T>
     std::vector<T> variable(const char* name, size_t expect) const
@@ -340,6 +347,161 @@ extern "C" int fjsph_tau_read(const char* mesh_file, const char* solution_file, 
     catch (const std::exception& e)
     {
         fj_set_error("tau_read: %s", e.what());
+        return FJSPH_ERR_IO;
+    }
+}
+
+// TAU 2D meshes (the reference's -DSIMDIM=2 build): TAU::Read_tau_mesh_EDGE + TAU::Read_SOLUTION (reference src/CDFIO.cpp:
+// 992-1097, 828-990, 462-600, 655-822; FJSPH.cpp:85-91) on the edge-based mesh file FJSPH's Cell2Edge writes and a TAU
+// solution file.  Faces are EDGES (points_of_element_edges); the plane of the mesh is given by the coordinate variable the
+// file LACKS (points_xc, points_yc or points_zc: exactly one must be missing); `vertices_in_use` maps every mesh point to
+// its point in the (3D, two-layer) solution file; `offset_axis` (the para's "2D offset vector", 1 = x, 2 = y, 3 = z) picks
+// the two velocity components, independently of the coordinates -- as in the reference.  The result is in the ABI's 3D
+// shape with z = 0 (verts, cCentre, cVel [n][3]), ready for fjsph_upload_mesh on a 2D engine.
+extern "C" int fjsph_tau_read_edge(const char* mesh_file, const char* solution_file, double scale, int32_t offset_axis,
+                                   FjsphFoamMesh** out)
+{
+    if (!mesh_file || !out)
+    {
+        fj_set_error("tau_read_edge: need the mesh file and an output pointer");
+        return FJSPH_ERR_INVALID;
+    }
+    try
+    {
+        std::unique_ptr<FjsphFoamMesh> M(new FjsphFoamMesh());
+        const ClassicFile mesh(mesh_file);
+        const size_t n_elem = mesh.need_dim("no_of_elements"), n_edge = mesh.need_dim("no_of_edges"),
+                     per = mesh.need_dim("points_per_edge"), n_surf = mesh.need_dim("no_of_surfaceelements"),
+                     n_pnts = mesh.need_dim("no_of_points");
+        if (per != 2)
+            throw TauError{"points_per_edge is " + std::to_string(per) + ", expected 2"};
+        const std::vector<int> pts = mesh.variable<int>("points_of_element_edges", n_edge * per);
+        M->face_ptr.push_back(0);
+        for (size_t f = 0; f < n_edge; ++f)
+        {
+            for (size_t k = 0; k < per; ++k)
+            {
+                const int v = pts[f * per + k];
+                if (v < 0 || size_t(v) >= n_pnts)
+                    throw TauError{"points_of_element_edges names point " + std::to_string(v) + " of " + std::to_string(n_pnts)};
+                M->face_vtx.push_back(v);
+            }
+            M->face_ptr.push_back(int64_t(M->face_vtx.size()));
+        }
+        const std::vector<int> used = mesh.variable<int>("vertices_in_use", n_pnts);
+        /* Get_Coordinates, 2D: the variable that is absent names the ignored dimension */
+        const bool hx = mesh.has_variable("points_xc"), hy = mesh.has_variable("points_yc"), hz = mesh.has_variable("points_zc");
+        if (int(!hx) + int(!hy) + int(!hz) > 1)
+            throw TauError{"More than one dimension was not aquired, meaning something went wrong."};
+        if (hx && hy && hz)
+            throw TauError{"The ignored dimension was not found."};
+        const std::vector<double> c0 = mesh.variable<double>(!hx ? "points_yc" : "points_xc", n_pnts),
+                                  c1 = mesh.variable<double>(!hz ? "points_yc" : "points_zc", n_pnts);
+        M->verts.assign(3 * n_pnts, 0.0);
+        for (size_t i = 0; i < n_pnts; ++i)
+        {
+            M->verts[3 * i] = c0[i] * scale;
+            M->verts[3 * i + 1] = c1[i] * scale;
+        }
+        /* Place_Edges */
+        const std::vector<int> left = mesh.variable<int>("left_element_of_edges", n_edge),
+                               right = mesh.variable<int>("right_element_of_edges", n_edge);
+        std::vector<std::vector<size_t>> cFaces(n_elem);
+        size_t n_boundary = 0;
+        M->leftright.resize(2 * n_edge);
+        for (size_t f = 0; f < n_edge; ++f)
+        {
+            if (left[f] < 0 || size_t(left[f]) >= n_elem || right[f] >= int(n_elem))
+                throw TauError{"edge " + std::to_string(f) + " names a cell outside the mesh"};
+            M->leftright[2 * f] = left[f];
+            M->leftright[2 * f + 1] = right[f];
+            cFaces[size_t(left[f])].push_back(f);
+            if (right[f] >= 0)
+                cFaces[size_t(right[f])].push_back(f);
+            else
+                ++n_boundary;
+        }
+        if (n_boundary != n_surf)
+            throw TauError{"Mismatch of number of surface faces identified, and the number given. Identified: " +
+                           std::to_string(n_boundary) + "  Given: " + std::to_string(n_surf)};
+        /* Read_SOLUTION, 2D: point data taken at vertices_in_use */
+        std::vector<double> u(n_pnts, 0.0), w(n_pnts, 0.0), pr(n_pnts, 0.0), rho(n_pnts, 0.0);
+        if (solution_file && solution_file[0])
+        {
+            const ClassicFile sol(solution_file);
+            const size_t sol_pts = sol.need_dim("no_of_points");
+            const char *n0 = nullptr, *n1 = nullptr;
+            if (offset_axis == 1)
+                n0 = "y_velocity", n1 = "z_velocity";
+            else if (offset_axis == 2)
+                n0 = "x_velocity", n1 = "z_velocity";
+            else if (offset_axis == 3)
+                n0 = "x_velocity", n1 = "y_velocity";
+            else
+                throw TauError{"velocities do not have the same number of vertices as the mesh (2D offset vector is " +
+                               std::to_string(offset_axis) + ", expected 1, 2 or 3)"};
+            const std::vector<double> su = sol.variable<double>(n0, sol_pts), sw = sol.variable<double>(n1, sol_pts),
+                                      sp = sol.variable<double>("pressure", sol_pts), sr = sol.variable<double>("density", sol_pts);
+            for (size_t i = 0; i < n_pnts; ++i)
+            {
+                if (used[i] < 0 || size_t(used[i]) >= sol_pts)
+                    throw TauError{"vertices_in_use names point " + std::to_string(used[i]) + " of the solution's " + std::to_string(sol_pts)};
+                const size_t k = size_t(used[i]);
+                u[i] = su[k];
+                w[i] = sw[k];
+                pr[i] = sp[k];
+                rho[i] = sr[k];
+            }
+        }
+        /* Average_Point_Data_to_Cell */
+        M->cell_ptr.push_back(0);
+        M->cCentre.assign(3 * n_elem, 0.0);
+        M->cVel.assign(3 * n_elem, 0.0);
+        M->cP.assign(n_elem, 0.0);
+        M->cRho.assign(n_elem, 0.0);
+        std::vector<size_t> elem;
+        for (size_t c = 0; c < n_elem; ++c)
+        {
+            elem.clear();
+            for (size_t f : cFaces[c])
+            {
+                M->cell_faces.push_back(int64_t(f));
+                for (int64_t k = M->face_ptr[f]; k < M->face_ptr[f + 1]; ++k) elem.push_back(size_t(M->face_vtx[size_t(k)]));
+            }
+            M->cell_ptr.push_back(int64_t(M->cell_faces.size()));
+            std::sort(elem.begin(), elem.end());
+            elem.erase(std::unique(elem.begin(), elem.end()), elem.end());
+            if (elem.empty())
+                throw TauError{"cell " + std::to_string(c) + " has no edges"};
+            const double nv = double(elem.size());
+            Kahan s[6];
+            for (size_t i : elem)
+            {
+                s[0].add(M->verts[3 * i]);
+                s[1].add(M->verts[3 * i + 1]);
+                s[2].add(u[i]);
+                s[3].add(w[i]);
+                s[4].add(pr[i]);
+                s[5].add(rho[i]);
+            }
+            M->cCentre[3 * c] = s[0].sum / nv;
+            M->cCentre[3 * c + 1] = s[1].sum / nv;
+            M->cVel[3 * c] = s[2].sum / nv;
+            M->cVel[3 * c + 1] = s[3].sum / nv;
+            M->cP[c] = s[4].sum / nv;
+            M->cRho[c] = s[5].sum / nv;
+        }
+        *out = M.release();
+        return FJSPH_OK;
+    }
+    catch (const TauError& e)
+    {
+        fj_set_error("tau_read_edge: %s", e.msg.c_str());
+        return FJSPH_ERR_IO;
+    }
+    catch (const std::exception& e)
+    {
+        fj_set_error("tau_read_edge: %s", e.what());
         return FJSPH_ERR_IO;
     }
 }

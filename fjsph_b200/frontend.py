@@ -73,6 +73,20 @@ def read_tau(mesh_file: str, solution_file: str | None = None, scale: float = 1.
     return _mesh_dict(L, h)
 
 
+def read_tau_edge(mesh_file: str, solution_file: str | None = None, scale: float = 1.0, offset_axis: int = 2) -> dict:
+    """TAU::Read_tau_mesh_EDGE + TAU::Read_SOLUTION of the reference's 2D build (reference src/CDFIO.cpp:992-1097,655-822): an
+    edge-based 2D mesh as the mesh dict a 2D Engine.upload_mesh / Oracle.set_mesh take (vector arrays [n,2])."""
+    L = _lib.lib()
+    h = C.c_void_p()
+    L.fjsph_tau_read_edge.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int32, C.POINTER(C.c_void_p)]
+    check(L.fjsph_tau_read_edge(str(mesh_file).encode(), None if not solution_file else str(solution_file).encode(),
+                                float(scale), int(offset_axis), C.byref(h)))
+    m = _mesh_dict(L, h)
+    for k in ("verts", "cCentre", "cVel"):
+        m[k] = np.ascontiguousarray(m[k][:, :2])
+    return m
+
+
 def read_foam(foam_dir: str, solution_dir: str | None = None, buoyant: bool = False, rho_fill: float = 1.29251) -> dict:
     """FOAM::Read_FOAM (reference src/FOAMIO.cpp:943-953) for an OpenFOAM case (ASCII or binary): the mesh dict Engine.upload_mesh and
     Oracle.set_mesh take (verts, face_ptr/face_vtx, leftright, cell_ptr/cell_faces, cCentre, cVel, cP, cRho)."""

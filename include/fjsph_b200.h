@@ -8,7 +8,7 @@
  * Conventions: opaque handle; every function returns 0 on success and a non-zero FjsphStatus on error
  * (text via fjsph_last_error()); never calls exit().  Single-threaded caller, one simulation per handle.
  * All arrays are caller-owned HOST memory, row-major, FP64 / int32 / int64, copied in/out explicitly.
- * Vectors are [n][3] (3D only on the device), L is [n][3][3].  Particle order is the reference's:
+ * Vectors are [n][3], L is [n][3][3], in the 2D build (dim = 2) too: third components 0.  Particle order is the reference's:
  * boundary blocks first, then fluid blocks (Init.cpp:298-475); the engine re-sorts internally and
  * returns everything in the caller's order.
  */
@@ -43,7 +43,8 @@ typedef struct FjsphParams
 {
     /* switches */
     int32_t dim;          /* SIMDIM (VarDefs.h:13-41): 3 or 2.  In 2D every view below keeps its [n][3] / [n][3][3] shape with
-                             the third components 0 (L: third row and column of the identity); aero meshes are 3D only */
+                             the third components 0 (L: third row and column of the identity); a 2D engine takes 2D aero meshes
+                             (faces = edges of two vertices, every z = 0) */
     int32_t ale;          /* 1 = the -DALE binary (shifting, surfzone-gated ST), 0 = the delta-SPH binary */
     int32_t pressure_rel; /* 0 Cole, 1 isothermal (Var.h:203-236, IO.cpp:397) */
     int32_t solver_type;  /* 0 Newmark-Beta, 1 Runge-Kutta (IO.cpp:393) */
@@ -282,6 +283,12 @@ int fjsph_foam_read(const char* foam_dir, const char* solution_dir, int buoyant,
  * boundary marker, cell values = Kahan-summed means of the point data over the cell's vertices; coordinates times `scale`
  * ("Grid scale").  solution_file NULL or "" = mesh only.  Same handle type as fjsph_foam_read (view / free below). */
 int fjsph_tau_read(const char* mesh_file, const char* solution_file, double scale, FjsphFoamMesh** out);
+/* TAU 2D case ingestion (the reference's -DSIMDIM=2 build): TAU::Read_tau_mesh_EDGE + TAU::Read_SOLUTION (reference src/CDFIO.cpp:
+ * 992-1097, 828-990, 655-822; FJSPH.cpp:85-91) on the edge-based mesh FJSPH's Cell2Edge writes.  Faces = edges; the mesh's
+ * plane is named by the coordinate variable the file lacks; `vertices_in_use` maps mesh points to solution points;
+ * offset_axis (the para's "2D offset vector": 1 = x, 2 = y, 3 = z) picks the two velocity components.  The view is in the
+ * ABI's shape with z = 0, for fjsph_upload_mesh on a 2D engine. */
+int fjsph_tau_read_edge(const char* mesh_file, const char* solution_file, double scale, int32_t offset_axis, FjsphFoamMesh** out);
 int fjsph_foam_view(const FjsphFoamMesh* m, FjsphMesh* view);
 void fjsph_foam_free(FjsphFoamMesh* m);
 
@@ -311,6 +318,7 @@ int64_t fjsph_case_count(const FjsphCase* c);
 int64_t fjsph_case_bound_points(const FjsphCase* c);
 int32_t fjsph_case_num_blocks(const FjsphCase* c);
 int32_t fjsph_case_dim(const FjsphCase* c);
+int32_t fjsph_case_offset_axis(const FjsphCase* c); /* "2D offset vector" (IO.cpp:358,686-705): 1 = x, 2 = y, 3 = z; 0 in 3D */
 int fjsph_case_params(const FjsphCase* c, FjsphParams* out);               /* after Set_Values */
 /* run control of the frame loop (FJSPH.cpp:262-330): "SPH frame count", "SPH maximum particle count" (-1 when the deck
  * does not set them), "Output files prefix", "SPH restart prefix" */

@@ -464,3 +464,10 @@ def kernel(r, H, Wc, dim=3) -> float:
 
 def get_n_full(dx, H, dim=3) -> float:
     return float(_load("%dd" % dim).orc_get_n_full(dx, H))
+
+
+def ref_read_tau_edge(o: "Oracle", mesh_file: str, sol_file: str, scale: float = 1.0, offset_axis: int = 2) -> dict:
+    """TAU::Read_tau_mesh_EDGE + TAU::Read_SOLUTION of the 2D build (CDFIO.cpp:992-1097,655-822); returns the mesh."""
+    o.lib.orc_ref_read_tau_edge.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_double, C.c_int]
+    o.lib.orc_ref_read_tau_edge(o.h, os.fsencode(mesh_file), os.fsencode(sol_file), float(scale), int(offset_axis))
+    return ref_mesh(o)

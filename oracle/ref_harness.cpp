@@ -639,6 +639,30 @@ int orc_ref_read_tau(Orc* o, const char* mesh_file, const char* sol_file, double
     return 0;
 }
 #endif
+#if SIMDIM == 2
+/* TAU::Read_tau_mesh_EDGE + TAU::Read_SOLUTION (CDFIO.cpp:992-1097,655-822; FJSPH.cpp:85-91) on an edge-based NetCDF mesh
+ * and a solution file, through the stand-in netcdf.h of shim/; `scale` carries the grid scale, offset_axis the para's
+ * "2D offset vector".  The mesh goes into the handle. */
+int orc_ref_read_tau_edge(Orc* o, const char* mesh_file, const char* sol_file, double scale, int offset_axis)
+{
+    o->svar.io.tau_mesh = mesh_file;
+    o->svar.io.tau_sol = sol_file;
+    o->svar.scale = scale;
+    o->svar.io.offset_axis = unsigned(offset_axis);
+    o->svar.Asource = meshInfl;
+    delete o->cell_tree;
+    o->cell_tree = nullptr;
+    o->cells = MESH();
+    o->cells.maxlength = 0.0;
+    o->cells.minlength = 1e300;
+    vector<uint> used;
+    TAU::Read_tau_mesh_EDGE(o->svar, o->cells, used);
+    TAU::Read_SOLUTION(o->svar, o->svar.io.offset_axis, o->cells, used);
+    o->cell_tree = new Vec_Tree(SIMDIM, o->cells.cCentre, 10);
+    o->cell_tree->index->buildIndex();
+    return 0;
+}
+#endif
 void orc_ref_mesh_sizes(Orc* o, int64_t* out /* verts, faces, cells, face_vtx total, cell_faces total */)
 {
     MESH const& M = o->cells;

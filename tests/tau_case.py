@@ -87,3 +87,71 @@ def write_tau(root, lo, hi, n, vel, p, rho, version=2, wall_marker=-1, outer_mar
                            ("z_velocity", U[:, 2]), ("pressure", [p(x) for x in pts])):
             f.createVariable(name, kind, ("no_of_points",))[:] = np.asarray(data, dtype=kind)
     return mesh_path, sol_path, pts, [f[0] for f in faces], left, right
+
+
+def write_tau_edge(root, lo, hi, n, vel, p, rho, plane="xz", version=2, wall_marker=-1, outer_marker=-2):
+    """A 2D TAU case as FJSPH's Cell2Edge leaves it: rectangle [lo, hi] of n = (nx, ny) quadrilateral cells stored by
+    EDGES (points_of_element_edges, left / right_element_of_edges), the two in-plane coordinates under the names of `plane`
+    ("xz": points_xc + points_zc, the y coordinate absent), and a solution file over the TWO-layer 3D point set the flow
+    solver ran on (2 x the mesh's points) which `vertices_in_use` indexes.  The boundary edges on the lower side carry
+    wall_marker, the others outer_marker.  Returns (mesh path, solution path, points [n,2], edges, left, right, used)."""
+    nx, ny = n
+    xs = [np.linspace(lo[d], hi[d], k + 1) for d, k in enumerate(n)]
+    vid = lambda i, j: j * (nx + 1) + i
+    cid = lambda i, j: j * nx + i
+    pts = np.array([(xs[0][i], xs[1][j]) for j in range(ny + 1) for i in range(nx + 1)])
+    edges = []
+    for j in range(ny):
+        for i in range(nx + 1):
+            e = (vid(i, j), vid(i, j + 1))
+            if i == 0:
+                edges.append((e, cid(0, j), outer_marker))
+            elif i == nx:
+                edges.append((e, cid(nx - 1, j), outer_marker))
+            else:
+                edges.append((e, cid(i - 1, j), cid(i, j)))
+    for j in range(ny + 1):
+        for i in range(nx):
+            e = (vid(i + 1, j), vid(i, j))
+            if j == 0:
+                edges.append((e, cid(i, 0), wall_marker))
+            elif j == ny:
+                edges.append((e, cid(i, ny - 1), outer_marker))
+            else:
+                edges.append((e, cid(i, j - 1), cid(i, j)))
+    left = np.array([e[1] for e in edges], dtype=np.int32)
+    right = np.array([e[2] for e in edges], dtype=np.int32)
+    n_surf = int((right < 0).sum())
+    npt = len(pts)
+    rng = np.random.default_rng(17)
+    used = rng.permutation(2 * npt)[:npt].astype(np.int32)  # where each mesh point sits in the solver's point set
+    mesh_path, sol_path = str(root / "plate.grid.edges"), str(root / "plate.pval")
+    names = {"x": "points_xc", "y": "points_yc", "z": "points_zc"}
+    with netcdf_file(mesh_path, "w", version=version) as f:
+        f.history = "tests/tau_case.py"
+        for name, size in (("no_of_elements", nx * ny), ("no_of_edges", len(edges)), ("points_per_edge", 2),
+                           ("no_of_surfaceelements", n_surf), ("no_of_points", npt)):
+            f.createDimension(name, size)
+        f.createVariable("points_of_element_edges", "i4", ("no_of_edges", "points_per_edge"))[:] = np.array(
+            [e[0] for e in edges], dtype=np.int32)
+        f.createVariable("vertices_in_use", "i4", ("no_of_points",))[:] = used
+        for d, axis in enumerate(plane):
+            v = f.createVariable(names[axis], "f8", ("no_of_points",))
+            v.units = "m"
+            v[:] = pts[:, d]
+        f.createVariable("left_element_of_edges", "i4", ("no_of_edges",))[:] = left
+        f.createVariable("right_element_of_edges", "i4", ("no_of_edges",))[:] = right
+        f.createVariable("boundarymarker_of_surfaces", "i4", ("no_of_surfaceelements",))[:] = np.arange(n_surf, dtype=np.int32) % 4 + 1
+    # the solver's point set: the mesh points scattered over 2 n slots (the other slots: the second layer, other values)
+    sol = {k: rng.normal(size=2 * npt) for k in ("density", "x_velocity", "y_velocity", "z_velocity", "pressure")}
+    U = np.array([vel(x) for x in pts])
+    comp = {"x": "x_velocity", "y": "y_velocity", "z": "z_velocity"}
+    sol[comp[plane[0]]][used] = U[:, 0]
+    sol[comp[plane[1]]][used] = U[:, 1]
+    sol["density"][used] = [rho(x) for x in pts]
+    sol["pressure"][used] = [p(x) for x in pts]
+    with netcdf_file(sol_path, "w", version=version) as f:
+        f.createDimension("no_of_points", 2 * npt)
+        for name, data in sol.items():
+            f.createVariable(name, "f8", ("no_of_points",))[:] = data
+    return mesh_path, sol_path, pts, [e[0] for e in edges], left, right, used

@@ -292,3 +292,25 @@ def test_arc_deck_steps_follow_the_reference_in_2d():
     assert np.array_equal(o.get("surf"), r.get("surf")) and np.array_equal(o.get("b"), r.get("b"))
     for f, tol in (("xi", 1e-14), ("rho", 1e-14), ("v", 1e-13), ("p", 1e-13), ("acc", 1e-13), ("Rrho", 1e-13)):
         assert relerr(o.get(f), r.get(f)) <= tol, (f, relerr(o.get(f), r.get(f)))
+
+
+@pytest.mark.parametrize("plane,offset_axis,version,scale", [("xz", 2, 2, 1.0), ("xy", 3, 1, 0.5), ("yz", 1, 2, 1.0)])
+def test_tau_edge_files_read_like_the_reference(tmp_path, plane, offset_axis, version, scale):
+    """The 2D build's TAU::Read_tau_mesh_EDGE + TAU::Read_SOLUTION (CDFIO.cpp:992-1097,828-990,655-822), compiled unmodified
+    with -DSIMDIM=2 against the stand-in netcdf.h, and fjsph_tau_read_edge on the same files: edges, left / right cells, the
+    cells' edge lists, the in-plane coordinates (the plane named by the coordinate the file lacks), and the Kahan-summed cell
+    centres, velocities (components picked by the 2D offset axis, values taken at vertices_in_use of a two-layer solution),
+    pressures and densities, all bit for bit."""
+    from tests.tau_case import write_tau_edge
+
+    if not _have("ref2d"):
+        pytest.skip("ref2d")
+    vel = lambda x: (1.0 + x[0], 3.0 - x[0] * x[1])
+    mesh, sol, *_ = write_tau_edge(tmp_path, (-0.1013, -0.1007), (0.1009, 0.1003), (7, 6), vel,
+                                   lambda x: 1.0e5 + 10.0 * x[1] + x[0], lambda x: 1.2 + 0.3 * x[1], plane=plane, version=version)
+    mine = frontend.read_tau_edge(mesh, sol, scale=scale, offset_axis=offset_axis)
+    ref = orc.Oracle(orc.default_params(2, ale=1, particle_step=1e-3), kind="ref2d")
+    theirs = orc.ref_read_tau_edge(ref, mesh, sol, scale, offset_axis)
+    for k in ("face_ptr", "face_vtx", "leftright", "cell_ptr", "cell_faces", "verts", "cCentre", "cVel", "cP", "cRho"):
+        assert np.array_equal(mine[k], theirs[k]), k
+    assert mine["verts"].shape[1] == 2 and np.abs(mine["cVel"]).max() > 1.0 and mine["cP"].min() > 9.0e4

@@ -256,3 +256,28 @@ def test_2d_state_after_500_steps():
     print("2D, 500 steps:", {k: "%.1e" % v for k, v in report.items()})
     assert report["xi"] <= 1e-8 and report["rho"] <= 1e-10 and report["v"] <= 1e-7, report
     assert np.abs(o.get("xi") - case["xi"]).max() > 2e-3  # the block really moved
+
+
+def test_2d_coupled_to_a_tau_edge_mesh(tmp_path):
+    """A 2D droplet coupled to a TAU edge-based mesh and its two-layer solution read by fjsph_tau_read_edge (the 2D build's
+    TAU::Read_tau_mesh_EDGE + Read_SOLUTION; pinned against the compiled reference in tests/test_frontend_vs_reference.py):
+    the engine on the read mesh follows the 2D oracle on the same mesh -- cells identical, the cell data on the particles."""
+    from tests.tau_case import write_tau_edge
+
+    vel = lambda x: (21.55 * (1.0 + 2.0 * x[1]), 1.5 * x[0])
+    mesh, sol, *_ = write_tau_edge(tmp_path, (-0.1013, -0.1007), (0.1009, 0.1003), (9, 8), vel,
+                                   lambda x: 1.0e5 + 300.0 * x[1], lambda x: 1.1025 + 0.1 * x[0], plane="xz")
+    tau = frontend.read_tau_edge(mesh, sol, offset_axis=2)
+    case = cases.droplet(dx=0.002, dim=2, jitter=0.05)
+    o, e = pair_with_mesh_2d(case, tau)
+    for step in range(3):
+        _, so = o.integrate()
+        se = e.integrate()
+        assert se.iterations == so.iterations and abs(se.dt - so.dt) <= 1e-12 * so.dt
+        got = e.download(("cellID", "cellV", "cellP", "xi", "rho", "Af", "acc"))
+        assert np.array_equal(got["cellID"], o.get("cellID")), step
+        hit = got["cellID"] >= 0
+        assert np.array_equal(got["cellV"][hit], o.get("cellV")[hit]) and np.array_equal(got["cellP"][hit], o.get("cellP")[hit])
+        assert relerr(got["xi"], o.get("xi")) <= 1e-10 and relerr(got["rho"], o.get("rho")) <= 1e-10
+        assert relerr(got["Af"], o.get("Af")) <= 1e-6 and relerr(got["acc"], o.get("acc")) <= 1e-6
+    assert hit.sum() > 50 and len(np.unique(got["cellID"][hit])) > 8 and np.abs(got["Af"]).max() > 1.0

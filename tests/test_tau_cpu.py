@@ -196,3 +196,48 @@ def test_coupled_run_on_quadrilateral_faces_follows_the_reference(tmp_path):
     assert (a["cellID"][found] != own[found]).sum() > 0.5 * found.sum()
     for f, tol in (("xi", 1e-13), ("rho", 1e-13), ("v", 1e-11), ("Af", 1e-11), ("cellV", 1e-14), ("cellP", 1e-14)):
         assert np.abs(a[f] - b[f]).max() <= tol * max(np.abs(b[f]).max(), 1e-300), f
+
+
+def test_edge_based_2d_mesh_round_trip_and_containment(tmp_path):
+    """fjsph_tau_read_edge (TAU::Read_tau_mesh_EDGE + Read_SOLUTION of the reference's 2D build, CDFIO.cpp:992-1097,655-822)
+    on a written edge-based case in the x-z plane: edges, left / right cells, the scaled in-plane coordinates, cell means of a
+    two-layer solution taken at vertices_in_use (exact for linear fields), and FindCell of the 2D oracle on the result."""
+    from tests.tau_case import write_tau_edge
+
+    lo, hi, n = np.array([-0.1013, -0.1007]), np.array([0.1009, 0.1003]), (7, 6)
+    vel = lambda x: (1.0 + x[0], 3.0 - x[1])
+    pr, rho = (lambda x: 1.0e5 + 10.0 * x[1] + x[0]), (lambda x: 1.2 + 0.3 * x[1])
+    mesh, sol, pts, edges, left, right, used = write_tau_edge(tmp_path, lo, hi, n, vel, pr, rho, plane="xz")
+    m = frontend.read_tau_edge(mesh, sol, scale=1.0, offset_axis=2)
+    nx, ny = n
+    nc = nx * ny
+    assert m["verts"].shape == (len(pts), 2) and np.array_equal(m["verts"], pts)
+    assert np.array_equal(np.diff(m["face_ptr"]), np.full(len(edges), 2)) and np.array_equal(m["face_vtx"], np.asarray(edges).ravel())
+    assert np.array_equal(m["leftright"][:, 0], left) and np.array_equal(m["leftright"][:, 1], right)
+    assert (m["leftright"][:, 1] == -1).sum() == nx and np.array_equal(np.diff(m["cell_ptr"]), np.full(nc, 4))
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    centre = np.empty((nc, 2))
+    centre[(j * nx + i).ravel()] = np.stack([lo[d] + (np.stack([i, j])[d].ravel() + 0.5) * (hi[d] - lo[d]) / n[d] for d in range(2)], axis=1)
+    assert np.allclose(m["cCentre"], centre, rtol=0, atol=1e-15)
+    assert np.allclose(m["cVel"], np.array([vel(x) for x in centre]), rtol=1e-13)
+    assert np.allclose(m["cP"], [pr(x) for x in centre], rtol=1e-14) and np.allclose(m["cRho"], [rho(x) for x in centre], rtol=1e-14)
+    half = frontend.read_tau_edge(mesh, sol, scale=0.5, offset_axis=2)
+    assert np.array_equal(half["verts"], 0.5 * pts)
+    # containment on the 2D oracle: every FREE particle of a 2D droplet lands in its analytic cell
+    case = cases.droplet(dx=0.004, dim=2, jitter=0.05)
+    o = orc.Oracle(orc.default_params(2, asource=1, **dict(case["params"], lam_cutoff=1e9)), kind="2d")
+    o.set_particles(case["xi"], case["v"], case["rho"], case["p"], case["m"], case["b"])
+    o.set_mesh(m)
+    o.update_neighbours()
+    o.prestep()
+    o.aero_velocity()
+    ij = np.floor((case["xi"] - lo) / ((hi - lo) / np.array(n))).astype(int)
+    assert np.array_equal(o.get("cellID"), ij[:, 1] * nx + ij[:, 0])
+    # errors: the plane must be named by exactly one absent coordinate, the offset axis must be 1, 2 or 3
+    with pytest.raises(_lib.FjsphError, match="velocities do not have the same number"):
+        frontend.read_tau_edge(mesh, sol, offset_axis=0)
+    with pytest.raises(_lib.FjsphError, match='no dimension "no_of_elements"'):
+        frontend.read_tau_edge(sol)  # a solution file is not a mesh
+    face_mesh, *_ = write_tau(tmp_path, LO, HI, (2, 2, 2), VEL, PR, RHO)
+    with pytest.raises(_lib.FjsphError, match='no dimension "no_of_edges"'):
+        frontend.read_tau_edge(face_mesh)
