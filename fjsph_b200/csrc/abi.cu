@@ -97,6 +97,14 @@ void fj_refresh_constants(FjsphEngine* e)
     C.W_dx = P.W_dx;
     C.iW_dx = 1.0 / P.W_dx;
     C.gk_fac = 5.0 * P.W_correc / (P.H * P.H);
+    C.mhalf_iH = -0.5 * C.iH;
+    {
+        const double tiny = 1e-12 * P.H;
+        C.tiny2 = tiny * tiny;
+    }
+    C.eps_f = 0.001 * C.H_sq;
+    C.eps_d = 0.0001 * C.H_sq;
+    C.q_st = 0.75 * C.iH;
     C.rho_rest = P.rho_rest;
     C.rho_min = P.rho_min;
     C.rho_max = P.rho_max;

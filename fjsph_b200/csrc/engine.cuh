@@ -53,6 +53,8 @@ struct DevConst
     double lam_cutoff, interp_fac, i_n_full, aero_L, A_sphere, A_plate, mu_g, sos2, gamma_g, ycoef, tab_Cb;
     double max_shift_vel, bnd_mass, sim_mass, c_sound, rho_g;
     int ale, pressure_rel, acase, asource, use_lam, use_TAB_def;
+    /* per-pair constants kept in the constant bank so that the sweeps' loops neither rebuild nor hold them in registers */
+    double mhalf_iH /* -1 / 2H */, tiny2 /* (1e-12 H)^2 */, eps_f /* 0.001 H^2 */, eps_d /* 0.0001 H^2 */, q_st /* 0.75 / H */;
     int dim; /* 2: SIMDIM=2, every z component exactly 0 (records keep their three components) */
 };
 

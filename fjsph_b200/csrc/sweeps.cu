@@ -286,9 +286,8 @@ __device__ __forceinline__ PairGeo pair_geo(const DevConst& C, const double4& pi
         g.rr = fma(ez, ez, fma(ey, ey, ex * ex));
     }
     g.ir = fj_rsqrt3(g.rr);
-    g.t = fma(g.rr * (-0.5 * C.iH), g.ir, 1.0);
-    const double tiny = 1e-12 * C.H;
-    g.gk = (g.rr < tiny * tiny) ? 0.0 : (RAW ? (g.t * g.t) * g.t : (C.gk_fac * g.t) * (g.t * g.t));
+    g.t = fma(g.rr * C.mhalf_iH, g.ir, 1.0);
+    g.gk = (g.rr < C.tiny2) ? 0.0 : (RAW ? (g.t * g.t) * g.t : (C.gk_fac * g.t) * (g.t * g.t));
     return g;
 }
 __device__ __forceinline__ double wend_W_t(const DevConst& C, double t)
@@ -568,7 +567,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
     /* cbar = (sqrt(B gam / rho_i) + sqrt(B gam / rho_j)) / 2, Kernel.h:217-244 */
     const double sqrt_Bgam = sqrt(C.Bgam);
     const double cs_i = DISS ? sqrt(C.Bgam / rho_i) : 0.0;
-    const double eps_d = 0.0001 * C.H_sq; /* Q3: 0.0001 here, 0.001 in the force loop */
+    const double eps_d = C.eps_d; /* 0.0001 H^2 -- Q3: 0.0001 here, 0.001 in the force loop */
     double nx = 0, ny = 0, nz = 0;
     double avx = 0, avy = 0, avz = 0, Rrhod = 0;
     const double cos_pi4 = 0.70710678118654757;
@@ -1172,9 +1171,9 @@ __global__ void __launch_bounds__(WARPS * 32, FJ_FORCE_MINB)
     const int b_i = S.b[i];
     const bool do_st = ALE ? (S.surfzone[i] == 1) : true;
     const double st_bound_fac = 1.0 + 0.5 * cos(0.5 * FJ_PI * 7.0 / 9.0);
-    const double eps_f = 0.001 * C.H_sq;
+    const double eps_f = C.eps_f; /* 0.001 H^2 */
     const double nu_irho_i = C.nu * irho_i;
-    const double q_st = 0.75 * C.iH; /* cos(3 pi/4 r/H) = cospi(0.75 r/H) */
+    const double q_st = C.q_st; /* cos(3 pi/4 r/H) = cospi(0.75 r/H) */
 
     /* pair sums, all in units of 5 Wc / H^2 (applied after the walk) */
     double ax = 0, ay = 0, az = 0;       /* acc_ (pressure) + visc_ + the pair part of acc_ale_ */
