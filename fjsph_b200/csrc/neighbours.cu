@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(FJ_ROW_WARPS * 32)
         srows[W] = min(kk, scap);
         if (kk > scap)
             atomicMax(flag, kk);
+        atomicMax(flag + 1, kk); /* the most slots any warp uses: what the exact runs (a subset, slot for slot) can need */
     }
 }
 
@@ -497,8 +498,10 @@ static int ensure_row_capacity(FjsphEngine* e, size_t n_rows)
     return FJSPH_OK;
 }
 
-// run arrays for n_warp work warps with scap skin slots (and as many exact slots) per warp; the per-warp partials of the
-// prestep's npd sum live in e->red, which grows with the warps
+// Run arrays for n_warp work warps.  The skin runs are sized for the worst case (scap slots per warp: every neighbouring
+// row of the disc, every class); the exact runs -- a subset of the skin runs, slot for slot -- for the most slots any warp
+// was SEEN to use in the skin build (ensure_exact_capacity, after it).  The per-warp partials of the prestep's npd sum live
+// in e->red, which grows with the warps.
 static int ensure_run_capacity(FjsphEngine* e, size_t n_warp, int scap)
 {
     if (n_warp > e->run_warps_cap || scap > e->scap)
@@ -515,19 +518,18 @@ static int ensure_run_capacity(FjsphEngine* e, size_t n_warp, int scap)
         const size_t slots = nw * size_t(scap) * 32u;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        if (slots * 12u + (64u << 20) > free_b)
+        if (slots * 4u + (64u << 20) > free_b)
         {
             fj_set_error("neighbour runs need %.1f GB (%zu work warps x %d row slots) but %.1f GB are free: rows too short "
                          "for this layout (a sheet of particles across the row axis?)",
-                         slots * 12.0 / 1e9, nw, scap, free_b / 1e9);
+                         slots * 4.0 / 1e9, nw, scap, free_b / 1e9);
             return FJSPH_ERR_CAPACITY;
         }
         FJ_CUDA(cudaMalloc(&e->srun, slots * sizeof(unsigned)));
-        FJ_CUDA(cudaMalloc(&e->erun, slots * sizeof(uint2)));
         FJ_CUDA(cudaMalloc(&e->srows, nw * sizeof(int)));
         FJ_CUDA(cudaMalloc(&e->erows, nw * sizeof(int)));
         e->run_warps_cap = nw;
-        e->scap = e->ecap = scap;
+        e->scap = scap;
     }
     if (n_warp + 16 > e->red_cap)
     {
@@ -539,6 +541,30 @@ static int ensure_run_capacity(FjsphEngine* e, size_t n_warp, int scap)
         FJ_CUDA(cudaMalloc(&e->red, want * sizeof(double)));
         e->red_cap = want;
     }
+    return FJSPH_OK;
+}
+
+static int ensure_exact_capacity(FjsphEngine* e, int slots_used)
+{
+    const int want = std::max(slots_used, 1);
+    if (e->erun && want <= e->ecap)
+        return FJSPH_OK;
+    if (e->erun)
+        cudaFree(e->erun);
+    e->erun = nullptr;
+    e->ecap = 0;
+    const int ecap = std::min(e->scap, want + want / 8 + 2); /* a margin, so that a slowly growing fluid does not reallocate at every build */
+    const size_t slots = e->run_warps_cap * size_t(ecap) * 32u;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (slots * sizeof(uint2) + (64u << 20) > free_b)
+    {
+        fj_set_error("neighbour runs need %.1f GB (%zu work warps x %d row slots) but %.1f GB are free", slots * 8.0 / 1e9,
+                     e->run_warps_cap, ecap, free_b / 1e9);
+        return FJSPH_ERR_CAPACITY;
+    }
+    FJ_CUDA(cudaMalloc(&e->erun, slots * sizeof(uint2)));
+    e->ecap = ecap;
     return FJSPH_OK;
 }
 
@@ -739,7 +765,7 @@ static int rebuild_skin(FjsphEngine* e)
         st = ensure_run_capacity(e, e->n_warp, scap);
         if (st)
             return st;
-        FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->stream));
+        FJ_CUDA(cudaMemsetAsync(e->d_flag, 0, 2 * sizeof(int), e->stream));
         const RowMap M = fj_row_map(e, 0, three ? 2 : 1);
         {
             KScope ks(e, "nb_skin", 1);
@@ -748,10 +774,13 @@ static int rebuild_skin(FjsphEngine* e)
                 e->srows, e->d_flag);
         }
         FJ_CUDA(cudaGetLastError());
-        FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        FJ_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
         FJ_CUDA(cudaStreamSynchronize(e->stream));
         if (e->h_flag[0] == 0)
         {
+            st = ensure_exact_capacity(e, e->h_flag[1]);
+            if (st)
+                return st;
             e->skin_valid = true;
             e->skin_n = e->n;
             e->skin_builds++;
