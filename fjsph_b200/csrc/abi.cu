@@ -717,6 +717,8 @@ int fjsph_create(const FjsphParams* p, int device, int64_t capacity, FjsphEngine
         e->list_stats = std::atoi(v) != 0;
     if (const char* v = std::getenv("FJSPH_B200_SWEEP_WARPS"))
         e->sweep_warps = (std::atoi(v) == 8) ? 8 : 4;
+    if (const char* parts = std::getenv("FJSPH_B200_UPLOAD_PARTS")) /* 2: fjsph_step_host uploads x | the rest (no early prestep) */
+        e->upload_parts = std::atoi(parts) == 2 ? 2 : 3;
     if (const char* split = std::getenv("FJSPH_B200_SPLIT_SURFACE"))
         e->split_surface_sweep = std::string(split) != "0";
     if (const char* v = std::getenv("FJSPH_B200_SPLIT_BELOW")) /* near-surface warp fraction below which the sweep splits */
@@ -783,6 +785,7 @@ int fjsph_destroy(FjsphEngine* e)
         cudaStreamSynchronize(e->upload_stream);
         cudaStreamDestroy(e->upload_stream);
         cudaEventDestroy(e->ev_upload_x);
+        cudaEventDestroy(e->ev_upload_b);
         cudaEventDestroy(e->ev_upload);
     }
     if (e->slab.comm_stream)
@@ -992,8 +995,14 @@ static int upload_state_split(FjsphEngine* e, const FjsphStateView* s, int64_t b
     {
         FJ_CUDA(cudaStreamCreateWithFlags(&e->upload_stream, cudaStreamNonBlocking));
         FJ_CUDA(cudaEventCreateWithFlags(&e->ev_upload_x, cudaEventDisableTiming));
+        FJ_CUDA(cudaEventCreateWithFlags(&e->ev_upload_b, cudaEventDisableTiming));
         FJ_CUDA(cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming));
     }
+    /* Three parts when the host hands over none of the fields dSPH_PreStep writes (gradRho, lam, norm, surf, lam_nb, the
+       colour terms, pDist, L): x | rho, m, b -- all the prestep reads -- | the rest.  The step then runs the neighbour build
+       beside part two and the prestep beside part three (fj_integrate_no_update). */
+    const bool early = e->upload_parts == 3 && !s->gradRho && !s->lam && !s->norm && !s->surf && !s->lam_nb && !s->colourG && !s->colour && !s->kernsum &&
+                       !s->pDist && !s->L;
     e->list_valid = false;
     {
         int64_t next = s->n;
@@ -1007,7 +1016,15 @@ static int upload_state_split(FjsphEngine* e, const FjsphStateView* s, int64_t b
     e->launches += 1;
     k_init_level<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[1], e->oidx, e->C, e->P.rho_g, e->P.p_ref, n);
     FJ_CUDA(cudaGetLastError());
-    /* first half: positions */
+    if (early)
+    {
+        /* pn = pnp1 (Init.cpp:496) for the fields the prestep will overwrite in pnp1: their upload-time values are the
+           defaults just set, so pn takes them now; the other fields follow when the upload is complete */
+        int stc = fj_copy_level(e, 0, 1, 1);
+        if (stc)
+            return stc;
+    }
+    /* first part: positions */
     FjsphStateView xs;
     std::memset(&xs, 0, sizeof(xs));
     xs.n = s->n;
@@ -1017,7 +1034,8 @@ static int upload_state_split(FjsphEngine* e, const FjsphStateView* s, int64_t b
     if (st)
         return st;
     FJ_CUDA(cudaEventRecord(e->ev_upload_x, e->stream));
-    /* second half: everything else, then pn = pnp1 (Init.cpp:496), on the upload stream behind the positions */
+    /* the other fields on the upload stream behind the positions: what the prestep reads first (three-part upload), then
+       the rest; in the two-part form pn = pnp1 (Init.cpp:496) follows on the same stream */
     FjsphStateView rest = *s;
     rest.xi = nullptr;
     FJ_CUDA(cudaStreamWaitEvent(e->upload_stream, e->ev_upload_x, 0));
@@ -1025,8 +1043,24 @@ static int upload_state_split(FjsphEngine* e, const FjsphStateView* s, int64_t b
     const bool timers = e->timers_on;
     e->timers_on = false; /* the lazily resolved event timers belong to the engine's stream */
     e->stream = e->upload_stream;
-    st = upload_fields(e, 1, &rest, false, &stage_off);
+    if (early)
+    {
+        FjsphStateView second;
+        std::memset(&second, 0, sizeof(second));
+        second.n = s->n;
+        second.rho = s->rho;
+        second.m = s->m;
+        second.b = s->b;
+        rest.rho = nullptr;
+        rest.m = nullptr;
+        rest.b = nullptr;
+        st = upload_fields(e, 1, &second, false, &stage_off);
+        if (!st && cudaEventRecord(e->ev_upload_b, e->upload_stream) != cudaSuccess)
+            st = FJSPH_ERR_CUDA;
+    }
     if (!st)
+        st = upload_fields(e, 1, &rest, false, &stage_off);
+    if (!st && !early)
         st = fj_copy_level(e, 0, 1);
     e->stream = main_stream;
     e->timers_on = timers;
@@ -1037,6 +1071,7 @@ static int upload_state_split(FjsphEngine* e, const FjsphStateView* s, int64_t b
     }
     FJ_CUDA(cudaEventRecord(e->ev_upload, e->upload_stream));
     e->upload_pending = true;
+    e->upload_early = early;
     return FJSPH_OK;
 }
 
@@ -1282,6 +1317,7 @@ int fjsph_step_host(FjsphEngine* e, const FjsphStateView* in, int64_t bound_poin
         cudaStreamSynchronize(e->upload_stream);
         e->upload_pending = false;
     }
+    e->upload_early = false;
     if (st)
         return st;
     return fjsph_download_state(e, 1, out);

@@ -264,8 +264,10 @@ struct FjsphEngine
     // engine's stream, everything else on upload_stream; upload_pending tells fj_integrate_no_update to run the build
     // ahead of find_timestep and to make the engine's stream wait for ev_upload before anything reads the other fields.
     cudaStream_t upload_stream = nullptr;
-    cudaEvent_t ev_upload_x = nullptr, ev_upload = nullptr;
+    cudaEvent_t ev_upload_x = nullptr, ev_upload_b = nullptr, ev_upload = nullptr;
     bool upload_pending = false;
+    int upload_parts = 3;      /* FJSPH_B200_UPLOAD_PARTS=2 keeps the two-part upload */
+    bool upload_early = false; /* three-part upload: the prestep may run as soon as x, rho, m, b are in (ev_upload_b) */
     // fused surface / shifting sweep in two launches (lean bulk + near-surface rest) when few warps are near a surface
     // (sweeps.cu, k_surf23_shift CLASS; FJSPH_B200_SPLIT_SURFACE=0 keeps the single launch)
     bool split_surface_sweep = true;
@@ -351,7 +353,7 @@ int fj_nb_iter(FjsphEngine* e, double npd, double* errsum);
 int fj_find_timestep(FjsphEngine* e, double* dt);
 int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s);
 int fj_step(FjsphEngine* e, FjsphStepStats* s);
-int fj_copy_level(FjsphEngine* e, int dst, int src);
+int fj_copy_level(FjsphEngine* e, int dst, int src, int which = 0); /* which: 0 all fields | 1 the prestep's outputs | 2 the rest */
 int fj_permute_levels(FjsphEngine* e);
 int fj_reduce_sum(FjsphEngine* e, int nblocks, int ncomp, double* out_host);
 void fj_refresh_constants(FjsphEngine* e);

@@ -429,15 +429,49 @@ __global__ void __launch_bounds__(TPB)
         err_partial[blockIdx.x] = tot;
 }
 
-__global__ void k_copy_level(Level in, Level out, int n)
+// which: 0 = every field; 1 = only what dSPH_PreStep writes (P3 = gradRho + lam, NP = its normal + lam_nb, SC = colour
+// terms, L); 2 = every field but those
+__global__ void k_copy_level(Level in, Level out, int n, int which)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-#define X(T, f) out.f[i] = in.f[i];
-    FJ_LEVEL_FIELDS(X)
-#undef X
+    if (which != 2)
+    {
+        out.P3[i] = in.P3[i];
+        out.NP[i] = in.NP[i];
+        out.SC[i] = in.SC[i];
+        out.L0[i] = in.L0[i];
+        out.L1[i] = in.L1[i];
+        out.L2[i] = in.L2[i];
+        out.L3[i] = in.L3[i];
+        out.L4[i] = in.L4[i];
+        out.L5[i] = in.L5[i];
+        out.L6[i] = in.L6[i];
+        out.L7[i] = in.L7[i];
+        out.L8[i] = in.L8[i];
+    }
+    if (which != 1)
+    {
+        out.P0[i] = in.P0[i];
+        out.P1[i] = in.P1[i];
+        out.P2[i] = in.P2[i];
+        out.P4[i] = in.P4[i];
+        out.ACC[i] = in.ACC[i];
+        out.AF[i] = in.AF[i];
+        out.AV[i] = in.AV[i];
+        out.CV[i] = in.CV[i];
+        out.BN[i] = in.BN[i];
+        out.TH[i] = in.TH[i];
+        out.part_id[i] = in.part_id[i];
+        out.cellID[i] = in.cellID[i];
+        out.b[i] = in.b[i];
+        out.surfzone[i] = in.surfzone[i];
+        out.internal[i] = in.internal[i];
+        out.surf_i[i] = in.surf_i[i];
+    }
 }
+static_assert(sizeof(Level) == 28 * sizeof(void*), "k_copy_level lists the fields of a Level by name: keep it in step with FJ_LEVEL_FIELDS");
 
 BlockTable make_block_table(FjsphEngine* e)
 {
@@ -487,14 +521,21 @@ int fj_upload_wait(FjsphEngine* e)
     }
     return FJSPH_OK;
 }
+// ... and for the fields dSPH_PreStep reads (x, rho, m, b), which cross PCIe ahead of the rest (three-part upload)
+static int upload_wait_prestep_inputs(FjsphEngine* e)
+{
+    if (e->upload_pending)
+        FJ_CUDA(cudaStreamWaitEvent(e->stream, e->ev_upload_b, 0));
+    return FJSPH_OK;
+}
 
-int fj_copy_level(FjsphEngine* e, int dst, int src)
+int fj_copy_level(FjsphEngine* e, int dst, int src, int which)
 {
     const int n = int(e->n);
     KScope ks(e, "copy_level", 1);
     if (dst == 1)
         e->x_moved = true; /* pnp1's positions may differ from the ones the list was built on: pair sweeps take r from x0 */
-    k_copy_level<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[src], e->lv[dst], n);
+    k_copy_level<<<fj_blocks(n, TPB), TPB, 0, e->stream>>>(e->lv[src], e->lv[dst], n, which);
     FJ_CUDA(cudaGetLastError());
     return FJSPH_OK;
 }
@@ -611,9 +652,9 @@ int fj_nb_iter(FjsphEngine* e, double npd, double* errsum)
     return FJSPH_OK;
 }
 
-static int frozen_terms(FjsphEngine* e, bool all)
+static int frozen_terms(FjsphEngine* e, bool all, bool prestep_done = false)
 {
-    int st = fj_prestep(e, nullptr);
+    int st = prestep_done ? FJSPH_OK : fj_prestep(e, nullptr);
     if (st || !all)
         return st;
     st = fj_aero_velocity(e); /* reads and writes particle i only: ahead of the exchange so that the surface sweep's
@@ -718,6 +759,7 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
      * keeps the global count), so it is read where it is used */
     #define nfluid fj_fluid_count(e)
 
+    bool prestep_done = false;
     if (e->upload_pending)
     {
         /* fjsph_step_host: only the positions are on the device yet.  The list needs nothing else and the time step does
@@ -725,9 +767,30 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
         st = fj_build_neighbours(e);
         if (st)
             return st;
+        if (e->upload_early)
+        {
+            /* three-part upload: x, rho, m and b are here, the rest is still crossing.  dSPH_PreStep reads nothing else and
+               neither it nor find_timestep depends on the other, so it runs now, beside the rest of the upload; pn = pnp1
+               (Init.cpp:496) follows once everything has landed, for every field but the ones the prestep has just written
+               -- those went to pn with their upload-time values before it ran (upload_state_split). */
+            st = upload_wait_prestep_inputs(e);
+            if (st)
+                return st;
+            st = fj_prestep(e, nullptr);
+            if (st)
+                return st;
+            prestep_done = true;
+        }
         st = fj_upload_wait(e);
         if (st)
             return st;
+        if (e->upload_early)
+        {
+            e->upload_early = false;
+            st = fj_copy_level(e, 0, 1, 2);
+            if (st)
+                return st;
+        }
         st = fj_find_timestep(e, &e->P.delta_t);
         if (st)
             return st;
@@ -747,7 +810,7 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
         /* ---- Runge-Kutta.  Get_First_RK builds st_1 from part_n = part_prev = pn (Runge_Kutta.cpp:462-476),
          * overwriting pnp1, so of the first frozen-term pass only npd (and the neighbour list) survives:
          * the prestep runs, the surface/dissipation/shifting passes are dead work and are skipped. */
-        st = frozen_terms(e, false);
+        st = frozen_terms(e, false, prestep_done);
         if (st)
             return st;
         st = fj_copy_level(e, 1, 0);
@@ -821,7 +884,7 @@ int fj_integrate_no_update(FjsphEngine* e, FjsphStepStats* s)
     else
     {
         /* ---- Newmark-Beta */
-        st = frozen_terms(e, true);
+        st = frozen_terms(e, true, prestep_done);
         if (st)
             return st;
         double errsum = 0.0;
