@@ -358,12 +358,15 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
         double l00 = 0, l01 = 0, l02 = 0, l11 = 0, l12 = 0, l22 = 0;
         double n00 = 0, n01 = 0, n02 = 0, n11 = 0, n12 = 0, n22 = 0;
         double g0 = 0, g1 = 0, g2 = 0, m0 = 0, m1 = 0, m2 = 0;
-        double kernsum = C.W_correc; /* self term, Shifting.cpp:39-45 */
+        /* Every sum below is linear in the kernel's constants: the pair loop takes gk = t^3 and W = t^4 (5 - 4 t), and
+           5 Wc / H^2 and Wc are applied once after the walk (two FP64 multiplications less per pair; the kernel sum and the
+           npd sum are the same sum, kept once). */
+        double ksum = 0.0; /* sum_j W' over fluid neighbours: kernsum = Wc (1 + ksum), Shifting.cpp:39-45; npd = Wc ksum */
         double colour = 0.0;
         auto pair = [&](const RecPre& q, const bool take) {
             const double4 pj = q.p;
-            const PairGeo g = pair_geo<FROZEN>(C, pi, x0i, pj, q.x0);
-            const double vg = pj.w * g.gk; /* V_j * gk ; Grad = GradK(-Rji) = -Rji*gk; 0 for a lane's own index */
+            const PairGeo g = pair_geo<FROZEN, true>(C, pi, x0i, pj, q.x0);
+            const double vg = pj.w * g.gk; /* V_j * t^3 ; Grad = GradK(-Rji) = -Rji*gk; 0 for a lane's own index */
             const double ax = vg * g.rx, ay = vg * g.ry, az = vg * g.rz;
             /* Lmat -= V Rji (x) Grad  ==  += V gk Rji (x) Rji */
             l00 = fma(ax, g.rx, l00);
@@ -388,10 +391,10 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
             m0 -= fx;
             m1 -= fy;
             m2 -= fz;
-            const double W_ = fl ? wend_W_t(C, g.t) : 0.0;
-            kernsum += W_;
+            const double t2 = g.t * g.t;
+            const double W_ = fl ? (t2 * t2) * fma(-4.0, g.t, 5.0) : 0.0;
+            ksum += W_;
             colour = fma(pj.w, W_, colour);
-            npd_ += W_;
         };
         for_neighbours2(
             lv, W, active, unsigned(i),
@@ -417,8 +420,29 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
                     stage_span(lv.x0, first, last);
                 }
             });
+        npd_ = C.W_correc * ksum;
         if (active)
         {
+        const double kernsum = fma(C.W_correc, ksum, C.W_correc);
+        colour *= C.W_correc;
+        l00 *= C.gk_fac;
+        l01 *= C.gk_fac;
+        l02 *= C.gk_fac;
+        l11 *= C.gk_fac;
+        l12 *= C.gk_fac;
+        l22 *= C.gk_fac;
+        n00 *= C.gk_fac;
+        n01 *= C.gk_fac;
+        n02 *= C.gk_fac;
+        n11 *= C.gk_fac;
+        n12 *= C.gk_fac;
+        n22 *= C.gk_fac;
+        g0 *= C.gk_fac;
+        g1 *= C.gk_fac;
+        g2 *= C.gk_fac;
+        m0 *= C.gk_fac;
+        m1 *= C.gk_fac;
+        m2 *= C.gk_fac;
         double Lm[3][3] = {{l00, l01, l02}, {l01, l11, l12}, {l02, l12, l22}};
         double Li[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
         if (C.dim == 2)
@@ -565,8 +589,9 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
     const bool hi_lam = lam_i > 0.7;
     const double lam_ref = hi_lam ? lam_i : 0.0;
     /* cbar = (sqrt(B gam / rho_i) + sqrt(B gam / rho_j)) / 2, Kernel.h:217-244 */
-    const double sqrt_Bgam = sqrt(C.Bgam);
-    const double cs_i = DISS ? sqrt(C.Bgam / rho_i) : 0.0;
+    /* the pair loop works in units of the sums' constants (gk = t^3, cbar in units of sqrt(B gam) / 2, ...): they are applied
+       once after the walk -- six FP64 instructions less per pair */
+    const double rs_i = DISS ? 1.0 / sqrt(rho_i) : 0.0; /* c_i / sqrt(B gam) */
     const double eps_d = C.eps_d; /* 0.0001 H^2 -- Q3: 0.0001 here, 0.001 in the force loop */
     double nx = 0, ny = 0, nz = 0;
     double avx = 0, avy = 0, avz = 0, Rrhod = 0;
@@ -576,8 +601,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
     auto pair = [&](const RecS1& q, const bool take, PairGeo& g) {
         const double4 pj = q.p;
         const double4 gj = q.g;
-        g = pair_geo<FROZEN>(C, pi, x0i, pj, q.x0);
-        const double vg = pj.w * g.gk; /* 0 for a lane's own index */
+        g = pair_geo<FROZEN, true>(C, pi, x0i, pj, q.x0);
+        const double vg = pj.w * g.gk; /* V_j t^3; 0 for a lane's own index */
         if (SURF)
         {
             /* normal from the eigenvalue gradient, GradK(Rij = xi - xj) = -Rji*gk (Geometry.cpp:109-137) */
@@ -595,17 +620,16 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
             const double drho = rho_j - rho_i;
             const bool fl = q.b > FJSPH_PISTON;
             const double vdotr = (vj.x - vi.x) * g.rx + (vj.y - vi.y) * g.ry + (vj.z - vi.z) * g.rz;
-            /* ArtVisc = 0 when Vji.Rji > 0, and for a non-fluid neighbour (selects, no branches) */
-            const double muij = C.H * vdotr * idist2;
-            const double cbar = 0.5 * (cs_i + sqrt_Bgam * fj_rsqrt3(rho_j));
-            /* m_j gk alpha cbar mu / rhobar, m_j = rho_j V_j, rhobar = (rho_i + rho_j)/2 */
-            double f = (rho_j * vg) * (C.visc_alpha * cbar) * muij * fj_rcp1(0.5 * (rho_i + rho_j));
+            /* ArtVisc = 0 when Vji.Rji > 0, and for a non-fluid neighbour (selects, no branches).
+               m_j gk alpha cbar mu / rhobar with m_j = rho_j V_j, mu = H Vji.Rji idist2, cbar = sqrt(B gam) (rho_i^-1/2 +
+               rho_j^-1/2) / 2, rhobar = (rho_i + rho_j) / 2: the constants 5 Wc / H^2 * alpha * sqrt(B gam) * H after the walk */
+            double f = (rho_j * vg) * (rs_i + fj_rsqrt3(rho_j)) * (vdotr * idist2) * fj_rcp1(rho_i + rho_j);
             f = (vdotr > 0.0 || !fl) ? 0.0 : f;
             avx = fma(f, g.rx, avx);
             avy = fma(f, g.ry, avy);
             avz = fma(f, g.rz, avz);
             const double gdot = (gi.x + gj.x) * g.rx + (gi.y + gj.y) * g.ry + (gi.z + gj.z) * g.rz;
-            Rrhod = fma(drho + (fl ? 0.5 * gdot : 0.0), w, Rrhod);
+            Rrhod = fma(fma(0.5, fl ? gdot : 0.0, drho), w, Rrhod);
         }
     };
     /* Detect_Surface's cone test (Geometry.cpp:60-103): only particles with 0.2 <= lam_nb < 0.75 */
@@ -675,6 +699,9 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         });
     if (SURF)
     {
+        nx *= C.gk_fac;
+        ny *= C.gk_fac;
+        nz *= C.gk_fac;
         const double tx = S.L0[i] * nx + S.L1[i] * ny + S.L2[i] * nz;
         const double ty = S.L3[i] * nx + S.L4[i] * ny + S.L5[i] * nz;
         const double tz = S.L6[i] * nx + S.L7[i] * ny + S.L8[i] * nz;
@@ -710,13 +737,14 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
     }
     if (DISS && active)
     {
+        const double k_av = C.gk_fac * C.visc_alpha * sqrt(C.Bgam) * C.H;
         double4 av = S.AV[i];
-        av.x = avx;
-        av.y = avy;
-        av.z = avz;
+        av.x = k_av * avx;
+        av.y = k_av * avy;
+        av.z = k_av * avz;
         S.AV[i] = av;
         double4 af = S.AF[i];
-        af.w = C.dsph_cont * Rrhod;
+        af.w = (C.dsph_cont * C.gk_fac) * Rrhod;
         S.AF[i] = af;
     }
 }
@@ -813,6 +841,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
     /* with the stage entry point surfzone is already known; fused, it is this loop's `zone` */
     const bool known_bulk = SHIFT && !SURF23 && (S.surfzone[i] == 0) && (lam_nb > 0.55);
     double dux = 0, duy = 0, duz = 0, maxU2 = 0.0;
+    const double kq_fac = C.W_correc * C.iW_dx;
     /* max_j acos(c_j) over c_j in [-1,1] == acos(min_j c_j); NaNs (|c|>1) are skipped by the reference's '>' */
     double min_c = 2.0;
     const bool need_pos = (SURF23 && (ni_nz || need_occl)) || do_shift;
@@ -822,7 +851,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
         const double4 nj = q.n;
         zone |= (take && nj.w != 0.0) ? 1 : 0;
         const double4 pj = q.p;
-        const PairGeo g = pair_geo<FROZEN>(C, pi, x0i, pj, q.x0);
+        const PairGeo g = pair_geo<FROZEN, true>(C, pi, x0i, pj, q.x0); /* gk = t^3: 5 Wc / H^2 once after the walk */
         if (SURF23)
         {
             if (CLASS != 1)
@@ -842,8 +871,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
         if (SHIFT)
         {
             const double4 vj = q.v;
-            const double W_ = wend_W_t(C, g.t);
-            const double kq = W_ * C.iW_dx;
+            const double t2 = g.t * g.t;
+            const double kq = ((t2 * t2) * fma(-4.0, g.t, 5.0)) * kq_fac; /* W(r) / W(dx) */
             const double kq2 = kq * kq;
             const double f = take ? fma(0.2, kq2 * kq2, 1.0) * g.gk * pj.w : 0.0;
             dux = fma(f, g.rx, dux);
@@ -920,7 +949,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
         np.z = ni.z;
         S.NP[i] = np; /* pi.norm = norms[ii] */
         double4 av = S.AV[i];
-        av.w = curve;
+        av.w = C.gk_fac * curve;
         S.AV[i] = av;
         double4 sc = S.SC[i];
         sc.w = S.P3[i].w; /* pDist = lam */
@@ -940,7 +969,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
         const int surfzone = SURF23 ? zone : S.surfzone[i];
         const bool bulk = (surfzone == 0) && (lam_nb > 0.55);
         const double vnorm = sqrt(vi.x * vi.x + vi.y * vi.y + vi.z * vi.z);
-        const double sc = -2.0 * C.H * vnorm;
+        const double sc = (-2.0 * C.H * C.gk_fac) * vnorm;
         dux *= sc;
         duy *= sc;
         duz *= sc;
