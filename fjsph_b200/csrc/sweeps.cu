@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
 struct RecS2
 {
     double4 n, p, v, x0;
-    int b;
+    int b, s; /* s: the surf flag as the lean class reads it (an int: no conversion, no FP64 compare per pair) */
 };
 
 #ifndef FJ_FUSE_SHIFT
@@ -849,7 +849,10 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
     /* one pair, branch-free: what a particle does not need is computed and dropped by a select */
     auto pair = [&](const RecS2& q, const bool take) {
         const double4 nj = q.n;
-        zone |= (take && nj.w != 0.0) ? 1 : 0;
+        if (CLASS == 1)
+            zone |= (take && q.s != 0) ? 1 : 0;
+        else
+            zone |= (take && nj.w != 0.0) ? 1 : 0;
         const double4 pj = q.p;
         const PairGeo g = pair_geo<FROZEN, true>(C, pi, x0i, pj, q.x0); /* gk = t^3: 5 Wc / H^2 once after the walk */
         if (SURF23)
@@ -896,7 +899,7 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
         [&](const unsigned j) {
             RecS2 q;
             if (CLASS == 1)
-                q.n.w = double(__ldg(&S.surf_i[j])); /* the surf flag is all a lean particle reads of n_j */
+                q.s = __ldg(&S.surf_i[j]); /* the surf flag is all a lean particle reads of n_j */
             else
                 q.n = gather(S.P4, j);
             q.p = gather(S.P0, j);
