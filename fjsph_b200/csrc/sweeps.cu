@@ -363,7 +363,16 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
            npd sum are the same sum, kept once). */
         double ksum = 0.0; /* sum_j W' over fluid neighbours: kernsum = Wc (1 + ksum), Shifting.cpp:39-45; npd = Wc ksum */
         double colour = 0.0;
-        auto pair = [&](const RecPre& q, const bool take) {
+        /* Lmat_nb and the prestep normal sum over FLUID neighbours only (b > PISTON).  Most warps have no other kind in
+           reach, so the loop sums over ALL neighbours (l**, and m = -sum a) and a second set of accumulators takes the
+           non-fluid ones under a warp-uniform vote -- skipped wherever there is no wall nearby; the fluid-only sums are the
+           differences (n** = l** - w**, m -= mw) formed after the walk. */
+        double w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0, mw0 = 0, mw1 = 0, mw2 = 0;
+        struct PreOut
+        {
+            double ax, ay, az, rx, ry, rz;
+        };
+        auto pair = [&](const RecPre& q, const bool take) -> PreOut {
             const double4 pj = q.p;
             const PairGeo g = pair_geo<FROZEN, true>(C, pi, x0i, pj, q.x0);
             const double vg = pj.w * g.gk; /* V_j * t^3 ; Grad = GradK(-Rji) = -Rji*gk; 0 for a lane's own index */
@@ -379,22 +388,28 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
             g0 = fma(-dr, ax, g0);
             g1 = fma(-dr, ay, g1);
             g2 = fma(-dr, az, g2);
-            /* fluid neighbours only (b > PISTON): selects, not branches */
+            m0 -= ax; /* a lane's own index contributes exact zeros */
+            m1 -= ay;
+            m2 -= az;
+            /* the kernel sums take fluid neighbours only (b > PISTON): a select, not a branch */
             const bool fl = take && q.b > FJSPH_PISTON;
-            const double fx = fl ? ax : 0.0, fy = fl ? ay : 0.0, fz = fl ? az : 0.0;
-            n00 = fma(fx, g.rx, n00);
-            n01 = fma(fx, g.ry, n01);
-            n02 = fma(fx, g.rz, n02);
-            n11 = fma(fy, g.ry, n11);
-            n12 = fma(fy, g.rz, n12);
-            n22 = fma(fz, g.rz, n22);
-            m0 -= fx;
-            m1 -= fy;
-            m2 -= fz;
             const double t2 = g.t * g.t;
             const double W_ = fl ? (t2 * t2) * fma(-4.0, g.t, 5.0) : 0.0;
             ksum += W_;
             colour = fma(pj.w, W_, colour);
+            return PreOut{ax, ay, az, g.rx, g.ry, g.rz};
+        };
+        auto pair_wall = [&](const PreOut& o, const bool nf) {
+            const double fx = nf ? o.ax : 0.0, fy = nf ? o.ay : 0.0, fz = nf ? o.az : 0.0;
+            w00 = fma(fx, o.rx, w00);
+            w01 = fma(fx, o.ry, w01);
+            w02 = fma(fx, o.rz, w02);
+            w11 = fma(fy, o.ry, w11);
+            w12 = fma(fy, o.rz, w12);
+            w22 = fma(fz, o.rz, w22);
+            mw0 -= fx;
+            mw1 -= fy;
+            mw2 -= fz;
         };
         for_neighbours2(
             lv, W, active, unsigned(i),
@@ -408,8 +423,14 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
                 return q;
             },
             [&](const RecPre& qa, const bool ta, const RecPre& qb, const bool tb) {
-                pair(qa, ta);
-                pair(qb, tb);
+                const PreOut oa = pair(qa, ta);
+                const PreOut ob = pair(qb, tb);
+                const bool nfa = ta && !(qa.b > FJSPH_PISTON), nfb = tb && !(qb.b > FJSPH_PISTON);
+                if (__any_sync(FJ_FULL, nfa || nfb))
+                {
+                    pair_wall(oa, nfa);
+                    pair_wall(ob, nfb);
+                }
             },
             [&](const unsigned first, const unsigned last) {
                 stage_span(S.P0, first, last);
@@ -423,6 +444,15 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, true))
         npd_ = C.W_correc * ksum;
         if (active)
         {
+        n00 = l00 - w00;
+        n01 = l01 - w01;
+        n02 = l02 - w02;
+        n11 = l11 - w11;
+        n12 = l12 - w12;
+        n22 = l22 - w22;
+        m0 -= mw0;
+        m1 -= mw1;
+        m2 -= mw2;
         const double kernsum = fma(C.W_correc, ksum, C.W_correc);
         colour *= C.W_correc;
         l00 *= C.gk_fac;
