@@ -625,6 +625,12 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
     const double eps_d = C.eps_d; /* 0.0001 H^2 -- Q3: 0.0001 here, 0.001 in the force loop */
     double nx = 0, ny = 0, nz = 0;
     double avx = 0, avy = 0, avz = 0, Rrhod = 0;
+    /* particle_shift limits the shifting velocity by max_j |v_j - v_i| / 2 (Shifting.cpp:253-256), the only thing the fused
+       surface + shifting sweep would gather the velocity record for.  This sweep holds v_j - v_i already (dissipation), so
+       when both halves run (the fused pass) it takes the maximum and leaves it in AV.w -- the curvature's slot, which the
+       sweep that follows reads first and then overwrites with the curvature. */
+    constexpr bool STASH = SURF && DISS;
+    double maxU2 = 0.0;
     const double cos_pi4 = 0.70710678118654757;
 
     /* main part of one pair, branch-free */
@@ -649,7 +655,10 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
             const double w = vg * (g.r2c * idist2); /* V_j (Rji . gradK) idist2 */
             const double drho = rho_j - rho_i;
             const bool fl = q.b > FJSPH_PISTON;
-            const double vdotr = (vj.x - vi.x) * g.rx + (vj.y - vi.y) * g.ry + (vj.z - vi.z) * g.rz;
+            const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
+            const double vdotr = ux * g.rx + uy * g.ry + uz * g.rz;
+            if (STASH)
+                maxU2 = fmax(maxU2, fma(uz, uz, fma(uy, uy, ux * ux)));
             /* ArtVisc = 0 when Vji.Rji > 0, and for a non-fluid neighbour (selects, no branches).
                m_j gk alpha cbar mu / rhobar with m_j = rho_j V_j, mu = H Vji.Rji idist2, cbar = sqrt(B gam) (rho_i^-1/2 +
                rho_j^-1/2) / 2, rhobar = (rho_i + rho_j) / 2: the constants 5 Wc / H^2 * alpha * sqrt(B gam) * H after the walk */
@@ -772,6 +781,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, false))
         av.x = k_av * avx;
         av.y = k_av * avy;
         av.z = k_av * avz;
+        if (STASH)
+            av.w = maxU2;
         S.AV[i] = av;
         double4 af = S.AF[i];
         af.w = (C.dsph_cont * C.gk_fac) * Rrhod;
@@ -870,7 +881,10 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
     const bool do_shift = SHIFT && !(lam_nb < 0.55 || b_i == FJSPH_BUFFER);
     /* with the stage entry point surfzone is already known; fused, it is this loop's `zone` */
     const bool known_bulk = SHIFT && !SURF23 && (S.surfzone[i] == 0) && (lam_nb > 0.55);
-    double dux = 0, duy = 0, duz = 0, maxU2 = 0.0;
+    /* fused pass: max_j |v_j - v_i|^2 was left in AV.w by the sweep before (k_surf1_diss), so the velocity record of j is
+       not gathered here at all */
+    constexpr bool STASHED = SURF23 && SHIFT;
+    double dux = 0, duy = 0, duz = 0, maxU2 = (STASHED && do_shift) ? S.AV[i].w : 0.0;
     const double kq_fac = C.W_correc * C.iW_dx;
     /* max_j acos(c_j) over c_j in [-1,1] == acos(min_j c_j); NaNs (|c|>1) are skipped by the reference's '>' */
     double min_c = 2.0;
@@ -920,8 +934,11 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
                 const double c = ni.x * nj.x + ni.y * nj.y + ni.z * nj.z;
                 min_c = (fl && !known_bulk && c >= -1.0 && c <= 1.0) ? fmin(min_c, c) : min_c;
             }
-            const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
-            maxU2 = fmax(maxU2, fma(uz, uz, fma(uy, uy, ux * ux)));
+            if (!STASHED)
+            {
+                const double ux = vj.x - vi.x, uy = vj.y - vi.y, uz = vj.z - vi.z;
+                maxU2 = fmax(maxU2, fma(uz, uz, fma(uy, uy, ux * ux)));
+            }
         }
     };
     for_neighbours2(
@@ -935,7 +952,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
             q.p = gather(S.P0, j);
             if (SHIFT)
             {
-                q.v = gather(S.P1, j);
+                if (!STASHED)
+                    q.v = gather(S.P1, j);
                 q.b = __ldg(&S.b[j]);
             }
             if (FROZEN)
@@ -958,7 +976,8 @@ __global__ void __launch_bounds__(WARPS * 32, min_blocks(WARPS, CLASS == 1))
             stage_span(S.P0, first, last);
             if (SHIFT)
             {
-                stage_span(S.P1, first, last);
+                if (!STASHED)
+                    stage_span(S.P1, first, last);
                 stage_span(S.b, first, last);
             }
             if (FROZEN)
@@ -1770,7 +1789,7 @@ int fj_surface_and_dissipation(FjsphEngine* e, bool do_surface, bool do_dissipat
         if (st)
             return st;
     }
-    if (do_surface && fuse_shift && e->P.ale && FJ_FUSE_SHIFT)
+    if (do_surface && do_dissipation && fuse_shift && e->P.ale && FJ_FUSE_SHIFT) /* the fused sweep reads what surf1 + diss left in AV.w */
     {
         SplitScope ks(e, "surf2+3+shift");
         /* Two launches (lean bulk, then the near-surface rest) pay when few warps hold near-surface particles: with the
