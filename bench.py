@@ -235,8 +235,9 @@ def cpu_reference(args, steps, warmup, sample_cells, kind_pref="reference"):
 def cpu_baseline_leg(args):
     """The `cpu_baseline` leg of the GPU arm: the reference arm itself (`--impl reference`, 2 warm-up + 4 timed steps, ~30 s)
     in a FRESH process, so that the CPU code runs under the conditions of the reference arm whatever this process holds (a
-    CUDA context, pinned buffers), and it is run FIRST (main): started after the GPU legs it measured 35-38 k
-    particle-steps/s on three boxes against 58-61 k as the reference arm; started first, 58.6 k."""
+    CUDA context, pinned buffers), and it is run FIRST (main).  The value has two regimes on these boxes -- 58-61 k
+    particle-steps/s on a quiet host, 35-38 k right after other large processes (the GPU arm's own allocations, a test
+    suite that has just exited): BASELINE.md 3."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4", "--warmup", "2",
            "--workload", args.workload, "--cpu-sample", args.cpu_sample, "--solver", args.solver, "--no-cpu-port"]
     env = dict(os.environ)
@@ -397,8 +398,7 @@ def main():
 
     # The cpu_baseline leg first, while this process holds nothing: run after the GPU legs -- beside ~16 GB of host
     # arrays, 2.5 GB of page-locked buffers and a CUDA context -- the same fresh-process run measured 35-38 k particle-steps/s
-    # three times on three boxes against 58-61 k as the reference arm: the big page-locked
-    # allocations leave the child's scattered list accesses without large pages.
+    # three times on three boxes against 58-61 k as the reference arm.
     cpu_early = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_early = cpu_baseline_leg(args)
