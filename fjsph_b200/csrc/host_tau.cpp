@@ -371,8 +371,19 @@ extern "C" int fjsph_tau_read_edge(const char* mesh_file, const char* solution_f
         std::unique_ptr<FjsphFoamMesh> M(new FjsphFoamMesh());
         const ClassicFile mesh(mesh_file);
         const size_t n_elem = mesh.need_dim("no_of_elements"), n_edge = mesh.need_dim("no_of_edges"),
-                     per = mesh.need_dim("points_per_edge"), n_surf = mesh.need_dim("no_of_surfaceelements"),
-                     n_pnts = mesh.need_dim("no_of_points");
+                     per = mesh.need_dim("points_per_edge"), n_pnts = mesh.need_dim("no_of_points");
+        /* the number of boundary edges: "no_of_surfaceelements" (what Read_tau_mesh_EDGE asks for, CDFIO.cpp:1040-1041), or --
+           files of the layout the reference's own Examples/RAE2822 ships, which its current reader stops at -- the wall and
+           far-field edge counts */
+        size_t n_surf = 0;
+        if (!mesh.dim("no_of_surfaceelements", n_surf))
+        {
+            size_t n_wall = 0, n_far = 0;
+            if (!mesh.dim("no_of_wall_edges", n_wall) || !mesh.dim("no_of_farfield_edges", n_far))
+                n_surf = mesh.need_dim("no_of_surfaceelements"); /* throws with the reference's diagnosis */
+            else
+                n_surf = n_wall + n_far;
+        }
         if (per != 2)
             throw TauError{"points_per_edge is " + std::to_string(per) + ", expected 2"};
         const std::vector<int> pts = mesh.variable<int>("points_of_element_edges", n_edge * per);

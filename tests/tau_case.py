@@ -89,12 +89,13 @@ def write_tau(root, lo, hi, n, vel, p, rho, version=2, wall_marker=-1, outer_mar
     return mesh_path, sol_path, pts, [f[0] for f in faces], left, right
 
 
-def write_tau_edge(root, lo, hi, n, vel, p, rho, plane="xz", version=2, wall_marker=-1, outer_marker=-2):
+def write_tau_edge(root, lo, hi, n, vel, p, rho, plane="xz", version=2, wall_marker=-1, outer_marker=-2, split_surface_dims=False):
     """A 2D TAU case as FJSPH's Cell2Edge leaves it: rectangle [lo, hi] of n = (nx, ny) quadrilateral cells stored by
     EDGES (points_of_element_edges, left / right_element_of_edges), the two in-plane coordinates under the names of `plane`
     ("xz": points_xc + points_zc, the y coordinate absent), and a solution file over the TWO-layer 3D point set the flow
     solver ran on (2 x the mesh's points) which `vertices_in_use` indexes.  The boundary edges on the lower side carry
-    wall_marker, the others outer_marker.  Returns (mesh path, solution path, points [n,2], edges, left, right, used)."""
+    wall_marker, the others outer_marker.  split_surface_dims: the boundary-edge count as "no_of_wall_edges" +
+    "no_of_farfield_edges" (the layout of the reference's own Examples/RAE2822) instead of "no_of_surfaceelements".  Returns (mesh path, solution path, points [n,2], edges, left, right, used)."""
     nx, ny = n
     xs = [np.linspace(lo[d], hi[d], k + 1) for d, k in enumerate(n)]
     vid = lambda i, j: j * (nx + 1) + i
@@ -129,8 +130,11 @@ def write_tau_edge(root, lo, hi, n, vel, p, rho, plane="xz", version=2, wall_mar
     names = {"x": "points_xc", "y": "points_yc", "z": "points_zc"}
     with netcdf_file(mesh_path, "w", version=version) as f:
         f.history = "tests/tau_case.py"
-        for name, size in (("no_of_elements", nx * ny), ("no_of_edges", len(edges)), ("points_per_edge", 2),
-                           ("no_of_surfaceelements", n_surf), ("no_of_points", npt)):
+        n_wall = int((right == wall_marker).sum())
+        surf_dims = ((("no_of_wall_edges", n_wall), ("no_of_farfield_edges", n_surf - n_wall)) if split_surface_dims
+                     else (("no_of_surfaceelements", n_surf),))
+        for name, size in (("no_of_elements", nx * ny), ("no_of_edges", len(edges)), ("points_per_edge", 2)) + surf_dims + (
+                ("no_of_points", npt),):
             f.createDimension(name, size)
         f.createVariable("points_of_element_edges", "i4", ("no_of_edges", "points_per_edge"))[:] = np.array(
             [e[0] for e in edges], dtype=np.int32)
@@ -141,7 +145,8 @@ def write_tau_edge(root, lo, hi, n, vel, p, rho, plane="xz", version=2, wall_mar
             v[:] = pts[:, d]
         f.createVariable("left_element_of_edges", "i4", ("no_of_edges",))[:] = left
         f.createVariable("right_element_of_edges", "i4", ("no_of_edges",))[:] = right
-        f.createVariable("boundarymarker_of_surfaces", "i4", ("no_of_surfaceelements",))[:] = np.arange(n_surf, dtype=np.int32) % 4 + 1
+        if not split_surface_dims:
+            f.createVariable("boundarymarker_of_surfaces", "i4", ("no_of_surfaceelements",))[:] = np.arange(n_surf, dtype=np.int32) % 4 + 1
     # the solver's point set: the mesh points scattered over 2 n slots (the other slots: the second layer, other values)
     sol = {k: rng.normal(size=2 * npt) for k in ("density", "x_velocity", "y_velocity", "z_velocity", "pressure")}
     U = np.array([vel(x) for x in pts])

@@ -241,3 +241,41 @@ def test_edge_based_2d_mesh_round_trip_and_containment(tmp_path):
     face_mesh, *_ = write_tau(tmp_path, LO, HI, (2, 2, 2), VEL, PR, RHO)
     with pytest.raises(_lib.FjsphError, match='no dimension "no_of_edges"'):
         frontend.read_tau_edge(face_mesh)
+
+
+def test_edge_mesh_with_wall_and_farfield_edge_counts(tmp_path):
+    """The edge-based layout the reference's own Examples/RAE2822 ships names its boundary edges by "no_of_wall_edges" and
+    "no_of_farfield_edges" and has no "no_of_surfaceelements" (what Read_tau_mesh_EDGE asks for, CDFIO.cpp:1032-1033):
+    fjsph_tau_read_edge takes the sum of the two, and a file with neither still fails with the reference's diagnosis.  The
+    same written case under both layouts reads identically; RAE2822 itself (where mounted) reads to consistent sizes."""
+    import os
+
+    from tests.tau_case import write_tau_edge
+
+    lo, hi, n = np.array([-0.1013, -0.1007]), np.array([0.1009, 0.1003]), (5, 4)
+    vel, pr, rho = (lambda x: (1.0 + x[0], 3.0 - x[1])), (lambda x: 1.0e5 + x[0]), (lambda x: 1.2 + 0.3 * x[1])
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    mesh_a, sol_a, *_ = write_tau_edge(tmp_path / "a", lo, hi, n, vel, pr, rho)
+    mesh_b, sol_b, *_ = write_tau_edge(tmp_path / "b", lo, hi, n, vel, pr, rho, split_surface_dims=True)
+    a = frontend.read_tau_edge(mesh_a, sol_a, scale=1.0, offset_axis=2)
+    b = frontend.read_tau_edge(mesh_b, sol_b, scale=1.0, offset_axis=2)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    from scipy.io import netcdf_file
+
+    with netcdf_file(str(tmp_path / "bare.edges"), "w", version=2) as f:   # neither layout: the reference's diagnosis
+        for name, size in (("no_of_elements", 4), ("no_of_edges", 12), ("points_per_edge", 2), ("no_of_points", 9)):
+            f.createDimension(name, size)
+        f.createVariable("vertices_in_use", "i4", ("no_of_points",))[:] = np.arange(9, dtype=np.int32)
+    with pytest.raises(_lib.FjsphError, match='no dimension "no_of_surfaceelements"'):
+        frontend.read_tau_edge(str(tmp_path / "bare.edges"))
+    rae = "/root/reference/Examples/RAE2822"
+    if os.path.exists(rae + "/mesh.grid.conf.edges"):
+        m = frontend.read_tau_edge(rae + "/mesh.grid.conf.edges", rae + "/sol.pval.10000", scale=1.0, offset_axis=2)
+        nc, nf = m["cCentre"].shape[0], m["leftright"].shape[0]
+        assert m["verts"].shape[1] == 2 and m["face_vtx"].size == 2 * nf and m["cell_ptr"].size == nc + 1
+        assert m["leftright"][:, 0].min() >= 0 and m["leftright"].max() < nc
+        assert np.bincount(m["leftright"][m["leftright"] >= 0], minlength=nc).min() >= 3      # every cell closed by >= 3 edges
+        assert np.isfinite(m["cVel"]).all() and (m["cRho"] > 0).all() and (m["cP"] > 0).all()
