@@ -48,6 +48,8 @@ FjsphStateView = struct_from_header("FjsphStateView")
 FjsphStepStats = struct_from_header("FjsphStepStats")
 FjsphMesh = struct_from_header("FjsphMesh")
 FjsphDeleted = struct_from_header("FjsphDeleted")
+FjsphIptSettings = struct_from_header("FjsphIptSettings")
+FjsphIptPoint = struct_from_header("FjsphIptPoint")
 
 
 # FjsphCommFn, include/fjsph_b200.h
@@ -130,6 +132,10 @@ def lib():
     L.fjsph_get_stream.argtypes = [vp, P(vp)]
     L.fjsph_slab_device_reductions.argtypes = [vp, C.c_int32]
     L.fjsph_take_deleted.argtypes = [vp, vp, C.c_int64, P(C.c_int64)]
+    L.fjsph_ipt_default_settings.argtypes = [P(FjsphParams), P(FjsphIptSettings)]
+    L.fjsph_read_para_ipt.argtypes = [C.c_char_p, C.c_double, P(C.c_int32), P(FjsphIptSettings)]
+    L.fjsph_mesh_max_length.argtypes = [P(FjsphMesh), C.c_int32, P(C.c_double)]
+    L.fjsph_ipt_integrate.argtypes = [vp, P(FjsphIptSettings), C.c_int64, vp, vp, vp, vp, C.c_int64, vp, P(C.c_int64), P(C.c_int64)]
     L.fjsph_slab_stats.argtypes = [vp, P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64), P(C.c_int64)]
     L.fjsph_foam_read.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, P(vp)]
     L.fjsph_foam_view.argtypes = [vp, P(FjsphMesh)]

@@ -221,12 +221,13 @@ def inlet_jet(n=(5, 5, 4), dx=1e-3, v_jet=10.0, fixed=0, n_buf=4, aero_x=1.5, de
     )
 
 
-def hex_mesh(lo, hi, n, vel=(0.0, 0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-2):
+def hex_mesh(lo, hi, n, vel=(0.0, 0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-2, triangulate=True):
     """Uniform hexahedral mesh of the box [lo, hi] with n = (nx, ny, nz) cells, every quad face split into two
     triangles (what FOAM::Read_FOAM produces by tri-fanning, FOAMIO.cpp:604-624), in the layout of the reference's
     MESH (Var.h:396-451): verts, faces as vertex lists (CSR), leftright = (owner cell, neighbour cell or the
     boundary marker: -2 outer, -1 inner wall), cell -> faces (CSR), cell centres and the cell solution.
-    vel / p / rho may be constants or callables of the cell centres [nc,3]."""
+    vel / p / rho may be constants or callables of the cell centres [nc,3].  triangulate=False keeps the quadrilaterals
+    four-cornered (what TAU::Read_tau_mesh_FACE leaves, CDFIO.cpp:1103-1227)."""
     lo, hi = np.asarray(lo, float), np.asarray(hi, float)
     nx, ny, nz = (int(k) for k in n)
     xs = [np.linspace(lo[d], hi[d], k + 1) for d, k in enumerate((nx, ny, nz))]
@@ -238,7 +239,7 @@ def hex_mesh(lo, hi, n, vel=(0.0, 0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-
     faces, leftright, cfaces = [], [], [[] for _ in range(nx * ny * nz)]
 
     def add_quad(q, left, right):
-        for tri in ((q[0], q[1], q[2]), (q[0], q[2], q[3])):
+        for tri in (((q[0], q[1], q[2]), (q[0], q[2], q[3])) if triangulate else (tuple(q),)):
             f = len(faces)
             faces.append(tri)
             leftright.append((left, right))
@@ -283,8 +284,9 @@ def hex_mesh(lo, hi, n, vel=(0.0, 0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-
     nc = centre.shape[0]
     ev = lambda f, shape: (np.asarray(f(centre), float) if callable(f) else np.broadcast_to(np.asarray(f, float), shape)).copy()
     face_vtx = np.asarray(faces, dtype=np.int64).ravel()
+    per = 3 if triangulate else 4
     return dict(
-        verts=verts, face_ptr=np.arange(0, 3 * len(faces) + 1, 3, dtype=np.int64), face_vtx=face_vtx,
+        verts=verts, face_ptr=np.arange(0, per * len(faces) + 1, per, dtype=np.int64), face_vtx=face_vtx,
         leftright=np.asarray(leftright, dtype=np.int32),
         cell_ptr=np.concatenate([[0], np.cumsum([len(c) for c in cfaces])]).astype(np.int64),
         cell_faces=np.concatenate([np.asarray(c, dtype=np.int64) for c in cfaces]),

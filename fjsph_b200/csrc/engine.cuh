@@ -158,6 +158,8 @@ struct DeviceMesh
     int n_cells = 0, n_faces = 0;
     double4* fx = nullptr;
     int* fmark = nullptr;
+    int* fown = nullptr;     // leftright.first (the tracker steps to the cell on the other side of a face, ipt.cu)
+    double4* fq = nullptr;   // {face[3].xyz, vertex count}: the fourth corner RayNormalIntersection reads (ipt.cu)
     int *cell_ptr = nullptr, *cell_faces = nullptr;
     double4 *cc = nullptr, *cvp = nullptr;
     double ox = 0, oy = 0, oz = 0, hx = 0, hy = 0, hz = 0, bin = 1;

@@ -453,7 +453,7 @@ int to_device(const std::vector<T>& h, T** d)
 void fj_free_mesh(FjsphEngine* e)
 {
     DeviceMesh& D = e->mesh;
-    void* ptrs[] = {D.fx, D.fmark, D.cell_ptr, D.cell_faces, D.cc, D.cvp, D.bin_start, D.bin_cells, D.counters};
+    void* ptrs[] = {D.fx, D.fmark, D.fown, D.fq, D.cell_ptr, D.cell_faces, D.cc, D.cvp, D.bin_start, D.bin_cells, D.counters};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -477,7 +477,8 @@ extern "C" int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m)
     }
     const size_t nf = size_t(m->n_faces), nc = size_t(m->n_cells);
     std::vector<double4> fx(3 * nf);
-    std::vector<int> fmark(nf);
+    std::vector<int> fmark(nf), fown(nf);
+    std::vector<double4> fq(nf);
     for (size_t f = 0; f < nf; ++f)
     {
         const int64_t a = m->face_ptr[f], b = m->face_ptr[f + 1];
@@ -506,10 +507,43 @@ extern "C" int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m)
         fx[3 * f + 1] = make_double4(v[1][1], v[1][2], v[2][0], v[2][1]);
         fx[3 * f + 2] = make_double4(v[2][2], v[3][0], v[3][1], v[3][2]);
         fmark[f] = m->leftright[2 * f + 1];
+        fown[f] = m->leftright[2 * f];
+        if (fown[f] < 0 || fown[f] >= m->n_cells || fmark[f] >= m->n_cells)
+        {
+            fj_set_error("upload_mesh: face %zu names a cell outside the mesh", f);
+            return FJSPH_ERR_INVALID;
+        }
+        /* face[3] (not the last vertex: they differ on polygons of five and more corners) */
+        const int64_t i3 = (b - a >= 4) ? m->face_vtx[a + 3] : id[3];
+        if (i3 < 0 || i3 >= m->n_verts)
+        {
+            fj_set_error("upload_mesh: vertex index out of range in face %zu", f);
+            return FJSPH_ERR_INVALID;
+        }
+        fq[f] = make_double4(m->verts[3 * i3], m->verts[3 * i3 + 1], m->verts[3 * i3 + 2], double(b - a));
     }
+    if (m->cell_ptr[0] != 0 || m->cell_ptr[nc] < 0 || m->cell_ptr[nc] > 0x7fffffff)
+    {
+        fj_set_error("upload_mesh: cell_ptr is not a CSR offset array");
+        return FJSPH_ERR_INVALID;
+    }
+    for (size_t c = 0; c < nc; ++c)
+        if (m->cell_ptr[c + 1] < m->cell_ptr[c])
+        {
+            fj_set_error("upload_mesh: cell_ptr decreases at cell %zu", c);
+            return FJSPH_ERR_INVALID;
+        }
     std::vector<int> cptr(nc + 1), cfaces(size_t(m->cell_ptr[nc]));
     for (size_t c = 0; c <= nc; ++c) cptr[c] = int(m->cell_ptr[c]);
-    for (size_t k = 0; k < cfaces.size(); ++k) cfaces[k] = int(m->cell_faces[k]);
+    for (size_t k = 0; k < cfaces.size(); ++k)
+    {
+        if (m->cell_faces[k] < 0 || m->cell_faces[k] >= m->n_faces)
+        {
+            fj_set_error("upload_mesh: cell_faces[%zu] is not a face of the mesh", k);
+            return FJSPH_ERR_INVALID;
+        }
+        cfaces[k] = int(m->cell_faces[k]);
+    }
     std::vector<double4> cc(nc), cvp(nc);
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (size_t c = 0; c < nc; ++c)
@@ -547,7 +581,8 @@ extern "C" int fjsph_upload_mesh(FjsphEngine* e, const FjsphMesh* m)
         for (size_t c = 0; c < nc; ++c) bcells[size_t(fill[bin_of(c)]++)] = int(c); /* ascending cell index per bin */
     }
     int st;
-    if ((st = to_device(fx, &D.fx)) || (st = to_device(fmark, &D.fmark)) || (st = to_device(cptr, &D.cell_ptr)) ||
+    if ((st = to_device(fx, &D.fx)) || (st = to_device(fmark, &D.fmark)) || (st = to_device(fown, &D.fown)) ||
+        (st = to_device(fq, &D.fq)) || (st = to_device(cptr, &D.cell_ptr)) ||
         (st = to_device(cfaces, &D.cell_faces)) || (st = to_device(cc, &D.cc)) || (st = to_device(cvp, &D.cvp)) ||
         (st = to_device(bstart, &D.bin_start)) || (st = to_device(bcells, &D.bin_cells)))
         return st;

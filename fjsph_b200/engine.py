@@ -24,6 +24,12 @@ SCALAR_FIELDS = tuple(
     "Rrho rho p m curve norm_curve woccl pDist deltaD cellP cellRho colourG colour lam lam_nb kernsum y".split()
 )
 ALL_FIELDS = INT64_FIELDS + INT32_FIELDS + VEC_FIELDS + ("L",) + SCALAR_FIELDS
+# FjsphDeleted / FjsphIptPoint as numpy record types (every member 8 bytes wide or a pair of int32: no padding)
+IPT_START = np.dtype([("part_id", "i8"), ("cellID", "i8"), ("t", "f8"), ("xi", "f8", 3), ("v", "f8", 3), ("mass", "f8"),
+                      ("cellV", "f8", 3), ("cellRho", "f8")])
+IPT_POINT = np.dtype([("part_id", "i8"), ("cellID", "i8"), ("faceID", "i8"), ("going", "i4"), ("failed", "i4"), ("t", "f8"),
+                      ("dt", "f8"), ("acc", "f8"), ("xi", "f8", 3), ("v", "f8", 3), ("cellV", "f8", 3), ("cellRho", "f8")])
+assert IPT_START.itemsize == C.sizeof(_lib.FjsphDeleted) and IPT_POINT.itemsize == C.sizeof(_lib.FjsphIptPoint)
 
 
 def default_params(dim: int = 3, **kw) -> FjsphParams:
@@ -47,6 +53,35 @@ def read_para(path: str, dim: int = 3, **kw):
     set_fields(p, **kw)
     check(L.fjsph_set_values(C.byref(p)))
     return p, fl.value.decode(), bd.value.decode()
+
+
+def ipt_settings(p: FjsphParams, para: str | None = None, scale: float = 1.0, **kw):
+    """IPT_SETT (Var.h:313-337) for the tracker: defaults + ipt_diam / ipt_area (IO.cpp:126-127) from `p`, then the IPT keys
+    of a para file (IO.cpp:447-453) when one is given, then kw.  Returns (settings, using_ipt)."""
+    s = _lib.FjsphIptSettings()
+    L = _lib.lib()
+    check(L.fjsph_ipt_default_settings(C.byref(p), C.byref(s)))
+    use = C.c_int32(1)
+    if para is not None:
+        check(L.fjsph_read_para_ipt(str(para).encode(), float(scale), C.byref(use), C.byref(s)))
+    set_fields(s, **kw)
+    return s, int(use.value)
+
+
+def mesh_max_length(mesh: dict, dim: int = 3) -> float:
+    """cells.maxlength as TAU::Read_tau_mesh_FACE / _EDGE leave it (CDFIO.cpp:867-898, 1117-1183)."""
+    m = FjsphMesh()
+    verts = np.asarray(mesh["verts"], dtype=np.float64)
+    if verts.shape[1] == 2:
+        verts = np.concatenate([verts, np.zeros((verts.shape[0], 1))], axis=1)
+    keep = dict(verts=np.ascontiguousarray(verts), face_ptr=np.ascontiguousarray(mesh["face_ptr"], dtype=np.int64),
+                face_vtx=np.ascontiguousarray(mesh["face_vtx"], dtype=np.int64))
+    for k, a in keep.items():
+        setattr(m, k, a.ctypes.data)
+    m.n_verts, m.n_faces = keep["verts"].shape[0], keep["face_ptr"].shape[0] - 1
+    out = C.c_double(0.0)
+    check(_lib.lib().fjsph_mesh_max_length(C.byref(m), int(dim), C.byref(out)))
+    return float(out.value)
 
 
 def set_fields(p, **kw):
@@ -370,6 +405,27 @@ class Engine:
                     xi=np.array([list(buf[i].xi) for i in range(k)]).reshape(k, 3),
                     v=np.array([list(buf[i].v) for i in range(k)]).reshape(k, 3),
                     cellV=np.array([list(buf[i].cellV) for i in range(k)]).reshape(k, 3))
+
+    def ipt_integrate(self, settings, start, record_cap: int = 0) -> dict:
+        """IPT::Integrate (IPT.cpp:871-1107) on the device for the hand-off records `start` -- the dict take_deleted returns,
+        or an IPT_START record array -- on the mesh of upload_mesh.  Returns last (IPT_POINT per particle: pnp1 as Integrate
+        leaves it), n_steps, n_records, records [n, record_cap] (the time_record handed to iptdata), n_success, n_failed."""
+        if isinstance(start, dict):
+            rec = np.zeros(len(start["part_id"]), dtype=IPT_START)
+            for k in IPT_START.names:
+                rec[k] = start[k]
+            start = rec
+        start = np.ascontiguousarray(start, dtype=IPT_START)
+        n = start.shape[0]
+        last = np.zeros(n, dtype=IPT_POINT)
+        n_steps, n_records = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        records = np.zeros((n, max(record_cap, 1)), dtype=IPT_POINT)
+        ok, bad = C.c_int64(0), C.c_int64(0)
+        check(self._L.fjsph_ipt_integrate(self._h, C.byref(settings), n, start.ctypes.data, last.ctypes.data, n_steps.ctypes.data,
+                                          records.ctypes.data if record_cap > 0 else None, int(record_cap),
+                                          n_records.ctypes.data, C.byref(ok), C.byref(bad)))
+        return dict(last=last, n_steps=n_steps, n_records=n_records, records=records[:, :record_cap], n_success=ok.value,
+                    n_failed=bad.value)
 
     def set_skin(self, skin_over_dx: float):
         """Width of the neighbour superset list in units of dx (0 = cell-list sweep at every update_neighbours)."""

@@ -125,6 +125,30 @@ typedef struct FjsphDeleted
     double cellV[3], cellRho;
 } FjsphDeleted;
 
+/* IPT_SETT (Var.h:313-337) and what IPT::Integrate reads from SIM / MESH beside it (IPT.cpp:871-1107). */
+typedef struct FjsphIptSettings
+{
+    int32_t eq_order;      /* ipt_eq_order: 1 BFD1, 2 BFD2 (IO.cpp:448, 668-672) */
+    int32_t max_subits;    /* svar.integrator.max_subits */
+    int32_t record;        /* streak_out == 1 || cells_out == 1: keep the state after every cell-to-cell step */
+    int32_t reserved0;
+    int64_t max_steps;     /* bound on the steps of one particle; the reference loops `while (pnp1.going != 0)` unbounded */
+    double relax, n_relax; /* Var.h:323-324 (n_relax is a real there) */
+    double max_x;          /* svar.ipt.max_x with the grid scale applied (IO.cpp:29) */
+    double max_length;     /* cells.maxlength: fjsph_mesh_max_length */
+    double diam, area;     /* ipt_diam, ipt_area (IO.cpp:126-127) */
+    double grav[3], mu_g, rho_rest;
+} FjsphIptSettings;
+
+/* An IPTPart (Var.h:645-813) as the tracker's outputs see it: the columns of Write_Point (IPT.cpp:180-190) and the ids. */
+typedef struct FjsphIptPoint
+{
+    int64_t part_id, cellID, faceID; /* cellID < 0: the boundary marker it left through; faceID -1: c_no_face */
+    int32_t going, failed;           /* failed 1: as the reference fails a particle; 2: stopped by max_steps */
+    double t, dt, acc;
+    double xi[3], v[3], cellV[3], cellRho;
+} FjsphIptPoint;
+
 /* The reference's MESH (Var.h:396-451) as plain arrays: vertices, faces as vertex lists (CSR), leftright (owner cell,
  * neighbour cell or boundary marker: -1 inner wall, -2 outer boundary), cell -> faces (CSR), cell centres and the
  * cell-averaged CFD solution.  What TAU::Read_* (CDFIO.cpp:1103-1356) or FOAM::Read_FOAM (FOAMIO.cpp:538-955) fill. */
@@ -199,6 +223,28 @@ int fjsph_step(FjsphEngine* e, FjsphStepStats* s);              /* Integrator::i
  * erases them.  Copies up to `capacity` records into `out` and drops them from the engine's queue; with out == NULL it
  * only reports how many are waiting.  Under slab decomposition every rank holds the particles erased on it. */
 int fjsph_take_deleted(FjsphEngine* e, FjsphDeleted* out, int64_t capacity, int64_t* n_out);
+
+/* Implicit particle tracking of the particles handed over at a delete plane: IPT::Integrate (IPT.cpp:871-1107) with
+ * FindFace / CheckCellFace (Containment.cpp:896-1079), Cross_Plane, MollerTrumbore and RayNormalIntersection
+ * (Geometry.cpp:399-478, 579-744), one device thread per particle, on the mesh of fjsph_upload_mesh -- what update_data
+ * does with to_del when `using_ipt` is set and the aero source is a mesh (Integration.cpp:151-169).
+ *   fjsph_ipt_default_settings  IPT_SETT's defaults, ipt_diam / ipt_area from the simulation mass (IO.cpp:126-127), gravity,
+ *                               gas viscosity, rest density and max_subits from `p`
+ *   fjsph_read_para_ipt         the para keys of IO.cpp:447-453; max_x is multiplied by `scale` (IO.cpp:29); *using_ipt is
+ *                               cleared when max_x < the SPH conversion coordinate (IO.cpp:674-679)
+ *   fjsph_mesh_max_length       cells.maxlength as the TAU readers leave it: the longest edge of a triangle, the longer
+ *                               diagonal of any other face (CDFIO.cpp:1117-1183); the edge length in 2D (CDFIO.cpp:867-898).
+ *                               FOAM::Read_FOAM never sets it (0: every particle would fail its first step)
+ *   fjsph_ipt_integrate         last[n]: pnp1 as Integrate leaves it; records[n][record_cap], n_records[n]: the time_record
+ *                               Terminate_Particle hands to iptdata (n_records counts them all, also those beyond
+ *                               record_cap, which are dropped); n_steps[n]: cell-to-cell steps taken.  Any output may be NULL.
+ * The surface-impact tallies of Terminate_Particle (IPT.cpp:746-798) follow from last[i].faceID and the host's marker table. */
+int fjsph_ipt_default_settings(const FjsphParams* p, FjsphIptSettings* s);
+int fjsph_read_para_ipt(const char* path, double scale, int32_t* using_ipt, FjsphIptSettings* s);
+int fjsph_mesh_max_length(const FjsphMesh* m, int32_t dim, double* max_length);
+int fjsph_ipt_integrate(FjsphEngine* e, const FjsphIptSettings* s, int64_t n, const FjsphDeleted* in, FjsphIptPoint* last,
+                        int32_t* n_steps, FjsphIptPoint* records, int64_t record_cap, int32_t* n_records, int64_t* n_success,
+                        int64_t* n_failed);
 
 /* Convenience for hosts that keep particles on the host between steps (the end-to-end path):
  * upload -> n_steps x fjsph_step -> download, one call.  When `in` holds the particle set the engine already has (same

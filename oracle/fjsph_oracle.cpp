@@ -2912,3 +2912,6 @@ double orc_kernel(double r, double H, double Wc) { return Kernel(r, H, Wc); }
 double orc_get_n_full(double dx, double H) { return get_n_full(dx, H); }
 
 } /* extern "C" */
+
+/* the implicit particle tracker downstream of the delete planes (IPT.cpp, Containment.cpp:896-1079) */
+#include "ipt_oracle.inc"

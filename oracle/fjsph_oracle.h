@@ -126,6 +126,44 @@ double orc_find_timestep(Orc* o);                         /* Integration.cpp:370
 double orc_integrate_no_update(Orc* o, OrcStepStats* s);  /* Integration.cpp:27-107 */
 double orc_integrate(Orc* o, OrcStepStats* s);            /* Integration.cpp:233-303 */
 
+/* The implicit particle tracker downstream of the delete planes (ipt_oracle.inc).  IPT_SETT (Var.h:313-337) and what
+ * IPT::Integrate reads from SIM / MESH beside it. */
+typedef struct OrcIptSettings
+{
+    int32_t eq_order;      /* ipt_eq_order: 1 BFD1, 2 BFD2 */
+    int32_t max_subits;    /* svar.integrator.max_subits */
+    int32_t record;        /* streak_out == 1 || cells_out == 1: time_record keeps every step */
+    int32_t reserved0;
+    int64_t max_steps;     /* bound on the cell-to-cell steps of one particle (the reference has none) */
+    double relax, n_relax; /* Var.h:323-324 */
+    double max_x;          /* svar.ipt.max_x, grid scale applied (IO.cpp:29) */
+    double max_length;     /* cells.maxlength (CDFIO.cpp:867-898, 1117-1183) */
+    double diam, area;     /* ipt_diam, ipt_area (IO.cpp:126-127) */
+    double grav[3], mu_g, rho_rest;
+} OrcIptSettings;
+/* what IPTPart(SPHPart const&, time, diam, area) copies from the erased particle (Var.h:737-763) */
+typedef struct OrcIptStart
+{
+    int64_t part_id, cellID;
+    double t;
+    double xi[3], v[3];
+    double mass;
+    double cellV[3], cellRho;
+} OrcIptStart;
+/* an IPTPart as the tracker's outputs see it (Write_Point, IPT.cpp:180-190, plus the ids) */
+typedef struct OrcIptPoint
+{
+    int64_t part_id, cellID, faceID; /* faceID -1: c_no_face */
+    int32_t going, failed;           /* failed 2: stopped by max_steps */
+    double t, dt, acc;
+    double xi[3], v[3], cellV[3], cellRho;
+} OrcIptPoint;
+/* IPT::Integrate (IPT.cpp:871-1107) for n particles on the mesh of orc_set_mesh.  last[n]: pnp1 as Integrate leaves it;
+ * records[n][record_cap] / n_records[n]: the time_record Terminate_Particle hands to iptdata; n_steps[n]: cell-to-cell
+ * steps taken (restatement builds only; the reference build leaves 0).  Any output pointer may be NULL. */
+int orc_ipt_integrate(Orc* o, const OrcIptSettings* s, int64_t n, const OrcIptStart* in, OrcIptPoint* last, int32_t* n_steps,
+                      OrcIptPoint* records, int64_t record_cap, int32_t* n_records, int64_t* n_success, int64_t* n_failed);
+
 /* Small-matrix restatements, exposed for unit tests. a is row-major dim x dim. */
 int orc_qr_inverse(const double* a, double* inv);          /* returns isInvertible */
 double orc_min_eigenvalue(const double* a);                /* SelfAdjointEigenSolver::computeDirect */

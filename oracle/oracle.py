@@ -40,6 +40,12 @@ def _struct_from_header(header: str, name: str):
 
 OrcParams = _struct_from_header(_HEADER, "OrcParams")
 OrcStepStats = _struct_from_header(_HEADER, "OrcStepStats")
+OrcIptSettings = _struct_from_header(_HEADER, "OrcIptSettings")
+# OrcIptStart / OrcIptPoint as numpy record types (every member 8 bytes wide or a pair of int32: no padding)
+IPT_START = np.dtype([("part_id", "i8"), ("cellID", "i8"), ("t", "f8"), ("xi", "f8", 3), ("v", "f8", 3), ("mass", "f8"),
+                      ("cellV", "f8", 3), ("cellRho", "f8")])
+IPT_POINT = np.dtype([("part_id", "i8"), ("cellID", "i8"), ("faceID", "i8"), ("going", "i4"), ("failed", "i4"), ("t", "f8"),
+                      ("dt", "f8"), ("acc", "f8"), ("xi", "f8", 3), ("v", "f8", 3), ("cellV", "f8", 3), ("cellRho", "f8")])
 
 BOUND, PISTON, BUFFER, BACK, PIPE, FREE, OUTLET, LOST = range(8)
 
@@ -150,6 +156,24 @@ def default_params(dim: int = 3, kind: str | None = None, **kw) -> "OrcParams":
     set_fields(p, **kw)
     lib.orc_set_values(C.byref(p))
     return p
+
+
+def ipt_settings(p: "OrcParams", **kw) -> "OrcIptSettings":
+    """IPT_SETT defaults (Var.h:313-337) with ipt_diam / ipt_area as Set_Values derives them (IO.cpp:126-127) and the
+    values IPT::Integrate reads from the rest of SIM (gravity, gas viscosity, rest density, max_subits)."""
+    s = OrcIptSettings()
+    s.eq_order, s.max_subits, s.record, s.max_steps = 2, p.max_subits, 1, 100000
+    s.relax, s.n_relax, s.max_x, s.max_length = 0.6, 5.0, 9999999.0, 0.0
+    s.diam = ((6.0 * p.sim_mass) / (np.pi * p.rho_rest)) ** (1.0 / 3.0)
+    s.area = np.pi * s.diam * s.diam / 4.0
+    s.grav[:] = list(p.grav)
+    s.mu_g, s.rho_rest = p.mu_g, p.rho_rest
+    for k, v in kw.items():
+        if k == "grav":
+            s.grav[:] = list(v)
+        else:
+            setattr(s, k, v)
+    return s
 
 
 def set_fields(p, **kw):
@@ -361,6 +385,23 @@ class Oracle:
         s = OrcStepStats()
         e = self.lib.orc_integrate(self.h, C.byref(s))
         return float(e), s
+
+    def ipt_integrate(self, settings: "OrcIptSettings", start: np.ndarray, record_cap: int = 0) -> dict:
+        """IPT::Integrate (IPT.cpp:871-1107) for the IPT_START records `start` on the mesh of set_mesh.  Returns last
+        (IPT_POINT per particle), n_steps, n_records, records [n, record_cap], n_success, n_failed."""
+        start = np.ascontiguousarray(start, dtype=IPT_START)
+        n = start.shape[0]
+        last = np.zeros(n, dtype=IPT_POINT)
+        n_steps, n_records = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        records = np.zeros((n, max(record_cap, 1)), dtype=IPT_POINT)
+        ok, bad = C.c_int64(0), C.c_int64(0)
+        self.lib.orc_ipt_integrate.argtypes = [C.c_void_p, C.POINTER(OrcIptSettings), C.c_int64] + [C.c_void_p] * 4 + [
+            C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        self.lib.orc_ipt_integrate.restype = C.c_int
+        self.lib.orc_ipt_integrate(self.h, C.byref(settings), n, _ptr(start), _ptr(last), _ptr(n_steps),
+                                   _ptr(records) if record_cap > 0 else None, int(record_cap), _ptr(n_records), C.byref(ok), C.byref(bad))
+        return dict(last=last, n_steps=n_steps, n_records=n_records, records=records[:, :record_cap], n_success=ok.value,
+                    n_failed=bad.value)
 
 
 # ---- FJSPH's own front end (reference libraries only): GetInput + Init_Particles, the LIMITS blocks, FOAM::Read_FOAM

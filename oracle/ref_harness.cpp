@@ -12,7 +12,7 @@
  *   - Eigen's / nanoflann's own arithmetic (QR inverse, direct eigenvalues, 4x4 determinant, search order) is the
  *     shim's restatement of the published algorithms and stays unpinned.
  * Nothing in fjsph_b200/ links or loads this.  Functions of the reference that the path links but never runs here
- * (IPT::Integrate, the VLM, the Tecplot-binary and h5part writers, Arc blocks) are stubs that abort.
+ * (the VLM, the Tecplot-binary and h5part writers) are stubs that abort.
  *
  * OpenMP: the reference's loops keep their pragmas; the harness pins one thread so that reductions are deterministic
  * and the npd data race cannot occur.
@@ -42,6 +42,7 @@
 #include "FOAMIO.h"
 #include "H5IO.h"
 #include "IO.h"
+#include "IPT.h"
 #include "Init.h"
 #include "shapes/arc.h"
 #include "shapes/inlet.h"
@@ -57,13 +58,22 @@ static void not_on_path(const char* what)
     std::fprintf(stderr, "ref_harness: %s is outside the time-step path and is not compiled\n", what);
     std::abort();
 }
+/* IPT.cpp is compiled (IPT::Integrate runs in orc_ipt_integrate); its Tecplot-binary writers live in BinaryIO.cpp */
 namespace IPT
 {
-void Integrate(SIM&, MESH const&, size_t const&, IPTPart&, IPTPart&, IPTPart&, vector<SURF>&, vector<IPTState>&)
+namespace BINARY
 {
-    not_on_path("IPT::Integrate");
+void Init_IPT_Files(SIM&) { not_on_path("IPT::BINARY::Init_IPT_Files"); }
+void Write_Point(SIM const&, IPTPart const&) { not_on_path("IPT::BINARY::Write_Point"); }
+void Write_State(SIM const&, IPTState const&, string const&, void*&) { not_on_path("IPT::BINARY::Write_State"); }
+void Write_Cells(SIM&, MESH const&, IPTState const&, int32_t const&, vector<StateVecD> const&, vector<int32_t> const&,
+                 vector<vector<int32_t>> const&, vector<int32_t> const&, vector<int32_t> const&)
+{
+    not_on_path("IPT::BINARY::Write_Cells");
 }
+} // namespace BINARY
 } // namespace IPT
+void flush_file(void*) { not_on_path("flush_file"); }
 #if SIMDIM == 3
 StateVecD VLM::getVelocity(StateVecD const&) const
 {
@@ -964,6 +974,79 @@ void orc_set_mesh(Orc* o, int64_t n_verts, const double* verts, int64_t n_faces,
     o->cell_tree->index->buildIndex();
 }
 int orc_first_cell_errors(Orc*) { return 0; } /* the reference exits instead */
+
+/* IPT::Integrate (IPT.cpp:871-1107) on the particles update_data would hand over (Integration.cpp:151-169) */
+static void ipt_point_out(IPTPart const& p, OrcIptPoint& q)
+{
+    q.part_id = int64_t(p.part_id);
+    q.cellID = p.cellID;
+    q.faceID = int64_t(int(p.faceID)); /* uint c_no_face -> -1 */
+    q.going = int32_t(p.going);
+    q.failed = int32_t(p.failed);
+    q.t = p.t;
+    q.dt = p.dt;
+    q.acc = p.acc;
+    q.cellRho = p.cellRho;
+    for (int d = 0; d < 3; ++d)
+    {
+        q.xi[d] = d < SIMDIM ? p.xi[d] : 0.0;
+        q.v[d] = d < SIMDIM ? p.v[d] : 0.0;
+        q.cellV[d] = d < SIMDIM ? p.cellV[d] : 0.0;
+    }
+}
+int orc_ipt_integrate(Orc* o, const OrcIptSettings* S, int64_t n, const OrcIptStart* in, OrcIptPoint* last, int32_t* n_steps,
+                      OrcIptPoint* records, int64_t record_cap, int32_t* n_records, int64_t* n_success, int64_t* n_failed)
+{
+    SIM& svar = o->svar;
+    svar.ipt.using_ipt = 1;
+    svar.ipt.ipt_eq_order = S->eq_order;
+    svar.ipt.relax = S->relax;
+    svar.ipt.n_relax = S->n_relax;
+    svar.ipt.max_x = S->max_x;
+    svar.ipt.ipt_diam = S->diam;
+    svar.ipt.ipt_area = S->area;
+    svar.ipt.streak_out = S->record ? 1 : 0;
+    svar.ipt.cells_out = 0;
+    svar.ipt.part_out = 0;
+    svar.ipt.ipt_n_success = 0;
+    svar.ipt.ipt_n_failed = 0;
+    svar.integrator.max_subits = uint(S->max_subits);
+    svar.grav = vec_from(S->grav);
+    svar.air.mu_g = S->mu_g;
+    svar.fluid.rho_rest = S->rho_rest;
+    o->cells.maxlength = S->max_length;
+    for (int64_t i = 0; i < n; ++i)
+    {
+        SPHPart sp;
+        sp.part_id = size_t(in[i].part_id);
+        sp.cellID = long(in[i].cellID);
+        sp.cellV = vec_from(in[i].cellV);
+        sp.cellRho = in[i].cellRho;
+        sp.v = vec_from(in[i].v);
+        sp.xi = vec_from(in[i].xi);
+        sp.m = in[i].mass;
+        IPTPart nm1(sp, in[i].t, svar.ipt.ipt_diam, svar.ipt.ipt_area); /* Integration.cpp:156-165 */
+        IPTPart pn = nm1, np1 = nm1;
+        o->iptdata.clear();
+        IPT::Integrate(svar, o->cells, size_t(i), nm1, pn, np1, o->surf_marks, o->iptdata);
+        if (last)
+            ipt_point_out(np1, last[i]);
+        if (n_steps)
+            n_steps[i] = 0;
+        IPTState const empty;
+        IPTState const& rec = o->iptdata.empty() ? empty : o->iptdata.back();
+        if (n_records)
+            n_records[i] = int32_t(rec.size());
+        if (records)
+            for (size_t k = 0; k < rec.size() && int64_t(k) < record_cap; ++k) ipt_point_out(rec[k], records[i * record_cap + int64_t(k)]);
+    }
+    o->iptdata.clear();
+    if (n_success)
+        *n_success = int64_t(svar.ipt.ipt_n_success);
+    if (n_failed)
+        *n_failed = int64_t(svar.ipt.ipt_n_failed);
+    return 0;
+}
 void orc_detect_surface(Orc* o)
 {
     Detect_Surface(o->svar, o->svar.bound_points, o->svar.total_points, o->outlist, o->cells, o->pnp1);

@@ -1,0 +1,159 @@
+"""The implicit particle tracker (IPT::Integrate on the particles erased at a delete plane) on the CPU side:
+the oracle restatement (oracle/ipt_oracle.inc) against FJSPH's own IPT.cpp / Containment.cpp / Geometry.cpp compiled in
+oracle/_ref -- live where the reference is mounted, and through the committed vectors of tests/golden/ipt_*.npz everywhere
+-- and the host-side settings functions of the product (fjsph_ipt_default_settings, fjsph_read_para_ipt,
+fjsph_mesh_max_length).  The device tracker is compared with the oracle in tests/test_gpu_ipt.py."""
+import ctypes as C
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from fjsph_b200 import _lib, cases, engine as eng
+from oracle import oracle as orc
+from tests import ipt_case
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "ipt_*.npz")))
+FIELDS = ipt_case.INT_FIELDS + ipt_case.FLOAT_FIELDS
+
+
+def run_oracle(dim, mesh, settings, start, kind=None, particle_step=1e-3, record_cap=ipt_case.RECORD_CAP):
+    p = orc.default_params(dim, asource=1, particle_step=particle_step)
+    o = orc.Oracle(p, kind=kind if kind else ("2d" if dim == 2 else None))
+    o.set_mesh(mesh)
+    return o.ipt_integrate(orc.ipt_settings(p, **settings), start, record_cap=record_cap)
+
+
+def assert_same_tracks(a, b, what):
+    """identical: every branch the tracker takes hangs on these numbers, and both sides evaluate the same expressions in the
+    same order without FMA contraction"""
+    assert (a["n_success"], a["n_failed"]) == (b["n_success"], b["n_failed"]), what
+    assert np.array_equal(a["n_records"], b["n_records"]), what
+    for f in FIELDS:
+        assert np.array_equal(a["last"][f], b["last"][f]), (what, "last", f)
+        assert np.array_equal(a["records"][f], b["records"][f]), (what, "records", f)
+
+
+def test_fixtures_present():
+    assert len(FIXTURES) == len(ipt_case.CASES), "tests/golden/ipt_*.npz missing: run tests/golden/make_ipt_vectors.py"
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[4:-4] for p in FIXTURES])
+def test_oracle_reproduces_the_reference_s_tracks(path):
+    """tests/golden/ipt_*.npz hold what IPT::Integrate of the compiled reference made of each case: the restatement lands on
+    the same cells, faces, outcomes and records, bit for bit -- including the particles the reference fails because
+    MollerTrumbore accepts only half of a parallelogram face (note Q9) and the extra time step of note Q10."""
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    mesh = {k[5:]: z[k] for k in z.files if k.startswith("mesh_")}
+    got = run_oracle(meta["dim"], mesh, meta["settings"], z["start"], particle_step=meta["particle_step"], record_cap=meta["record_cap"])
+    ref = dict(last=z["last"], records=z["records"], n_records=z["n_records"], n_success=meta["n_success"], n_failed=meta["n_failed"])
+    assert_same_tracks(got, ref, os.path.basename(path))
+    assert got["n_steps"].max() >= 6 and (got["n_steps"] >= 1).all()
+    # the record of a successful particle: start, one entry per completed step, the final state once more (Terminate_Particle)
+    ok = (got["last"]["failed"] == 0)
+    assert np.array_equal(got["n_records"][ok], got["n_steps"][ok] + 1)
+    assert np.array_equal(got["n_records"][~ok], got["n_steps"][~ok])
+
+
+@pytest.mark.parametrize("name", list(ipt_case.CASES))
+def test_oracle_follows_the_compiled_reference(name):
+    """live: the same inputs through oracle/_ref (skipped where /root/reference was never mounted), without records too"""
+    case = ipt_case.build(name, n=120, seed=11)
+    dim = case["dim"]
+    kind = "ref2d" if dim == 2 else "ref3d"
+    if not orc.have_ref(kind):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    p = orc.default_params(dim, asource=1, particle_step=case["particle_step"])
+    start = ipt_case.start_records(case, orc.IPT_START, p.sim_mass)
+    for record in (1, 0):
+        settings = dict(case["settings"], record=record, max_length=case["length_factor"] * eng.mesh_max_length(case["mesh"], dim))
+        a = run_oracle(dim, case["mesh"], settings, start)
+        b = run_oracle(dim, case["mesh"], settings, start, kind=kind)
+        assert_same_tracks(a, b, (name, record))
+        if not record:   # without streaks the record holds the start and, for a success, the end (IPT.cpp:881, 742-743)
+            assert np.array_equal(a["n_records"], 1 + (a["last"]["failed"] == 0))
+
+
+def test_outcomes_and_the_product_s_own_bounds():
+    """What ends a track: the outer boundary (cellID = the marker), max_x, the speed and step-length bounds, a start outside
+    the mesh, and max_steps (the reference loops unbounded: note Q11)."""
+    mesh = cases.quad_mesh([-0.1, -0.1], [0.5, 0.1], (12, 5), vel=(40.0, 0.0), rho=1.2)
+    p = orc.default_params(2, asource=1, particle_step=1e-3)
+    start = np.zeros(4, dtype=orc.IPT_START)
+    start["part_id"] = np.arange(4)
+    start["xi"][:, :2] = [(-0.08, 0.013), (-0.08, 0.013), (-0.08, 0.013), (0.7, 0.0)]
+    start["cellID"] = [0 + 12 * 2, 0 + 12 * 2, 0 + 12 * 2, -3]
+    start["v"][:, 0] = [10.0, 10.0, 2000.0, 10.0]
+    start["mass"] = p.sim_mass
+    start["cellV"][:, 0] = 40.0
+    start["cellRho"] = 1.2
+    base = dict(eq_order=1, max_length=1.0, grav=[0.0, 0.0, 0.0])
+    out = run_oracle(2, mesh, dict(base, max_x=0.2), start)
+    last = out["last"]
+    assert list(last["failed"]) == [0, 0, 1, 1] and (last["going"] == 0).all()
+    assert last["xi"][0, 0] > 0.2 and last["cellID"][0] >= 0                   # stopped by max_x, still inside the mesh
+    assert (out["n_success"], out["n_failed"]) == (2, 2)
+    assert np.array_equal(last["xi"][3], start["xi"][3]) and out["n_steps"][3] == 1   # outside the mesh: no face, failed at once
+    out = run_oracle(2, mesh, dict(base, max_x=9.0), start[:1])
+    assert out["last"]["cellID"][0] == -2 and out["last"]["failed"][0] == 0 and out["n_steps"][0] == 12   # left through the outer boundary
+    assert abs(out["last"]["xi"][0, 0] - 0.5) < 1e-6 and abs(out["last"]["xi"][0, 1] - 0.013) < 1e-12
+    out = run_oracle(2, mesh, dict(base, max_x=9.0, max_steps=5), start[:1])
+    assert out["last"]["failed"][0] == 2 and out["n_steps"][0] == 5 and out["n_failed"] == 1
+    out = run_oracle(2, mesh, dict(base, max_x=9.0, max_length=0.049), start[:1])   # one cell is 0.05 long
+    assert out["last"]["failed"][0] == 1
+
+
+def test_ipt_settings_of_the_host(tmp_path):
+    """fjsph_ipt_default_settings: IPT_SETT's defaults and ipt_diam / ipt_area as Set_Values derives them (IO.cpp:126-127);
+    fjsph_read_para_ipt: the keys of IO.cpp:447-453, max_x scaled (IO.cpp:29), no tracking when max_x lies upstream of the SPH
+    conversion coordinate (IO.cpp:674-679), an equation order other than 1 or 2 is an error (the reference exits)."""
+    p = eng.default_params(3, particle_step=2e-3, rho_rest=800.0, mu_g=1.8e-5, max_subits=17, grav=(0.0, -3.0, -9.0))
+    s, use = eng.ipt_settings(p)
+    assert (s.eq_order, s.max_subits, s.record, use) == (2, 17, 1, 1) and (s.relax, s.n_relax, s.max_x) == (0.6, 5.0, 9999999.0)
+    diam = ((6.0 * p.sim_mass) / (np.pi * 800.0)) ** (1.0 / 3.0)
+    assert abs(s.diam - diam) <= 2e-16 * diam and abs(s.area - np.pi * diam * diam / 4.0) <= 1e-15 * s.area
+    assert list(s.grav) == [0.0, -3.0, -9.0] and (s.mu_g, s.rho_rest) == (1.8e-5, 800.0)
+    o = orc.ipt_settings(orc.default_params(3, particle_step=2e-3, rho_rest=800.0, mu_g=1.8e-5, max_subits=17))
+    assert abs(o.diam - s.diam) <= 2e-16 * diam   # the oracle's helper and the product's agree
+    para = tmp_path / "para"
+    para.write_text(" Transition to IPT (0/1): 1\n Velocity equation order (1/2): 1\n SPH tracking conversion x coordinate: 0.3\n"
+                    " Maximum x trajectory coordinate: 1.5   # metres of the unscaled grid\n Particle streak output (0/1/2): 0\n")
+    s, use = eng.ipt_settings(p, para=para, scale=0.5)
+    assert (use, s.eq_order, s.record) == (1, 1, 0) and s.max_x == 0.75
+    para.write_text(" Transition to IPT (0/1): 1\n Particle streak output (0/1/2): 0\n Particle cell intersection output (0/1/2): 1\n"
+                    " SPH tracking conversion x coordinate: 2\n Maximum x trajectory coordinate: 1.5\n")
+    s, use = eng.ipt_settings(p, para=para)
+    assert (use, s.record) == (0, 1)
+    para.write_text(" Transition to IPT (0/1): 1\n Velocity equation order (1/2): 3\n")
+    with pytest.raises(_lib.FjsphError, match="Equation order not 1 or 2"):
+        eng.ipt_settings(p, para=para)
+    para.write_text(" Transition to IPT (0/1): 0\n Velocity equation order (1/2): 3\n")   # only checked when tracking is on
+    assert eng.ipt_settings(p, para=para)[1] == 0
+    with pytest.raises(_lib.FjsphError, match="could not open"):
+        eng.ipt_settings(p, para=tmp_path / "absent")
+
+
+def test_mesh_max_length():
+    """cells.maxlength as the TAU readers leave it: longest edge of a triangle, longer diagonal of a quadrilateral
+    (CDFIO.cpp:1117-1183), the edge length in 2D (CDFIO.cpp:867-898)."""
+    lo, hi, n = [0.0, 0.0, 0.0], [1.0, 2.0, 3.0], (2, 2, 2)
+    assert eng.mesh_max_length(cases.hex_mesh(lo, hi, n, triangulate=False)) == np.sqrt(1.0 + 1.5 ** 2)
+    assert eng.mesh_max_length(cases.hex_mesh(lo, hi, n)) == np.sqrt(1.0 + 1.5 ** 2)   # the diagonal is an edge of both halves
+    assert eng.mesh_max_length(cases.quad_mesh(lo[:2], hi[:2], n[:2]), 2) == 1.0
+    bad = cases.quad_mesh(lo[:2], hi[:2], n[:2])
+    bad["face_vtx"] = bad["face_vtx"].copy()
+    bad["face_vtx"][3] = 999
+    with pytest.raises(_lib.FjsphError, match="vertex index out of range"):
+        eng.mesh_max_length(bad, 2)
+
+
+def test_record_types_match_the_header():
+    assert eng.IPT_START.itemsize == C.sizeof(_lib.FjsphDeleted) == orc.IPT_START.itemsize
+    assert eng.IPT_POINT.itemsize == C.sizeof(_lib.FjsphIptPoint) == orc.IPT_POINT.itemsize
+    for name in ("eq_order", "max_subits", "record", "max_steps", "relax", "n_relax", "max_x", "max_length", "diam", "area",
+                 "grav", "mu_g", "rho_rest"):
+        assert getattr(_lib.FjsphIptSettings, name).offset == getattr(orc.OrcIptSettings, name).offset
