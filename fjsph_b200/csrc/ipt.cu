@@ -13,7 +13,7 @@
 // fourth corner.  This file is compiled with -fmad=false and every expression keeps the reference's order of
 // operations, so a trajectory differs from the CPU's only through pow() and log10() (GetCd, the convergence test).
 //
-// Kept as the reference has them (oracle/ipt_oracle.inc, notes Q9-Q11): MollerTrumbore's e2 = v2 - v1, which makes the
+// Kept as the reference has them (notes Q9-Q11): MollerTrumbore's e2 = v2 - v1, which makes the
 // tracker accept only the half (v0, v1, v3) of a parallelogram face -- a particle leaving through the other half is
 // stopped and counted as failed; pnp1.t advanced once more after a particle that ends in its very first step.
 // The product's own: max_steps bounds the march (failed = 2), a containing cell outside the mesh counts as "no face".
