@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -66,6 +67,92 @@ static int write_frame(FjsphEngine* e, const std::string& prefix, int frame, dou
     std::fclose(f);
     return 0;
 }
+
+/* The tracker's side of the frame loop: Integration.cpp:151-169 hands the erased particles to IPT::Integrate at every step,
+   Terminate_Particle queues their time records in iptdata, IPT::Write_Data (IPT.cpp:650-733) writes and clears the queue at
+   every frame.  ASCII streaks only (ASCII::Write_Streaks / Write_Point, IPT.cpp:180-190,205-224); the reference's header
+   leaves out the line break after its VARIABLES line (IPT.cpp:52-68), which is put in here. */
+struct IptOutput
+{
+    FILE* streaks = nullptr;
+    std::vector<FjsphIptPoint> queue;  /* the records of the particles ended since the last frame, one after the other */
+    std::vector<int32_t> lengths;      /* records per particle */
+    long long n_tracked = 0, n_success = 0, n_failed = 0;
+    static constexpr int64_t CAP = 4096; /* records kept per particle */
+    ~IptOutput()
+    {
+        if (streaks)
+            std::fclose(streaks);
+    }
+    int open(const std::string& name, bool append, int offset_axis)
+    {
+        streaks = std::fopen(name.c_str(), append ? "a" : "w");
+        if (!streaks)
+        {
+            std::fprintf(stderr, "Couldn't open the IPT streaks output file.\n");
+            return 1;
+        }
+        if (!append)
+        {
+            const char* xyz = offset_axis == 1 ? "\"Y\", \"Z\"" : offset_axis == 2 ? "\"X\", \"Z\"" : offset_axis == 3 ? "\"X\", \"Y\""
+                                                                                                      : "\"X\", \"Y\", \"Z\"";
+            std::fprintf(streaks, "TITLE = \"IPT Streaks\"\nVARIABLES = %s, \"t\", \"dt\", \"v\", \"a\", \"ptID\", \"Cell_V\", \"Cell_Rho\", "
+                                  "\"Cell_ID\"\n", xyz);
+        }
+        return 0;
+    }
+    int follow(FjsphEngine* e, const FjsphIptSettings& S)
+    {
+        int64_t n = 0;
+        if (fjsph_take_deleted(e, nullptr, 0, &n))
+            return 1;
+        if (n == 0)
+            return 0;
+        std::vector<FjsphDeleted> in(static_cast<size_t>(n));
+        if (fjsph_take_deleted(e, in.data(), n, &n))
+            return 1;
+        std::vector<FjsphIptPoint> rec(static_cast<size_t>(n) * size_t(CAP));
+        std::vector<int32_t> n_rec(static_cast<size_t>(n));
+        int64_t ok = 0, bad = 0;
+        if (fjsph_ipt_integrate(e, &S, n, in.data(), nullptr, nullptr, rec.data(), CAP, n_rec.data(), &ok, &bad))
+            return 1;
+        for (int64_t i = 0; i < n; ++i)
+        {
+            const int32_t k = int32_t(std::min<int64_t>(n_rec[size_t(i)], CAP));
+            queue.insert(queue.end(), rec.begin() + i * CAP, rec.begin() + i * CAP + k);
+            lengths.push_back(k);
+        }
+        n_tracked += n;
+        n_success += ok;
+        n_failed += bad;
+        return 0;
+    }
+    void write(int dim, double scale, bool streak_out)
+    {
+        size_t at = 0;
+        for (const int32_t k : lengths)
+        {
+            if (streak_out && k > 0 && streaks)
+            {
+                std::fprintf(streaks, "ZONE T=\"Particle %lld\"\nI= %d, J=1, K=1, DATAPACKING=POINT\n", (long long)queue[at].part_id, k);
+                for (int32_t j = 0; j < k; ++j)
+                {
+                    const FjsphIptPoint& q = queue[at + size_t(j)];
+                    for (int d = 0; d < dim; ++d) std::fprintf(streaks, " %2.7e", q.xi[d] / scale);
+                    std::fprintf(streaks, " %2.7e %2.7e %2.7e %2.7e %lld %2.7e %2.7e %6lld\n", q.t, q.dt,
+                                 std::sqrt(q.v[0] * q.v[0] + q.v[1] * q.v[1] + q.v[2] * q.v[2]), q.acc, (long long)q.part_id,
+                                 std::sqrt(q.cellV[0] * q.cellV[0] + q.cellV[1] * q.cellV[1] + q.cellV[2] * q.cellV[2]), q.cellRho,
+                                 (long long)q.cellID);
+                }
+            }
+            at += size_t(k);
+        }
+        if (streaks)
+            std::fflush(streaks);
+        queue.clear();
+        lengths.clear();
+    }
+};
 
 static int run(int argc, char** argv, int rank, int world, const char* nccl_id);
 
@@ -194,10 +281,10 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
        (FOAM::Read_FOAM, or TAU::Read_tau_mesh_FACE + Read_SOLUTION; Read_BMAP is part of fjsph_case_read); uploaded for
        the containment lookup once the particles are on the device */
     FjsphFoamMesh* aero_mesh = nullptr;
+    double tscale = 1.0, mesh_max_length = 0.0;
     {
         char fdir[1024] = "", fsol[1024] = "", tmesh[1024] = "", tsol[1024] = "";
         int32_t buoyant = 0;
-        double tscale = 1.0;
         FjsphMesh view;
         fjsph_case_foam(c, fdir, fsol, &buoyant, 1024);
         fjsph_case_tau(c, tmesh, tsol, &tscale, 1024);
@@ -209,6 +296,9 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
                 fjsph_foam_view(aero_mesh, &view))
                 return fail("reading the TAU mesh");
             std::printf("TAU mesh: %lld cells, %lld faces\n", (long long)view.n_cells, (long long)view.n_faces);
+            /* cells.maxlength, the tracker's bound on one step; only the TAU readers set it (CDFIO.cpp:867-898, 1117-1183) */
+            if (fjsph_mesh_max_length(&view, dim, &mesh_max_length))
+                return fail("measuring the TAU mesh");
         }
         else if (fdir[0])
         {
@@ -361,6 +451,16 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
         fjsph_foam_free(aero_mesh);
     }
     fjsph_get_params(e, &P);
+    /* particle tracking downstream of the delete planes (FJSPH.cpp:206-210, Integration.cpp:151-169): only with an aero mesh */
+    FjsphIptSettings ipt;
+    int32_t using_ipt = 0;
+    if (fjsph_ipt_default_settings(&P, &ipt) || fjsph_read_para_ipt(para, tscale, &using_ipt, &ipt))
+        return fail("reading the particle-tracking settings");
+    ipt.max_length = mesh_max_length;
+    using_ipt = using_ipt && P.asource != 0;
+    IptOutput tracks;
+    if (using_ipt && tracks.open(prefix + "_IPT_streaks.dat", !restart_file.empty(), fjsph_case_offset_axis(c)))
+        return 1;
     long long n_all = 0, n_bound = 0;
     if (global_counts(n_all, n_bound))
         return 1;
@@ -408,6 +508,8 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
             fjsph_get_params(e, &P);
             error = st.rms_error;
             deleted += st.n_del;
+            if (using_ipt && st.n_del > 0 && tracks.follow(e, ipt))
+                return fail("tracking the deleted particles");
             if (!quiet)
                 std::printf("%9.3e | %7.2e | %4.2f | %9.4f | %3d | %8.3f | %9.3e | %9.3e | %9.3e | %14ld|\n", P.current_time - st.dt,
                             st.dt, st.cfl_ratio, st.rms_error, st.iterations, st.maxRho_pc, st.maxf, st.maxAf, st.maxShift, long(ms));
@@ -434,6 +536,8 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
         }
         if (write_frame(e, prefix, fr, P.current_time, P.rho_rest))
             return fail("writing a frame");
+        if (using_ipt) /* IPT::Write_Data, FJSPH.cpp:319-320 */
+            tracks.write(dim, tscale, ipt.record != 0);
         /* march the frame time forward (FJSPH.cpp:326-327) BEFORE the checkpoint, so that a resumed run clamps its
            first steps to the end of the NEXT frame (find_timestep, Integration.cpp:433-440) */
         P.last_frame_time += P.frame_time_interval;
@@ -443,6 +547,9 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
             return fail("writing the restart file");
     }
     std::fclose(info);
+    if (using_ipt)
+        std::printf("Particle tracking: %lld particles followed, %lld left the mesh or passed the end plane, %lld failed\n",
+                    tracks.n_tracked, tracks.n_success, tracks.n_failed);
     if (rank == 0)
         std::printf("Simulation complete!\nTime taken:\t%.3f seconds\nTotal simulation time:\t%.7g seconds\n", seconds(), P.current_time);
     if (comm && rank == 0)
