@@ -2,7 +2,8 @@
  *
  * C ABI of the CPU oracle: a dependency-free restatement of FJSPH's WCSPH time-step path
  * (reference: /root/reference/src/{IO,Neighbours,Shifting,Geometry,Resid,Aero,Newmark_Beta,
- * Runge_Kutta,Integration}.cpp, Kernel.h, Var.h, shapes/inlet.cpp).
+ * Runge_Kutta,Integration}.cpp, Kernel.h, Var.h, shapes/inlet.cpp) and of the particle tracker downstream of it
+ * (IPT.cpp, Containment.cpp:896-1079; ipt_oracle.inc).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this library.  The product (fjsph_b200/) never links, imports or calls it.
