@@ -111,16 +111,29 @@ struct IptOutput
         std::vector<FjsphDeleted> in(static_cast<size_t>(n));
         if (fjsph_take_deleted(e, in.data(), n, &n))
             return 1;
-        std::vector<FjsphIptPoint> rec(static_cast<size_t>(n) * size_t(CAP));
-        std::vector<int32_t> n_rec(static_cast<size_t>(n));
+        /* two passes over batches of particles: the first counts the records of every track, the second keeps them in a
+           table as wide as the longest one (the marches cost little next to a step) */
         int64_t ok = 0, bad = 0;
-        if (fjsph_ipt_integrate(e, &S, n, in.data(), nullptr, nullptr, rec.data(), CAP, n_rec.data(), &ok, &bad))
-            return 1;
-        for (int64_t i = 0; i < n; ++i)
+        const int64_t BATCH = 65536;
+        for (int64_t at = 0; at < n; at += BATCH)
         {
-            const int32_t k = int32_t(std::min<int64_t>(n_rec[size_t(i)], CAP));
-            queue.insert(queue.end(), rec.begin() + i * CAP, rec.begin() + i * CAP + k);
-            lengths.push_back(k);
+            const int64_t m = std::min(BATCH, n - at);
+            std::vector<int32_t> n_rec(static_cast<size_t>(m));
+            int64_t ok1 = 0, bad1 = 0;
+            if (fjsph_ipt_integrate(e, &S, m, in.data() + at, nullptr, nullptr, nullptr, 0, n_rec.data(), &ok1, &bad1))
+                return 1;
+            ok += ok1;
+            bad += bad1;
+            const int64_t cap = std::min<int64_t>(*std::max_element(n_rec.begin(), n_rec.end()), CAP);
+            std::vector<FjsphIptPoint> rec(static_cast<size_t>(m) * size_t(cap));
+            if (fjsph_ipt_integrate(e, &S, m, in.data() + at, nullptr, nullptr, rec.data(), cap, n_rec.data(), nullptr, nullptr))
+                return 1;
+            for (int64_t i = 0; i < m; ++i)
+            {
+                const int32_t k = int32_t(std::min<int64_t>(n_rec[size_t(i)], cap));
+                queue.insert(queue.end(), rec.begin() + i * cap, rec.begin() + i * cap + k);
+                lengths.push_back(k);
+            }
         }
         n_tracked += n;
         n_success += ok;

@@ -394,17 +394,10 @@ class Engine:
         arrays (part_id, cellID, t, xi, v, mass, cellV, cellRho) in the reference's order; the engine's queue is emptied."""
         n = C.c_int64(0)
         check(self._L.fjsph_take_deleted(self._h, None, 0, C.byref(n)))
-        buf = (_lib.FjsphDeleted * max(1, n.value))()
+        buf = np.zeros(max(1, n.value), dtype=IPT_START)
         got = C.c_int64(0)
-        check(self._L.fjsph_take_deleted(self._h, C.cast(buf, C.c_void_p), n.value, C.byref(got)))
-        k = got.value
-        return dict(part_id=np.array([buf[i].part_id for i in range(k)], dtype=np.int64),
-                    cellID=np.array([buf[i].cellID for i in range(k)], dtype=np.int64),
-                    t=np.array([buf[i].t for i in range(k)]), mass=np.array([buf[i].mass for i in range(k)]),
-                    cellRho=np.array([buf[i].cellRho for i in range(k)]),
-                    xi=np.array([list(buf[i].xi) for i in range(k)]).reshape(k, 3),
-                    v=np.array([list(buf[i].v) for i in range(k)]).reshape(k, 3),
-                    cellV=np.array([list(buf[i].cellV) for i in range(k)]).reshape(k, 3))
+        check(self._L.fjsph_take_deleted(self._h, buf.ctypes.data, n.value, C.byref(got)))
+        return {k: buf[k][:got.value].copy() for k in IPT_START.names}
 
     def ipt_integrate(self, settings, start, record_cap: int = 0) -> dict:
         """IPT::Integrate (IPT.cpp:871-1107) on the device for the hand-off records `start` -- the dict take_deleted returns,
