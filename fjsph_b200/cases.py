@@ -294,6 +294,69 @@ def hex_mesh(lo, hi, n, vel=(0.0, 0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-
     )
 
 
+def tet_mesh(lo, hi, n, vel=(0.0, 0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-2):
+    """Tetrahedral mesh of the box [lo, hi]: every one of the n = (nx, ny, nz) bricks cut into the six tetrahedra of the Kuhn
+    triangulation (the paths from its corner (0,0,0) to (1,1,1) along the axes in each of the 6 orders), which fits together
+    across bricks.  Same layout as hex_mesh; every face a triangle in general position.  Also returns `locate(x)`: the
+    cell holding each point (brick by floor, tetrahedron by the order of the fractional coordinates)."""
+    import itertools
+
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    nx, ny, nz = (int(k) for k in n)
+    xs = [np.linspace(lo[d], hi[d], k + 1) for d, k in enumerate((nx, ny, nz))]
+    vid = lambda i, j, k: (k * (ny + 1) + j) * (nx + 1) + i
+    gi, gj, gk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    verts = np.zeros(((nx + 1) * (ny + 1) * (nz + 1), 3))
+    verts[vid(gi, gj, gk).ravel()] = np.stack([xs[0][gi.ravel()], xs[1][gj.ravel()], xs[2][gk.ravel()]], axis=1)
+    perms = list(itertools.permutations(range(3)))
+    faces, leftright, face_of, cells = [], [], {}, []
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                for perm in perms:
+                    at = [i, j, k]
+                    tet = [vid(*at)]
+                    for axis in perm:
+                        at[axis] += 1
+                        tet.append(vid(*at))
+                    c = len(cells)
+                    mine = []
+                    for skip in range(4):
+                        tri = tuple(v for q, v in enumerate(tet) if q != skip)
+                        key = tuple(sorted(tri))
+                        f = face_of.get(key)
+                        if f is None:
+                            f = face_of[key] = len(faces)
+                            faces.append(tri)
+                            leftright.append([c, outer_marker])
+                        else:
+                            leftright[f][1] = c
+                        mine.append(f)
+                    cells.append((tet, mine))
+    centre = np.array([verts[list(tet)].mean(axis=0) for tet, _ in cells])
+    nc = centre.shape[0]
+    ev = lambda f, shape: (np.asarray(f(centre), float) if callable(f) else np.broadcast_to(np.asarray(f, float), shape)).copy()
+    width = (hi - lo) / np.array([nx, ny, nz])
+    rank = {perm: q for q, perm in enumerate(perms)}
+
+    def locate(x):
+        rel = (np.asarray(x, float) - lo) / width
+        ijk = np.minimum(np.floor(rel).astype(int), np.array([nx, ny, nz]) - 1)
+        frac = rel - ijk
+        order = np.argsort(-frac, axis=1, kind="stable")      # the axis with the largest fraction is stepped along first
+        which = np.array([rank[tuple(o)] for o in order])
+        return ((ijk[:, 2] * ny + ijk[:, 1]) * nx + ijk[:, 0]) * 6 + which
+
+    mesh = dict(
+        verts=verts, face_ptr=np.arange(0, 3 * len(faces) + 1, 3, dtype=np.int64),
+        face_vtx=np.asarray(faces, dtype=np.int64).ravel(), leftright=np.asarray(leftright, dtype=np.int32),
+        cell_ptr=np.arange(0, 4 * nc + 1, 4, dtype=np.int64),
+        cell_faces=np.asarray([m for _, m in cells], dtype=np.int64).ravel(),
+        cCentre=centre, cVel=ev(vel, (nc, 3)), cP=ev(p, (nc,)), cRho=ev(rho, (nc,)),
+    )
+    return mesh, locate
+
+
 def quad_mesh(lo, hi, n, vel=(0.0, 0.0), p=100000.0, rho=1.2, outer_marker=-2):
     """2D counterpart of hex_mesh: uniform mesh of the rectangle [lo, hi] with n = (nx, ny) quadrilateral cells in the
     layout of the reference's 2D MESH (what TAU::Read_tau_mesh_EDGE fills, CDFIO.cpp:1103-1227): verts [nv,2], faces =

@@ -15,6 +15,8 @@ CASES = {
     "hex_tri_o2_lane": (3, "tri", 2, "lane"),
     "hex_quad_o1_lane": (3, "quad", 1, "lane"),
     "hex_quad_o2_scatter": (3, "quad", 2, "scatter"),
+    "tet_o1_scatter": (3, "tet", 1, "scatter"),
+    "tet_o2_scatter": (3, "tet", 2, "scatter"),
     "quad2d_o1_scatter": (2, "edge", 1, "scatter"),
     "quad2d_o2_long": (2, "edge", 2, "long"),
 }
@@ -35,7 +37,11 @@ def build(name, n=160, seed=5):
             vel = lambda c: np.stack([30 + 40 * c[:, 0] + 20 * c[:, 2], 0.4 * np.sin(9 * c[:, 0]) - 0.3, -0.5 + 1.5 * c[:, 1]], 1)
         else:
             vel = lambda c: np.stack([30 + 40 * c[:, 0] + 20 * c[:, 2], 5 * np.sin(9 * c[:, 0]) + 3 * c[:, 1], -4 + 10 * c[:, 1]], 1)
-        mesh = cases.hex_mesh(lo, hi, cells, vel=vel, rho=lambda c: 1.1 + c[:, 2] + 0.3 * c[:, 0], triangulate=(kind == "tri"))
+        rho = lambda c: 1.1 + c[:, 2] + 0.3 * c[:, 0]
+        if kind == "tet":   # six tetrahedra per brick: triangles in general position, four faces per cell
+            mesh, locate = cases.tet_mesh(lo, hi, cells, vel=vel, rho=rho)
+        else:
+            mesh = cases.hex_mesh(lo, hi, cells, vel=vel, rho=rho, triangulate=(kind == "tri"))
         grav = [0.0, 0.0, -9.81]
     else:
         lo, hi, cells = np.array([-0.1, -0.1]), np.array([0.5, 0.1]), (12, 5)
@@ -52,6 +58,8 @@ def build(name, n=160, seed=5):
         v = rng.normal(scale=3.0, size=(n, dim)) + np.array([10.0, 0.0, 0.0])[:dim]
     x = lo + (ijk + frac) * width
     cid = ijk[:, 0] + cells[0] * ijk[:, 1] + (cells[0] * cells[1] * ijk[:, 2] if dim == 3 else 0)
+    if kind == "tet":
+        cid = locate(x)
     pad = lambda a: np.concatenate([a, np.zeros((n, 3 - dim))], axis=1)
     start = dict(part_id=np.arange(n, dtype=np.int64) + 100, cellID=cid.astype(np.int64), t=np.full(n, 0.25),
                  xi=pad(x), v=pad(v), cellV=pad(mesh["cVel"][cid]), cellRho=mesh["cRho"][cid].copy())
