@@ -157,3 +157,35 @@ def test_record_types_match_the_header():
     for name in ("eq_order", "max_subits", "record", "max_steps", "relax", "n_relax", "max_x", "max_length", "diam", "area",
                  "grav", "mu_g", "rho_rest"):
         assert getattr(_lib.FjsphIptSettings, name).offset == getattr(orc.OrcIptSettings, name).offset
+
+
+def test_tracks_on_the_reference_s_own_rae2822_mesh():
+    """Examples/RAE2822 (the one mesh the reference ships: 23 552 cells around an aerofoil, its 2D edge-based TAU layout read by
+    fjsph_tau_read_edge) with the flow solution beside it: 300 droplets started at cell centres upstream of and around the
+    aerofoil at 30 % of the local gas velocity.  The restatement and the compiled reference follow every one of them through
+    up to ~230 cells to the same end -- the aerofoil's wall (marker -1) or the end plane at x = 1.5 -- bit for bit."""
+    from fjsph_b200 import frontend
+
+    rae = "/root/reference/Examples/RAE2822"
+    if not os.path.exists(rae + "/mesh.grid.conf.edges"):
+        pytest.skip("the reference's Examples are not mounted here")
+    if not orc.have_ref("ref2d"):
+        pytest.skip("oracle/_ref not built")
+    mesh = frontend.read_tau_edge(rae + "/mesh.grid.conf.edges", rae + "/sol.pval.10000", scale=1.0, offset_axis=2)
+    c = mesh["cCentre"]
+    near = np.where((c[:, 0] > -0.5) & (c[:, 0] < 0.2) & (np.abs(c[:, 1]) < 0.4))[0]
+    pick = np.random.default_rng(1).choice(near, 300, replace=False)
+    p = orc.default_params(2, asource=1, particle_step=1e-4)
+    start = np.zeros(300, dtype=orc.IPT_START)
+    start["part_id"], start["cellID"], start["mass"] = np.arange(300), pick, p.sim_mass
+    start["xi"][:, :2], start["v"][:, :2] = c[pick], 0.3 * mesh["cVel"][pick]
+    start["cellV"][:, :2], start["cellRho"] = mesh["cVel"][pick], mesh["cRho"][pick]
+    # (the shipped points_zc ends in 1354 NetCDF fill values, so cells.maxlength is 1e37 here: no bound on a step)
+    settings = dict(eq_order=2, max_x=1.5, max_length=eng.mesh_max_length(mesh, 2), grav=[0.0, -9.81, 0.0], max_steps=5000)
+    a = run_oracle(2, mesh, settings, start, particle_step=1e-4, record_cap=8)
+    b = run_oracle(2, mesh, settings, start, kind="ref2d", particle_step=1e-4, record_cap=8)
+    assert_same_tracks(a, b, "RAE2822")
+    last = a["last"]
+    assert a["n_failed"] == 0 and a["n_steps"].max() > 150
+    hit_wall, passed = last["cellID"] == -1, last["xi"][:, 0] > 1.5
+    assert hit_wall.sum() > 20 and passed.sum() > 200 and (hit_wall | passed).all()
