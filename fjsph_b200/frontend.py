@@ -14,7 +14,9 @@ from ._lib import FjsphBlock, FjsphMesh, FjsphParams, FjsphStateView, check
 
 def read_case(para_path: str, dim: int = 3) -> dict:
     """Returns dict(xi [n,dim], v [n,dim], rho, p, m, b, part_id, bound_points, params (FjsphParams after Set_Values),
-    blocks (list of dicts with the bound_block fields, ready for Engine.set_blocks), dim)."""
+    blocks (list of dicts with the bound_block fields, ready for Engine.set_blocks), dim, foam / tau (the aero mesh the deck
+    names), ipt = (FjsphIptSettings, using_ipt): the tracker's settings as GetInput + Set_Values leave them, IO.cpp:29,126-127,
+    447-453,666-680 -- using_ipt also needs an aero mesh, Integration.cpp:151)."""
     L = _lib.lib()
     h = C.c_void_p()
     check(L.fjsph_case_read(str(para_path).encode(), int(dim), C.byref(h)))
@@ -54,7 +56,11 @@ def read_case(para_path: str, dim: int = 3) -> dict:
         tmesh, tsol, tscale = C.create_string_buffer(1024), C.create_string_buffer(1024), C.c_double(1.0)
         L.fjsph_case_tau.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_double), C.c_int32]
         check(L.fjsph_case_tau(h, tmesh, tsol, C.byref(tscale), 1024))
+        ipt, using_ipt = _lib.FjsphIptSettings(), C.c_int32(0)
+        check(L.fjsph_ipt_default_settings(C.byref(params), C.byref(ipt)))
+        check(L.fjsph_read_para_ipt(str(para_path).encode(), float(tscale.value), C.byref(using_ipt), C.byref(ipt)))
         out.update(bound_points=int(L.fjsph_case_bound_points(h)), params=params, blocks=blocks, dim=dim,
+                   ipt=(ipt, int(using_ipt.value) if params.asource != 0 else 0),
                    foam=(fdir.value.decode(), fsol.value.decode(), int(buoy.value)),
                    tau=(tmesh.value.decode(), tsol.value.decode(), float(tscale.value)))
         return out

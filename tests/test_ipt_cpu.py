@@ -135,6 +135,22 @@ def test_ipt_settings_of_the_host(tmp_path):
     assert eng.ipt_settings(p, para=para)[1] == 0
     with pytest.raises(_lib.FjsphError, match="could not open"):
         eng.ipt_settings(p, para=tmp_path / "absent")
+    # through the case front end: a deck that names an aero mesh and switches the tracker on
+    from fjsph_b200 import frontend
+
+    (tmp_path / "f.bmap").write_text("   Name: W\n  Shape: Sphere\n Centre coordinate: 0,0,0\n Radius: 0.03\n Particle spacing: 0.01\n block end\n")
+    (tmp_path / "none.bmap").write_text("\n")
+    deck = (" Input boundary definition filename: %s\n Input fluid definition filename: %s\n SPH initial spacing: 0.01\n"
+            " SPH frame time interval: 1\n Transition to IPT (0/1): 1\n Velocity equation order (1/2): 1\n Grid scale: 0.5\n"
+            " SPH aerodynamic case: Gissler\n"
+            " SPH tracking conversion x coordinate: 0.2\n Maximum x trajectory coordinate: 3\n" % (tmp_path / "none.bmap", tmp_path / "f.bmap"))
+    para.write_text(deck)
+    s, use = frontend.read_case(str(para), 3)["ipt"]
+    assert use == 0 and (s.eq_order, s.max_x) == (1, 1.5)            # constant free stream: nothing to track through (Integration.cpp:151)
+    para.write_text(deck + " OpenFOAM input directory: foam\n OpenFOAM solution directory: 100\n")
+    c = frontend.read_case(str(para), 3)
+    s, use = c["ipt"]
+    assert c["params"].asource == 1 and use == 1 and s.max_x == 1.5 and s.diam > 0.0   # max_x *= scale whatever the mesh (IO.cpp:29)
 
 
 def test_mesh_max_length():
