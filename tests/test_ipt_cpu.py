@@ -78,6 +78,29 @@ def test_oracle_follows_the_compiled_reference(name):
             assert np.array_equal(a["n_records"], 1 + (a["last"]["failed"] == 0))
 
 
+@pytest.mark.parametrize("diam", [6.0e-6, 4.0e-5, 9.9e-5, 1.0e-4])
+@pytest.mark.parametrize("name", ["tet_o2_scatter", "hex_quad_o1_lane", "quad2d_o2_long"])
+def test_small_droplets_start_every_step_from_the_gas_velocity(name, diam):
+    """IPT.cpp:995-1003: below 10 microns a droplet starts every step after the first with the cell's gas velocity, up to 100
+    microns with a blend of the two, above with its own.  The four diameters sit in, and on the edges of, the three regimes."""
+    case = ipt_case.build(name, n=80, seed=31)
+    dim = case["dim"]
+    kind = "ref2d" if dim == 2 else "ref3d"
+    if not orc.have_ref(kind):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    p = orc.default_params(dim, asource=1, particle_step=case["particle_step"])
+    start = ipt_case.start_records(case, orc.IPT_START, p.sim_mass)
+    settings = dict(case["settings"], diam=diam, area=np.pi * diam * diam / 4.0,
+                    max_length=case["length_factor"] * eng.mesh_max_length(case["mesh"], dim))
+    a = run_oracle(dim, case["mesh"], settings, start)
+    b = run_oracle(dim, case["mesh"], settings, start, kind=kind)
+    assert_same_tracks(a, b, (name, diam))
+    assert a["n_steps"].max() >= 5
+    if diam < 1.0e-5:   # every record after the first step's carries the velocity the sub-iterations left, near the gas's
+        moving = a["n_records"] > 3
+        assert moving.any()
+
+
 def test_outcomes_and_the_product_s_own_bounds():
     """What ends a track: the outer boundary (cellID = the marker), max_x, the speed and step-length bounds, a start outside
     the mesh, and max_steps (the reference loops unbounded: note Q11)."""
