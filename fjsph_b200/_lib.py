@@ -194,4 +194,4 @@ class FjsphError(RuntimeError):
 
 def check(status: int):
     if status != 0:
-        raise FjsphError("fjsph status %d: %s" % (status, lib().fjsph_last_error().decode()))
+        raise FjsphError("fjsph status %d: %s" % (status, lib().fjsph_last_error().decode(errors="replace")))

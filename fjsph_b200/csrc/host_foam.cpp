@@ -49,6 +49,12 @@ struct Format /* what Read_Header takes from a FoamFile dictionary */
     int label_bits = 32, scalar_bits = 64;
 };
 
+size_t file_bytes(const std::string& file)
+{
+    std::ifstream f(file, std::ifstream::binary | std::ifstream::ate);
+    return f.is_open() ? size_t(std::max<std::streamoff>(f.tellg(), 0)) : 0;
+}
+
 // FoamFile header + the element count that follows it (Read_Preamble)
 size_t preamble(std::ifstream& fin, const std::string& file, const char* exp_class, Format& fmt, const char* binary_class = nullptr)
 {
@@ -102,6 +108,9 @@ size_t preamble(std::ifstream& fin, const std::string& file, const char* exp_cla
     std::istringstream iss(line);
     if (!(iss >> n))
         throw FoamError{file + ": expected the list size, found \"" + line + "\""};
+    /* an entry takes at least one byte of the file: a damaged count must not size a vector of its own making */
+    if (n > file_bytes(file))
+        throw FoamError{file + ": the list size " + std::to_string(n) + " exceeds the file"};
     return n;
 }
 
@@ -238,6 +247,8 @@ void read_faces(const std::string& file, std::vector<std::vector<size_t>>& faces
         }
         for (char drop : {'\n', '\r', '(', ')'}) interim.erase(std::remove(interim.begin(), interim.end(), drop), interim.end());
         const long n_labels = std::atol(interim.c_str());
+        if (n_labels < 0 || size_t(n_labels) > file_bytes(file))
+            throw FoamError{file + ": the vertex label count " + std::to_string(n_labels) + " exceeds the file"};
         if (index[0] != 0 || index[n - 1] != n_labels)
             throw FoamError{file + ": face offsets do not match the " + std::to_string(n_labels) + " vertex labels"};
         std::vector<int64_t> labels(size_t(n_labels), 0);
@@ -349,11 +360,20 @@ extern "C" int fjsph_foam_read(const char* foam_dir, const char* solution_dir, i
         read_labels(poly + "neighbour", right, n_cells);
         /* Post_Process: the neighbour file stops at the internal faces; patch faces follow in patch order */
         if (right.size() != left.size())
-            for (size_t k = 0; k < walls.size(); ++k) right.insert(right.end(), patches[k].first, walls[k] == 1 ? -1 : -2);
+            for (size_t k = 0; k < walls.size(); ++k)
+            {
+                if (patches[k].first > faces_.size()) /* a damaged nFaces entry must not size the list */
+                    throw FoamError{"patch " + std::to_string(k) + " claims " + std::to_string(patches[k].first) + " of the " +
+                                    std::to_string(faces_.size()) + " faces"};
+                right.insert(right.end(), patches[k].first, walls[k] == 1 ? -1 : -2);
+            }
         if (left.size() != faces_.size() || right.size() != faces_.size())
             throw FoamError{"Mismatch of number of faces (" + std::to_string(faces_.size()) + "), owner size (" +
                             std::to_string(left.size()) + ") and neighbour + patch size (" + std::to_string(right.size()) + ")"};
         const size_t n_pts = M->verts.size() / 3;
+        if (n_cells > 2 * faces_.size()) /* every face touches at most two cells: a damaged label names a cell far outside */
+            throw FoamError{"the owner / neighbour files name cell " + std::to_string(n_cells - 1) + ", the mesh has " +
+                            std::to_string(faces_.size()) + " faces"};
         std::vector<std::vector<size_t>> cFaces(n_cells);
         M->face_ptr.push_back(0);
         for (size_t f = 0; f < faces_.size(); ++f)
