@@ -4,7 +4,7 @@
 //   IPT_SETT defaults                          reference src/Var.h:313-337
 //   the IPT keys of GetInput's para parser      reference src/IO.cpp:447-453, checks at IO.cpp:666-680
 //   ipt_diam / ipt_area, max_x *= scale         reference src/IO.cpp:29,126-127
-//   cells.maxlength                             reference src/CDFIO.cpp:867-898 (edges), 1117-1183 (faces)
+//   cells.maxlength                             reference src/CDFIO.cpp:867-898,931 (edges), 1117-1183,1214 (faces)
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -149,6 +149,7 @@ extern "C" int fjsph_mesh_max_length(const FjsphMesh* m, int32_t dim, double* ma
             e = std::max(dist(v[0], v[2]), dist(v[1], v[3]));
         longest = std::max(longest, e);
     }
-    *max_length = longest;
+    /* the readers leave a multiple of it: maxedge *= 5.0 for faces (CDFIO.cpp:1214), maxedge *= 4.0 for edges (CDFIO.cpp:931) */
+    *max_length = longest * (dim == 2 ? 4.0 : 5.0);
     return FJSPH_OK;
 }

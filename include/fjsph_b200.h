@@ -232,8 +232,8 @@ int fjsph_take_deleted(FjsphEngine* e, FjsphDeleted* out, int64_t capacity, int6
  *                               gas viscosity, rest density and max_subits from `p`
  *   fjsph_read_para_ipt         the para keys of IO.cpp:447-453; max_x is multiplied by `scale` (IO.cpp:29); *using_ipt is
  *                               cleared when max_x < the SPH conversion coordinate (IO.cpp:674-679)
- *   fjsph_mesh_max_length       cells.maxlength as the TAU readers leave it: the longest edge of a triangle, the longer
- *                               diagonal of any other face (CDFIO.cpp:1117-1183); the edge length in 2D (CDFIO.cpp:867-898).
+ *   fjsph_mesh_max_length       cells.maxlength as the TAU readers leave it: 5 x the longest edge of a triangle / longer
+ *                               diagonal of any other face (CDFIO.cpp:1117-1183,1214); 4 x the longest edge in 2D (CDFIO.cpp:867-898,931).
  *                               FOAM::Read_FOAM never sets it (0: every particle would fail its first step)
  *   fjsph_ipt_integrate         last[n]: pnp1 as Integrate leaves it; records[n][record_cap], n_records[n]: the time_record
  *                               Terminate_Particle hands to iptdata (n_records counts them all, also those beyond

@@ -673,6 +673,8 @@ int orc_ref_read_tau_edge(Orc* o, const char* mesh_file, const char* sol_file, d
     return 0;
 }
 #endif
+/* cells.maxlength as the TAU readers leave it (CDFIO.cpp:867-898, 1117-1183): the particle tracker's bound on one step */
+double orc_ref_mesh_max_length(Orc* o) { return o->cells.maxlength; }
 void orc_ref_mesh_sizes(Orc* o, int64_t* out /* verts, faces, cells, face_vtx total, cell_faces total */)
 {
     MESH const& M = o->cells;

@@ -24,7 +24,7 @@ def main():
         p = orc.default_params(dim, asource=1, particle_step=case["particle_step"])
         o = orc.Oracle(p, kind="ref2d" if dim == 2 else "ref3d")
         o.set_mesh(case["mesh"])
-        settings = dict(case["settings"], max_length=case["length_factor"] * eng.mesh_max_length(case["mesh"], dim))
+        settings = dict(case["settings"], max_length=case["length_factor"] * ipt_case.longest_edge(case["mesh"], dim))
         S = orc.ipt_settings(p, **settings)
         start = ipt_case.start_records(case, orc.IPT_START, p.sim_mass)
         out = o.ipt_integrate(S, start, record_cap=ipt_case.RECORD_CAP)

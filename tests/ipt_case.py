@@ -20,9 +20,10 @@ CASES = {
     "quad2d_o1_scatter": (2, "edge", 1, "scatter"),
     "quad2d_o2_long": (2, "edge", 2, "long"),
 }
-# "long": scatter starts with max_length four times the mesh's longest edge.  On a uniform 2D mesh the reference's
-# cells.maxlength is the longer cell side, so every particle that crosses a whole cell at an angle moves further than that
-# in one step and is failed (IPT.cpp:949, 1059); TAU meshes carry far-field cells that make the bound lenient.
+# The bound on one step (cells.maxlength, IPT.cpp:949, 1059) is set deliberately TIGHT here -- the mesh's longest edge /
+# face diagonal itself, where the TAU readers leave 5 x (4 x in 2D) that -- so that the "moved too far in one step" failure
+# is exercised: on the uniform 2D mesh every particle that crosses a whole cell at an angle trips it.  "long": scatter starts
+# with four times the longest edge, the reference's own 2D value.
 LENGTH_FACTOR = {"long": 4.0}
 RECORD_CAP = 48
 
@@ -66,6 +67,23 @@ def build(name, n=160, seed=5):
     settings = dict(eq_order=order, record=1, max_steps=4000, max_x=0.45, grav=grav)
     return dict(dim=dim, mesh=mesh, start=start, settings=settings, particle_step=1e-3,
                 length_factor=LENGTH_FACTOR.get(pattern, 1.0))
+
+
+def longest_edge(mesh, dim):
+    """the longest edge of a triangle / longer diagonal of a quadrilateral (the edge length in 2D) over the faces of a mesh"""
+    v, ptr, vtx = np.asarray(mesh["verts"], float), np.asarray(mesh["face_ptr"]), np.asarray(mesh["face_vtx"])
+    d = lambda a, b: np.sqrt(((v[a] - v[b]) ** 2).sum(axis=-1))
+    best = 0.0
+    for k in np.unique(np.diff(ptr)):
+        f = vtx[(ptr[:-1][np.diff(ptr) == k])[:, None] + np.arange(k)[None, :]]
+        if dim == 2:
+            e = d(f[:, 0], f[:, 1])
+        elif k == 3:
+            e = np.maximum(d(f[:, 0], f[:, 1]), np.maximum(d(f[:, 0], f[:, 2]), d(f[:, 1], f[:, 2])))
+        else:
+            e = np.maximum(d(f[:, 0], f[:, 2]), d(f[:, 1], f[:, 3]))
+        best = max(best, float(e.max()))
+    return best
 
 
 def start_records(case, dtype, mass):

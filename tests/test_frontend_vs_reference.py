@@ -15,7 +15,7 @@ import os
 import numpy as np
 import pytest
 
-from fjsph_b200 import frontend
+from fjsph_b200 import engine, frontend
 from oracle import oracle as orc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -259,6 +259,16 @@ def test_tau_files_read_like_the_reference(tmp_path, version, scale, float_solut
     for k in ("face_ptr", "face_vtx", "leftright", "cell_ptr", "cell_faces", "verts", "cCentre", "cVel", "cP", "cRho"):
         assert np.array_equal(mine[k], theirs[k]), k
     assert np.abs(mine["cVel"]).max() > 1.0 and mine["cP"].min() > 9.0e4
+    # cells.maxlength (longest edge of a triangle, longer diagonal of a quadrilateral): the tracker's bound on one step
+    assert engine.mesh_max_length(mine) == _ref_max_length(ref) > 0.0
+
+
+def _ref_max_length(ref):
+    import ctypes as C
+
+    ref.lib.orc_ref_mesh_max_length.restype = C.c_double
+    ref.lib.orc_ref_mesh_max_length.argtypes = [C.c_void_p]
+    return float(ref.lib.orc_ref_mesh_max_length(ref.h))
 
 
 def test_arc_deck_steps_follow_the_reference_in_2d():
@@ -314,3 +324,4 @@ def test_tau_edge_files_read_like_the_reference(tmp_path, plane, offset_axis, ve
     for k in ("face_ptr", "face_vtx", "leftright", "cell_ptr", "cell_faces", "verts", "cCentre", "cVel", "cP", "cRho"):
         assert np.array_equal(mine[k], theirs[k]), k
     assert mine["verts"].shape[1] == 2 and np.abs(mine["cVel"]).max() > 1.0 and mine["cP"].min() > 9.0e4
+    assert engine.mesh_max_length(mine, 2) == _ref_max_length(ref) > 0.0   # the longest edge (CDFIO.cpp:867-898)

@@ -68,7 +68,7 @@ def assert_tracks_close(got, ref, what, leftright, steps=True):
 def test_device_tracker_against_the_oracle(name):
     case = ipt_case.build(name, n=400, seed=23)
     dim = case["dim"]
-    settings = dict(case["settings"], max_length=case["length_factor"] * eng.mesh_max_length(case["mesh"], dim))
+    settings = dict(case["settings"], max_length=case["length_factor"] * ipt_case.longest_edge(case["mesh"], dim))
     p = eng.default_params(dim, particle_step=case["particle_step"])
     for record in (1, 0):
         s = dict(settings, record=record)
@@ -95,7 +95,7 @@ def test_record_cap_bounds_and_errors():
     """Records beyond record_cap are dropped but counted; max_steps stops a march (failed = 2); the call needs a mesh and an
     equation order of 1 or 2; no particles is not an error."""
     case = ipt_case.build("quad2d_o2_long", n=50)
-    settings = dict(case["settings"], max_length=4.0 * eng.mesh_max_length(case["mesh"], 2))
+    settings = dict(case["settings"], max_length=4.0 * ipt_case.longest_edge(case["mesh"], 2))
     p = eng.default_params(2, asource=1, particle_step=1e-3)
     start = ipt_case.start_records(case, eng.IPT_START, p.sim_mass)
     full = device_tracks(2, case["mesh"], settings, start)
@@ -143,7 +143,7 @@ def test_hand_off_from_the_delete_plane_to_the_tracker():
     n = start["part_id"].shape[0]
     assert n >= 25 and (start["cellID"] >= 0).all() and np.abs(start["cellV"][:, 1]).min() > 1.0   # found by FindCell, solution attached
     p = e.params
-    s, _ = eng.ipt_settings(p, eq_order=2, max_length=eng.mesh_max_length(mesh), max_steps=2000)
+    s, _ = eng.ipt_settings(p, eq_order=2, max_length=ipt_case.longest_edge(mesh, 3), max_steps=2000)   # (a tight bound: ipt_case)
     got = e.ipt_integrate(s, start, record_cap=40)
     rec = np.zeros(n, dtype=orc.IPT_START)
     for k in orc.IPT_START.names:

@@ -70,7 +70,7 @@ def test_oracle_follows_the_compiled_reference(name):
     p = orc.default_params(dim, asource=1, particle_step=case["particle_step"])
     start = ipt_case.start_records(case, orc.IPT_START, p.sim_mass)
     for record in (1, 0):
-        settings = dict(case["settings"], record=record, max_length=case["length_factor"] * eng.mesh_max_length(case["mesh"], dim))
+        settings = dict(case["settings"], record=record, max_length=case["length_factor"] * ipt_case.longest_edge(case["mesh"], dim))
         a = run_oracle(dim, case["mesh"], settings, start)
         b = run_oracle(dim, case["mesh"], settings, start, kind=kind)
         assert_same_tracks(a, b, (name, record))
@@ -91,7 +91,7 @@ def test_small_droplets_start_every_step_from_the_gas_velocity(name, diam):
     p = orc.default_params(dim, asource=1, particle_step=case["particle_step"])
     start = ipt_case.start_records(case, orc.IPT_START, p.sim_mass)
     settings = dict(case["settings"], diam=diam, area=np.pi * diam * diam / 4.0,
-                    max_length=case["length_factor"] * eng.mesh_max_length(case["mesh"], dim))
+                    max_length=case["length_factor"] * ipt_case.longest_edge(case["mesh"], dim))
     a = run_oracle(dim, case["mesh"], settings, start)
     b = run_oracle(dim, case["mesh"], settings, start, kind=kind)
     assert_same_tracks(a, b, (name, diam))
@@ -177,12 +177,17 @@ def test_ipt_settings_of_the_host(tmp_path):
 
 
 def test_mesh_max_length():
-    """cells.maxlength as the TAU readers leave it: longest edge of a triangle, longer diagonal of a quadrilateral
-    (CDFIO.cpp:1117-1183), the edge length in 2D (CDFIO.cpp:867-898)."""
+    """cells.maxlength as the TAU readers leave it: 5 x the longest edge of a triangle / longer diagonal of a quadrilateral
+    (CDFIO.cpp:1117-1183, 1214), 4 x the longest edge in 2D (CDFIO.cpp:867-898, 931).  Pinned against the compiled readers in
+    tests/test_frontend_vs_reference.py; here the arithmetic, and that the tests' own tight bound is the un-multiplied length."""
     lo, hi, n = [0.0, 0.0, 0.0], [1.0, 2.0, 3.0], (2, 2, 2)
-    assert eng.mesh_max_length(cases.hex_mesh(lo, hi, n, triangulate=False)) == np.sqrt(1.0 + 1.5 ** 2)
-    assert eng.mesh_max_length(cases.hex_mesh(lo, hi, n)) == np.sqrt(1.0 + 1.5 ** 2)   # the diagonal is an edge of both halves
-    assert eng.mesh_max_length(cases.quad_mesh(lo[:2], hi[:2], n[:2]), 2) == 1.0
+    diag = np.sqrt(1.0 + 1.5 ** 2)
+    for mesh in (cases.hex_mesh(lo, hi, n, triangulate=False), cases.hex_mesh(lo, hi, n)):   # the diagonal is an edge of both halves
+        assert eng.mesh_max_length(mesh) == 5.0 * diag and ipt_case.longest_edge(mesh, 3) == diag
+    quad = cases.quad_mesh(lo[:2], hi[:2], n[:2])
+    assert eng.mesh_max_length(quad, 2) == 4.0 and ipt_case.longest_edge(quad, 2) == 1.0
+    tets, _ = cases.tet_mesh(lo, hi, n)
+    assert eng.mesh_max_length(tets) == 5.0 * ipt_case.longest_edge(tets, 3) == 5.0 * np.sqrt(0.25 + 1.0 + 2.25)
     bad = cases.quad_mesh(lo[:2], hi[:2], n[:2])
     bad["face_vtx"] = bad["face_vtx"].copy()
     bad["face_vtx"][3] = 999

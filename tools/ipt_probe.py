@@ -41,7 +41,8 @@ def main():
     start["cellV"], start["cellRho"] = mesh["cVel"][cid], mesh["cRho"][cid]
     p = eng.default_params(3, asource=1, particle_step=1e-3)
     start["mass"] = p.sim_mass
-    s, _ = eng.ipt_settings(p, eq_order=2, record=0, max_steps=4000, max_length=eng.mesh_max_length(mesh))
+    # the bound on one step: the longest face diagonal itself (a fifth of cells.maxlength), as the committed measurement ran
+    s, _ = eng.ipt_settings(p, eq_order=2, record=0, max_steps=4000, max_length=eng.mesh_max_length(mesh) / 5.0)
     out = dict(particles=n, cells=int(np.prod(cells)), mesh_build_s=round(t_mesh, 2))
     if not a.no_gpu:
         e = eng.Engine(p, 64)
