@@ -537,6 +537,23 @@ Orc* orc_ref_read_case(const char* para_path)
     o->integ = new Integrator(int(o->svar.integrator.solver_type));
     return o;
 }
+/* IPT_SETT as GetInput + Set_Values leave it (IO.cpp:29,126-127,447-453,666-680): using_ipt, ipt_eq_order, streak_out,
+ * cells_out, part_out, then max_x, max_x_sph, ipt_diam, ipt_area, relax, n_relax */
+void orc_ref_ipt_settings(Orc* o, int32_t* ints /* 5 */, double* reals /* 6 */)
+{
+    IPT_SETT const& I = o->svar.ipt;
+    ints[0] = I.using_ipt;
+    ints[1] = I.ipt_eq_order;
+    ints[2] = int32_t(I.streak_out);
+    ints[3] = int32_t(I.cells_out);
+    ints[4] = int32_t(I.part_out);
+    reals[0] = I.max_x;
+    reals[1] = I.max_x_sph;
+    reals[2] = I.ipt_diam;
+    reals[3] = I.ipt_area;
+    reals[4] = I.relax;
+    reals[5] = I.n_relax;
+}
 int orc_ref_num_blocks(Orc* o) { return int(o->limits.size()); }
 int orc_ref_num_bound_blocks(Orc* o) { return int(o->svar.n_bound_blocks); }
 /* sizes first (ints: nTimes, n_back, n_buf, bound_solver, no_slip, block_type, fixed_vel_or_dynamic, particle_order),

@@ -325,3 +325,40 @@ def test_tau_edge_files_read_like_the_reference(tmp_path, plane, offset_axis, ve
         assert np.array_equal(mine[k], theirs[k]), k
     assert mine["verts"].shape[1] == 2 and np.abs(mine["cVel"]).max() > 1.0 and mine["cP"].min() > 9.0e4
     assert engine.mesh_max_length(mine, 2) == _ref_max_length(ref) > 0.0   # the longest edge (CDFIO.cpp:867-898)
+
+
+def test_ipt_settings_read_like_the_reference(tmp_path):
+    """The tracker's settings: GetInput's IPT keys (IO.cpp:447-453), max_x scaled by the grid scale (IO.cpp:29), ipt_diam and
+    ipt_area from the simulation mass (IO.cpp:126-127), tracking switched off when max_x lies upstream of the SPH conversion
+    coordinate (IO.cpp:674-679) -- the compiled IO.cpp and fjsph_read_para_ipt / fjsph_ipt_default_settings on the same decks."""
+    import ctypes as C
+
+    if not _have("ref3d"):
+        pytest.skip("ref3d")
+    import shutil
+
+    for f in ("jet3d_fluid.bmap", "jet3d_pipe.bmap"):
+        shutil.copy(os.path.join(HERE, "decks", f), tmp_path / f)
+    base = open(os.path.join(HERE, "decks", "jet3d.para")).read() + "\n SPH frame count: 1\n Reference dispersed density: 810\n"
+    decks = {
+        "on": " Transition to IPT (0/1): 1\n Velocity equation order (1/2): 1\n Grid scale: 0.5\n SPH tracking conversion x coordinate: 0.2\n"
+              " Maximum x trajectory coordinate: 3\n Particle streak output (0/1/2): 0\n Particle cell intersection output (0/1/2): 1\n",
+        "upstream": " Transition to IPT (0/1): 1\n SPH tracking conversion x coordinate: 2\n Maximum x trajectory coordinate: 1.5\n",
+        "off": " Particle scatter output (0/1/2): 1\n",
+    }
+    for name, extra in decks.items():
+        para = tmp_path / ("para_" + name)
+        para.write_text(base + extra)
+        ref = orc.ref_read_case(str(para), "ref3d")
+        ints, reals = (C.c_int32 * 5)(), (C.c_double * 6)()
+        ref.lib.orc_ref_ipt_settings.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        ref.lib.orc_ref_ipt_settings(ref.h, ints, reals)
+        using, order, streak, cells_out, _ = list(ints)
+        max_x, _, diam, area, relax, n_relax = list(reals)
+        mine, mine_using = frontend.read_case(str(para), 3)["ipt"]
+        # (the product also wants an aero mesh before it tracks, Integration.cpp:151; these decks have none)
+        s, use_para = engine.ipt_settings(engine.read_para(str(para), 3)[0], para=para, scale=0.5 if name == "on" else 1.0)
+        assert mine_using == 0 and use_para == using, name
+        assert (s.eq_order, s.record) == (order, int(streak == 1 or cells_out == 1)) == (mine.eq_order, mine.record), name
+        assert s.max_x == max_x == mine.max_x and (s.relax, s.n_relax) == (relax, n_relax), name
+        assert s.diam == diam == mine.diam and s.area == area == mine.area, name
