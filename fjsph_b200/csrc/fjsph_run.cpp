@@ -471,6 +471,9 @@ static int run(int argc, char** argv, int rank, int world, const char* nccl_id)
         return fail("reading the particle-tracking settings");
     ipt.max_length = mesh_max_length;
     using_ipt = using_ipt && P.asource != 0;
+    if (using_ipt && mesh_max_length == 0.0 && rank == 0)
+        std::printf("WARNING: cells.maxlength is 0 (only the TAU readers set it, CDFIO.cpp:931,1214): as in FJSPH, every tracked "
+                    "particle fails its first step on this mesh.\n");
     IptOutput tracks;
     if (using_ipt && tracks.open(prefix + "_IPT_streaks.dat", !restart_file.empty(), fjsph_case_offset_axis(c)))
         return 1;
