@@ -279,3 +279,24 @@ def test_edge_mesh_with_wall_and_farfield_edge_counts(tmp_path):
         assert m["leftright"][:, 0].min() >= 0 and m["leftright"].max() < nc
         assert np.bincount(m["leftright"][m["leftright"] >= 0], minlength=nc).min() >= 3      # every cell closed by >= 3 edges
         assert np.isfinite(m["cVel"]).all() and (m["cRho"] > 0).all() and (m["cP"] > 0).all()
+        # against an independent reading of the same two files (scipy's NetCDF-3 reader): the arrays as stored, and the
+        # cell means over each cell's corners (every corner of a closed polygon ends two of its edges)
+        with netcdf_file(rae + "/mesh.grid.conf.edges", "r", mmap=False) as f, netcdf_file(rae + "/sol.pval.10000", "r", mmap=False) as sol:
+            edges = f.variables["points_of_element_edges"][:].astype(np.int64)
+            assert np.array_equal(m["verts"][:, 0], f.variables["points_xc"][:]) and np.array_equal(m["verts"][:, 1], f.variables["points_zc"][:])
+            assert np.array_equal(m["face_vtx"].reshape(-1, 2), edges)
+            assert np.array_equal(m["leftright"][:, 0], f.variables["left_element_of_edges"][:])
+            assert np.array_equal(m["leftright"][:, 1], f.variables["right_element_of_edges"][:])
+            used = f.variables["vertices_in_use"][:].astype(np.int64)
+            owner = np.repeat(np.arange(nc), np.diff(m["cell_ptr"]))
+            ends = edges[m["cell_faces"]]                                  # [cell-edge incidences, 2]
+            count = np.bincount(owner, minlength=nc) * 2.0
+            mean = lambda a: (np.bincount(owner, weights=a[ends[:, 0]], minlength=nc) + np.bincount(owner, weights=a[ends[:, 1]], minlength=nc)) / count
+            for got, name in ((m["cRho"], "density"), (m["cP"], "pressure"), (m["cVel"][:, 0], "x_velocity"), (m["cVel"][:, 1], "z_velocity")):
+                want = mean(sol.variables[name][:][used].astype(np.float64))
+                assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), name
+            finite = np.abs(m["verts"][:, 1]) < 1e30                        # (points_zc ends in 1354 NetCDF fill values)
+            inside = finite[ends].all(axis=1)
+            ok_cells = np.bincount(owner, weights=~inside, minlength=nc) == 0
+            assert ok_cells.sum() > 0.9 * nc
+            assert np.abs(m["cCentre"][ok_cells, 0] - mean(m["verts"][:, 0].copy())[ok_cells]).max() <= 1e-12 * 25.0
