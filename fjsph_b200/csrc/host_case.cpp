@@ -2416,6 +2416,10 @@ static int case_read_impl(const char* para_path, int dim, FjsphCase** out)
             fj_set_error("Input TAU solution file not defined.");
             return FJSPH_ERR_INVALID;
         }
+        /* like the block files: a name the working directory does not hold is looked for beside the para file */
+        c->tau_bmap = resolve(c->tau_bmap, dir_of(para_path));
+        c->tau_mesh = resolve(c->tau_mesh, dir_of(para_path));
+        c->tau_sol = resolve(c->tau_sol, dir_of(para_path));
         /* TAU::Read_BMAP (CDFIO.cpp:234-315), the part the time step sees: the map may restate the angle of attack, and
            gravity is turned by it -- g_z cos(alpha), and g_x = -g_Y sin(alpha) as the reference writes it in 3D too */
         std::ifstream bm(c->tau_bmap);
@@ -2432,7 +2436,7 @@ static int case_read_impl(const char* para_path, int dim, FjsphCase** out)
                 continue;
             get_number(line, "Angle alpha (degree)", c->angle_alpha);
         }
-        const double alpha = c->angle_alpha * M_PI / 180.0;
+        const double alpha = c->angle_alpha * (M_PI / 180.0); /* `angle_alpha *= M_PI / 180.0`, CDFIO.cpp:219,301 */
         const double g1 = c->params.grav[1];
         c->params.grav[dim - 1] = c->params.grav[dim - 1] * std::cos(alpha);
         c->params.grav[0] = -g1 * std::sin(alpha);
@@ -2446,6 +2450,7 @@ static int case_read_impl(const char* para_path, int dim, FjsphCase** out)
             fj_set_error("OpenFOAM solution directory not defined.");
             return FJSPH_ERR_INVALID;
         }
+        c->foam_dir = resolve(c->foam_dir, dir_of(para_path));
         c->params.asource = 1;
     }
     st = fjsph_set_values(&c->params);
