@@ -2108,6 +2108,7 @@ struct FjsphCase
     long long max_points = -1;      /* "SPH maximum particle count" (IO.cpp:428) */
     std::string output_prefix, restart_prefix; /* IO.cpp:373,355 */
     std::string foam_dir, foam_sol, tau_mesh, tau_bmap, tau_sol; /* IO.cpp:352-354,359-360 */
+    std::string vlm_file;                                        /* IO.cpp:366 */
     double scale = 1.0, angle_alpha = 0.0;     /* IO.cpp:356-357 */
     int foam_buoyant = 0;                      /* IO.cpp:364 */
     int offset_axis = -1;                      /* IO.cpp:358; -1 = not in the deck: Var.h:99-103 (0 in 3D, 2 in 2D) */
@@ -2381,6 +2382,7 @@ static int case_read_impl(const char* para_path, int dim, FjsphCase** out)
             get_string(line, "Output files prefix", c->output_prefix);
             get_string(line, "SPH restart prefix", c->restart_prefix);
             get_string(line, "OpenFOAM input directory", c->foam_dir);
+            get_string(line, "VLM definition filename", c->vlm_file);
             get_string(line, "OpenFOAM solution directory", c->foam_sol);
             get_number(line, "OpenFOAM buoyant (0/1)", c->foam_buoyant);
             get_string(line, "Primary grid face filename", c->tau_mesh);
@@ -2453,6 +2455,11 @@ static int case_read_impl(const char* para_path, int dim, FjsphCase** out)
         c->foam_dir = resolve(c->foam_dir, dir_of(para_path));
         c->params.asource = 1;
     }
+    /* IO.cpp:465-477: with no mesh named, a 3D deck that names a VLM definition takes the vortex-lattice aero source.  The
+       engine has no such source (out of scope) and says so at fjsph_create; the deck must not run on a constant free stream
+       unnoticed */
+    if (c->tau_mesh.empty() && c->foam_dir.empty() && dim == 3 && !c->vlm_file.empty())
+        c->params.asource = 2;
     st = fjsph_set_values(&c->params);
     if (st)
         return st;

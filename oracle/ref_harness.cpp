@@ -80,10 +80,12 @@ StateVecD VLM::getVelocity(StateVecD const&) const
     not_on_path("VLM::getVelocity");
     return StateVecD::Zero();
 }
-void VLM::Init(std::string) { not_on_path("VLM::Init"); }
-void VLM::GetGamma(StateVecD) { not_on_path("VLM::GetGamma"); }
-void VLM::write_VLM_Panels(std::string&) { not_on_path("VLM::write_VLM_Panels"); }
-void VLM::Plot_Streamlines(std::string&) { not_on_path("VLM::Plot_Streamlines"); }
+/* Set_Values sets the lattice up when a deck names the VLM aero source (IO.cpp:101-108): nothing to set up here, so that
+   GetInput + Init_Particles of such a deck (Examples/VC10, Examples/VLM) can still be compared; asking it for a velocity aborts */
+void VLM::Init(std::string) {}
+void VLM::GetGamma(StateVecD) {}
+void VLM::write_VLM_Panels(std::string&) {}
+void VLM::Plot_Streamlines(std::string&) {}
 #endif
 /* TECIO / HDF5 writers (BinaryIO.cpp, H5IO.cpp need the absent libraries) */
 void Write_Binary_Timestep(SIM const&, real const&, SPHState const&, bound_block const&, char const*, int32_t const&,

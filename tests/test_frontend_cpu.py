@@ -367,3 +367,23 @@ def test_dam2d_example_deck_is_the_references():
     pm, pr = params_to_dict(mine["params"]), params_to_dict(ref["params"])
     differing = [k for k in pm if pm[k] != pr[k] and not (isinstance(pm[k], float) and np.isnan(pm[k]) and np.isnan(pr[k]))]
     assert differing == [], differing
+
+
+def test_a_vlm_deck_is_read_and_then_refused(tmp_path):
+    """A 3D deck that names a VLM definition (and no mesh) takes the vortex-lattice aero source (IO.cpp:465-477): the front end
+    reads it -- asource 2, the particles as for any deck -- and fjsph_create refuses it by name; it never runs on a constant
+    free stream unnoticed.  A 2D build ignores the key, as the reference does."""
+    import shutil
+
+    from fjsph_b200 import _lib, engine
+
+    for f in ("droplet3d.para", "droplet3d_fluid.bmap", "droplet3d_boundary.bmap", "dam2d.para", "dam2d_fluid.bmap", "dam2d_boundary.bmap"):
+        shutil.copy(os.path.join(DECKS, f), tmp_path / f)
+    for name in ("droplet3d.para", "dam2d.para"):
+        with open(tmp_path / name, "a") as f:
+            f.write("\n VLM definition filename: (thisfile)\n")
+    c3 = frontend.read_case(str(tmp_path / "droplet3d.para"), 3)
+    assert c3["params"].asource == 2 and c3["xi"].shape[0] == frontend.read_case(os.path.join(DECKS, "droplet3d.para"), 3)["xi"].shape[0]
+    with pytest.raises(_lib.FjsphError, match="aero source 2 is not supported.*VLM is out of scope"):
+        engine.Engine(c3["params"], 16)                # refused before a device is asked for
+    assert frontend.read_case(str(tmp_path / "dam2d.para"), 2)["params"].asource == 0

@@ -49,6 +49,8 @@ DECKS = [
     ("Coflow_3D", EXAMPLES + "/Coflow/para3D", 3),
     ("Crossflow_3D", EXAMPLES + "/Crossflow/para3D", 3),
     ("RAE2822", EXAMPLES + "/RAE2822/para", 2),                       # the one deck that names a TAU mesh (2D, edge-based)
+    ("VC10", EXAMPLES + "/VC10/para", 3),                             # the VLM aero source (asource 2: read, then refused by the engine)
+    ("VLM", EXAMPLES + "/VLM/para", 3),
 ]
 
 # settings both sides carry (FjsphParams mirrors OrcParams name for name)
