@@ -370,3 +370,57 @@ def test_ipt_settings_read_like_the_reference(tmp_path):
         assert (s.eq_order, s.record) == (order, int(streak == 1 or cells_out == 1)) == (mine.eq_order, mine.record), name
         assert s.max_x == max_x == mine.max_x and (s.relax, s.n_relax) == (relax, n_relax), name
         assert s.diam == diam == mine.diam and s.area == area == mine.area, name
+
+
+def test_rae2822_example_steps_follow_the_reference():
+    """The one example the reference ships WITH its mesh: Examples/RAE2822 (2D, a dynamic inlet under an aerofoil, induced-
+    pressure aero model) coupled to its own TAU edge mesh and flow solution.  Deck and mesh through the product's front end
+    (fjsph_case_read, fjsph_tau_read_edge -- the reference's own edge reader stops at this file's layout), then the 2D build of
+    the compiled reference and the 2D oracle march two frames of it as FJSPH's main does: the same sub-iterations, time steps
+    and insertions at every step, the same cells from FindCell / FirstCell on a real unstructured mesh, state to 1e-12."""
+    from tests.util import relerr, INPUT_PARAMS
+
+    rae = EXAMPLES + "/RAE2822"
+    if not os.path.exists(rae + "/para"):
+        pytest.skip("the reference's Examples are not mounted here")
+    if not _have("ref2d"):
+        pytest.skip("ref2d")
+    mine = frontend.read_case(rae + "/para", 2)
+    P = mine["params"]
+    assert P.asource == 1 and mine["xi"].shape[0] == 1273
+    mesh = frontend.read_tau_edge(mine["tau"][0], mine["tau"][1], scale=mine["tau"][2], offset_axis=2)
+    params = {k: (tuple(getattr(P, k)) if hasattr(getattr(P, k), "__len__") else getattr(P, k)) for k in INPUT_PARAMS}
+
+    def fed(kind):
+        a = orc.Oracle(orc.default_params(2, **params), kind=kind)
+        a.set_particles(mine["xi"], mine["v"], mine["rho"], mine["p"], mine["m"], mine["b"], mine["bound_points"])
+        a.lib.orc_clear_blocks(a.h)
+        for B in mine["blocks"]:
+            a.add_block(B["is_fluid"], B["first"], B["second"], bound_solver=B["bound_solver"], no_slip=B["no_slip"],
+                        block_type=B["block_type"], fixed_vel_or_dynamic=B["fixed_vel_or_dynamic"], times=B["times"],
+                        vels=B["vels"], insert_norm=B["insert_norm"], insconst=B["insconst"], delete_norm=B["delete_norm"],
+                        delconst=B["delconst"], aero_norm=B["aero_norm"], aeroconst=B["aeroconst"], back=B.get("back"),
+                        buffer=B.get("buffer"))
+        a.set_mesh(mesh)
+        return a
+
+    o, r = fed("2d"), fed("ref2d")
+    steps = added = 0
+    for frame in range(2):                       # FJSPH.cpp:262-330: step until the frame is full, then march the frame time
+        stept = 0.0
+        while stept + 0.1 * P.delta_t_min < P.frame_time_interval:
+            _, so = o.integrate()
+            _, sr = r.integrate()
+            assert (so.iterations, so.n_add, so.n_del, so.total_points) == (sr.iterations, sr.n_add, sr.n_del, sr.total_points), steps
+            assert so.dt == sr.dt > 0.0, steps
+            stept += so.dt
+            steps += 1
+            added += so.n_add
+            assert steps < 40
+        for a in (o, r):
+            a.set_params(last_frame_time=a.params.last_frame_time + P.frame_time_interval)
+    assert steps >= 4 and added >= 54
+    assert np.array_equal(o.get("b"), r.get("b")) and np.array_equal(o.get("cellID"), r.get("cellID"))
+    assert (o.get("cellID") >= 0).sum() > 100           # FREE particles found in the mesh, carrying its solution
+    for f, tol in (("xi", 1e-14), ("rho", 1e-13), ("v", 1e-12), ("p", 1e-11), ("acc", 1e-11), ("Af", 1e-12), ("cellV", 0.0), ("cellP", 0.0)):
+        assert relerr(o.get(f), r.get(f)) <= tol, (f, relerr(o.get(f), r.get(f)))
