@@ -356,7 +356,10 @@ int fjsph_read_restart(FjsphEngine* e, const char* path, int32_t* frame);
  * inlet blocks as PIPE layers | BACK row | BUFFER rows with their back / buffer tables.  dim is the SIMDIM of the
  * build the deck was written for (shape names differ: Line/Plane, Square/Cube, Circle/Sphere); xi and v of
  * fjsph_case_state are [n][dim].  Arc / Arch blocks (shapes/arc.cpp) and JSON block files (the reference's JSON keys, blocks
- * in key order) are read as well; what arc.cpp answers with exit() is an error return here. */
+ * in key order) are read as well; what arc.cpp answers with exit() is an error return here.  The aero source follows
+ * IO.cpp:465-533: a TAU mesh, else an OpenFOAM case (asource 1; file names the working directory does not hold are looked for
+ * beside the para file), else in 3D a VLM definition (asource 2, which fjsph_create refuses: the vortex lattice is out of
+ * scope), else the constant free stream. */
 typedef struct FjsphCase FjsphCase;
 int fjsph_case_read(const char* para_path, int dim, FjsphCase** out);
 void fjsph_case_free(FjsphCase* c);
