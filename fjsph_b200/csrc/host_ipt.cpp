@@ -31,7 +31,7 @@ extern "C" int fjsph_ipt_default_settings(const FjsphParams* p, FjsphIptSettings
     s->eq_order = 2;
     s->max_subits = p->max_subits;
     s->record = 1; /* streak_out = 1 */
-    s->max_steps = 1000000;
+    s->max_steps = 100000; /* far beyond any mesh crossing; bounds what a particle caught between two cells can cost */
     s->relax = 0.6;
     s->n_relax = 5;
     s->max_x = 9999999;
