@@ -1035,7 +1035,8 @@ int orc_ipt_integrate(Orc* o, const OrcIptSettings* S, int64_t n, const OrcIptSt
     svar.grav = vec_from(S->grav);
     svar.air.mu_g = S->mu_g;
     svar.fluid.rho_rest = S->rho_rest;
-    o->cells.maxlength = S->max_length;
+    if (S->max_length >= 0.0) /* negative: keep what the reference's own mesh reader left */
+        o->cells.maxlength = S->max_length;
     for (int64_t i = 0; i < n; ++i)
     {
         SPHPart sp;

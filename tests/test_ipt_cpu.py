@@ -233,3 +233,40 @@ def test_tracks_on_the_reference_s_own_rae2822_mesh():
     assert a["n_failed"] == 0 and a["n_steps"].max() > 150
     hit_wall, passed = last["cellID"] == -1, last["xi"][:, 0] > 1.5
     assert hit_wall.sum() > 20 and passed.sum() > 200 and (hit_wall | passed).all()
+
+
+def test_tracks_on_a_tau_file_read_by_either_side(tmp_path):
+    """The whole chain as the reference runs it: a TAU face mesh (triangles and quadrilaterals) and its solution in NetCDF files,
+    read by TAU::Read_tau_mesh_FACE + Read_SOLUTION on one side and by fjsph_tau_read on the other; the bound on one step is
+    each reader's own cells.maxlength (5 x the longest face diagonal).  IPT::Integrate on the reference's MESH and the restatement
+    on the product's: the same tracks, bit for bit."""
+    from fjsph_b200 import frontend
+    from tests.tau_case import write_tau
+
+    if not orc.have_ref("ref3d"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    lo, hi, n = np.array([-0.1, -0.1, -0.1]), np.array([0.5, 0.1, 0.1]), (12, 5, 4)
+    vel = lambda x: (30 + 40 * x[0] + 20 * x[2], 0.4 * np.sin(9 * x[0]) - 0.3, -0.5 + 1.5 * x[1])
+    mesh_file, sol_file, *_ = write_tau(tmp_path, lo, hi, n, vel, lambda x: 1.0e5, lambda x: 1.1 + x[2] + 0.3 * x[0], split="y")
+    mine = frontend.read_tau(mesh_file, sol_file)
+    assert set(np.diff(mine["face_ptr"])) == {3, 4}
+    p = orc.default_params(3, asource=1, particle_step=1e-3)
+    ref = orc.Oracle(p, kind="ref3d")
+    theirs = orc.ref_read_tau(ref, mesh_file, sol_file, 1.0)
+    assert np.array_equal(mine["cVel"], theirs["cVel"])
+    rng = np.random.default_rng(41)
+    k = 200
+    cells = rng.integers(0, mine["cCentre"].shape[0] // 3, size=k)          # the upstream third
+    start = np.zeros(k, dtype=orc.IPT_START)
+    start["part_id"], start["cellID"], start["t"], start["mass"] = np.arange(k), cells, 0.1, p.sim_mass
+    start["xi"] = mine["cCentre"][cells] + rng.uniform(-0.2, 0.2, size=(k, 3)) * (hi - lo) / np.array(n)
+    start["v"] = rng.normal(scale=1.0, size=(k, 3)) + np.array([10.0, 0.0, 0.0])
+    start["cellV"], start["cellRho"] = mine["cVel"][cells], mine["cRho"][cells]
+    settings = orc.ipt_settings(p, eq_order=2, max_x=0.45, max_length=eng.mesh_max_length(mine), max_steps=4000)
+    theirs_settings = orc.ipt_settings(p, eq_order=2, max_x=0.45, max_length=-1.0, max_steps=4000)   # -1: the reader's own maxlength
+    b = ref.ipt_integrate(theirs_settings, start, record_cap=40)              # on the MESH the reference read itself
+    o = orc.Oracle(p)
+    o.set_mesh(mine)
+    a = o.ipt_integrate(settings, start, record_cap=40)
+    assert_same_tracks(a, b, "tau file")
+    assert a["n_success"] > 5 and a["n_steps"].max() >= 8
