@@ -270,3 +270,38 @@ def test_tracks_on_a_tau_file_read_by_either_side(tmp_path):
     a = o.ipt_integrate(settings, start, record_cap=40)
     assert_same_tracks(a, b, "tau file")
     assert a["n_success"] > 5 and a["n_steps"].max() >= 8
+
+
+def test_tracks_on_a_tau_edge_file_read_by_either_side(tmp_path):
+    """The 2D build's chain: an edge-based TAU mesh and its two-layer solution read by TAU::Read_tau_mesh_EDGE on one side and
+    by fjsph_tau_read_edge on the other, each side's own cells.maxlength (4 x the longest edge), then the tracker."""
+    from fjsph_b200 import frontend
+    from tests.tau_case import write_tau_edge
+
+    if not orc.have_ref("ref2d"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    lo, hi, n = np.array([-0.1, -0.1]), np.array([0.5, 0.1]), (12, 5)
+    vel = lambda x: (30 + 40 * x[0] + 20 * x[1], 5 * np.sin(9 * x[0]) + 3 * x[1])
+    mesh_file, sol_file, *_ = write_tau_edge(tmp_path, lo, hi, n, vel, lambda x: 1.0e5, lambda x: 1.1 + x[1] + 0.3 * x[0], plane="xz")
+    mine = frontend.read_tau_edge(mesh_file, sol_file, scale=1.0, offset_axis=2)
+    p = orc.default_params(2, asource=1, particle_step=1e-3)
+    ref = orc.Oracle(p, kind="ref2d")
+    theirs = orc.ref_read_tau_edge(ref, mesh_file, sol_file, 1.0, 2)
+    assert np.array_equal(mine["cVel"], theirs["cVel"])
+    rng = np.random.default_rng(43)
+    k = 200
+    cells = rng.integers(0, mine["cCentre"].shape[0], size=k)
+    cells = cells[mine["cCentre"][cells, 0] < 0.1][:120]
+    k = len(cells)
+    start = np.zeros(k, dtype=orc.IPT_START)
+    start["part_id"], start["cellID"], start["t"], start["mass"] = np.arange(k), cells, 0.1, p.sim_mass
+    start["xi"][:, :2] = mine["cCentre"][cells] + rng.uniform(-0.3, 0.3, size=(k, 2)) * (hi - lo) / np.array(n)
+    start["v"][:, :2] = rng.normal(scale=3.0, size=(k, 2)) + np.array([10.0, 0.0])
+    start["cellV"][:, :2], start["cellRho"] = mine["cVel"][cells], mine["cRho"][cells]
+    common = dict(eq_order=1, max_x=0.45, max_steps=4000, grav=[0.0, -9.81, 0.0])
+    b = ref.ipt_integrate(orc.ipt_settings(p, max_length=-1.0, **common), start, record_cap=40)
+    o = orc.Oracle(p, kind="2d")
+    o.set_mesh(mine)
+    a = o.ipt_integrate(orc.ipt_settings(p, max_length=eng.mesh_max_length(mine, 2), **common), start, record_cap=40)
+    assert_same_tracks(a, b, "tau edge file")
+    assert a["n_failed"] == 0 and a["n_steps"].max() >= 8      # at the readers' 4 x bound nothing trips the step-length test
